@@ -1,0 +1,142 @@
+/*
+ * pansvr_b200.h -- C ABI of the B200-native `panSVR aln` realignment hot path.
+ *
+ * Plain C types only; every entry point names the reference interface it replaces.
+ * Reference paths are relative to the hitbc/panSVR tree.
+ *
+ * Error model: the reference has no error codes on this path (ksw returns void and signals
+ * trouble through ez->zdropped / KSW_NEG_INF; src/kswlib/ksw2_extd2_sse.c:68,93).  Entry points
+ * that can fail for reasons the reference does not have (no GPU, out of device memory) return
+ * 0 on success and a negative PANSVR_E_* code otherwise; pansvr_last_error() holds the text.
+ * There is no CPU fallback: without a usable B200 every compute entry point fails loudly.
+ */
+#ifndef PANSVR_B200_H_
+#define PANSVR_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PANSVR_E_CUDA      (-1)   /* a CUDA call failed (no device, OOM, launch error) */
+#define PANSVR_E_ARG       (-2)   /* invalid argument */
+#define PANSVR_E_UNSUPPORTED (-3) /* parameter set outside what the device kernels implement */
+
+/* flags of src/kswlib/ksw2.h:9-15 (same values) */
+#define PANSVR_KSW_SCORE_ONLY  0x01
+#define PANSVR_KSW_RIGHT       0x02
+#define PANSVR_KSW_GENERIC_SC  0x04
+#define PANSVR_KSW_APPROX_MAX  0x08
+#define PANSVR_KSW_APPROX_DROP 0x10
+#define PANSVR_KSW_EXTZ_ONLY   0x40
+#define PANSVR_KSW_REV_CIGAR   0x80
+#define PANSVR_KSW_NEG_INF     (-0x40000000)
+
+/* Same layout as the reference's ksw_extz_t (src/kswlib/ksw2.h:26-35). */
+typedef struct {
+	uint32_t max:31, zdropped:1;
+	int max_q, max_t;
+	int mqe, mqe_t;
+	int mte, mte_q;
+	int score;
+	int m_cigar, n_cigar;
+	int reach_end;
+	uint32_t *cigar;
+} pansvr_ksw_extz_t;
+
+/* One result row of a batch: the fields of ksw_extz_t as 12 int32 words. */
+enum {
+	PANSVR_RES_MAX = 0, PANSVR_RES_ZDROPPED, PANSVR_RES_MAX_Q, PANSVR_RES_MAX_T, PANSVR_RES_MQE, PANSVR_RES_MQE_T,
+	PANSVR_RES_MTE, PANSVR_RES_MTE_Q, PANSVR_RES_SCORE, PANSVR_RES_N_CIGAR, PANSVR_RES_REACH_END,
+	PANSVR_RES_STATUS,           /* bit 0: CIGAR longer than cigar_cap (n_cigar is still exact) */
+	PANSVR_RES_WORDS
+};
+
+/* Scoring / band parameters of one batch: the trailing arguments of ksw_extd2_sse
+ * (src/kswlib/ksw2.h:63-64); fc_aln passes one set for the whole run
+ * (src/PanSVgenerateVCF/read_realignment.cpp:817-827,889). */
+typedef struct {
+	int32_t m;              /* alphabet size; last symbol is the wildcard */
+	const int8_t *mat;      /* m*m scores (host pointer) */
+	int8_t gapo, gape, gapo2, gape2;
+	int32_t w, zdrop, end_bonus, flag;
+} pansvr_ksw_params_t;
+
+/* Counters of the last batch call on a context (for bench.py's gpu_launches / roofline). */
+typedef struct {
+	int64_t kernel_launches;    /* our kernels launched */
+	int64_t tasks_fast_wrap, tasks_fast_nowrap, tasks_generic, tasks_trivial;
+	double kernel_ms;           /* CUDA-event time of the kernels only, on the context's stream */
+	double total_ms;            /* CUDA-event time of the whole call: H2D + kernels + D2H */
+	int64_t h2d_bytes, d2h_bytes;
+	int64_t tb_bytes_per_warp, resident_warps;
+} pansvr_ksw_stats_t;
+
+typedef struct pansvr_ksw_ctx pansvr_ksw_ctx;
+
+/* One context = one GPU + one stream + reusable device scratch.  Not thread-safe; use one per
+ * host thread, like the reference's per-thread KSW_ALN_handler (read_realignment.hpp:183-275). */
+int  pansvr_ksw_create(int device, pansvr_ksw_ctx **out);
+void pansvr_ksw_destroy(pansvr_ksw_ctx *ctx);
+const char *pansvr_last_error(void);
+
+/* Pinned host memory for the caller's batch buffers (the read/candidate-window batcher). */
+void *pansvr_host_alloc(size_t bytes);
+void  pansvr_host_free(void *p);
+
+/*
+ * Batched ksw_extd2_sse: task i aligns query qseq[qoff[i] .. +qlen[i]) against target
+ * tseq[toff[i] .. +tlen[i]) (one base per byte, values < m) and fills results[i*12 .. +12) and
+ * cigar[i*cigar_cap .. +n_cigar) exactly as the reference would fill ksw_extz_t for that call.
+ * All pointers are HOST pointers; copies to and from the device happen inside.
+ * Replaces: the per-call loop around KSW_ALN_handler::align_non_splice
+ * (read_realignment.cpp:872-891) -> ksw_extd2_sse (ksw2_extd2_sse.c:26).
+ */
+int pansvr_ksw_extd2_batch(pansvr_ksw_ctx *ctx, int64_t n,
+                           const uint8_t *qseq, int64_t qseq_bytes, const int64_t *qoff, const int32_t *qlen,
+                           const uint8_t *tseq, int64_t tseq_bytes, const int64_t *toff, const int32_t *tlen,
+                           const pansvr_ksw_params_t *params,
+                           int32_t *results, uint32_t *cigar, int32_t cigar_cap);
+
+/* Same, with every array already resident in device memory (DEVICE pointers) and the results
+ * left there; only the small per-task plan is built on the host from host copies of the
+ * lengths.  Used when the sequences were produced on the GPU (seed/chain stage) and for
+ * kernel-only timing. */
+int pansvr_ksw_extd2_batch_device(pansvr_ksw_ctx *ctx, int64_t n,
+                                  const uint8_t *d_qseq, const int64_t *d_qoff, const int32_t *d_qlen,
+                                  const uint8_t *d_tseq, const int64_t *d_toff, const int32_t *d_tlen,
+                                  const int32_t *h_qlen, const int32_t *h_tlen,
+                                  const pansvr_ksw_params_t *params,
+                                  int32_t *d_results, uint32_t *d_cigar, int32_t cigar_cap);
+
+int pansvr_ksw_last_stats(const pansvr_ksw_ctx *ctx, pansvr_ksw_stats_t *out);
+
+/* Measured 32-bit integer-ALU throughput of the device in Gop/s (IADD3/LOP3/VIMNMX chains, no
+ * memory): the denominator of the DP kernel's roofline (cells/s x 55 ops per cell). */
+int pansvr_int_alu_peak(pansvr_ksw_ctx *ctx, double *gops);
+
+/* In-band DP cells of one task, the work unit GCUPS is quoted in (ksw2_extd2_sse.c:131-138). */
+int64_t pansvr_ksw_band_cells(int32_t qlen, int32_t tlen, int32_t w);
+
+/*
+ * Drop-in for the reference kernel, identical signature and ownership rules
+ * (src/kswlib/ksw2.h:63-64): `km` is ignored, `ez` is caller-owned and reused, ez->cigar grows
+ * with realloc and is never freed here.  A batch of one on a process-wide context for the
+ * current device; meant for parity checks and for callers that have not been batched yet.
+ * Aborts with a message if no GPU is usable (the reference signature cannot carry an error).
+ */
+void pansvr_ksw_extd2(void *km, int qlen, const uint8_t *query, int tlen, const uint8_t *target, int8_t m,
+                      const int8_t *mat, int8_t gapo, int8_t gape, int8_t gapo2, int8_t gape2, int w, int zdrop,
+                      int end_bonus, int flag, pansvr_ksw_extz_t *ez);
+/* The same function under the reference's own symbol name, so that the reference links
+ * against libpansvr_b200.so instead of compiling src/kswlib/ksw2_extd2_sse.c. */
+void ksw_extd2_sse(void *km, int qlen, const uint8_t *query, int tlen, const uint8_t *target, int8_t m,
+                   const int8_t *mat, int8_t gapo, int8_t gape, int8_t gapo2, int8_t gape2, int w, int zdrop,
+                   int end_bonus, int flag, pansvr_ksw_extz_t *ez);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PANSVR_B200_H_ */

@@ -62,7 +62,18 @@ typedef struct {
 	uint32_t *cigar;
 } ora_extz_t;
 
-static inline int8_t w8(int v) { return (int8_t)(uint8_t)(v & 0xff); } /* int8 wrap-around */
+/* Range telemetry (tests only): extremes of the stored rows and the number of int8 operations
+ * that actually wrapped, accumulated over all calls since the last ksw_extd2_oracle_stats_reset(). */
+static __thread int64_t g_wraps;
+static __thread int g_rng[8]; /* uv_min uv_max x_max x2_max s_min s_max - - */
+static inline int8_t w8(int v) { /* int8 wrap-around */
+	if (v < -128 || v > 127) ++g_wraps;
+	return (int8_t)(uint8_t)(v & 0xff);
+}
+void ksw_extd2_oracle_stats_reset(void) { g_wraps = 0; g_rng[0] = 127; g_rng[1] = -128; g_rng[2] = g_rng[3] = -128; }
+void ksw_extd2_oracle_stats(int64_t *out) { int k; out[0] = g_wraps; for (k = 0; k < 4; ++k) out[1 + k] = g_rng[k]; }
+#define TRACK_UV(v) do { if ((v) < g_rng[0]) g_rng[0] = (v); if ((v) > g_rng[1]) g_rng[1] = (v); } while (0)
+#define TRACK_X(v, k) do { if ((v) > g_rng[k]) g_rng[k] = (v); } while (0)
 
 static void ora_reset(ora_extz_t *ez) /* K2H:238-243 */
 {
@@ -277,6 +288,7 @@ void ksw_extd2_oracle(void *km, int qlen, const uint8_t *query, int tlen, const 
 				X2[t] = w8((a2 >= 0 ? a2 : 0) - (q2 + e2)); if (a2 >= 0) d |= 0x20;
 				Y2[t] = w8((b2 >= 0 ? b2 : 0) - (q2 + e2)); if (b2 >= 0) d |= 0x40;
 			}
+			TRACK_UV(U[t]); TRACK_UV(V[t]); TRACK_X(X[t], 2); TRACK_X(Y[t], 2); TRACK_X(X2[t], 3); TRACK_X(Y2[t], 3);
 			if (with_cigar) dir[(size_t)r * stride + (size_t)(t - lo)] = d;
 		}
 		if (!approx_max) {                      /* exact H row and its argmax (KSW:316-359) */

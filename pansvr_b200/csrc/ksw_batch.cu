@@ -1,0 +1,486 @@
+// ksw_batch.cu -- device kernels, batch planner and C ABI of the ksw extension stage.
+//
+// Replaces the reference's per-call CPU path
+//   KSW_ALN_handler::align_non_splice -> ksw_extd2_sse
+//   (src/PanSVgenerateVCF/read_realignment.cpp:872-891, src/kswlib/ksw2_extd2_sse.c:26-396)
+// with a batched launch: the host plans the batch (kernel variant per task, longest-first
+// order, scratch), persistent CTAs pull alignments from a global counter, one warp per alignment
+// (ksw_fast.cuh).  No CPU fallback: every entry point fails if CUDA does.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <algorithm>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/pansvr_b200.h"
+#include "ksw_fast.cuh"
+#include "ksw_generic.cuh"
+#include "ksw_host.hpp"
+
+namespace {
+
+thread_local std::string g_err;
+int fail(int code, const std::string &msg) { g_err = msg; return code; }
+#define CU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) \
+	return fail(PANSVR_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); } while (0)
+
+constexpr int WARPS_PER_CTA = 4;
+constexpr int THREADS = WARPS_PER_CTA * 32;
+
+struct KArgs {
+	kswfast::Params P;
+	int n;                       // tasks of this launch
+	const int *order;            // task ids, longest first
+	int *counter;                // work queue head
+	const uint8_t *qseq; const int64_t *qoff; const int32_t *qlen;
+	const uint8_t *tseq; const int64_t *toff; const int32_t *tlen;
+	int32_t *res; uint32_t *cigar; int cigar_cap;
+	uint8_t *tb; size_t tb_per_warp;
+	int smem_per_warp;
+};
+
+// Persistent CTAs; each warp pulls the next alignment from the queue until it is empty.
+template <int CPL, bool WRAP>
+__global__ void __launch_bounds__(THREADS) ksw_fast_kernel(const __grid_constant__ KArgs a)
+{
+	extern __shared__ __align__(16) uint8_t smem[];
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	int32_t *Hs = (int32_t*)(smem + (size_t)warp * a.smem_per_warp);
+	uint8_t *QS = (uint8_t*)(Hs + 32 * CPL);
+	uint8_t *tb = a.tb + (size_t)(blockIdx.x * WARPS_PER_CTA + warp) * a.tb_per_warp;
+	for (;;) {
+		int idx = 0;
+		if (lane == 0) idx = atomicAdd(a.counter, 1);
+		idx = __shfl_sync(0xffffffffu, idx, 0);
+		if (idx >= a.n) break;
+		const int t = a.order[idx];
+		kswfast::align_task<CPL, WRAP>(a.P, a.qlen[t], a.qseq + a.qoff[t], a.tlen[t], a.tseq + a.toff[t],
+		                               a.res + (size_t)t * kswfast::RES_WORDS, a.cigar + (size_t)t * a.cigar_cap,
+		                               a.cigar_cap, tb, Hs, QS);
+	}
+}
+
+// Tasks the reference answers without running the DP (KSW:68, KSW:93): ksw_reset_extz only.
+__global__ void ksw_reset_kernel(int n, const int *order, int32_t *res)
+{
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	int32_t *o = res + (size_t)order[i] * kswfast::RES_WORDS;
+	o[0] = 0; o[1] = 0; o[2] = -1; o[3] = -1; o[4] = kswfast::NEG_INF; o[5] = -1; o[6] = kswfast::NEG_INF; o[7] = -1;
+	o[8] = kswfast::NEG_INF; o[9] = 0; o[10] = 0; o[11] = 0;
+}
+
+// Integer-ALU yardstick for the roofline: 32 independent dependency chains
+// per thread of the 32-bit integer instructions the DP is made of (IADD3 / LOP3 / VIMNMX), so the
+// ALU+FMA integer issue rate is the only limit.  One "op" = one 32-bit lane operation.
+__global__ void __launch_bounds__(256) int_alu_peak_kernel(uint32_t *out, int iters, uint32_t seed)
+{
+	uint32_t a[16];
+#pragma unroll
+	for (int k = 0; k < 16; ++k) a[k] = seed * (threadIdx.x + 1) + k * 0x9e3779b9u;
+	const uint32_t c1 = seed | 1u, c2 = seed ^ 0x5bd1e995u;
+	for (int it = 0; it < iters; ++it) {
+#pragma unroll
+		for (int k = 0; k < 16; ++k) {
+			a[k] = a[k] + c1 + (uint32_t)it;                      // IADD3
+			a[k] = (a[k] ^ c2) & ~c1;                             // LOP3
+			a[k] = (uint32_t)max((int)a[k], (int)c2);             // VIMNMX.S32
+			a[k] = a[k] - c2 + c1;                                // IADD3
+		}
+	}
+	uint32_t r = 0;
+#pragma unroll
+	for (int k = 0; k < 16; ++k) r ^= a[k];
+	if (r == 0x12345678u) out[blockIdx.x * blockDim.x + threadIdx.x] = r;   // keeps the chains alive
+}
+
+struct DevBuf {
+	void *p = nullptr; size_t cap = 0;
+	cudaError_t reserve(size_t bytes)
+	{
+		if (bytes <= cap) return cudaSuccess;
+		if (p) cudaFree(p);
+		p = nullptr; cap = 0;
+		size_t want = bytes + bytes / 8 + 256;
+		cudaError_t e = cudaMalloc(&p, want);
+		if (e == cudaSuccess) cap = want;
+		return e;
+	}
+	void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+enum { V_TRIVIAL = 0, V_GENERIC = 1, V_FAST0 = 2 };   // fast variants: V_FAST0 + 2*log2(cpl/2) + wrap
+constexpr int N_VARIANTS = V_FAST0 + 8;
+
+} // namespace
+
+struct pansvr_ksw_ctx {
+	int device = 0, sm_count = 0;
+	cudaStream_t stream = nullptr;
+	cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+	DevBuf qseq, tseq, qoff, toff, qlen, tlen, res, cigar, order, counters, tb, gscratch;
+	std::vector<int> h_order;
+	std::vector<uint8_t> h_variant;
+	std::vector<int> h_rows;
+	pansvr_ksw_stats_t stats;
+};
+
+namespace {
+
+struct Shape { int rows, cpl; };
+
+// Builds ctx->h_order (task ids grouped by kernel variant, most anti-diagonals first inside a
+// group) and returns per-variant [begin,end) plus the largest row count / query length per variant.
+struct BatchPlan {
+	int begin[N_VARIANTS + 1];
+	int max_rows[N_VARIANTS], max_qlen[N_VARIANTS], max_tlen[N_VARIANTS];
+};
+
+void plan_batch(pansvr_ksw_ctx *ctx, const kswhost::Plan &pl, int64_t n, const int32_t *qlen, const int32_t *tlen, BatchPlan &bp)
+{
+	const int w = pl.P.w;
+	ctx->h_variant.resize(n);
+	ctx->h_rows.resize(n);
+	ctx->h_order.resize(n);
+	std::unordered_map<uint64_t, Shape> memo;
+	uint64_t last_key = ~0ull; Shape last{0, 0};
+	int64_t count[N_VARIANTS];
+	memset(count, 0, sizeof(count));
+	for (int v = 0; v < N_VARIANTS; ++v) bp.max_rows[v] = bp.max_qlen[v] = bp.max_tlen[v] = 0;
+	for (int64_t i = 0; i < n; ++i) {
+		const int ql = qlen[i], tl = tlen[i];
+		int v;
+		Shape sh{0, 0};
+		if (pl.trivial || ql <= 0 || tl <= 0) v = V_TRIVIAL;
+		else {
+			const uint64_t key = (uint64_t)(uint32_t)ql << 32 | (uint32_t)tl;
+			if (key == last_key) sh = last;
+			else {
+				auto it = memo.find(key);
+				if (it == memo.end()) {
+					sh.rows = kswhost::n_diagonals(ql, tl, w);
+					sh.cpl = kswhost::pick_cpl(ql, tl, w);
+					memo.emplace(key, sh);
+				} else sh = it->second;
+				last_key = key; last = sh;
+			}
+			if (!pl.fast_params || sh.cpl == 0 || ql > 16000) v = V_GENERIC;
+			else {
+				const bool wrap = !pl.nowrap_ok || kswhost::band_clips(ql, tl, w);
+				int lg = sh.cpl == 2 ? 0 : sh.cpl == 4 ? 1 : sh.cpl == 8 ? 2 : 3;
+				v = V_FAST0 + 2 * lg + (wrap ? 1 : 0);
+			}
+		}
+		ctx->h_variant[i] = (uint8_t)v;
+		ctx->h_rows[i] = sh.rows;
+		++count[v];
+		bp.max_rows[v] = std::max(bp.max_rows[v], sh.rows);
+		bp.max_qlen[v] = std::max(bp.max_qlen[v], ql);
+		bp.max_tlen[v] = std::max(bp.max_tlen[v], tl);
+	}
+	bp.begin[0] = 0;
+	for (int v = 0; v < N_VARIANTS; ++v) bp.begin[v + 1] = bp.begin[v] + (int)count[v];
+	// counting sort inside a variant: 256 levels of row count, longest first
+	std::vector<int> pos((size_t)N_VARIANTS * 256, 0);
+	auto level = [&](int64_t i) { int v = ctx->h_variant[i]; int mr = std::max(bp.max_rows[v], 1);
+	                              return 255 - (int)((int64_t)ctx->h_rows[i] * 255 / mr); };
+	for (int64_t i = 0; i < n; ++i) ++pos[(size_t)ctx->h_variant[i] * 256 + level(i)];
+	for (int v = 0; v < N_VARIANTS; ++v) {
+		int run = bp.begin[v];
+		for (int l = 0; l < 256; ++l) { int c = pos[(size_t)v * 256 + l]; pos[(size_t)v * 256 + l] = run; run += c; }
+	}
+	for (int64_t i = 0; i < n; ++i) ctx->h_order[pos[(size_t)ctx->h_variant[i] * 256 + level(i)]++] = (int)i;
+}
+
+template <int CPL, bool WRAP>
+int launch_fast(pansvr_ksw_ctx *ctx, KArgs a, int max_rows, int max_qlen)
+{
+	constexpr int W = 32 * CPL;
+	a.smem_per_warp = W * 4 + ((max_qlen + 2 + 15) & ~15);
+	const int smem = a.smem_per_warp * WARPS_PER_CTA;
+	auto kern = ksw_fast_kernel<CPL, WRAP>;
+	CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+	int per_sm = 0;
+	CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, THREADS, smem));
+	if (per_sm < 1) return fail(PANSVR_E_UNSUPPORTED, "ksw fast kernel does not fit an SM (query too long)");
+	int grid = ctx->sm_count * per_sm;
+	grid = std::min<int64_t>(grid, ((int64_t)a.n + WARPS_PER_CTA - 1) / WARPS_PER_CTA);
+	a.tb_per_warp = (a.P.flag & kswfast::F_SCORE_ONLY) ? 0 : (((size_t)max_rows + 1) * W + 255) & ~(size_t)255;
+	const size_t tb_cap = (size_t)24 << 30;               // keep the traceback scratch under 24 GiB
+	while (grid > 1 && a.tb_per_warp * (size_t)grid * WARPS_PER_CTA > tb_cap) grid = (grid + 1) / 2;
+	CU(ctx->tb.reserve(a.tb_per_warp * (size_t)grid * WARPS_PER_CTA + 256));
+	a.tb = (uint8_t*)ctx->tb.p;
+	ctx->stats.tb_bytes_per_warp = (int64_t)a.tb_per_warp;
+	ctx->stats.resident_warps = (int64_t)grid * WARPS_PER_CTA;
+	kern<<<grid, THREADS, smem, ctx->stream>>>(a);
+	CU(cudaGetLastError());
+	++ctx->stats.kernel_launches;
+	return 0;
+}
+
+// everything after the inputs are on the device: plan, launch each variant, leave results on the device
+int run_device(pansvr_ksw_ctx *ctx, int64_t n, const uint8_t *d_qseq, const int64_t *d_qoff, const int32_t *d_qlen,
+               const uint8_t *d_tseq, const int64_t *d_toff, const int32_t *d_tlen, const int32_t *h_qlen,
+               const int32_t *h_tlen, const pansvr_ksw_params_t *pr, int32_t *d_res, uint32_t *d_cigar, int cigar_cap)
+{
+	if (pr->m > 1 && !pr->mat) return fail(PANSVR_E_ARG, "params->mat is NULL");
+	kswhost::Plan pl = kswhost::make_plan(pr->m, pr->mat, pr->gapo, pr->gape, pr->gapo2, pr->gape2, pr->w, pr->zdrop,
+	                                      pr->end_bonus, pr->flag);
+	BatchPlan bp;
+	plan_batch(ctx, pl, n, h_qlen, h_tlen, bp);
+	CU(ctx->order.reserve(sizeof(int) * (size_t)n));
+	CU(ctx->counters.reserve(sizeof(int) * N_VARIANTS));
+	CU(cudaMemcpyAsync(ctx->order.p, ctx->h_order.data(), sizeof(int) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+	CU(cudaMemsetAsync(ctx->counters.p, 0, sizeof(int) * N_VARIANTS, ctx->stream));
+	ctx->stats.h2d_bytes += (int64_t)sizeof(int) * n;
+	CU(cudaEventRecord(ctx->ev[1], ctx->stream));
+	KArgs a;
+	a.P = pl.P;
+	a.qseq = d_qseq; a.qoff = d_qoff; a.qlen = d_qlen; a.tseq = d_tseq; a.toff = d_toff; a.tlen = d_tlen;
+	a.res = d_res; a.cigar = d_cigar; a.cigar_cap = cigar_cap; a.tb = nullptr; a.tb_per_warp = 0; a.smem_per_warp = 0;
+	for (int v = 0; v < N_VARIANTS; ++v) {
+		const int cnt = bp.begin[v + 1] - bp.begin[v];
+		if (cnt == 0) continue;
+		a.n = cnt;
+		a.order = (const int*)ctx->order.p + bp.begin[v];
+		a.counter = (int*)ctx->counters.p + v;
+		int rc = 0;
+		if (v == V_TRIVIAL) {
+			ksw_reset_kernel<<<(cnt + 255) / 256, 256, 0, ctx->stream>>>(cnt, a.order, d_res);
+			CU(cudaGetLastError());
+			++ctx->stats.kernel_launches;
+			ctx->stats.tasks_trivial += cnt;
+		} else if (v == V_GENERIC) {
+			rc = kswgeneric::launch(ctx->stream, ctx->sm_count, pr, pl.P, cnt, a.order, d_qseq, d_qoff, d_qlen, d_tseq, d_toff,
+			                        d_tlen, d_res, d_cigar, cigar_cap, bp.max_qlen[v], bp.max_tlen[v], &ctx->gscratch.p,
+			                        &ctx->gscratch.cap, &ctx->stats.kernel_launches, g_err);
+			ctx->stats.tasks_generic += cnt;
+		} else {
+			const int lg = (v - V_FAST0) >> 1, wrap = (v - V_FAST0) & 1;
+			const int mr = bp.max_rows[v], mq = bp.max_qlen[v];
+			switch (lg * 2 + wrap) {
+			case 0: rc = launch_fast<2, false>(ctx, a, mr, mq); break;
+			case 1: rc = launch_fast<2, true>(ctx, a, mr, mq); break;
+			case 2: rc = launch_fast<4, false>(ctx, a, mr, mq); break;
+			case 3: rc = launch_fast<4, true>(ctx, a, mr, mq); break;
+			case 4: rc = launch_fast<8, false>(ctx, a, mr, mq); break;
+			case 5: rc = launch_fast<8, true>(ctx, a, mr, mq); break;
+			case 6: rc = launch_fast<16, false>(ctx, a, mr, mq); break;
+			default: rc = launch_fast<16, true>(ctx, a, mr, mq); break;
+			}
+			(wrap ? ctx->stats.tasks_fast_wrap : ctx->stats.tasks_fast_nowrap) += cnt;
+		}
+		if (rc) return rc;
+	}
+	CU(cudaEventRecord(ctx->ev[2], ctx->stream));
+	return 0;
+}
+
+int finish_stats(pansvr_ksw_ctx *ctx)
+{
+	CU(cudaEventRecord(ctx->ev[3], ctx->stream));
+	CU(cudaStreamSynchronize(ctx->stream));
+	float k = 0, t = 0;
+	CU(cudaEventElapsedTime(&k, ctx->ev[1], ctx->ev[2]));
+	CU(cudaEventElapsedTime(&t, ctx->ev[0], ctx->ev[3]));
+	ctx->stats.kernel_ms = k; ctx->stats.total_ms = t;
+	return 0;
+}
+
+} // namespace
+
+extern "C" {
+
+const char *pansvr_last_error(void) { return g_err.c_str(); }
+
+int pansvr_ksw_create(int device, pansvr_ksw_ctx **out)
+{
+	if (!out) return fail(PANSVR_E_ARG, "out is NULL");
+	*out = nullptr;
+	int ndev = 0;
+	CU(cudaGetDeviceCount(&ndev));
+	if (device < 0 || device >= ndev) return fail(PANSVR_E_CUDA, "no such CUDA device");
+	CU(cudaSetDevice(device));
+	cudaDeviceProp prop;
+	CU(cudaGetDeviceProperties(&prop, device));
+	if (prop.major < 10) return fail(PANSVR_E_CUDA, std::string("device is not sm_100 class: ") + prop.name);
+	pansvr_ksw_ctx *c = new pansvr_ksw_ctx();
+	c->device = device; c->sm_count = prop.multiProcessorCount;
+	memset(&c->stats, 0, sizeof(c->stats));
+	CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+	for (auto &e : c->ev) CU(cudaEventCreate(&e));
+	*out = c;
+	return 0;
+}
+
+void pansvr_ksw_destroy(pansvr_ksw_ctx *c)
+{
+	if (!c) return;
+	cudaSetDevice(c->device);
+	cudaStreamSynchronize(c->stream);
+	for (DevBuf *b : {&c->qseq, &c->tseq, &c->qoff, &c->toff, &c->qlen, &c->tlen, &c->res, &c->cigar, &c->order, &c->counters,
+	                  &c->tb, &c->gscratch}) b->release();
+	for (auto &e : c->ev) if (e) cudaEventDestroy(e);
+	if (c->stream) cudaStreamDestroy(c->stream);
+	delete c;
+}
+
+void *pansvr_host_alloc(size_t bytes)
+{
+	void *p = nullptr;
+	if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) { g_err = "cudaHostAlloc failed"; return nullptr; }
+	return p;
+}
+void pansvr_host_free(void *p) { if (p) cudaFreeHost(p); }
+
+int64_t pansvr_ksw_band_cells(int32_t qlen, int32_t tlen, int32_t w)
+{
+	if (qlen <= 0 || tlen <= 0) return 0;
+	if (w < 0) w = std::max(qlen, tlen);
+	int64_t n = 0;
+	for (int r = 0; r < qlen + tlen - 1; ++r) {
+		int lo, hi;
+		kswfast::band(r, qlen, tlen, w, lo, hi);
+		if (lo > hi) break;
+		n += hi - lo + 1;
+	}
+	return n;
+}
+
+int pansvr_ksw_extd2_batch_device(pansvr_ksw_ctx *ctx, int64_t n, const uint8_t *d_qseq, const int64_t *d_qoff,
+                                  const int32_t *d_qlen, const uint8_t *d_tseq, const int64_t *d_toff, const int32_t *d_tlen,
+                                  const int32_t *h_qlen, const int32_t *h_tlen, const pansvr_ksw_params_t *params,
+                                  int32_t *d_results, uint32_t *d_cigar, int32_t cigar_cap)
+{
+	if (!ctx || !params || n < 0 || n > 0x7fffffff || cigar_cap < 0) return fail(PANSVR_E_ARG, "bad argument");
+	CU(cudaSetDevice(ctx->device));
+	memset(&ctx->stats, 0, sizeof(ctx->stats));
+	CU(cudaEventRecord(ctx->ev[0], ctx->stream));
+	if (n > 0) {
+		int rc = run_device(ctx, n, d_qseq, d_qoff, d_qlen, d_tseq, d_toff, d_tlen, h_qlen, h_tlen, params, d_results, d_cigar, cigar_cap);
+		if (rc) return rc;
+	} else { CU(cudaEventRecord(ctx->ev[1], ctx->stream)); CU(cudaEventRecord(ctx->ev[2], ctx->stream)); }
+	return finish_stats(ctx);
+}
+
+int pansvr_ksw_extd2_batch(pansvr_ksw_ctx *ctx, int64_t n, const uint8_t *qseq, int64_t qseq_bytes, const int64_t *qoff,
+                           const int32_t *qlen, const uint8_t *tseq, int64_t tseq_bytes, const int64_t *toff,
+                           const int32_t *tlen, const pansvr_ksw_params_t *params, int32_t *results, uint32_t *cigar,
+                           int32_t cigar_cap)
+{
+	if (!ctx || !params || n < 0 || n > 0x7fffffff || cigar_cap < 0 || qseq_bytes < 0 || tseq_bytes < 0)
+		return fail(PANSVR_E_ARG, "bad argument");
+	CU(cudaSetDevice(ctx->device));
+	memset(&ctx->stats, 0, sizeof(ctx->stats));
+	CU(cudaEventRecord(ctx->ev[0], ctx->stream));
+	if (n == 0) { CU(cudaEventRecord(ctx->ev[1], ctx->stream)); CU(cudaEventRecord(ctx->ev[2], ctx->stream)); return finish_stats(ctx); }
+	for (int64_t i = 0; i < n; ++i) {
+		if (qlen[i] > 0 && (qoff[i] < 0 || qoff[i] + qlen[i] > qseq_bytes)) return fail(PANSVR_E_ARG, "query window outside qseq");
+		if (tlen[i] > 0 && (toff[i] < 0 || toff[i] + tlen[i] > tseq_bytes)) return fail(PANSVR_E_ARG, "target window outside tseq");
+	}
+	const size_t nn = (size_t)n;
+	CU(ctx->qseq.reserve((size_t)qseq_bytes + 16)); CU(ctx->tseq.reserve((size_t)tseq_bytes + 16));
+	CU(ctx->qoff.reserve(nn * 8)); CU(ctx->toff.reserve(nn * 8)); CU(ctx->qlen.reserve(nn * 4)); CU(ctx->tlen.reserve(nn * 4));
+	CU(ctx->res.reserve(nn * sizeof(int32_t) * PANSVR_RES_WORDS));
+	CU(ctx->cigar.reserve(nn * sizeof(uint32_t) * (size_t)std::max(cigar_cap, 1)));
+	cudaStream_t s = ctx->stream;
+	CU(cudaMemcpyAsync(ctx->qseq.p, qseq, (size_t)qseq_bytes, cudaMemcpyHostToDevice, s));
+	CU(cudaMemcpyAsync(ctx->tseq.p, tseq, (size_t)tseq_bytes, cudaMemcpyHostToDevice, s));
+	CU(cudaMemcpyAsync(ctx->qoff.p, qoff, nn * 8, cudaMemcpyHostToDevice, s));
+	CU(cudaMemcpyAsync(ctx->toff.p, toff, nn * 8, cudaMemcpyHostToDevice, s));
+	CU(cudaMemcpyAsync(ctx->qlen.p, qlen, nn * 4, cudaMemcpyHostToDevice, s));
+	CU(cudaMemcpyAsync(ctx->tlen.p, tlen, nn * 4, cudaMemcpyHostToDevice, s));
+	ctx->stats.h2d_bytes = qseq_bytes + tseq_bytes + (int64_t)nn * 24;
+	int rc = run_device(ctx, n, (const uint8_t*)ctx->qseq.p, (const int64_t*)ctx->qoff.p, (const int32_t*)ctx->qlen.p,
+	                    (const uint8_t*)ctx->tseq.p, (const int64_t*)ctx->toff.p, (const int32_t*)ctx->tlen.p, qlen, tlen, params,
+	                    (int32_t*)ctx->res.p, (uint32_t*)ctx->cigar.p, cigar_cap);
+	if (rc) return rc;
+	CU(cudaMemcpyAsync(results, ctx->res.p, nn * sizeof(int32_t) * PANSVR_RES_WORDS, cudaMemcpyDeviceToHost, s));
+	if (cigar_cap > 0 && !(params->flag & PANSVR_KSW_SCORE_ONLY))
+		CU(cudaMemcpyAsync(cigar, ctx->cigar.p, nn * sizeof(uint32_t) * (size_t)cigar_cap, cudaMemcpyDeviceToHost, s));
+	ctx->stats.d2h_bytes = (int64_t)(nn * sizeof(int32_t) * PANSVR_RES_WORDS) +
+	                       ((cigar_cap > 0 && !(params->flag & PANSVR_KSW_SCORE_ONLY)) ? (int64_t)(nn * 4 * (size_t)cigar_cap) : 0);
+	return finish_stats(ctx);
+}
+
+int pansvr_int_alu_peak(pansvr_ksw_ctx *ctx, double *gops)
+{
+	if (!ctx || !gops) return fail(PANSVR_E_ARG, "bad argument");
+	CU(cudaSetDevice(ctx->device));
+	CU(ctx->counters.reserve(4096));
+	const int iters = 4096, grid = ctx->sm_count * 8, ops_per_iter = 16 * 4;
+	double best = 0;
+	for (int rep = 0; rep < 5; ++rep) {
+		CU(cudaEventRecord(ctx->ev[0], ctx->stream));
+		int_alu_peak_kernel<<<grid, 256, 0, ctx->stream>>>((uint32_t*)ctx->counters.p, iters, 0x2545f491u + rep);
+		CU(cudaGetLastError());
+		CU(cudaEventRecord(ctx->ev[3], ctx->stream));
+		CU(cudaStreamSynchronize(ctx->stream));
+		float ms = 0;
+		CU(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[3]));
+		const double g = (double)grid * 256 * iters * ops_per_iter / (ms * 1e-3) * 1e-9;
+		if (rep > 0 && g > best) best = g;
+	}
+	*gops = best;
+	return 0;
+}
+
+int pansvr_ksw_last_stats(const pansvr_ksw_ctx *ctx, pansvr_ksw_stats_t *out)
+{
+	if (!ctx || !out) return fail(PANSVR_E_ARG, "bad argument");
+	*out = ctx->stats;
+	return 0;
+}
+
+void pansvr_ksw_extd2(void *km, int qlen, const uint8_t *query, int tlen, const uint8_t *target, int8_t m, const int8_t *mat,
+                      int8_t gapo, int8_t gape, int8_t gapo2, int8_t gape2, int w, int zdrop, int end_bonus, int flag,
+                      pansvr_ksw_extz_t *ez)
+{
+	(void)km;
+	static thread_local pansvr_ksw_ctx *ctx = nullptr;
+	if (!ctx) {
+		int dev = 0;
+		if (cudaGetDevice(&dev) != cudaSuccess || pansvr_ksw_create(dev, &ctx) != 0) {
+			fprintf(stderr, "pansvr_b200: ksw_extd2 needs a B200 and there is no CPU fallback: %s\n", pansvr_last_error());
+			abort();
+		}
+	}
+	pansvr_ksw_params_t pr;
+	pr.m = m; pr.mat = mat; pr.gapo = gapo; pr.gape = gape; pr.gapo2 = gapo2; pr.gape2 = gape2;
+	pr.w = w; pr.zdrop = zdrop; pr.end_bonus = end_bonus; pr.flag = flag;
+	const int64_t zero = 0;
+	int32_t res[PANSVR_RES_WORDS];
+	int cap = std::max(ez->m_cigar, 16);
+	std::vector<uint32_t> cig;
+	for (;;) {
+		cig.assign((size_t)cap, 0);
+		const int32_t ql = qlen, tl = tlen;
+		int rc = pansvr_ksw_extd2_batch(ctx, 1, query, qlen > 0 ? qlen : 0, &zero, &ql, target, tlen > 0 ? tlen : 0, &zero, &tl,
+		                                &pr, res, cig.data(), cap);
+		if (rc != 0) { fprintf(stderr, "pansvr_b200: ksw_extd2 failed: %s\n", pansvr_last_error()); abort(); }
+		if (!(res[PANSVR_RES_STATUS] & 1)) break;
+		cap = res[PANSVR_RES_N_CIGAR] + 1;
+	}
+	ez->max = (uint32_t)res[0]; ez->zdropped = (uint32_t)res[1]; ez->max_q = res[2]; ez->max_t = res[3];
+	ez->mqe = res[4]; ez->mqe_t = res[5]; ez->mte = res[6]; ez->mte_q = res[7]; ez->score = res[8];
+	ez->n_cigar = res[9]; ez->reach_end = res[10];
+	if (ez->n_cigar > 0) {                  // grow ez->cigar the way ksw_push_cigar does (ksw2.h:106-116)
+		int mc = ez->m_cigar;
+		while (mc < ez->n_cigar) mc = mc ? mc << 1 : 4;
+		if (mc != ez->m_cigar) { ez->cigar = (uint32_t*)realloc(ez->cigar, (size_t)mc << 2); ez->m_cigar = mc; }
+		memcpy(ez->cigar, cig.data(), sizeof(uint32_t) * (size_t)ez->n_cigar);
+	}
+}
+
+void ksw_extd2_sse(void *km, int qlen, const uint8_t *query, int tlen, const uint8_t *target, int8_t m, const int8_t *mat,
+                   int8_t gapo, int8_t gape, int8_t gapo2, int8_t gape2, int w, int zdrop, int end_bonus, int flag,
+                   pansvr_ksw_extz_t *ez)
+{
+	pansvr_ksw_extd2(km, qlen, query, tlen, target, m, mat, gapo, gape, gapo2, gape2, w, zdrop, end_bonus, flag, ez);
+}
+
+} // extern "C"
