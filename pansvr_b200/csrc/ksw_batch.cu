@@ -65,11 +65,12 @@ __global__ void __launch_bounds__(THREADS) ksw_fast_kernel(const __grid_constant
 }
 
 // Tasks the reference answers without running the DP (KSW:68, KSW:93): ksw_reset_extz only.
-__global__ void ksw_reset_kernel(int n, const int *order, int32_t *res)
+__global__ void ksw_reset_kernel(int n, const int *order, int32_t *res, uint32_t *cigar, int cigar_cap)
 {
 	const int i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= n) return;
 	int32_t *o = res + (size_t)order[i] * kswfast::RES_WORDS;
+	for (int k = 0; k < cigar_cap; ++k) cigar[(size_t)order[i] * cigar_cap + k] = 0;
 	o[0] = 0; o[1] = 0; o[2] = -1; o[3] = -1; o[4] = kswfast::NEG_INF; o[5] = -1; o[6] = kswfast::NEG_INF; o[7] = -1;
 	o[8] = kswfast::NEG_INF; o[9] = 0; o[10] = 0; o[11] = 0;
 }
@@ -250,7 +251,7 @@ int run_device(pansvr_ksw_ctx *ctx, int64_t n, const uint8_t *d_qseq, const int6
 		a.counter = (int*)ctx->counters.p + v;
 		int rc = 0;
 		if (v == V_TRIVIAL) {
-			ksw_reset_kernel<<<(cnt + 255) / 256, 256, 0, ctx->stream>>>(cnt, a.order, d_res);
+			ksw_reset_kernel<<<(cnt + 255) / 256, 256, 0, ctx->stream>>>(cnt, a.order, d_res, d_cigar, cigar_cap);
 			CU(cudaGetLastError());
 			++ctx->stats.kernel_launches;
 			ctx->stats.tasks_trivial += cnt;

@@ -440,6 +440,7 @@ LANE_DEV void align_task(const Params &P, int qlen, const uint8_t *__restrict__ 
 			}
 		}
 	}
+	for (int k = n_cigar + lane; k < cigar_cap; k += 32) cigar[k] = 0;   // deterministic tail of the CIGAR row
 	if (lane == 0) {
 		res[0] = ez_max; res[1] = zdropped; res[2] = ez_max_q; res[3] = ez_max_t;
 		res[4] = mqe; res[5] = mqe_t; res[6] = mte8 == NEG_INF ? NEG_INF : mte8 >> 3; res[7] = mte_q;

@@ -186,6 +186,7 @@ __device__ inline void g_align(const GArgs &a, int qlen, const uint8_t *query, i
 			g_backtrack(ez, cigar, a.cigar_cap, rev, dir, stride, qlen, tlen, w, ez.mqe_t, qlen - 1);
 		} else if (ez.max_t >= 0 && ez.max_q >= 0) g_backtrack(ez, cigar, a.cigar_cap, rev, dir, stride, qlen, tlen, w, ez.max_t, ez.max_q);
 	}
+	for (int k = ez.n_cigar; k < a.cigar_cap; ++k) cigar[k] = 0;
 	res[0] = ez.max; res[1] = ez.zdropped; res[2] = ez.max_q; res[3] = ez.max_t; res[4] = ez.mqe; res[5] = ez.mqe_t;
 	res[6] = ez.mte; res[7] = ez.mte_q; res[8] = ez.score; res[9] = ez.n_cigar; res[10] = ez.reach_end; res[11] = ez.overflow;
 }
