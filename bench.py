@@ -289,7 +289,7 @@ def main():
         "gpu_launches": int(launches + e_launches),
         "roofline": {"bound": "int_alu", "achieved": achieved_gops, "peak": int_peak, "unit": "Gop/s",
                      "frac": achieved_gops / int_peak if int_peak else None, "traffic": None,
-                     "kernel": "ksw_fast_kernel<8,true>", "kernel_ms_per_launch": kern_ms / args.steps,
+                     "kernel": "ksw_team_kernel<8,true>", "kernel_ms_per_launch": kern_ms / args.steps,
                      "ops_per_cell": OPS_PER_CELL, "gcups": kernel_gcups,
                      "peak_source": "pansvr_int_alu_peak measured live on this GPU (IADD3/LOP3/VIMNMX chains)",
                      "hbm": {"achieved": hbm_gbs, "peak": peaks.get("hbm_gbs"), "unit": "GB/s",

@@ -17,7 +17,8 @@
 #include <vector>
 
 #include "../../include/pansvr_b200.h"
-#include "ksw_fast.cuh"
+#include "ksw_common.cuh"
+#include "ksw_team.cuh"
 #include "ksw_generic.cuh"
 #include "ksw_host.hpp"
 
@@ -39,28 +40,34 @@ struct KArgs {
 	const uint8_t *qseq; const int64_t *qoff; const int32_t *qlen;
 	const uint8_t *tseq; const int64_t *toff; const int32_t *tlen;
 	int32_t *res; uint32_t *cigar; int cigar_cap;
-	uint8_t *tb; size_t tb_per_warp;
-	int smem_per_warp;
+	uint8_t *tb; size_t tb_per_team;
+	int smem_per_team;
 };
 
-// Persistent CTAs; each warp pulls the next alignment from the queue until it is empty.
-template <int CPL, bool WRAP>
-__global__ void __launch_bounds__(THREADS) ksw_fast_kernel(const __grid_constant__ KArgs a)
+// Persistent CTAs; each warp pulls the next 32/TEAM alignments from the queue until it is empty.
+template <int TEAM, bool WRAP>
+__global__ void __launch_bounds__(THREADS) ksw_team_kernel(const __grid_constant__ KArgs a)
 {
 	extern __shared__ __align__(16) uint8_t smem[];
-	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-	int32_t *Hs = (int32_t*)(smem + (size_t)warp * a.smem_per_warp);
-	uint8_t *QS = (uint8_t*)(Hs + 32 * CPL);
-	uint8_t *tb = a.tb + (size_t)(blockIdx.x * WARPS_PER_CTA + warp) * a.tb_per_warp;
+	constexpr int NT = 32 / TEAM, W = 16 * TEAM;
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, team = lane / TEAM;
+	uint8_t *wbase = smem + (size_t)warp * ((size_t)NT * a.smem_per_team + 32 * 32);
+	uint8_t *base = wbase + (size_t)team * a.smem_per_team;
+	int32_t *Hs = (int32_t*)base, *Hsnap = Hs + W;
+	uint8_t *QS = (uint8_t*)(Hsnap + W);
+	uint8_t *Ssp = base + a.smem_per_team - 32;
+	uint32_t *scr = (uint32_t*)(wbase + (size_t)NT * a.smem_per_team) + lane * 8;
+	uint8_t *tb = a.tb + ((size_t)(blockIdx.x * WARPS_PER_CTA + warp) * NT + team) * a.tb_per_team;
 	for (;;) {
 		int idx = 0;
-		if (lane == 0) idx = atomicAdd(a.counter, 1);
+		if (lane == 0) idx = atomicAdd(a.counter, NT);
 		idx = __shfl_sync(0xffffffffu, idx, 0);
 		if (idx >= a.n) break;
-		const int t = a.order[idx];
-		kswfast::align_task<CPL, WRAP>(a.P, a.qlen[t], a.qseq + a.qoff[t], a.tlen[t], a.tseq + a.toff[t],
-		                               a.res + (size_t)t * kswfast::RES_WORDS, a.cigar + (size_t)t * a.cigar_cap,
-		                               a.cigar_cap, tb, Hs, QS);
+		const bool have = idx + team < a.n;
+		const int t = have ? a.order[idx + team] : a.order[idx];
+		kswteam::align_team<TEAM, WRAP>(a.P, have, have ? a.qlen[t] : 0, a.qseq + a.qoff[t], have ? a.tlen[t] : 0, a.tseq + a.toff[t],
+		                                a.res + (size_t)t * kswfast::RES_WORDS, a.cigar + (size_t)t * a.cigar_cap, a.cigar_cap,
+		                                tb, Hs, Hsnap, QS, Ssp, scr);
 	}
 }
 
@@ -114,8 +121,8 @@ struct DevBuf {
 	void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
 };
 
-enum { V_TRIVIAL = 0, V_GENERIC = 1, V_FAST0 = 2 };   // fast variants: V_FAST0 + 2*log2(cpl/2) + wrap
-constexpr int N_VARIANTS = V_FAST0 + 8;
+enum { V_TRIVIAL = 0, V_GENERIC = 1, V_FAST0 = 2 };   // team variants: V_FAST0 + 2*log2(TEAM/2) + wrap
+constexpr int N_VARIANTS = V_FAST0 + 10;
 
 } // namespace
 
@@ -132,7 +139,7 @@ struct pansvr_ksw_ctx {
 
 namespace {
 
-struct Shape { int rows, cpl; };
+struct Shape { int rows, team; };
 
 // Builds ctx->h_order (task ids grouped by kernel variant, most anti-diagonals first inside a
 // group) and returns per-variant [begin,end) plus the largest row count / query length per variant.
@@ -164,15 +171,16 @@ void plan_batch(pansvr_ksw_ctx *ctx, const kswhost::Plan &pl, int64_t n, const i
 				auto it = memo.find(key);
 				if (it == memo.end()) {
 					sh.rows = kswhost::n_diagonals(ql, tl, w);
-					sh.cpl = kswhost::pick_cpl(ql, tl, w);
+					sh.team = kswhost::pick_team(ql, tl, w);
 					memo.emplace(key, sh);
 				} else sh = it->second;
 				last_key = key; last = sh;
 			}
-			if (!pl.fast_params || sh.cpl == 0 || ql > 16000) v = V_GENERIC;
+			if (!pl.fast_params || sh.team == 0 || ql > 8000) v = V_GENERIC;
 			else {
 				const bool wrap = !pl.nowrap_ok || kswhost::band_clips(ql, tl, w);
-				int lg = sh.cpl == 2 ? 0 : sh.cpl == 4 ? 1 : sh.cpl == 8 ? 2 : 3;
+				int lg = 0;
+				while ((2 << lg) < sh.team) ++lg;
 				v = V_FAST0 + 2 * lg + (wrap ? 1 : 0);
 			}
 		}
@@ -197,25 +205,25 @@ void plan_batch(pansvr_ksw_ctx *ctx, const kswhost::Plan &pl, int64_t n, const i
 	for (int64_t i = 0; i < n; ++i) ctx->h_order[pos[(size_t)ctx->h_variant[i] * 256 + level(i)]++] = (int)i;
 }
 
-template <int CPL, bool WRAP>
-int launch_fast(pansvr_ksw_ctx *ctx, KArgs a, int max_rows, int max_qlen)
+template <int TEAM, bool WRAP>
+int launch_team(pansvr_ksw_ctx *ctx, KArgs a, int max_rows, int max_qlen)
 {
-	constexpr int W = 32 * CPL;
-	a.smem_per_warp = W * 4 + ((max_qlen + 2 + 15) & ~15);
-	const int smem = a.smem_per_warp * WARPS_PER_CTA;
-	auto kern = ksw_fast_kernel<CPL, WRAP>;
+	constexpr int W = 16 * TEAM, NT = 32 / TEAM;
+	a.smem_per_team = kswteam::team_smem_bytes(TEAM, max_qlen);
+	const int smem = (a.smem_per_team * NT + 32 * 32) * WARPS_PER_CTA;
+	auto kern = ksw_team_kernel<TEAM, WRAP>;
 	CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
 	int per_sm = 0;
 	CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, THREADS, smem));
-	if (per_sm < 1) return fail(PANSVR_E_UNSUPPORTED, "ksw fast kernel does not fit an SM (query too long)");
+	if (per_sm < 1) return fail(PANSVR_E_UNSUPPORTED, "ksw team kernel does not fit an SM (query too long)");
 	int grid = ctx->sm_count * per_sm;
-	grid = std::min<int64_t>(grid, ((int64_t)a.n + WARPS_PER_CTA - 1) / WARPS_PER_CTA);
-	a.tb_per_warp = (a.P.flag & kswfast::F_SCORE_ONLY) ? 0 : (((size_t)max_rows + 1) * W + 255) & ~(size_t)255;
+	grid = (int)std::min<int64_t>(grid, ((int64_t)a.n + WARPS_PER_CTA * NT - 1) / (WARPS_PER_CTA * NT));
+	a.tb_per_team = (a.P.flag & kswfast::F_SCORE_ONLY) ? 0 : (((size_t)max_rows + 1) * W + 255) & ~(size_t)255;
 	const size_t tb_cap = (size_t)24 << 30;               // keep the traceback scratch under 24 GiB
-	while (grid > 1 && a.tb_per_warp * (size_t)grid * WARPS_PER_CTA > tb_cap) grid = (grid + 1) / 2;
-	CU(ctx->tb.reserve(a.tb_per_warp * (size_t)grid * WARPS_PER_CTA + 256));
+	while (grid > 1 && a.tb_per_team * (size_t)grid * WARPS_PER_CTA * NT > tb_cap) grid = (grid + 1) / 2;
+	CU(ctx->tb.reserve(a.tb_per_team * (size_t)grid * WARPS_PER_CTA * NT + 256));
 	a.tb = (uint8_t*)ctx->tb.p;
-	ctx->stats.tb_bytes_per_warp = (int64_t)a.tb_per_warp;
+	ctx->stats.tb_bytes_per_warp = (int64_t)a.tb_per_team * NT;
 	ctx->stats.resident_warps = (int64_t)grid * WARPS_PER_CTA;
 	kern<<<grid, THREADS, smem, ctx->stream>>>(a);
 	CU(cudaGetLastError());
@@ -242,7 +250,7 @@ int run_device(pansvr_ksw_ctx *ctx, int64_t n, const uint8_t *d_qseq, const int6
 	KArgs a;
 	a.P = pl.P;
 	a.qseq = d_qseq; a.qoff = d_qoff; a.qlen = d_qlen; a.tseq = d_tseq; a.toff = d_toff; a.tlen = d_tlen;
-	a.res = d_res; a.cigar = d_cigar; a.cigar_cap = cigar_cap; a.tb = nullptr; a.tb_per_warp = 0; a.smem_per_warp = 0;
+	a.res = d_res; a.cigar = d_cigar; a.cigar_cap = cigar_cap; a.tb = nullptr; a.tb_per_team = 0; a.smem_per_team = 0;
 	for (int v = 0; v < N_VARIANTS; ++v) {
 		const int cnt = bp.begin[v + 1] - bp.begin[v];
 		if (cnt == 0) continue;
@@ -264,14 +272,16 @@ int run_device(pansvr_ksw_ctx *ctx, int64_t n, const uint8_t *d_qseq, const int6
 			const int lg = (v - V_FAST0) >> 1, wrap = (v - V_FAST0) & 1;
 			const int mr = bp.max_rows[v], mq = bp.max_qlen[v];
 			switch (lg * 2 + wrap) {
-			case 0: rc = launch_fast<2, false>(ctx, a, mr, mq); break;
-			case 1: rc = launch_fast<2, true>(ctx, a, mr, mq); break;
-			case 2: rc = launch_fast<4, false>(ctx, a, mr, mq); break;
-			case 3: rc = launch_fast<4, true>(ctx, a, mr, mq); break;
-			case 4: rc = launch_fast<8, false>(ctx, a, mr, mq); break;
-			case 5: rc = launch_fast<8, true>(ctx, a, mr, mq); break;
-			case 6: rc = launch_fast<16, false>(ctx, a, mr, mq); break;
-			default: rc = launch_fast<16, true>(ctx, a, mr, mq); break;
+			case 0: rc = launch_team<2, false>(ctx, a, mr, mq); break;
+			case 1: rc = launch_team<2, true>(ctx, a, mr, mq); break;
+			case 2: rc = launch_team<4, false>(ctx, a, mr, mq); break;
+			case 3: rc = launch_team<4, true>(ctx, a, mr, mq); break;
+			case 4: rc = launch_team<8, false>(ctx, a, mr, mq); break;
+			case 5: rc = launch_team<8, true>(ctx, a, mr, mq); break;
+			case 6: rc = launch_team<16, false>(ctx, a, mr, mq); break;
+			case 7: rc = launch_team<16, true>(ctx, a, mr, mq); break;
+			case 8: rc = launch_team<32, false>(ctx, a, mr, mq); break;
+			default: rc = launch_team<32, true>(ctx, a, mr, mq); break;
 			}
 			(wrap ? ctx->stats.tasks_fast_wrap : ctx->stats.tasks_fast_nowrap) += cnt;
 		}

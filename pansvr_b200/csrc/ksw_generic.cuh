@@ -1,7 +1,7 @@
 // ksw_generic.cuh -- catch-all device kernel: one thread per alignment, rows in global scratch.
 //
-// Covers what the fast kernel (ksw_fast.cuh) declines: KSW_EZ_RIGHT, KSW_EZ_GENERIC_SC,
-// KSW_EZ_APPROX_MAX/DROP, bands wider than 496 cells, gap costs above 127.  It executes the
+// Covers what the team kernel (ksw_team.cuh) declines: KSW_EZ_RIGHT, KSW_EZ_GENERIC_SC,
+// KSW_EZ_APPROX_MAX/DROP, bands wider than 32 blocks of 16 cells, gap costs above 127.  It executes the
 // reference's 16-lane int8 machine literally (src/kswlib/ksw2_extd2_sse.c:26-396,
 // src/kswlib/ksw2.h:106-151,238-261): seven int8 rows indexed by target position, band rounded
 // to 16-cell blocks, byte arithmetic with wrap-around, int32 H row with the SSE scan's tie
@@ -12,7 +12,7 @@
 #include <stdint.h>
 #include <string>
 #include "../../include/pansvr_b200.h"
-#include "ksw_fast.cuh"
+#include "ksw_common.cuh"
 
 namespace kswgeneric {
 

@@ -5,14 +5,14 @@
 #pragma once
 #include <stdint.h>
 #include <algorithm>
-#include "ksw_fast.cuh"
+#include "ksw_common.cuh"
 
 namespace kswhost {
 
 struct Plan {
 	kswfast::Params P;
 	bool trivial;        // reference returns right after ksw_reset_extz (KSW:68 m<=1, KSW:93 mismatch too large)
-	bool fast_params;    // flags + scoring admit the fast kernel (WRAP variant, always exact)
+	bool fast_params;    // flags + scoring admit the team kernel (WRAP variant, always exact)
 	bool nowrap_ok;      // ... and unclipped tasks may use the variant without wrap masks
 };
 
@@ -91,16 +91,16 @@ static inline int n_col_blocks(int qlen, int tlen, int w)
 	return (std::min(n, w + 1) + 15) / 16 + 1;
 }
 
-// smallest cells-per-lane whose window holds the widest rounded band plus the one block the
-// score refresh may run ahead: 32*CPL >= (n_col_blocks+1)*16.  0 = too wide for the fast kernel.
 // does the band ever cut the matrix?  (unclipped iff qlen,tlen <= w+1)
 static inline bool band_clips(int qlen, int tlen, int w) { return w >= 0 && (qlen > w + 1 || tlen > w + 1); }
 
-static inline int pick_cpl(int qlen, int tlen, int w)
+// lanes per alignment of the team kernel: one lane per 16-cell block of the widest rounded band
+// (n_col_blocks), rounded up to a power of two.  0 = wider than a warp.
+static inline int pick_team(int qlen, int tlen, int w)
 {
-	const int need = (n_col_blocks(qlen, tlen, w) + 1) * 16;
-	for (int cpl = 2; cpl <= 16; cpl *= 2)
-		if (32 * cpl >= need) return cpl;
+	const int need = n_col_blocks(qlen, tlen, w);
+	for (int t = 2; t <= 32; t *= 2)
+		if (t >= need) return t;
 	return 0;
 }
 

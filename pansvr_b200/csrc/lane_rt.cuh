@@ -94,6 +94,7 @@ LANE_FN uint32_t hi16u(uint32_t v) { return v >> 16; }
 LANE_FN int lane_id() { return (int)(threadIdx.x & 31u); }
 LANE_FN uint32_t shfl(uint32_t v, int src) { return __shfl_sync(0xffffffffu, v, src); }           // SHFL.IDX
 LANE_FN int shfl(int v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+LANE_FN int shfl_xor(int v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }                  // SHFL.BFLY
 LANE_FN int wmax(int v) { return __reduce_max_sync(0xffffffffu, v); }                             // CREDUX.MAX.S32
 LANE_FN int wmin(int v) { return __reduce_min_sync(0xffffffffu, v); }
 LANE_FN uint32_t wballot(bool p) { return __ballot_sync(0xffffffffu, p); }
@@ -104,6 +105,7 @@ LANE_FN int popc32(uint32_t v) { return __popc(v); }
 LANE_FN int lane_id() { return WarpEmul::lane(); }
 LANE_FN uint32_t shfl(uint32_t v, int src) { return WarpEmul::shfl(v, src); }
 LANE_FN int shfl(int v, int src) { return (int)WarpEmul::shfl((uint32_t)v, src); }
+LANE_FN int shfl_xor(int v, int m) { return (int)WarpEmul::shfl((uint32_t)v, WarpEmul::lane() ^ m); }
 LANE_FN int wmax(int v) { return WarpEmul::wmax(v); }
 LANE_FN int wmin(int v) { return -WarpEmul::wmax(-v); }
 LANE_FN uint32_t wballot(bool p) { return WarpEmul::ballot(p); }
@@ -111,5 +113,42 @@ LANE_FN void wsync() { WarpEmul::sync(); }
 LANE_FN int ffs32(uint32_t v) { return __builtin_ffs((int)v); }
 LANE_FN int popc32(uint32_t v) { return __builtin_popcount(v); }
 #endif
+
+// 8 registers <-> 32 bytes of 16-byte aligned shared memory (two 128-bit accesses on the device)
+LANE_FN void st8(uint32_t *p, const uint32_t *r)
+{
+#ifndef PANSVR_HOST_EMUL
+	((uint4*)p)[0] = make_uint4(r[0], r[1], r[2], r[3]);
+	((uint4*)p)[1] = make_uint4(r[4], r[5], r[6], r[7]);
+#else
+	for (int i = 0; i < 8; ++i) p[i] = r[i];
+#endif
+}
+LANE_FN void ld8(const uint32_t *p, uint32_t *r)
+{
+#ifndef PANSVR_HOST_EMUL
+	const uint4 a = ((const uint4*)p)[0], b = ((const uint4*)p)[1];
+	r[0] = a.x; r[1] = a.y; r[2] = a.z; r[3] = a.w; r[4] = b.x; r[5] = b.y; r[6] = b.z; r[7] = b.w;
+#else
+	for (int i = 0; i < 8; ++i) r[i] = p[i];
+#endif
+}
+// 4 ints <-> 16 bytes of 16-byte aligned shared memory
+LANE_FN void ld4i(const int32_t *p, int *r)
+{
+#ifndef PANSVR_HOST_EMUL
+	const int4 a = *(const int4*)p; r[0] = a.x; r[1] = a.y; r[2] = a.z; r[3] = a.w;
+#else
+	for (int i = 0; i < 4; ++i) r[i] = p[i];
+#endif
+}
+LANE_FN void st4i(int32_t *p, int a, int b, int c, int d)
+{
+#ifndef PANSVR_HOST_EMUL
+	*(int4*)p = make_int4(a, b, c, d);
+#else
+	p[0] = a; p[1] = b; p[2] = c; p[3] = d;
+#endif
+}
 
 } // namespace lanert
