@@ -45,8 +45,8 @@ struct KArgs {
 };
 
 // Persistent CTAs; each warp pulls the next 32/TEAM alignments from the queue until it is empty.
-template <int TEAM, bool WRAP>
-__global__ void __launch_bounds__(THREADS) ksw_team_kernel(const __grid_constant__ KArgs a)
+template <int TEAM, bool WRAP, bool WC>
+__global__ void __launch_bounds__(THREADS, 4) ksw_team_kernel(const __grid_constant__ KArgs a)
 {
 	extern __shared__ __align__(16) uint8_t smem[];
 	constexpr int NT = 32 / TEAM, W = 16 * TEAM;
@@ -57,6 +57,9 @@ __global__ void __launch_bounds__(THREADS) ksw_team_kernel(const __grid_constant
 	uint8_t *QS = (uint8_t*)(Hsnap + W);
 	uint8_t *Ssp = base + a.smem_per_team - 32;
 	uint32_t *scr = (uint32_t*)(wbase + (size_t)NT * a.smem_per_team) + lane * 8;
+	uint32_t *mask_tab = (uint32_t*)(smem + (size_t)WARPS_PER_CTA * ((size_t)NT * a.smem_per_team + 32 * 32));
+	kswteam::fill_mask_table(mask_tab, threadIdx.x, THREADS);
+	__syncthreads();
 	uint8_t *tb = a.tb + ((size_t)(blockIdx.x * WARPS_PER_CTA + warp) * NT + team) * a.tb_per_team;
 	for (;;) {
 		int idx = 0;
@@ -65,9 +68,9 @@ __global__ void __launch_bounds__(THREADS) ksw_team_kernel(const __grid_constant
 		if (idx >= a.n) break;
 		const bool have = idx + team < a.n;
 		const int t = have ? a.order[idx + team] : a.order[idx];
-		kswteam::align_team<TEAM, WRAP>(a.P, have, have ? a.qlen[t] : 0, a.qseq + a.qoff[t], have ? a.tlen[t] : 0, a.tseq + a.toff[t],
+		kswteam::align_team<TEAM, WRAP, WC>(a.P, have, have ? a.qlen[t] : 0, a.qseq + a.qoff[t], have ? a.tlen[t] : 0, a.tseq + a.toff[t],
 		                                a.res + (size_t)t * kswfast::RES_WORDS, a.cigar + (size_t)t * a.cigar_cap, a.cigar_cap,
-		                                tb, Hs, Hsnap, QS, Ssp, scr);
+		                                tb, Hs, Hsnap, QS, Ssp, scr, mask_tab);
 	}
 }
 
@@ -205,13 +208,13 @@ void plan_batch(pansvr_ksw_ctx *ctx, const kswhost::Plan &pl, int64_t n, const i
 	for (int64_t i = 0; i < n; ++i) ctx->h_order[pos[(size_t)ctx->h_variant[i] * 256 + level(i)]++] = (int)i;
 }
 
-template <int TEAM, bool WRAP>
-int launch_team(pansvr_ksw_ctx *ctx, KArgs a, int max_rows, int max_qlen)
+template <int TEAM, bool WRAP, bool WC>
+int launch_team_wc(pansvr_ksw_ctx *ctx, KArgs a, int max_rows, int max_qlen)
 {
 	constexpr int W = 16 * TEAM, NT = 32 / TEAM;
 	a.smem_per_team = kswteam::team_smem_bytes(TEAM, max_qlen);
-	const int smem = (a.smem_per_team * NT + 32 * 32) * WARPS_PER_CTA;
-	auto kern = ksw_team_kernel<TEAM, WRAP>;
+	const int smem = (a.smem_per_team * NT + 32 * 32) * WARPS_PER_CTA + 512;
+	auto kern = ksw_team_kernel<TEAM, WRAP, WC>;
 	CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
 	int per_sm = 0;
 	CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, THREADS, smem));
@@ -229,6 +232,13 @@ int launch_team(pansvr_ksw_ctx *ctx, KArgs a, int max_rows, int max_qlen)
 	CU(cudaGetLastError());
 	++ctx->stats.kernel_launches;
 	return 0;
+}
+
+template <int TEAM, bool WRAP>
+int launch_team(pansvr_ksw_ctx *ctx, const KArgs &a, int max_rows, int max_qlen)
+{
+	return (a.P.flag & kswfast::F_SCORE_ONLY) ? launch_team_wc<TEAM, WRAP, false>(ctx, a, max_rows, max_qlen)
+	                                          : launch_team_wc<TEAM, WRAP, true>(ctx, a, max_rows, max_qlen);
 }
 
 // everything after the inputs are on the device: plan, launch each variant, leave results on the device

@@ -29,8 +29,12 @@ struct Params {           // one per batch, filled by the host (ksw_batch.cu: ma
 	int qe_as_passed;     // q+e before the swap (KSW:60)
 	int long_thres, long_diff;
 	int sc_mch, sc_mis, sc_N;
+	uint32_t one, mone;   // 1 and -1 the compiler cannot see through: a*one+b keeps an add on the FMA pipe (IMAD), see fadd()
 };
 
+// Integer adds that must not compete with LOP3/VIMNMX/PRMT for the ALU pipe: IMAD runs on the FMA pipe.
+LANE_FN uint32_t fadd(const Params &P, uint32_t a, uint32_t b) { return a * P.one + b; }        // a + b
+LANE_FN uint32_t fsub(const Params &P, uint32_t a, uint32_t z) { return z * P.mone + a; }       // a - z
 LANE_FN uint32_t k32(int v) { return (uint32_t)((int64_t)v * 65537); } // add v to both halves with a 32-bit add
 
 // band of anti-diagonal r before rounding (KSW:131-134)

@@ -48,6 +48,7 @@ static inline Plan make_plan(int m, const int8_t *mat, int q, int e, int q2, int
 	q = (int8_t)q; e = (int8_t)e; q2 = (int8_t)q2; e2 = (int8_t)e2;  // the reference takes int8_t arguments
 	P.qe_as_passed = q + e;
 	if (q2 + e2 < q + e) { std::swap(q, q2); std::swap(e, e2); }
+	P.one = 1u; P.mone = 0xffffffffu;
 	P.wild = m - 1; P.w = w; P.zdrop = zdrop; P.end_bonus = end_bonus; P.flag = flag;
 	P.q = q; P.e = e; P.q2 = q2; P.e2 = e2;
 	P.sc_mch = P.sc_mis = P.sc_N = 0; P.long_thres = P.long_diff = 0;

@@ -42,6 +42,8 @@ using namespace lanert;
 using kswfast::Params;
 using kswfast::band;
 using kswfast::k32;
+using kswfast::fadd;
+using kswfast::fsub;
 using kswfast::enc_t;
 using kswfast::enc_q;
 using kswfast::QS_PAD;
@@ -56,6 +58,16 @@ template <int TEAM> LANE_FN int team_max(int v)
 #pragma unroll
 	for (int o = TEAM / 2; o > 0; o >>= 1) { const int x = shfl_xor(v, o); v = x > v ? x : v; }
 	return v;
+}
+
+// Refresh-mask table: row a (0..15) holds, for the 8 registers of a block, the halves whose cell index is >= a.
+// 512 bytes of shared memory per CTA, filled once (ksw_batch.cu / the emulator harness).
+LANE_HD void fill_mask_table(uint32_t *tab, int first, int step)
+{
+	for (int e = first; e < 16 * 8; e += step) {
+		const int a = e >> 3, i = e & 7;
+		tab[e] = (2 * i >= a ? 0x0000ffffu : 0u) | (2 * i + 1 >= a ? 0xffff0000u : 0u);
+	}
 }
 
 // per-team shared memory, in bytes (Hs | Hsnap | QS | Ssp)
@@ -84,20 +96,20 @@ LANE_FN int resolve_argmax(const int32_t *H, int tl, int st0, int en0, int M)
 
 // 32/TEAM alignments, one per team of TEAM lanes; all arguments are team-uniform.
 //   Hs, Hsnap : 16*TEAM int32 of shared memory each (this team's)     QS : >= qlen+2 bytes (this team's)
-//   Ssp : 32 bytes (this team's)     scr : 8 words (this lane's)
+//   Ssp : 32 bytes (this team's)     scr : 8 words (this lane's)     mask_tab : fill_mask_table(), 128 words
 //   tb : this team's traceback scratch, >= (anti-diagonals+1) * 16*TEAM bytes (unused with SCORE_ONLY)
-template <int TEAM, bool WRAP>
+template <int TEAM, bool WRAP, bool WC>
 LANE_DEV void align_team(const Params &P, bool have_task, int qlen, const uint8_t *__restrict__ query, int tlen,
                          const uint8_t *__restrict__ target, int32_t *__restrict__ res, uint32_t *__restrict__ cigar,
                          int cigar_cap, uint8_t *__restrict__ tb, int32_t *Hs, int32_t *Hsnap, uint8_t *QS, uint8_t *Ssp,
-                         uint32_t *scr)
+                         uint32_t *scr, const uint32_t *mask_tab)
 {
 	constexpr int NR = 8;                // registers per row per lane (16 cells)
 	constexpr int W = 16 * TEAM;         // cells resident in the team
 	const int lane = lane_id(), tl = lane & (TEAM - 1);
 	const int left = (lane & ~(TEAM - 1)) | ((tl + TEAM - 1) & (TEAM - 1));
 	const int w = P.w < 0 ? (tlen > qlen ? tlen : qlen) : P.w;
-	const bool with_cigar = !(P.flag & kswfast::F_SCORE_ONLY);
+	constexpr bool with_cigar = WC;   // WC == !(flag & SCORE_ONLY), chosen by the launcher
 	const int q8 = P.q * 8, qe8 = (P.q + P.e) * 8, q28 = P.q2 * 8, qe28 = (P.q2 + P.e2) * 8;
 
 	// packed constants (k32: added with a 32-bit add; dup16: operand of a 16x2 min/max)
@@ -128,7 +140,7 @@ LANE_DEV void align_team(const Params &P, bool have_task, int qlen, const uint8_
 	wsync();
 
 	// ---- per-lane rows of block blk
-	uint32_t U[NR], V[NR], MX[NR], MY[NR], MX2[NR], MY2[NR], S[NR], TB[NR], QB[NR], MA[NR];
+	uint32_t U[NR], V[NR], MX[NR], MY[NR], MX2[NR], MY2[NR], S[NR], TB[NR], QB[NR];
 	int blk = tl;
 	int ssp0 = -1, ssp1 = -1;            // block whose refreshed-ahead scores sit in Ssp[0..15] / Ssp[16..31]
 	bool t_wild = false;
@@ -159,7 +171,6 @@ LANE_DEV void align_team(const Params &P, bool have_task, int qlen, const uint8_
 		}
 	};
 	if (have_task) load_group(-1);
-	int a_cur = -1;
 
 	// ---- running ez (H-like quantities are scaled by 8)
 	int ez_max8 = 0, ez_max_t = -1, ez_max_q = -1, mqe8 = NEG_INF, mqe_t = -1, mte8 = NEG_INF, mte_q = -1, score8 = NEG_INF;
@@ -168,13 +179,12 @@ LANE_DEV void align_team(const Params &P, bool have_task, int qlen, const uint8_
 	const int n_diag = qlen + tlen - 1;
 	int32_t *hp = Hs + 16 * tl;
 
+	int st0n = 0, en0n = -1;                 // band of the next diagonal (computed once, used twice)
+	if (!done && n_diag > 0) band(0, qlen, tlen, w, st0n, en0n);
 	for (int r = 0; ; ++r) {
-		int st0 = 0, en0 = -1;
+		const int st0 = st0n, en0 = en0n;
 		bool live = !done && r < n_diag;
-		if (live) {
-			band(r, qlen, tlen, w, st0, en0);
-			if (st0 > en0) { zdropped = 1; done = true; live = false; }
-		}
+		if (live && st0 > en0) { zdropped = 1; done = true; live = false; }
 		if (!wballot(live)) break;
 		const int bs = st0 >> 4, be = en0 >> 4, a = st0 & 15;
 
@@ -224,43 +234,43 @@ LANE_DEV void align_team(const Params &P, bool have_task, int qlen, const uint8_
 				}
 			}
 			// -- boundary of the first block of the band (KSW:142-152)
-			const int uval = r == 0 ? -(P.q + P.e) : r < P.long_thres ? -P.e : r == P.long_thres ? P.long_diff : -P.e2;
+			auto first_val = [&]() __attribute__((always_inline)) {   // value of the first row / column on diagonal r (KSW:151,155)
+				return r == 0 ? -(P.q + P.e) : r < P.long_thres ? -P.e : r == P.long_thres ? P.long_diff : -P.e2;
+			};
 			if (blk == bs && !(bs > 0 && bs != last_bs)) {
-				const int bv = bs > 0 ? -(P.q + P.e) : uval;
+				const int bv = bs > 0 ? -(P.q + P.e) : first_val();
 				rcv1 = pk(bM, (uint32_t)(bv * 8 + bV));
 				rcv2 = BMd;
 			}
 			// -- first-row cell t = r (KSW:153-156): one half of three rows, through the lane's scratch
 			if ((be | 0) * 16 + 15 >= r && blk == (r >> 4)) {
-				const int k = r & 15, kw = k >> 1;
+				const int k = r & 15, kw = k >> 1, uval = first_val();
 				const uint32_t keep = (k & 1) ? 0x0000ffffu : 0xffff0000u, sh = (k & 1) ? 16 : 0;
 				st8(scr, MY); scr[kw] = (scr[kw] & keep) | ((uint32_t)bM << sh); ld8(scr, MY);
 				st8(scr, MY2); scr[kw] = (scr[kw] & keep) | ((uint32_t)bM << sh); ld8(scr, MY2);
 				st8(scr, U); scr[kw] = (scr[kw] & keep) | ((uint32_t)((uval * 8 + bU) & 0xffff) << sh); ld8(scr, U);
 			}
 			// -- substitution scores on [st0, st0+16*nbk): block bs cells >= a, then full blocks, then block bs+nbk cells < a
-			if (a != a_cur) {
-				a_cur = a;
-#pragma unroll
-				for (int i = 0; i < NR; ++i) MA[i] = (2 * i >= a ? 0x0000ffffu : 0u) | (2 * i + 1 >= a ? 0xffff0000u : 0u);
-			}
 			{
 				const bool in1 = blk >= bs && blk < bs + nbk, in2 = blk > bs && blk <= bs + nbk;
 				if (in1 || in2) {
-					const uint32_t L1 = in1 ? ~0u : 0u, L2 = in2 ? ~0u : 0u;
+					// refreshed halves: MA (first block), ~MA (block after the last full one), all (in between)
+					const uint32_t XM = (in2 && !in1) ? ~0u : 0u, YM = (in1 && in2) ? ~0u : 0u;
+					uint32_t MA[NR];
+					ld8(mask_tab + 8 * a, MA);
 					if (q_wild || t_wild) {
 #pragma unroll
 						for (int i = 0; i < NR; ++i) {
 							const uint32_t x = TB[i] ^ QB[i];
 							const uint32_t sn = SBASE + minu(x, ONE2) * (uint32_t)D1 + minu(x & 0x00300030u, ONE2) * (uint32_t)E2;
-							const uint32_t rm = (MA[i] & L1) | (~MA[i] & L2);
+							const uint32_t rm = (MA[i] ^ XM) | YM;
 							S[i] = (S[i] & ~rm) | (sn & rm);
 						}
 					} else {
 #pragma unroll
 						for (int i = 0; i < NR; ++i) {
 							const uint32_t sn = SBASE + minu(TB[i] ^ QB[i], ONE2) * (uint32_t)D1;
-							const uint32_t rm = (MA[i] & L1) | (~MA[i] & L2);
+							const uint32_t rm = (MA[i] ^ XM) | YM;
 							S[i] = (S[i] & ~rm) | (sn & rm);
 						}
 					}
@@ -270,43 +280,45 @@ LANE_DEV void align_team(const Params &P, bool have_task, int qlen, const uint8_
 			// -- the 16 cells of this lane, right to left so that [i-1] is still last diagonal's
 			active = blk >= bs && blk <= be;
 			if (active) {
-				uint32_t tbw[NR];
+				uint32_t pk4[4], tb_hi = 0;
 #pragma unroll
 				for (int i = NR - 1; i >= 0; --i) {
 					const uint32_t mxt1 = i > 0 ? prmt(MX[i > 0 ? i - 1 : 0], MX[i], 0x5432) : prmt(rcv1, MX[0], 0x5410);
 					const uint32_t vt1 = i > 0 ? prmt(V[i > 0 ? i - 1 : 0], V[i], 0x5432) : prmt(rcv1, V[0], 0x5432);
 					const uint32_t mx2t1 = i > 0 ? prmt(MX2[i > 0 ? i - 1 : 0], MX2[i], 0x5432) : prmt(rcv2, MX2[0], 0x5432);
 					const uint32_t ut = U[i];
-					uint32_t A = mxt1 + vt1 + CA, Bv = MY[i] + ut + CB;   // a b a2 b2 with their priority tags
-					uint32_t A2 = mx2t1 + vt1 + CA2, B2 = MY2[i] + ut + CB2;
+					// a b a2 b2 with their priority tags (adds on the FMA pipe)
+					uint32_t A = fadd(P, mxt1, fadd(P, vt1, CA)), Bv = fadd(P, MY[i], fadd(P, ut, CB));
+					uint32_t A2 = fadd(P, mx2t1, fadd(P, vt1, CA2)), B2 = fadd(P, MY2[i], fadd(P, ut, CB2));
 					if (WRAP) { A &= WM; Bv &= WM; A2 &= WM; B2 &= WM; }
 					uint32_t zk = max3u(S[i], A, Bv);
 					zk = max3u(zk, A2, B2);
 					const uint32_t Z = minu(zk & 0xfff8fff8u, MCH);
-					U[i] = Z - vt1 + CU;
-					V[i] = Z - ut + CV;
+					U[i] = fsub(P, fadd(P, Z, CU), vt1);
+					V[i] = fsub(P, fadd(P, Z, CV), ut);
 					if (WRAP) {
 						V[i] &= WM;
-						MX[i] = maxu((A - Z + CNA) & WM, BMd);
-						MY[i] = maxu((Bv - Z + CNB) & WM, BMd);
-						MX2[i] = maxu((A2 - Z + CNA2) & WM, BMd);
-						MY2[i] = maxu((B2 - Z + CNB2) & WM, BMd);
+						MX[i] = maxu(fsub(P, fadd(P, A, CNA), Z) & WM, BMd);
+						MY[i] = maxu(fsub(P, fadd(P, Bv, CNB), Z) & WM, BMd);
+						MX2[i] = maxu(fsub(P, fadd(P, A2, CNA2), Z) & WM, BMd);
+						MY2[i] = maxu(fsub(P, fadd(P, B2, CNB2), Z) & WM, BMd);
 					} else {
-						MX[i] = addmaxu(A, CNA - Z, BMd);
-						MY[i] = addmaxu(Bv, CNB - Z, BMd);
-						MX2[i] = addmaxu(A2, CNA2 - Z, BMd);
-						MY2[i] = addmaxu(B2, CNB2 - Z, BMd);
+						MX[i] = addmaxu(A, fsub(P, CNA, Z), BMd);
+						MY[i] = addmaxu(Bv, fsub(P, CNB, Z), BMd);
+						MX2[i] = addmaxu(A2, fsub(P, CNA2, Z), BMd);
+						MY2[i] = addmaxu(B2, fsub(P, CNB2, Z), BMd);
 					}
-					if (with_cigar)
-						tbw[i] = (zk & 0x00070007u) + minu(MX[i], BM8d) + 2u * minu(MY[i], BM8d) + 4u * minu(MX2[i], BM8d)
-						         + 8u * minu(MY2[i], BM8d) + CTB;
+					if (with_cigar) {                                 // traceback byte: tag + 8,16,32,64 for the four continuations
+						uint32_t tw = fadd(P, zk & 0x00070007u, CTB);
+						tw = minu(MY2[i], BM8d) * 8u + tw;
+						tw = minu(MX2[i], BM8d) * 4u + tw;
+						tw = minu(MY[i], BM8d) * 2u + tw;
+						tw = fadd(P, minu(MX[i], BM8d), tw);
+						if (i & 1) tb_hi = tw; else pk4[i >> 1] = prmt(tw, tb_hi, 0x6420);
+					}
 				}
-				if (with_cigar) {                                     // one traceback byte per cell, column = t mod W
-					uint32_t pk4[4];
-#pragma unroll
-					for (int i = 0; i < 4; ++i) pk4[i] = prmt(tbw[2 * i], tbw[2 * i + 1], 0x6420);
+				if (with_cigar)                                       // one traceback byte per cell, column = t mod W
 					kswfast::store_cells<16>(tb + (size_t)r * W + 16 * tl, pk4);
-				}
 			}
 
 			// -- exact H row (KSW:316-351), scaled by 8, in shared memory at column t mod W.  Cells outside
@@ -324,18 +336,24 @@ LANE_DEV void align_team(const Params &P, bool have_task, int qlen, const uint8_
 					for (int i = 0; i < NR; i += 2) {
 						int h[4];
 						ld4i(hp + 2 * i, h);
-						h[0] += (int)lo16u(V[i]) - bV; h[1] += (int)hi16u(V[i]) - bV;
-						h[2] += (int)lo16u(V[i + 1]) - bV; h[3] += (int)hi16u(V[i + 1]) - bV;
+						const uint32_t nbv = (uint32_t)(-bV);
+						h[0] = (int)fadd(P, lo16u(V[i]), fadd(P, (uint32_t)h[0], nbv)); h[1] = (int)fadd(P, hi16u(V[i]), fadd(P, (uint32_t)h[1], nbv));
+						h[2] = (int)fadd(P, lo16u(V[i + 1]), fadd(P, (uint32_t)h[2], nbv)); h[3] = (int)fadd(P, hi16u(V[i + 1]), fadd(P, (uint32_t)h[3], nbv));
 						st4i(hp + 2 * i, h[0], h[1], h[2], h[3]);
 						lmax = max3s(lmax, h[0], h[1]);
 						lmax = max3s(lmax, h[2], h[3]);
 					}
 				}
 				if (own_en) {                                         // the special last element (KSW:322)
-					if (en0 > 0) st8(scr, U); else st8(scr, V);
-					int d = (int)((ken & 1) ? hi16u(scr[ken >> 1]) : lo16u(scr[ken >> 1]));
-					if (en0 > 0) d = WRAP ? (d & 0x7ff) - 0x400 : d - bU;  // stored u is not wrapped yet
-					else d -= bV;
+					int d;
+					if (en0 > 0) {
+						st8(scr, U);
+						d = (int)((ken & 1) ? hi16u(scr[ken >> 1]) : lo16u(scr[ken >> 1]));
+						d = WRAP ? (d & 0x7ff) - 0x400 : d - bU;        // stored u is not wrapped yet
+					} else {                                          // single-column corner: H[0] += v[0]
+						st8(scr, V);
+						d = (int)((ken & 1) ? hi16u(scr[ken >> 1]) : lo16u(scr[ken >> 1])) - bV;
+					}
 					hp[ken] = Hprev + d;
 				}
 			} else if (blk == 0) hp[0] = (int)lo16u(V[0]) - bV - P.qe_as_passed * 8;   // r == 0 (KSW:351)
@@ -385,10 +403,9 @@ LANE_DEV void align_team(const Params &P, bool have_task, int qlen, const uint8_
 		if (live) {
 			// H[en0'-1] as it stands now is what the next diagonal's last element starts from; if that cell already
 			// left the band before this diagonal it has not changed since the value we hold
-			int st1, en1n;
-			band(r + 1, qlen, tlen, w, st1, en1n);
-			if (r + 1 < n_diag && st1 <= en1n) {
-				const int c = en1n > 0 ? en1n - 1 : 0;
+			band(r + 1, qlen, tlen, w, st0n, en0n);
+			if (r + 1 < n_diag && st0n <= en0n) {
+				const int c = en0n > 0 ? en0n - 1 : 0;
 				if (!(c < st0)) Hprev = Hs[c & (W - 1)];
 			}
 			last_bs = bs; st0_prev = st0;

@@ -9,8 +9,8 @@
 #include "../../pansvr_b200/csrc/ksw_team.cuh"
 
 // ---- team kernel: 32/TEAM alignments per emulated warp
-template <int TEAM, bool WRAP>
-static void run_team(const kswfast::Params &P, int nt, const int *ids, const uint8_t *qseq, const int64_t *qoff, const int32_t *qlen,
+template <int TEAM, bool WRAP, bool WC>
+static void run_team_wc(const kswfast::Params &P, int nt, const int *ids, const uint8_t *qseq, const int64_t *qoff, const int32_t *qlen,
                      const uint8_t *tseq, const int64_t *toff, const int32_t *tlen, int32_t *res, uint32_t *cigar, int cigar_cap)
 {
 	constexpr int NT = 32 / TEAM, W = 16 * TEAM;
@@ -21,7 +21,8 @@ static void run_team(const kswfast::Params &P, int nt, const int *ids, const uin
 	}
 	const int per_team = kswteam::team_smem_bytes(TEAM, maxq);
 	std::vector<uint8_t> smem((size_t)per_team * NT + 64, 0xCD);
-	std::vector<uint32_t> scr(32 * 8, 0xDEADBEEF);
+	std::vector<uint32_t> scr(32 * 8, 0xDEADBEEF), mtab(128);
+	kswteam::fill_mask_table(mtab.data(), 0, 1);
 	const size_t tb_per_team = ((size_t)maxrows + 1) * W + 64;
 	std::vector<uint8_t> tb(tb_per_team * NT, 0xEE);
 	uint8_t *sm = (uint8_t*)(((uintptr_t)smem.data() + 15) & ~(uintptr_t)15);
@@ -33,11 +34,19 @@ static void run_team(const kswfast::Params &P, int nt, const int *ids, const uin
 		int32_t *Hs = (int32_t*)base, *Hsnap = Hs + W;
 		uint8_t *QS = (uint8_t*)(Hsnap + W);
 		uint8_t *Ssp = base + per_team - 32;
-		kswteam::align_team<TEAM, WRAP>(P, have, have ? qlen[id] : 0, qseq + (have ? qoff[id] : 0), have ? tlen[id] : 0,
+		kswteam::align_team<TEAM, WRAP, WC>(P, have, have ? qlen[id] : 0, qseq + (have ? qoff[id] : 0), have ? tlen[id] : 0,
 		                                tseq + (have ? toff[id] : 0), res + (size_t)id * kswfast::RES_WORDS,
 		                                cigar + (size_t)id * cigar_cap, cigar_cap, tb.data() + (size_t)team * tb_per_team, Hs, Hsnap,
-		                                QS, Ssp, scr.data() + lane * 8);
+		                                QS, Ssp, scr.data() + lane * 8, mtab.data());
 	});
+}
+
+template <int TEAM, bool WRAP>
+static void run_team(const kswfast::Params &P, int nt, const int *ids, const uint8_t *qseq, const int64_t *qoff, const int32_t *qlen,
+                     const uint8_t *tseq, const int64_t *toff, const int32_t *tlen, int32_t *res, uint32_t *cigar, int cigar_cap)
+{
+	if (P.flag & kswfast::F_SCORE_ONLY) run_team_wc<TEAM, WRAP, false>(P, nt, ids, qseq, qoff, qlen, tseq, toff, tlen, res, cigar, cigar_cap);
+	else run_team_wc<TEAM, WRAP, true>(P, nt, ids, qseq, qoff, qlen, tseq, toff, tlen, res, cigar, cigar_cap);
 }
 
 extern "C" int emul_ksw_team_batch(int n, const uint8_t *qseq, const int64_t *qoff, const int32_t *qlen, const uint8_t *tseq,
