@@ -46,7 +46,7 @@ struct KArgs {
 
 // Persistent CTAs; each warp pulls the next 32/TEAM alignments from the queue until it is empty.
 template <int TEAM, bool WRAP, bool WC>
-__global__ void __launch_bounds__(THREADS, 4) ksw_team_kernel(const __grid_constant__ KArgs a)
+__global__ void __launch_bounds__(THREADS, 3) ksw_team_kernel(const __grid_constant__ KArgs a)
 {
 	extern __shared__ __align__(16) uint8_t smem[];
 	constexpr int NT = 32 / TEAM, W = 16 * TEAM;
@@ -67,7 +67,7 @@ __global__ void __launch_bounds__(THREADS, 4) ksw_team_kernel(const __grid_const
 		idx = __shfl_sync(0xffffffffu, idx, 0);
 		if (idx >= a.n) break;
 		const bool have = idx + team < a.n;
-		const int t = have ? a.order[idx + team] : a.order[idx];
+		const int t = a.order ? a.order[have ? idx + team : idx] : (have ? idx + team : idx);   // order == NULL: identity
 		kswteam::align_team<TEAM, WRAP, WC>(a.P, have, have ? a.qlen[t] : 0, a.qseq + a.qoff[t], have ? a.tlen[t] : 0, a.tseq + a.toff[t],
 		                                a.res + (size_t)t * kswfast::RES_WORDS, a.cigar + (size_t)t * a.cigar_cap, a.cigar_cap,
 		                                tb, Hs, Hsnap, QS, Ssp, scr, mask_tab);
@@ -147,6 +147,7 @@ struct Shape { int rows, team; };
 // Builds ctx->h_order (task ids grouped by kernel variant, most anti-diagonals first inside a
 // group) and returns per-variant [begin,end) plus the largest row count / query length per variant.
 struct BatchPlan {
+	bool identity;               // every task has the same shape: one variant, tasks in input order, no order[] upload
 	int begin[N_VARIANTS + 1];
 	int max_rows[N_VARIANTS], max_qlen[N_VARIANTS], max_tlen[N_VARIANTS];
 };
@@ -154,6 +155,26 @@ struct BatchPlan {
 void plan_batch(pansvr_ksw_ctx *ctx, const kswhost::Plan &pl, int64_t n, const int32_t *qlen, const int32_t *tlen, BatchPlan &bp)
 {
 	const int w = pl.P.w;
+	bp.identity = false;
+	{   // uniform batches (the common benchmark / fixed-read-length case) need no per-task plan at all
+		const int q0 = qlen[0], t0 = tlen[0];
+		int64_t i = 1;
+		while (i < n && qlen[i] == q0 && tlen[i] == t0) ++i;
+		if (i == n && !pl.trivial && q0 > 0 && t0 > 0 && pl.fast_params && q0 <= 8000) {
+			const int team = kswhost::pick_team(q0, t0, w);
+			if (team != 0) {
+				const bool wrap = !pl.nowrap_ok || kswhost::band_clips(q0, t0, w);
+				int lg = 0;
+				while ((2 << lg) < team) ++lg;
+				const int v = V_FAST0 + 2 * lg + (wrap ? 1 : 0);
+				for (int k = 0; k < N_VARIANTS; ++k) { bp.max_rows[k] = bp.max_qlen[k] = bp.max_tlen[k] = 0; bp.begin[k] = k <= v ? 0 : (int)n; }
+				bp.begin[N_VARIANTS] = (int)n;
+				bp.max_rows[v] = kswhost::n_diagonals(q0, t0, w); bp.max_qlen[v] = q0; bp.max_tlen[v] = t0;
+				bp.identity = true;
+				return;
+			}
+		}
+	}
 	ctx->h_variant.resize(n);
 	ctx->h_rows.resize(n);
 	ctx->h_order.resize(n);
@@ -251,11 +272,13 @@ int run_device(pansvr_ksw_ctx *ctx, int64_t n, const uint8_t *d_qseq, const int6
 	                                      pr->end_bonus, pr->flag);
 	BatchPlan bp;
 	plan_batch(ctx, pl, n, h_qlen, h_tlen, bp);
-	CU(ctx->order.reserve(sizeof(int) * (size_t)n));
 	CU(ctx->counters.reserve(sizeof(int) * N_VARIANTS));
-	CU(cudaMemcpyAsync(ctx->order.p, ctx->h_order.data(), sizeof(int) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+	if (!bp.identity) {
+		CU(ctx->order.reserve(sizeof(int) * (size_t)n));
+		CU(cudaMemcpyAsync(ctx->order.p, ctx->h_order.data(), sizeof(int) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+		ctx->stats.h2d_bytes += (int64_t)sizeof(int) * n;
+	}
 	CU(cudaMemsetAsync(ctx->counters.p, 0, sizeof(int) * N_VARIANTS, ctx->stream));
-	ctx->stats.h2d_bytes += (int64_t)sizeof(int) * n;
 	CU(cudaEventRecord(ctx->ev[1], ctx->stream));
 	KArgs a;
 	a.P = pl.P;
@@ -265,7 +288,7 @@ int run_device(pansvr_ksw_ctx *ctx, int64_t n, const uint8_t *d_qseq, const int6
 		const int cnt = bp.begin[v + 1] - bp.begin[v];
 		if (cnt == 0) continue;
 		a.n = cnt;
-		a.order = (const int*)ctx->order.p + bp.begin[v];
+		a.order = bp.identity ? nullptr : (const int*)ctx->order.p + bp.begin[v];
 		a.counter = (int*)ctx->counters.p + v;
 		int rc = 0;
 		if (v == V_TRIVIAL) {
