@@ -136,6 +136,41 @@ void ksw_extd2_sse(void *km, int qlen, const uint8_t *query, int tlen, const uin
                    const int8_t *mat, int8_t gapo, int8_t gape, int8_t gapo2, int8_t gape2, int w, int zdrop,
                    int end_bonus, int flag, pansvr_ksw_extz_t *ez);
 
+/* ------------------------------------------------------------------------------------------------
+ * The aln stage itself (`panSVR fc_aln`): seed -> chain -> ksw -> pairing -> SAM, one block of read pairs
+ * per call.  Replaces deCOY_CLASSIFY_MAIN::init_run / classify_pipeline step 1 / align_read_pair
+ * (src/PanSVgenerateVCF/read_realignment.cpp:26-176, 745-799).  Output is defined against
+ * `fc_aln -t 1` (the reference is only deterministic single-threaded).
+ */
+typedef struct {                /* MAP_PARA, read_realignment.hpp:43-128; 0 in every field = the reference's defaults */
+	int32_t match, mismatch, gap_open, gap_ex, gap_open2, gap_ex2, zdrop, band_width;
+	int32_t not_ori;            /* -Q */
+	int32_t max_use_read;       /* -R */
+} pansvr_aln_options_t;
+
+typedef struct {
+	int64_t reads, mems, ksw_tasks, ksw_cells, deferred_pairs;
+	double stage_seconds[6];    /* A encode/census, B seeding (GPU), C merge/expand/chain, D ksw planning, E ksw (GPU), F replay + SAM */
+} pansvr_aln_stats_t;
+
+typedef struct pansvr_aln_ctx pansvr_aln_ctx;
+
+/* Loads the deBGA index directory (the 8 files `deBGA index -k 22` writes + unipath.chr) and the header SAM of the
+ * original BAM, uploads the index to `device`.  Replaces deBGA_INDEX::load_index_file (deBGA_index.cpp:33-80). */
+int  pansvr_aln_create(const char *index_dir, const char *header_sam, const pansvr_aln_options_t *opt, int device, pansvr_aln_ctx **out);
+void pansvr_aln_destroy(pansvr_aln_ctx *ctx);
+/* Header text the reference writes in front of its output (the original header, verbatim). */
+const char *pansvr_aln_header_text(const pansvr_aln_ctx *ctx);
+/* One block: `fastq` holds interleaved pairs in the wire format of `fc_signal` (4-line FASTQ, alignment of the original
+ * BAM in the comment).  *sam / *ori receive malloc'ed, NUL-terminated SAM body text (records only) of the main output
+ * and of the `-p` output; free with pansvr_free.  The rand() replay state carries over from block to block. */
+int  pansvr_aln_block(pansvr_aln_ctx *ctx, const char *fastq, size_t fastq_bytes, char **sam, size_t *sam_bytes, char **ori, size_t *ori_bytes);
+int  pansvr_aln_last_stats(const pansvr_aln_ctx *ctx, pansvr_aln_stats_t *out);
+void pansvr_free(void *p);
+/* Same command line as `panSVR fc_aln` (classify_main, src/main.cpp:18-25): [options] <IndexDir> <reads.fq|-> <header.sam>.
+ * -S (SAM) output only. */
+int  pansvr_fc_aln_main(int argc, char **argv);
+
 #ifdef __cplusplus
 }
 #endif

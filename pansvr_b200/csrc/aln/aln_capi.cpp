@@ -1,0 +1,231 @@
+// aln_capi.cpp -- C ABI and command line of the aln stage (declared in include/pansvr_b200.h).
+#include <getopt.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <zlib.h>
+#include <string>
+#include <vector>
+
+#include "../../../include/pansvr_b200.h"
+#include "pipeline.hpp"
+
+using namespace pansvr;
+
+namespace { thread_local std::string g_aln_err; }
+
+struct pansvr_aln_ctx {
+	DebgaIndex idx;
+	AlnOptions opt;
+	SeedService *seeds = nullptr;
+	pansvr_ksw_ctx *ksw = nullptr;
+	AlnPipeline *pipe = nullptr;
+};
+
+namespace {
+
+// 4-line FASTQ records out of a memory buffer: "@name comment\nseq\n+...\nqual\n" (kseq_read, clib/utils.c:953-990)
+void parse_fastq(const char *p, size_t n, std::vector<FastqRec> &out)
+{
+	size_t i = 0;
+	auto line = [&](std::string &dst) -> bool {
+		if (i >= n) return false;
+		size_t e = i;
+		while (e < n && p[e] != '\n') ++e;
+		size_t l = e;
+		if (l > i && p[l - 1] == '\r') --l;
+		dst.assign(p + i, l - i);
+		i = e + 1;
+		return true;
+	};
+	std::string h, plus;
+	for (;;) {
+		FastqRec r;
+		do { if (!line(h)) return; } while (h.empty());
+		if (h[0] != '@' && h[0] != '>') return;
+		size_t sp = 1;
+		while (sp < h.size() && h[sp] != ' ' && h[sp] != '\t') ++sp;
+		r.name = h.substr(1, sp - 1);
+		while (sp < h.size() && (h[sp] == ' ' || h[sp] == '\t')) ++sp;
+		r.comment = sp < h.size() ? h.substr(sp) : std::string();
+		if (!line(r.seq) || !line(plus) || !line(r.qual)) return;
+		out.push_back(r);
+	}
+}
+
+AlnOptions from_c(const pansvr_aln_options_t *o)
+{
+	AlnOptions a;
+	if (!o) return a;
+	if (o->match) a.match = o->match;
+	if (o->mismatch) a.mismatch = o->mismatch;
+	if (o->gap_open) a.gap_open = o->gap_open;
+	if (o->gap_ex) a.gap_ex = o->gap_ex;
+	if (o->gap_open2) a.gap_open2 = o->gap_open2;
+	a.gap_ex2 = o->gap_ex2;
+	if (o->zdrop) a.zdrop = o->zdrop;
+	if (o->band_width) a.bw = o->band_width;
+	a.not_ori = o->not_ori != 0;
+	if (o->max_use_read > 0) a.max_use_read = o->max_use_read;
+	return a;
+}
+
+char *dup_out(const std::string &s, size_t *len)
+{
+	char *p = (char*)malloc(s.size() + 1);
+	if (!p) return nullptr;
+	memcpy(p, s.data(), s.size());
+	p[s.size()] = 0;
+	if (len) *len = s.size();
+	return p;
+}
+
+} // namespace
+
+extern "C" {
+
+int pansvr_aln_create(const char *index_dir, const char *header_sam, const pansvr_aln_options_t *opt, int device, pansvr_aln_ctx **out)
+{
+	if (!index_dir || !header_sam || !out) return PANSVR_E_ARG;
+	*out = nullptr;
+	pansvr_aln_ctx *c = new pansvr_aln_ctx();
+	c->opt = from_c(opt);
+	std::string err;
+	if (!c->idx.load(index_dir, header_sam, err)) { g_aln_err = err; delete c; return PANSVR_E_ARG; }
+	if (pansvr_ksw_create(device, &c->ksw) != 0) { g_aln_err = pansvr_last_error(); delete c; return PANSVR_E_CUDA; }
+	c->seeds = seed_service_create(c->idx, device, err);
+	if (!c->seeds) { g_aln_err = err; pansvr_ksw_destroy(c->ksw); delete c; return PANSVR_E_CUDA; }
+	c->pipe = new AlnPipeline(c->idx, c->opt, c->seeds, c->ksw);
+	*out = c;
+	return 0;
+}
+
+void pansvr_aln_destroy(pansvr_aln_ctx *c)
+{
+	if (!c) return;
+	delete c->pipe;
+	seed_service_destroy(c->seeds);
+	pansvr_ksw_destroy(c->ksw);
+	delete c;
+}
+
+const char *pansvr_aln_header_text(const pansvr_aln_ctx *c) { return c ? c->idx.header_text.c_str() : ""; }
+const char *pansvr_aln_last_error(void) { return g_aln_err.c_str(); }
+
+int pansvr_aln_block(pansvr_aln_ctx *c, const char *fastq, size_t n, char **sam, size_t *sam_bytes, char **ori, size_t *ori_bytes)
+{
+	if (!c || !fastq || !sam || !ori) return PANSVR_E_ARG;
+	std::vector<FastqRec> recs;
+	parse_fastq(fastq, n, recs);
+	std::vector<PairOutput> outp;
+	std::string err;
+	if (!c->pipe->align_block(recs, outp, err)) { g_aln_err = err; return PANSVR_E_CUDA; }
+	std::string s, o;
+	for (const PairOutput &p : outp) for (int k = 0; k < 2; ++k) if (!p.sam[k].empty()) { s += p.sam[k]; s += '\n'; }
+	for (const PairOutput &p : outp) for (int k = 0; k < 2; ++k) if (!p.ori[k].empty()) { o += p.ori[k]; o += '\n'; }
+	*sam = dup_out(s, sam_bytes);
+	*ori = dup_out(o, ori_bytes);
+	return 0;
+}
+
+int pansvr_aln_last_stats(const pansvr_aln_ctx *c, pansvr_aln_stats_t *out)
+{
+	if (!c || !out) return PANSVR_E_ARG;
+	const AlnPipeline::Stats &s = c->pipe->stats;
+	out->reads = (int64_t)s.reads; out->mems = (int64_t)s.mems; out->ksw_tasks = (int64_t)s.ksw_tasks; out->ksw_cells = (int64_t)s.ksw_cells;
+	out->deferred_pairs = (int64_t)s.deferred_pairs;
+	for (int i = 0; i < 6; ++i) out->stage_seconds[i] = s.t_stage[i];
+	return 0;
+}
+
+void pansvr_free(void *p) { free(p); }
+
+// ---- `panSVR fc_aln` command line (MAP_PARA::get_option, read_realignment.hpp:82-128)
+int pansvr_fc_aln_main(int argc, char **argv)
+{
+	pansvr_aln_options_t o;
+	memset(&o, 0, sizeof o);
+	std::string out_path = "./output.bam", ori_path = "./output_ori.bam";
+	bool sam = false;
+	int threads = 4, device = 0;
+	static const struct option lo[] = {
+		{"thread", 1, 0, 't'}, {"gap-open1", 1, 0, 'O'}, {"gap-open2", 1, 0, 'P'}, {"gap-extension1", 1, 0, 'E'}, {"gap-extension2", 1, 0, 'F'},
+		{"match-score", 1, 0, 'M'}, {"mis-score", 1, 0, 'm'}, {"zdrop", 1, 0, 'z'}, {"band-width", 1, 0, 'w'}, {"output", 1, 0, 'o'},
+		{"output_signal_ori", 1, 0, 'p'}, {"not-ori", 0, 0, 'Q'}, {"SAM", 0, 0, 'S'}, {"max_use_read", 1, 0, 'R'}, {"device", 1, 0, 'd'}, {0, 0, 0, 0}};
+	optind = 1;
+	int ch;
+	bool f_given = false;
+	while ((ch = getopt_long(argc, argv, "t:O:P:E:F:M:m:z:w:o:p:QSR:d:", lo, 0)) != -1) {
+		switch (ch) {
+		case 't': threads = atoi(optarg); break;
+		case 'O': o.gap_open = atoi(optarg); break;
+		case 'P': o.gap_open2 = atoi(optarg); break;
+		case 'E': o.gap_ex = atoi(optarg); break;
+		case 'F': o.gap_ex2 = atoi(optarg); f_given = true; break;
+		case 'M': o.match = atoi(optarg); break;
+		case 'm': o.mismatch = atoi(optarg); break;
+		case 'z': o.zdrop = atoi(optarg); break;
+		case 'w': o.band_width = atoi(optarg); break;     // parsed and ignored, like the reference (RR:817-827)
+		case 'o': out_path = optarg; break;
+		case 'p': ori_path = optarg; break;
+		case 'Q': o.not_ori = 1; break;
+		case 'S': sam = true; break;
+		case 'R': o.max_use_read = atoi(optarg); break;
+		case 'd': device = atoi(optarg); break;
+		default: return 1;
+		}
+	}
+	(void)f_given; (void)threads;                             // -t: host helper threads; the output is that of `-t 1`
+	if (argc - optind < 3) {
+		fprintf(stderr, "Usage: fc_aln [Options] <IndexDir> <ReadFiles.fq|-> <ori_header.sam>\n");
+		return 1;
+	}
+	if (!sam) { fprintf(stderr, "pansvr_b200 fc_aln: only SAM output (-S) is implemented\n"); return 1; }
+	pansvr_aln_ctx *ctx = nullptr;
+	int rc = pansvr_aln_create(argv[optind], argv[optind + 2], &o, device, &ctx);
+	if (rc != 0) { fprintf(stderr, "pansvr_b200 fc_aln: %s\n", pansvr_aln_last_error()); return 1; }
+	FILE *fo = fopen(out_path.c_str(), "w"), *fp = fopen(ori_path.c_str(), "w");
+	if (!fo || !fp) { fprintf(stderr, "pansvr_b200 fc_aln: cannot open the output files\n"); return 1; }
+	fputs(pansvr_aln_header_text(ctx), fo);
+	fputs(pansvr_aln_header_text(ctx), fp);
+	gzFile in = strcmp(argv[optind + 1], "-") == 0 ? gzdopen(0, "r") : gzopen(argv[optind + 1], "r");
+	if (!in) { fprintf(stderr, "pansvr_b200 fc_aln: cannot open %s\n", argv[optind + 1]); return 1; }
+	// blocks of at most 2 M pairs / 100 Mbp like load_reads (RR:109,126)
+	std::string block;
+	std::vector<char> buf(1 << 20);
+	long pairs_in_block = 0, lines = 0, bases = 0, total_pairs = 0;
+	const long max_pairs = o.max_use_read > 0 ? o.max_use_read : 0x7fffffff;
+	auto flush = [&]() -> bool {
+		if (block.empty()) return true;
+		char *s = nullptr, *r = nullptr; size_t sl = 0, rl = 0;
+		if (pansvr_aln_block(ctx, block.data(), block.size(), &s, &sl, &r, &rl) != 0) { fprintf(stderr, "pansvr_b200 fc_aln: %s\n", pansvr_aln_last_error()); return false; }
+		fwrite(s, 1, sl, fo); fwrite(r, 1, rl, fp);
+		pansvr_free(s); pansvr_free(r);
+		block.clear(); pairs_in_block = 0; bases = 0;
+		return true;
+	};
+	bool ok = true;
+	while (ok && total_pairs < max_pairs && gzgets(in, buf.data(), (int)buf.size())) {
+		const size_t l = strlen(buf.data());
+		block.append(buf.data(), l);
+		if (l && buf[l - 1] != '\n') continue;                 // long line, keep reading
+		++lines;
+		if (lines % 4 == 2) bases += (long)l;
+		if (lines % 8 == 0) {
+			++pairs_in_block; ++total_pairs;
+			if (pairs_in_block >= 2000000 || bases >= 100000000) ok = flush();
+		}
+	}
+	if (ok) ok = flush();
+	gzclose(in);
+	fclose(fo); fclose(fp);
+	pansvr_aln_stats_t st;
+	pansvr_aln_last_stats(ctx, &st);
+	fprintf(stderr, "pansvr_b200 fc_aln: %ld reads, %ld MEMs, %ld ksw tasks; stage seconds A %.3f B %.3f C %.3f D %.3f E %.3f F %.3f\n",
+	        (long)st.reads, (long)st.mems, (long)st.ksw_tasks, st.stage_seconds[0], st.stage_seconds[1], st.stage_seconds[2], st.stage_seconds[3],
+	        st.stage_seconds[4], st.stage_seconds[5]);
+	pansvr_aln_destroy(ctx);
+	return ok ? 0 : 1;
+}
+
+} // extern "C"

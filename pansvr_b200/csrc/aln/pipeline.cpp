@@ -1,0 +1,979 @@
+// pipeline.cpp -- see pipeline.hpp for the stage layout and the reference line numbers.
+#include "pipeline.hpp"
+
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <algorithm>
+#include <chrono>
+
+#include "../../../include/pansvr_b200.h"
+
+namespace pansvr {
+
+namespace {
+
+enum { FORWARD = 1, REVERSE = 0 };                         // clib/utils.h:72-73
+enum { ALN_LEFT = 0, ALN_RIGHT = 1, ALN_E2E = 2 };        // KSW_ALN_* read_realignment.hpp:185-187
+enum { MAX_OUTPUT_NUMBER = 6, MIN_CHAIN_SCORE = 20, MAX_CHAIN_SCORE_DIFF = 30, MIN_CHAIN_SCORE2 = 30, MIN_ALN_SCORE = 40 };
+enum { POS_N_MAX = 500, POS_N_MAX_LEVEL2 = 8000, RANDOM_NUM = 500, WAITING_LEN = 3, EINDEL = 1 };
+enum { MIN_STR_REPEAT_COUNT = 4, MIN_STR_DETECT_LEN = 15 };
+const uint32_t U32MAX = 0xffffffffu;
+const int I32MAX = 0x7fffffff;
+
+double now() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
+// ---------------------------------------------------------------------------------------------- small pieces
+uint8_t dna5(unsigned char c)                                  // charToDna5n, read_realignment.cpp:180-202
+{
+	switch (c) { case 'C': case 'c': return 1; case 'G': case 'g': return 2; case 'T': case 't': return 3; case 'n': return 4; default: return 0; }
+}
+char rev_char(char c)                                           // getReverseChar, clib/bam_file.c:320-328
+{
+	switch (c) { case 'A': case 'a': return 'T'; case 'C': case 'c': return 'G'; case 'G': case 'g': return 'C'; case 'T': case 't': return 'A'; }
+	return 'N';
+}
+void rev_str(std::string &s)                                    // getReverseStr_char, clib/bam_file.c:330-340
+{
+	const int len = (int)s.size(), half = len >> 1;
+	for (int i = 0; i < half; ++i) { const char t = s[i]; s[i] = rev_char(s[len - 1 - i]); s[len - 1 - i] = rev_char(t); }
+	if (len & 1) s[half] = rev_char(s[half]);
+}
+template <class T> void rev_qual(T *q, int len)                 // getReverseStr_qual(_char), clib/bam_file.c:342-360
+{                                                               // sic: i runs to len/2 inclusive, so an even length re-swaps its middle pair
+	const int half = len >> 1;
+	for (int i = 0; i < half + 1; ++i) { const int ri = len - 1 - i; const T t = q[i]; q[i] = q[ri]; q[ri] = t; }
+}
+
+CigarPath cig_char(char t, int size)                            // CIGAR_PATH(char, uint16_t), read_realignment.hpp:133-149
+{
+	static const char *ops = "MIDNSHP=XB";
+	const char *p = strchr(ops, t);
+	CigarPath c;
+	c.type = p ? (uint8_t)(p - ops) : 0;
+	c.size = (int16_t)(uint16_t)size;
+	return c;
+}
+CigarPath cig_bin(uint32_t w) { CigarPath c; c.type = (uint8_t)(w & 0xf); c.size = (int16_t)(w >> 4); return c; }
+bool cig_try_merge(CigarPath &a, const CigarPath &b)            // CIGAR_PATH::try_merge, read_realignment.hpp:159-178
+{
+	if (b.size < 0) {
+		if (a.type == 0) { a.size = (int16_t)(a.size + b.size); return true; }
+		if (a.type == 2) { a.size = (int16_t)(a.size - b.size); return true; }
+		return true;                                            // the reference asserts here
+	}
+	if (a.type == b.type || b.size == 0) { a.size = (int16_t)(a.size + b.size); return true; }
+	return false;
+}
+
+struct UniSeed { uint32_t read_begin, read_end, seed_id, ref_begin, ref_end, cov; };   // UNI_SEED, graph.hpp:42-49
+struct VertexU { uint64_t uid; uint32_t read_pos, uni_pos_off, length1, length2, pos_n, cov; };
+struct PathNode { float dist; int32_t pre_node; uint8_t used; };
+struct Edge { uint32_t to, from; int weight; float penalty; };
+
+int cmp_mem(const void *a, const void *b)                       // vertex_MEM::cmp, deBGA_index.hpp:33-50
+{
+	const Mem *x = (const Mem*)a, *y = (const Mem*)b;
+	if (x->uid > y->uid) return 1;
+	if (x->uid < y->uid) return -1;
+	if (x->read_pos > y->read_pos) return 1;
+	if (x->read_pos < y->read_pos) return -1;
+	return 0;
+}
+int cmp_seed(const void *a, const void *b)                      // UNI_SEED::cmp, graph.cpp:14-33
+{
+	const UniSeed *x = (const UniSeed*)a, *y = (const UniSeed*)b;
+	if (x->ref_end > y->ref_end) return 1;
+	if (x->ref_end < y->ref_end) return -1;
+	if (x->ref_begin > y->ref_begin) return 1;
+	if (x->ref_begin < y->ref_begin) return -1;
+	return 0;
+}
+
+// one chained strand of a read: sorted seeds + longest-path table (Graph_handler)
+struct Graph {
+	std::vector<UniSeed> v;
+	std::vector<PathNode> path;
+	bool is_str = false;
+	// state of sort_output
+	float max_distance = 0; uint32_t max_index = 0;
+	std::vector<int> same_top;
+};
+
+// a candidate alignment (MAX_IDX_OUTPUT, read_realignment.hpp:232-318)
+struct Result {
+	uint32_t align_score = 0, chain_score = 0, max_index = 0, read_bg = 0;
+	const SvInfo *sv = nullptr;
+	uint8_t mapq = 0;
+	bool has_mate = false;
+	uint32_t mate_chr = 0, mate_ref_bg = 0;
+	const SvInfo *mate_sv = nullptr;
+	bool is_ori = false;
+	uint32_t chr = 0, ref_bg = 0;
+	int direction = FORWARD;
+	std::vector<CigarPath> cigar;
+	int rst_idx = 0;
+};
+
+// what get_ksw_score yields for one (strand, end node): pieces in emission order
+struct Piece {
+	int kind;                      // 0 = literal CIGAR entry, 1 = ksw task
+	CigarPath lit;
+	int task, type;                // ksw task id in the block list, KSW_ALN_* type
+};
+struct NodeAln {
+	std::vector<Piece> pieces;
+	int fixed_score = 0;           // everything but the ksw scores
+	int read_begin_alignment = 0;
+	bool planned = false;
+};
+
+} // namespace
+
+// ================================================================================================ per-read state
+struct ReadState {
+	const FastqRec *rec = nullptr;
+	std::string seq, qual, comment;            // mutable copies (the reference edits its kseq_t in place)
+	int read_l = 0;
+	bool has_n = false, skip = false;          // skip: early-out of single_end_handler::align (RR:413-414)
+	// original alignment (parse_ori_mapping_rst)
+	Result ori;
+	bool ori_unmapped = false;
+	// encoded read
+	std::vector<uint8_t> bin[2];
+	bool is_str = false;
+	std::vector<uint8_t> seed_list[2];
+	int job[2] = {-1, -1};
+	Graph g[2];
+	std::map<uint64_t, NodeAln> node_aln;      // key = strand << 32 | node
+	// results
+	int result_num = 0;
+	Result result[2 * MAX_OUTPUT_NUMBER];
+	Result *primary = nullptr, *secondary = nullptr;
+};
+
+struct KswTaskList {
+	std::vector<uint8_t> q, t;
+	std::vector<int64_t> qoff, toff;
+	std::vector<int32_t> qlen, tlen;
+	std::vector<int32_t> res;
+	std::vector<uint32_t> cig;
+	int cap = 64;
+	int add(const uint8_t *qs, int ql, const uint8_t *ts, int tl)
+	{
+		qoff.push_back((int64_t)q.size()); toff.push_back((int64_t)t.size());
+		qlen.push_back(ql); tlen.push_back(tl);
+		q.insert(q.end(), qs, qs + ql); t.insert(t.end(), ts, ts + tl);
+		return (int)qlen.size() - 1;
+	}
+	void clear() { q.clear(); t.clear(); qoff.clear(); toff.clear(); qlen.clear(); tlen.clear(); res.clear(); cig.clear(); }
+};
+
+struct AlnPipeline::Impl {
+	AlnPipeline &P;
+	const DebgaIndex &idx;
+	explicit Impl(AlnPipeline &p) : P(p), idx(p.idx_) {}
+
+	// ---------------------------------------------------------------- stage A
+	void parse_ori(ReadState &r)                                // parse_ori_mapping_rst, read_realignment.hpp:392-429
+	{
+		Result &o = r.ori;
+		o = Result();
+		o.is_ori = true;
+		std::string &c = r.comment;
+		std::vector<std::string> tok;
+		size_t i = 0;
+		std::vector<size_t> nul_at;
+		while (tok.size() < 10 && i < c.size()) {                // strtok_r(.., "_"): skip separators, cut at the next one
+			while (i < c.size() && c[i] == '_') ++i;
+			if (i >= c.size()) break;
+			size_t j = i;
+			while (j < c.size() && c[j] != '_') ++j;
+			tok.push_back(c.substr(i, j - i));
+			if (j < c.size()) nul_at.push_back(j);
+			i = j + 1;
+		}
+		while (tok.size() < 10) tok.push_back("");
+		o.chr = (uint32_t)atoi(tok[0].c_str());
+		o.ref_bg = (uint32_t)atoi(tok[1].c_str());
+		o.read_bg = (uint32_t)atoi(tok[2].c_str());
+		o.align_score = (uint32_t)atoi(tok[3].c_str());
+		o.mapq = (uint8_t)atoi(tok[4].c_str());
+		o.direction = (!tok[9].empty() && tok[9][0] == 'F') ? FORWARD : REVERSE;
+		r.ori_unmapped = tok[9].size() > 1 && tok[9][1] == 'Y';
+		o.cigar.clear();
+		if (o.read_bg > 0) o.cigar.push_back(cig_char('S', (int)o.read_bg));
+		o.cigar.push_back(cig_char('M', r.read_l - (int)o.read_bg));
+		o.sv = nullptr; o.has_mate = false;
+		if (o.ref_bg >= (uint32_t)I32MAX) o.ref_bg = 1;
+		for (size_t p : nul_at) if (p + 1 < c.size()) c[p] = ',';  // separators the tokenizer consumed come back as ','
+	}
+
+	void encode(ReadState &r)                                    // binary_read_2_bit, read_realignment.cpp:646-654
+	{
+		const int L = r.read_l;
+		r.bin[0].assign(L, 0); r.bin[1].assign(L, 0);
+		for (int i = 0; i < L; ++i) {
+			char ch = r.seq[i];
+			if (ch == 'N') ch = "ACGT"[P.rand_.next() % 4];
+			const uint8_t c = dna5((unsigned char)ch);
+			r.bin[0][i] = c;
+			r.bin[1][L - i - 1] = c ^ 3;
+		}
+	}
+
+	static void pack64(const std::vector<uint8_t> &b, std::vector<uint64_t> &out, size_t off)   // binary_read_64_bit, RR:295-300
+	{
+		for (size_t i = 0; i < b.size(); ++i) out[off + (i >> 5)] |= (uint64_t)b[i] << ((31 - (i & 0x1f)) << 1);
+	}
+
+	// STR census of the forward strand (read_realignment.cpp:553-598): k-mer multiplicities, mask, forced seeds
+	void str_census(ReadState &r, const uint64_t *bits)
+	{
+		const uint32_t L = (uint32_t)r.read_l, kn = L - LEN_KMER + 1;
+		std::vector<uint64_t> km(kn), sorted;
+		for (uint32_t i = 0; i < kn; ++i) km[i] = get_kmer(i, bits);
+		sorted = km;
+		std::sort(sorted.begin(), sorted.end());
+		const size_t distinct = (size_t)(std::unique(sorted.begin(), sorted.end()) - sorted.begin());
+		r.is_str = distinct < (size_t)kn - MIN_STR_DETECT_LEN;
+		r.seed_list[0].clear(); r.seed_list[1].clear();
+		if (!r.is_str) return;
+		std::vector<uint64_t> all = km;
+		std::sort(all.begin(), all.end());
+		std::vector<uint8_t> &sl = r.seed_list[0];
+		sl.assign(L, 0);                                         // repeat_seed_info is per handler and larger; only [0,kn) is read
+		for (uint32_t i = 0; i < kn; ++i) {
+			const int cnt = (int)(std::upper_bound(all.begin(), all.end(), km[i]) - std::lower_bound(all.begin(), all.end(), km[i]));
+			sl[i] = cnt >= MIN_STR_REPEAT_COUNT ? 0 : 1;
+		}
+		int bg = 0, ed = 0;
+		for (uint32_t i = 0; i < SEED_STEP; ++i) {
+			bg += sl[i] == 0; ed += sl[L - LEN_KMER - i] == 0;
+			sl[i] += 2; sl[L - LEN_KMER - i] += 4;
+		}
+		if (bg < SEED_STEP && ed < SEED_STEP) {
+			int n = 0;
+			for (uint32_t i = 0; n < SEED_STEP && i < kn; ++i) { if (sl[i] > 0) continue; sl[i] += 8; ++n; }
+		}
+		r.seed_list[1].assign(sl.begin(), sl.begin() + kn);
+		rev_qual(r.seed_list[1].data(), (int)kn);                // getReverseStr_qual(seed_list, kn), RR:601
+		r.seed_list[0].resize(kn);
+	}
+
+	// ---------------------------------------------------------------- stage C
+	void merge_mems(std::vector<Mem> &m, std::vector<VertexU> &out)   // merge_seed_in_unipath, deBGA_index.cpp:151-217
+	{
+		out.clear();
+		const uint32_t n = (uint32_t)m.size();
+		if (n == 0) return;
+		if (n == 1) {
+			VertexU u; u.uid = m[0].uid; u.read_pos = m[0].read_pos; u.uni_pos_off = m[0].uni_pos_off; u.pos_n = m[0].pos_n;
+			u.length1 = u.length2 = u.cov = m[0].length;
+			out.push_back(u);
+			return;
+		}
+		qsort(m.data(), n, sizeof(Mem), cmp_mem);
+		m.push_back(Mem());                                      // the reference reads one element past the end in its loop conditions
+		m[n].uid = ~0ull; m[n].uni_pos_off = 0;
+		uint64_t uid_t = m[0].uid;
+		uint32_t j = 0;
+		while (j < n) {
+			const uint32_t s1 = j;
+			uint32_t cov = m[s1].length;
+			++j;
+			while (uid_t == m[j].uid && m[j].uni_pos_off > m[j - 1].uni_pos_off && j < n) {
+				const int diff = (int)(m[j].read_pos - m[j - 1].read_pos - m[j - 1].length);
+				if (diff > WAITING_LEN) break;
+				const int c_eindel = (int)((m[j].uni_pos_off - m[j - 1].uni_pos_off) - (m[j].read_pos - m[j - 1].read_pos));
+				if (std::abs(c_eindel) < EINDEL) { cov += diff > 0 ? m[j].length : (uint32_t)(diff + (int)m[j].length); ++j; }
+				else break;
+			}
+			const uint32_t e1 = j - 1;
+			VertexU u;
+			u.uid = m[s1].uid; u.read_pos = m[s1].read_pos; u.uni_pos_off = m[s1].uni_pos_off; u.pos_n = m[s1].pos_n; u.cov = cov;
+			if (s1 == e1) u.length1 = u.length2 = m[s1].length;
+			else {
+				u.length1 = m[e1].read_pos + m[e1].length - m[s1].read_pos;
+				u.length2 = m[e1].uni_pos_off + m[e1].length - m[s1].uni_pos_off;
+			}
+			out.push_back(u);
+			uid_t = m[j].uid;
+		}
+		m.pop_back();
+	}
+
+	void expand(const std::vector<VertexU> &vu, std::vector<UniSeed> &out, GlibcRandom &rr)   // expand_seed, deBGA_index.cpp:219-258
+	{
+		for (uint32_t i = 0; i < vu.size(); ++i) {
+			const VertexU &u = vu[i];
+			auto push = [&](uint32_t mpos) {
+				UniSeed s;
+				s.seed_id = i; s.read_begin = u.read_pos; s.read_end = u.read_pos + u.length1 - 1;
+				s.ref_begin = (uint32_t)(idx.pos[mpos + idx.posp[u.uid]] + u.uni_pos_off - 1);
+				s.ref_end = s.ref_begin + u.length2 - 1; s.cov = u.cov;
+				out.push_back(s);
+			};
+			if (u.pos_n > POS_N_MAX) {
+				if (u.pos_n > POS_N_MAX_LEVEL2) return;          // sic: abandons every remaining vertex
+				for (int k = 0; k < RANDOM_NUM; ++k) push((uint32_t)(rr.next() % (int32_t)u.pos_n));
+			} else for (uint32_t mpos = 0; mpos < u.pos_n; ++mpos) push(mpos);
+		}
+	}
+
+	void chain(Graph &g)                                          // Graph_handler::process + dynamic_programming_path, graph.cpp:53-150
+	{
+		std::vector<UniSeed> &v = g.v;
+		const uint32_t n = (uint32_t)v.size();
+		g.path.clear();
+		if (n == 0) return;
+		qsort(v.data(), n, sizeof(UniSeed), cmp_seed);
+		const int max_ref_dis = g.is_str ? 400 : 50, max_read_dis = g.is_str ? 400 : 50;
+		const uint32_t max_step = g.is_str ? 80 : 40, max_gap = g.is_str ? 20 : 50;
+		const uint32_t step = std::min(n, max_step);
+		g.path.resize(n);
+		for (uint32_t i = 0; i < n; ++i) { g.path[i].dist = (float)v[i].cov; g.path[i].pre_node = -1; g.path[i].used = 0; }
+		std::vector<Edge> edges;
+		for (uint32_t a = 0; a + 1 < n; ++a) {
+			const uint32_t read_end = v[a].read_end, ref_end = v[a].ref_end, seed_id = v[a].seed_id;
+			const uint32_t stop = std::min(n, a + step);
+			for (uint32_t b = a + 1; b < stop; ++b) {
+				if (v[b].seed_id == seed_id) continue;
+				if (v[b].ref_end == ref_end) continue;
+				const int32_t dis_ref = (int32_t)(v[b].ref_begin - ref_end);
+				if (dis_ref > max_ref_dis) break;
+				const int32_t dis_read = (int32_t)(v[b].read_begin - read_end);
+				if (dis_read > max_read_dis) continue;
+				const uint32_t abs_gap = dis_read > dis_ref ? (uint32_t)(dis_read - dis_ref) : (uint32_t)(dis_ref - dis_read);
+				if (abs_gap > max_gap) continue;
+				const float penalty = abs_gap == 0 ? 0.f : (float)((abs_gap >> 3) + 3);
+				uint32_t weight;
+				if (dis_read == dis_ref) weight = v[b].cov - (uint32_t)std::max(1 - dis_read, 0);
+				else if (dis_read > 0 && dis_ref > 0) weight = v[b].cov;
+				else if (dis_read >= -5 && dis_read <= 0 && dis_ref >= -5) weight = v[b].cov + (uint32_t)std::min(dis_read, dis_ref);
+				else continue;
+				Edge e; e.to = b; e.from = a; e.weight = (int)weight; e.penalty = penalty;
+				edges.push_back(e);
+			}
+		}
+		if (edges.empty()) return;
+		std::stable_sort(edges.begin(), edges.end(), [](const Edge &x, const Edge &y) { return x.to < y.to; });   // per node, in insertion order
+		size_t k = 0;
+		while (k < edges.size()) {
+			const uint32_t to = edges[k].to;
+			float cur = 0; int32_t pre = -1;
+			for (; k < edges.size() && edges[k].to == to; ++k) {
+				const float temp = g.path[edges[k].from].dist + (float)edges[k].weight - edges[k].penalty;
+				if (cur <= temp) { cur = temp; pre = (int32_t)edges[k].from; }
+			}
+			g.path[to].dist = cur; g.path[to].pre_node = pre;
+		}
+	}
+
+	// ---------------------------------------------------------------- stage D: get_ksw_score as a plan (RR:308-400, 893-986)
+	struct Planner {
+		Impl &I; ReadState &r; int strand; KswTaskList &tasks; NodeAln &out;
+		std::vector<uint8_t> tseq, qrev;
+		int total_q_len = 0; bool last_simple = false;
+		Planner(Impl &i, ReadState &rs, int s, KswTaskList &t, NodeAln &o) : I(i), r(rs), strand(s), tasks(t), out(o) {}
+		void lit(char t, int size) { Piece p; p.kind = 0; p.lit = cig_char(t, size); p.task = -1; p.type = 0; out.pieces.push_back(p); }
+		int mismatch(int rs, int re, int fs, int fe)             // get_misMatch, RR:893-908
+		{
+			int qlen = re - rs, tlen = fe - fs;
+			if (fe < fs) { tlen = 0; qlen += fs - fe; }
+			tseq.resize(std::max(tlen, qlen) + 1);
+			I.idx.refseq(tseq.data(), (uint32_t)tlen, (uint32_t)fs);
+			const uint8_t *q = r.bin[strand].data() + rs;
+			int nm = 0;
+			for (int i = 0; i < qlen; ++i) nm += (i < tlen ? q[i] != tseq[i] : 1);
+			return nm > 3 ? 3 : nm;
+		}
+		void alignment(int rs, int re, int fs, int fe, int type)  // KSW_ALN_handler::alignment, RR:910-986
+		{
+			int qlen = re - rs, tlen = fe - fs;
+			if (fe < fs) { tlen = 0; qlen += fs - fe; }
+			tseq.assign((size_t)std::max(tlen, 0) + 1, 0);
+			I.idx.refseq(tseq.data(), (uint32_t)tlen, (uint32_t)fs);
+			const uint8_t *q = r.bin[strand].data() + rs;
+			if (type == ALN_LEFT) {
+				std::reverse(tseq.begin(), tseq.begin() + tlen);
+				qrev.assign(q, q + qlen);
+				std::reverse(qrev.begin(), qrev.end());
+				q = qrev.data();
+			}
+			total_q_len += qlen;
+			bool simple = false; uint32_t nm = 0;
+			if (qlen == 0 || tlen == 0) { simple = true; nm = (uint32_t)(qlen + tlen); }
+			else if (qlen == tlen || type != ALN_E2E) {
+				for (int i = 0; i < qlen && nm < 6; ++i) nm += (i < tlen ? q[i] != tseq[i] : 1);
+				if (nm == 1 || (nm < 6 && (int)(nm << 3) < qlen)) simple = true;
+			}
+			last_simple = simple;
+			const AlnOptions &o = I.P.opt;
+			if (simple) {
+				if (qlen == 0 || tlen == 0) {
+					if (nm != 0) out.fixed_score -= std::min(o.gap_open + ((int)nm - 1) * o.gap_ex, o.gap_open2 + ((int)nm - 1) * o.gap_ex2);
+				} else out.fixed_score += qlen * o.match - (int)nm * (o.match + o.mismatch);
+				if (qlen == 0) lit('D', tlen); else if (tlen == 0) lit('I', qlen); else lit('M', qlen);
+				if (fe < fs) lit('D', fe - fs);
+			} else if ((int64_t)tlen * qlen > 1000000) {           // align_non_splice guard, RR:874-887: fixed 2-element CIGAR, reset ez
+				const int sc = type == ALN_E2E ? 0 : PANSVR_KSW_NEG_INF;
+				out.fixed_score += sc;
+				const uint32_t c0 = (uint32_t)qlen << 4 | 1, c1 = (uint32_t)tlen << 4 | 3;
+				Piece a, b; a.kind = b.kind = 0; a.task = b.task = -1; a.type = b.type = 0;
+				a.lit = cig_bin(type == ALN_LEFT ? c0 : c1); b.lit = cig_bin(type == ALN_LEFT ? c1 : c0);
+				out.pieces.push_back(a); out.pieces.push_back(b);
+			} else {
+				Piece p; p.kind = 1; p.type = type; p.lit = CigarPath{0, 0};
+				p.task = tasks.add(q, qlen, tseq.data(), tlen);
+				out.pieces.push_back(p);
+			}
+		}
+		void run(int first_node)
+		{
+			const Graph &g = r.g[strand];
+			const AlnOptions &o = I.P.opt;
+			const int read_l = r.read_l;
+			int aln_read_begin = read_l, aln_read_end = read_l, aln_ref_begin = I32MAX, aln_ref_end = I32MAX;
+			int last_aln_begin = read_l, last_ref_begin = I32MAX, unitig_mis = 0;
+			for (int node = first_node; node != -1;) {
+				const UniSeed &s = g.v[node];
+				const int m_rb = (int)s.read_begin, m_re = (int)s.read_end, m_fb = (int)s.ref_begin, m_fe = (int)s.ref_end;
+				aln_read_begin = std::min(aln_read_begin, m_re);
+				aln_ref_begin = std::min(aln_ref_begin, m_fe);
+				if (aln_read_begin <= aln_read_end) {
+					if (aln_read_end < last_aln_begin) {
+						const int mem_len = last_aln_begin - aln_read_end;
+						unitig_mis += mismatch(aln_read_end, aln_read_end + mem_len, last_ref_begin, last_ref_begin + mem_len);
+						lit('M', mem_len);
+					}
+					last_aln_begin = aln_read_begin;
+					if (aln_ref_end == I32MAX) {
+						aln_ref_end = aln_ref_begin + (aln_read_end - aln_read_begin) + 30;
+						alignment(aln_read_begin, aln_read_end, aln_ref_begin, aln_ref_end, ALN_RIGHT);
+					} else alignment(aln_read_begin, aln_read_end, aln_ref_begin, aln_ref_end, ALN_E2E);
+				} else {
+					const int d_read = aln_read_end - aln_read_begin, d_ref = aln_ref_end - aln_ref_begin;
+					if (d_read != d_ref) {
+						const int del = std::abs(d_ref - d_read);
+						out.fixed_score -= std::min(o.gap_open + (del - 1) * o.gap_ex, o.gap_open2 + (del - 1) * o.gap_ex2);
+					}
+				}
+				aln_read_end = m_rb; last_ref_begin = m_fb; aln_ref_end = m_fb;
+				(void)m_re;
+				const int next = g.path[node].pre_node;
+				if (next == -1) break;
+				node = next;
+			}
+			if (aln_read_end < last_aln_begin) {
+				const int mem_len = last_aln_begin - aln_read_end;
+				unitig_mis += mismatch(aln_read_end, aln_read_end + mem_len, last_ref_begin, last_ref_begin + mem_len);
+				lit('M', mem_len);
+			}
+			aln_read_begin = 0; aln_ref_begin = 0;
+			int rba = 0;
+			if (aln_read_begin < aln_read_end) {
+				aln_ref_begin = std::max(0, aln_ref_end - (aln_read_end - aln_read_begin) - 30);
+				alignment(aln_read_begin, aln_read_end, aln_ref_begin, aln_ref_end, ALN_LEFT);
+				if (aln_ref_end > aln_ref_begin) rba = last_simple ? aln_ref_end - aln_ref_begin - 30 : aln_ref_end - aln_ref_begin;
+			}
+			out.fixed_score += (read_l - total_q_len) * o.match;
+			out.fixed_score -= unitig_mis * (o.match + o.mismatch);
+			out.read_begin_alignment = rba;
+			out.planned = true;
+		}
+	};
+
+	void plan_read(ReadState &r, KswTaskList &tasks)
+	{
+		r.node_aln.clear();
+		uint32_t best = 0;                                         // chain scores are compared as uint32 (RR:423-429, 442)
+		for (int s = 0; s < 2; ++s) for (const PathNode &p : r.g[s].path) best = std::max(best, (uint32_t)p.dist);
+		if (best < (uint32_t)MIN_CHAIN_SCORE) return;
+		for (int s = 0; s < 2; ++s) {
+			const Graph &g = r.g[s];
+			for (uint32_t n = 0; n < g.path.size(); ++n) {
+				const uint32_t c = (uint32_t)g.path[n].dist;
+				if (c < (uint32_t)MIN_CHAIN_SCORE2 || c + MAX_CHAIN_SCORE_DIFF < best) continue;
+				NodeAln &na = r.node_aln[(uint64_t)s << 32 | n];
+				Planner pl(*this, r, s, tasks, na);                // g[1] is the reverse strand, bin[1] its sequence
+				pl.run((int)n);
+			}
+		}
+	}
+
+	// ---------------------------------------------------------------- stage F
+	int sort_output(ReadState &r, int s, Result &rst, int direction)   // read_realignment.cpp:212-293
+	{
+		Graph &g = r.g[s];
+		const int n = (int)g.path.size();
+		if (n == 0) return 0;
+		for (;;) {
+			g.max_index = U32MAX; g.max_distance = 0;
+			g.same_top.clear(); g.same_top.push_back((int)g.max_index);
+			for (int i = n - 1; i >= 0; --i) {
+				if (g.path[i].used) continue;
+				const float d = g.path[i].dist;
+				if (g.max_distance < d) { g.max_distance = d; g.max_index = (uint32_t)i; g.same_top.clear(); g.same_top.push_back(i); }
+				else if (g.max_distance == d) g.same_top.push_back(i);
+			}
+			if (g.max_index == U32MAX) return 0;
+			int used = 0, fresh = 0;
+			const uint32_t same = (uint32_t)g.same_top.size();
+			if (same > 1) g.max_index = (uint32_t)g.same_top[P.rand_.next() % (int32_t)same];
+			int node = (int)g.max_index;
+			const int first = node;
+			for (; node != -1;) {
+				if (g.path[node].used) ++used; else ++fresh;
+				g.path[node].used = 1;
+				const int next = g.path[node].pre_node;
+				if (next == -1) break;
+				node = next;
+			}
+			const int last = node;
+			if (first - last > ((fresh + used + 5) << 1))
+				for (int k = last; k < first; ++k) g.path[k].used = 1;
+			if (used >= fresh) continue;                           // tail recursion in the reference
+			const int ref_begin = (int)g.v[node].ref_begin;
+			const int chr = idx.chromosome_id((uint32_t)ref_begin);
+			rst.direction = direction;
+			rst.max_index = g.max_index;
+			rst.chain_score = (uint32_t)g.max_distance;
+			rst.read_bg = g.v[node].read_begin;
+			rst.chr = (uint32_t)chr;
+			rst.ref_bg = (uint32_t)(ref_begin - (int)idx.chr_end_before(chr));
+			return 1;
+		}
+	}
+
+	static int cmp_chain(const void *a, const void *b)           // cmp_chain_score, read_realignment.hpp:303-308 (returns 0/1, sic)
+	{
+		const Result *x = *(Result* const*)a, *y = *(Result* const*)b;
+		if (x->chain_score != y->chain_score) return x->chain_score < y->chain_score;
+		return x->max_index > y->max_index;
+	}
+	static int cmp_align(const void *a, const void *b)           // cmp_align_score, read_realignment.hpp:310-315
+	{
+		const Result *x = *(Result* const*)a, *y = *(Result* const*)b;
+		if (x->align_score != y->align_score) return x->align_score < y->align_score;
+		return x->max_index > y->max_index;
+	}
+	// qsort of an array of large structs: glibc sorts pointers and permutes afterwards, same comparison order
+	void sort_results(Result *res, int n, int (*cmp)(const void*, const void*))
+	{
+		if (n < 2) return;
+		std::vector<Result*> p(n);
+		for (int i = 0; i < n; ++i) p[i] = res + i;
+		qsort(p.data(), n, sizeof(Result*), cmp);
+		std::vector<Result> tmp(n);
+		for (int i = 0; i < n; ++i) tmp[i] = *p[i];
+		for (int i = 0; i < n; ++i) res[i] = tmp[i];
+	}
+
+	bool reverse_cigar(Result &c, const std::vector<CigarPath> &tmp, int read_len)   // reverseGIGAR, read_realignment.hpp:277-301
+	{
+		c.cigar.clear();
+		if (tmp.empty()) return false;
+		c.cigar.push_back(tmp.back());
+		for (int i = (int)tmp.size() - 2; i >= 0; --i)
+			if (!cig_try_merge(c.cigar.back(), tmp[i])) c.cigar.push_back(tmp[i]);
+		if (!c.cigar.empty() && c.cigar[0].size == 0) c.cigar.erase(c.cigar.begin());
+		int total = 0;
+		for (const CigarPath &ci : c.cigar) if (ci.type == 0 || ci.type == 1 || ci.type == 3 || ci.type == 4) total += ci.size;
+		return total == read_len;
+	}
+
+	// the rest of single_end_handler::align once chains and ksw results exist (RR:416-475)
+	void finish_read(ReadState &r, const KswTaskList &tasks)
+	{
+		r.result_num = 0; r.primary = r.secondary = nullptr;
+		if (r.skip) return;
+		uint32_t max_chain = 0;
+		for (int s = 0; s < 2; ++s) {
+			const int direction = s == 0 ? FORWARD : REVERSE;
+			for (int i = 0; i < MAX_OUTPUT_NUMBER; ++i) {
+				Result &slot = r.result[r.result_num];
+				if (!sort_output(r, s, slot, direction)) break;
+				const uint32_t c = slot.chain_score;
+				max_chain = std::max(c, max_chain);
+				if (c + MAX_CHAIN_SCORE_DIFF < max_chain || c < MIN_CHAIN_SCORE2) break;
+				++r.result_num;
+			}
+		}
+		sort_results(r.result, r.result_num, cmp_chain);
+		if (r.result_num == 0 || max_chain < MIN_CHAIN_SCORE) return;
+		for (int k = 0; k < r.result_num; ++k) {
+			Result &c = r.result[k];
+			if (c.chain_score + MAX_CHAIN_SCORE_DIFF < max_chain) { r.result_num = k; break; }
+			const int s = c.direction == REVERSE ? 1 : 0;
+			auto it = r.node_aln.find((uint64_t)s << 32 | c.max_index);
+			if (it == r.node_aln.end() || !it->second.planned) {     // cannot happen: the plan is a superset
+				fprintf(stderr, "pansvr_b200: internal error, chain end %u of strand %d was not planned\n", c.max_index, s);
+				abort();
+			}
+			const NodeAln &na = it->second;
+			int score = na.fixed_score;
+			std::vector<CigarPath> tmp;
+			for (const Piece &p : na.pieces) {
+				if (p.kind == 0) { tmp.push_back(p.lit); continue; }
+				const int32_t *res = tasks.res.data() + (size_t)p.task * PANSVR_RES_WORDS;
+				const uint32_t *cg = tasks.cig.data() + (size_t)p.task * tasks.cap;
+				const int nc = res[PANSVR_RES_N_CIGAR];
+				if (p.type == ALN_E2E) { score += res[PANSVR_RES_SCORE]; for (int i = nc - 1; i >= 0; --i) tmp.push_back(cig_bin(cg[i])); }
+				else if (p.type == ALN_LEFT) { score += res[PANSVR_RES_MQE]; for (int i = 0; i < nc; ++i) tmp.push_back(cig_bin(cg[i])); }
+				else { score += res[PANSVR_RES_MQE]; for (int i = nc - 1; i >= 0; --i) tmp.push_back(cig_bin(cg[i])); }
+			}
+			c.ref_bg -= (uint32_t)na.read_begin_alignment;
+			c.align_score = (uint32_t)std::max(score, 0);
+			if (!reverse_cigar(c, tmp, r.read_l)) fprintf(stderr, "ERROR cigar: read_len: %d %s\n", r.read_l, r.seq.c_str());
+		}
+		sort_results(r.result, r.result_num, cmp_align);
+		if (r.result[0].align_score < (uint32_t)MIN_ALN_SCORE) { r.result_num = 0; return; }
+		for (int i = 0; i < r.result_num; ++i) {
+			Result &c = r.result[i];
+			const uint32_t sv_id = c.chr;
+			c.sv = &idx.sv_info[sv_id];
+			c.chr = c.sv->chr_id;
+			c.ref_bg += (uint32_t)c.sv->st_pos;
+			if (c.ref_bg >= (uint32_t)I32MAX) c.ref_bg = 5;
+			c.is_ori = false; c.rst_idx = i; c.mapq = 0; c.has_mate = false;
+		}
+		if (r.result_num > 0) {
+			const int32_t d = (int32_t)(r.result[0].align_score - (r.result_num > 1 ? r.result[1].align_score : 0));
+			r.result[0].mapq = (uint8_t)(d > 40 ? 40 : d);
+		}
+	}
+
+	// ---- PE_score (read_realignment.hpp:434-628)
+	struct PE {
+		int max_same = 1, max_score = 0, cur_isize = 0;
+		bool proper = false, gain = false;
+		Result *m1 = nullptr, *m2 = nullptr;
+	};
+	int get_isize(int p1, int p2, int d1, int d2) const
+	{
+		if (d1 == d2) return 0;
+		const int max_isize = P.opt.isize_max + 200, min_isize = std::max(0, P.opt.isize_min - 200);
+		const int isize = P.opt.read_len + (d1 == FORWARD ? p2 - p1 : p1 - p2);
+		return (isize < max_isize && isize > min_isize) ? isize : 0;
+	}
+	int proper_mated(const Result *a, const Result *b) const
+	{
+		if (!a || !b || a->chr != b->chr) return 0;
+		const int a1 = (int)a->ref_bg, a2 = a1 + (a->is_ori ? 0 : a->sv->end_offset);
+		const int b1 = (int)b->ref_bg, b2 = b1 + (b->is_ori ? 0 : b->sv->end_offset);
+		int v;
+		if ((v = get_isize(a1, b1, a->direction, b->direction)) > 0) return v;
+		if ((v = get_isize(a1, b2, a->direction, b->direction)) > 0) return v;
+		if ((v = get_isize(a2, b1, a->direction, b->direction)) > 0) return v;
+		if ((v = get_isize(a2, b2, a->direction, b->direction)) > 0) return v;
+		return 0;
+	}
+	void store_pair(PE &pe, Result *a, Result *b)
+	{
+		const int isize = proper_mated(a, b);
+		const int basic = (a ? (int)a->align_score : 0) + (b ? (int)b->align_score : 0);
+		const bool one_new = (a && !a->is_ori) || (b && !b->is_ori);
+		const int fin = basic + (isize > 0 ? 0 : -60) + (one_new ? 0 : 1);
+		if (fin >= pe.max_score) {
+			bool store = true;
+			if (fin > pe.max_score) pe.max_same = 1;
+			else if (fin == pe.max_score) { ++pe.max_same; if (P.rand_.next() % pe.max_same != 0) store = false; }
+			if (store) { pe.m1 = a; pe.m2 = b; pe.max_score = fin; pe.cur_isize = isize; pe.proper = isize > 0; }
+		}
+	}
+	void pair_up(ReadState *se, PE &pe)
+	{
+		pe = PE();
+		int n0 = se[0].result_num, n1 = se[1].result_num;
+		if (!se[0].ori_unmapped) ++n0;
+		if (!se[1].ori_unmapped) ++n1;
+		auto pick = [](ReadState &r, int i) -> Result* { return i < r.result_num ? &r.result[i] : &r.ori; };
+		for (int i = 0; i < n0; ++i) store_pair(pe, pick(se[0], i), nullptr);
+		for (int j = 0; j < n1; ++j) store_pair(pe, nullptr, pick(se[1], j));
+		for (int i = 0; i < n0; ++i) for (int j = 0; j < n1; ++j) store_pair(pe, pick(se[0], i), pick(se[1], j));
+		pe.gain = pe.max_score > 0 && ((pe.m1 && !pe.m1->is_ori) || (pe.m2 && !pe.m2->is_ori));
+	}
+	void set_primary(ReadState *se, PE &pe)                      // set_primary_secondary_mate, RRH:501-534
+	{
+		for (int i = 0; i < 2; ++i) {
+			Result *c = i == 0 ? pe.m1 : pe.m2;
+			if (!c) continue;
+			ReadState &h = se[i];
+			h.primary = c; h.secondary = nullptr;
+			if (c->is_ori && h.result_num > 0) h.secondary = &h.result[0];
+			else if (h.result_num > 1) h.secondary = c->rst_idx == 0 ? &h.result[1] : &h.result[0];
+			Result *m = i == 0 ? pe.m2 : pe.m1;
+			if (m && m->chr != U32MAX) {
+				c->has_mate = true; c->mate_chr = m->chr; c->mate_ref_bg = m->ref_bg; c->mate_sv = m->sv;
+				if (c->is_ori) c->sv = c->mate_sv;
+			} else { c->has_mate = false; c->mate_chr = 0; c->mate_sv = nullptr; }
+		}
+	}
+
+	// SAM text of one record after htslib's parse->format round trip (RR:479-536; sam.c sam_parse1 / sam_format1)
+	static void append_int(std::string &s, long v) { char b[32]; snprintf(b, sizeof b, "%ld", v); s += b; }
+	std::string target_name(uint32_t id) const { return id < idx.target_names.size() ? idx.target_names[id] : std::string("*"); }
+
+	void output_bam(ReadState &r, std::string &out, bool first, int abs_isize)
+	{
+		out.clear();
+		Result *p = r.primary;
+		if (!p || p->chr == U32MAX) return;
+		if (P.opt.not_ori && p->is_ori) return;
+		const int dir = p->direction;
+		const uint8_t flag = (uint8_t)((first ? 0x40 : 0) + (dir == REVERSE ? 0x10 : 0) + (p->has_mate ? 0 : 0x08));
+		out += r.rec->name; out += '\t'; append_int(out, flag); out += '\t';
+		out += target_name(p->chr); out += '\t'; append_int(out, (int)p->ref_bg); out += '\t'; append_int(out, p->mapq); out += '\t';
+		if (p->cigar.empty()) out += '*';
+		for (const CigarPath &c : p->cigar) { append_int(out, c.size); out += "MIDNSHP=XB"[c.type]; }
+		out += '\t';
+		const int isize = dir == FORWARD ? abs_isize : -abs_isize;
+		if (p->has_mate) {
+			out += (p->mate_chr == p->chr) ? std::string("=") : target_name(p->mate_chr);
+			out += '\t'; append_int(out, (int)p->mate_ref_bg); out += '\t'; append_int(out, isize); out += '\t';
+		} else out += "*\t0\t0\t";
+		if (dir == REVERSE) { rev_str(r.seq); rev_qual(&r.qual[0], r.read_l); }
+		out += r.seq; out += '\t'; out += r.qual; out += '\t';
+		out += "AS:i:"; append_int(out, (int)p->align_score);
+		if (dir == REVERSE) { rev_str(r.seq); rev_qual(&r.qual[0], r.read_l); }
+		out += "\tOS:i:"; append_int(out, (int)r.ori.align_score);
+		out += "\tOA:Z:"; append_int(out, (int)r.ori.chr); out += ','; append_int(out, (int)r.ori.ref_bg); out += ',';
+		append_int(out, (int)r.ori.read_bg); out += ','; append_int(out, r.ori.mapq); out += ','; out += r.ori_unmapped ? 'U' : 'M'; out += ';';
+		if (!p->is_ori) { out += "\tCS:i:"; append_int(out, (int)p->chain_score); }
+		if (p->sv) { out += "\tSV:Z:"; out += p->sv->vcf_print; }
+		if (p->mate_sv) { out += "\tMV:Z:"; out += p->mate_sv->vcf_print; }
+		if (r.secondary) {
+			const Result *s = r.secondary;
+			out += "\tXA:Z:"; append_int(out, (int)s->chr); out += ','; append_int(out, (int)s->ref_bg); out += ','; append_int(out, (int)s->read_bg);
+			out += ','; append_int(out, (int)s->align_score); out += ','; out += s->direction == FORWARD ? 'F' : 'R'; out += ',';
+			out += s->sv ? s->sv->vcf_id : std::string("*"); out += ';';
+		}
+		out += "\tRC:Z:"; out += r.comment;
+	}
+
+	// output_ori_bam (RR:656-717): the original alignment rebuilt from the comment; returns whether the original CIGAR shows a clip >= 25 / unmapped
+	void output_ori(ReadState &r, std::string &out, int max_score, bool &clip_or_unmapped)
+	{
+		out.clear(); clip_or_unmapped = true;
+		std::string &c = r.comment;
+		const size_t fpos = c.find("FLAG_");
+		if (fpos == std::string::npos) return;
+		unsigned flag = 0, qual = 0;
+		sscanf(c.c_str() + fpos + 5, "%u_%u_", &flag, &qual);
+		const size_t cpos = c.find("CIGAR_", fpos + 5);
+		if (cpos == std::string::npos) return;
+		const size_t cig_b = cpos + 6;
+		size_t cig_e = cig_b;
+		while (cig_e < c.size() && c[cig_e] != '_') ++cig_e;
+		const std::string cigar = c.substr(cig_b, cig_e - cig_b);
+		const size_t mate_b = cig_e + 1 + 5;
+		int mchr = 0, mpos = 0, isize = 0;
+		if (mate_b < c.size()) sscanf(c.c_str() + mate_b, "%d_%d_%d_", &mchr, &mpos, &isize);
+		mpos += 1;
+		std::string tags;
+		const size_t tpos = c.find("TAG_", mate_b < c.size() ? mate_b : c.size());
+		if (tpos != std::string::npos) tags = c.substr(tpos + 4);
+		const int tag_len = (int)tags.size();
+		for (int i = 0; i < tag_len - 5; ++i) if (tags[i] == '_' && tags[i + 3] == ':' && tags[i + 5] == ':') tags[i] = '\t';
+		if (tag_len > 0) tags.resize(tag_len - 1);
+		// the reference cuts the comment in place at the end of the CIGAR and edits the tags
+		c[cig_e < c.size() ? cig_e : c.size() - 1] = '\0';
+		out += r.rec->name; out += '\t'; append_int(out, flag); out += '\t'; out += target_name(r.ori.chr); out += '\t';
+		append_int(out, (long)(r.ori.ref_bg + 1)); out += '\t'; append_int(out, qual); out += '\t';
+		out += cigar.empty() ? std::string("*") : cigar; out += '\t';
+		out += ((uint32_t)mchr == r.ori.chr) ? std::string("=") : target_name((uint32_t)mchr);
+		out += '\t'; append_int(out, mpos); out += '\t'; append_int(out, isize); out += '\t';
+		const bool fwd = (flag & 0x10) == 0;
+		if (!fwd) { rev_str(r.seq); rev_qual(&r.qual[0], r.read_l); }
+		out += r.seq; out += '\t'; out += r.qual;
+		if (!fwd) { rev_str(r.seq); rev_qual(&r.qual[0], r.read_l); }
+		if (tag_len) { out += '\t'; out += tags; }
+		out += "\tMS:i:"; append_int(out, max_score);
+		// bam_has_clip_or_unmapped_ori (RR:721-733) on the CIGAR just written
+		if (cigar.empty()) { clip_or_unmapped = true; return; }
+		std::vector<std::pair<int, char>> ops;
+		for (size_t i = 0; i < cigar.size();) {
+			int len = 0;
+			while (i < cigar.size() && cigar[i] >= '0' && cigar[i] <= '9') len = len * 10 + (cigar[i++] - '0');
+			if (i < cigar.size()) ops.push_back(std::make_pair(len, cigar[i++]));
+		}
+		int clip = 0;
+		if (!ops.empty()) {
+			if (ops.front().second == 'S' || ops.front().second == 'H') clip += ops.front().first;
+			if (ops.back().second == 'S' || ops.back().second == 'H') clip += ops.back().first;
+		}
+		clip_or_unmapped = ops.empty() || clip >= 25;
+	}
+};
+
+// ================================================================================================ public
+AlnPipeline::AlnPipeline(const DebgaIndex &idx, const AlnOptions &o, SeedService *seeds, void *ksw_ctx)
+	: opt(o), idx_(idx), seeds_(seeds), ksw_(ksw_ctx), rand_(1)
+{
+	// Classify_buff_pool of thread 0: two single_end_handlers, each seeds its random_r state with rand() (RR:62-67, RRH:339-340)
+	for (int i = 0; i < 2; ++i) rand_r_[i].reseed((unsigned)rand_.next());
+}
+
+bool AlnPipeline::align_block(const std::vector<FastqRec> &recs, std::vector<PairOutput> &out, std::string &err)
+{
+	Impl I(*this);
+	const size_t n_reads = recs.size() & ~(size_t)1, n_pairs = n_reads / 2;
+	out.assign(n_pairs, PairOutput());
+	if (n_pairs == 0) return true;
+	double t0 = now();
+
+	// read statistics from the first comment (load_reads, RR:134-148)
+	if (!opt.stat_set) {
+		const char *st = strstr(recs[0].comment.c_str(), "STAT_");
+		if (!st || sscanf(st + 5, "%d_%d_%d_%d_", &opt.read_len, &opt.isize_min, &opt.isize_mid, &opt.isize_max) == -1) {
+			opt.read_len = 150; opt.isize_min = 100; opt.isize_mid = 500; opt.isize_max = 900;
+		}
+		min_filter_score_ = std::max(opt.read_len * opt.match * 2 - 80, 50);
+		opt.stat_set = true;
+	}
+
+	// ---- stage A
+	std::vector<ReadState> rs(n_reads);
+	SeedBatch sb;
+	for (size_t i = 0; i < n_reads; ++i) {
+		ReadState &r = rs[i];
+		r.rec = &recs[i];
+		r.seq = recs[i].seq; r.qual = recs[i].qual; r.comment = recs[i].comment;
+		r.read_l = (int)r.seq.size();
+		I.parse_ori(r);
+		if (r.ori.chr > 24) r.ori_unmapped = true;                        // RR:413
+		r.skip = !r.ori_unmapped && r.ori.align_score == (uint32_t)(r.read_l * opt.match);   // RR:414
+		r.has_n = r.seq.find('N') != std::string::npos;
+	}
+	// Reads with 'N' draw their replacement bases from rand() at their turn in the replay; a pair with such a read
+	// is aligned synchronously in stage F.  Everything else is batched.
+	auto stage_AC_prepare = [&](size_t i, SeedBatch &sb) {                    // encode + census + job registration
+		ReadState &r = rs[i];
+		I.encode(r);
+		const size_t words = (size_t)(r.read_l >> 5) + 2;
+		for (int s = 0; s < 2; ++s) {
+			SeedJob j;
+			j.bits_off = (uint32_t)sb.bits.size(); j.read_len = (uint32_t)r.read_l; j.is_str = 0; j.list_off = 0;
+			sb.bits.resize(sb.bits.size() + words, 0);
+			Impl::pack64(r.bin[s], sb.bits, j.bits_off);
+			if (s == 0) I.str_census(r, sb.bits.data() + j.bits_off);
+			if (r.is_str) {
+				j.is_str = 1; j.list_off = (uint32_t)sb.seed_list.size();
+				sb.seed_list.insert(sb.seed_list.end(), r.seed_list[s].begin(), r.seed_list[s].end());
+			}
+			r.job[s] = (int)sb.jobs.size();
+			sb.jobs.push_back(j);
+		}
+	};
+	auto stage_C = [&](size_t i, const SeedBatch &b) {                       // merge, expand, chain
+		ReadState &r = rs[i];
+		for (int s = 0; s < 2; ++s) {
+			const int j = r.job[s];
+			std::vector<Mem> mems(b.mems.begin() + b.mem_off[j], b.mems.begin() + b.mem_off[j + 1]);
+			std::vector<VertexU> vu;
+			I.merge_mems(mems, vu);
+			Graph &g = r.g[s];
+			g.v.clear(); g.is_str = r.is_str;
+			I.expand(vu, g.v, rand_r_[i & 1]);
+			I.chain(g);
+			stats.mems += mems.size();
+		}
+	};
+	for (size_t i = 0; i < n_reads; ++i) {
+		ReadState &r = rs[i];
+		const bool pair_has_n = rs[i & ~(size_t)1].has_n || rs[i | 1].has_n;
+		if (r.skip || pair_has_n || r.read_l < LEN_KMER) continue;
+		stage_AC_prepare(i, sb);
+	}
+	stats.t_stage[0] += now() - t0; t0 = now();
+	// ---- stage B
+	if (!sb.jobs.empty() && !seed_service_run(seeds_, sb, err)) return false;
+	stats.t_stage[1] += now() - t0; t0 = now();
+	// ---- stage C (in read order: the random_r streams are per mate handler)
+	KswTaskList tasks;
+	for (size_t i = 0; i < n_reads; ++i) if (rs[i].job[0] >= 0) stage_C(i, sb);
+	stats.t_stage[2] += now() - t0; t0 = now();
+	// ---- stage D
+	for (size_t i = 0; i < n_reads; ++i) if (rs[i].job[0] >= 0) I.plan_read(rs[i], tasks);
+	stats.t_stage[3] += now() - t0; t0 = now();
+	// ---- stage E
+	const int8_t m = (int8_t)opt.match, x = (int8_t)-opt.mismatch;
+	int8_t mat[25];
+	for (int a = 0, k = 0; a < 5; ++a) for (int b = 0; b < 5; ++b, ++k) mat[k] = (a == 4 || b == 4) ? 0 : (a == b ? m : x);   // ksw_gen_mat_D, RR:829-844
+	pansvr_ksw_params_t kp;
+	kp.m = 5; kp.mat = mat; kp.gapo = (int8_t)opt.gap_open; kp.gape = (int8_t)opt.gap_ex; kp.gapo2 = (int8_t)opt.gap_open2; kp.gape2 = (int8_t)opt.gap_ex2;
+	kp.w = 200; kp.zdrop = (uint16_t)opt.zdrop; kp.end_bonus = -1; kp.flag = 0;      // copy_option, RR:817-827
+	auto run_ksw = [&](KswTaskList &tl) -> bool {
+		const size_t n = tl.qlen.size();
+		tl.res.assign(n * PANSVR_RES_WORDS, 0);
+		tl.cig.assign(n * (size_t)tl.cap, 0);
+		if (n == 0) return true;
+		for (;;) {
+			const int rc = pansvr_ksw_extd2_batch((pansvr_ksw_ctx*)ksw_, (int64_t)n, tl.q.data(), (int64_t)tl.q.size(), tl.qoff.data(), tl.qlen.data(),
+			                                      tl.t.data(), (int64_t)tl.t.size(), tl.toff.data(), tl.tlen.data(), &kp, tl.res.data(), tl.cig.data(), tl.cap);
+			if (rc != 0) { err = std::string("ksw batch: ") + pansvr_last_error(); return false; }
+			int need = 0;
+			for (size_t i = 0; i < n; ++i) if (tl.res[i * PANSVR_RES_WORDS + PANSVR_RES_STATUS] & 1) need = std::max(need, tl.res[i * PANSVR_RES_WORDS + PANSVR_RES_N_CIGAR]);
+			if (!need) break;
+			tl.cap = need + 8;                                         // a CIGAR did not fit: redo the batch with room for the longest
+			tl.cig.assign(n * (size_t)tl.cap, 0);
+		}
+		stats.ksw_tasks += n;
+		for (size_t i = 0; i < n; ++i) stats.ksw_cells += (uint64_t)pansvr_ksw_band_cells(tl.qlen[i], tl.tlen[i], kp.w);
+		return true;
+	};
+	if (!run_ksw(tasks)) return false;
+	stats.t_stage[4] += now() - t0; t0 = now();
+
+	// ---- stage F: replay in input order
+	for (size_t pi = 0; pi < n_pairs; ++pi) {
+		ReadState *se = &rs[2 * pi];
+		if (se[0].has_n || se[1].has_n) {                                 // deferred pair: rand() position is only known now
+			++stats.deferred_pairs;
+			KswTaskList local;
+			for (int k = 0; k < 2; ++k) {
+				ReadState &r = se[k];
+				if (!r.skip && r.read_l >= LEN_KMER) {
+					SeedBatch one;
+					stage_AC_prepare(2 * pi + k, one);
+					if (!seed_service_run(seeds_, one, err)) return false;
+					stage_C(2 * pi + k, one);
+					I.plan_read(r, local);
+					if (!run_ksw(local)) return false;
+				}
+				I.finish_read(r, local);
+			}
+		} else {
+			for (int k = 0; k < 2; ++k) I.finish_read(se[k], tasks);
+		}
+		Impl::PE pe;
+		I.pair_up(se, pe);
+		PairOutput &po = out[pi];
+		if (pe.gain) {
+			I.set_primary(se, pe);
+			for (int k = 0; k < 2; ++k) I.output_bam(se[k], po.sam[k], k == 0, pe.cur_isize);
+		}
+		if (pe.max_score <= min_filter_score_ && (int)se[0].ori.chr != -1 && (int)se[1].ori.chr != -1) {   // RR:776-797
+			bool clip[2] = {true, true};
+			for (int k = 0; k < 2; ++k) I.output_ori(se[k], po.ori[k], pe.max_score, clip[k]);
+			bool proper = pe.proper;
+			for (int k = 0; proper && k < 2; ++k) {
+				const Result *c = k == 0 ? pe.m1 : pe.m2;
+				if (!c) { proper = false; break; }
+				if (c->is_ori && clip[k]) proper = false;
+				if (proper && !c->is_ori) {
+					int ins = 0;
+					for (const CigarPath &ci : c->cigar) if (ci.type == 1) ins += ci.size;
+					if (c->cigar.empty() || ins >= 25) proper = false;
+				}
+			}
+			if (proper) { po.ori[0].clear(); po.ori[1].clear(); }
+		}
+		stats.reads += 2;
+	}
+	stats.t_stage[5] += now() - t0;
+	return true;
+}
+
+} // namespace pansvr

@@ -1,0 +1,91 @@
+// pipeline.hpp -- the `panSVR fc_aln` block pipeline, restructured for a batched GPU back end.
+//
+// Reference: src/PanSVgenerateVCF/read_realignment.{cpp,hpp} (fc_aln), src/cpp_lib/graph.{cpp,hpp}
+// (chaining), src/PanSVgenerateVCF/deBGA_index.cpp (merge/expand of seeds).  The reference handles
+// one pair at a time on a CPU thread; here one block of pairs goes through stages so that the two
+// hot steps run as device batches:
+//
+//   A  host   2-bit encode, STR k-mer census, 64-bit packing                    (RR:646-654, 538-598, 295-300)
+//   B  GPU    seed lookup + MEM extension for every read strand                 (seed_core.cuh)
+//   C  host   merge MEMs per unipath, expand to reference positions, chain DP   (deBGA_index.cpp:151-305, graph.cpp:53-150)
+//   D  host   plan the ksw windows of every chain end that can still be chosen  (RR:308-400, 910-986)
+//   E  GPU    ksw_extd2 batch                                                   (ksw_team.cuh)
+//   F  host   sequential replay in input order: chain selection, result sort, pairing, SAM text,
+//             consuming the libc rand() stream exactly as the reference does   (RR:212-293, 406-476, 479-536, 745-799; RRH:434-628)
+//
+// Stage D works on a superset because which chain ends get extended depends on rand() tie-breaks
+// whose stream position depends on the ksw results of earlier pairs:
+// get_ksw_score is a pure function of (strand, end node), so every node with
+// dist >= max(30, best-30) is planned and the replay picks from the table.
+//
+// The output is defined against `panSVR fc_aln -t 1` (the only deterministic mode).
+#pragma once
+#include <stdint.h>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "index.hpp"
+#include "refrand.hpp"
+#include "seed_core.cuh"
+
+namespace pansvr {
+
+struct AlnOptions {                   // MAP_PARA, read_realignment.hpp:43-128 (defaults :33-41)
+	int match = 2, mismatch = 12, gap_open = 16, gap_ex = 1, gap_open2 = 32, gap_ex2 = 0;
+	int zdrop = 400, bw = 500;        // -w is parsed and ignored by the reference (RR:817-827): ksw runs with w=200
+	bool not_ori = false;             // -Q
+	int max_use_read = 0x7fffffff;
+	// read statistics (STAT_ field of the first comment, RR:134-148)
+	bool stat_set = false;
+	int read_len = 150, isize_min = 100, isize_mid = 500, isize_max = 900;
+};
+
+struct FastqRec { std::string name, comment, seq, qual; };
+
+// ---- device services (link-time: CUDA in the product library, host emulation in tests/emul) ---------------------
+struct SeedJob {                      // one read strand
+	uint32_t bits_off, read_len;      // word offset into SeedBatch::bits
+	uint32_t list_off;                // offset into SeedBatch::seed_list (STR reads only)
+	uint32_t is_str;
+};
+struct SeedBatch {
+	std::vector<uint64_t> bits;       // packed reads, 32 bases per word, one spare zero word after each read
+	std::vector<uint8_t> seed_list;
+	std::vector<SeedJob> jobs;
+	std::vector<Mem> mems;            // out: MEMs of job i are mems[mem_off[i] .. mem_off[i+1])
+	std::vector<uint32_t> mem_off;
+};
+struct SeedService;                   // opaque; owns the device-resident index
+SeedService *seed_service_create(const DebgaIndex &idx, int device, std::string &err);
+void seed_service_destroy(SeedService *s);
+bool seed_service_run(SeedService *s, SeedBatch &b, std::string &err);
+
+// ---- results of one pair --------------------------------------------------------------------------------------------
+struct PairOutput {
+	std::string sam[2];               // main output records (empty = none), without trailing newline
+	std::string ori[2];               // `-p` output: pairs still poorly aligned
+};
+
+struct CigarPath { uint8_t type; int16_t size; };
+
+class AlnPipeline {
+public:
+	AlnPipeline(const DebgaIndex &idx, const AlnOptions &opt, SeedService *seeds, void *ksw_ctx);
+	// Aligns n_pairs interleaved pairs (recs[2i], recs[2i+1]); out[i] receives the SAM text of pair i.
+	bool align_block(const std::vector<FastqRec> &recs, std::vector<PairOutput> &out, std::string &err);
+	struct Stats { uint64_t reads = 0, probes_reads = 0, mems = 0, ksw_tasks = 0, ksw_cells = 0, deferred_pairs = 0;
+	               double t_stage[6] = {0, 0, 0, 0, 0, 0}; } stats;
+	AlnOptions opt;                   // stat_set / read_len / isize_* are filled from the first comment
+private:
+	struct Impl;
+	const DebgaIndex &idx_;
+	SeedService *seeds_;
+	void *ksw_;
+	GlibcRandom rand_;                // the process-global rand() of the reference
+	GlibcRandom rand_r_[2];           // per-handler random_r states (RRH:339-340), seeded from rand_ at start-up
+	int min_filter_score_ = 0;
+	friend struct Impl;
+};
+
+} // namespace pansvr

@@ -1,0 +1,140 @@
+// seed_gpu.cu -- device-resident deBGA index and the batched seed lookup kernel (stage B).
+//
+// The eight index arrays are uploaded once, in their on-disk layout (so lookups are trivially the
+// reference's: SURVEY.md section 3.3), and stay in HBM for the life of the service: 2 GiB of
+// bucket starts + k-mer/offset/unipath tables.  One thread per read strand runs seed_read_strand()
+// (seed_core.cuh): its probes are dependent random accesses, so throughput comes from having
+// every SM full of strands in flight, not from per-thread speed.  Two passes (count, exclusive
+// scan, fill) give a compact MEM list without a worst-case buffer per strand.
+#include <cuda_runtime.h>
+#include <cub/device/device_scan.cuh>
+#include <string>
+
+#include "pipeline.hpp"
+
+namespace pansvr {
+
+namespace {
+
+#define SCU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { err = std::string(#call) + ": " + cudaGetErrorString(e_); return false; } } while (0)
+
+__global__ void seed_count_kernel(IndexView ix, const uint64_t *bits, const uint8_t *seed_list, const SeedJob *jobs, int n, uint32_t *count)
+{
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	const SeedJob j = jobs[i];
+	count[i] = (uint32_t)seed_read_strand(ix, bits + j.bits_off, j.read_len, j.is_str != 0, seed_list + j.list_off, (Mem*)nullptr, 0);
+}
+
+__global__ void seed_fill_kernel(IndexView ix, const uint64_t *bits, const uint8_t *seed_list, const SeedJob *jobs, int n,
+                                 const uint32_t *off, Mem *mems)
+{
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	const SeedJob j = jobs[i];
+	const int cap = (int)(off[i + 1] - off[i]);
+	if (cap > 0) seed_read_strand(ix, bits + j.bits_off, j.read_len, j.is_str != 0, seed_list + j.list_off, mems + off[i], cap);
+}
+
+struct Buf {
+	void *p = nullptr; size_t cap = 0;
+	bool reserve(size_t bytes, std::string &err)
+	{
+		if (bytes <= cap) return true;
+		if (p) cudaFree(p);
+		p = nullptr; cap = 0;
+		const size_t want = bytes + bytes / 4 + 256;
+		SCU(cudaMalloc(&p, want));
+		cap = want;
+		return true;
+	}
+	~Buf() { if (p) cudaFree(p); }
+};
+
+template <class T> bool upload(const std::vector<T> &h, T *&d, std::string &err)
+{
+	d = nullptr;
+	SCU(cudaMalloc((void**)&d, std::max<size_t>(h.size(), 1) * sizeof(T)));
+	SCU(cudaMemcpy(d, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+	return true;
+}
+
+} // namespace
+
+struct SeedService {
+	int device = 0;
+	cudaStream_t stream = nullptr;
+	uint64_t *seqb = nullptr, *seqf = nullptr, *posp = nullptr, *hash = nullptr, *off_g = nullptr;
+	uint32_t *kmer_g = nullptr;
+	IndexView view;
+	Buf bits, list, jobs, count, off, mems, tmp;
+	size_t index_bytes = 0;
+};
+
+SeedService *seed_service_create(const DebgaIndex &idx, int device, std::string &err)
+{
+	int ndev = 0;
+	if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) {
+		err = "seed service: no usable CUDA device (the seeding stage has no CPU fallback)";
+		return nullptr;
+	}
+	cudaSetDevice(device);
+	SeedService *s = new SeedService();
+	s->device = device;
+	auto fail = [&]() -> SeedService* { seed_service_destroy(s); return nullptr; };
+	if (cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking) != cudaSuccess) { err = "cudaStreamCreate failed"; return fail(); }
+	if (!upload(idx.seqb, s->seqb, err) || !upload(idx.seqf, s->seqf, err) || !upload(idx.posp, s->posp, err) ||
+	    !upload(idx.hash, s->hash, err) || !upload(idx.off_g, s->off_g, err) || !upload(idx.kmer_g, s->kmer_g, err)) return fail();
+	s->index_bytes = (idx.seqb.size() + idx.seqf.size() + idx.posp.size() + idx.hash.size() + idx.off_g.size()) * 8 + idx.kmer_g.size() * 4;
+	s->view.seqb = s->seqb; s->view.seqf = s->seqf; s->view.posp = s->posp; s->view.hash = s->hash; s->view.off_g = s->off_g;
+	s->view.kmer_g = s->kmer_g; s->view.n_seqf = idx.seqf.size();
+	return s;
+}
+
+void seed_service_destroy(SeedService *s)
+{
+	if (!s) return;
+	cudaSetDevice(s->device);
+	for (void *p : {(void*)s->seqb, (void*)s->seqf, (void*)s->posp, (void*)s->hash, (void*)s->off_g, (void*)s->kmer_g}) if (p) cudaFree(p);
+	if (s->stream) cudaStreamDestroy(s->stream);
+	delete s;
+}
+
+bool seed_service_run(SeedService *s, SeedBatch &b, std::string &err)
+{
+	const int n = (int)b.jobs.size();
+	b.mem_off.assign((size_t)n + 1, 0);
+	b.mems.clear();
+	if (n == 0) return true;
+	SCU(cudaSetDevice(s->device));
+	cudaStream_t st = s->stream;
+	if (!s->bits.reserve(b.bits.size() * 8 + 8, err) || !s->list.reserve(b.seed_list.size() + 8, err) ||
+	    !s->jobs.reserve((size_t)n * sizeof(SeedJob), err) || !s->count.reserve(((size_t)n + 1) * 4, err) ||
+	    !s->off.reserve(((size_t)n + 1) * 4, err)) return false;
+	SCU(cudaMemcpyAsync(s->bits.p, b.bits.data(), b.bits.size() * 8, cudaMemcpyHostToDevice, st));
+	if (!b.seed_list.empty()) SCU(cudaMemcpyAsync(s->list.p, b.seed_list.data(), b.seed_list.size(), cudaMemcpyHostToDevice, st));
+	SCU(cudaMemcpyAsync(s->jobs.p, b.jobs.data(), (size_t)n * sizeof(SeedJob), cudaMemcpyHostToDevice, st));
+	SCU(cudaMemsetAsync(s->count.p, 0, ((size_t)n + 1) * 4, st));
+	const int threads = 128, blocks = (n + threads - 1) / threads;
+	seed_count_kernel<<<blocks, threads, 0, st>>>(s->view, (const uint64_t*)s->bits.p, (const uint8_t*)s->list.p, (const SeedJob*)s->jobs.p, n,
+	                                              (uint32_t*)s->count.p);
+	SCU(cudaGetLastError());
+	size_t tmp_bytes = 0;
+	SCU(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, (const uint32_t*)s->count.p, (uint32_t*)s->off.p, n + 1, st));
+	if (!s->tmp.reserve(tmp_bytes, err)) return false;
+	SCU(cub::DeviceScan::ExclusiveSum(s->tmp.p, tmp_bytes, (const uint32_t*)s->count.p, (uint32_t*)s->off.p, n + 1, st));
+	SCU(cudaMemcpyAsync(b.mem_off.data(), s->off.p, ((size_t)n + 1) * 4, cudaMemcpyDeviceToHost, st));
+	SCU(cudaStreamSynchronize(st));
+	const size_t total = b.mem_off[n];
+	b.mems.resize(total);
+	if (total == 0) return true;
+	if (!s->mems.reserve(total * sizeof(Mem), err)) return false;
+	seed_fill_kernel<<<blocks, threads, 0, st>>>(s->view, (const uint64_t*)s->bits.p, (const uint8_t*)s->list.p, (const SeedJob*)s->jobs.p, n,
+	                                             (const uint32_t*)s->off.p, (Mem*)s->mems.p);
+	SCU(cudaGetLastError());
+	SCU(cudaMemcpyAsync(b.mems.data(), s->mems.p, total * sizeof(Mem), cudaMemcpyDeviceToHost, st));
+	SCU(cudaStreamSynchronize(st));
+	return true;
+}
+
+} // namespace pansvr

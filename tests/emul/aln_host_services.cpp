@@ -1,0 +1,75 @@
+// aln_host_services.cpp -- TEST INFRASTRUCTURE ONLY.
+// Host stand-ins for the two device services of the aln pipeline, so that the host-side logic of
+// pansvr_b200/csrc/aln/pipeline.cpp (stages A, C, D, F) can be checked against the reference's SAM on a machine
+// without a GPU: seeding steps seed_core.cuh on the host, ksw calls the oracle (oracle/libksw_oracle.so).
+// The product library links seed_gpu.cu and ksw_batch.cu instead; nothing here is ever part of it.
+#include <dlfcn.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <string>
+
+#include "../../include/pansvr_b200.h"
+#include "../../pansvr_b200/csrc/aln/pipeline.hpp"
+
+namespace pansvr {
+
+struct SeedService { IndexView view; };
+
+SeedService *seed_service_create(const DebgaIndex &idx, int, std::string &)
+{
+	SeedService *s = new SeedService();
+	s->view.seqb = idx.seqb.data(); s->view.seqf = idx.seqf.data(); s->view.posp = idx.posp.data(); s->view.hash = idx.hash.data();
+	s->view.off_g = idx.off_g.data(); s->view.kmer_g = idx.kmer_g.data(); s->view.n_seqf = idx.seqf.size();
+	return s;
+}
+void seed_service_destroy(SeedService *s) { delete s; }
+bool seed_service_run(SeedService *s, SeedBatch &b, std::string &)
+{
+	const size_t n = b.jobs.size();
+	b.mem_off.assign(n + 1, 0);
+	b.mems.clear();
+	std::vector<Mem> tmp(1024);
+	for (size_t i = 0; i < n; ++i) {
+		const SeedJob &j = b.jobs[i];
+		int c = seed_read_strand(s->view, b.bits.data() + j.bits_off, j.read_len, j.is_str != 0, b.seed_list.data() + j.list_off, tmp.data(), (int)tmp.size());
+		if (c > (int)tmp.size()) { tmp.resize(c); c = seed_read_strand(s->view, b.bits.data() + j.bits_off, j.read_len, j.is_str != 0, b.seed_list.data() + j.list_off, tmp.data(), c); }
+		b.mems.insert(b.mems.end(), tmp.begin(), tmp.begin() + c);
+		b.mem_off[i + 1] = (uint32_t)b.mems.size();
+	}
+	return true;
+}
+
+} // namespace pansvr
+
+// ---- ksw through the oracle
+typedef double (*batch_fn)(const char*, const char*, int, const uint8_t*, const int64_t*, const int32_t*, const uint8_t*, const int64_t*,
+                           const int32_t*, int, const int8_t*, int, int, int, int, int, int, int, int, int, int32_t*, uint32_t*, int);
+typedef int64_t (*cells_fn)(int, int, int);
+static batch_fn g_batch = nullptr;
+static cells_fn g_cells = nullptr;
+static std::string g_err;
+static bool load_oracle()
+{
+	if (g_batch) return true;
+	const char *p = getenv("PANSVR_ORACLE_SO");
+	void *h = dlopen(p ? p : "oracle/libksw_oracle.so", RTLD_NOW | RTLD_LOCAL);
+	if (!h) { g_err = dlerror(); return false; }
+	g_batch = (batch_fn)dlsym(h, "ksw_batch_run");
+	g_cells = (cells_fn)dlsym(h, "ksw_extd2_oracle_cells");
+	return g_batch && g_cells;
+}
+extern "C" {
+const char *pansvr_last_error(void) { return g_err.c_str(); }
+int pansvr_ksw_create(int, pansvr_ksw_ctx **out) { *out = (pansvr_ksw_ctx*)1; return load_oracle() ? 0 : PANSVR_E_CUDA; }
+void pansvr_ksw_destroy(pansvr_ksw_ctx*) {}
+int64_t pansvr_ksw_band_cells(int32_t q, int32_t t, int32_t w) { return load_oracle() ? g_cells(q, t, w) : 0; }
+int pansvr_ksw_extd2_batch(pansvr_ksw_ctx*, int64_t n, const uint8_t *qseq, int64_t, const int64_t *qoff, const int32_t *qlen, const uint8_t *tseq,
+                           int64_t, const int64_t *toff, const int32_t *tlen, const pansvr_ksw_params_t *p, int32_t *res, uint32_t *cig, int32_t cap)
+{
+	if (!load_oracle()) return PANSVR_E_CUDA;
+	const double s = g_batch("", "", (int)n, qseq, qoff, qlen, tseq, toff, tlen, p->m, p->mat, p->gapo, p->gape, p->gapo2, p->gape2, p->w, p->zdrop,
+	                         p->end_bonus, p->flag, 4, res, cig, cap);
+	return s < 0 ? PANSVR_E_CUDA : 0;
+}
+}
