@@ -161,6 +161,7 @@ int  pansvr_aln_create(const char *index_dir, const char *header_sam, const pans
 void pansvr_aln_destroy(pansvr_aln_ctx *ctx);
 /* Header text the reference writes in front of its output (the original header, verbatim). */
 const char *pansvr_aln_header_text(const pansvr_aln_ctx *ctx);
+const char *pansvr_aln_last_error(void);
 /* One block: `fastq` holds interleaved pairs in the wire format of `fc_signal` (4-line FASTQ, alignment of the original
  * BAM in the comment).  *sam / *ori receive malloc'ed, NUL-terminated SAM body text (records only) of the main output
  * and of the `-p` output; free with pansvr_free.  The rand() replay state carries over from block to block. */

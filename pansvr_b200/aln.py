@@ -1,0 +1,88 @@
+"""Host-side mirror of the `panSVR fc_aln` entry over the C ABI (include/pansvr_b200.h).
+
+`AlnContext(index_dir, header_sam)` loads the deBGA index of the SV anchor reference into HBM;
+`align_fastq(text)` realigns one block of interleaved signal read pairs and returns the SAM body text of the
+main output and of the `-p` output, byte-identical to `panSVR fc_aln -t 1 -S` (deCOY_CLASSIFY_MAIN::init_run,
+src/PanSVgenerateVCF/read_realignment.cpp:26).  `fc_aln_main(argv)` is the reference's command line.
+No CPU fallback: without the CUDA library and a B200 these raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+from .ksw import load_library
+
+
+class AlnOptionsC(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("match", "mismatch", "gap_open", "gap_ex", "gap_open2", "gap_ex2", "zdrop", "band_width",
+                                         "not_ori", "max_use_read")]
+
+
+class AlnStatsC(C.Structure):
+    _fields_ = [("reads", C.c_int64), ("mems", C.c_int64), ("ksw_tasks", C.c_int64), ("ksw_cells", C.c_int64),
+                ("deferred_pairs", C.c_int64), ("stage_seconds", C.c_double * 6)]
+
+
+def _bind(lib):
+    lib.pansvr_aln_create.argtypes = [C.c_char_p, C.c_char_p, C.POINTER(AlnOptionsC), C.c_int, C.POINTER(C.c_void_p)]
+    lib.pansvr_aln_destroy.argtypes = [C.c_void_p]
+    lib.pansvr_aln_header_text.restype = C.c_char_p
+    lib.pansvr_aln_header_text.argtypes = [C.c_void_p]
+    lib.pansvr_aln_last_error.restype = C.c_char_p
+    lib.pansvr_aln_block.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t),
+                                     C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
+    lib.pansvr_aln_last_stats.argtypes = [C.c_void_p, C.POINTER(AlnStatsC)]
+    lib.pansvr_free.argtypes = [C.c_void_p]
+    lib.pansvr_fc_aln_main.argtypes = [C.c_int, C.POINTER(C.c_char_p)]
+    return lib
+
+
+class AlnContext:
+    def __init__(self, index_dir: str, header_sam: str, device: int = 0, lib=None, **options):
+        self.lib = _bind(lib or load_library())
+        o = AlnOptionsC(**options)
+        h = C.c_void_p()
+        rc = self.lib.pansvr_aln_create(index_dir.encode(), header_sam.encode(), C.byref(o), device, C.byref(h))
+        if rc != 0:
+            raise RuntimeError(f"pansvr_aln_create failed ({rc}): {self.lib.pansvr_aln_last_error().decode()}")
+        self.h = h
+
+    def header_text(self) -> str:
+        return self.lib.pansvr_aln_header_text(self.h).decode()
+
+    def align_fastq(self, fastq: bytes):
+        s, o = C.c_void_p(), C.c_void_p()
+        sl, ol = C.c_size_t(), C.c_size_t()
+        rc = self.lib.pansvr_aln_block(self.h, fastq, len(fastq), C.byref(s), C.byref(sl), C.byref(o), C.byref(ol))
+        if rc != 0:
+            raise RuntimeError(f"pansvr_aln_block failed ({rc}): {self.lib.pansvr_aln_last_error().decode()}")
+        try:
+            return C.string_at(s, sl.value), C.string_at(o, ol.value)
+        finally:
+            self.lib.pansvr_free(s); self.lib.pansvr_free(o)
+
+    def stats(self) -> dict:
+        st = AlnStatsC()
+        self.lib.pansvr_aln_last_stats(self.h, C.byref(st))
+        d = {k: getattr(st, k) for k in ("reads", "mems", "ksw_tasks", "ksw_cells", "deferred_pairs")}
+        d["stage_seconds"] = list(st.stage_seconds)
+        return d
+
+    def close(self):
+        if self.h:
+            self.lib.pansvr_aln_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def fc_aln_main(argv, lib=None) -> int:
+    """`panSVR fc_aln` command line: fc_aln_main(["-t", "1", "-S", "-o", out, "-p", ori, index_dir, reads_fq, header_sam])."""
+    lib = _bind(lib or load_library())
+    args = [b"fc_aln"] + [a.encode() if isinstance(a, str) else a for a in argv]
+    arr = (C.c_char_p * (len(args) + 1))(*args, None)
+    return lib.pansvr_fc_aln_main(len(args), arr)

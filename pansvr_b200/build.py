@@ -9,7 +9,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libpansvr_b200.so")
-SOURCES = ["ksw_batch.cu"]
+SOURCES = ["ksw_batch.cu", "aln/seed_gpu.cu", "aln/pipeline.cpp", "aln/index.cpp", "aln/aln_capi.cpp"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 
@@ -25,14 +25,14 @@ def stale() -> bool:
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, "..", "include", "pansvr_b200.h")]
+    deps = [os.path.join(r, f) for r, _, fs in os.walk(CSRC) for f in fs] + [os.path.join(HERE, "..", "include", "pansvr_b200.h")]
     return any(os.path.getmtime(d) > t for d in deps if os.path.isfile(d))
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not stale():
         return LIB
-    cmd = [nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
+    cmd = [nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES] + ["-lz"]
     subprocess.check_call(cmd)
     return LIB
 

@@ -1,0 +1,56 @@
+"""Helpers of the aln (pipeline-level) tests: seeded demo data sets and the reference's SAM for them."""
+import gzip
+import os
+import shutil
+import tempfile
+
+import pytest
+
+from pansvr_b200 import synth_pipeline as sp
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+DATASETS = {
+    # name: make_demo kwargs (config 1; config-3-like shared flanks; reads with N)
+    "demo": dict(),
+    "multi_allele": dict(seed=21, genome_len=300_000, n_sv=40, alleles_per_locus=3, pairs_per_sv=30),
+    "n_bases": dict(seed=22, n_sv=20, pairs_per_sv=30, n_frac=0.004),
+}
+
+
+def need_ref_tools():
+    if not sp.have_reference_tools():
+        pytest.skip("oracle/_ref/panSVR and deBGA not built (oracle/build_ref_pipeline.sh)")
+
+
+class Demo:
+    """A data set on disk plus the reference's output for it (run once per session)."""
+
+    def __init__(self, name):
+        self.name = name
+        self.wd = tempfile.mkdtemp(prefix=f"pansvr_{name}_")
+        self.data = sp.make_demo(self.wd, **DATASETS[name])
+        self.ref_sam = os.path.join(self.wd, "ref_out.sam")
+        self.ref_ori = os.path.join(self.wd, "ref_ori.sam")
+        sp.run_reference_aln(self.data, self.ref_sam, self.ref_ori, threads=1)
+
+    def cleanup(self):
+        shutil.rmtree(self.wd, ignore_errors=True)
+
+
+def read(path):
+    with open(path, "rb") as f:
+        return f.read()
+
+
+def golden(name):
+    with gzip.open(os.path.join(GOLDEN_DIR, name), "rb") as f:
+        return f.read()
+
+
+def first_diff(a: bytes, b: bytes):
+    la, lb = a.split(b"\n"), b.split(b"\n")
+    for i, (x, y) in enumerate(zip(la, lb)):
+        if x != y:
+            return i, x[:300], y[:300]
+    return (min(len(la), len(lb)), b"<eof>", b"<eof>") if len(la) != len(lb) else None
