@@ -146,6 +146,7 @@ typedef struct {                /* MAP_PARA, read_realignment.hpp:43-128; 0 in e
 	int32_t match, mismatch, gap_open, gap_ex, gap_open2, gap_ex2, zdrop, band_width;
 	int32_t not_ori;            /* -Q */
 	int32_t max_use_read;       /* -R */
+	int32_t threads;            /* -t: host helper threads of the parallel stages; 0 = all cores (max 32).  The output is that of `-t 1`. */
 } pansvr_aln_options_t;
 
 typedef struct {

@@ -15,7 +15,7 @@ from .ksw import load_library
 
 class AlnOptionsC(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ("match", "mismatch", "gap_open", "gap_ex", "gap_open2", "gap_ex2", "zdrop", "band_width",
-                                         "not_ori", "max_use_read")]
+                                         "not_ori", "max_use_read", "threads")]
 
 
 class AlnStatsC(C.Structure):

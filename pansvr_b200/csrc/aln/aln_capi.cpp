@@ -4,7 +4,9 @@
 #include <stdlib.h>
 #include <string.h>
 #include <zlib.h>
+#include <algorithm>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../../include/pansvr_b200.h"
@@ -56,6 +58,7 @@ void parse_fastq(const char *p, size_t n, std::vector<FastqRec> &out)
 AlnOptions from_c(const pansvr_aln_options_t *o)
 {
 	AlnOptions a;
+	a.threads = 0;
 	if (!o) return a;
 	if (o->match) a.match = o->match;
 	if (o->mismatch) a.mismatch = o->mismatch;
@@ -67,6 +70,7 @@ AlnOptions from_c(const pansvr_aln_options_t *o)
 	if (o->band_width) a.bw = o->band_width;
 	a.not_ori = o->not_ori != 0;
 	if (o->max_use_read > 0) a.max_use_read = o->max_use_read;
+	a.threads = o->threads;
 	return a;
 }
 
@@ -90,6 +94,7 @@ int pansvr_aln_create(const char *index_dir, const char *header_sam, const pansv
 	*out = nullptr;
 	pansvr_aln_ctx *c = new pansvr_aln_ctx();
 	c->opt = from_c(opt);
+	if (c->opt.threads <= 0) c->opt.threads = (int)std::min(32u, std::max(1u, std::thread::hardware_concurrency()));
 	std::string err;
 	if (!c->idx.load(index_dir, header_sam, err)) { g_aln_err = err; delete c; return PANSVR_E_ARG; }
 	if (pansvr_ksw_create(device, &c->ksw) != 0) { g_aln_err = pansvr_last_error(); delete c; return PANSVR_E_CUDA; }
@@ -157,7 +162,7 @@ int pansvr_fc_aln_main(int argc, char **argv)
 	bool f_given = false;
 	while ((ch = getopt_long(argc, argv, "t:O:P:E:F:M:m:z:w:o:p:QSR:d:", lo, 0)) != -1) {
 		switch (ch) {
-		case 't': threads = atoi(optarg); break;
+		case 't': threads = atoi(optarg); o.threads = threads; break;
 		case 'O': o.gap_open = atoi(optarg); break;
 		case 'P': o.gap_open2 = atoi(optarg); break;
 		case 'E': o.gap_ex = atoi(optarg); break;
@@ -175,7 +180,8 @@ int pansvr_fc_aln_main(int argc, char **argv)
 		default: return 1;
 		}
 	}
-	(void)f_given; (void)threads;                             // -t: host helper threads; the output is that of `-t 1`
+	(void)f_given;                                            // -t: host helper threads; the output is that of `-t 1`
+	if (o.threads <= 0) o.threads = threads;
 	if (argc - optind < 3) {
 		fprintf(stderr, "Usage: fc_aln [Options] <IndexDir> <ReadFiles.fq|-> <ori_header.sam>\n");
 		return 1;

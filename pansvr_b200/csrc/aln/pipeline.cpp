@@ -5,7 +5,9 @@
 #include <stdlib.h>
 #include <string.h>
 #include <algorithm>
+#include <atomic>
 #include <chrono>
+#include <thread>
 
 #include "../../../include/pansvr_b200.h"
 
@@ -20,6 +22,20 @@ enum { POS_N_MAX = 500, POS_N_MAX_LEVEL2 = 8000, RANDOM_NUM = 500, WAITING_LEN =
 enum { MIN_STR_REPEAT_COUNT = 4, MIN_STR_DETECT_LEN = 15 };
 const uint32_t U32MAX = 0xffffffffu;
 const int I32MAX = 0x7fffffff;
+
+// static-chunk parallel loop over [0,n): fn(begin, end, thread_index)
+template <class F> void parallel_chunks(size_t n, int threads, F fn)
+{
+	if (threads <= 1 || n < 256) { fn((size_t)0, n, 0); return; }
+	std::vector<std::thread> th;
+	const size_t per = (n + threads - 1) / threads;
+	for (int t = 0; t < threads; ++t) {
+		const size_t b = std::min(n, per * t), e = std::min(n, per * (t + 1));
+		if (b >= e) break;
+		th.emplace_back([=]() { fn(b, e, t); });
+	}
+	for (std::thread &x : th) x.join();
+}
 
 double now() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
@@ -66,8 +82,8 @@ bool cig_try_merge(CigarPath &a, const CigarPath &b)            // CIGAR_PATH::t
 	return false;
 }
 
-struct UniSeed { uint32_t read_begin, read_end, seed_id, ref_begin, ref_end, cov; };   // UNI_SEED, graph.hpp:42-49
 struct VertexU { uint64_t uid; uint32_t read_pos, uni_pos_off, length1, length2, pos_n, cov; };
+struct UniSeed { uint32_t read_begin, read_end, seed_id, ref_begin, ref_end, cov; };   // UNI_SEED, graph.hpp:42-49
 struct PathNode { float dist; int32_t pre_node; uint8_t used; };
 struct Edge { uint32_t to, from; int weight; float penalty; };
 
@@ -143,6 +159,9 @@ struct ReadState {
 	std::vector<uint8_t> bin[2];
 	bool is_str = false;
 	std::vector<uint8_t> seed_list[2];
+	std::vector<uint64_t> bits[2];             // 32 bases per word, one spare zero word
+	bool batched = false, needs_rand = false;  // needs_rand: a unipath with > 500 positions draws from random_r (expand_seed)
+	std::vector<VertexU> vu[2];
 	int job[2] = {-1, -1};
 	Graph g[2];
 	std::map<uint64_t, NodeAln> node_aln;      // key = strand << 32 | node
@@ -833,69 +852,103 @@ bool AlnPipeline::align_block(const std::vector<FastqRec> &recs, std::vector<Pai
 		opt.stat_set = true;
 	}
 
-	// ---- stage A
+	// ---- stage A (parallel over reads; reads of a pair with an 'N' are left for the replay, see below)
+	const int T = std::max(1, opt.threads);
 	std::vector<ReadState> rs(n_reads);
-	SeedBatch sb;
-	for (size_t i = 0; i < n_reads; ++i) {
-		ReadState &r = rs[i];
-		r.rec = &recs[i];
-		r.seq = recs[i].seq; r.qual = recs[i].qual; r.comment = recs[i].comment;
-		r.read_l = (int)r.seq.size();
-		I.parse_ori(r);
-		if (r.ori.chr > 24) r.ori_unmapped = true;                        // RR:413
-		r.skip = !r.ori_unmapped && r.ori.align_score == (uint32_t)(r.read_l * opt.match);   // RR:414
-		r.has_n = r.seq.find('N') != std::string::npos;
-	}
-	// Reads with 'N' draw their replacement bases from rand() at their turn in the replay; a pair with such a read
-	// is aligned synchronously in stage F.  Everything else is batched.
-	auto stage_AC_prepare = [&](size_t i, SeedBatch &sb) {                    // encode + census + job registration
-		ReadState &r = rs[i];
+	parallel_chunks(n_reads, T, [&](size_t b, size_t e, int) {
+		for (size_t i = b; i < e; ++i) {
+			ReadState &r = rs[i];
+			r.rec = &recs[i];
+			r.seq = recs[i].seq; r.qual = recs[i].qual; r.comment = recs[i].comment;
+			r.read_l = (int)r.seq.size();
+			I.parse_ori(r);
+			if (r.ori.chr > 24) r.ori_unmapped = true;                    // RR:413
+			r.skip = !r.ori_unmapped && r.ori.align_score == (uint32_t)(r.read_l * opt.match);   // RR:414
+			r.has_n = r.seq.find('N') != std::string::npos;
+		}
+	});
+	auto prepare_read = [&](ReadState &r) {                                   // encode + pack + STR census
 		I.encode(r);
 		const size_t words = (size_t)(r.read_l >> 5) + 2;
+		for (int s = 0; s < 2; ++s) { r.bits[s].assign(words, 0); Impl::pack64(r.bin[s], r.bits[s], 0); }
+		I.str_census(r, r.bits[0].data());
+	};
+	auto register_jobs = [&](ReadState &r, SeedBatch &sb) {
 		for (int s = 0; s < 2; ++s) {
 			SeedJob j;
-			j.bits_off = (uint32_t)sb.bits.size(); j.read_len = (uint32_t)r.read_l; j.is_str = 0; j.list_off = 0;
-			sb.bits.resize(sb.bits.size() + words, 0);
-			Impl::pack64(r.bin[s], sb.bits, j.bits_off);
-			if (s == 0) I.str_census(r, sb.bits.data() + j.bits_off);
-			if (r.is_str) {
-				j.is_str = 1; j.list_off = (uint32_t)sb.seed_list.size();
-				sb.seed_list.insert(sb.seed_list.end(), r.seed_list[s].begin(), r.seed_list[s].end());
-			}
+			j.bits_off = (uint32_t)sb.bits.size(); j.read_len = (uint32_t)r.read_l; j.is_str = r.is_str ? 1 : 0; j.list_off = 0;
+			sb.bits.insert(sb.bits.end(), r.bits[s].begin(), r.bits[s].end());
+			if (r.is_str) { j.list_off = (uint32_t)sb.seed_list.size(); sb.seed_list.insert(sb.seed_list.end(), r.seed_list[s].begin(), r.seed_list[s].end()); }
 			r.job[s] = (int)sb.jobs.size();
 			sb.jobs.push_back(j);
 		}
 	};
-	auto stage_C = [&](size_t i, const SeedBatch &b) {                       // merge, expand, chain
-		ReadState &r = rs[i];
+	auto merge_read = [&](ReadState &r, const SeedBatch &b) {                // stage C, part 1: no random numbers
+		r.needs_rand = false;
 		for (int s = 0; s < 2; ++s) {
 			const int j = r.job[s];
 			std::vector<Mem> mems(b.mems.begin() + b.mem_off[j], b.mems.begin() + b.mem_off[j + 1]);
-			std::vector<VertexU> vu;
-			I.merge_mems(mems, vu);
-			Graph &g = r.g[s];
-			g.v.clear(); g.is_str = r.is_str;
-			I.expand(vu, g.v, rand_r_[i & 1]);
-			I.chain(g);
-			stats.mems += mems.size();
+			I.merge_mems(mems, r.vu[s]);
+			for (const VertexU &u : r.vu[s]) if (u.pos_n > POS_N_MAX) r.needs_rand = true;
 		}
 	};
-	for (size_t i = 0; i < n_reads; ++i) {
-		ReadState &r = rs[i];
-		const bool pair_has_n = rs[i & ~(size_t)1].has_n || rs[i | 1].has_n;
-		if (r.skip || pair_has_n || r.read_l < LEN_KMER) continue;
-		stage_AC_prepare(i, sb);
-	}
+	auto chain_read = [&](ReadState &r, size_t i) {                          // stage C, part 2: expand + chain
+		for (int s = 0; s < 2; ++s) {
+			Graph &g = r.g[s];
+			g.v.clear(); g.is_str = r.is_str;
+			I.expand(r.vu[s], g.v, rand_r_[i & 1]);
+			I.chain(g);
+		}
+	};
+	parallel_chunks(n_reads, T, [&](size_t b, size_t e, int) {
+		for (size_t i = b; i < e; ++i) {
+			ReadState &r = rs[i];
+			const bool pair_has_n = rs[i & ~(size_t)1].has_n || rs[i | 1].has_n;
+			r.batched = !(r.skip || pair_has_n || r.read_l < LEN_KMER);
+			if (r.batched) prepare_read(r);
+		}
+	});
+	SeedBatch sb;
+	for (size_t i = 0; i < n_reads; ++i) if (rs[i].batched) register_jobs(rs[i], sb);
 	stats.t_stage[0] += now() - t0; t0 = now();
 	// ---- stage B
 	if (!sb.jobs.empty() && !seed_service_run(seeds_, sb, err)) return false;
+	stats.mems += sb.mems.size();
 	stats.t_stage[1] += now() - t0; t0 = now();
-	// ---- stage C (in read order: the random_r streams are per mate handler)
-	KswTaskList tasks;
-	for (size_t i = 0; i < n_reads; ++i) if (rs[i].job[0] >= 0) stage_C(i, sb);
+	// ---- stage C: reads whose expansion draws from the per-handler random_r stream go in input order, the rest in parallel
+	parallel_chunks(n_reads, T, [&](size_t b, size_t e, int) {
+		for (size_t i = b; i < e; ++i) {
+			ReadState &r = rs[i];
+			if (!r.batched) continue;
+			merge_read(r, sb);
+			if (!r.needs_rand) chain_read(r, i);
+		}
+	});
+	for (size_t i = 0; i < n_reads; ++i) if (rs[i].batched && rs[i].needs_rand) chain_read(rs[i], i);
 	stats.t_stage[2] += now() - t0; t0 = now();
-	// ---- stage D
-	for (size_t i = 0; i < n_reads; ++i) if (rs[i].job[0] >= 0) I.plan_read(rs[i], tasks);
+	// ---- stage D: per-thread task lists, concatenated afterwards
+	KswTaskList tasks;
+	{
+		std::vector<KswTaskList> part((size_t)T);
+		std::vector<size_t> lo((size_t)T, 0), hi((size_t)T, 0);
+		parallel_chunks(n_reads, T, [&](size_t b, size_t e, int t) {
+			lo[t] = b; hi[t] = e;
+			for (size_t i = b; i < e; ++i) if (rs[i].batched) I.plan_read(rs[i], part[t]);
+		});
+		for (int t = 0; t < T; ++t) {
+			const int base = (int)tasks.qlen.size();
+			const int64_t qb = (int64_t)tasks.q.size(), tb = (int64_t)tasks.t.size();
+			KswTaskList &p = part[t];
+			tasks.q.insert(tasks.q.end(), p.q.begin(), p.q.end());
+			tasks.t.insert(tasks.t.end(), p.t.begin(), p.t.end());
+			for (size_t k = 0; k < p.qlen.size(); ++k) {
+				tasks.qoff.push_back(p.qoff[k] + qb); tasks.toff.push_back(p.toff[k] + tb);
+				tasks.qlen.push_back(p.qlen[k]); tasks.tlen.push_back(p.tlen[k]);
+			}
+			if (base) for (size_t i = lo[t]; i < hi[t]; ++i)
+				for (auto &kv : rs[i].node_aln) for (Piece &pc : kv.second.pieces) if (pc.kind == 1) pc.task += base;
+		}
+	}
 	stats.t_stage[3] += now() - t0; t0 = now();
 	// ---- stage E
 	const int8_t m = (int8_t)opt.match, x = (int8_t)-opt.mismatch;
@@ -926,7 +979,8 @@ bool AlnPipeline::align_block(const std::vector<FastqRec> &recs, std::vector<Pai
 	if (!run_ksw(tasks)) return false;
 	stats.t_stage[4] += now() - t0; t0 = now();
 
-	// ---- stage F: replay in input order
+	// ---- stage F: replay in input order (everything that consumes rand()), then the SAM text
+	std::vector<Impl::PE> pes(n_pairs);
 	for (size_t pi = 0; pi < n_pairs; ++pi) {
 		ReadState *se = &rs[2 * pi];
 		if (se[0].has_n || se[1].has_n) {                                 // deferred pair: rand() position is only known now
@@ -936,9 +990,12 @@ bool AlnPipeline::align_block(const std::vector<FastqRec> &recs, std::vector<Pai
 				ReadState &r = se[k];
 				if (!r.skip && r.read_l >= LEN_KMER) {
 					SeedBatch one;
-					stage_AC_prepare(2 * pi + k, one);
+					prepare_read(r);
+					register_jobs(r, one);
 					if (!seed_service_run(seeds_, one, err)) return false;
-					stage_C(2 * pi + k, one);
+					stats.mems += one.mems.size();
+					merge_read(r, one);
+					chain_read(r, 2 * pi + k);
 					I.plan_read(r, local);
 					if (!run_ksw(local)) return false;
 				}
@@ -947,31 +1004,36 @@ bool AlnPipeline::align_block(const std::vector<FastqRec> &recs, std::vector<Pai
 		} else {
 			for (int k = 0; k < 2; ++k) I.finish_read(se[k], tasks);
 		}
-		Impl::PE pe;
-		I.pair_up(se, pe);
-		PairOutput &po = out[pi];
-		if (pe.gain) {
-			I.set_primary(se, pe);
-			for (int k = 0; k < 2; ++k) I.output_bam(se[k], po.sam[k], k == 0, pe.cur_isize);
-		}
-		if (pe.max_score <= min_filter_score_ && (int)se[0].ori.chr != -1 && (int)se[1].ori.chr != -1) {   // RR:776-797
-			bool clip[2] = {true, true};
-			for (int k = 0; k < 2; ++k) I.output_ori(se[k], po.ori[k], pe.max_score, clip[k]);
-			bool proper = pe.proper;
-			for (int k = 0; proper && k < 2; ++k) {
-				const Result *c = k == 0 ? pe.m1 : pe.m2;
-				if (!c) { proper = false; break; }
-				if (c->is_ori && clip[k]) proper = false;
-				if (proper && !c->is_ori) {
-					int ins = 0;
-					for (const CigarPath &ci : c->cigar) if (ci.type == 1) ins += ci.size;
-					if (c->cigar.empty() || ins >= 25) proper = false;
-				}
-			}
-			if (proper) { po.ori[0].clear(); po.ori[1].clear(); }
-		}
+		I.pair_up(se, pes[pi]);
+		if (pes[pi].gain) I.set_primary(se, pes[pi]);
 		stats.reads += 2;
 	}
+	// ---- SAM text of every pair (no random numbers involved any more: parallel)
+	parallel_chunks(n_pairs, T, [&](size_t pb, size_t pe_, int) {
+		for (size_t pi = pb; pi < pe_; ++pi) {
+			ReadState *se = &rs[2 * pi];
+			const Impl::PE &pe = pes[pi];
+			PairOutput &po = out[pi];
+			if (pe.gain)
+				for (int k = 0; k < 2; ++k) I.output_bam(se[k], po.sam[k], k == 0, pe.cur_isize);
+			if (pe.max_score <= min_filter_score_ && (int)se[0].ori.chr != -1 && (int)se[1].ori.chr != -1) {   // RR:776-797
+				bool clip[2] = {true, true};
+				for (int k = 0; k < 2; ++k) I.output_ori(se[k], po.ori[k], pe.max_score, clip[k]);
+				bool proper = pe.proper;
+				for (int k = 0; proper && k < 2; ++k) {
+					const Result *c = k == 0 ? pe.m1 : pe.m2;
+					if (!c) { proper = false; break; }
+					if (c->is_ori && clip[k]) proper = false;
+					if (proper && !c->is_ori) {
+						int ins = 0;
+						for (const CigarPath &ci : c->cigar) if (ci.type == 1) ins += ci.size;
+						if (c->cigar.empty() || ins >= 25) proper = false;
+					}
+				}
+				if (proper) { po.ori[0].clear(); po.ori[1].clear(); }
+			}
+		}
+	});
 	stats.t_stage[5] += now() - t0;
 	return true;
 }

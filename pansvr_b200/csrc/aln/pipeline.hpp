@@ -36,6 +36,7 @@ struct AlnOptions {                   // MAP_PARA, read_realignment.hpp:43-128 (
 	int zdrop = 400, bw = 500;        // -w is parsed and ignored by the reference (RR:817-827): ksw runs with w=200
 	bool not_ori = false;             // -Q
 	int max_use_read = 0x7fffffff;
+	int threads = 1;                  // host helper threads of the parallel stages (the output does not depend on it)
 	// read statistics (STAT_ field of the first comment, RR:134-148)
 	bool stat_set = false;
 	int read_len = 150, isize_min = 100, isize_mid = 500, isize_max = 900;
