@@ -151,7 +151,8 @@ typedef struct {                /* MAP_PARA, read_realignment.hpp:43-128; 0 in e
 
 typedef struct {
 	int64_t reads, mems, ksw_tasks, ksw_cells, deferred_pairs;
-	double stage_seconds[6];    /* A encode/census, B seeding (GPU), C merge/expand/chain, D ksw planning, E ksw (GPU), F replay + SAM */
+	double stage_seconds[8];    /* A encode/census, B seeding (GPU), C merge/expand/chain, D ksw planning, E ksw (GPU), F replay + SAM text,
+	                               FASTQ parse, output assembly */
 } pansvr_aln_stats_t;
 
 typedef struct pansvr_aln_ctx pansvr_aln_ctx;

@@ -20,7 +20,7 @@ class AlnOptionsC(C.Structure):
 
 class AlnStatsC(C.Structure):
     _fields_ = [("reads", C.c_int64), ("mems", C.c_int64), ("ksw_tasks", C.c_int64), ("ksw_cells", C.c_int64),
-                ("deferred_pairs", C.c_int64), ("stage_seconds", C.c_double * 6)]
+                ("deferred_pairs", C.c_int64), ("stage_seconds", C.c_double * 8)]
 
 
 def _bind(lib):

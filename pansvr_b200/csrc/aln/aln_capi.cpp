@@ -5,6 +5,7 @@
 #include <string.h>
 #include <zlib.h>
 #include <algorithm>
+#include <chrono>
 #include <string>
 #include <thread>
 #include <vector>
@@ -26,31 +27,34 @@ struct pansvr_aln_ctx {
 
 namespace {
 
-// 4-line FASTQ records out of a memory buffer: "@name comment\nseq\n+...\nqual\n" (kseq_read, clib/utils.c:953-990)
+// 4-line FASTQ records out of a memory buffer: "@name comment\nseq\n+...\nqual\n" (kseq_read, clib/utils.c:953-990).
+// Records are views into the buffer.
 void parse_fastq(const char *p, size_t n, std::vector<FastqRec> &out)
 {
 	size_t i = 0;
-	auto line = [&](std::string &dst) -> bool {
+	auto line = [&](const char *&b, uint32_t &l) -> bool {
 		if (i >= n) return false;
-		size_t e = i;
-		while (e < n && p[e] != '\n') ++e;
-		size_t l = e;
-		if (l > i && p[l - 1] == '\r') --l;
-		dst.assign(p + i, l - i);
+		const char *nl = (const char*)memchr(p + i, '\n', n - i);
+		const size_t e = nl ? (size_t)(nl - p) : n;
+		size_t len = e - i;
+		if (len && p[i + len - 1] == '\r') --len;
+		b = p + i; l = (uint32_t)len;
 		i = e + 1;
 		return true;
 	};
-	std::string h, plus;
+	out.reserve(n / 300 + 16);
 	for (;;) {
 		FastqRec r;
-		do { if (!line(h)) return; } while (h.empty());
+		const char *h; uint32_t hl;
+		do { if (!line(h, hl)) return; } while (hl == 0);
 		if (h[0] != '@' && h[0] != '>') return;
-		size_t sp = 1;
-		while (sp < h.size() && h[sp] != ' ' && h[sp] != '\t') ++sp;
-		r.name = h.substr(1, sp - 1);
-		while (sp < h.size() && (h[sp] == ' ' || h[sp] == '\t')) ++sp;
-		r.comment = sp < h.size() ? h.substr(sp) : std::string();
-		if (!line(r.seq) || !line(plus) || !line(r.qual)) return;
+		uint32_t sp = 1;
+		while (sp < hl && h[sp] != ' ' && h[sp] != '\t') ++sp;
+		r.name = h + 1; r.name_l = sp - 1;
+		while (sp < hl && (h[sp] == ' ' || h[sp] == '\t')) ++sp;
+		r.comment = h + sp; r.comment_l = hl - sp;
+		const char *plus; uint32_t pl;
+		if (!line(r.seq, r.seq_l) || !line(plus, pl) || !line(r.qual, r.qual_l)) return;
 		out.push_back(r);
 	}
 }
@@ -72,16 +76,6 @@ AlnOptions from_c(const pansvr_aln_options_t *o)
 	if (o->max_use_read > 0) a.max_use_read = o->max_use_read;
 	a.threads = o->threads;
 	return a;
-}
-
-char *dup_out(const std::string &s, size_t *len)
-{
-	char *p = (char*)malloc(s.size() + 1);
-	if (!p) return nullptr;
-	memcpy(p, s.data(), s.size());
-	p[s.size()] = 0;
-	if (len) *len = s.size();
-	return p;
 }
 
 } // namespace
@@ -120,16 +114,50 @@ const char *pansvr_aln_last_error(void) { return g_aln_err.c_str(); }
 int pansvr_aln_block(pansvr_aln_ctx *c, const char *fastq, size_t n, char **sam, size_t *sam_bytes, char **ori, size_t *ori_bytes)
 {
 	if (!c || !fastq || !sam || !ori) return PANSVR_E_ARG;
+	const auto tick = []() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+	double t0 = tick();
 	std::vector<FastqRec> recs;
 	parse_fastq(fastq, n, recs);
+	c->pipe->stats.t_stage[6] += tick() - t0;
 	std::vector<PairOutput> outp;
 	std::string err;
 	if (!c->pipe->align_block(recs, outp, err)) { g_aln_err = err; return PANSVR_E_CUDA; }
-	std::string s, o;
-	for (const PairOutput &p : outp) for (int k = 0; k < 2; ++k) if (!p.sam[k].empty()) { s += p.sam[k]; s += '\n'; }
-	for (const PairOutput &p : outp) for (int k = 0; k < 2; ++k) if (!p.ori[k].empty()) { o += p.ori[k]; o += '\n'; }
-	*sam = dup_out(s, sam_bytes);
-	*ori = dup_out(o, ori_bytes);
+	t0 = tick();
+	// total sizes, then every pair copies its records to its own offset (parallel)
+	const size_t np = outp.size();
+	std::vector<size_t> off_s(np + 1, 0), off_o(np + 1, 0);
+	for (size_t i = 0; i < np; ++i) {
+		size_t a = 0, b = 0;
+		for (int k = 0; k < 2; ++k) { if (!outp[i].sam[k].empty()) a += outp[i].sam[k].size() + 1; if (!outp[i].ori[k].empty()) b += outp[i].ori[k].size() + 1; }
+		off_s[i + 1] = off_s[i] + a; off_o[i + 1] = off_o[i] + b;
+	}
+	char *sbuf = (char*)malloc(off_s[np] + 1), *obuf = (char*)malloc(off_o[np] + 1);
+	if (!sbuf || !obuf) { free(sbuf); free(obuf); g_aln_err = "out of memory"; return PANSVR_E_ARG; }
+	{
+		const int T = std::max(1, c->opt.threads);
+		std::vector<std::thread> th;
+		const size_t per = (np + T - 1) / T;
+		for (int t = 0; t < T; ++t) {
+			const size_t b = std::min(np, per * t), e = std::min(np, per * (t + 1));
+			if (b >= e) break;
+			th.emplace_back([&, b, e]() {
+				for (size_t i = b; i < e; ++i) {
+					char *ps = sbuf + off_s[i], *po = obuf + off_o[i];
+					for (int k = 0; k < 2; ++k) {
+						const std::string &x = outp[i].sam[k], &y = outp[i].ori[k];
+						if (!x.empty()) { memcpy(ps, x.data(), x.size()); ps += x.size(); *ps++ = '\n'; }
+						if (!y.empty()) { memcpy(po, y.data(), y.size()); po += y.size(); *po++ = '\n'; }
+					}
+				}
+			});
+		}
+		for (std::thread &x : th) x.join();
+	}
+	sbuf[off_s[np]] = 0; obuf[off_o[np]] = 0;
+	*sam = sbuf; *ori = obuf;
+	if (sam_bytes) *sam_bytes = off_s[np];
+	if (ori_bytes) *ori_bytes = off_o[np];
+	c->pipe->stats.t_stage[7] += tick() - t0;
 	return 0;
 }
 
@@ -139,7 +167,7 @@ int pansvr_aln_last_stats(const pansvr_aln_ctx *c, pansvr_aln_stats_t *out)
 	const AlnPipeline::Stats &s = c->pipe->stats;
 	out->reads = (int64_t)s.reads; out->mems = (int64_t)s.mems; out->ksw_tasks = (int64_t)s.ksw_tasks; out->ksw_cells = (int64_t)s.ksw_cells;
 	out->deferred_pairs = (int64_t)s.deferred_pairs;
-	for (int i = 0; i < 6; ++i) out->stage_seconds[i] = s.t_stage[i];
+	for (int i = 0; i < 8; ++i) out->stage_seconds[i] = s.t_stage[i];
 	return 0;
 }
 
@@ -227,9 +255,9 @@ int pansvr_fc_aln_main(int argc, char **argv)
 	fclose(fo); fclose(fp);
 	pansvr_aln_stats_t st;
 	pansvr_aln_last_stats(ctx, &st);
-	fprintf(stderr, "pansvr_b200 fc_aln: %ld reads, %ld MEMs, %ld ksw tasks; stage seconds A %.3f B %.3f C %.3f D %.3f E %.3f F %.3f\n",
+	fprintf(stderr, "pansvr_b200 fc_aln: %ld reads, %ld MEMs, %ld ksw tasks; stage seconds A %.3f B %.3f C %.3f D %.3f E %.3f F %.3f parse %.3f emit %.3f\n",
 	        (long)st.reads, (long)st.mems, (long)st.ksw_tasks, st.stage_seconds[0], st.stage_seconds[1], st.stage_seconds[2], st.stage_seconds[3],
-	        st.stage_seconds[4], st.stage_seconds[5]);
+	        st.stage_seconds[4], st.stage_seconds[5], st.stage_seconds[6], st.stage_seconds[7]);
 	pansvr_aln_destroy(ctx);
 	return ok ? 0 : 1;
 }

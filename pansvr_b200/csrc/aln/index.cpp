@@ -3,6 +3,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <algorithm>
 
 namespace pansvr {
 
@@ -19,8 +20,28 @@ bool slurp(const std::string &dir, const char *fn, std::vector<T> &out, size_t e
 	fseek(f, 0, SEEK_END);
 	const size_t bytes = (size_t)ftell(f);
 	rewind(f);
-	out.assign((bytes + extra_bytes + sizeof(T) - 1) / sizeof(T), 0);
-	const size_t got = fread(out.data(), 1, bytes, f);
+	const size_t n_el = (bytes + extra_bytes + sizeof(T) - 1) / sizeof(T);
+	out.clear();
+	out.reserve(n_el);
+	// read straight into the vector's storage in 64 MiB pieces (no zero fill of the 2 GiB bucket table first)
+	size_t got = 0;
+	{
+		const size_t full = bytes / sizeof(T);
+		std::vector<T> chunk;
+		const size_t step = ((size_t)64 << 20) / sizeof(T);
+		for (size_t done = 0; done < full;) {
+			const size_t k = std::min(step, full - done);
+			chunk.resize(k);
+			const size_t r = fread(chunk.data(), sizeof(T), k, f);
+			out.insert(out.end(), chunk.begin(), chunk.begin() + r);
+			got += r * sizeof(T);
+			done += k;
+			if (r != k) break;
+		}
+		const size_t tail = bytes - full * sizeof(T);
+		if (tail) { T last = 0; got += fread(&last, 1, tail, f); out.push_back(last); }
+	}
+	out.resize(n_el, 0);
 	fclose(f);
 	if (got != bytes) { err = "short read on " + path; return false; }
 	return true;

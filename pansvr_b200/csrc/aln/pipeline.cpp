@@ -149,7 +149,8 @@ struct NodeAln {
 // ================================================================================================ per-read state
 struct ReadState {
 	const FastqRec *rec = nullptr;
-	std::string seq, qual, comment;            // mutable copies (the reference edits its kseq_t in place)
+	std::string comment;                       // mutable copy (the reference edits its kseq_t in place)
+	std::string seq, qual;                     // filled only while the SAM text is written (output_bam reverses them in place)
 	int read_l = 0;
 	bool has_n = false, skip = false;          // skip: early-out of single_end_handler::align (RR:413-414)
 	// original alignment (parse_ori_mapping_rst)
@@ -167,7 +168,7 @@ struct ReadState {
 	std::map<uint64_t, NodeAln> node_aln;      // key = strand << 32 | node
 	// results
 	int result_num = 0;
-	Result result[2 * MAX_OUTPUT_NUMBER];
+	std::vector<Result> result;                // at most 2 * MAX_OUTPUT_NUMBER, reserved once so that pointers stay valid
 	Result *primary = nullptr, *secondary = nullptr;
 };
 
@@ -200,32 +201,41 @@ struct AlnPipeline::Impl {
 		o = Result();
 		o.is_ori = true;
 		std::string &c = r.comment;
-		std::vector<std::string> tok;
+		const char *tok[10]; size_t tok_l[10]; size_t nul_at[10];
+		int nt = 0, nn = 0;
 		size_t i = 0;
-		std::vector<size_t> nul_at;
-		while (tok.size() < 10 && i < c.size()) {                // strtok_r(.., "_"): skip separators, cut at the next one
+		while (nt < 10 && i < c.size()) {                        // strtok_r(.., "_"): skip separators, cut at the next one
 			while (i < c.size() && c[i] == '_') ++i;
 			if (i >= c.size()) break;
 			size_t j = i;
 			while (j < c.size() && c[j] != '_') ++j;
-			tok.push_back(c.substr(i, j - i));
-			if (j < c.size()) nul_at.push_back(j);
+			tok[nt] = c.data() + i; tok_l[nt] = j - i; ++nt;
+			if (j < c.size()) nul_at[nn++] = j;
 			i = j + 1;
 		}
-		while (tok.size() < 10) tok.push_back("");
-		o.chr = (uint32_t)atoi(tok[0].c_str());
-		o.ref_bg = (uint32_t)atoi(tok[1].c_str());
-		o.read_bg = (uint32_t)atoi(tok[2].c_str());
-		o.align_score = (uint32_t)atoi(tok[3].c_str());
-		o.mapq = (uint8_t)atoi(tok[4].c_str());
-		o.direction = (!tok[9].empty() && tok[9][0] == 'F') ? FORWARD : REVERSE;
-		r.ori_unmapped = tok[9].size() > 1 && tok[9][1] == 'Y';
+		auto num = [&](int k) -> int {                            // atoi of token k
+			if (k >= nt) return 0;
+			const char *p = tok[k], *e = p + tok_l[k];
+			while (p < e && (*p == ' ' || *p == '\t')) ++p;
+			bool neg = false;
+			if (p < e && (*p == '-' || *p == '+')) { neg = *p == '-'; ++p; }
+			long v = 0;
+			while (p < e && *p >= '0' && *p <= '9') v = v * 10 + (*p++ - '0');
+			return (int)(neg ? -v : v);
+		};
+		o.chr = (uint32_t)num(0);
+		o.ref_bg = (uint32_t)num(1);
+		o.read_bg = (uint32_t)num(2);
+		o.align_score = (uint32_t)num(3);
+		o.mapq = (uint8_t)num(4);
+		o.direction = (nt > 9 && tok_l[9] > 0 && tok[9][0] == 'F') ? FORWARD : REVERSE;
+		r.ori_unmapped = nt > 9 && tok_l[9] > 1 && tok[9][1] == 'Y';
 		o.cigar.clear();
 		if (o.read_bg > 0) o.cigar.push_back(cig_char('S', (int)o.read_bg));
 		o.cigar.push_back(cig_char('M', r.read_l - (int)o.read_bg));
 		o.sv = nullptr; o.has_mate = false;
 		if (o.ref_bg >= (uint32_t)I32MAX) o.ref_bg = 1;
-		for (size_t p : nul_at) if (p + 1 < c.size()) c[p] = ',';  // separators the tokenizer consumed come back as ','
+		for (int k = 0; k < nn; ++k) if (nul_at[k] + 1 < c.size()) c[nul_at[k]] = ',';  // separators the tokenizer consumed come back as ','
 	}
 
 	void encode(ReadState &r)                                    // binary_read_2_bit, read_realignment.cpp:646-654
@@ -233,7 +243,7 @@ struct AlnPipeline::Impl {
 		const int L = r.read_l;
 		r.bin[0].assign(L, 0); r.bin[1].assign(L, 0);
 		for (int i = 0; i < L; ++i) {
-			char ch = r.seq[i];
+			char ch = r.rec->seq[i];
 			if (ch == 'N') ch = "ACGT"[P.rand_.next() % 4];
 			const uint8_t c = dna5((unsigned char)ch);
 			r.bin[0][i] = c;
@@ -250,22 +260,26 @@ struct AlnPipeline::Impl {
 	void str_census(ReadState &r, const uint64_t *bits)
 	{
 		const uint32_t L = (uint32_t)r.read_l, kn = L - LEN_KMER + 1;
-		std::vector<uint64_t> km(kn), sorted;
-		for (uint32_t i = 0; i < kn; ++i) km[i] = get_kmer(i, bits);
-		sorted = km;
-		std::sort(sorted.begin(), sorted.end());
-		const size_t distinct = (size_t)(std::unique(sorted.begin(), sorted.end()) - sorted.begin());
-		r.is_str = distinct < (size_t)kn - MIN_STR_DETECT_LEN;
+		// multiplicity of every 20-mer (the reference's std::map<kmer,count>): open addressing, 4x slots
+		uint32_t cap = 64;
+		while (cap < 4 * kn) cap <<= 1;
+		std::vector<uint64_t> keys(cap);
+		std::vector<uint16_t> cnt(cap, 0), slot_of(kn);
+		uint32_t distinct = 0;
+		for (uint32_t i = 0; i < kn; ++i) {
+			const uint64_t k = get_kmer(i, bits);
+			uint32_t h = (uint32_t)((k * 0x9E3779B97F4A7C15ull) >> 40) & (cap - 1);
+			while (cnt[h] != 0 && keys[h] != k) h = (h + 1) & (cap - 1);
+			if (cnt[h] == 0) { keys[h] = k; ++distinct; }
+			++cnt[h];
+			slot_of[i] = (uint16_t)h;
+		}
+		r.is_str = (size_t)distinct < (size_t)kn - MIN_STR_DETECT_LEN;
 		r.seed_list[0].clear(); r.seed_list[1].clear();
 		if (!r.is_str) return;
-		std::vector<uint64_t> all = km;
-		std::sort(all.begin(), all.end());
 		std::vector<uint8_t> &sl = r.seed_list[0];
 		sl.assign(L, 0);                                         // repeat_seed_info is per handler and larger; only [0,kn) is read
-		for (uint32_t i = 0; i < kn; ++i) {
-			const int cnt = (int)(std::upper_bound(all.begin(), all.end(), km[i]) - std::lower_bound(all.begin(), all.end(), km[i]));
-			sl[i] = cnt >= MIN_STR_REPEAT_COUNT ? 0 : 1;
-		}
+		for (uint32_t i = 0; i < kn; ++i) sl[i] = cnt[slot_of[i]] >= MIN_STR_REPEAT_COUNT ? 0 : 1;
 		int bg = 0, ed = 0;
 		for (uint32_t i = 0; i < SEED_STEP; ++i) {
 			bg += sl[i] == 0; ed += sl[L - LEN_KMER - i] == 0;
@@ -585,8 +599,8 @@ struct AlnPipeline::Impl {
 		for (int i = 0; i < n; ++i) p[i] = res + i;
 		qsort(p.data(), n, sizeof(Result*), cmp);
 		std::vector<Result> tmp(n);
-		for (int i = 0; i < n; ++i) tmp[i] = *p[i];
-		for (int i = 0; i < n; ++i) res[i] = tmp[i];
+		for (int i = 0; i < n; ++i) tmp[i] = std::move(*p[i]);
+		for (int i = 0; i < n; ++i) res[i] = std::move(tmp[i]);
 	}
 
 	bool reverse_cigar(Result &c, const std::vector<CigarPath> &tmp, int read_len)   // reverseGIGAR, read_realignment.hpp:277-301
@@ -606,20 +620,23 @@ struct AlnPipeline::Impl {
 	void finish_read(ReadState &r, const KswTaskList &tasks)
 	{
 		r.result_num = 0; r.primary = r.secondary = nullptr;
+		r.result.clear();
 		if (r.skip) return;
+		r.result.reserve(2 * MAX_OUTPUT_NUMBER);
 		uint32_t max_chain = 0;
 		for (int s = 0; s < 2; ++s) {
 			const int direction = s == 0 ? FORWARD : REVERSE;
 			for (int i = 0; i < MAX_OUTPUT_NUMBER; ++i) {
-				Result &slot = r.result[r.result_num];
+				Result slot;
 				if (!sort_output(r, s, slot, direction)) break;
 				const uint32_t c = slot.chain_score;
 				max_chain = std::max(c, max_chain);
 				if (c + MAX_CHAIN_SCORE_DIFF < max_chain || c < MIN_CHAIN_SCORE2) break;
+				r.result.push_back(slot);
 				++r.result_num;
 			}
 		}
-		sort_results(r.result, r.result_num, cmp_chain);
+		sort_results(r.result.data(), r.result_num, cmp_chain);
 		if (r.result_num == 0 || max_chain < MIN_CHAIN_SCORE) return;
 		for (int k = 0; k < r.result_num; ++k) {
 			Result &c = r.result[k];
@@ -644,9 +661,9 @@ struct AlnPipeline::Impl {
 			}
 			c.ref_bg -= (uint32_t)na.read_begin_alignment;
 			c.align_score = (uint32_t)std::max(score, 0);
-			if (!reverse_cigar(c, tmp, r.read_l)) fprintf(stderr, "ERROR cigar: read_len: %d %s\n", r.read_l, r.seq.c_str());
+			if (!reverse_cigar(c, tmp, r.read_l)) fprintf(stderr, "ERROR cigar: read_len: %d %.*s\n", r.read_l, r.read_l, r.rec->seq);
 		}
-		sort_results(r.result, r.result_num, cmp_align);
+		sort_results(r.result.data(), r.result_num, cmp_align);
 		if (r.result[0].align_score < (uint32_t)MIN_ALN_SCORE) { r.result_num = 0; return; }
 		for (int i = 0; i < r.result_num; ++i) {
 			Result &c = r.result[i];
@@ -742,7 +759,7 @@ struct AlnPipeline::Impl {
 		if (P.opt.not_ori && p->is_ori) return;
 		const int dir = p->direction;
 		const uint8_t flag = (uint8_t)((first ? 0x40 : 0) + (dir == REVERSE ? 0x10 : 0) + (p->has_mate ? 0 : 0x08));
-		out += r.rec->name; out += '\t'; append_int(out, flag); out += '\t';
+		out.append(r.rec->name, r.rec->name_l); out += '\t'; append_int(out, flag); out += '\t';
 		out += target_name(p->chr); out += '\t'; append_int(out, (int)p->ref_bg); out += '\t'; append_int(out, p->mapq); out += '\t';
 		if (p->cigar.empty()) out += '*';
 		for (const CigarPath &c : p->cigar) { append_int(out, c.size); out += "MIDNSHP=XB"[c.type]; }
@@ -798,7 +815,7 @@ struct AlnPipeline::Impl {
 		if (tag_len > 0) tags.resize(tag_len - 1);
 		// the reference cuts the comment in place at the end of the CIGAR and edits the tags
 		c[cig_e < c.size() ? cig_e : c.size() - 1] = '\0';
-		out += r.rec->name; out += '\t'; append_int(out, flag); out += '\t'; out += target_name(r.ori.chr); out += '\t';
+		out.append(r.rec->name, r.rec->name_l); out += '\t'; append_int(out, flag); out += '\t'; out += target_name(r.ori.chr); out += '\t';
 		append_int(out, (long)(r.ori.ref_bg + 1)); out += '\t'; append_int(out, qual); out += '\t';
 		out += cigar.empty() ? std::string("*") : cigar; out += '\t';
 		out += ((uint32_t)mchr == r.ori.chr) ? std::string("=") : target_name((uint32_t)mchr);
@@ -844,7 +861,8 @@ bool AlnPipeline::align_block(const std::vector<FastqRec> &recs, std::vector<Pai
 
 	// read statistics from the first comment (load_reads, RR:134-148)
 	if (!opt.stat_set) {
-		const char *st = strstr(recs[0].comment.c_str(), "STAT_");
+		const std::string c0(recs[0].comment, recs[0].comment_l);
+		const char *st = strstr(c0.c_str(), "STAT_");
 		if (!st || sscanf(st + 5, "%d_%d_%d_%d_", &opt.read_len, &opt.isize_min, &opt.isize_mid, &opt.isize_max) == -1) {
 			opt.read_len = 150; opt.isize_min = 100; opt.isize_mid = 500; opt.isize_max = 900;
 		}
@@ -854,17 +872,24 @@ bool AlnPipeline::align_block(const std::vector<FastqRec> &recs, std::vector<Pai
 
 	// ---- stage A (parallel over reads; reads of a pair with an 'N' are left for the replay, see below)
 	const int T = std::max(1, opt.threads);
-	std::vector<ReadState> rs(n_reads);
+	// per-read state is constructed and destroyed by the worker threads (it is ~0.5 KB of containers per read)
+	struct ReadArray {
+		ReadState *p; size_t n; int T;
+		ReadArray(size_t n_, int T_) : p((ReadState*)malloc(sizeof(ReadState) * std::max<size_t>(n_, 1))), n(n_), T(T_)
+		{ parallel_chunks(n, T, [&](size_t b, size_t e, int) { for (size_t i = b; i < e; ++i) new (p + i) ReadState(); }); }
+		~ReadArray() { parallel_chunks(n, T, [&](size_t b, size_t e, int) { for (size_t i = b; i < e; ++i) p[i].~ReadState(); }); free(p); }
+		ReadState &operator[](size_t i) { return p[i]; }
+	} rs(n_reads, T);
 	parallel_chunks(n_reads, T, [&](size_t b, size_t e, int) {
 		for (size_t i = b; i < e; ++i) {
 			ReadState &r = rs[i];
 			r.rec = &recs[i];
-			r.seq = recs[i].seq; r.qual = recs[i].qual; r.comment = recs[i].comment;
-			r.read_l = (int)r.seq.size();
+			r.comment.assign(recs[i].comment, recs[i].comment_l);
+			r.read_l = (int)recs[i].seq_l;
 			I.parse_ori(r);
 			if (r.ori.chr > 24) r.ori_unmapped = true;                    // RR:413
 			r.skip = !r.ori_unmapped && r.ori.align_score == (uint32_t)(r.read_l * opt.match);   // RR:414
-			r.has_n = r.seq.find('N') != std::string::npos;
+			r.has_n = memchr(recs[i].seq, 'N', recs[i].seq_l) != nullptr;
 		}
 	});
 	auto prepare_read = [&](ReadState &r) {                                   // encode + pack + STR census
@@ -900,16 +925,44 @@ bool AlnPipeline::align_block(const std::vector<FastqRec> &recs, std::vector<Pai
 			I.chain(g);
 		}
 	};
-	parallel_chunks(n_reads, T, [&](size_t b, size_t e, int) {
-		for (size_t i = b; i < e; ++i) {
+	SeedBatch sb;
+	{
+		std::vector<uint32_t> word_off(n_reads + 1, 0), job_of(n_reads + 1, 0);
+		for (size_t i = 0; i < n_reads; ++i) {                               // layout of the packed-read pool (two strands per read)
 			ReadState &r = rs[i];
 			const bool pair_has_n = rs[i & ~(size_t)1].has_n || rs[i | 1].has_n;
 			r.batched = !(r.skip || pair_has_n || r.read_l < LEN_KMER);
-			if (r.batched) prepare_read(r);
+			word_off[i + 1] = word_off[i] + (r.batched ? 2u * (uint32_t)((r.read_l >> 5) + 2) : 0u);
+			job_of[i + 1] = job_of[i] + (r.batched ? 2u : 0u);
 		}
-	});
-	SeedBatch sb;
-	for (size_t i = 0; i < n_reads; ++i) if (rs[i].batched) register_jobs(rs[i], sb);
+		sb.bits.assign(word_off[n_reads], 0);
+		sb.jobs.resize(job_of[n_reads]);
+		parallel_chunks(n_reads, T, [&](size_t b, size_t e, int) {
+			for (size_t i = b; i < e; ++i) {
+				ReadState &r = rs[i];
+				if (!r.batched) continue;
+				I.encode(r);
+				const uint32_t words = (uint32_t)((r.read_l >> 5) + 2);
+				for (int s = 0; s < 2; ++s) {
+					const uint32_t off = word_off[i] + (uint32_t)s * words;
+					Impl::pack64(r.bin[s], sb.bits, off);
+					SeedJob &j = sb.jobs[job_of[i] + s];
+					j.bits_off = off; j.read_len = (uint32_t)r.read_l; j.is_str = 0; j.list_off = 0;
+					r.job[s] = (int)(job_of[i] + s);
+				}
+				I.str_census(r, sb.bits.data() + word_off[i]);
+			}
+		});
+		for (size_t i = 0; i < n_reads; ++i) {                               // STR reads are rare: their seed lists are appended in order
+			ReadState &r = rs[i];
+			if (!r.batched || !r.is_str) continue;
+			for (int s = 0; s < 2; ++s) {
+				SeedJob &j = sb.jobs[r.job[s]];
+				j.is_str = 1; j.list_off = (uint32_t)sb.seed_list.size();
+				sb.seed_list.insert(sb.seed_list.end(), r.seed_list[s].begin(), r.seed_list[s].end());
+			}
+		}
+	}
 	stats.t_stage[0] += now() - t0; t0 = now();
 	// ---- stage B
 	if (!sb.jobs.empty() && !seed_service_run(seeds_, sb, err)) return false;
@@ -1008,12 +1061,14 @@ bool AlnPipeline::align_block(const std::vector<FastqRec> &recs, std::vector<Pai
 		if (pes[pi].gain) I.set_primary(se, pes[pi]);
 		stats.reads += 2;
 	}
+	if (getenv("PANSVR_TIMING")) fprintf(stderr, "[timing] replay %.3f s\n", now() - t0);
 	// ---- SAM text of every pair (no random numbers involved any more: parallel)
 	parallel_chunks(n_pairs, T, [&](size_t pb, size_t pe_, int) {
 		for (size_t pi = pb; pi < pe_; ++pi) {
 			ReadState *se = &rs[2 * pi];
 			const Impl::PE &pe = pes[pi];
 			PairOutput &po = out[pi];
+			for (int k = 0; k < 2; ++k) { se[k].seq.assign(se[k].rec->seq, se[k].rec->seq_l); se[k].qual.assign(se[k].rec->qual, se[k].rec->qual_l); }
 			if (pe.gain)
 				for (int k = 0; k < 2; ++k) I.output_bam(se[k], po.sam[k], k == 0, pe.cur_isize);
 			if (pe.max_score <= min_filter_score_ && (int)se[0].ori.chr != -1 && (int)se[1].ori.chr != -1) {   // RR:776-797

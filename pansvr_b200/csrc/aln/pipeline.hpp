@@ -42,7 +42,10 @@ struct AlnOptions {                   // MAP_PARA, read_realignment.hpp:43-128 (
 	int read_len = 150, isize_min = 100, isize_mid = 500, isize_max = 900;
 };
 
-struct FastqRec { std::string name, comment, seq, qual; };
+struct FastqRec {                     // views into the caller's FASTQ text (no copies)
+	const char *name = nullptr, *comment = nullptr, *seq = nullptr, *qual = nullptr;
+	uint32_t name_l = 0, comment_l = 0, seq_l = 0, qual_l = 0;
+};
 
 // ---- device services (link-time: CUDA in the product library, host emulation in tests/emul) ---------------------
 struct SeedJob {                      // one read strand
@@ -76,7 +79,7 @@ public:
 	// Aligns n_pairs interleaved pairs (recs[2i], recs[2i+1]); out[i] receives the SAM text of pair i.
 	bool align_block(const std::vector<FastqRec> &recs, std::vector<PairOutput> &out, std::string &err);
 	struct Stats { uint64_t reads = 0, probes_reads = 0, mems = 0, ksw_tasks = 0, ksw_cells = 0, deferred_pairs = 0;
-	               double t_stage[6] = {0, 0, 0, 0, 0, 0}; } stats;
+	               double t_stage[8] = {0, 0, 0, 0, 0, 0, 0, 0}; } stats;   // A..F, FASTQ parse, output assembly
 	AlnOptions opt;                   // stat_set / read_len / isize_* are filled from the first comment
 private:
 	struct Impl;
