@@ -55,14 +55,14 @@ def main():
         t_create = time.time() - t0
         fq = open(d.reads_fq, "rb").read()
         times, last = [], None
-        for _ in range(a.repeat):
-            c2 = aln.AlnContext(d.index_dir, d.header_sam, threads=threads)     # fresh replay state: same bytes every run
+        hdr = ctx.header_text().encode()
+        for _ in range(a.repeat + 1):                                          # first pass warms the device buffers
+            ctx.reset()                                                        # fresh replay state: same bytes every run
             t0 = time.time()
-            sam, ori = c2.align_fastq(fq)
+            sam, ori = ctx.align_fastq(fq)
             times.append(time.time() - t0)
-            last = c2.stats()
-            hdr = c2.header_text().encode()
-            c2.close()
+            last = ctx.stats()
+        times = times[1:]
         ctx.close()
         same = (hdr + sam == open(os.path.join(wd, "ref1.sam"), "rb").read()) and (hdr + ori == open(os.path.join(wd, "ref1_ori.sam"), "rb").read())
         best = min(times)

@@ -169,6 +169,8 @@ const char *pansvr_aln_last_error(void);
  * and of the `-p` output; free with pansvr_free.  The rand() replay state carries over from block to block. */
 int  pansvr_aln_block(pansvr_aln_ctx *ctx, const char *fastq, size_t fastq_bytes, char **sam, size_t *sam_bytes, char **ori, size_t *ori_bytes);
 int  pansvr_aln_last_stats(const pansvr_aln_ctx *ctx, pansvr_aln_stats_t *out);
+/* Puts the replay back to the state of a freshly started `fc_aln` (rand() streams, counters); the index stays resident. */
+int  pansvr_aln_reset(pansvr_aln_ctx *ctx);
 void pansvr_free(void *p);
 /* Same command line as `panSVR fc_aln` (classify_main, src/main.cpp:18-25): [options] <IndexDir> <reads.fq|-> <header.sam>.
  * -S (SAM) output only. */

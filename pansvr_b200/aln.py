@@ -32,6 +32,7 @@ def _bind(lib):
     lib.pansvr_aln_block.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t),
                                      C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
     lib.pansvr_aln_last_stats.argtypes = [C.c_void_p, C.POINTER(AlnStatsC)]
+    lib.pansvr_aln_reset.argtypes = [C.c_void_p]
     lib.pansvr_free.argtypes = [C.c_void_p]
     lib.pansvr_fc_aln_main.argtypes = [C.c_int, C.POINTER(C.c_char_p)]
     return lib
@@ -60,6 +61,9 @@ class AlnContext:
             return C.string_at(s, sl.value), C.string_at(o, ol.value)
         finally:
             self.lib.pansvr_free(s); self.lib.pansvr_free(o)
+
+    def reset(self):
+        self.lib.pansvr_aln_reset(self.h)
 
     def stats(self) -> dict:
         st = AlnStatsC()

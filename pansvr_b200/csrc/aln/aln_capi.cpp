@@ -173,6 +173,13 @@ int pansvr_aln_last_stats(const pansvr_aln_ctx *c, pansvr_aln_stats_t *out)
 
 void pansvr_free(void *p) { free(p); }
 
+int pansvr_aln_reset(pansvr_aln_ctx *c)
+{
+	if (!c) return PANSVR_E_ARG;
+	c->pipe->reset();
+	return 0;
+}
+
 // ---- `panSVR fc_aln` command line (MAP_PARA::get_option, read_realignment.hpp:82-128)
 int pansvr_fc_aln_main(int argc, char **argv)
 {

@@ -847,6 +847,14 @@ struct AlnPipeline::Impl {
 AlnPipeline::AlnPipeline(const DebgaIndex &idx, const AlnOptions &o, SeedService *seeds, void *ksw_ctx)
 	: opt(o), idx_(idx), seeds_(seeds), ksw_(ksw_ctx), rand_(1)
 {
+	reset();
+}
+
+void AlnPipeline::reset()
+{
+	rand_.reseed(1);
+	stats = Stats();
+	opt.stat_set = false;
 	// Classify_buff_pool of thread 0: two single_end_handlers, each seeds its random_r state with rand() (RR:62-67, RRH:339-340)
 	for (int i = 0; i < 2; ++i) rand_r_[i].reseed((unsigned)rand_.next());
 }
@@ -1026,7 +1034,11 @@ bool AlnPipeline::align_block(const std::vector<FastqRec> &recs, std::vector<Pai
 			tl.cig.assign(n * (size_t)tl.cap, 0);
 		}
 		stats.ksw_tasks += n;
-		for (size_t i = 0; i < n; ++i) stats.ksw_cells += (uint64_t)pansvr_ksw_band_cells(tl.qlen[i], tl.tlen[i], kp.w);
+		{
+			std::atomic<uint64_t> cells(0);
+			parallel_chunks(n, T, [&](size_t b, size_t e, int) { uint64_t c = 0; for (size_t i = b; i < e; ++i) c += (uint64_t)pansvr_ksw_band_cells(tl.qlen[i], tl.tlen[i], kp.w); cells += c; });
+			stats.ksw_cells += cells.load();
+		}
 		return true;
 	};
 	if (!run_ksw(tasks)) return false;

@@ -78,6 +78,7 @@ public:
 	AlnPipeline(const DebgaIndex &idx, const AlnOptions &opt, SeedService *seeds, void *ksw_ctx);
 	// Aligns n_pairs interleaved pairs (recs[2i], recs[2i+1]); out[i] receives the SAM text of pair i.
 	bool align_block(const std::vector<FastqRec> &recs, std::vector<PairOutput> &out, std::string &err);
+	void reset();                     // back to the state of a freshly started `fc_aln` (rand() streams, counters)
 	struct Stats { uint64_t reads = 0, probes_reads = 0, mems = 0, ksw_tasks = 0, ksw_cells = 0, deferred_pairs = 0;
 	               double t_stage[8] = {0, 0, 0, 0, 0, 0, 0, 0}; } stats;   // A..F, FASTQ parse, output assembly
 	AlnOptions opt;                   // stat_set / read_len / isize_* are filled from the first comment
