@@ -115,6 +115,20 @@ int pansvr_aln_block(pansvr_aln_ctx *c, const char *fastq, size_t n, char **sam,
 {
 	if (!c || !fastq || !sam || !ori) return PANSVR_E_ARG;
 	const auto tick = []() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+	const double t_enter = tick();
+	double t_sum0 = 0;
+	for (int i = 0; i < 8; ++i) t_sum0 += c->pipe->stats.t_stage[i];
+	struct Report {                                             // PANSVR_TIMING=1: wall time of the call next to the sum of its stages
+		pansvr_aln_ctx *c; double t_enter, t_sum0;
+		~Report()
+		{
+			if (!getenv("PANSVR_TIMING")) return;
+			double s = 0;
+			for (int i = 0; i < 8; ++i) s += c->pipe->stats.t_stage[i];
+			const double now = std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+			fprintf(stderr, "[timing] pansvr_aln_block %.3f s, stages %.3f s\n", now - t_enter, s - t_sum0);
+		}
+	} report{c, t_enter, t_sum0};
 	double t0 = tick();
 	std::vector<FastqRec> recs;
 	parse_fastq(fastq, n, recs);
@@ -122,6 +136,7 @@ int pansvr_aln_block(pansvr_aln_ctx *c, const char *fastq, size_t n, char **sam,
 	std::vector<PairOutput> outp;
 	std::string err;
 	if (!c->pipe->align_block(recs, outp, err)) { g_aln_err = err; return PANSVR_E_CUDA; }
+	if (getenv("PANSVR_TIMING")) fprintf(stderr, "[timing] align_block returned at %.3f s\n", tick() - t_enter);
 	t0 = tick();
 	// total sizes, then every pair copies its records to its own offset (parallel)
 	const size_t np = outp.size();
@@ -133,31 +148,22 @@ int pansvr_aln_block(pansvr_aln_ctx *c, const char *fastq, size_t n, char **sam,
 	}
 	char *sbuf = (char*)malloc(off_s[np] + 1), *obuf = (char*)malloc(off_o[np] + 1);
 	if (!sbuf || !obuf) { free(sbuf); free(obuf); g_aln_err = "out of memory"; return PANSVR_E_ARG; }
-	{
-		const int T = std::max(1, c->opt.threads);
-		std::vector<std::thread> th;
-		const size_t per = (np + T - 1) / T;
-		for (int t = 0; t < T; ++t) {
-			const size_t b = std::min(np, per * t), e = std::min(np, per * (t + 1));
-			if (b >= e) break;
-			th.emplace_back([&, b, e]() {
-				for (size_t i = b; i < e; ++i) {
-					char *ps = sbuf + off_s[i], *po = obuf + off_o[i];
-					for (int k = 0; k < 2; ++k) {
-						const std::string &x = outp[i].sam[k], &y = outp[i].ori[k];
-						if (!x.empty()) { memcpy(ps, x.data(), x.size()); ps += x.size(); *ps++ = '\n'; }
-						if (!y.empty()) { memcpy(po, y.data(), y.size()); po += y.size(); *po++ = '\n'; }
-					}
-				}
-			});
+	c->pipe->parallel(np, [&](size_t b, size_t e, int) {
+		for (size_t i = b; i < e; ++i) {
+			char *ps = sbuf + off_s[i], *po = obuf + off_o[i];
+			for (int k = 0; k < 2; ++k) {
+				const std::string &x = outp[i].sam[k], &y = outp[i].ori[k];
+				if (!x.empty()) { memcpy(ps, x.data(), x.size()); ps += x.size(); *ps++ = '\n'; }
+				if (!y.empty()) { memcpy(po, y.data(), y.size()); po += y.size(); *po++ = '\n'; }
+			}
 		}
-		for (std::thread &x : th) x.join();
-	}
+	});
 	sbuf[off_s[np]] = 0; obuf[off_o[np]] = 0;
 	*sam = sbuf; *ori = obuf;
 	if (sam_bytes) *sam_bytes = off_s[np];
 	if (ori_bytes) *ori_bytes = off_o[np];
 	c->pipe->stats.t_stage[7] += tick() - t0;
+	if (getenv("PANSVR_TIMING")) fprintf(stderr, "[timing] emit done at %.3f s\n", tick() - t_enter);
 	return 0;
 }
 

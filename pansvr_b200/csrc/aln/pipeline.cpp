@@ -7,6 +7,8 @@
 #include <algorithm>
 #include <atomic>
 #include <chrono>
+#include <condition_variable>
+#include <mutex>
 #include <thread>
 
 #include "../../../include/pansvr_b200.h"
@@ -23,19 +25,67 @@ enum { MIN_STR_REPEAT_COUNT = 4, MIN_STR_DETECT_LEN = 15 };
 const uint32_t U32MAX = 0xffffffffu;
 const int I32MAX = 0x7fffffff;
 
-// static-chunk parallel loop over [0,n): fn(begin, end, thread_index)
-template <class F> void parallel_chunks(size_t n, int threads, F fn)
-{
-	if (threads <= 1 || n < 256) { fn((size_t)0, n, 0); return; }
+} // namespace
+
+// Persistent helper threads.  Chunk t of every parallel region runs on worker t, and regions over reads are cut at
+// pair boundaries, so the per-read containers a worker allocates are later grown and freed by the same thread (its own
+// malloc arena: no cross-thread frees, no lock contention when a block of a million reads is torn down).
+struct AlnPipeline::Workers {
 	std::vector<std::thread> th;
-	const size_t per = (n + threads - 1) / threads;
-	for (int t = 0; t < threads; ++t) {
-		const size_t b = std::min(n, per * t), e = std::min(n, per * (t + 1));
-		if (b >= e) break;
-		th.emplace_back([=]() { fn(b, e, t); });
+	std::mutex m;
+	std::condition_variable go, done;
+	uint64_t generation = 0;
+	int chunks = 0, pending = 0;
+	bool stop = false;
+	const std::function<void(int)> *job = nullptr;
+	explicit Workers(int n)
+	{
+		for (int i = 0; i < n; ++i) th.emplace_back([this, i]() {
+			uint64_t seen = 0;
+			for (;;) {
+				const std::function<void(int)> *f;
+				{
+					std::unique_lock<std::mutex> lk(m);
+					go.wait(lk, [&]() { return stop || generation != seen; });
+					if (stop) return;
+					seen = generation;
+					if (i >= chunks) continue;
+					f = job;
+				}
+				(*f)(i);
+				{
+					std::lock_guard<std::mutex> lk(m);
+					if (--pending == 0) done.notify_one();
+				}
+			}
+		});
 	}
-	for (std::thread &x : th) x.join();
+	~Workers()
+	{
+		{ std::lock_guard<std::mutex> lk(m); stop = true; }
+		go.notify_all();
+		for (std::thread &t : th) t.join();
+	}
+	void run(int n_chunks, const std::function<void(int)> &f)
+	{
+		std::unique_lock<std::mutex> lk(m);
+		job = &f; chunks = n_chunks; pending = n_chunks; ++generation;
+		go.notify_all();
+		done.wait(lk, [&]() { return pending == 0; });
+	}
+};
+
+// static-chunk parallel loop over [0,n): fn(begin, end, chunk_index)
+void AlnPipeline::parallel(size_t n, const std::function<void(size_t, size_t, int)> &fn)
+{
+	const int T = workers_ ? (int)workers_->th.size() : 1;
+	if (T <= 1 || n < 256) { fn((size_t)0, n, 0); return; }
+	const size_t per = (n + T - 1) / T;
+	const int chunks = (int)((n + per - 1) / per);
+	workers_->run(chunks, [&](int t) { fn(std::min(n, per * t), std::min(n, per * (t + 1)), t); });
 }
+
+namespace {
 
 double now() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
@@ -49,9 +99,9 @@ char rev_char(char c)                                           // getReverseCha
 	switch (c) { case 'A': case 'a': return 'T'; case 'C': case 'c': return 'G'; case 'G': case 'g': return 'C'; case 'T': case 't': return 'A'; }
 	return 'N';
 }
-void rev_str(std::string &s)                                    // getReverseStr_char, clib/bam_file.c:330-340
+void rev_str(char *s, int len)                                  // getReverseStr_char, clib/bam_file.c:330-340
 {
-	const int len = (int)s.size(), half = len >> 1;
+	const int half = len >> 1;
 	for (int i = 0; i < half; ++i) { const char t = s[i]; s[i] = rev_char(s[len - 1 - i]); s[len - 1 - i] = rev_char(t); }
 	if (len & 1) s[half] = rev_char(s[half]);
 }
@@ -150,7 +200,6 @@ struct NodeAln {
 struct ReadState {
 	const FastqRec *rec = nullptr;
 	std::string comment;                       // mutable copy (the reference edits its kseq_t in place)
-	std::string seq, qual;                     // filled only while the SAM text is written (output_bam reverses them in place)
 	int read_l = 0;
 	bool has_n = false, skip = false;          // skip: early-out of single_end_handler::align (RR:413-414)
 	// original alignment (parse_ori_mapping_rst)
@@ -165,7 +214,7 @@ struct ReadState {
 	std::vector<VertexU> vu[2];
 	int job[2] = {-1, -1};
 	Graph g[2];
-	std::map<uint64_t, NodeAln> node_aln;      // key = strand << 32 | node
+	std::vector<std::pair<uint64_t, NodeAln>> node_aln;   // key = strand << 32 | node, ascending
 	// results
 	int result_num = 0;
 	std::vector<Result> result;                // at most 2 * MAX_OUTPUT_NUMBER, reserved once so that pointers stay valid
@@ -187,6 +236,15 @@ struct KswTaskList {
 		return (int)qlen.size() - 1;
 	}
 	void clear() { q.clear(); t.clear(); qoff.clear(); toff.clear(); qlen.clear(); tlen.clear(); res.clear(); cig.clear(); }
+};
+
+// The process-wide rand() stream as the replay sees it: the real generator, or a probe that only records that it
+// was asked (a pair that never asks is independent of the stream position and can be finished on any thread).
+struct RandTap {
+	GlibcRandom *real = nullptr;
+	uint32_t calls = 0;
+	int32_t next() { ++calls; return real ? real->next() : 0; }
+	std::vector<CigarPath> cigar_scratch;                    // (per-thread scratch of finish_read rides along)
 };
 
 struct AlnPipeline::Impl {
@@ -231,6 +289,7 @@ struct AlnPipeline::Impl {
 		o.direction = (nt > 9 && tok_l[9] > 0 && tok[9][0] == 'F') ? FORWARD : REVERSE;
 		r.ori_unmapped = nt > 9 && tok_l[9] > 1 && tok[9][1] == 'Y';
 		o.cigar.clear();
+		o.cigar.reserve(2);
 		if (o.read_bg > 0) o.cigar.push_back(cig_char('S', (int)o.read_bg));
 		o.cigar.push_back(cig_char('M', r.read_l - (int)o.read_bg));
 		o.sv = nullptr; o.has_mate = false;
@@ -253,24 +312,46 @@ struct AlnPipeline::Impl {
 
 	static void pack64(const std::vector<uint8_t> &b, std::vector<uint64_t> &out, size_t off)   // binary_read_64_bit, RR:295-300
 	{
-		for (size_t i = 0; i < b.size(); ++i) out[off + (i >> 5)] |= (uint64_t)b[i] << ((31 - (i & 0x1f)) << 1);
+		const size_t n = b.size();
+		size_t i = 0;
+		for (; i + 32 <= n; i += 32) {
+			uint64_t w = 0;
+			for (int k = 0; k < 32; ++k) w = (w << 2) | b[i + k];
+			out[off + (i >> 5)] = w;
+		}
+		if (i < n) {
+			uint64_t w = 0;
+			for (size_t k = i; k < n; ++k) w = (w << 2) | b[k];
+			out[off + (i >> 5)] = w << ((32 - (n - i)) << 1);
+		}
 	}
 
+	// scratch of str_census, one per worker: slots are valid when their stamp equals the current read's
+	struct CensusScratch {
+		std::vector<uint64_t> keys;
+		std::vector<uint32_t> stamp;
+		std::vector<uint16_t> cnt, slot_of;
+		uint32_t now = 0;
+	};
+
 	// STR census of the forward strand (read_realignment.cpp:553-598): k-mer multiplicities, mask, forced seeds
-	void str_census(ReadState &r, const uint64_t *bits)
+	void str_census(ReadState &r, const uint64_t *bits, CensusScratch &cs)
 	{
 		const uint32_t L = (uint32_t)r.read_l, kn = L - LEN_KMER + 1;
 		// multiplicity of every 20-mer (the reference's std::map<kmer,count>): open addressing, 4x slots
 		uint32_t cap = 64;
 		while (cap < 4 * kn) cap <<= 1;
-		std::vector<uint64_t> keys(cap);
-		std::vector<uint16_t> cnt(cap, 0), slot_of(kn);
+		if (cs.keys.size() < cap) { cs.keys.assign(cap, 0); cs.stamp.assign(cap, 0); cs.cnt.assign(cap, 0); cs.now = 0; }
+		if (cs.slot_of.size() < kn) cs.slot_of.resize(kn);
+		if (++cs.now == 0) { std::fill(cs.stamp.begin(), cs.stamp.end(), 0u); cs.now = 1; }
+		uint64_t *keys = cs.keys.data(); uint32_t *stamp = cs.stamp.data(); uint16_t *cnt = cs.cnt.data(), *slot_of = cs.slot_of.data();
+		const uint32_t tick = cs.now;
 		uint32_t distinct = 0;
 		for (uint32_t i = 0; i < kn; ++i) {
 			const uint64_t k = get_kmer(i, bits);
 			uint32_t h = (uint32_t)((k * 0x9E3779B97F4A7C15ull) >> 40) & (cap - 1);
-			while (cnt[h] != 0 && keys[h] != k) h = (h + 1) & (cap - 1);
-			if (cnt[h] == 0) { keys[h] = k; ++distinct; }
+			while (stamp[h] == tick && keys[h] != k) h = (h + 1) & (cap - 1);
+			if (stamp[h] != tick) { stamp[h] = tick; keys[h] = k; cnt[h] = 0; ++distinct; }
 			++cnt[h];
 			slot_of[i] = (uint16_t)h;
 		}
@@ -295,27 +376,27 @@ struct AlnPipeline::Impl {
 	}
 
 	// ---------------------------------------------------------------- stage C
-	void merge_mems(std::vector<Mem> &m, std::vector<VertexU> &out)   // merge_seed_in_unipath, deBGA_index.cpp:151-217
+	// m[0..n) is sorted in place.  The reference reads one element past the end in its loop conditions (a slot that can never
+	// match); the `j < n` tests below come first instead.
+	void merge_mems(Mem *m, uint32_t n, std::vector<VertexU> &out)   // merge_seed_in_unipath, deBGA_index.cpp:151-217
 	{
 		out.clear();
-		const uint32_t n = (uint32_t)m.size();
 		if (n == 0) return;
+		out.reserve(n);
 		if (n == 1) {
 			VertexU u; u.uid = m[0].uid; u.read_pos = m[0].read_pos; u.uni_pos_off = m[0].uni_pos_off; u.pos_n = m[0].pos_n;
 			u.length1 = u.length2 = u.cov = m[0].length;
 			out.push_back(u);
 			return;
 		}
-		qsort(m.data(), n, sizeof(Mem), cmp_mem);
-		m.push_back(Mem());                                      // the reference reads one element past the end in its loop conditions
-		m[n].uid = ~0ull; m[n].uni_pos_off = 0;
+		qsort(m, n, sizeof(Mem), cmp_mem);
 		uint64_t uid_t = m[0].uid;
 		uint32_t j = 0;
 		while (j < n) {
 			const uint32_t s1 = j;
 			uint32_t cov = m[s1].length;
 			++j;
-			while (uid_t == m[j].uid && m[j].uni_pos_off > m[j - 1].uni_pos_off && j < n) {
+			while (j < n && uid_t == m[j].uid && m[j].uni_pos_off > m[j - 1].uni_pos_off) {
 				const int diff = (int)(m[j].read_pos - m[j - 1].read_pos - m[j - 1].length);
 				if (diff > WAITING_LEN) break;
 				const int c_eindel = (int)((m[j].uni_pos_off - m[j - 1].uni_pos_off) - (m[j].read_pos - m[j - 1].read_pos));
@@ -331,13 +412,15 @@ struct AlnPipeline::Impl {
 				u.length2 = m[e1].uni_pos_off + m[e1].length - m[s1].uni_pos_off;
 			}
 			out.push_back(u);
-			uid_t = m[j].uid;
+			if (j < n) uid_t = m[j].uid;
 		}
-		m.pop_back();
 	}
 
 	void expand(const std::vector<VertexU> &vu, std::vector<UniSeed> &out, GlibcRandom &rr)   // expand_seed, deBGA_index.cpp:219-258
 	{
+		size_t total = 0;
+		for (const VertexU &u : vu) total += u.pos_n > POS_N_MAX ? (size_t)RANDOM_NUM : u.pos_n;
+		out.reserve(total);
 		for (uint32_t i = 0; i < vu.size(); ++i) {
 			const VertexU &u = vu[i];
 			auto push = [&](uint32_t mpos) {
@@ -354,7 +437,7 @@ struct AlnPipeline::Impl {
 		}
 	}
 
-	void chain(Graph &g)                                          // Graph_handler::process + dynamic_programming_path, graph.cpp:53-150
+	void chain(Graph &g, std::vector<Edge> &edges)                // Graph_handler::process + dynamic_programming_path, graph.cpp:53-150
 	{
 		std::vector<UniSeed> &v = g.v;
 		const uint32_t n = (uint32_t)v.size();
@@ -366,7 +449,7 @@ struct AlnPipeline::Impl {
 		const uint32_t step = std::min(n, max_step);
 		g.path.resize(n);
 		for (uint32_t i = 0; i < n; ++i) { g.path[i].dist = (float)v[i].cov; g.path[i].pre_node = -1; g.path[i].used = 0; }
-		std::vector<Edge> edges;
+		edges.clear();
 		for (uint32_t a = 0; a + 1 < n; ++a) {
 			const uint32_t read_end = v[a].read_end, ref_end = v[a].ref_end, seed_id = v[a].seed_id;
 			const uint32_t stop = std::min(n, a + step);
@@ -404,11 +487,12 @@ struct AlnPipeline::Impl {
 	}
 
 	// ---------------------------------------------------------------- stage D: get_ksw_score as a plan (RR:308-400, 893-986)
+	struct PlanScratch { std::vector<uint8_t> tseq, qrev; };
 	struct Planner {
 		Impl &I; ReadState &r; int strand; KswTaskList &tasks; NodeAln &out;
-		std::vector<uint8_t> tseq, qrev;
+		std::vector<uint8_t> &tseq, &qrev;
 		int total_q_len = 0; bool last_simple = false;
-		Planner(Impl &i, ReadState &rs, int s, KswTaskList &t, NodeAln &o) : I(i), r(rs), strand(s), tasks(t), out(o) {}
+		Planner(Impl &i, ReadState &rs, int s, KswTaskList &t, NodeAln &o, PlanScratch &sc) : I(i), r(rs), strand(s), tasks(t), out(o), tseq(sc.tseq), qrev(sc.qrev) {}
 		void lit(char t, int size) { Piece p; p.kind = 0; p.lit = cig_char(t, size); p.task = -1; p.type = 0; out.pieces.push_back(p); }
 		int mismatch(int rs, int re, int fs, int fe)             // get_misMatch, RR:893-908
 		{
@@ -517,7 +601,7 @@ struct AlnPipeline::Impl {
 		}
 	};
 
-	void plan_read(ReadState &r, KswTaskList &tasks)
+	void plan_read(ReadState &r, KswTaskList &tasks, PlanScratch &scratch)
 	{
 		r.node_aln.clear();
 		uint32_t best = 0;                                         // chain scores are compared as uint32 (RR:423-429, 442)
@@ -528,15 +612,17 @@ struct AlnPipeline::Impl {
 			for (uint32_t n = 0; n < g.path.size(); ++n) {
 				const uint32_t c = (uint32_t)g.path[n].dist;
 				if (c < (uint32_t)MIN_CHAIN_SCORE2 || c + MAX_CHAIN_SCORE_DIFF < best) continue;
-				NodeAln &na = r.node_aln[(uint64_t)s << 32 | n];
-				Planner pl(*this, r, s, tasks, na);                // g[1] is the reverse strand, bin[1] its sequence
+				r.node_aln.emplace_back((uint64_t)s << 32 | n, NodeAln());
+				NodeAln &na = r.node_aln.back().second;
+				na.pieces.reserve(8);
+				Planner pl(*this, r, s, tasks, na, scratch);       // g[1] is the reverse strand, bin[1] its sequence
 				pl.run((int)n);
 			}
 		}
 	}
 
 	// ---------------------------------------------------------------- stage F
-	int sort_output(ReadState &r, int s, Result &rst, int direction)   // read_realignment.cpp:212-293
+	int sort_output(ReadState &r, int s, Result &rst, int direction, RandTap &rnd)   // read_realignment.cpp:212-293
 	{
 		Graph &g = r.g[s];
 		const int n = (int)g.path.size();
@@ -553,7 +639,7 @@ struct AlnPipeline::Impl {
 			if (g.max_index == U32MAX) return 0;
 			int used = 0, fresh = 0;
 			const uint32_t same = (uint32_t)g.same_top.size();
-			if (same > 1) g.max_index = (uint32_t)g.same_top[P.rand_.next() % (int32_t)same];
+			if (same > 1) g.max_index = (uint32_t)g.same_top[rnd.next() % (int32_t)same];
 			int node = (int)g.max_index;
 			const int first = node;
 			for (; node != -1;) {
@@ -595,10 +681,13 @@ struct AlnPipeline::Impl {
 	void sort_results(Result *res, int n, int (*cmp)(const void*, const void*))
 	{
 		if (n < 2) return;
-		std::vector<Result*> p(n);
+		Result *p[2 * MAX_OUTPUT_NUMBER];
 		for (int i = 0; i < n; ++i) p[i] = res + i;
-		qsort(p.data(), n, sizeof(Result*), cmp);
-		std::vector<Result> tmp(n);
+		qsort(p, n, sizeof(Result*), cmp);
+		bool moved = false;
+		for (int i = 0; i < n; ++i) moved |= p[i] != res + i;
+		if (!moved) return;
+		Result tmp[2 * MAX_OUTPUT_NUMBER];
 		for (int i = 0; i < n; ++i) tmp[i] = std::move(*p[i]);
 		for (int i = 0; i < n; ++i) res[i] = std::move(tmp[i]);
 	}
@@ -607,6 +696,7 @@ struct AlnPipeline::Impl {
 	{
 		c.cigar.clear();
 		if (tmp.empty()) return false;
+		c.cigar.reserve(tmp.size());
 		c.cigar.push_back(tmp.back());
 		for (int i = (int)tmp.size() - 2; i >= 0; --i)
 			if (!cig_try_merge(c.cigar.back(), tmp[i])) c.cigar.push_back(tmp[i]);
@@ -617,18 +707,19 @@ struct AlnPipeline::Impl {
 	}
 
 	// the rest of single_end_handler::align once chains and ksw results exist (RR:416-475)
-	void finish_read(ReadState &r, const KswTaskList &tasks)
+	void finish_read(ReadState &r, const KswTaskList &tasks, RandTap &rnd)
 	{
 		r.result_num = 0; r.primary = r.secondary = nullptr;
 		r.result.clear();
 		if (r.skip) return;
+		for (int s = 0; s < 2; ++s) for (PathNode &p : r.g[s].path) p.used = 0;   // a probed pair is finished a second time
 		r.result.reserve(2 * MAX_OUTPUT_NUMBER);
 		uint32_t max_chain = 0;
 		for (int s = 0; s < 2; ++s) {
 			const int direction = s == 0 ? FORWARD : REVERSE;
 			for (int i = 0; i < MAX_OUTPUT_NUMBER; ++i) {
 				Result slot;
-				if (!sort_output(r, s, slot, direction)) break;
+				if (!sort_output(r, s, slot, direction, rnd)) break;
 				const uint32_t c = slot.chain_score;
 				max_chain = std::max(c, max_chain);
 				if (c + MAX_CHAIN_SCORE_DIFF < max_chain || c < MIN_CHAIN_SCORE2) break;
@@ -642,14 +733,16 @@ struct AlnPipeline::Impl {
 			Result &c = r.result[k];
 			if (c.chain_score + MAX_CHAIN_SCORE_DIFF < max_chain) { r.result_num = k; break; }
 			const int s = c.direction == REVERSE ? 1 : 0;
-			auto it = r.node_aln.find((uint64_t)s << 32 | c.max_index);
-			if (it == r.node_aln.end() || !it->second.planned) {     // cannot happen: the plan is a superset
+			const uint64_t key = (uint64_t)s << 32 | c.max_index;
+			auto it = std::lower_bound(r.node_aln.begin(), r.node_aln.end(), key, [](const std::pair<uint64_t, NodeAln> &a, uint64_t k) { return a.first < k; });
+			if (it == r.node_aln.end() || it->first != key || !it->second.planned) {     // cannot happen: the plan is a superset
 				fprintf(stderr, "pansvr_b200: internal error, chain end %u of strand %d was not planned\n", c.max_index, s);
 				abort();
 			}
 			const NodeAln &na = it->second;
 			int score = na.fixed_score;
-			std::vector<CigarPath> tmp;
+			std::vector<CigarPath> &tmp = rnd.cigar_scratch;
+			tmp.clear();
 			for (const Piece &p : na.pieces) {
 				if (p.kind == 0) { tmp.push_back(p.lit); continue; }
 				const int32_t *res = tasks.res.data() + (size_t)p.task * PANSVR_RES_WORDS;
@@ -705,7 +798,7 @@ struct AlnPipeline::Impl {
 		if ((v = get_isize(a2, b2, a->direction, b->direction)) > 0) return v;
 		return 0;
 	}
-	void store_pair(PE &pe, Result *a, Result *b)
+	void store_pair(PE &pe, Result *a, Result *b, RandTap &rnd)
 	{
 		const int isize = proper_mated(a, b);
 		const int basic = (a ? (int)a->align_score : 0) + (b ? (int)b->align_score : 0);
@@ -714,20 +807,20 @@ struct AlnPipeline::Impl {
 		if (fin >= pe.max_score) {
 			bool store = true;
 			if (fin > pe.max_score) pe.max_same = 1;
-			else if (fin == pe.max_score) { ++pe.max_same; if (P.rand_.next() % pe.max_same != 0) store = false; }
+			else if (fin == pe.max_score) { ++pe.max_same; if (rnd.next() % pe.max_same != 0) store = false; }
 			if (store) { pe.m1 = a; pe.m2 = b; pe.max_score = fin; pe.cur_isize = isize; pe.proper = isize > 0; }
 		}
 	}
-	void pair_up(ReadState *se, PE &pe)
+	void pair_up(ReadState *se, PE &pe, RandTap &rnd)
 	{
 		pe = PE();
 		int n0 = se[0].result_num, n1 = se[1].result_num;
 		if (!se[0].ori_unmapped) ++n0;
 		if (!se[1].ori_unmapped) ++n1;
 		auto pick = [](ReadState &r, int i) -> Result* { return i < r.result_num ? &r.result[i] : &r.ori; };
-		for (int i = 0; i < n0; ++i) store_pair(pe, pick(se[0], i), nullptr);
-		for (int j = 0; j < n1; ++j) store_pair(pe, nullptr, pick(se[1], j));
-		for (int i = 0; i < n0; ++i) for (int j = 0; j < n1; ++j) store_pair(pe, pick(se[0], i), pick(se[1], j));
+		for (int i = 0; i < n0; ++i) store_pair(pe, pick(se[0], i), nullptr, rnd);
+		for (int j = 0; j < n1; ++j) store_pair(pe, nullptr, pick(se[1], j), rnd);
+		for (int i = 0; i < n0; ++i) for (int j = 0; j < n1; ++j) store_pair(pe, pick(se[0], i), pick(se[1], j), rnd);
 		pe.gain = pe.max_score > 0 && ((pe.m1 && !pe.m1->is_ori) || (pe.m2 && !pe.m2->is_ori));
 	}
 	void set_primary(ReadState *se, PE &pe)                      // set_primary_secondary_mate, RRH:501-534
@@ -748,7 +841,21 @@ struct AlnPipeline::Impl {
 	}
 
 	// SAM text of one record after htslib's parse->format round trip (RR:479-536; sam.c sam_parse1 / sam_format1)
-	static void append_int(std::string &s, long v) { char b[32]; snprintf(b, sizeof b, "%ld", v); s += b; }
+	static void append_int(std::string &s, long v)
+	{
+		char b[24]; int n = 24;
+		unsigned long u = v < 0 ? 0ul - (unsigned long)v : (unsigned long)v;
+		do { b[--n] = (char)('0' + u % 10); u /= 10; } while (u);
+		if (v < 0) b[--n] = '-';
+		s.append(b + n, 24 - n);
+	}
+	// SEQ and QUAL columns: the reference reverses its kseq_t in place around the write and restores it afterwards
+	void append_seq_qual(std::string &out, const ReadState &r, bool reversed)
+	{
+		const size_t at = out.size();
+		out.append(r.rec->seq, r.rec->seq_l); out += '\t'; out.append(r.rec->qual, r.rec->qual_l);
+		if (reversed) { rev_str(&out[at], r.read_l); rev_qual(&out[at + r.rec->seq_l + 1], r.read_l); }
+	}
 	std::string target_name(uint32_t id) const { return id < idx.target_names.size() ? idx.target_names[id] : std::string("*"); }
 
 	void output_bam(ReadState &r, std::string &out, bool first, int abs_isize)
@@ -757,6 +864,7 @@ struct AlnPipeline::Impl {
 		Result *p = r.primary;
 		if (!p || p->chr == U32MAX) return;
 		if (P.opt.not_ori && p->is_ori) return;
+		out.reserve(2 * (size_t)r.read_l + r.rec->name_l + r.comment.size() + 256);
 		const int dir = p->direction;
 		const uint8_t flag = (uint8_t)((first ? 0x40 : 0) + (dir == REVERSE ? 0x10 : 0) + (p->has_mate ? 0 : 0x08));
 		out.append(r.rec->name, r.rec->name_l); out += '\t'; append_int(out, flag); out += '\t';
@@ -769,10 +877,8 @@ struct AlnPipeline::Impl {
 			out += (p->mate_chr == p->chr) ? std::string("=") : target_name(p->mate_chr);
 			out += '\t'; append_int(out, (int)p->mate_ref_bg); out += '\t'; append_int(out, isize); out += '\t';
 		} else out += "*\t0\t0\t";
-		if (dir == REVERSE) { rev_str(r.seq); rev_qual(&r.qual[0], r.read_l); }
-		out += r.seq; out += '\t'; out += r.qual; out += '\t';
+		append_seq_qual(out, r, dir == REVERSE); out += '\t';
 		out += "AS:i:"; append_int(out, (int)p->align_score);
-		if (dir == REVERSE) { rev_str(r.seq); rev_qual(&r.qual[0], r.read_l); }
 		out += "\tOS:i:"; append_int(out, (int)r.ori.align_score);
 		out += "\tOA:Z:"; append_int(out, (int)r.ori.chr); out += ','; append_int(out, (int)r.ori.ref_bg); out += ',';
 		append_int(out, (int)r.ori.read_bg); out += ','; append_int(out, r.ori.mapq); out += ','; out += r.ori_unmapped ? 'U' : 'M'; out += ';';
@@ -815,15 +921,14 @@ struct AlnPipeline::Impl {
 		if (tag_len > 0) tags.resize(tag_len - 1);
 		// the reference cuts the comment in place at the end of the CIGAR and edits the tags
 		c[cig_e < c.size() ? cig_e : c.size() - 1] = '\0';
+		out.reserve(2 * (size_t)r.read_l + r.rec->name_l + tags.size() + cigar.size() + 128);
 		out.append(r.rec->name, r.rec->name_l); out += '\t'; append_int(out, flag); out += '\t'; out += target_name(r.ori.chr); out += '\t';
 		append_int(out, (long)(r.ori.ref_bg + 1)); out += '\t'; append_int(out, qual); out += '\t';
 		out += cigar.empty() ? std::string("*") : cigar; out += '\t';
 		out += ((uint32_t)mchr == r.ori.chr) ? std::string("=") : target_name((uint32_t)mchr);
 		out += '\t'; append_int(out, mpos); out += '\t'; append_int(out, isize); out += '\t';
 		const bool fwd = (flag & 0x10) == 0;
-		if (!fwd) { rev_str(r.seq); rev_qual(&r.qual[0], r.read_l); }
-		out += r.seq; out += '\t'; out += r.qual;
-		if (!fwd) { rev_str(r.seq); rev_qual(&r.qual[0], r.read_l); }
+		append_seq_qual(out, r, !fwd);
 		if (tag_len) { out += '\t'; out += tags; }
 		out += "\tMS:i:"; append_int(out, max_score);
 		// bam_has_clip_or_unmapped_ori (RR:721-733) on the CIGAR just written
@@ -847,8 +952,11 @@ struct AlnPipeline::Impl {
 AlnPipeline::AlnPipeline(const DebgaIndex &idx, const AlnOptions &o, SeedService *seeds, void *ksw_ctx)
 	: opt(o), idx_(idx), seeds_(seeds), ksw_(ksw_ctx), rand_(1)
 {
+	if (opt.threads > 1) workers_ = new Workers(opt.threads);
 	reset();
 }
+
+AlnPipeline::~AlnPipeline() { delete workers_; }
 
 void AlnPipeline::reset()
 {
@@ -881,14 +989,16 @@ bool AlnPipeline::align_block(const std::vector<FastqRec> &recs, std::vector<Pai
 	// ---- stage A (parallel over reads; reads of a pair with an 'N' are left for the replay, see below)
 	const int T = std::max(1, opt.threads);
 	// per-read state is constructed and destroyed by the worker threads (it is ~0.5 KB of containers per read)
+	// loops over reads are cut at pair boundaries: the same worker owns a pair's two reads in every stage
+	auto par_reads = [&](const std::function<void(size_t, size_t, int)> &fn) { parallel(n_pairs, [&](size_t b, size_t e, int t) { fn(2 * b, 2 * e, t); }); };
 	struct ReadArray {
-		ReadState *p; size_t n; int T;
-		ReadArray(size_t n_, int T_) : p((ReadState*)malloc(sizeof(ReadState) * std::max<size_t>(n_, 1))), n(n_), T(T_)
-		{ parallel_chunks(n, T, [&](size_t b, size_t e, int) { for (size_t i = b; i < e; ++i) new (p + i) ReadState(); }); }
-		~ReadArray() { parallel_chunks(n, T, [&](size_t b, size_t e, int) { for (size_t i = b; i < e; ++i) p[i].~ReadState(); }); free(p); }
+		ReadState *p; size_t n; decltype(par_reads) &par;
+		ReadArray(size_t n_, decltype(par_reads) &par_) : p((ReadState*)malloc(sizeof(ReadState) * std::max<size_t>(n_, 1))), n(n_), par(par_)
+		{ par([&](size_t b, size_t e, int) { for (size_t i = b; i < e; ++i) new (p + i) ReadState(); }); }
+		~ReadArray() { par([&](size_t b, size_t e, int) { for (size_t i = b; i < e; ++i) p[i].~ReadState(); }); free(p); }
 		ReadState &operator[](size_t i) { return p[i]; }
-	} rs(n_reads, T);
-	parallel_chunks(n_reads, T, [&](size_t b, size_t e, int) {
+	} rs(n_reads, par_reads);
+	par_reads([&](size_t b, size_t e, int) {
 		for (size_t i = b; i < e; ++i) {
 			ReadState &r = rs[i];
 			r.rec = &recs[i];
@@ -900,11 +1010,12 @@ bool AlnPipeline::align_block(const std::vector<FastqRec> &recs, std::vector<Pai
 			r.has_n = memchr(recs[i].seq, 'N', recs[i].seq_l) != nullptr;
 		}
 	});
+	Impl::CensusScratch census_main;
 	auto prepare_read = [&](ReadState &r) {                                   // encode + pack + STR census
 		I.encode(r);
 		const size_t words = (size_t)(r.read_l >> 5) + 2;
 		for (int s = 0; s < 2; ++s) { r.bits[s].assign(words, 0); Impl::pack64(r.bin[s], r.bits[s], 0); }
-		I.str_census(r, r.bits[0].data());
+		I.str_census(r, r.bits[0].data(), census_main);
 	};
 	auto register_jobs = [&](ReadState &r, SeedBatch &sb) {
 		for (int s = 0; s < 2; ++s) {
@@ -916,21 +1027,20 @@ bool AlnPipeline::align_block(const std::vector<FastqRec> &recs, std::vector<Pai
 			sb.jobs.push_back(j);
 		}
 	};
-	auto merge_read = [&](ReadState &r, const SeedBatch &b) {                // stage C, part 1: no random numbers
+	auto merge_read = [&](ReadState &r, SeedBatch &b) {                      // stage C, part 1: no random numbers
 		r.needs_rand = false;
 		for (int s = 0; s < 2; ++s) {
 			const int j = r.job[s];
-			std::vector<Mem> mems(b.mems.begin() + b.mem_off[j], b.mems.begin() + b.mem_off[j + 1]);
-			I.merge_mems(mems, r.vu[s]);
+			I.merge_mems(b.mems.data() + b.mem_off[j], b.mem_off[j + 1] - b.mem_off[j], r.vu[s]);
 			for (const VertexU &u : r.vu[s]) if (u.pos_n > POS_N_MAX) r.needs_rand = true;
 		}
 	};
-	auto chain_read = [&](ReadState &r, size_t i) {                          // stage C, part 2: expand + chain
+	auto chain_read = [&](ReadState &r, size_t i, std::vector<Edge> &edges) {   // stage C, part 2: expand + chain
 		for (int s = 0; s < 2; ++s) {
 			Graph &g = r.g[s];
 			g.v.clear(); g.is_str = r.is_str;
 			I.expand(r.vu[s], g.v, rand_r_[i & 1]);
-			I.chain(g);
+			I.chain(g, edges);
 		}
 	};
 	SeedBatch sb;
@@ -945,7 +1055,8 @@ bool AlnPipeline::align_block(const std::vector<FastqRec> &recs, std::vector<Pai
 		}
 		sb.bits.assign(word_off[n_reads], 0);
 		sb.jobs.resize(job_of[n_reads]);
-		parallel_chunks(n_reads, T, [&](size_t b, size_t e, int) {
+		par_reads([&](size_t b, size_t e, int) {
+			Impl::CensusScratch census;
 			for (size_t i = b; i < e; ++i) {
 				ReadState &r = rs[i];
 				if (!r.batched) continue;
@@ -958,7 +1069,7 @@ bool AlnPipeline::align_block(const std::vector<FastqRec> &recs, std::vector<Pai
 					j.bits_off = off; j.read_len = (uint32_t)r.read_l; j.is_str = 0; j.list_off = 0;
 					r.job[s] = (int)(job_of[i] + s);
 				}
-				I.str_census(r, sb.bits.data() + word_off[i]);
+				I.str_census(r, sb.bits.data() + word_off[i], census);
 			}
 		});
 		for (size_t i = 0; i < n_reads; ++i) {                               // STR reads are rare: their seed lists are appended in order
@@ -977,24 +1088,28 @@ bool AlnPipeline::align_block(const std::vector<FastqRec> &recs, std::vector<Pai
 	stats.mems += sb.mems.size();
 	stats.t_stage[1] += now() - t0; t0 = now();
 	// ---- stage C: reads whose expansion draws from the per-handler random_r stream go in input order, the rest in parallel
-	parallel_chunks(n_reads, T, [&](size_t b, size_t e, int) {
+	par_reads([&](size_t b, size_t e, int) {
+		std::vector<Edge> edges;
 		for (size_t i = b; i < e; ++i) {
 			ReadState &r = rs[i];
 			if (!r.batched) continue;
 			merge_read(r, sb);
-			if (!r.needs_rand) chain_read(r, i);
+			if (!r.needs_rand) chain_read(r, i, edges);
 		}
 	});
-	for (size_t i = 0; i < n_reads; ++i) if (rs[i].batched && rs[i].needs_rand) chain_read(rs[i], i);
+	std::vector<Edge> edges_main;
+	Impl::PlanScratch plan_main;
+	for (size_t i = 0; i < n_reads; ++i) if (rs[i].batched && rs[i].needs_rand) chain_read(rs[i], i, edges_main);
 	stats.t_stage[2] += now() - t0; t0 = now();
 	// ---- stage D: per-thread task lists, concatenated afterwards
 	KswTaskList tasks;
 	{
 		std::vector<KswTaskList> part((size_t)T);
 		std::vector<size_t> lo((size_t)T, 0), hi((size_t)T, 0);
-		parallel_chunks(n_reads, T, [&](size_t b, size_t e, int t) {
+		par_reads([&](size_t b, size_t e, int t) {
 			lo[t] = b; hi[t] = e;
-			for (size_t i = b; i < e; ++i) if (rs[i].batched) I.plan_read(rs[i], part[t]);
+			Impl::PlanScratch scratch;
+			for (size_t i = b; i < e; ++i) if (rs[i].batched) I.plan_read(rs[i], part[t], scratch);
 		});
 		for (int t = 0; t < T; ++t) {
 			const int base = (int)tasks.qlen.size();
@@ -1036,7 +1151,7 @@ bool AlnPipeline::align_block(const std::vector<FastqRec> &recs, std::vector<Pai
 		stats.ksw_tasks += n;
 		{
 			std::atomic<uint64_t> cells(0);
-			parallel_chunks(n, T, [&](size_t b, size_t e, int) { uint64_t c = 0; for (size_t i = b; i < e; ++i) c += (uint64_t)pansvr_ksw_band_cells(tl.qlen[i], tl.tlen[i], kp.w); cells += c; });
+			parallel(n, [&](size_t b, size_t e, int) { uint64_t c = 0; for (size_t i = b; i < e; ++i) c += (uint64_t)pansvr_ksw_band_cells(tl.qlen[i], tl.tlen[i], kp.w); cells += c; });
 			stats.ksw_cells += cells.load();
 		}
 		return true;
@@ -1044,9 +1159,30 @@ bool AlnPipeline::align_block(const std::vector<FastqRec> &recs, std::vector<Pai
 	if (!run_ksw(tasks)) return false;
 	stats.t_stage[4] += now() - t0; t0 = now();
 
-	// ---- stage F: replay in input order (everything that consumes rand()), then the SAM text
+	// ---- stage F: chain selection, result sort and pairing.  Only exact ties consume rand() (RR:247, RRH:553), so every
+	// pair is first finished on a worker thread against a probe; pairs that asked for a random number, and the deferred
+	// pairs, are then replayed in input order against the real stream -- the stream sees exactly the reference's calls.
 	std::vector<Impl::PE> pes(n_pairs);
+	std::vector<uint8_t> redo(n_pairs, 0);
+	parallel(n_pairs, [&](size_t pb, size_t pe_, int) {
+		RandTap probe;
+		for (size_t pi = pb; pi < pe_; ++pi) {
+			ReadState *se = &rs[2 * pi];
+			if (se[0].has_n || se[1].has_n) { redo[pi] = 1; continue; }
+			probe.calls = 0;
+			for (int k = 0; k < 2; ++k) I.finish_read(se[k], tasks, probe);
+			if (probe.calls) { redo[pi] = 1; continue; }
+			I.pair_up(se, pes[pi], probe);
+			if (probe.calls) { redo[pi] = 2; continue; }                     // the candidate lists stand, only the pairing tie is redrawn
+			if (pes[pi].gain) I.set_primary(se, pes[pi]);
+		}
+	});
+	const double t_probe = now() - t0;
+	size_t n_redo = 0;
+	RandTap real; real.real = &rand_;
 	for (size_t pi = 0; pi < n_pairs; ++pi) {
+		if (!redo[pi]) continue;
+		++n_redo;
 		ReadState *se = &rs[2 * pi];
 		if (se[0].has_n || se[1].has_n) {                                 // deferred pair: rand() position is only known now
 			++stats.deferred_pairs;
@@ -1060,27 +1196,26 @@ bool AlnPipeline::align_block(const std::vector<FastqRec> &recs, std::vector<Pai
 					if (!seed_service_run(seeds_, one, err)) return false;
 					stats.mems += one.mems.size();
 					merge_read(r, one);
-					chain_read(r, 2 * pi + k);
-					I.plan_read(r, local);
+					chain_read(r, 2 * pi + k, edges_main);
+					I.plan_read(r, local, plan_main);
 					if (!run_ksw(local)) return false;
 				}
-				I.finish_read(r, local);
+				I.finish_read(r, local, real);
 			}
-		} else {
-			for (int k = 0; k < 2; ++k) I.finish_read(se[k], tasks);
+		} else if (redo[pi] == 1) {
+			for (int k = 0; k < 2; ++k) I.finish_read(se[k], tasks, real);
 		}
-		I.pair_up(se, pes[pi]);
+		I.pair_up(se, pes[pi], real);
 		if (pes[pi].gain) I.set_primary(se, pes[pi]);
-		stats.reads += 2;
 	}
-	if (getenv("PANSVR_TIMING")) fprintf(stderr, "[timing] replay %.3f s\n", now() - t0);
+	stats.reads += 2 * n_pairs;
+	if (getenv("PANSVR_TIMING")) fprintf(stderr, "[timing] finish: probe %.3f s, in-order replay of %zu/%zu pairs %.3f s\n", t_probe, n_redo, n_pairs, now() - t0 - t_probe);
 	// ---- SAM text of every pair (no random numbers involved any more: parallel)
-	parallel_chunks(n_pairs, T, [&](size_t pb, size_t pe_, int) {
+	parallel(n_pairs, [&](size_t pb, size_t pe_, int) {
 		for (size_t pi = pb; pi < pe_; ++pi) {
 			ReadState *se = &rs[2 * pi];
 			const Impl::PE &pe = pes[pi];
 			PairOutput &po = out[pi];
-			for (int k = 0; k < 2; ++k) { se[k].seq.assign(se[k].rec->seq, se[k].rec->seq_l); se[k].qual.assign(se[k].rec->qual, se[k].rec->qual_l); }
 			if (pe.gain)
 				for (int k = 0; k < 2; ++k) I.output_bam(se[k], po.sam[k], k == 0, pe.cur_isize);
 			if (pe.max_score <= min_filter_score_ && (int)se[0].ori.chr != -1 && (int)se[1].ori.chr != -1) {   // RR:776-797
@@ -1102,6 +1237,7 @@ bool AlnPipeline::align_block(const std::vector<FastqRec> &recs, std::vector<Pai
 		}
 	});
 	stats.t_stage[5] += now() - t0;
+	if (getenv("PANSVR_TIMING")) { double a = 0; for (int i = 0; i < 6; ++i) a += stats.t_stage[i]; fprintf(stderr, "[timing] align_block body done, stages A-F %.3f s\n", a); }
 	return true;
 }
 

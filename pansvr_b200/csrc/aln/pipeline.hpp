@@ -21,6 +21,7 @@
 // The output is defined against `panSVR fc_aln -t 1` (the only deterministic mode).
 #pragma once
 #include <stdint.h>
+#include <functional>
 #include <map>
 #include <string>
 #include <vector>
@@ -76,6 +77,11 @@ struct CigarPath { uint8_t type; int16_t size; };
 class AlnPipeline {
 public:
 	AlnPipeline(const DebgaIndex &idx, const AlnOptions &opt, SeedService *seeds, void *ksw_ctx);
+	~AlnPipeline();
+	AlnPipeline(const AlnPipeline&) = delete;
+	AlnPipeline &operator=(const AlnPipeline&) = delete;
+	// static-chunk parallel loop over [0,n) on the pipeline's helper threads: fn(begin, end, chunk_index)
+	void parallel(size_t n, const std::function<void(size_t, size_t, int)> &fn);
 	// Aligns n_pairs interleaved pairs (recs[2i], recs[2i+1]); out[i] receives the SAM text of pair i.
 	bool align_block(const std::vector<FastqRec> &recs, std::vector<PairOutput> &out, std::string &err);
 	void reset();                     // back to the state of a freshly started `fc_aln` (rand() streams, counters)
@@ -84,6 +90,8 @@ public:
 	AlnOptions opt;                   // stat_set / read_len / isize_* are filled from the first comment
 private:
 	struct Impl;
+	struct Workers;
+	Workers *workers_ = nullptr;
 	const DebgaIndex &idx_;
 	SeedService *seeds_;
 	void *ksw_;
