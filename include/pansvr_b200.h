@@ -168,12 +168,24 @@ const char *pansvr_aln_last_error(void);
  * BAM in the comment).  *sam / *ori receive malloc'ed, NUL-terminated SAM body text (records only) of the main output
  * and of the `-p` output; free with pansvr_free.  The rand() replay state carries over from block to block. */
 int  pansvr_aln_block(pansvr_aln_ctx *ctx, const char *fastq, size_t fastq_bytes, char **sam, size_t *sam_bytes, char **ori, size_t *ori_bytes);
+/* Same block, BAM records instead of text: *bam / *ori receive the concatenated records exactly as htslib's bam_write1
+ * hands them to BGZF after sam_parse1 (little-endian [block_size][refID,pos,bin_mq_nl,flag_nc,l_seq,next_refID,next_pos,tlen]
+ * [read_name][cigar][seq][qual][aux]); replaces sam_parse1 in output_BAM / output_ori_bam (read_realignment.cpp:479-536,656-717). */
+int  pansvr_aln_block_bam(pansvr_aln_ctx *ctx, const char *fastq, size_t fastq_bytes, uint8_t **bam, size_t *bam_bytes, uint8_t **ori, size_t *ori_bytes);
+/* BAM file writer: hts_open(path, "wb") + sam_hdr_write, sam_write1 per record, hts_close (read_realignment.cpp:85-94,
+ * 165-175).  BGZF blocks are cut where htslib 1.9 cuts them and deflated at zlib's default level on the context's helper
+ * threads, so the file equals the reference's byte for byte (same zlib).  `records` = output of pansvr_aln_block_bam. */
+typedef struct pansvr_bam_file pansvr_bam_file;
+int  pansvr_bam_open(pansvr_aln_ctx *ctx, const char *path, pansvr_bam_file **out);
+int  pansvr_bam_write(pansvr_bam_file *f, const uint8_t *records, size_t bytes);
+int  pansvr_bam_close(pansvr_bam_file *f);
 int  pansvr_aln_last_stats(const pansvr_aln_ctx *ctx, pansvr_aln_stats_t *out);
 /* Puts the replay back to the state of a freshly started `fc_aln` (rand() streams, counters); the index stays resident. */
 int  pansvr_aln_reset(pansvr_aln_ctx *ctx);
 void pansvr_free(void *p);
 /* Same command line as `panSVR fc_aln` (classify_main, src/main.cpp:18-25): [options] <IndexDir> <reads.fq|-> <header.sam>.
- * -S (SAM) output only. */
+ * Writes BAM, or SAM text with -S, like the reference; -d <gpu> selects the device; -t is the number of host helper threads
+ * (the output is that of the reference's `-t 1`, the only deterministic mode). */
 int  pansvr_fc_aln_main(int argc, char **argv);
 
 #ifdef __cplusplus

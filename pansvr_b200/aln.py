@@ -31,6 +31,10 @@ def _bind(lib):
     lib.pansvr_aln_last_error.restype = C.c_char_p
     lib.pansvr_aln_block.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t),
                                      C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
+    lib.pansvr_aln_block_bam.argtypes = lib.pansvr_aln_block.argtypes
+    lib.pansvr_bam_open.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_void_p)]
+    lib.pansvr_bam_write.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t]
+    lib.pansvr_bam_close.argtypes = [C.c_void_p]
     lib.pansvr_aln_last_stats.argtypes = [C.c_void_p, C.POINTER(AlnStatsC)]
     lib.pansvr_aln_reset.argtypes = [C.c_void_p]
     lib.pansvr_free.argtypes = [C.c_void_p]
@@ -61,6 +65,31 @@ class AlnContext:
             return C.string_at(s, sl.value), C.string_at(o, ol.value)
         finally:
             self.lib.pansvr_free(s); self.lib.pansvr_free(o)
+
+    def align_fastq_bam(self, fastq: bytes):
+        """Like align_fastq, records in uncompressed BAM form (what htslib's bam_write1 hands to BGZF)."""
+        s, o = C.c_void_p(), C.c_void_p()
+        sl, ol = C.c_size_t(), C.c_size_t()
+        rc = self.lib.pansvr_aln_block_bam(self.h, fastq, len(fastq), C.byref(s), C.byref(sl), C.byref(o), C.byref(ol))
+        if rc != 0:
+            raise RuntimeError(f"pansvr_aln_block_bam failed ({rc}): {self.lib.pansvr_aln_last_error().decode()}")
+        try:
+            return C.string_at(s, sl.value), C.string_at(o, ol.value)
+        finally:
+            self.lib.pansvr_free(s); self.lib.pansvr_free(o)
+
+    def write_bam(self, path: str, record_chunks) -> None:
+        """BAM file = header + the given chunks of records (outputs of align_fastq_bam), BGZF-compressed like htslib does."""
+        f = C.c_void_p()
+        if self.lib.pansvr_bam_open(self.h, path.encode(), C.byref(f)) != 0:
+            raise RuntimeError(self.lib.pansvr_aln_last_error().decode())
+        try:
+            for chunk in record_chunks:
+                if self.lib.pansvr_bam_write(f, chunk, len(chunk)) != 0:
+                    raise RuntimeError(self.lib.pansvr_aln_last_error().decode())
+        finally:
+            if self.lib.pansvr_bam_close(f) != 0:
+                raise RuntimeError(self.lib.pansvr_aln_last_error().decode())
 
     def reset(self):
         self.lib.pansvr_aln_reset(self.h)

@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "../../../include/pansvr_b200.h"
+#include "bam_out.hpp"
 #include "pipeline.hpp"
 
 using namespace pansvr;
@@ -23,6 +24,13 @@ struct pansvr_aln_ctx {
 	SeedService *seeds = nullptr;
 	pansvr_ksw_ctx *ksw = nullptr;
 	AlnPipeline *pipe = nullptr;
+	BamHeaderInfo bam_hdr;
+};
+
+struct pansvr_bam_file {
+	FILE *f = nullptr;
+	BamWriter *w = nullptr;
+	~pansvr_bam_file() { delete w; if (f) fclose(f); }
 };
 
 namespace {
@@ -95,6 +103,7 @@ int pansvr_aln_create(const char *index_dir, const char *header_sam, const pansv
 	c->seeds = seed_service_create(c->idx, device, err);
 	if (!c->seeds) { g_aln_err = err; pansvr_ksw_destroy(c->ksw); delete c; return PANSVR_E_CUDA; }
 	c->pipe = new AlnPipeline(c->idx, c->opt, c->seeds, c->ksw);
+	c->bam_hdr.parse(c->idx.header_text);
 	*out = c;
 	return 0;
 }
@@ -111,33 +120,44 @@ void pansvr_aln_destroy(pansvr_aln_ctx *c)
 const char *pansvr_aln_header_text(const pansvr_aln_ctx *c) { return c ? c->idx.header_text.c_str() : ""; }
 const char *pansvr_aln_last_error(void) { return g_aln_err.c_str(); }
 
-int pansvr_aln_block(pansvr_aln_ctx *c, const char *fastq, size_t n, char **sam, size_t *sam_bytes, char **ori, size_t *ori_bytes)
+namespace {
+
+// parse + align one block; `outp` receives the record text of every pair
+int run_block(pansvr_aln_ctx *c, const char *fastq, size_t n, std::vector<PairOutput> &outp)
 {
-	if (!c || !fastq || !sam || !ori) return PANSVR_E_ARG;
 	const auto tick = []() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
-	const double t_enter = tick();
-	double t_sum0 = 0;
-	for (int i = 0; i < 8; ++i) t_sum0 += c->pipe->stats.t_stage[i];
-	struct Report {                                             // PANSVR_TIMING=1: wall time of the call next to the sum of its stages
-		pansvr_aln_ctx *c; double t_enter, t_sum0;
-		~Report()
-		{
-			if (!getenv("PANSVR_TIMING")) return;
-			double s = 0;
-			for (int i = 0; i < 8; ++i) s += c->pipe->stats.t_stage[i];
-			const double now = std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
-			fprintf(stderr, "[timing] pansvr_aln_block %.3f s, stages %.3f s\n", now - t_enter, s - t_sum0);
-		}
-	} report{c, t_enter, t_sum0};
-	double t0 = tick();
+	const double t0 = tick();
 	std::vector<FastqRec> recs;
 	parse_fastq(fastq, n, recs);
 	c->pipe->stats.t_stage[6] += tick() - t0;
-	std::vector<PairOutput> outp;
 	std::string err;
 	if (!c->pipe->align_block(recs, outp, err)) { g_aln_err = err; return PANSVR_E_CUDA; }
-	if (getenv("PANSVR_TIMING")) fprintf(stderr, "[timing] align_block returned at %.3f s\n", tick() - t_enter);
-	t0 = tick();
+	return 0;
+}
+
+struct CallReport {                                           // PANSVR_TIMING=1: wall time of the call next to the sum of its stages
+	pansvr_aln_ctx *c; double t_enter, t_sum0;
+	static double now() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+	explicit CallReport(pansvr_aln_ctx *c_) : c(c_), t_enter(now()), t_sum0(0) { for (int i = 0; i < 8; ++i) t_sum0 += c->pipe->stats.t_stage[i]; }
+	~CallReport()
+	{
+		if (!getenv("PANSVR_TIMING")) return;
+		double s = 0;
+		for (int i = 0; i < 8; ++i) s += c->pipe->stats.t_stage[i];
+		fprintf(stderr, "[timing] block call %.3f s, stages %.3f s\n", now() - t_enter, s - t_sum0);
+	}
+};
+
+} // namespace
+
+int pansvr_aln_block(pansvr_aln_ctx *c, const char *fastq, size_t n, char **sam, size_t *sam_bytes, char **ori, size_t *ori_bytes)
+{
+	if (!c || !fastq || !sam || !ori) return PANSVR_E_ARG;
+	CallReport report(c);
+	std::vector<PairOutput> outp;
+	const int rc = run_block(c, fastq, n, outp);
+	if (rc != 0) return rc;
+	const double t0 = CallReport::now();
 	// total sizes, then every pair copies its records to its own offset (parallel)
 	const size_t np = outp.size();
 	std::vector<size_t> off_s(np + 1, 0), off_o(np + 1, 0);
@@ -162,8 +182,84 @@ int pansvr_aln_block(pansvr_aln_ctx *c, const char *fastq, size_t n, char **sam,
 	*sam = sbuf; *ori = obuf;
 	if (sam_bytes) *sam_bytes = off_s[np];
 	if (ori_bytes) *ori_bytes = off_o[np];
-	c->pipe->stats.t_stage[7] += tick() - t0;
-	if (getenv("PANSVR_TIMING")) fprintf(stderr, "[timing] emit done at %.3f s\n", tick() - t_enter);
+	c->pipe->stats.t_stage[7] += CallReport::now() - t0;
+	return 0;
+}
+
+// Same block, records in BAM form: every record as bam_write1 hands it to BGZF ([block_size][core][name][cigar][seq][qual][aux]).
+int pansvr_aln_block_bam(pansvr_aln_ctx *c, const char *fastq, size_t n, uint8_t **bam, size_t *bam_bytes, uint8_t **ori, size_t *ori_bytes)
+{
+	if (!c || !fastq || !bam || !ori) return PANSVR_E_ARG;
+	CallReport report(c);
+	std::vector<PairOutput> outp;
+	const int rc = run_block(c, fastq, n, outp);
+	if (rc != 0) return rc;
+	const double t0 = CallReport::now();
+	const size_t np = outp.size();
+	const int T = std::max(1, c->opt.threads);
+	std::vector<std::vector<uint8_t>> part_s((size_t)T), part_o((size_t)T);
+	std::vector<std::string> errs((size_t)T);
+	c->pipe->parallel(np, [&](size_t b, size_t e, int t) {
+		for (size_t i = b; i < e && errs[t].empty(); ++i)
+			for (int k = 0; k < 2; ++k) {
+				const std::string &x = outp[i].sam[k], &y = outp[i].ori[k];
+				if (!x.empty() && !bam_encode_record(x.data(), x.size(), c->bam_hdr, part_s[t], errs[t])) break;
+				if (!y.empty() && !bam_encode_record(y.data(), y.size(), c->bam_hdr, part_o[t], errs[t])) break;
+			}
+	});
+	for (const std::string &e : errs) if (!e.empty()) { g_aln_err = e; return PANSVR_E_ARG; }
+	auto join = [&](std::vector<std::vector<uint8_t>> &parts, uint8_t **out, size_t *bytes) -> bool {
+		size_t tot = 0;
+		for (auto &p : parts) tot += p.size();
+		uint8_t *buf = (uint8_t*)malloc(tot + 1);
+		if (!buf) return false;
+		size_t off = 0;
+		for (auto &p : parts) { if (!p.empty()) memcpy(buf + off, p.data(), p.size()); off += p.size(); }
+		*out = buf;
+		if (bytes) *bytes = tot;
+		return true;
+	};
+	if (!join(part_s, bam, bam_bytes) || !join(part_o, ori, ori_bytes)) { g_aln_err = "out of memory"; return PANSVR_E_ARG; }
+	c->pipe->stats.t_stage[7] += CallReport::now() - t0;
+	return 0;
+}
+
+// ---- BAM files (hts_open(.., "wb") + sam_hdr_write + sam_write1 + hts_close of the reference, RR:85-94,165-175)
+int pansvr_bam_open(pansvr_aln_ctx *c, const char *path, pansvr_bam_file **out)
+{
+	if (!c || !path || !out) return PANSVR_E_ARG;
+	*out = nullptr;
+	pansvr_bam_file *b = new pansvr_bam_file();
+	b->f = fopen(path, "wb");
+	if (!b->f) { g_aln_err = std::string("cannot open ") + path; delete b; return PANSVR_E_ARG; }
+	AlnPipeline *pipe = c->pipe;
+	b->w = new BamWriter(b->f, [pipe](size_t n, const std::function<void(size_t, size_t, int)> &fn) { pipe->parallel(n, fn); });
+	if (!b->w->write_header(c->bam_hdr)) { g_aln_err = "BAM header write failed"; delete b; return PANSVR_E_ARG; }
+	*out = b;
+	return 0;
+}
+
+int pansvr_bam_write(pansvr_bam_file *b, const uint8_t *records, size_t bytes)
+{
+	if (!b || (!records && bytes)) return PANSVR_E_ARG;
+	std::vector<uint32_t> sizes;
+	for (size_t off = 0; off < bytes;) {
+		if (off + 4 > bytes) { g_aln_err = "truncated BAM record stream"; return PANSVR_E_ARG; }
+		uint32_t bl; memcpy(&bl, records + off, 4);
+		if (off + 4 + bl > bytes) { g_aln_err = "truncated BAM record stream"; return PANSVR_E_ARG; }
+		sizes.push_back(4 + bl);
+		off += 4 + (size_t)bl;
+	}
+	if (!b->w->write_records(records, sizes)) { g_aln_err = "BAM write failed"; return PANSVR_E_ARG; }
+	return 0;
+}
+
+int pansvr_bam_close(pansvr_bam_file *b)
+{
+	if (!b) return PANSVR_E_ARG;
+	const bool ok = b->w->close();
+	delete b;
+	if (!ok) { g_aln_err = "BAM close failed"; return PANSVR_E_ARG; }
 	return 0;
 }
 
@@ -227,14 +323,20 @@ int pansvr_fc_aln_main(int argc, char **argv)
 		fprintf(stderr, "Usage: fc_aln [Options] <IndexDir> <ReadFiles.fq|-> <ori_header.sam>\n");
 		return 1;
 	}
-	if (!sam) { fprintf(stderr, "pansvr_b200 fc_aln: only SAM output (-S) is implemented\n"); return 1; }
 	pansvr_aln_ctx *ctx = nullptr;
 	int rc = pansvr_aln_create(argv[optind], argv[optind + 2], &o, device, &ctx);
 	if (rc != 0) { fprintf(stderr, "pansvr_b200 fc_aln: %s\n", pansvr_aln_last_error()); return 1; }
-	FILE *fo = fopen(out_path.c_str(), "w"), *fp = fopen(ori_path.c_str(), "w");
-	if (!fo || !fp) { fprintf(stderr, "pansvr_b200 fc_aln: cannot open the output files\n"); return 1; }
-	fputs(pansvr_aln_header_text(ctx), fo);
-	fputs(pansvr_aln_header_text(ctx), fp);
+	FILE *fo = nullptr, *fp = nullptr;
+	pansvr_bam_file *bo = nullptr, *bp = nullptr;
+	if (sam) {
+		fo = fopen(out_path.c_str(), "w"); fp = fopen(ori_path.c_str(), "w");
+		if (!fo || !fp) { fprintf(stderr, "pansvr_b200 fc_aln: cannot open the output files\n"); return 1; }
+		fputs(pansvr_aln_header_text(ctx), fo);
+		fputs(pansvr_aln_header_text(ctx), fp);
+	} else if (pansvr_bam_open(ctx, out_path.c_str(), &bo) != 0 || pansvr_bam_open(ctx, ori_path.c_str(), &bp) != 0) {
+		fprintf(stderr, "pansvr_b200 fc_aln: %s\n", pansvr_aln_last_error());
+		return 1;
+	}
 	gzFile in = strcmp(argv[optind + 1], "-") == 0 ? gzdopen(0, "r") : gzopen(argv[optind + 1], "r");
 	if (!in) { fprintf(stderr, "pansvr_b200 fc_aln: cannot open %s\n", argv[optind + 1]); return 1; }
 	// blocks of at most 2 M pairs / 100 Mbp like load_reads (RR:109,126)
@@ -244,10 +346,20 @@ int pansvr_fc_aln_main(int argc, char **argv)
 	const long max_pairs = o.max_use_read > 0 ? o.max_use_read : 0x7fffffff;
 	auto flush = [&]() -> bool {
 		if (block.empty()) return true;
-		char *s = nullptr, *r = nullptr; size_t sl = 0, rl = 0;
-		if (pansvr_aln_block(ctx, block.data(), block.size(), &s, &sl, &r, &rl) != 0) { fprintf(stderr, "pansvr_b200 fc_aln: %s\n", pansvr_aln_last_error()); return false; }
-		fwrite(s, 1, sl, fo); fwrite(r, 1, rl, fp);
-		pansvr_free(s); pansvr_free(r);
+		if (sam) {
+			char *s = nullptr, *r = nullptr; size_t sl = 0, rl = 0;
+			if (pansvr_aln_block(ctx, block.data(), block.size(), &s, &sl, &r, &rl) != 0) { fprintf(stderr, "pansvr_b200 fc_aln: %s\n", pansvr_aln_last_error()); return false; }
+			fwrite(s, 1, sl, fo); fwrite(r, 1, rl, fp);
+			pansvr_free(s); pansvr_free(r);
+		} else {
+			uint8_t *s = nullptr, *r = nullptr; size_t sl = 0, rl = 0;
+			if (pansvr_aln_block_bam(ctx, block.data(), block.size(), &s, &sl, &r, &rl) != 0 ||
+			    pansvr_bam_write(bo, s, sl) != 0 || pansvr_bam_write(bp, r, rl) != 0) {
+				fprintf(stderr, "pansvr_b200 fc_aln: %s\n", pansvr_aln_last_error());
+				return false;
+			}
+			pansvr_free(s); pansvr_free(r);
+		}
 		block.clear(); pairs_in_block = 0; bases = 0;
 		return true;
 	};
@@ -265,7 +377,8 @@ int pansvr_fc_aln_main(int argc, char **argv)
 	}
 	if (ok) ok = flush();
 	gzclose(in);
-	fclose(fo); fclose(fp);
+	if (sam) { fclose(fo); fclose(fp); }
+	else if (pansvr_bam_close(bo) != 0 || pansvr_bam_close(bp) != 0) { fprintf(stderr, "pansvr_b200 fc_aln: %s\n", pansvr_aln_last_error()); ok = false; }
 	pansvr_aln_stats_t st;
 	pansvr_aln_last_stats(ctx, &st);
 	fprintf(stderr, "pansvr_b200 fc_aln: %ld reads, %ld MEMs, %ld ksw tasks; stage seconds A %.3f B %.3f C %.3f D %.3f E %.3f F %.3f parse %.3f emit %.3f\n",

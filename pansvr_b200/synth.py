@@ -172,6 +172,37 @@ def config4_batch(n: int, kind: str = "ext", seed: int = 13, pool_bases: int = 1
     return KswBatch(np.concatenate(qs), qoff, qlens, pool, toff, tlens, KswParams(w=w), name=f"config4_global_w{w}")
 
 
+def fcsv_batch(n: int, seed: int = 19, pool_bases: int = 1 << 23) -> KswBatch:
+    """the `fc_sv` contig alignments (SignalAssembly.hpp:411-421,459-464; SignalAssembly.cpp:822-831).
+
+    An assembled contig of 200-1500 bp against the anchor window it was assembled over, the window reaching 60 bp past
+    the contig's expected end; scoring 2/-10, gaps min(24+2k, 32+1k), w = zdrop = 132, flag 0.  Half of the contigs
+    carry one SV-sized indel (30-300 bp) relative to the window, all carry ~0.5 % substitutions."""
+    rng = np.random.default_rng(seed)
+    pool = rng.integers(0, 4, size=pool_bases + 4096, dtype=np.uint8)
+    toff = rng.integers(0, pool_bases, size=n, dtype=np.int64)
+    qs, qlens, tlens = [], np.empty(n, np.int32), np.empty(n, np.int32)
+    for i in range(n):
+        L = int(rng.integers(200, 1501))
+        t = pool[toff[i]:toff[i] + L]
+        qv = t.copy()
+        if rng.random() < 0.5:
+            sv = int(rng.integers(30, 301))
+            p = int(rng.integers(60, max(61, qv.size - 60)))
+            if rng.random() < 0.5 and qv.size - sv > 120:
+                qv = np.concatenate([qv[:p], qv[p + sv:]])
+            else:
+                qv = np.concatenate([qv[:p], rng.integers(0, 4, sv, dtype=np.uint8), qv[p:]])
+        sub = rng.random(qv.size) < 0.005
+        qv = np.where(sub, (qv + rng.integers(1, 4, qv.size, dtype=np.uint8)) & 3, qv).astype(np.uint8)
+        qs.append(qv)
+        qlens[i], tlens[i] = qv.size, L + 60
+    qoff = np.zeros(n, np.int64)
+    qoff[1:] = np.cumsum(qlens[:-1])
+    return KswBatch(np.concatenate(qs), qoff, qlens, pool, toff, tlens,
+                    KswParams(mat=dna_matrix(2, 10), q=24, e=2, q2=32, e2=1, w=132, zdrop=132), name="fc_sv_contigs")
+
+
 def pipeline_like_batch(n: int, seed: int = 17, pool_bases: int = 1 << 22) -> KswBatch:
     """Task shapes fc_aln really emits: extensions with qlen p50 26 / p90 90 / max 121 and
     tlen = qlen + 30, plus short end-to-end gaps (qlen, tlen <= 50), w=200, zdrop=400, flag=0."""

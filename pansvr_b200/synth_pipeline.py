@@ -158,11 +158,12 @@ def build_anchor_index(d: PipelineData, edge_len: int = 500) -> None:
                               stdout=log, stderr=log)
 
 
-def run_reference_aln(d: PipelineData, out_sam: str, ori_sam: str, threads: int = 1, extra=()) -> float:
-    """`panSVR fc_aln -t N -S` of the reference; returns wall seconds.  threads=1 is the SAM oracle."""
+def run_reference_aln(d: PipelineData, out_sam: str, ori_sam: str, threads: int = 1, extra=(), bam: bool = False) -> float:
+    """`panSVR fc_aln -t N -S` of the reference (BAM files without -S when bam=True); returns wall seconds.
+    threads=1 is the output oracle."""
     import time
     t0 = time.time()
     with open(os.path.join(d.workdir, "fc_aln.log"), "w") as log:
-        subprocess.check_call([os.path.join(REF_BIN, "panSVR"), "fc_aln", "-t", str(threads), "-S", "-o", out_sam, "-p", ori_sam,
-                               *extra, d.index_dir, d.reads_fq, d.header_sam], stdout=log, stderr=log)
+        subprocess.check_call([os.path.join(REF_BIN, "panSVR"), "fc_aln", "-t", str(threads), *(() if bam else ("-S",)),
+                               "-o", out_sam, "-p", ori_sam, *extra, d.index_dir, d.reads_fq, d.header_sam], stdout=log, stderr=log)
     return time.time() - t0

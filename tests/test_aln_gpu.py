@@ -5,7 +5,7 @@ import os
 
 import pytest
 
-from pansvr_b200 import aln
+from pansvr_b200 import aln, synth_pipeline as sp
 from tests.alntest_util import DATASETS, Demo, first_diff, golden, need_ref_tools, read
 
 pytestmark = pytest.mark.gpu
@@ -50,5 +50,17 @@ def test_command_line_and_block_boundaries():
         ctx.close()
         assert hdr + s1 + s2 == read(demo.ref_sam)
         assert hdr + o1 + o2 == read(demo.ref_ori)
+        # BAM mode of the command line (the reference's default output) and the BAM record API written in two calls
+        rb, rbo = os.path.join(demo.wd, "ref.bam"), os.path.join(demo.wd, "ref_ori.bam")
+        sp.run_reference_aln(demo.data, rb, rbo, threads=1, bam=True)
+        mb, mbo = os.path.join(demo.wd, "cli.bam"), os.path.join(demo.wd, "cli_ori.bam")
+        assert aln.fc_aln_main(["-t", "4", "-o", mb, "-p", mbo, demo.data.index_dir, demo.data.reads_fq, demo.data.header_sam]) == 0
+        assert read(mb) == read(rb) and read(mbo) == read(rbo)
+        ctx = aln.AlnContext(demo.data.index_dir, demo.data.header_sam)
+        b1 = ctx.align_fastq_bam(b"\n".join(fq[:half]) + b"\n")
+        b2 = ctx.align_fastq_bam(b"\n".join(fq[half:]))
+        ctx.write_bam(mb, [b1[0], b2[0]])
+        ctx.close()
+        assert read(mb) == read(rb)
     finally:
         demo.cleanup()

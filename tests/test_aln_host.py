@@ -2,11 +2,13 @@
 with host stand-ins for its two device services (tests/emul/aln_host_services.cpp: seed_core.cuh stepped on the host, ksw
 through the oracle) and must reproduce the reference's `fc_aln -t 1 -S` output byte for byte."""
 import ctypes as C
+import gzip
 import os
 import subprocess
 
 import pytest
 
+from pansvr_b200 import synth_pipeline as sp
 from tests.alntest_util import DATASETS, Demo, first_diff, golden, need_ref_tools, read
 
 HERE = os.path.dirname(os.path.abspath(__file__))
@@ -19,8 +21,8 @@ def fc_aln_emul():
     subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle"), os.path.join(ROOT, "oracle", "libksw_oracle.so")])
     env = dict(os.environ, PANSVR_ORACLE_SO=os.path.join(ROOT, "oracle", "libksw_oracle.so"))
 
-    def run(d, out, ori, extra=()):
-        subprocess.check_call([os.path.join(HERE, "emul", "fc_aln_emul"), "-t", "1", "-S", "-o", out, "-p", ori, *extra,
+    def run(d, out, ori, extra=("-S",), threads=1):
+        subprocess.check_call([os.path.join(HERE, "emul", "fc_aln_emul"), "-t", str(threads), "-o", out, "-p", ori, *extra,
                                d.index_dir, d.reads_fq, d.header_sam], env=env, stderr=subprocess.DEVNULL)
     return run
 
@@ -47,6 +49,40 @@ def test_host_pipeline_matches_reference_sam(fc_aln_emul, name):
         if name == "demo":      # and the recorded fixture of the reference's output for this seed
             assert read(demo.ref_sam) == golden("aln_demo.sam.gz")
             assert read(demo.ref_ori) == golden("aln_demo_ori.sam.gz")
+        # BAM mode (the reference's default): whole files byte-identical, BGZF blocks and deflate streams included
+        rb, rbo = os.path.join(demo.wd, "ref.bam"), os.path.join(demo.wd, "ref_ori.bam")
+        sp.run_reference_aln(demo.data, rb, rbo, threads=1, bam=True)
+        mb, mbo = os.path.join(demo.wd, "my.bam"), os.path.join(demo.wd, "my_ori.bam")
+        fc_aln_emul(demo.data, mb, mbo, extra=(), threads=3)
+        assert read(mb) == read(rb) and read(mbo) == read(rbo)
+        assert gzip.decompress(read(mb))[:4] == b"BAM\x01"
+    finally:
+        demo.cleanup()
+
+
+def test_bam_records_and_writer_across_calls(fc_aln_emul):
+    """pansvr_aln_block_bam + pansvr_bam_open/write/close through the C ABI of the host build: records written in several
+    calls (open BGZF block carried over) give the reference's BAM file; every record equals its SAM line re-encoded."""
+    need_ref_tools()
+    from pansvr_b200 import aln
+    os.environ["PANSVR_ORACLE_SO"] = os.path.join(ROOT, "oracle", "libksw_oracle.so")
+    lib = C.CDLL(os.path.join(HERE, "emul", "libaln_emul.so"))
+    demo = Demo("multi_allele")
+    try:
+        rb, rbo = os.path.join(demo.wd, "ref.bam"), os.path.join(demo.wd, "ref_ori.bam")
+        sp.run_reference_aln(demo.data, rb, rbo, threads=1, bam=True)
+        fq = read(demo.data.reads_fq).split(b"\n")
+        cuts = [0, (len(fq) // 8 // 3) * 8, (len(fq) // 8 // 2) * 8, len(fq)]
+        ctx = aln.AlnContext(demo.data.index_dir, demo.data.header_sam, lib=lib, threads=4)
+        chunks = [ctx.align_fastq_bam(b"\n".join(fq[a:b]) + b"\n") for a, b in zip(cuts[:-1], cuts[1:])]
+        mb, mbo = os.path.join(demo.wd, "my.bam"), os.path.join(demo.wd, "my_ori.bam")
+        ctx.write_bam(mb, [c[0] for c in chunks])
+        ctx.write_bam(mbo, [c[1] for c in chunks])
+        ctx.close()
+        assert read(mb) == read(rb) and read(mbo) == read(rbo)
+        # the uncompressed stream is header + exactly our records
+        raw = gzip.decompress(read(rb))
+        assert raw.endswith(b"".join(c[0] for c in chunks))
     finally:
         demo.cleanup()
 

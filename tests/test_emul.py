@@ -44,6 +44,7 @@ CASES = [
     ("rev_cigar_team32", lambda: synth.fuzz_batch(30, 34, max_len=80, params=synth.KswParams(w=64, zdrop=200, flag=0x80)), 32, 0),
     ("zdrop_tight", lambda: synth.fuzz_batch(60, 36, params=synth.KswParams(w=30, zdrop=20)), 0, 0),
     ("tiny_bands", lambda: synth.fuzz_batch(60, 37, max_len=120, params=synth.KswParams(w=2, zdrop=400)), 0, 0),
+    ("fc_sv_contigs", lambda: synth.fcsv_batch(3, pool_bases=1 << 16), 0, 0),
     ("wide_w500", lambda: synth.fuzz_batch(6, 35, max_len=460, params=synth.KswParams(w=500)), 0, 0),
 ]
 

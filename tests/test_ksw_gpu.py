@@ -57,6 +57,14 @@ def test_pipeline_like_and_config4(ksw_ctx):
     assert st["kernel_launches"] >= 1
 
 
+def test_fc_sv_contig_tasks(ksw_ctx):
+    """contig-vs-anchor-window alignments of fc_sv (clipped band, thousands of anti-diagonals)."""
+    b = synth.fcsv_batch(400)
+    res, cig = ksw_ctx.extd2_batch(b, cigar_cap=96)
+    r0, c0, _ = pyoracle.run(b, "oracle", threads=8, cigar_cap=96)
+    assert_same(r0, c0, res, cig, b.name)
+
+
 def test_empty_ragged_and_trivial(ksw_ctx):
     p = synth.KswParams()
     res, cig = ksw_ctx.extd2_batch(synth.KswBatch(np.zeros(0, np.uint8), np.zeros(0, np.int64), np.zeros(0, np.int32),

@@ -25,6 +25,14 @@ def test_oracle_matches_live_reference(seed, w, zdrop, flag):
     assert_same(r0, c0, r1, c1, f"seed {seed}")
 
 
+@pytest.mark.skipif(not pyoracle.have_ref(), reason="oracle/_ref not built (reference sources absent)")
+def test_oracle_matches_live_reference_on_fc_sv_contigs():
+    b = synth.fcsv_batch(60)                                   # SignalAssembly.hpp:411-421,459-464
+    r0, c0, _ = pyoracle.run(b, "ref", threads=4, cigar_cap=128)
+    r1, c1, _ = pyoracle.run(b, "oracle", threads=4, cigar_cap=128)
+    assert_same(r0, c0, r1, c1, b.name)
+
+
 def test_cells_definition():
     # SURVEY.md section 8d table
     assert pyoracle.cells(150, 180, 200) == 27000
