@@ -210,6 +210,13 @@ struct ReadState {
 	bool is_str = false;
 	std::vector<uint8_t> seed_list[2];
 	std::vector<uint64_t> bits[2];             // 32 bases per word, one spare zero word
+	// A read with 1..3 'N' is prepared once per possible substitution ("variant" read states appended after the real ones);
+	// the replay draws the real rand()%4 values and adopts the matching variant.
+	int n_draws = 0;                           // 'N' bases = rand() draws of binary_read_2_bit
+	int64_t var_base = -1;                     // real read: index of its first variant (4^n_draws of them), -1 = none
+	int64_t var_of = -1;                       // variant: index of the real read
+	uint32_t var_code = 0;                     // variant: substitution of the j-th N = (var_code >> 2j) & 3
+	bool in_order_only = false;                // real read: must be prepared during the replay (too many N, or random_r needed)
 	bool batched = false, needs_rand = false;  // needs_rand: a unipath with > 500 positions draws from random_r (expand_seed)
 	std::vector<VertexU> vu[2];
 	int job[2] = {-1, -1};
@@ -301,9 +308,10 @@ struct AlnPipeline::Impl {
 	{
 		const int L = r.read_l;
 		r.bin[0].assign(L, 0); r.bin[1].assign(L, 0);
+		int nth = 0;
 		for (int i = 0; i < L; ++i) {
 			char ch = r.rec->seq[i];
-			if (ch == 'N') ch = "ACGT"[P.rand_.next() % 4];
+			if (ch == 'N') ch = "ACGT"[r.var_of >= 0 ? (r.var_code >> (2 * nth++)) & 3 : (uint32_t)(P.rand_.next() % 4)];
 			const uint8_t c = dna5((unsigned char)ch);
 			r.bin[0][i] = c;
 			r.bin[1][L - i - 1] = c ^ 3;
@@ -991,13 +999,34 @@ bool AlnPipeline::align_block(const std::vector<FastqRec> &recs, std::vector<Pai
 	// per-read state is constructed and destroyed by the worker threads (it is ~0.5 KB of containers per read)
 	// loops over reads are cut at pair boundaries: the same worker owns a pair's two reads in every stage
 	auto par_reads = [&](const std::function<void(size_t, size_t, int)> &fn) { parallel(n_pairs, [&](size_t b, size_t e, int t) { fn(2 * b, 2 * e, t); }); };
+	// 'N' census: a read with 1..3 N gets 4^n variant states behind the real reads (indices n_reads ..)
+	enum { MAX_VARIANT_DRAWS = 3 };
+	std::vector<uint8_t> n_count(n_reads, 0);
+	par_reads([&](size_t b, size_t e, int) {
+		for (size_t i = b; i < e; ++i) {
+			uint32_t c = 0;
+			const char *q = recs[i].seq, *qe = q + recs[i].seq_l;
+			while ((q = (const char*)memchr(q, 'N', (size_t)(qe - q))) != nullptr) { ++c; ++q; }
+			n_count[i] = (uint8_t)std::min<uint32_t>(c, 255);
+		}
+	});
+	std::vector<std::pair<size_t, size_t>> var_src;                       // (real read, first variant index) of reads with variants
+	size_t n_var = 0;
+	for (size_t i = 0; i < n_reads; ++i)
+		if (n_count[i] >= 1 && n_count[i] <= MAX_VARIANT_DRAWS && recs[i].seq_l >= LEN_KMER) { var_src.push_back(std::make_pair(i, n_reads + n_var)); n_var += (size_t)1 << (2 * n_count[i]); }
+	const size_t n_all = n_reads + n_var;
+	// every loop over read states: the real reads in pair chunks, then the variants
+	auto par_all = [&](const std::function<void(size_t, size_t, int)> &fn) {
+		par_reads(fn);
+		if (n_var) parallel(n_var, [&](size_t b, size_t e, int t) { fn(n_reads + b, n_reads + e, t); });
+	};
 	struct ReadArray {
-		ReadState *p; size_t n; decltype(par_reads) &par;
-		ReadArray(size_t n_, decltype(par_reads) &par_) : p((ReadState*)malloc(sizeof(ReadState) * std::max<size_t>(n_, 1))), n(n_), par(par_)
+		ReadState *p; size_t n; decltype(par_all) &par;
+		ReadArray(size_t n_, decltype(par_all) &par_) : p((ReadState*)malloc(sizeof(ReadState) * std::max<size_t>(n_, 1))), n(n_), par(par_)
 		{ par([&](size_t b, size_t e, int) { for (size_t i = b; i < e; ++i) new (p + i) ReadState(); }); }
 		~ReadArray() { par([&](size_t b, size_t e, int) { for (size_t i = b; i < e; ++i) p[i].~ReadState(); }); free(p); }
 		ReadState &operator[](size_t i) { return p[i]; }
-	} rs(n_reads, par_reads);
+	} rs(n_all, par_all);
 	par_reads([&](size_t b, size_t e, int) {
 		for (size_t i = b; i < e; ++i) {
 			ReadState &r = rs[i];
@@ -1007,9 +1036,21 @@ bool AlnPipeline::align_block(const std::vector<FastqRec> &recs, std::vector<Pai
 			I.parse_ori(r);
 			if (r.ori.chr > 24) r.ori_unmapped = true;                    // RR:413
 			r.skip = !r.ori_unmapped && r.ori.align_score == (uint32_t)(r.read_l * opt.match);   // RR:414
-			r.has_n = memchr(recs[i].seq, 'N', recs[i].seq_l) != nullptr;
+			r.n_draws = n_count[i];
+			r.has_n = n_count[i] != 0;
+			r.in_order_only = n_count[i] > MAX_VARIANT_DRAWS;
 		}
 	});
+	for (const auto &vs : var_src) {
+		ReadState &base = rs[vs.first];
+		base.var_base = (int64_t)vs.second;
+		const size_t nv = (size_t)1 << (2 * base.n_draws);
+		for (size_t c = 0; c < nv; ++c) {
+			ReadState &v = rs[vs.second + c];
+			v.rec = base.rec; v.read_l = base.read_l; v.skip = base.skip;
+			v.var_of = (int64_t)vs.first; v.var_code = (uint32_t)c;
+		}
+	}
 	Impl::CensusScratch census_main;
 	auto prepare_read = [&](ReadState &r) {                                   // encode + pack + STR census
 		I.encode(r);
@@ -1045,17 +1086,17 @@ bool AlnPipeline::align_block(const std::vector<FastqRec> &recs, std::vector<Pai
 	};
 	SeedBatch sb;
 	{
-		std::vector<uint32_t> word_off(n_reads + 1, 0), job_of(n_reads + 1, 0);
-		for (size_t i = 0; i < n_reads; ++i) {                               // layout of the packed-read pool (two strands per read)
+		std::vector<uint32_t> word_off(n_all + 1, 0), job_of(n_all + 1, 0);
+		for (size_t i = 0; i < n_all; ++i) {                                 // layout of the packed-read pool (two strands per read)
 			ReadState &r = rs[i];
-			const bool pair_has_n = rs[i & ~(size_t)1].has_n || rs[i | 1].has_n;
-			r.batched = !(r.skip || pair_has_n || r.read_l < LEN_KMER);
+			// a real read with N is not encoded here (its bases depend on the draws); the N-free mate of such a read is
+			r.batched = !(r.skip || r.has_n || r.read_l < LEN_KMER);
 			word_off[i + 1] = word_off[i] + (r.batched ? 2u * (uint32_t)((r.read_l >> 5) + 2) : 0u);
 			job_of[i + 1] = job_of[i] + (r.batched ? 2u : 0u);
 		}
-		sb.bits.assign(word_off[n_reads], 0);
-		sb.jobs.resize(job_of[n_reads]);
-		par_reads([&](size_t b, size_t e, int) {
+		sb.bits.assign(word_off[n_all], 0);
+		sb.jobs.resize(job_of[n_all]);
+		par_all([&](size_t b, size_t e, int) {
 			Impl::CensusScratch census;
 			for (size_t i = b; i < e; ++i) {
 				ReadState &r = rs[i];
@@ -1072,7 +1113,7 @@ bool AlnPipeline::align_block(const std::vector<FastqRec> &recs, std::vector<Pai
 				I.str_census(r, sb.bits.data() + word_off[i], census);
 			}
 		});
-		for (size_t i = 0; i < n_reads; ++i) {                               // STR reads are rare: their seed lists are appended in order
+		for (size_t i = 0; i < n_all; ++i) {                                 // STR reads are rare: their seed lists are appended in order
 			ReadState &r = rs[i];
 			if (!r.batched || !r.is_str) continue;
 			for (int s = 0; s < 2; ++s) {
@@ -1088,7 +1129,7 @@ bool AlnPipeline::align_block(const std::vector<FastqRec> &recs, std::vector<Pai
 	stats.mems += sb.mems.size();
 	stats.t_stage[1] += now() - t0; t0 = now();
 	// ---- stage C: reads whose expansion draws from the per-handler random_r stream go in input order, the rest in parallel
-	par_reads([&](size_t b, size_t e, int) {
+	par_all([&](size_t b, size_t e, int) {
 		std::vector<Edge> edges;
 		for (size_t i = b; i < e; ++i) {
 			ReadState &r = rs[i];
@@ -1100,6 +1141,8 @@ bool AlnPipeline::align_block(const std::vector<FastqRec> &recs, std::vector<Pai
 	std::vector<Edge> edges_main;
 	Impl::PlanScratch plan_main;
 	for (size_t i = 0; i < n_reads; ++i) if (rs[i].batched && rs[i].needs_rand) chain_read(rs[i], i, edges_main);
+	for (size_t i = n_reads; i < n_all; ++i)                               // a variant that needs random_r: its read waits for its turn
+		if (rs[i].batched && rs[i].needs_rand) { rs[rs[i].var_of].in_order_only = true; rs[i].batched = false; }
 	stats.t_stage[2] += now() - t0; t0 = now();
 	// ---- stage D: per-thread task lists, concatenated afterwards
 	KswTaskList tasks;
@@ -1124,6 +1167,8 @@ bool AlnPipeline::align_block(const std::vector<FastqRec> &recs, std::vector<Pai
 			if (base) for (size_t i = lo[t]; i < hi[t]; ++i)
 				for (auto &kv : rs[i].node_aln) for (Piece &pc : kv.second.pieces) if (pc.kind == 1) pc.task += base;
 		}
+		for (size_t i = n_reads; i < n_all; ++i)                           // variants (rare): straight into the joined list
+			if (rs[i].batched && !rs[rs[i].var_of].in_order_only) I.plan_read(rs[i], tasks, plan_main);
 	}
 	stats.t_stage[3] += now() - t0; t0 = now();
 	// ---- stage E
@@ -1178,18 +1223,28 @@ bool AlnPipeline::align_block(const std::vector<FastqRec> &recs, std::vector<Pai
 		}
 	});
 	const double t_probe = now() - t0;
-	size_t n_redo = 0;
+	size_t n_redo = 0, n_in_order = 0;
 	RandTap real; real.real = &rand_;
 	for (size_t pi = 0; pi < n_pairs; ++pi) {
 		if (!redo[pi]) continue;
 		++n_redo;
 		ReadState *se = &rs[2 * pi];
-		if (se[0].has_n || se[1].has_n) {                                 // deferred pair: rand() position is only known now
+		if (se[0].has_n || se[1].has_n) {                                 // deferred pair: its rand() draws happen now
 			++stats.deferred_pairs;
 			KswTaskList local;
+			bool own[2] = {false, false};
 			for (int k = 0; k < 2; ++k) {
 				ReadState &r = se[k];
-				if (!r.skip && r.read_l >= LEN_KMER) {
+				if (r.skip || r.read_l < LEN_KMER || !r.has_n) { /* nothing drawn: skipped, too short, or prepared in the batch */ }
+				else if (r.var_base >= 0 && !r.in_order_only) {                // draw the substitutions, adopt the variant prepared for them
+					uint32_t code = 0;
+					for (int j = 0; j < r.n_draws; ++j) code |= (uint32_t)(rand_.next() % 4) << (2 * j);
+					ReadState &v = rs[(size_t)r.var_base + code];
+					for (int s = 0; s < 2; ++s) { r.bin[s].swap(v.bin[s]); r.vu[s].swap(v.vu[s]); std::swap(r.g[s], v.g[s]); }
+					r.is_str = v.is_str; r.node_aln.swap(v.node_aln);
+				} else {
+					++n_in_order;
+					own[k] = true;
 					SeedBatch one;
 					prepare_read(r);
 					register_jobs(r, one);
@@ -1200,7 +1255,7 @@ bool AlnPipeline::align_block(const std::vector<FastqRec> &recs, std::vector<Pai
 					I.plan_read(r, local, plan_main);
 					if (!run_ksw(local)) return false;
 				}
-				I.finish_read(r, local, real);
+				I.finish_read(r, own[k] ? local : tasks, real);
 			}
 		} else if (redo[pi] == 1) {
 			for (int k = 0; k < 2; ++k) I.finish_read(se[k], tasks, real);
@@ -1209,7 +1264,9 @@ bool AlnPipeline::align_block(const std::vector<FastqRec> &recs, std::vector<Pai
 		if (pes[pi].gain) I.set_primary(se, pes[pi]);
 	}
 	stats.reads += 2 * n_pairs;
-	if (getenv("PANSVR_TIMING")) fprintf(stderr, "[timing] finish: probe %.3f s, in-order replay of %zu/%zu pairs %.3f s\n", t_probe, n_redo, n_pairs, now() - t0 - t_probe);
+	if (getenv("PANSVR_TIMING"))
+		fprintf(stderr, "[timing] finish: probe %.3f s, in-order replay of %zu/%zu pairs %.3f s (%zu variant states for reads with N, %zu reads prepared in order)\n",
+		        t_probe, n_redo, n_pairs, now() - t0 - t_probe, n_var, n_in_order);
 	// ---- SAM text of every pair (no random numbers involved any more: parallel)
 	parallel(n_pairs, [&](size_t pb, size_t pe_, int) {
 		for (size_t pi = pb; pi < pe_; ++pi) {
