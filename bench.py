@@ -38,6 +38,9 @@ OPS_PER_CELL = 55               # int ops per DP cell with traceba
 CIGAR_CAP = 16
 
 
+NCU_DRAM_BYTES_PER_TASK = 65840       # profiles/r1h_ksw_team_full.md
+
+
 def env_int(name, default):
     try:
         return int(os.environ.get(name, default))
@@ -288,7 +291,11 @@ def main():
                 "gcups": e2e_reads_s * CELLS_PER_TASK / 1e9},
         "gpu_launches": int(launches + e_launches),
         "roofline": {"bound": "int_alu", "achieved": achieved_gops, "peak": int_peak, "unit": "Gop/s",
-                     "frac": achieved_gops / int_peak if int_peak else None, "traffic": None,
+                     "frac": achieved_gops / int_peak if int_peak else None,
+                     # DRAM bytes per launch of this kernel from the ncu --set full capture in profiles/r1h_ksw_team_full.md
+                     # (65.84 GB at 1 M tasks: dram__bytes_read 30.13 GB + dram__bytes_write 35.71 GB), scaled to this launch
+                     "traffic": NCU_DRAM_BYTES_PER_TASK * n, "traffic_unit": "bytes/launch",
+                     "algorithmic_bytes": bytes_per_task * n,
                      "kernel": "ksw_team_kernel<8,true>", "kernel_ms_per_launch": kern_ms / args.steps,
                      "ops_per_cell": OPS_PER_CELL, "gcups": kernel_gcups,
                      "peak_source": "pansvr_int_alu_peak measured live on this GPU (IADD3/LOP3/VIMNMX chains)",
