@@ -167,7 +167,7 @@ def main():
         return
 
     import torch
-    from pansvr_b200 import ksw, synth
+    from pansvr_b200 import ksw, shard, synth
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the B200 path has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
@@ -180,7 +180,7 @@ def main():
 
     # ---- synthetic workload (every rank its own seed: weak scaling, reads shard trivially)
     n = args.tasks
-    batch = synth.config2_batch(n, seed=11 + rank)
+    batch = synth.config2_batch(n, seed=shard.shard_seed(11, rank))
     p = batch.params
     cells = CELLS_PER_TASK * n
     # pinned host staging (the batcher's buffers) and the device-resident copy
@@ -226,10 +226,7 @@ def main():
             tot_ms += last["total_ms"]; kern_ms += last["kernel_ms"]; launches += last["kernel_launches"]
         barrier()
         wall_ms = (time.perf_counter() - t0) * 1e3
-        if dist is not None:
-            t = torch.tensor([tot_ms, kern_ms, wall_ms], dtype=torch.float64, device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            tot_ms, kern_ms, wall_ms = (float(x) for x in t.cpu())
+        tot_ms, kern_ms, wall_ms = shard.max_over_ranks([tot_ms, kern_ms, wall_ms], dist, dev)
         return tot_ms, kern_ms, launches, wall_ms, last
 
     for _ in range(args.warmup):
@@ -260,8 +257,8 @@ def main():
         return
 
     peaks, peak_src = measured_peaks()
-    reads_s = world * n * args.steps / (tot_ms * 1e-3)
-    e2e_reads_s = world * n * args.steps / (e_tot_ms * 1e-3)
+    reads_s = shard.whole_job_rate(n, args.steps, world, tot_ms)
+    e2e_reads_s = shard.whole_job_rate(n, args.steps, world, e_tot_ms)
     kernel_gcups = cells * args.steps / (kern_ms * 1e-3) / 1e9                  # per GPU, dominant kernel only
     achieved_gops = kernel_gcups * OPS_PER_CELL
     # HBM view of the same kernel: bytes it must move per task (query + touched target + traceback written
