@@ -67,6 +67,71 @@ void parse_fastq(const char *p, size_t n, std::vector<FastqRec> &out)
 	}
 }
 
+// The same records, found on all helper threads: strict 4-line FASTQ (what fc_signal writes) has its record starts at the
+// lines whose index is a multiple of four, so every thread counts the newlines of its slice of the buffer, a prefix sum
+// gives the index of the first line starting in each slice, and each thread parses the records that start in its slice
+// straight into their final slots.  Anything that does not look like strict 4-line FASTQ (blank lines, a header not
+// starting with '@', a third line not starting with '+') returns false and the sequential parser above is used.
+bool parse_fastq_parallel(const char *p, size_t n, AlnPipeline &pipe, int threads, std::vector<FastqRec> &out)
+{
+	if (threads <= 1 || n < (1u << 20)) return false;
+	const size_t T = (size_t)threads, per = (n + T - 1) / T;
+	std::vector<size_t> nl(T + 1, 0);
+	pipe.parallel(T, [&](size_t b, size_t e, int) {
+		for (size_t t = b; t < e; ++t) {
+			const size_t s0 = std::min(n, per * t), s1 = std::min(n, per * (t + 1));
+			size_t c = 0;
+			for (const char *q = p + s0, *qe = p + s1; (q = (const char*)memchr(q, '\n', (size_t)(qe - q))) != nullptr; ++q) ++c;
+			nl[t + 1] = c;
+		}
+	}, 2);
+	for (size_t t = 0; t < T; ++t) nl[t + 1] += nl[t];
+	const size_t lines = nl[T] + (n && p[n - 1] != '\n' ? 1 : 0);
+	if (lines % 4 != 0) return false;
+	out.assign(lines / 4, FastqRec());
+	std::vector<uint8_t> bad(T, 0);
+	pipe.parallel(T, [&](size_t b, size_t e, int) {
+		for (size_t t = b; t < e; ++t) {
+			const size_t s0 = std::min(n, per * t), s1 = std::min(n, per * (t + 1));
+			if (s0 >= s1) continue;
+			size_t q = s0, idx = nl[t];                           // idx = newlines before q = index of the line containing q
+			if (q != 0 && p[q - 1] != '\n') {                      // q is inside a line that started earlier: go to the next line start
+				const char *x = (const char*)memchr(p + q, '\n', s1 - q);
+				if (!x) continue;                                  // no line starts in this slice
+				q = (size_t)(x - p) + 1; ++idx;
+			}
+			while (idx % 4 != 0 && q < s1) {                       // the tail of a record that started in an earlier slice
+				const char *x = (const char*)memchr(p + q, '\n', n - q);
+				if (!x) { q = n; break; }
+				q = (size_t)(x - p) + 1; ++idx;
+			}
+			while (q < s1 && q < n) {                              // records starting in [s0, s1)
+				const char *ln[4]; uint32_t ll[4];
+				for (int k = 0; k < 4; ++k) {
+					const char *x = q < n ? (const char*)memchr(p + q, '\n', n - q) : nullptr;
+					const size_t e2 = x ? (size_t)(x - p) : n;
+					size_t len = e2 - q;
+					if (len && p[q + len - 1] == '\r') --len;
+					ln[k] = p + q; ll[k] = (uint32_t)len;
+					q = e2 + 1;
+				}
+				if (ll[0] == 0 || (ln[0][0] != '@' && ln[0][0] != '>') || ll[2] == 0 || ln[2][0] != '+') { bad[t] = 1; break; }
+				FastqRec r;
+				uint32_t sp = 1;
+				while (sp < ll[0] && ln[0][sp] != ' ' && ln[0][sp] != '\t') ++sp;
+				r.name = ln[0] + 1; r.name_l = sp - 1;
+				while (sp < ll[0] && (ln[0][sp] == ' ' || ln[0][sp] == '\t')) ++sp;
+				r.comment = ln[0] + sp; r.comment_l = ll[0] - sp;
+				r.seq = ln[1]; r.seq_l = ll[1]; r.qual = ln[3]; r.qual_l = ll[3];
+				out[idx / 4] = r;
+				idx += 4;
+			}
+		}
+	}, 2);
+	for (uint8_t x : bad) if (x) { out.clear(); return false; }
+	return true;
+}
+
 AlnOptions from_c(const pansvr_aln_options_t *o)
 {
 	AlnOptions a;
@@ -123,12 +188,12 @@ const char *pansvr_aln_last_error(void) { return g_aln_err.c_str(); }
 namespace {
 
 // parse + align one block; `outp` receives the record text of every pair
-int run_block(pansvr_aln_ctx *c, const char *fastq, size_t n, std::vector<PairOutput> &outp)
+int run_block(pansvr_aln_ctx *c, const char *fastq, size_t n, BlockOutput &outp)
 {
 	const auto tick = []() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
 	const double t0 = tick();
 	std::vector<FastqRec> recs;
-	parse_fastq(fastq, n, recs);
+	if (!parse_fastq_parallel(fastq, n, *c->pipe, c->opt.threads, recs)) parse_fastq(fastq, n, recs);
 	c->pipe->stats.t_stage[6] += tick() - t0;
 	std::string err;
 	if (!c->pipe->align_block(recs, outp, err)) { g_aln_err = err; return PANSVR_E_CUDA; }
@@ -154,34 +219,25 @@ int pansvr_aln_block(pansvr_aln_ctx *c, const char *fastq, size_t n, char **sam,
 {
 	if (!c || !fastq || !sam || !ori) return PANSVR_E_ARG;
 	CallReport report(c);
-	std::vector<PairOutput> outp;
+	BlockOutput outp;
 	const int rc = run_block(c, fastq, n, outp);
 	if (rc != 0) return rc;
 	const double t0 = CallReport::now();
-	// total sizes, then every pair copies its records to its own offset (parallel)
-	const size_t np = outp.size();
-	std::vector<size_t> off_s(np + 1, 0), off_o(np + 1, 0);
-	for (size_t i = 0; i < np; ++i) {
-		size_t a = 0, b = 0;
-		for (int k = 0; k < 2; ++k) { if (!outp[i].sam[k].empty()) a += outp[i].sam[k].size() + 1; if (!outp[i].ori[k].empty()) b += outp[i].ori[k].size() + 1; }
-		off_s[i + 1] = off_s[i] + a; off_o[i + 1] = off_o[i] + b;
-	}
-	char *sbuf = (char*)malloc(off_s[np] + 1), *obuf = (char*)malloc(off_o[np] + 1);
-	if (!sbuf || !obuf) { free(sbuf); free(obuf); g_aln_err = "out of memory"; return PANSVR_E_ARG; }
-	c->pipe->parallel(np, [&](size_t b, size_t e, int) {
-		for (size_t i = b; i < e; ++i) {
-			char *ps = sbuf + off_s[i], *po = obuf + off_o[i];
-			for (int k = 0; k < 2; ++k) {
-				const std::string &x = outp[i].sam[k], &y = outp[i].ori[k];
-				if (!x.empty()) { memcpy(ps, x.data(), x.size()); ps += x.size(); *ps++ = '\n'; }
-				if (!y.empty()) { memcpy(po, y.data(), y.size()); po += y.size(); *po++ = '\n'; }
-			}
-		}
-	});
-	sbuf[off_s[np]] = 0; obuf[off_o[np]] = 0;
-	*sam = sbuf; *ori = obuf;
-	if (sam_bytes) *sam_bytes = off_s[np];
-	if (ori_bytes) *ori_bytes = off_o[np];
+	auto join = [&](std::vector<std::string> &parts, char **out, size_t *bytes) -> bool {     // chunk buffers -> one malloc'ed text
+		const size_t np = parts.size();
+		std::vector<size_t> off(np + 1, 0);
+		for (size_t i = 0; i < np; ++i) off[i + 1] = off[i] + parts[i].size();
+		char *buf = (char*)malloc(off[np] + 1);
+		if (!buf) return false;
+		std::vector<std::thread> th;
+		for (size_t i = 0; i < np; ++i) if (!parts[i].empty()) th.emplace_back([&, i]() { memcpy(buf + off[i], parts[i].data(), parts[i].size()); std::string().swap(parts[i]); });
+		for (std::thread &x : th) x.join();
+		buf[off[np]] = 0;
+		*out = buf;
+		if (bytes) *bytes = off[np];
+		return true;
+	};
+	if (!join(outp.sam, sam, sam_bytes) || !join(outp.ori, ori, ori_bytes)) { g_aln_err = "out of memory"; return PANSVR_E_ARG; }
 	c->pipe->stats.t_stage[7] += CallReport::now() - t0;
 	return 0;
 }
@@ -191,22 +247,27 @@ int pansvr_aln_block_bam(pansvr_aln_ctx *c, const char *fastq, size_t n, uint8_t
 {
 	if (!c || !fastq || !bam || !ori) return PANSVR_E_ARG;
 	CallReport report(c);
-	std::vector<PairOutput> outp;
+	BlockOutput outp;
 	const int rc = run_block(c, fastq, n, outp);
 	if (rc != 0) return rc;
 	const double t0 = CallReport::now();
-	const size_t np = outp.size();
-	const int T = std::max(1, c->opt.threads);
-	std::vector<std::vector<uint8_t>> part_s((size_t)T), part_o((size_t)T);
-	std::vector<std::string> errs((size_t)T);
-	c->pipe->parallel(np, [&](size_t b, size_t e, int t) {
-		for (size_t i = b; i < e && errs[t].empty(); ++i)
-			for (int k = 0; k < 2; ++k) {
-				const std::string &x = outp[i].sam[k], &y = outp[i].ori[k];
-				if (!x.empty() && !bam_encode_record(x.data(), x.size(), c->bam_hdr, part_s[t], errs[t])) break;
-				if (!y.empty() && !bam_encode_record(y.data(), y.size(), c->bam_hdr, part_o[t], errs[t])) break;
-			}
-	});
+	const size_t np = outp.sam.size();
+	std::vector<std::vector<uint8_t>> part_s(np), part_o(np);
+	std::vector<std::string> errs(np);
+	auto encode_lines = [&](const std::string &text, std::vector<uint8_t> &dst, std::string &err) {
+		dst.reserve(text.size() / 2);
+		for (size_t p = 0; p < text.size() && err.empty();) {
+			const char *nl = (const char*)memchr(text.data() + p, '\n', text.size() - p);
+			const size_t e = nl ? (size_t)(nl - text.data()) : text.size();
+			if (e > p) bam_encode_record(text.data() + p, e - p, c->bam_hdr, dst, err);
+			p = e + 1;
+		}
+	};
+	{
+		std::vector<std::thread> th;                              // one thread per chunk buffer (as many as helper threads)
+		for (size_t i = 0; i < np; ++i) th.emplace_back([&, i]() { encode_lines(outp.sam[i], part_s[i], errs[i]); if (errs[i].empty()) encode_lines(outp.ori[i], part_o[i], errs[i]); });
+		for (std::thread &x : th) x.join();
+	}
 	for (const std::string &e : errs) if (!e.empty()) { g_aln_err = e; return PANSVR_E_ARG; }
 	auto join = [&](std::vector<std::vector<uint8_t>> &parts, uint8_t **out, size_t *bytes) -> bool {
 		size_t tot = 0;
@@ -233,7 +294,7 @@ int pansvr_bam_open(pansvr_aln_ctx *c, const char *path, pansvr_bam_file **out)
 	b->f = fopen(path, "wb");
 	if (!b->f) { g_aln_err = std::string("cannot open ") + path; delete b; return PANSVR_E_ARG; }
 	AlnPipeline *pipe = c->pipe;
-	b->w = new BamWriter(b->f, [pipe](size_t n, const std::function<void(size_t, size_t, int)> &fn) { pipe->parallel(n, fn); });
+	b->w = new BamWriter(b->f, [pipe](size_t n, const std::function<void(size_t, size_t, int)> &fn) { pipe->parallel(n, fn, 2); });
 	if (!b->w->write_header(c->bam_hdr)) { g_aln_err = "BAM header write failed"; delete b; return PANSVR_E_ARG; }
 	*out = b;
 	return 0;

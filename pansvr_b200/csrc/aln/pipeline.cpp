@@ -76,10 +76,10 @@ struct AlnPipeline::Workers {
 };
 
 // static-chunk parallel loop over [0,n): fn(begin, end, chunk_index)
-void AlnPipeline::parallel(size_t n, const std::function<void(size_t, size_t, int)> &fn)
+void AlnPipeline::parallel(size_t n, const std::function<void(size_t, size_t, int)> &fn, size_t serial_below)
 {
 	const int T = workers_ ? (int)workers_->th.size() : 1;
-	if (T <= 1 || n < 256) { fn((size_t)0, n, 0); return; }
+	if (T <= 1 || n < serial_below) { fn((size_t)0, n, 0); return; }
 	const size_t per = (n + T - 1) / T;
 	const int chunks = (int)((n + per - 1) / per);
 	workers_->run(chunks, [&](int t) { fn(std::min(n, per * t), std::min(n, per * (t + 1)), t); });
@@ -868,11 +868,9 @@ struct AlnPipeline::Impl {
 
 	void output_bam(ReadState &r, std::string &out, bool first, int abs_isize)
 	{
-		out.clear();
-		Result *p = r.primary;
+		Result *p = r.primary;                                   // appends one line (with its newline) to `out`, or nothing
 		if (!p || p->chr == U32MAX) return;
 		if (P.opt.not_ori && p->is_ori) return;
-		out.reserve(2 * (size_t)r.read_l + r.rec->name_l + r.comment.size() + 256);
 		const int dir = p->direction;
 		const uint8_t flag = (uint8_t)((first ? 0x40 : 0) + (dir == REVERSE ? 0x10 : 0) + (p->has_mate ? 0 : 0x08));
 		out.append(r.rec->name, r.rec->name_l); out += '\t'; append_int(out, flag); out += '\t';
@@ -900,12 +898,13 @@ struct AlnPipeline::Impl {
 			out += s->sv ? s->sv->vcf_id : std::string("*"); out += ';';
 		}
 		out += "\tRC:Z:"; out += r.comment;
+		out += '\n';
 	}
 
 	// output_ori_bam (RR:656-717): the original alignment rebuilt from the comment; returns whether the original CIGAR shows a clip >= 25 / unmapped
 	void output_ori(ReadState &r, std::string &out, int max_score, bool &clip_or_unmapped)
 	{
-		out.clear(); clip_or_unmapped = true;
+		clip_or_unmapped = true;                                 // appends one line (with its newline) to `out`, or nothing
 		std::string &c = r.comment;
 		const size_t fpos = c.find("FLAG_");
 		if (fpos == std::string::npos) return;
@@ -929,7 +928,6 @@ struct AlnPipeline::Impl {
 		if (tag_len > 0) tags.resize(tag_len - 1);
 		// the reference cuts the comment in place at the end of the CIGAR and edits the tags
 		c[cig_e < c.size() ? cig_e : c.size() - 1] = '\0';
-		out.reserve(2 * (size_t)r.read_l + r.rec->name_l + tags.size() + cigar.size() + 128);
 		out.append(r.rec->name, r.rec->name_l); out += '\t'; append_int(out, flag); out += '\t'; out += target_name(r.ori.chr); out += '\t';
 		append_int(out, (long)(r.ori.ref_bg + 1)); out += '\t'; append_int(out, qual); out += '\t';
 		out += cigar.empty() ? std::string("*") : cigar; out += '\t';
@@ -939,6 +937,7 @@ struct AlnPipeline::Impl {
 		append_seq_qual(out, r, !fwd);
 		if (tag_len) { out += '\t'; out += tags; }
 		out += "\tMS:i:"; append_int(out, max_score);
+		out += '\n';
 		// bam_has_clip_or_unmapped_ori (RR:721-733) on the CIGAR just written
 		if (cigar.empty()) { clip_or_unmapped = true; return; }
 		std::vector<std::pair<int, char>> ops;
@@ -975,11 +974,12 @@ void AlnPipeline::reset()
 	for (int i = 0; i < 2; ++i) rand_r_[i].reseed((unsigned)rand_.next());
 }
 
-bool AlnPipeline::align_block(const std::vector<FastqRec> &recs, std::vector<PairOutput> &out, std::string &err)
+bool AlnPipeline::align_block(const std::vector<FastqRec> &recs, BlockOutput &out, std::string &err)
 {
 	Impl I(*this);
 	const size_t n_reads = recs.size() & ~(size_t)1, n_pairs = n_reads / 2;
-	out.assign(n_pairs, PairOutput());
+	out.sam.assign((size_t)std::max(1, opt.threads), std::string());
+	out.ori.assign((size_t)std::max(1, opt.threads), std::string());
 	if (n_pairs == 0) return true;
 	double t0 = now();
 
@@ -1268,16 +1268,18 @@ bool AlnPipeline::align_block(const std::vector<FastqRec> &recs, std::vector<Pai
 		fprintf(stderr, "[timing] finish: probe %.3f s, in-order replay of %zu/%zu pairs %.3f s (%zu variant states for reads with N, %zu reads prepared in order)\n",
 		        t_probe, n_redo, n_pairs, now() - t0 - t_probe, n_var, n_in_order);
 	// ---- SAM text of every pair (no random numbers involved any more: parallel)
-	parallel(n_pairs, [&](size_t pb, size_t pe_, int) {
+	parallel(n_pairs, [&](size_t pb, size_t pe_, int t) {                 // chunk t writes its pairs, in order, into buffer t
+		std::string &sam = out.sam[(size_t)t], &ori = out.ori[(size_t)t];
+		sam.reserve((pe_ - pb) * 2 * (2 * (size_t)opt.read_len + 400));
 		for (size_t pi = pb; pi < pe_; ++pi) {
 			ReadState *se = &rs[2 * pi];
 			const Impl::PE &pe = pes[pi];
-			PairOutput &po = out[pi];
 			if (pe.gain)
-				for (int k = 0; k < 2; ++k) I.output_bam(se[k], po.sam[k], k == 0, pe.cur_isize);
+				for (int k = 0; k < 2; ++k) I.output_bam(se[k], sam, k == 0, pe.cur_isize);
 			if (pe.max_score <= min_filter_score_ && (int)se[0].ori.chr != -1 && (int)se[1].ori.chr != -1) {   // RR:776-797
 				bool clip[2] = {true, true};
-				for (int k = 0; k < 2; ++k) I.output_ori(se[k], po.ori[k], pe.max_score, clip[k]);
+				const size_t ori_mark = ori.size();
+				for (int k = 0; k < 2; ++k) I.output_ori(se[k], ori, pe.max_score, clip[k]);
 				bool proper = pe.proper;
 				for (int k = 0; proper && k < 2; ++k) {
 					const Result *c = k == 0 ? pe.m1 : pe.m2;
@@ -1289,7 +1291,7 @@ bool AlnPipeline::align_block(const std::vector<FastqRec> &recs, std::vector<Pai
 						if (c->cigar.empty() || ins >= 25) proper = false;
 					}
 				}
-				if (proper) { po.ori[0].clear(); po.ori[1].clear(); }
+				if (proper) ori.resize(ori_mark);                          // a proper pair after all: nothing goes to the -p file
 			}
 		}
 	});

@@ -67,9 +67,9 @@ void seed_service_destroy(SeedService *s);
 bool seed_service_run(SeedService *s, SeedBatch &b, std::string &err);
 
 // ---- results of one pair --------------------------------------------------------------------------------------------
-struct PairOutput {
-	std::string sam[2];               // main output records (empty = none), without trailing newline
-	std::string ori[2];               // `-p` output: pairs still poorly aligned
+struct BlockOutput {                  // record text of one block: buffer t holds the lines ("...\n") of the t-th chunk of pairs,
+	std::vector<std::string> sam;     // concatenating the buffers in order gives the block's output in input order
+	std::vector<std::string> ori;     // `-p` output: pairs still poorly aligned
 };
 
 struct CigarPath { uint8_t type; int16_t size; };
@@ -81,9 +81,9 @@ public:
 	AlnPipeline(const AlnPipeline&) = delete;
 	AlnPipeline &operator=(const AlnPipeline&) = delete;
 	// static-chunk parallel loop over [0,n) on the pipeline's helper threads: fn(begin, end, chunk_index)
-	void parallel(size_t n, const std::function<void(size_t, size_t, int)> &fn);
-	// Aligns n_pairs interleaved pairs (recs[2i], recs[2i+1]); out[i] receives the SAM text of pair i.
-	bool align_block(const std::vector<FastqRec> &recs, std::vector<PairOutput> &out, std::string &err);
+	void parallel(size_t n, const std::function<void(size_t, size_t, int)> &fn, size_t serial_below = 256);
+	// Aligns n_pairs interleaved pairs (recs[2i], recs[2i+1]); `out` receives the SAM text in input order.
+	bool align_block(const std::vector<FastqRec> &recs, BlockOutput &out, std::string &err);
 	void reset();                     // back to the state of a freshly started `fc_aln` (rand() streams, counters)
 	struct Stats { uint64_t reads = 0, probes_reads = 0, mems = 0, ksw_tasks = 0, ksw_cells = 0, deferred_pairs = 0;
 	               double t_stage[8] = {0, 0, 0, 0, 0, 0, 0, 0}; } stats;   // A..F, FASTQ parse, output assembly

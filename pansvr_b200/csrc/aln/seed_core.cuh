@@ -96,7 +96,63 @@ SEED_HD int64_t unipath_of(const IndexView &ix, uint64_t x)
 	return high;
 }
 
-// extend one k-mer hit to a maximal exact match inside its unipath
+// ---- word-wise comparison of packed sequences (32 bases per 64-bit word, MSB first).  Both arrays carry one spare word
+// after their last base (index.cpp pads unipath.seqb, stage A pads every packed read), so a window may read one word past
+// the last base; what it sees there is cut off by the caller's cap.
+SEED_HD uint32_t clz64(uint64_t x)
+{
+#if defined(__CUDA_ARCH__)
+	return (uint32_t)__clzll((long long)x);
+#else
+	return (uint32_t)__builtin_clzll(x);
+#endif
+}
+SEED_HD uint32_t ctz64(uint64_t x)
+{
+#if defined(__CUDA_ARCH__)
+	return (uint32_t)(__ffsll((long long)x) - 1);
+#else
+	return (uint32_t)__builtin_ctzll(x);
+#endif
+}
+// the 32 bases pos .. pos+31
+SEED_HD uint64_t window_at(const uint64_t *seq, uint64_t pos)
+{
+	const uint64_t w = pos >> 5;
+	const uint32_t k = (uint32_t)(pos & 0x1f);
+	return k ? (seq[w] << (k << 1)) | (seq[w + 1] >> ((32 - k) << 1)) : seq[w];
+}
+// the 32 bases pos-32 .. pos-1 (pos >= 1); for pos < 32 the pos existing bases, right-aligned
+SEED_HD uint64_t window_before(const uint64_t *seq, uint64_t pos)
+{
+	return pos >= 32 ? window_at(seq, pos - 32) : seq[0] >> ((32 - (uint32_t)pos) << 1);
+}
+// length of the common prefix of a[ap..] and b[bp..], at most cap
+SEED_HD uint32_t match_right(const uint64_t *a, uint64_t ap, const uint64_t *b, uint64_t bp, uint32_t cap)
+{
+	uint32_t m = 0;
+	while (m < cap) {
+		const uint64_t x = window_at(a, ap + m) ^ window_at(b, bp + m);
+		if (x) { m += clz64(x) >> 1; break; }
+		m += 32;
+	}
+	return m < cap ? m : cap;
+}
+// length of the common suffix of a[..ap) and b[..bp), at most cap (cap <= ap, cap <= bp)
+SEED_HD uint32_t match_left(const uint64_t *a, uint64_t ap, const uint64_t *b, uint64_t bp, uint32_t cap)
+{
+	uint32_t m = 0;
+	while (m < cap) {
+		const uint64_t x = window_before(a, ap - m) ^ window_before(b, bp - m);
+		if (x) { m += ctz64(x) >> 1; break; }
+		m += 32;
+	}
+	return m < cap ? m : cap;
+}
+
+// extend one k-mer hit to a maximal exact match inside its unipath.  The reference walks base by base
+// (deBGA_index.cpp:118-131: left_i / right_i stop at the first mismatch, at the unipath end or at the read end);
+// the same counts come out of 32-base XOR windows.
 SEED_HD void unitig_mem(const IndexView &ix, uint64_t kmer_index, const uint64_t *read_bit, uint32_t read_off, uint32_t read_length,
                         uint32_t seed_id, Mem &out, uint32_t &max_right_i)
 {
@@ -104,11 +160,11 @@ SEED_HD void unitig_mem(const IndexView &ix, uint64_t kmer_index, const uint64_t
 	const int64_t uid = unipath_of(ix, kpos);
 	const uint32_t off_l = (uint32_t)(kpos - ix.seqf[uid]);
 	const uint32_t off_r = (uint32_t)(ix.seqf[uid + 1] - (kpos + LEN_KMER));
-	uint32_t left_i, right_i;
-	for (left_i = 1; left_i <= off_l && left_i <= read_off; ++left_i)
-		if (base_at(ix.seqb, kpos - left_i) != base_at(read_bit, read_off - left_i)) break;
-	for (right_i = 1; right_i <= off_r && right_i <= read_length - read_off - LEN_KMER; ++right_i)
-		if (base_at(ix.seqb, kpos + LEN_KMER - 1 + right_i) != base_at(read_bit, read_off + LEN_KMER - 1 + right_i)) break;
+	const uint32_t cap_l = off_l < read_off ? off_l : read_off;
+	const uint32_t room_r = read_length - read_off - LEN_KMER;
+	const uint32_t cap_r = off_r < room_r ? off_r : room_r;
+	const uint32_t left_i = 1 + match_left(ix.seqb, kpos, read_bit, read_off, cap_l);
+	const uint32_t right_i = 1 + match_right(ix.seqb, kpos + LEN_KMER, read_bit, read_off + LEN_KMER, cap_r);
 	out.uid = (uint64_t)uid;
 	out.seed_id = seed_id;
 	out.read_pos = read_off + 1 - left_i;

@@ -36,6 +36,17 @@ def test_glibc_random_replica_matches_libc():
     os.unlink(exe)
 
 
+def test_wordwise_mem_extension_matches_base_by_base():
+    """seed_core.cuh extends MEMs with 32-base XOR windows; the reference walks base by base (deBGA_index.cpp:118-131)."""
+    src = os.path.join(HERE, "emul", "seed_check.cpp")
+    exe = os.path.join(HERE, "emul", "seed_check")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-x", "c++", src, "-o", exe])
+    try:
+        assert subprocess.run([exe], stdout=subprocess.DEVNULL).returncode == 0
+    finally:
+        os.unlink(exe)
+
+
 @pytest.mark.parametrize("name", list(DATASETS))
 def test_host_pipeline_matches_reference_sam(fc_aln_emul, name):
     need_ref_tools()
