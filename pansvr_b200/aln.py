@@ -66,6 +66,22 @@ class AlnContext:
         finally:
             self.lib.pansvr_free(s); self.lib.pansvr_free(o)
 
+    def align_fastq_view(self, fastq: bytes):
+        """Like align_fastq without the copy into Python bytes: returns (sam, ori, release) where sam/ori are memoryviews of
+        the library's buffers and release() frees them (call it once the views are no longer used)."""
+        s, o = C.c_void_p(), C.c_void_p()
+        sl, ol = C.c_size_t(), C.c_size_t()
+        rc = self.lib.pansvr_aln_block(self.h, fastq, len(fastq), C.byref(s), C.byref(sl), C.byref(o), C.byref(ol))
+        if rc != 0:
+            raise RuntimeError(f"pansvr_aln_block failed ({rc}): {self.lib.pansvr_aln_last_error().decode()}")
+        sam = memoryview((C.c_char * sl.value).from_address(s.value)).cast("B") if sl.value else memoryview(b"")
+        ori = memoryview((C.c_char * ol.value).from_address(o.value)).cast("B") if ol.value else memoryview(b"")
+
+        def release():
+            sam.release(); ori.release()
+            self.lib.pansvr_free(s); self.lib.pansvr_free(o)
+        return sam, ori, release
+
     def align_fastq_bam(self, fastq: bytes):
         """Like align_fastq, records in uncompressed BAM form (what htslib's bam_write1 hands to BGZF)."""
         s, o = C.c_void_p(), C.c_void_p()

@@ -192,6 +192,11 @@ struct NodeAln {
 	int fixed_score = 0;           // everything but the ksw scores
 	int read_begin_alignment = 0;
 	bool planned = false;
+	// filled the first time a candidate ending at this node is extended (finish_read); a pair that is finished twice
+	// -- against the probe, then in the replay -- reuses it
+	bool resolved = false;
+	uint32_t align_score = 0;
+	std::vector<CigarPath> cigar;
 };
 
 } // namespace
@@ -228,6 +233,7 @@ struct ReadState {
 	Result *primary = nullptr, *secondary = nullptr;
 };
 
+struct KswView { const int32_t *res; const uint32_t *cig; int cap; };   // results of a task list, as finish_read reads them
 struct KswTaskList {
 	std::vector<uint8_t> q, t;
 	std::vector<int64_t> qoff, toff;
@@ -243,6 +249,7 @@ struct KswTaskList {
 		return (int)qlen.size() - 1;
 	}
 	void clear() { q.clear(); t.clear(); qoff.clear(); toff.clear(); qlen.clear(); tlen.clear(); res.clear(); cig.clear(); }
+	KswView view() const { KswView v; v.res = res.data(); v.cig = cig.data(); v.cap = cap; return v; }
 };
 
 // The process-wide rand() stream as the replay sees it: the real generator, or a probe that only records that it
@@ -318,9 +325,11 @@ struct AlnPipeline::Impl {
 		}
 	}
 
-	static void pack64(const std::vector<uint8_t> &b, std::vector<uint64_t> &out, size_t off)   // binary_read_64_bit, RR:295-300
+	// `words` words are written at out[off..]: the packed bases, then zeros (the spare word the k-mer and window reads rely on)
+	static void pack64(const std::vector<uint8_t> &b, uint64_t *out, size_t off, size_t words)   // binary_read_64_bit, RR:295-300
 	{
 		const size_t n = b.size();
+		for (size_t k = n >> 5; k < words; ++k) out[off + k] = 0;
 		size_t i = 0;
 		for (; i + 32 <= n; i += 32) {
 			uint64_t w = 0;
@@ -700,22 +709,22 @@ struct AlnPipeline::Impl {
 		for (int i = 0; i < n; ++i) res[i] = std::move(tmp[i]);
 	}
 
-	bool reverse_cigar(Result &c, const std::vector<CigarPath> &tmp, int read_len)   // reverseGIGAR, read_realignment.hpp:277-301
+	bool reverse_cigar(std::vector<CigarPath> &out, const std::vector<CigarPath> &tmp, int read_len)   // reverseGIGAR, read_realignment.hpp:277-301
 	{
-		c.cigar.clear();
+		out.clear();
 		if (tmp.empty()) return false;
-		c.cigar.reserve(tmp.size());
-		c.cigar.push_back(tmp.back());
+		out.reserve(tmp.size());
+		out.push_back(tmp.back());
 		for (int i = (int)tmp.size() - 2; i >= 0; --i)
-			if (!cig_try_merge(c.cigar.back(), tmp[i])) c.cigar.push_back(tmp[i]);
-		if (!c.cigar.empty() && c.cigar[0].size == 0) c.cigar.erase(c.cigar.begin());
+			if (!cig_try_merge(out.back(), tmp[i])) out.push_back(tmp[i]);
+		if (!out.empty() && out[0].size == 0) out.erase(out.begin());
 		int total = 0;
-		for (const CigarPath &ci : c.cigar) if (ci.type == 0 || ci.type == 1 || ci.type == 3 || ci.type == 4) total += ci.size;
+		for (const CigarPath &ci : out) if (ci.type == 0 || ci.type == 1 || ci.type == 3 || ci.type == 4) total += ci.size;
 		return total == read_len;
 	}
 
 	// the rest of single_end_handler::align once chains and ksw results exist (RR:416-475)
-	void finish_read(ReadState &r, const KswTaskList &tasks, RandTap &rnd)
+	void finish_read(ReadState &r, const KswView &tasks, RandTap &rnd)
 	{
 		r.result_num = 0; r.primary = r.secondary = nullptr;
 		r.result.clear();
@@ -747,22 +756,27 @@ struct AlnPipeline::Impl {
 				fprintf(stderr, "pansvr_b200: internal error, chain end %u of strand %d was not planned\n", c.max_index, s);
 				abort();
 			}
-			const NodeAln &na = it->second;
+			NodeAln &na = it->second;
+			if (!na.resolved) {
 			int score = na.fixed_score;
 			std::vector<CigarPath> &tmp = rnd.cigar_scratch;
 			tmp.clear();
 			for (const Piece &p : na.pieces) {
 				if (p.kind == 0) { tmp.push_back(p.lit); continue; }
-				const int32_t *res = tasks.res.data() + (size_t)p.task * PANSVR_RES_WORDS;
-				const uint32_t *cg = tasks.cig.data() + (size_t)p.task * tasks.cap;
+				const int32_t *res = tasks.res + (size_t)p.task * PANSVR_RES_WORDS;
+				const uint32_t *cg = tasks.cig + (size_t)p.task * tasks.cap;
 				const int nc = res[PANSVR_RES_N_CIGAR];
 				if (p.type == ALN_E2E) { score += res[PANSVR_RES_SCORE]; for (int i = nc - 1; i >= 0; --i) tmp.push_back(cig_bin(cg[i])); }
 				else if (p.type == ALN_LEFT) { score += res[PANSVR_RES_MQE]; for (int i = 0; i < nc; ++i) tmp.push_back(cig_bin(cg[i])); }
 				else { score += res[PANSVR_RES_MQE]; for (int i = nc - 1; i >= 0; --i) tmp.push_back(cig_bin(cg[i])); }
 			}
+			na.align_score = (uint32_t)std::max(score, 0);
+			if (!reverse_cigar(na.cigar, tmp, r.read_l)) fprintf(stderr, "ERROR cigar: read_len: %d %.*s\n", r.read_l, r.read_l, r.rec->seq);
+			na.resolved = true;
+			}
 			c.ref_bg -= (uint32_t)na.read_begin_alignment;
-			c.align_score = (uint32_t)std::max(score, 0);
-			if (!reverse_cigar(c, tmp, r.read_l)) fprintf(stderr, "ERROR cigar: read_len: %d %.*s\n", r.read_l, r.read_l, r.rec->seq);
+			c.align_score = na.align_score;
+			c.cigar = na.cigar;
 		}
 		sort_results(r.result.data(), r.result_num, cmp_align);
 		if (r.result[0].align_score < (uint32_t)MIN_ALN_SCORE) { r.result_num = 0; return; }
@@ -1055,14 +1069,14 @@ bool AlnPipeline::align_block(const std::vector<FastqRec> &recs, BlockOutput &ou
 	auto prepare_read = [&](ReadState &r) {                                   // encode + pack + STR census
 		I.encode(r);
 		const size_t words = (size_t)(r.read_l >> 5) + 2;
-		for (int s = 0; s < 2; ++s) { r.bits[s].assign(words, 0); Impl::pack64(r.bin[s], r.bits[s], 0); }
+		for (int s = 0; s < 2; ++s) { r.bits[s].assign(words, 0); Impl::pack64(r.bin[s], r.bits[s].data(), 0, words); }
 		I.str_census(r, r.bits[0].data(), census_main);
 	};
 	auto register_jobs = [&](ReadState &r, SeedBatch &sb) {
 		for (int s = 0; s < 2; ++s) {
 			SeedJob j;
 			j.bits_off = (uint32_t)sb.bits.size(); j.read_len = (uint32_t)r.read_l; j.is_str = r.is_str ? 1 : 0; j.list_off = 0;
-			sb.bits.insert(sb.bits.end(), r.bits[s].begin(), r.bits[s].end());
+			sb.bits.append(r.bits[s].data(), r.bits[s].data() + r.bits[s].size());
 			if (r.is_str) { j.list_off = (uint32_t)sb.seed_list.size(); sb.seed_list.insert(sb.seed_list.end(), r.seed_list[s].begin(), r.seed_list[s].end()); }
 			r.job[s] = (int)sb.jobs.size();
 			sb.jobs.push_back(j);
@@ -1084,7 +1098,8 @@ bool AlnPipeline::align_block(const std::vector<FastqRec> &recs, BlockOutput &ou
 			I.chain(g, edges);
 		}
 	};
-	SeedBatch sb;
+	SeedBatch &sb = seed_main_;
+	sb.clear();
 	{
 		std::vector<uint32_t> word_off(n_all + 1, 0), job_of(n_all + 1, 0);
 		for (size_t i = 0; i < n_all; ++i) {                                 // layout of the packed-read pool (two strands per read)
@@ -1094,7 +1109,7 @@ bool AlnPipeline::align_block(const std::vector<FastqRec> &recs, BlockOutput &ou
 			word_off[i + 1] = word_off[i] + (r.batched ? 2u * (uint32_t)((r.read_l >> 5) + 2) : 0u);
 			job_of[i + 1] = job_of[i] + (r.batched ? 2u : 0u);
 		}
-		sb.bits.assign(word_off[n_all], 0);
+		sb.bits.resize(word_off[n_all]);
 		sb.jobs.resize(job_of[n_all]);
 		par_all([&](size_t b, size_t e, int) {
 			Impl::CensusScratch census;
@@ -1105,7 +1120,7 @@ bool AlnPipeline::align_block(const std::vector<FastqRec> &recs, BlockOutput &ou
 				const uint32_t words = (uint32_t)((r.read_l >> 5) + 2);
 				for (int s = 0; s < 2; ++s) {
 					const uint32_t off = word_off[i] + (uint32_t)s * words;
-					Impl::pack64(r.bin[s], sb.bits, off);
+					Impl::pack64(r.bin[s], sb.bits.data(), off, words);
 					SeedJob &j = sb.jobs[job_of[i] + s];
 					j.bits_off = off; j.read_len = (uint32_t)r.read_l; j.is_str = 0; j.list_off = 0;
 					r.job[s] = (int)(job_of[i] + s);
@@ -1145,30 +1160,39 @@ bool AlnPipeline::align_block(const std::vector<FastqRec> &recs, BlockOutput &ou
 		if (rs[i].batched && rs[i].needs_rand) { rs[rs[i].var_of].in_order_only = true; rs[i].batched = false; }
 	stats.t_stage[2] += now() - t0; t0 = now();
 	// ---- stage D: per-thread task lists, concatenated afterwards
-	KswTaskList tasks;
+	KswBatchBuf &tasks = ksw_main_;
 	{
-		std::vector<KswTaskList> part((size_t)T);
+		std::vector<KswTaskList> part((size_t)T + 1);                      // one list per chunk of reads, the last one for the variants
 		std::vector<size_t> lo((size_t)T, 0), hi((size_t)T, 0);
 		par_reads([&](size_t b, size_t e, int t) {
 			lo[t] = b; hi[t] = e;
 			Impl::PlanScratch scratch;
 			for (size_t i = b; i < e; ++i) if (rs[i].batched) I.plan_read(rs[i], part[t], scratch);
 		});
-		for (int t = 0; t < T; ++t) {
-			const int base = (int)tasks.qlen.size();
-			const int64_t qb = (int64_t)tasks.q.size(), tb = (int64_t)tasks.t.size();
-			KswTaskList &p = part[t];
-			tasks.q.insert(tasks.q.end(), p.q.begin(), p.q.end());
-			tasks.t.insert(tasks.t.end(), p.t.begin(), p.t.end());
-			for (size_t k = 0; k < p.qlen.size(); ++k) {
-				tasks.qoff.push_back(p.qoff[k] + qb); tasks.toff.push_back(p.toff[k] + tb);
-				tasks.qlen.push_back(p.qlen[k]); tasks.tlen.push_back(p.tlen[k]);
+		for (size_t i = n_reads; i < n_all; ++i)
+			if (rs[i].batched && !rs[rs[i].var_of].in_order_only) I.plan_read(rs[i], part[T], plan_main);
+		// joined on the helper threads: every list is copied to its place and the task ids of its reads are rebased
+		std::vector<size_t> kb((size_t)T + 2, 0), qb((size_t)T + 2, 0), tb((size_t)T + 2, 0);
+		for (int t = 0; t <= T; ++t) { kb[t + 1] = kb[t] + part[t].qlen.size(); qb[t + 1] = qb[t] + part[t].q.size(); tb[t + 1] = tb[t] + part[t].t.size(); }
+		const size_t nk = kb[T + 1];
+		tasks.q.resize(qb[T + 1]); tasks.t.resize(tb[T + 1]);
+		tasks.qoff.resize(nk); tasks.toff.resize(nk); tasks.qlen.resize(nk); tasks.tlen.resize(nk);
+		parallel((size_t)T + 1, [&](size_t b, size_t e, int) {
+			for (size_t t = b; t < e; ++t) {
+				const KswTaskList &p = part[t];
+				if (!p.q.empty()) memcpy(tasks.q.data() + qb[t], p.q.data(), p.q.size());
+				if (!p.t.empty()) memcpy(tasks.t.data() + tb[t], p.t.data(), p.t.size());
+				for (size_t k = 0; k < p.qlen.size(); ++k) {
+					tasks.qoff[kb[t] + k] = p.qoff[k] + (int64_t)qb[t]; tasks.toff[kb[t] + k] = p.toff[k] + (int64_t)tb[t];
+					tasks.qlen[kb[t] + k] = p.qlen[k]; tasks.tlen[kb[t] + k] = p.tlen[k];
+				}
+				const int base = (int)kb[t];
+				if (!base) continue;
+				const size_t ib = t < (size_t)T ? lo[t] : n_reads, ie = t < (size_t)T ? hi[t] : n_all;
+				for (size_t i = ib; i < ie; ++i)
+					for (auto &kv : rs[i].node_aln) for (Piece &pc : kv.second.pieces) if (pc.kind == 1) pc.task += base;
 			}
-			if (base) for (size_t i = lo[t]; i < hi[t]; ++i)
-				for (auto &kv : rs[i].node_aln) for (Piece &pc : kv.second.pieces) if (pc.kind == 1) pc.task += base;
-		}
-		for (size_t i = n_reads; i < n_all; ++i)                           // variants (rare): straight into the joined list
-			if (rs[i].batched && !rs[rs[i].var_of].in_order_only) I.plan_read(rs[i], tasks, plan_main);
+		}, 2);
 	}
 	stats.t_stage[3] += now() - t0; t0 = now();
 	// ---- stage E
@@ -1178,30 +1202,44 @@ bool AlnPipeline::align_block(const std::vector<FastqRec> &recs, BlockOutput &ou
 	pansvr_ksw_params_t kp;
 	kp.m = 5; kp.mat = mat; kp.gapo = (int8_t)opt.gap_open; kp.gape = (int8_t)opt.gap_ex; kp.gapo2 = (int8_t)opt.gap_open2; kp.gape2 = (int8_t)opt.gap_ex2;
 	kp.w = 200; kp.zdrop = (uint16_t)opt.zdrop; kp.end_bonus = -1; kp.flag = 0;      // copy_option, RR:817-827
-	auto run_ksw = [&](KswTaskList &tl) -> bool {
-		const size_t n = tl.qlen.size();
-		tl.res.assign(n * PANSVR_RES_WORDS, 0);
-		tl.cig.assign(n * (size_t)tl.cap, 0);
+	// one ksw batch over a task list; the CIGAR rows are `cap` words, a list whose longest CIGAR does not fit is run again
+	auto ksw_batch = [&](size_t n, const uint8_t *q, size_t q_bytes, const int64_t *qoff, const int32_t *qlen, const uint8_t *t, size_t t_bytes,
+	                     const int64_t *toff, const int32_t *tlen, int &cap, const std::function<void(int32_t*&, uint32_t*&)> &out_buffers) -> bool {
 		if (n == 0) return true;
 		for (;;) {
-			const int rc = pansvr_ksw_extd2_batch((pansvr_ksw_ctx*)ksw_, (int64_t)n, tl.q.data(), (int64_t)tl.q.size(), tl.qoff.data(), tl.qlen.data(),
-			                                      tl.t.data(), (int64_t)tl.t.size(), tl.toff.data(), tl.tlen.data(), &kp, tl.res.data(), tl.cig.data(), tl.cap);
+			int32_t *res; uint32_t *cig;
+			out_buffers(res, cig);
+			const int rc = pansvr_ksw_extd2_batch((pansvr_ksw_ctx*)ksw_, (int64_t)n, q, (int64_t)q_bytes, qoff, qlen, t, (int64_t)t_bytes, toff, tlen, &kp, res, cig, cap);
 			if (rc != 0) { err = std::string("ksw batch: ") + pansvr_last_error(); return false; }
-			int need = 0;
-			for (size_t i = 0; i < n; ++i) if (tl.res[i * PANSVR_RES_WORDS + PANSVR_RES_STATUS] & 1) need = std::max(need, tl.res[i * PANSVR_RES_WORDS + PANSVR_RES_N_CIGAR]);
-			if (!need) break;
-			tl.cap = need + 8;                                         // a CIGAR did not fit: redo the batch with room for the longest
-			tl.cig.assign(n * (size_t)tl.cap, 0);
-		}
-		stats.ksw_tasks += n;
-		{
+			std::atomic<int> need(0);
 			std::atomic<uint64_t> cells(0);
-			parallel(n, [&](size_t b, size_t e, int) { uint64_t c = 0; for (size_t i = b; i < e; ++i) c += (uint64_t)pansvr_ksw_band_cells(tl.qlen[i], tl.tlen[i], kp.w); cells += c; });
-			stats.ksw_cells += cells.load();
+			parallel(n, [&](size_t b, size_t e, int) {
+				int nd = 0; uint64_t c = 0;
+				for (size_t i = b; i < e; ++i) {
+					if (res[i * PANSVR_RES_WORDS + PANSVR_RES_STATUS] & 1) nd = std::max(nd, res[i * PANSVR_RES_WORDS + PANSVR_RES_N_CIGAR]);
+					c += (uint64_t)pansvr_ksw_band_cells(qlen[i], tlen[i], kp.w);
+				}
+				cells += c;
+				int cur = need.load();
+				while (nd > cur && !need.compare_exchange_weak(cur, nd)) {}
+			});
+			if (!need.load()) { stats.ksw_tasks += n; stats.ksw_cells += cells.load(); return true; }
+			cap = need.load() + 8;
 		}
-		return true;
 	};
-	if (!run_ksw(tasks)) return false;
+	auto run_ksw = [&](KswTaskList &tl) -> bool {
+		const size_t n = tl.qlen.size();
+		return ksw_batch(n, tl.q.data(), tl.q.size(), tl.qoff.data(), tl.qlen.data(), tl.t.data(), tl.t.size(), tl.toff.data(), tl.tlen.data(), tl.cap,
+		                 [&](int32_t *&res, uint32_t *&cig) { tl.res.resize(n * PANSVR_RES_WORDS); tl.cig.resize(n * (size_t)tl.cap); res = tl.res.data(); cig = tl.cig.data(); });
+	};
+	{
+		const size_t n = tasks.qlen.size();
+		tasks.cap = 16;
+		if (!ksw_batch(n, tasks.q.data(), tasks.q.size(), tasks.qoff.data(), tasks.qlen.data(), tasks.t.data(), tasks.t.size(), tasks.toff.data(), tasks.tlen.data(),
+		               tasks.cap, [&](int32_t *&res, uint32_t *&cig) { tasks.res.resize(n * PANSVR_RES_WORDS); tasks.cig.resize(n * (size_t)tasks.cap); res = tasks.res.data(); cig = tasks.cig.data(); }))
+			return false;
+	}
+	const KswView tasks_view{tasks.res.data(), tasks.cig.data(), tasks.cap};
 	stats.t_stage[4] += now() - t0; t0 = now();
 
 	// ---- stage F: chain selection, result sort and pairing.  Only exact ties consume rand() (RR:247, RRH:553), so every
@@ -1215,7 +1253,7 @@ bool AlnPipeline::align_block(const std::vector<FastqRec> &recs, BlockOutput &ou
 			ReadState *se = &rs[2 * pi];
 			if (se[0].has_n || se[1].has_n) { redo[pi] = 1; continue; }
 			probe.calls = 0;
-			for (int k = 0; k < 2; ++k) I.finish_read(se[k], tasks, probe);
+			for (int k = 0; k < 2; ++k) I.finish_read(se[k], tasks_view, probe);
 			if (probe.calls) { redo[pi] = 1; continue; }
 			I.pair_up(se, pes[pi], probe);
 			if (probe.calls) { redo[pi] = 2; continue; }                     // the candidate lists stand, only the pairing tie is redrawn
@@ -1225,8 +1263,26 @@ bool AlnPipeline::align_block(const std::vector<FastqRec> &recs, BlockOutput &ou
 	const double t_probe = now() - t0;
 	size_t n_redo = 0, n_in_order = 0;
 	RandTap real; real.real = &rand_;
-	for (size_t pi = 0; pi < n_pairs; ++pi) {
-		if (!redo[pi]) continue;
+	// the replay walks cold per-read data on one thread: pull the state of the pairs a few steps ahead into the cache
+	std::vector<uint32_t> redo_list;
+	for (size_t pi = 0; pi < n_pairs; ++pi) if (redo[pi]) redo_list.push_back((uint32_t)pi);
+	auto prefetch_state = [&](size_t k) { if (k < redo_list.size()) { const char *p = (const char*)&rs[2 * (size_t)redo_list[k]]; for (size_t o = 0; o < 2 * sizeof(ReadState); o += 64) __builtin_prefetch(p + o); } };
+	auto prefetch_arrays = [&](size_t k) {
+		if (k >= redo_list.size()) return;
+		for (int m = 0; m < 2; ++m) {
+			const ReadState &r = rs[2 * (size_t)redo_list[k] + m];
+			for (int s2 = 0; s2 < 2; ++s2) {
+				const char *p = (const char*)r.g[s2].path.data(); const size_t n = r.g[s2].path.size() * sizeof(PathNode);
+				for (size_t o = 0; o < n && o < 512; o += 64) __builtin_prefetch(p + o);
+				__builtin_prefetch(r.g[s2].v.data());
+			}
+			__builtin_prefetch(r.node_aln.data());
+			__builtin_prefetch(r.result.data());
+		}
+	};
+	for (size_t ri = 0; ri < redo_list.size(); ++ri) {
+		const size_t pi = redo_list[ri];
+		prefetch_state(ri + 8); prefetch_arrays(ri + 3);
 		++n_redo;
 		ReadState *se = &rs[2 * pi];
 		if (se[0].has_n || se[1].has_n) {                                 // deferred pair: its rand() draws happen now
@@ -1245,7 +1301,8 @@ bool AlnPipeline::align_block(const std::vector<FastqRec> &recs, BlockOutput &ou
 				} else {
 					++n_in_order;
 					own[k] = true;
-					SeedBatch one;
+					SeedBatch &one = seed_small_;
+					one.clear();
 					prepare_read(r);
 					register_jobs(r, one);
 					if (!seed_service_run(seeds_, one, err)) return false;
@@ -1255,10 +1312,10 @@ bool AlnPipeline::align_block(const std::vector<FastqRec> &recs, BlockOutput &ou
 					I.plan_read(r, local, plan_main);
 					if (!run_ksw(local)) return false;
 				}
-				I.finish_read(r, own[k] ? local : tasks, real);
+				I.finish_read(r, own[k] ? local.view() : tasks_view, real);
 			}
 		} else if (redo[pi] == 1) {
-			for (int k = 0; k < 2; ++k) I.finish_read(se[k], tasks, real);
+			for (int k = 0; k < 2; ++k) I.finish_read(se[k], tasks_view, real);
 		}
 		I.pair_up(se, pes[pi], real);
 		if (pes[pi].gain) I.set_primary(se, pes[pi]);

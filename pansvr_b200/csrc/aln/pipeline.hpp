@@ -21,7 +21,9 @@
 // The output is defined against `panSVR fc_aln -t 1` (the only deterministic mode).
 #pragma once
 #include <stdint.h>
+#include <string.h>
 #include <functional>
+#include <new>
 #include <map>
 #include <string>
 #include <vector>
@@ -49,17 +51,64 @@ struct FastqRec {                     // views into the caller's FASTQ text (no 
 };
 
 // ---- device services (link-time: CUDA in the product library, host emulation in tests/emul) ---------------------
+// Staging memory of the two device batches: page-locked in the product (cudaHostAlloc in seed_gpu.cu), so that the
+// copies of a block are direct DMA; plain malloc in the host test build.
+void *staging_alloc(size_t bytes);
+void staging_free(void *p);
+
+// The part of std::vector the pipeline needs, for trivially copyable T, on staging memory; grow-only, contents are
+// not initialised by resize().  The pipeline keeps its batch buffers across blocks, so they are pinned once.
+template <class T> class HostVec {
+public:
+	HostVec() {}
+	HostVec(const HostVec&) = delete;
+	HostVec &operator=(const HostVec&) = delete;
+	~HostVec() { if (p_) staging_free(p_); }
+	T *data() { return p_; }
+	const T *data() const { return p_; }
+	size_t size() const { return n_; }
+	bool empty() const { return n_ == 0; }
+	void clear() { n_ = 0; }
+	T &operator[](size_t i) { return p_[i]; }
+	const T &operator[](size_t i) const { return p_[i]; }
+	void reserve(size_t m)
+	{
+		if (m <= cap_) return;
+		const size_t want = m + m / 2 + 64;
+		T *q = (T*)staging_alloc(want * sizeof(T));
+		if (!q) throw std::bad_alloc();
+		if (n_) memcpy(q, p_, n_ * sizeof(T));
+		if (p_) staging_free(p_);
+		p_ = q; cap_ = want;
+	}
+	void resize(size_t m) { reserve(m); n_ = m; }
+	void assign(size_t m, const T &v) { resize(m); for (size_t i = 0; i < m; ++i) p_[i] = v; }
+	void push_back(const T &v) { reserve(n_ + 1); p_[n_++] = v; }
+	void append(const T *b, const T *e) { const size_t k = (size_t)(e - b); reserve(n_ + k); if (k) memcpy(p_ + n_, b, k * sizeof(T)); n_ += k; }
+private:
+	T *p_ = nullptr;
+	size_t n_ = 0, cap_ = 0;
+};
+
 struct SeedJob {                      // one read strand
 	uint32_t bits_off, read_len;      // word offset into SeedBatch::bits
 	uint32_t list_off;                // offset into SeedBatch::seed_list (STR reads only)
 	uint32_t is_str;
 };
 struct SeedBatch {
-	std::vector<uint64_t> bits;       // packed reads, 32 bases per word, one spare zero word after each read
+	HostVec<uint64_t> bits;           // packed reads, 32 bases per word, one spare zero word after each read
 	std::vector<uint8_t> seed_list;
-	std::vector<SeedJob> jobs;
-	std::vector<Mem> mems;            // out: MEMs of job i are mems[mem_off[i] .. mem_off[i+1])
-	std::vector<uint32_t> mem_off;
+	HostVec<SeedJob> jobs;
+	HostVec<Mem> mems;                // out: MEMs of job i are mems[mem_off[i] .. mem_off[i+1])
+	HostVec<uint32_t> mem_off;
+	void clear() { bits.clear(); seed_list.clear(); jobs.clear(); mems.clear(); mem_off.clear(); }
+};
+struct KswBatchBuf {                  // the ksw tasks of one block, joined (stage D -> E -> F)
+	HostVec<uint8_t> q, t;
+	HostVec<int64_t> qoff, toff;
+	HostVec<int32_t> qlen, tlen, res;
+	HostVec<uint32_t> cig;
+	int cap = 16;                     // CIGAR words per task; a block whose longest CIGAR does not fit is run again with room
 };
 struct SeedService;                   // opaque; owns the device-resident index
 SeedService *seed_service_create(const DebgaIndex &idx, int device, std::string &err);
@@ -95,6 +144,8 @@ private:
 	const DebgaIndex &idx_;
 	SeedService *seeds_;
 	void *ksw_;
+	SeedBatch seed_main_, seed_small_;    // batch buffers live across blocks (staging memory is pinned once)
+	KswBatchBuf ksw_main_;
 	GlibcRandom rand_;                // the process-global rand() of the reference
 	GlibcRandom rand_r_[2];           // per-handler random_r states (RRH:339-340), seeded from rand_ at start-up
 	int min_filter_score_ = 0;

@@ -61,6 +61,13 @@ template <class T> bool upload(const std::vector<T> &h, T *&d, std::string &err)
 
 } // namespace
 
+void *staging_alloc(size_t bytes)
+{
+	void *p = nullptr;
+	return cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) == cudaSuccess ? p : nullptr;
+}
+void staging_free(void *p) { if (p) cudaFreeHost(p); }
+
 struct SeedService {
 	int device = 0;
 	cudaStream_t stream = nullptr;

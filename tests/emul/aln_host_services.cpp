@@ -14,6 +14,9 @@
 
 namespace pansvr {
 
+void *staging_alloc(size_t bytes) { return malloc(bytes ? bytes : 1); }
+void staging_free(void *p) { free(p); }
+
 struct SeedService { IndexView view; };
 
 SeedService *seed_service_create(const DebgaIndex &idx, int, std::string &)
@@ -34,7 +37,7 @@ bool seed_service_run(SeedService *s, SeedBatch &b, std::string &)
 		const SeedJob &j = b.jobs[i];
 		int c = seed_read_strand(s->view, b.bits.data() + j.bits_off, j.read_len, j.is_str != 0, b.seed_list.data() + j.list_off, tmp.data(), (int)tmp.size());
 		if (c > (int)tmp.size()) { tmp.resize(c); c = seed_read_strand(s->view, b.bits.data() + j.bits_off, j.read_len, j.is_str != 0, b.seed_list.data() + j.list_off, tmp.data(), c); }
-		b.mems.insert(b.mems.end(), tmp.begin(), tmp.begin() + c);
+		b.mems.append(tmp.data(), tmp.data() + c);
 		b.mem_off[i + 1] = (uint32_t)b.mems.size();
 	}
 	return true;
