@@ -25,6 +25,7 @@ struct pansvr_aln_ctx {
 	pansvr_ksw_ctx *ksw = nullptr;
 	AlnPipeline *pipe = nullptr;
 	BamHeaderInfo bam_hdr;
+	BlockOutput out;                  // chunk buffers of the record text, kept across blocks
 };
 
 struct pansvr_bam_file {
@@ -219,7 +220,7 @@ int pansvr_aln_block(pansvr_aln_ctx *c, const char *fastq, size_t n, char **sam,
 {
 	if (!c || !fastq || !sam || !ori) return PANSVR_E_ARG;
 	CallReport report(c);
-	BlockOutput outp;
+	BlockOutput &outp = c->out;
 	const int rc = run_block(c, fastq, n, outp);
 	if (rc != 0) return rc;
 	const double t0 = CallReport::now();
@@ -230,7 +231,7 @@ int pansvr_aln_block(pansvr_aln_ctx *c, const char *fastq, size_t n, char **sam,
 		char *buf = (char*)malloc(off[np] + 1);
 		if (!buf) return false;
 		std::vector<std::thread> th;
-		for (size_t i = 0; i < np; ++i) if (!parts[i].empty()) th.emplace_back([&, i]() { memcpy(buf + off[i], parts[i].data(), parts[i].size()); std::string().swap(parts[i]); });
+		for (size_t i = 0; i < np; ++i) if (!parts[i].empty()) th.emplace_back([&, i]() { memcpy(buf + off[i], parts[i].data(), parts[i].size()); });
 		for (std::thread &x : th) x.join();
 		buf[off[np]] = 0;
 		*out = buf;
@@ -247,7 +248,7 @@ int pansvr_aln_block_bam(pansvr_aln_ctx *c, const char *fastq, size_t n, uint8_t
 {
 	if (!c || !fastq || !bam || !ori) return PANSVR_E_ARG;
 	CallReport report(c);
-	BlockOutput outp;
+	BlockOutput &outp = c->out;
 	const int rc = run_block(c, fastq, n, outp);
 	if (rc != 0) return rc;
 	const double t0 = CallReport::now();

@@ -90,10 +90,12 @@ namespace {
 double now() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
 // ---------------------------------------------------------------------------------------------- small pieces
-uint8_t dna5(unsigned char c)                                  // charToDna5n, read_realignment.cpp:180-202
-{
-	switch (c) { case 'C': case 'c': return 1; case 'G': case 'g': return 2; case 'T': case 't': return 3; case 'n': return 4; default: return 0; }
-}
+struct Dna5Table {                                              // charToDna5n, read_realignment.cpp:180-202, as a table (no branches)
+	uint8_t t[256];
+	Dna5Table() { memset(t, 0, sizeof t); t['C'] = t['c'] = 1; t['G'] = t['g'] = 2; t['T'] = t['t'] = 3; t['n'] = 4; }
+};
+const Dna5Table g_dna5;
+inline uint8_t dna5(unsigned char c) { return g_dna5.t[c]; }
 char rev_char(char c)                                           // getReverseChar, clib/bam_file.c:320-328
 {
 	switch (c) { case 'A': case 'a': return 'T'; case 'C': case 'c': return 'G'; case 'G': case 'g': return 'C'; case 'T': case 't': return 'A'; }
@@ -314,14 +316,20 @@ struct AlnPipeline::Impl {
 	void encode(ReadState &r)                                    // binary_read_2_bit, read_realignment.cpp:646-654
 	{
 		const int L = r.read_l;
-		r.bin[0].assign(L, 0); r.bin[1].assign(L, 0);
+		r.bin[0].resize(L); r.bin[1].resize(L);
+		uint8_t *f = r.bin[0].data(), *rv = r.bin[1].data();
+		const char *seq = r.rec->seq;
+		if (r.n_draws == 0 && r.var_of < 0) {                     // no 'N': nothing to draw
+			for (int i = 0; i < L; ++i) { const uint8_t c = dna5((unsigned char)seq[i]); f[i] = c; rv[L - i - 1] = c ^ 3; }
+			return;
+		}
 		int nth = 0;
 		for (int i = 0; i < L; ++i) {
-			char ch = r.rec->seq[i];
+			char ch = seq[i];
 			if (ch == 'N') ch = "ACGT"[r.var_of >= 0 ? (r.var_code >> (2 * nth++)) & 3 : (uint32_t)(P.rand_.next() % 4)];
 			const uint8_t c = dna5((unsigned char)ch);
-			r.bin[0][i] = c;
-			r.bin[1][L - i - 1] = c ^ 3;
+			f[i] = c;
+			rv[L - i - 1] = c ^ 3;
 		}
 	}
 
@@ -364,8 +372,18 @@ struct AlnPipeline::Impl {
 		uint64_t *keys = cs.keys.data(); uint32_t *stamp = cs.stamp.data(); uint16_t *cnt = cs.cnt.data(), *slot_of = cs.slot_of.data();
 		const uint32_t tick = cs.now;
 		uint32_t distinct = 0;
+		// the 20-mer at i is get_kmer(i, bits); when every base code is 0..3 (no lower-case 'n', whose code 4 spills into
+		// the neighbouring base of the packed word) it is also the rolling value over the byte codes, which is cheaper
+		const uint8_t *bin = r.bin[0].data();
+		bool plain = true;
+		for (uint32_t i = 0; i < L; ++i) plain &= bin[i] < 4;
+		const uint64_t kmask = (1ull << (2 * LEN_KMER)) - 1;
+		uint64_t roll = 0;
+		if (plain) for (uint32_t i = 0; i + 1 < LEN_KMER; ++i) roll = (roll << 2) | bin[i];
 		for (uint32_t i = 0; i < kn; ++i) {
-			const uint64_t k = get_kmer(i, bits);
+			uint64_t k;
+			if (plain) { roll = ((roll << 2) | bin[i + LEN_KMER - 1]) & kmask; k = roll; }
+			else k = get_kmer(i, bits);
 			uint32_t h = (uint32_t)((k * 0x9E3779B97F4A7C15ull) >> 40) & (cap - 1);
 			while (stamp[h] == tick && keys[h] != k) h = (h + 1) & (cap - 1);
 			if (stamp[h] != tick) { stamp[h] = tick; keys[h] = k; cnt[h] = 0; ++distinct; }
@@ -992,8 +1010,10 @@ bool AlnPipeline::align_block(const std::vector<FastqRec> &recs, BlockOutput &ou
 {
 	Impl I(*this);
 	const size_t n_reads = recs.size() & ~(size_t)1, n_pairs = n_reads / 2;
-	out.sam.assign((size_t)std::max(1, opt.threads), std::string());
-	out.ori.assign((size_t)std::max(1, opt.threads), std::string());
+	out.sam.resize((size_t)std::max(1, opt.threads));                     // the caller may keep `out` across blocks: capacity is reused
+	out.ori.resize((size_t)std::max(1, opt.threads));
+	for (std::string &x : out.sam) x.clear();
+	for (std::string &x : out.ori) x.clear();
 	if (n_pairs == 0) return true;
 	double t0 = now();
 
@@ -1014,6 +1034,9 @@ bool AlnPipeline::align_block(const std::vector<FastqRec> &recs, BlockOutput &ou
 	// loops over reads are cut at pair boundaries: the same worker owns a pair's two reads in every stage
 	auto par_reads = [&](const std::function<void(size_t, size_t, int)> &fn) { parallel(n_pairs, [&](size_t b, size_t e, int t) { fn(2 * b, 2 * e, t); }); };
 	// 'N' census: a read with 1..3 N gets 4^n variant states behind the real reads (indices n_reads ..)
+	const bool timing = getenv("PANSVR_TIMING") != nullptr;
+	double ta = now();
+	auto lap = [&](const char *what) { if (timing) { const double t = now(); fprintf(stderr, "[timing]   A/%s %.3f s\n", what, t - ta); ta = t; } };
 	enum { MAX_VARIANT_DRAWS = 3 };
 	std::vector<uint8_t> n_count(n_reads, 0);
 	par_reads([&](size_t b, size_t e, int) {
@@ -1029,6 +1052,7 @@ bool AlnPipeline::align_block(const std::vector<FastqRec> &recs, BlockOutput &ou
 	for (size_t i = 0; i < n_reads; ++i)
 		if (n_count[i] >= 1 && n_count[i] <= MAX_VARIANT_DRAWS && recs[i].seq_l >= LEN_KMER) { var_src.push_back(std::make_pair(i, n_reads + n_var)); n_var += (size_t)1 << (2 * n_count[i]); }
 	const size_t n_all = n_reads + n_var;
+	lap("N census");
 	// every loop over read states: the real reads in pair chunks, then the variants
 	auto par_all = [&](const std::function<void(size_t, size_t, int)> &fn) {
 		par_reads(fn);
@@ -1041,6 +1065,7 @@ bool AlnPipeline::align_block(const std::vector<FastqRec> &recs, BlockOutput &ou
 		~ReadArray() { par([&](size_t b, size_t e, int) { for (size_t i = b; i < e; ++i) p[i].~ReadState(); }); free(p); }
 		ReadState &operator[](size_t i) { return p[i]; }
 	} rs(n_all, par_all);
+	lap("state array");
 	par_reads([&](size_t b, size_t e, int) {
 		for (size_t i = b; i < e; ++i) {
 			ReadState &r = rs[i];
@@ -1065,6 +1090,7 @@ bool AlnPipeline::align_block(const std::vector<FastqRec> &recs, BlockOutput &ou
 			v.var_of = (int64_t)vs.first; v.var_code = (uint32_t)c;
 		}
 	}
+	lap("comment parse");
 	Impl::CensusScratch census_main;
 	auto prepare_read = [&](ReadState &r) {                                   // encode + pack + STR census
 		I.encode(r);
@@ -1111,6 +1137,7 @@ bool AlnPipeline::align_block(const std::vector<FastqRec> &recs, BlockOutput &ou
 		}
 		sb.bits.resize(word_off[n_all]);
 		sb.jobs.resize(job_of[n_all]);
+		lap("layout");
 		par_all([&](size_t b, size_t e, int) {
 			Impl::CensusScratch census;
 			for (size_t i = b; i < e; ++i) {
@@ -1128,6 +1155,7 @@ bool AlnPipeline::align_block(const std::vector<FastqRec> &recs, BlockOutput &ou
 				I.str_census(r, sb.bits.data() + word_off[i], census);
 			}
 		});
+		lap("encode + pack + STR census");
 		for (size_t i = 0; i < n_all; ++i) {                                 // STR reads are rare: their seed lists are appended in order
 			ReadState &r = rs[i];
 			if (!r.batched || !r.is_str) continue;
@@ -1251,12 +1279,14 @@ bool AlnPipeline::align_block(const std::vector<FastqRec> &recs, BlockOutput &ou
 		RandTap probe;
 		for (size_t pi = pb; pi < pe_; ++pi) {
 			ReadState *se = &rs[2 * pi];
-			if (se[0].has_n || se[1].has_n) { redo[pi] = 1; continue; }
+			if (se[0].has_n || se[1].has_n) { redo[pi] = 16; continue; }
 			probe.calls = 0;
-			for (int k = 0; k < 2; ++k) I.finish_read(se[k], tasks_view, probe);
-			if (probe.calls) { redo[pi] = 1; continue; }
+			I.finish_read(se[0], tasks_view, probe);
+			const uint32_t c0 = probe.calls;
+			I.finish_read(se[1], tasks_view, probe);
+			if (probe.calls) { redo[pi] = (uint8_t)(4 | (c0 ? 1 : 0) | (probe.calls > c0 ? 2 : 0)); continue; }   // which read's candidate list has ties
 			I.pair_up(se, pes[pi], probe);
-			if (probe.calls) { redo[pi] = 2; continue; }                     // the candidate lists stand, only the pairing tie is redrawn
+			if (probe.calls) { redo[pi] = 8; continue; }                     // the candidate lists stand, only the pairing tie is redrawn
 			if (pes[pi].gain) I.set_primary(se, pes[pi]);
 		}
 	});
@@ -1314,8 +1344,8 @@ bool AlnPipeline::align_block(const std::vector<FastqRec> &recs, BlockOutput &ou
 				}
 				I.finish_read(r, own[k] ? local.view() : tasks_view, real);
 			}
-		} else if (redo[pi] == 1) {
-			for (int k = 0; k < 2; ++k) I.finish_read(se[k], tasks_view, real);
+		} else if (redo[pi] & 4) {
+			for (int k = 0; k < 2; ++k) if (redo[pi] & (1 << k)) I.finish_read(se[k], tasks_view, real);   // a tie-free list is final already
 		}
 		I.pair_up(se, pes[pi], real);
 		if (pes[pi].gain) I.set_primary(se, pes[pi]);
