@@ -1354,9 +1354,12 @@ bool AlnPipeline::align_block(const std::vector<FastqRec> &recs, BlockOutput &ou
 	if (getenv("PANSVR_TIMING"))
 		fprintf(stderr, "[timing] finish: probe %.3f s, in-order replay of %zu/%zu pairs %.3f s (%zu variant states for reads with N, %zu reads prepared in order)\n",
 		        t_probe, n_redo, n_pairs, now() - t0 - t_probe, n_var, n_in_order);
+	const double t_text = now();
 	// ---- SAM text of every pair (no random numbers involved any more: parallel)
 	parallel(n_pairs, [&](size_t pb, size_t pe_, int t) {                 // chunk t writes its pairs, in order, into buffer t
-		std::string &sam = out.sam[(size_t)t], &ori = out.ori[(size_t)t];
+		// the string headers of neighbouring chunks share cache lines and every append updates the length: work on locals
+		std::string sam, ori;
+		sam.swap(out.sam[(size_t)t]); ori.swap(out.ori[(size_t)t]);
 		sam.reserve((pe_ - pb) * 2 * (2 * (size_t)opt.read_len + 400));
 		for (size_t pi = pb; pi < pe_; ++pi) {
 			ReadState *se = &rs[2 * pi];
@@ -1381,8 +1384,10 @@ bool AlnPipeline::align_block(const std::vector<FastqRec> &recs, BlockOutput &ou
 				if (proper) ori.resize(ori_mark);                          // a proper pair after all: nothing goes to the -p file
 			}
 		}
+		sam.swap(out.sam[(size_t)t]); ori.swap(out.ori[(size_t)t]);
 	});
 	stats.t_stage[5] += now() - t0;
+	if (timing) fprintf(stderr, "[timing]   F/record text %.3f s\n", now() - t_text);
 	if (getenv("PANSVR_TIMING")) { double a = 0; for (int i = 0; i < 6; ++i) a += stats.t_stage[i]; fprintf(stderr, "[timing] align_block body done, stages A-F %.3f s\n", a); }
 	return true;
 }
