@@ -3,7 +3,12 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
 #include <algorithm>
+#include <thread>
 
 namespace pansvr {
 
@@ -44,6 +49,60 @@ bool slurp(const std::string &dir, const char *fn, std::vector<T> &out, size_t e
 	out.resize(n_el, 0);
 	fclose(f);
 	if (got != bytes) { err = "short read on " + path; return false; }
+	return true;
+}
+
+// The bucket table, compacted: non-empty buckets and a directory over their top 20 bits.
+bool load_buckets(const std::string &dir, DebgaIndex &ix, std::string &err)
+{
+	std::string path = dir;
+	if (!path.empty() && path.back() != '/') path += '/';
+	path += "unipath_g.hash";
+	const int fd = open(path.c_str(), O_RDONLY);
+	if (fd < 0) { err = "cannot open " + path; return false; }
+	struct stat st;
+	const size_t n_bkt = (size_t)1 << 28;                     // 4^14 buckets, n_bkt + 1 starts
+	if (fstat(fd, &st) != 0 || (size_t)st.st_size < (n_bkt + 1) * 8) { close(fd); err = "short bucket table " + path; return false; }
+	const uint64_t *h = (const uint64_t*)mmap(nullptr, (n_bkt + 1) * 8, PROT_READ, MAP_PRIVATE, fd, 0);
+	close(fd);
+	if (h == MAP_FAILED) { err = "mmap failed on " + path; return false; }
+	madvise((void*)h, (n_bkt + 1) * 8, MADV_SEQUENTIAL);
+	const unsigned T = std::max(1u, std::min(32u, std::thread::hardware_concurrency()));
+	std::vector<std::vector<uint32_t>> keys(T);
+	std::vector<std::vector<uint64_t>> starts(T);
+	std::vector<uint8_t> bad(T, 0);
+	{
+		std::vector<std::thread> th;
+		const size_t per = (n_bkt + T - 1) / T;
+		for (unsigned t = 0; t < T; ++t) th.emplace_back([&, t]() {
+			const size_t b = std::min(n_bkt, per * t), e = std::min(n_bkt, per * (t + 1));
+			uint64_t prev = b < e ? h[b] : 0;
+			for (size_t i = b; i < e; ++i) {
+				const uint64_t next = h[i + 1];
+				if (next != prev) {
+					if (next < prev) { bad[t] = 1; return; }
+					keys[t].push_back((uint32_t)i); starts[t].push_back(prev);
+				}
+				prev = next;
+			}
+		});
+		for (std::thread &x : th) x.join();
+	}
+	const uint64_t total = h[n_bkt];
+	munmap((void*)h, (n_bkt + 1) * 8);
+	for (uint8_t b : bad) if (b) { err = "bucket table is not monotone: " + path; return false; }
+	ix.bkt_key.clear(); ix.bkt_start.clear();
+	for (unsigned t = 0; t < T; ++t) {
+		ix.bkt_key.insert(ix.bkt_key.end(), keys[t].begin(), keys[t].end());
+		ix.bkt_start.insert(ix.bkt_start.end(), starts[t].begin(), starts[t].end());
+	}
+	ix.bkt_start.push_back(total);
+	ix.bkt_dir.assign(((size_t)1 << 20) + 1, 0);
+	size_t j = 0;
+	for (size_t x = 0; x <= ((size_t)1 << 20); ++x) {
+		while (j < ix.bkt_key.size() && (ix.bkt_key[j] >> 8) < x) ++j;
+		ix.bkt_dir[x] = (uint32_t)j;
+	}
 	return true;
 }
 
@@ -107,7 +166,7 @@ bool DebgaIndex::load(const std::string &index_dir, const std::string &header_sa
 	if (!slurp(index_dir, "unipath.seqfb", seqf, 0, err)) return false;
 	if (!slurp(index_dir, "unipath.pos", pos, 0, err)) return false;
 	if (!slurp(index_dir, "unipath.posp", posp, 0, err)) return false;
-	if (!slurp(index_dir, "unipath_g.hash", hash, 0, err)) return false;
+	if (!load_buckets(index_dir, *this, err)) return false;
 	if (!slurp(index_dir, "unipath_g.kmer", kmer_g, 0, err)) return false;
 	if (!slurp(index_dir, "unipath_g.offset", off_g, 0, err)) return false;
 

@@ -28,8 +28,14 @@ struct SvInfo {                       // SV_chr_info, deBGA_index.hpp:74-155
 
 struct DebgaIndex {
 	// the eight arrays, as stored on disk
-	std::vector<uint64_t> ref_seq, seqb, seqf, pos, posp, hash, off_g;
+	std::vector<uint64_t> ref_seq, seqb, seqf, pos, posp, off_g;
 	std::vector<uint32_t> kmer_g;
+	// unipath_g.hash holds 4^14+1 bucket starts (2 GiB) of which only the non-empty buckets carry information: it is
+	// scanned once through mmap and kept as the sorted list of non-empty buckets plus a 2^20-entry directory over the
+	// top 20 bits of the 28-bit bucket number.  Lookups return exactly hash[h], hash[h+1].
+	std::vector<uint32_t> bkt_dir;    // bkt_dir[x] = first entry of bkt_key with key >= x << 8;  2^20 + 1 entries
+	std::vector<uint32_t> bkt_key;    // bucket numbers h with hash[h+1] > hash[h], ascending
+	std::vector<uint64_t> bkt_start;  // hash[h] of those buckets, then the total; one entry more than bkt_key
 	// anchors
 	int chr_file_n = 0;
 	std::vector<std::string> chr_names;

@@ -24,7 +24,9 @@ struct IndexView {                 // device or host pointers to the index array
 	const uint64_t *seqb;          // 2-bit unipath sequence, 32 bases per word, MSB first
 	const uint64_t *seqf;          // start offset of each unipath in seqb
 	const uint64_t *posp;          // CSR pointers into the reference-position list
-	const uint64_t *hash;          // 4^14+1 bucket starts
+	const uint32_t *bkt_dir;       // compacted bucket table (index.hpp): directory over the top 20 bits of the bucket number,
+	const uint32_t *bkt_key;       //   non-empty bucket numbers,
+	const uint64_t *bkt_start;     //   and their starts (hash_g[h]); lookups give exactly hash_g[h], hash_g[h+1]
 	const uint64_t *off_g;         // offset of each indexed 22-mer in seqb
 	const uint32_t *kmer_g;        // low 16 bits of each indexed 22-mer
 	uint64_t n_seqf;
@@ -45,13 +47,21 @@ SEED_HD uint64_t get_kmer(uint32_t read_off, const uint64_t *read_bit)
 
 SEED_HD uint32_t base_at(const uint64_t *seq, uint64_t i) { return (uint32_t)(seq[i >> 5] >> ((31 - (i & 0x1f)) << 1)) & 3u; }
 
-// range of index k-mers equal to the read 20-mer: 14 bases through the bucket table, the remaining 6 against
+// range of index k-mers equal to the read 20-mer: 14 bases through the (compacted) bucket table, the remaining 6 against
 // kmer_g >> 4 by binary search for the first and last equal key.  false = no hit.
 SEED_HD bool search_kmer(const IndexView &ix, uint64_t kmer, int64_t range[2])
 {
 	const uint64_t key = kmer & 0xfff, h = kmer >> 12;
-	const uint64_t base = ix.hash[h];
-	const int64_t n = (int64_t)(ix.hash[h + 1] - base);
+	uint32_t blo = ix.bkt_dir[h >> 8];
+	const uint32_t bend = ix.bkt_dir[(h >> 8) + 1];
+	uint32_t bhi = bend;
+	while (blo < bhi) {                                // first non-empty bucket >= h among those sharing h's top 20 bits
+		const uint32_t m = (blo + bhi) >> 1;
+		if (ix.bkt_key[m] < (uint32_t)h) blo = m + 1; else bhi = m;
+	}
+	if (blo == bend || ix.bkt_key[blo] != (uint32_t)h) return false;   // hash_g[h+1] == hash_g[h]: empty bucket
+	const uint64_t base = ix.bkt_start[blo];
+	const int64_t n = (int64_t)(ix.bkt_start[blo + 1] - base);
 	const uint32_t *v = ix.kmer_g + base;
 	int64_t l = 0, r = n - 1;
 	while (l <= r) {

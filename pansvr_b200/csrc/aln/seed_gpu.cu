@@ -1,8 +1,8 @@
 // seed_gpu.cu -- device-resident deBGA index and the batched seed lookup kernel (stage B).
 //
-// The eight index arrays are uploaded once, in their on-disk layout (so lookups are trivially the
-// reference's: SURVEY.md section 3.3), and stay in HBM for the life of the service: 2 GiB of
-// bucket starts + k-mer/offset/unipath tables.  One thread per read strand runs seed_read_strand()
+// The index arrays are uploaded once and stay in HBM for the life of the service: the k-mer/offset/unipath tables in
+// their on-disk layout and the bucket table in its compacted form (index.hpp: the 2 GiB of bucket
+// starts reduce to the non-empty buckets plus a 4 MB directory, which also keeps the lookups in L2).  One thread per read strand runs seed_read_strand()
 // (seed_core.cuh): its probes are dependent random accesses, so throughput comes from having
 // every SM full of strands in flight, not from per-thread speed.  Two passes (count, exclusive
 // scan, fill) give a compact MEM list without a worst-case buffer per strand.
@@ -71,8 +71,8 @@ void staging_free(void *p) { if (p) cudaFreeHost(p); }
 struct SeedService {
 	int device = 0;
 	cudaStream_t stream = nullptr;
-	uint64_t *seqb = nullptr, *seqf = nullptr, *posp = nullptr, *hash = nullptr, *off_g = nullptr;
-	uint32_t *kmer_g = nullptr;
+	uint64_t *seqb = nullptr, *seqf = nullptr, *posp = nullptr, *bkt_start = nullptr, *off_g = nullptr;
+	uint32_t *kmer_g = nullptr, *bkt_dir = nullptr, *bkt_key = nullptr;
 	IndexView view;
 	Buf bits, list, jobs, count, off, mems, tmp;
 	size_t index_bytes = 0;
@@ -91,9 +91,12 @@ SeedService *seed_service_create(const DebgaIndex &idx, int device, std::string 
 	auto fail = [&]() -> SeedService* { seed_service_destroy(s); return nullptr; };
 	if (cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking) != cudaSuccess) { err = "cudaStreamCreate failed"; return fail(); }
 	if (!upload(idx.seqb, s->seqb, err) || !upload(idx.seqf, s->seqf, err) || !upload(idx.posp, s->posp, err) ||
-	    !upload(idx.hash, s->hash, err) || !upload(idx.off_g, s->off_g, err) || !upload(idx.kmer_g, s->kmer_g, err)) return fail();
-	s->index_bytes = (idx.seqb.size() + idx.seqf.size() + idx.posp.size() + idx.hash.size() + idx.off_g.size()) * 8 + idx.kmer_g.size() * 4;
-	s->view.seqb = s->seqb; s->view.seqf = s->seqf; s->view.posp = s->posp; s->view.hash = s->hash; s->view.off_g = s->off_g;
+	    !upload(idx.bkt_dir, s->bkt_dir, err) || !upload(idx.bkt_key, s->bkt_key, err) || !upload(idx.bkt_start, s->bkt_start, err) ||
+	    !upload(idx.off_g, s->off_g, err) || !upload(idx.kmer_g, s->kmer_g, err)) return fail();
+	s->index_bytes = (idx.seqb.size() + idx.seqf.size() + idx.posp.size() + idx.bkt_start.size() + idx.off_g.size()) * 8 +
+	                 (idx.kmer_g.size() + idx.bkt_dir.size() + idx.bkt_key.size()) * 4;
+	s->view.seqb = s->seqb; s->view.seqf = s->seqf; s->view.posp = s->posp; s->view.off_g = s->off_g;
+	s->view.bkt_dir = s->bkt_dir; s->view.bkt_key = s->bkt_key; s->view.bkt_start = s->bkt_start;
 	s->view.kmer_g = s->kmer_g; s->view.n_seqf = idx.seqf.size();
 	return s;
 }
@@ -102,7 +105,7 @@ void seed_service_destroy(SeedService *s)
 {
 	if (!s) return;
 	cudaSetDevice(s->device);
-	for (void *p : {(void*)s->seqb, (void*)s->seqf, (void*)s->posp, (void*)s->hash, (void*)s->off_g, (void*)s->kmer_g}) if (p) cudaFree(p);
+	for (void *p : {(void*)s->seqb, (void*)s->seqf, (void*)s->posp, (void*)s->bkt_dir, (void*)s->bkt_key, (void*)s->bkt_start, (void*)s->off_g, (void*)s->kmer_g}) if (p) cudaFree(p);
 	if (s->stream) cudaStreamDestroy(s->stream);
 	delete s;
 }

@@ -22,7 +22,8 @@ struct SeedService { IndexView view; };
 SeedService *seed_service_create(const DebgaIndex &idx, int, std::string &)
 {
 	SeedService *s = new SeedService();
-	s->view.seqb = idx.seqb.data(); s->view.seqf = idx.seqf.data(); s->view.posp = idx.posp.data(); s->view.hash = idx.hash.data();
+	s->view.seqb = idx.seqb.data(); s->view.seqf = idx.seqf.data(); s->view.posp = idx.posp.data();
+	s->view.bkt_dir = idx.bkt_dir.data(); s->view.bkt_key = idx.bkt_key.data(); s->view.bkt_start = idx.bkt_start.data();
 	s->view.off_g = idx.off_g.data(); s->view.kmer_g = idx.kmer_g.data(); s->view.n_seqf = idx.seqf.size();
 	return s;
 }
