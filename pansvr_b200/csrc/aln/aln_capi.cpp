@@ -164,12 +164,20 @@ int pansvr_aln_create(const char *index_dir, const char *header_sam, const pansv
 	c->opt = from_c(opt);
 	if (c->opt.threads <= 0) c->opt.threads = (int)std::min(32u, std::max(1u, std::thread::hardware_concurrency()));
 	std::string err;
+	const auto tick = []() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+	const bool timing = getenv("PANSVR_TIMING") != nullptr;
+	double t0 = tick();
+	auto lap = [&](const char *what) { if (timing) { const double t = tick(); fprintf(stderr, "[timing] create/%s %.3f s\n", what, t - t0); t0 = t; } };
 	if (!c->idx.load(index_dir, header_sam, err)) { g_aln_err = err; delete c; return PANSVR_E_ARG; }
+	lap("index files");
 	if (pansvr_ksw_create(device, &c->ksw) != 0) { g_aln_err = pansvr_last_error(); delete c; return PANSVR_E_CUDA; }
+	lap("ksw context (CUDA init)");
 	c->seeds = seed_service_create(c->idx, device, err);
 	if (!c->seeds) { g_aln_err = err; pansvr_ksw_destroy(c->ksw); delete c; return PANSVR_E_CUDA; }
+	lap("index upload");
 	c->pipe = new AlnPipeline(c->idx, c->opt, c->seeds, c->ksw);
 	c->bam_hdr.parse(c->idx.header_text);
+	lap("pipeline");
 	*out = c;
 	return 0;
 }
