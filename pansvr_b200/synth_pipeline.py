@@ -55,20 +55,25 @@ def _revcomp(a: np.ndarray) -> np.ndarray:
 def make_demo(workdir: str, seed: int = 7, genome_len: int = 200_000, n_sv: int = 25, sv_step: int = 7000,
               sv_lens=(60, 150, 400, 1000), alleles_per_locus: int = 1, pairs_per_sv: int = 40, read_len: int = 150,
               sub_rate: float = 0.01, frag=(300, 500), edge_len: int = 500, build_index: bool = True,
-              n_frac: float = 0.0) -> PipelineData:
+              n_frac: float = 0.0, n_chrom: int = 1, mate_elsewhere: float = 0.0) -> PipelineData:
     """SURVEY.md 8d config 1 with the defaults; alleles_per_locus > 1 gives config-3-like shared flanks
-    (several INS alleles at one locus => multi-candidate reads and exact score ties)."""
+    (several INS alleles at one locus => multi-candidate reads and exact score ties).  n_chrom > 1 spreads the loci
+    round-robin over chromosomes "1", "2", ...; mate_elsewhere is the fraction of pairs whose ORIGINAL alignment had the
+    mate on another chromosome (RNEXT / MATE_ fields of the -p output)."""
     os.makedirs(workdir, exist_ok=True)
     rng = np.random.default_rng(seed)
-    genome = ACGT[rng.integers(0, 4, genome_len)]
-    chrom = "1"
+    genomes = [ACGT[rng.integers(0, 4, genome_len)] for _ in range(n_chrom)]
+    chroms = [str(c + 1) for c in range(n_chrom)]
     ref_fa = os.path.join(workdir, "ref.fa")
     with open(ref_fa, "w") as f:
-        f.write(f">{chrom}\n{_wrap(genome.tobytes())}\n")
+        for chrom, genome in zip(chroms, genomes):
+            f.write(f">{chrom}\n{_wrap(genome.tobytes())}\n")
     # ---- variants
-    svs = []   # (pos1 (1-based, anchor base), type, ref_bytes, alt_bytes, id)
+    svs = []   # (pos1 (1-based, anchor base), type, ref_bytes, alt_bytes, id, chromosome index)
     for k in range(n_sv):
-        pos = 5000 + k * sv_step
+        ci = k % n_chrom
+        genome = genomes[ci]
+        pos = 5000 + (k // n_chrom) * sv_step
         if pos + 2000 > genome_len:
             break
         L = int(sv_lens[k % len(sv_lens)])
@@ -77,28 +82,31 @@ def make_demo(workdir: str, seed: int = 7, genome_len: int = 200_000, n_sv: int 
         for a in range(alleles_per_locus if kind == "INS" else 1):
             if kind == "INS":
                 ins = ACGT[rng.integers(0, 4, L + 37 * a)]
-                svs.append((pos, "INS", base.tobytes(), base.tobytes() + ins.tobytes(), f"sv{k}a{a}"))
+                svs.append((pos, "INS", base.tobytes(), base.tobytes() + ins.tobytes(), f"sv{k}a{a}", ci))
             else:
-                svs.append((pos, "DEL", genome[pos - 1:pos + L].tobytes(), base.tobytes(), f"sv{k}a{a}"))
+                svs.append((pos, "DEL", genome[pos - 1:pos + L].tobytes(), base.tobytes(), f"sv{k}a{a}", ci))
+    svs.sort(key=lambda v: v[5])        # the VCF is grouped by chromosome (stable: positions stay ascending)
     vcf = os.path.join(workdir, "sv.vcf")
     with open(vcf, "w") as f:
         f.write("##fileformat=VCFv4.2\n")
-        f.write(f"##contig=<ID={chrom},length={genome_len}>\n")
+        for chrom in chroms:
+            f.write(f"##contig=<ID={chrom},length={genome_len}>\n")
         f.write('##INFO=<ID=SVTYPE,Number=1,Type=String,Description="Type of structural variant">\n')
         f.write('##INFO=<ID=SVLEN,Number=1,Type=Integer,Description="Length of structural variant">\n')
         f.write("#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\n")
-        for pos, kind, r, a, vid in svs:
+        for pos, kind, r, a, vid, ci in svs:
             svlen = len(a) - len(r)
-            f.write(f"{chrom}\t{pos}\t{vid}\t{r.decode()}\t{a.decode()}\t.\tPASS\tSVTYPE={kind};SVLEN={svlen}\n")
+            f.write(f"{chroms[ci]}\t{pos}\t{vid}\t{r.decode()}\t{a.decode()}\t.\tPASS\tSVTYPE={kind};SVLEN={svlen}\n")
     header_sam = os.path.join(workdir, "header.sam")
     with open(header_sam, "w") as f:
-        f.write(f"@HD\tVN:1.6\tSO:coordinate\n@SQ\tSN:{chrom}\tLN:{genome_len}\n")
+        f.write("@HD\tVN:1.6\tSO:coordinate\n" + "".join(f"@SQ\tSN:{chrom}\tLN:{genome_len}\n" for chrom in chroms))
     # ---- read pairs from the ALT haplotype of each allele
     reads_fq = os.path.join(workdir, "reads.fq")
     n_pairs = 0
     with open(reads_fq, "w") as f:
         first = True
-        for si, (pos, kind, r, a, vid) in enumerate(svs):
+        for si, (pos, kind, r, a, vid, ci) in enumerate(svs):
+            genome = genomes[ci]
             lo = max(0, pos - 1 - 700)
             left = genome[lo:pos - 1]
             alt = np.frombuffer(a, dtype=np.uint8)
@@ -125,13 +133,16 @@ def make_demo(workdir: str, seed: int = 7, genome_len: int = 200_000, n_sv: int 
                 sc1 = 2 * (read_len - soft1) - int(rng.integers(10, 90))
                 sc2 = 2 * (read_len - soft2) - int(rng.integers(10, 90))
                 name = f"r{si}x{p}"
+                mate_tid = ci
+                if mate_elsewhere > 0 and rng.random() < mate_elsewhere:
+                    mate_tid = (ci + 1) % n_chrom
                 for mate, (rd, rp, sl, sc, fl, mfl, flag, mp) in enumerate((
                         (r1, ref_pos1, soft1, sc1, "FNNY", "RNNY", 99, ref_pos2),
                         (r2, ref_pos2, soft2, sc2, "RNNY", "FNNY", 147, ref_pos1))):
                     stat = f"STAT_{read_len}_{frag[0]}_{(frag[0] + frag[1]) // 2}_{frag[1]}_" if first and mate == 0 else ""
                     cig = (f"{sl}S{read_len - sl}M" if sl else f"{read_len}M")
-                    comment = (f"0_{rp}_{sl}_{sc}_60_60_0_0_{isize}_{fl}_{mfl}_{stat}FLAG_{flag}_60_CIGAR_{cig}_"
-                               f"MATE_0_{mp}_{isize if mate == 0 else -isize}_TAG_NM:i:{int(rng.integers(0, 6))}_")
+                    comment = (f"{ci}_{rp}_{sl}_{sc}_60_60_0_0_{isize}_{fl}_{mfl}_{stat}FLAG_{flag}_60_CIGAR_{cig}_"
+                               f"MATE_{mate_tid}_{mp}_{isize if mate == 0 else -isize}_TAG_NM:i:{int(rng.integers(0, 6))}_")
                     qual = "I" * read_len
                     f.write(f"@{name} {comment}\n{rd.tobytes().decode()}\n+\n{qual}\n")
                 first = False

@@ -15,6 +15,9 @@ DATASETS = {
     "demo": dict(),
     "multi_allele": dict(seed=21, genome_len=300_000, n_sv=40, alleles_per_locus=3, pairs_per_sv=30),
     "n_bases": dict(seed=22, n_sv=20, pairs_per_sv=30, n_frac=0.004),
+    # three chromosomes, a fifth of the original mates elsewhere (RNAME / RNEXT ids), 250 bp reads (BASELINE configs[3] shape)
+    "chroms_250bp": dict(seed=23, genome_len=120_000, n_sv=24, alleles_per_locus=2, pairs_per_sv=25, read_len=250, frag=(500, 700),
+                         n_chrom=3, mate_elsewhere=0.2, n_frac=0.0005),
 }
 
 

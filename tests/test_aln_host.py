@@ -71,6 +71,29 @@ def test_host_pipeline_matches_reference_sam(fc_aln_emul, name):
         demo.cleanup()
 
 
+def test_edge_inputs_match_reference(fc_aln_emul):
+    """Empty input, a single pair, a dangling unpaired read and a missing final newline: same files as the reference."""
+    need_ref_tools()
+    demo = Demo("demo")
+    try:
+        fq = read(demo.data.reads_fq).decode().split("\n")
+        cases = {"empty": "", "one_pair": "\n".join(fq[:8]) + "\n", "three_reads": "\n".join(fq[:12]) + "\n",
+                 "no_final_newline": "\n".join(fq[:16])}
+        for name, text in cases.items():
+            path = os.path.join(demo.wd, name + ".fq")
+            with open(path, "w") as f:
+                f.write(text)
+            d = sp.PipelineData(demo.data.workdir, demo.data.ref_fa, demo.data.vcf, demo.data.anchors_fa, demo.data.index_dir, path,
+                                demo.data.header_sam, 0, 0)
+            r, ro = os.path.join(demo.wd, name + "_ref.sam"), os.path.join(demo.wd, name + "_ref_ori.sam")
+            m, mo = os.path.join(demo.wd, name + "_my.sam"), os.path.join(demo.wd, name + "_my_ori.sam")
+            sp.run_reference_aln(d, r, ro, threads=1)
+            fc_aln_emul(d, m, mo, threads=2)
+            assert read(m) == read(r) and read(mo) == read(ro), name
+    finally:
+        demo.cleanup()
+
+
 def test_bam_records_and_writer_across_calls(fc_aln_emul):
     """pansvr_aln_block_bam + pansvr_bam_open/write/close through the C ABI of the host build: records written in several
     calls (open BGZF block carried over) give the reference's BAM file; every record equals its SAM line re-encoded."""
