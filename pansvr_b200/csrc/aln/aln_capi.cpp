@@ -25,7 +25,7 @@ struct pansvr_aln_ctx {
 	pansvr_ksw_ctx *ksw = nullptr;
 	AlnPipeline *pipe = nullptr;
 	BamHeaderInfo bam_hdr;
-	BlockOutput out;                  // chunk buffers of the record text, kept across blocks
+	std::vector<BlockOutput> outs;    // chunk buffers of the record text of every sub-block, kept across calls
 };
 
 struct pansvr_bam_file {
@@ -197,15 +197,46 @@ const char *pansvr_aln_last_error(void) { return g_aln_err.c_str(); }
 namespace {
 
 // parse + align one block; `outp` receives the record text of every pair
-int run_block(pansvr_aln_ctx *c, const char *fastq, size_t n, BlockOutput &outp)
+// parse + align one block; `text` receives, in input order, the buffers that hold the record text.
+// A large block is cut into sub-blocks and two of them are in flight at a time: the single-threaded in-order replay of one
+// overlaps the parallel stages of the next (AlnPipeline::align_block keeps the random streams in sequence).
+int run_block(pansvr_aln_ctx *c, const char *fastq, size_t n, std::vector<const std::string*> &sam, std::vector<const std::string*> &ori)
 {
 	const auto tick = []() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
 	const double t0 = tick();
 	std::vector<FastqRec> recs;
 	if (!parse_fastq_parallel(fastq, n, *c->pipe, c->opt.threads, recs)) parse_fastq(fastq, n, recs);
 	c->pipe->stats.t_stage[6] += tick() - t0;
-	std::string err;
-	if (!c->pipe->align_block(recs, outp, err)) { g_aln_err = err; return PANSVR_E_CUDA; }
+	const size_t n_pairs = recs.size() / 2;
+	size_t per = n_pairs;                                     // pairs per sub-block
+	if (c->opt.threads > 1 && n_pairs >= 65536) per = std::min<size_t>(262144, std::max<size_t>(32768, (n_pairs + 3) / 4));
+	if (const char *e = getenv("PANSVR_SUB_PAIRS")) { const long v = atol(e); if (v > 0) per = (size_t)v; }   // tests: force the cut
+	const size_t n_sub = n_pairs ? (n_pairs + per - 1) / per : 1;
+	if (c->outs.size() < n_sub) c->outs.resize(n_sub);
+	if (!recs.empty()) c->pipe->ensure_read_stats(recs[0]);
+	std::vector<std::string> errs(n_sub);
+	std::vector<uint8_t> ok(n_sub, 1);
+	std::vector<uint64_t> seqs(n_sub);
+	for (size_t k = 0; k < n_sub; ++k) seqs[k] = c->pipe->next_seq();
+	auto run_sub = [&](size_t k) {
+		const size_t pb = std::min(n_pairs, per * k), pe = std::min(n_pairs, per * (k + 1));
+		ok[k] = c->pipe->align_block(recs.data() + 2 * pb, 2 * (pe - pb), c->outs[k], errs[k], seqs[k]) ? 1 : 0;
+	};
+	if (n_sub == 1) run_sub(0);
+	else {
+		std::vector<std::thread> th(n_sub);
+		for (size_t k = 0; k < n_sub; ++k) {
+			if (k >= 2) th[k - 2].join();                       // two in flight
+			th[k] = std::thread(run_sub, k);
+		}
+		for (size_t k = n_sub >= 2 ? n_sub - 2 : 0; k < n_sub; ++k) th[k].join();
+	}
+	for (size_t k = 0; k < n_sub; ++k) if (!ok[k]) { g_aln_err = errs[k]; return PANSVR_E_CUDA; }
+	sam.clear(); ori.clear();
+	for (size_t k = 0; k < n_sub; ++k) {
+		for (const std::string &x : c->outs[k].sam) sam.push_back(&x);
+		for (const std::string &x : c->outs[k].ori) ori.push_back(&x);
+	}
 	return 0;
 }
 
@@ -228,25 +259,23 @@ int pansvr_aln_block(pansvr_aln_ctx *c, const char *fastq, size_t n, char **sam,
 {
 	if (!c || !fastq || !sam || !ori) return PANSVR_E_ARG;
 	CallReport report(c);
-	BlockOutput &outp = c->out;
-	const int rc = run_block(c, fastq, n, outp);
+	std::vector<const std::string*> text_sam, text_ori;
+	const int rc = run_block(c, fastq, n, text_sam, text_ori);
 	if (rc != 0) return rc;
 	const double t0 = CallReport::now();
-	auto join = [&](std::vector<std::string> &parts, char **out, size_t *bytes) -> bool {     // chunk buffers -> one malloc'ed text
+	auto join = [&](const std::vector<const std::string*> &parts, char **out, size_t *bytes) -> bool {     // chunk buffers -> one malloc'ed text
 		const size_t np = parts.size();
 		std::vector<size_t> off(np + 1, 0);
-		for (size_t i = 0; i < np; ++i) off[i + 1] = off[i] + parts[i].size();
+		for (size_t i = 0; i < np; ++i) off[i + 1] = off[i] + parts[i]->size();
 		char *buf = (char*)malloc(off[np] + 1);
 		if (!buf) return false;
-		std::vector<std::thread> th;
-		for (size_t i = 0; i < np; ++i) if (!parts[i].empty()) th.emplace_back([&, i]() { memcpy(buf + off[i], parts[i].data(), parts[i].size()); });
-		for (std::thread &x : th) x.join();
+		c->pipe->parallel(np, [&](size_t b, size_t e, int) { for (size_t i = b; i < e; ++i) if (!parts[i]->empty()) memcpy(buf + off[i], parts[i]->data(), parts[i]->size()); }, 2);
 		buf[off[np]] = 0;
 		*out = buf;
 		if (bytes) *bytes = off[np];
 		return true;
 	};
-	if (!join(outp.sam, sam, sam_bytes) || !join(outp.ori, ori, ori_bytes)) { g_aln_err = "out of memory"; return PANSVR_E_ARG; }
+	if (!join(text_sam, sam, sam_bytes) || !join(text_ori, ori, ori_bytes)) { g_aln_err = "out of memory"; return PANSVR_E_ARG; }
 	c->pipe->stats.t_stage[7] += CallReport::now() - t0;
 	return 0;
 }
@@ -256,11 +285,11 @@ int pansvr_aln_block_bam(pansvr_aln_ctx *c, const char *fastq, size_t n, uint8_t
 {
 	if (!c || !fastq || !bam || !ori) return PANSVR_E_ARG;
 	CallReport report(c);
-	BlockOutput &outp = c->out;
-	const int rc = run_block(c, fastq, n, outp);
+	std::vector<const std::string*> text_sam, text_ori;
+	const int rc = run_block(c, fastq, n, text_sam, text_ori);
 	if (rc != 0) return rc;
 	const double t0 = CallReport::now();
-	const size_t np = outp.sam.size();
+	const size_t np = text_sam.size();
 	std::vector<std::vector<uint8_t>> part_s(np), part_o(np);
 	std::vector<std::string> errs(np);
 	auto encode_lines = [&](const std::string &text, std::vector<uint8_t> &dst, std::string &err) {
@@ -272,11 +301,9 @@ int pansvr_aln_block_bam(pansvr_aln_ctx *c, const char *fastq, size_t n, uint8_t
 			p = e + 1;
 		}
 	};
-	{
-		std::vector<std::thread> th;                              // one thread per chunk buffer (as many as helper threads)
-		for (size_t i = 0; i < np; ++i) th.emplace_back([&, i]() { encode_lines(outp.sam[i], part_s[i], errs[i]); if (errs[i].empty()) encode_lines(outp.ori[i], part_o[i], errs[i]); });
-		for (std::thread &x : th) x.join();
-	}
+	c->pipe->parallel(np, [&](size_t b, size_t e, int) {
+		for (size_t i = b; i < e; ++i) { encode_lines(*text_sam[i], part_s[i], errs[i]); if (errs[i].empty()) encode_lines(*text_ori[i], part_o[i], errs[i]); }
+	}, 2);
 	for (const std::string &e : errs) if (!e.empty()) { g_aln_err = e; return PANSVR_E_ARG; }
 	auto join = [&](std::vector<std::vector<uint8_t>> &parts, uint8_t **out, size_t *bytes) -> bool {
 		size_t tot = 0;

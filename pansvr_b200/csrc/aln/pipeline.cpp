@@ -32,7 +32,7 @@ const int I32MAX = 0x7fffffff;
 // malloc arena: no cross-thread frees, no lock contention when a block of a million reads is torn down).
 struct AlnPipeline::Workers {
 	std::vector<std::thread> th;
-	std::mutex m;
+	std::mutex m, region;                                       // region: one parallel region at a time (two blocks may be in flight)
 	std::condition_variable go, done;
 	uint64_t generation = 0;
 	int chunks = 0, pending = 0;
@@ -68,6 +68,7 @@ struct AlnPipeline::Workers {
 	}
 	void run(int n_chunks, const std::function<void(int)> &f)
 	{
+		std::lock_guard<std::mutex> one_region(region);
 		std::unique_lock<std::mutex> lk(m);
 		job = &f; chunks = n_chunks; pending = n_chunks; ++generation;
 		go.notify_all();
@@ -997,8 +998,22 @@ AlnPipeline::AlnPipeline(const DebgaIndex &idx, const AlnOptions &o, SeedService
 
 AlnPipeline::~AlnPipeline() { delete workers_; }
 
+// read statistics from the first comment of the input (load_reads, RR:134-148); must have run before two blocks are in flight
+void AlnPipeline::ensure_read_stats(const FastqRec &first)
+{
+	if (opt.stat_set) return;
+	const std::string c0(first.comment, first.comment_l);
+	const char *st = strstr(c0.c_str(), "STAT_");
+	if (!st || sscanf(st + 5, "%d_%d_%d_%d_", &opt.read_len, &opt.isize_min, &opt.isize_mid, &opt.isize_max) == -1) {
+		opt.read_len = 150; opt.isize_min = 100; opt.isize_mid = 500; opt.isize_max = 900;
+	}
+	min_filter_score_ = std::max(opt.read_len * opt.match * 2 - 80, 50);
+	opt.stat_set = true;
+}
+
 void AlnPipeline::reset()
 {
+	replay_turn_ = 0; seq_issued_ = 0;
 	rand_.reseed(1);
 	stats = Stats();
 	opt.stat_set = false;
@@ -1006,10 +1021,18 @@ void AlnPipeline::reset()
 	for (int i = 0; i < 2; ++i) rand_r_[i].reseed((unsigned)rand_.next());
 }
 
-bool AlnPipeline::align_block(const std::vector<FastqRec> &recs, BlockOutput &out, std::string &err)
+bool AlnPipeline::align_block(const FastqRec *recs, size_t n_reads_in, BlockOutput &out, std::string &err, uint64_t seq)
 {
 	Impl I(*this);
-	const size_t n_reads = recs.size() & ~(size_t)1, n_pairs = n_reads / 2;
+	const size_t n_reads = n_reads_in & ~(size_t)1, n_pairs = n_reads / 2;
+	// in-order sections: wait until every earlier block has finished its replay; leave by passing the turn on
+	auto wait_turn = [&]() { std::unique_lock<std::mutex> lk(turn_m_); turn_cv_.wait(lk, [&]() { return replay_turn_ == seq; }); };
+	struct TurnGuard {                                                    // whatever happens, the next block must not wait for ever
+		AlnPipeline &P; uint64_t seq; bool passed = false;
+		void pass() { if (passed) return; passed = true; { std::lock_guard<std::mutex> lk(P.turn_m_); if (P.replay_turn_ == seq) P.replay_turn_ = seq + 1; } P.turn_cv_.notify_all(); }
+		~TurnGuard() { if (!passed) { std::unique_lock<std::mutex> lk(P.turn_m_); P.turn_cv_.wait(lk, [&]() { return P.replay_turn_ == seq; }); lk.unlock(); pass(); } }
+	} turn{*this, seq};
+	auto add_time = [&](int stage, double dt) { std::lock_guard<std::mutex> lk(stats_m_); stats.t_stage[stage] += dt; };
 	out.sam.resize((size_t)std::max(1, opt.threads));                     // the caller may keep `out` across blocks: capacity is reused
 	out.ori.resize((size_t)std::max(1, opt.threads));
 	for (std::string &x : out.sam) x.clear();
@@ -1017,16 +1040,7 @@ bool AlnPipeline::align_block(const std::vector<FastqRec> &recs, BlockOutput &ou
 	if (n_pairs == 0) return true;
 	double t0 = now();
 
-	// read statistics from the first comment (load_reads, RR:134-148)
-	if (!opt.stat_set) {
-		const std::string c0(recs[0].comment, recs[0].comment_l);
-		const char *st = strstr(c0.c_str(), "STAT_");
-		if (!st || sscanf(st + 5, "%d_%d_%d_%d_", &opt.read_len, &opt.isize_min, &opt.isize_mid, &opt.isize_max) == -1) {
-			opt.read_len = 150; opt.isize_min = 100; opt.isize_mid = 500; opt.isize_max = 900;
-		}
-		min_filter_score_ = std::max(opt.read_len * opt.match * 2 - 80, 50);
-		opt.stat_set = true;
-	}
+	ensure_read_stats(recs[0]);
 
 	// ---- stage A (parallel over reads; reads of a pair with an 'N' are left for the replay, see below)
 	const int T = std::max(1, opt.threads);
@@ -1124,7 +1138,7 @@ bool AlnPipeline::align_block(const std::vector<FastqRec> &recs, BlockOutput &ou
 			I.chain(g, edges);
 		}
 	};
-	SeedBatch &sb = seed_main_;
+	SeedBatch &sb = seed_main_[seq & 1];
 	sb.clear();
 	{
 		std::vector<uint32_t> word_off(n_all + 1, 0), job_of(n_all + 1, 0);
@@ -1166,11 +1180,14 @@ bool AlnPipeline::align_block(const std::vector<FastqRec> &recs, BlockOutput &ou
 			}
 		}
 	}
-	stats.t_stage[0] += now() - t0; t0 = now();
+	add_time(0, now() - t0); t0 = now();
 	// ---- stage B
-	if (!sb.jobs.empty() && !seed_service_run(seeds_, sb, err)) return false;
-	stats.mems += sb.mems.size();
-	stats.t_stage[1] += now() - t0; t0 = now();
+	{
+		std::lock_guard<std::mutex> dev(dev_m_);
+		if (!sb.jobs.empty() && !seed_service_run(seeds_, sb, err)) return false;
+	}
+	{ std::lock_guard<std::mutex> lk(stats_m_); stats.mems += sb.mems.size(); }
+	add_time(1, now() - t0); t0 = now();
 	// ---- stage C: reads whose expansion draws from the per-handler random_r stream go in input order, the rest in parallel
 	par_all([&](size_t b, size_t e, int) {
 		std::vector<Edge> edges;
@@ -1183,12 +1200,17 @@ bool AlnPipeline::align_block(const std::vector<FastqRec> &recs, BlockOutput &ou
 	});
 	std::vector<Edge> edges_main;
 	Impl::PlanScratch plan_main;
-	for (size_t i = 0; i < n_reads; ++i) if (rs[i].batched && rs[i].needs_rand) chain_read(rs[i], i, edges_main);
+	{
+		bool any = false;
+		for (size_t i = 0; i < n_reads && !any; ++i) any = rs[i].batched && rs[i].needs_rand;
+		if (any) wait_turn();                                              // random_r draws: after every earlier block's replay
+		for (size_t i = 0; i < n_reads; ++i) if (rs[i].batched && rs[i].needs_rand) chain_read(rs[i], i, edges_main);
+	}
 	for (size_t i = n_reads; i < n_all; ++i)                               // a variant that needs random_r: its read waits for its turn
 		if (rs[i].batched && rs[i].needs_rand) { rs[rs[i].var_of].in_order_only = true; rs[i].batched = false; }
-	stats.t_stage[2] += now() - t0; t0 = now();
+	add_time(2, now() - t0); t0 = now();
 	// ---- stage D: per-thread task lists, concatenated afterwards
-	KswBatchBuf &tasks = ksw_main_;
+	KswBatchBuf &tasks = ksw_main_[seq & 1];
 	{
 		std::vector<KswTaskList> part((size_t)T + 1);                      // one list per chunk of reads, the last one for the variants
 		std::vector<size_t> lo((size_t)T, 0), hi((size_t)T, 0);
@@ -1222,7 +1244,7 @@ bool AlnPipeline::align_block(const std::vector<FastqRec> &recs, BlockOutput &ou
 			}
 		}, 2);
 	}
-	stats.t_stage[3] += now() - t0; t0 = now();
+	add_time(3, now() - t0); t0 = now();
 	// ---- stage E
 	const int8_t m = (int8_t)opt.match, x = (int8_t)-opt.mismatch;
 	int8_t mat[25];
@@ -1237,8 +1259,10 @@ bool AlnPipeline::align_block(const std::vector<FastqRec> &recs, BlockOutput &ou
 		for (;;) {
 			int32_t *res; uint32_t *cig;
 			out_buffers(res, cig);
+			std::unique_lock<std::mutex> dev(dev_m_);
 			const int rc = pansvr_ksw_extd2_batch((pansvr_ksw_ctx*)ksw_, (int64_t)n, q, (int64_t)q_bytes, qoff, qlen, t, (int64_t)t_bytes, toff, tlen, &kp, res, cig, cap);
 			if (rc != 0) { err = std::string("ksw batch: ") + pansvr_last_error(); return false; }
+			dev.unlock();
 			std::atomic<int> need(0);
 			std::atomic<uint64_t> cells(0);
 			parallel(n, [&](size_t b, size_t e, int) {
@@ -1251,7 +1275,7 @@ bool AlnPipeline::align_block(const std::vector<FastqRec> &recs, BlockOutput &ou
 				int cur = need.load();
 				while (nd > cur && !need.compare_exchange_weak(cur, nd)) {}
 			});
-			if (!need.load()) { stats.ksw_tasks += n; stats.ksw_cells += cells.load(); return true; }
+			if (!need.load()) { std::lock_guard<std::mutex> lk(stats_m_); stats.ksw_tasks += n; stats.ksw_cells += cells.load(); return true; }
 			cap = need.load() + 8;
 		}
 	};
@@ -1268,7 +1292,7 @@ bool AlnPipeline::align_block(const std::vector<FastqRec> &recs, BlockOutput &ou
 			return false;
 	}
 	const KswView tasks_view{tasks.res.data(), tasks.cig.data(), tasks.cap};
-	stats.t_stage[4] += now() - t0; t0 = now();
+	add_time(4, now() - t0); t0 = now();
 
 	// ---- stage F: chain selection, result sort and pairing.  Only exact ties consume rand() (RR:247, RRH:553), so every
 	// pair is first finished on a worker thread against a probe; pairs that asked for a random number, and the deferred
@@ -1291,11 +1315,12 @@ bool AlnPipeline::align_block(const std::vector<FastqRec> &recs, BlockOutput &ou
 		}
 	});
 	const double t_probe = now() - t0;
-	size_t n_redo = 0, n_in_order = 0;
+	size_t n_redo = 0, n_in_order = 0, n_deferred = 0, n_mems_late = 0;
 	RandTap real; real.real = &rand_;
 	// the replay walks cold per-read data on one thread: pull the state of the pairs a few steps ahead into the cache
 	std::vector<uint32_t> redo_list;
 	for (size_t pi = 0; pi < n_pairs; ++pi) if (redo[pi]) redo_list.push_back((uint32_t)pi);
+	wait_turn();                                                          // ---- in input order from here: the rand() stream
 	auto prefetch_state = [&](size_t k) { if (k < redo_list.size()) { const char *p = (const char*)&rs[2 * (size_t)redo_list[k]]; for (size_t o = 0; o < 2 * sizeof(ReadState); o += 64) __builtin_prefetch(p + o); } };
 	auto prefetch_arrays = [&](size_t k) {
 		if (k >= redo_list.size()) return;
@@ -1316,7 +1341,7 @@ bool AlnPipeline::align_block(const std::vector<FastqRec> &recs, BlockOutput &ou
 		++n_redo;
 		ReadState *se = &rs[2 * pi];
 		if (se[0].has_n || se[1].has_n) {                                 // deferred pair: its rand() draws happen now
-			++stats.deferred_pairs;
+			++n_deferred;
 			KswTaskList local;
 			bool own[2] = {false, false};
 			for (int k = 0; k < 2; ++k) {
@@ -1335,8 +1360,11 @@ bool AlnPipeline::align_block(const std::vector<FastqRec> &recs, BlockOutput &ou
 					one.clear();
 					prepare_read(r);
 					register_jobs(r, one);
-					if (!seed_service_run(seeds_, one, err)) return false;
-					stats.mems += one.mems.size();
+					{
+						std::lock_guard<std::mutex> dev(dev_m_);
+						if (!seed_service_run(seeds_, one, err)) return false;
+					}
+					n_mems_late += one.mems.size();
 					merge_read(r, one);
 					chain_read(r, 2 * pi + k, edges_main);
 					I.plan_read(r, local, plan_main);
@@ -1350,7 +1378,8 @@ bool AlnPipeline::align_block(const std::vector<FastqRec> &recs, BlockOutput &ou
 		I.pair_up(se, pes[pi], real);
 		if (pes[pi].gain) I.set_primary(se, pes[pi]);
 	}
-	stats.reads += 2 * n_pairs;
+	turn.pass();                                                          // the next block may replay now
+	{ std::lock_guard<std::mutex> lk(stats_m_); stats.reads += 2 * n_pairs; stats.deferred_pairs += n_deferred; stats.mems += n_mems_late; }
 	if (getenv("PANSVR_TIMING"))
 		fprintf(stderr, "[timing] finish: probe %.3f s, in-order replay of %zu/%zu pairs %.3f s (%zu variant states for reads with N, %zu reads prepared in order)\n",
 		        t_probe, n_redo, n_pairs, now() - t0 - t_probe, n_var, n_in_order);
@@ -1386,7 +1415,7 @@ bool AlnPipeline::align_block(const std::vector<FastqRec> &recs, BlockOutput &ou
 		}
 		sam.swap(out.sam[(size_t)t]); ori.swap(out.ori[(size_t)t]);
 	});
-	stats.t_stage[5] += now() - t0;
+	add_time(5, now() - t0);
 	if (timing) fprintf(stderr, "[timing]   F/record text %.3f s\n", now() - t_text);
 	if (getenv("PANSVR_TIMING")) { double a = 0; for (int i = 0; i < 6; ++i) a += stats.t_stage[i]; fprintf(stderr, "[timing] align_block body done, stages A-F %.3f s\n", a); }
 	return true;

@@ -22,7 +22,9 @@
 #pragma once
 #include <stdint.h>
 #include <string.h>
+#include <condition_variable>
 #include <functional>
+#include <mutex>
 #include <new>
 #include <map>
 #include <string>
@@ -131,8 +133,13 @@ public:
 	AlnPipeline &operator=(const AlnPipeline&) = delete;
 	// static-chunk parallel loop over [0,n) on the pipeline's helper threads: fn(begin, end, chunk_index)
 	void parallel(size_t n, const std::function<void(size_t, size_t, int)> &fn, size_t serial_below = 256);
-	// Aligns n_pairs interleaved pairs (recs[2i], recs[2i+1]); `out` receives the SAM text in input order.
-	bool align_block(const std::vector<FastqRec> &recs, BlockOutput &out, std::string &err);
+	// Aligns n_reads/2 interleaved pairs (recs[2i], recs[2i+1]); `out` receives the SAM text in input order.
+	// Blocks are numbered by the caller (`seq` = 0, 1, 2, ... since the last reset) and two blocks with consecutive numbers
+	// may be in flight on two threads: everything that consumes a random stream is serialised in `seq` order inside, the
+	// rest (stages A-E, the probe, the record text) of one block overlaps the in-order replay of the other.
+	bool align_block(const FastqRec *recs, size_t n_reads, BlockOutput &out, std::string &err, uint64_t seq);
+	uint64_t next_seq() { return seq_issued_++; }
+	void ensure_read_stats(const FastqRec &first);   // STAT_ fields of the input's first comment; call before overlapping blocks
 	void reset();                     // back to the state of a freshly started `fc_aln` (rand() streams, counters)
 	struct Stats { uint64_t reads = 0, probes_reads = 0, mems = 0, ksw_tasks = 0, ksw_cells = 0, deferred_pairs = 0;
 	               double t_stage[8] = {0, 0, 0, 0, 0, 0, 0, 0}; } stats;   // A..F, FASTQ parse, output assembly
@@ -144,8 +151,13 @@ private:
 	const DebgaIndex &idx_;
 	SeedService *seeds_;
 	void *ksw_;
-	SeedBatch seed_main_, seed_small_;    // batch buffers live across blocks (staging memory is pinned once)
-	KswBatchBuf ksw_main_;
+	SeedBatch seed_main_[2], seed_small_; // batch buffers live across blocks (staging memory is pinned once); slot = seq & 1
+	KswBatchBuf ksw_main_[2];
+	std::mutex dev_m_;                    // the two device services take one batch at a time
+	std::mutex stats_m_;
+	std::mutex turn_m_;                   // blocks take their in-order sections by sequence number
+	std::condition_variable turn_cv_;
+	uint64_t replay_turn_ = 0, seq_issued_ = 0;
 	GlibcRandom rand_;                // the process-global rand() of the reference
 	GlibcRandom rand_r_[2];           // per-handler random_r states (RRH:339-340), seeded from rand_ at start-up
 	int min_filter_score_ = 0;

@@ -21,9 +21,10 @@ def fc_aln_emul():
     subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle"), os.path.join(ROOT, "oracle", "libksw_oracle.so")])
     env = dict(os.environ, PANSVR_ORACLE_SO=os.path.join(ROOT, "oracle", "libksw_oracle.so"))
 
-    def run(d, out, ori, extra=("-S",), threads=1):
+    def run(d, out, ori, extra=("-S",), threads=1, sub_pairs=0):
+        e = dict(env, PANSVR_SUB_PAIRS=str(sub_pairs)) if sub_pairs else env
         subprocess.check_call([os.path.join(HERE, "emul", "fc_aln_emul"), "-t", str(threads), "-o", out, "-p", ori, *extra,
-                               d.index_dir, d.reads_fq, d.header_sam], env=env, stderr=subprocess.DEVNULL)
+                               d.index_dir, d.reads_fq, d.header_sam], env=e, stderr=subprocess.DEVNULL)
     return run
 
 
@@ -60,6 +61,9 @@ def test_host_pipeline_matches_reference_sam(fc_aln_emul, name):
         if name == "demo":      # and the recorded fixture of the reference's output for this seed
             assert read(demo.ref_sam) == golden("aln_demo.sam.gz")
             assert read(demo.ref_ori) == golden("aln_demo_ori.sam.gz")
+        # the block cut into overlapping sub-blocks (two in flight, in-order sections passed on by sequence number)
+        fc_aln_emul(demo.data, out, ori, threads=4, sub_pairs=97)
+        assert read(out) == read(demo.ref_sam) and read(ori) == read(demo.ref_ori)
         # BAM mode (the reference's default): whole files byte-identical, BGZF blocks and deflate streams included
         rb, rbo = os.path.join(demo.wd, "ref.bam"), os.path.join(demo.wd, "ref_ori.bam")
         sp.run_reference_aln(demo.data, rb, rbo, threads=1, bam=True)
