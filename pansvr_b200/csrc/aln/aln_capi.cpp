@@ -5,7 +5,11 @@
 #include <string.h>
 #include <zlib.h>
 #include <algorithm>
+#include <atomic>
 #include <chrono>
+#include <condition_variable>
+#include <deque>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -132,6 +136,33 @@ bool parse_fastq_parallel(const char *p, size_t n, AlnPipeline &pipe, int thread
 	for (uint8_t x : bad) if (x) { out.clear(); return false; }
 	return true;
 }
+
+// bounded hand-over between the three steps of the command line
+template <class T> class Queue {
+public:
+	explicit Queue(size_t depth) : depth_(depth) {}
+	void push(T &&v)
+	{
+		std::unique_lock<std::mutex> lk(m_);
+		room_.wait(lk, [&]() { return q_.size() < depth_; });
+		q_.push_back(std::move(v));
+		item_.notify_one();
+	}
+	T pop()
+	{
+		std::unique_lock<std::mutex> lk(m_);
+		item_.wait(lk, [&]() { return !q_.empty(); });
+		T v = std::move(q_.front());
+		q_.pop_front();
+		room_.notify_one();
+		return v;
+	}
+private:
+	size_t depth_;
+	std::deque<T> q_;
+	std::mutex m_;
+	std::condition_variable room_, item_;
+};
 
 AlnOptions from_c(const pansvr_aln_options_t *o)
 {
@@ -436,43 +467,70 @@ int pansvr_fc_aln_main(int argc, char **argv)
 	}
 	gzFile in = strcmp(argv[optind + 1], "-") == 0 ? gzdopen(0, "r") : gzopen(argv[optind + 1], "r");
 	if (!in) { fprintf(stderr, "pansvr_b200 fc_aln: cannot open %s\n", argv[optind + 1]); return 1; }
-	// blocks of at most 2 M pairs / 100 Mbp like load_reads (RR:109,126)
-	std::string block;
-	std::vector<char> buf(1 << 20);
-	long pairs_in_block = 0, lines = 0, bases = 0, total_pairs = 0;
+	gzbuffer(in, 1 << 20);
+	// Three overlapping steps like the reference's kt_pipeline (RR:110-119): a reader thread cuts the input into blocks at
+	// pair boundaries, this thread aligns them in order, a writer thread puts the records out.  The block size is ours
+	// (512 k pairs): the output does not depend on it.
+	struct Job { std::string fastq; bool last = false; };
+	struct Result { void *main = nullptr, *ori = nullptr; size_t main_n = 0, ori_n = 0; bool last = false; };
 	const long max_pairs = o.max_use_read > 0 ? o.max_use_read : 0x7fffffff;
-	auto flush = [&]() -> bool {
-		if (block.empty()) return true;
-		if (sam) {
-			char *s = nullptr, *r = nullptr; size_t sl = 0, rl = 0;
-			if (pansvr_aln_block(ctx, block.data(), block.size(), &s, &sl, &r, &rl) != 0) { fprintf(stderr, "pansvr_b200 fc_aln: %s\n", pansvr_aln_last_error()); return false; }
-			fwrite(s, 1, sl, fo); fwrite(r, 1, rl, fp);
-			pansvr_free(s); pansvr_free(r);
-		} else {
-			uint8_t *s = nullptr, *r = nullptr; size_t sl = 0, rl = 0;
-			if (pansvr_aln_block_bam(ctx, block.data(), block.size(), &s, &sl, &r, &rl) != 0 ||
-			    pansvr_bam_write(bo, s, sl) != 0 || pansvr_bam_write(bp, r, rl) != 0) {
-				fprintf(stderr, "pansvr_b200 fc_aln: %s\n", pansvr_aln_last_error());
-				return false;
+	Queue<Job> jobs(2);
+	Queue<Result> results(2);
+	std::atomic<bool> failed(false);
+	std::thread reader([&]() {
+		std::string cur;
+		std::vector<char> chunk(4 << 20);
+		long lines = 0, total_pairs = 0, pairs_in_block = 0;
+		size_t boundary = 0;                                    // end of the last complete pair in `cur`
+		bool stop = false;
+		auto hand_over = [&](size_t upto, bool last) {
+			Job j; j.fastq.assign(cur, 0, upto); j.last = last;
+			cur.erase(0, upto); boundary = 0; pairs_in_block = 0;
+			jobs.push(std::move(j));
+		};
+		while (!stop && !failed) {
+			const int got = gzread(in, chunk.data(), (unsigned)chunk.size());
+			if (got <= 0) break;
+			const size_t base = cur.size();
+			cur.append(chunk.data(), (size_t)got);
+			for (const char *q = cur.data() + base, *e = cur.data() + cur.size(); (q = (const char*)memchr(q, '\n', (size_t)(e - q))) != nullptr; ++q) {
+				if (++lines % 8 != 0) continue;
+				boundary = (size_t)(q - cur.data()) + 1;
+				++pairs_in_block;
+				if (++total_pairs >= max_pairs) { stop = true; break; }
 			}
-			pansvr_free(s); pansvr_free(r);
+			if (stop) { cur.resize(boundary); break; }
+			if (pairs_in_block >= 524288 || boundary >= ((size_t)256 << 20)) hand_over(boundary, false);
 		}
-		block.clear(); pairs_in_block = 0; bases = 0;
-		return true;
-	};
+		hand_over(cur.size(), true);                            // whatever is left (an unterminated last line included)
+	});
+	std::thread writer([&]() {
+		for (;;) {
+			Result r = results.pop();
+			if (!failed) {
+				if (sam) { if (fwrite(r.main, 1, r.main_n, fo) != r.main_n || fwrite(r.ori, 1, r.ori_n, fp) != r.ori_n) failed = true; }
+				else if (pansvr_bam_write(bo, (const uint8_t*)r.main, r.main_n) != 0 || pansvr_bam_write(bp, (const uint8_t*)r.ori, r.ori_n) != 0) failed = true;
+			}
+			pansvr_free(r.main); pansvr_free(r.ori);
+			if (r.last) break;
+		}
+	});
 	bool ok = true;
-	while (ok && total_pairs < max_pairs && gzgets(in, buf.data(), (int)buf.size())) {
-		const size_t l = strlen(buf.data());
-		block.append(buf.data(), l);
-		if (l && buf[l - 1] != '\n') continue;                 // long line, keep reading
-		++lines;
-		if (lines % 4 == 2) bases += (long)l;
-		if (lines % 8 == 0) {
-			++pairs_in_block; ++total_pairs;
-			if (pairs_in_block >= 2000000 || bases >= 100000000) ok = flush();
+	for (;;) {
+		Job j = jobs.pop();
+		Result r; r.last = j.last;
+		if (ok && !failed && !j.fastq.empty()) {
+			int rc;
+			if (sam) rc = pansvr_aln_block(ctx, j.fastq.data(), j.fastq.size(), (char**)&r.main, &r.main_n, (char**)&r.ori, &r.ori_n);
+			else rc = pansvr_aln_block_bam(ctx, j.fastq.data(), j.fastq.size(), (uint8_t**)&r.main, &r.main_n, (uint8_t**)&r.ori, &r.ori_n);
+			if (rc != 0) { fprintf(stderr, "pansvr_b200 fc_aln: %s\n", pansvr_aln_last_error()); ok = false; failed = true; }
 		}
+		results.push(std::move(r));
+		if (j.last) break;
 	}
-	if (ok) ok = flush();
+	reader.join();
+	writer.join();
+	if (failed && ok) { fprintf(stderr, "pansvr_b200 fc_aln: writing the output failed: %s\n", pansvr_aln_last_error()); ok = false; }
 	gzclose(in);
 	if (sam) { fclose(fo); fclose(fp); }
 	else if (pansvr_bam_close(bo) != 0 || pansvr_bam_close(bp) != 0) { fprintf(stderr, "pansvr_b200 fc_aln: %s\n", pansvr_aln_last_error()); ok = false; }

@@ -94,6 +94,19 @@ def test_edge_inputs_match_reference(fc_aln_emul):
             sp.run_reference_aln(d, r, ro, threads=1)
             fc_aln_emul(d, m, mo, threads=2)
             assert read(m) == read(r) and read(mo) == read(ro), name
+        # gzip-compressed input, and -R (max_use_read) cutting the input after 100 pairs
+        gz = os.path.join(demo.wd, "reads.fq.gz")
+        with open(demo.data.reads_fq, "rb") as f, gzip.open(gz, "wb", compresslevel=1) as g:
+            g.write(f.read())
+        d = sp.PipelineData(demo.data.workdir, demo.data.ref_fa, demo.data.vcf, demo.data.anchors_fa, demo.data.index_dir, gz,
+                            demo.data.header_sam, 0, 0)
+        m, mo = os.path.join(demo.wd, "gz_my.sam"), os.path.join(demo.wd, "gz_my_ori.sam")
+        fc_aln_emul(d, m, mo, threads=2)
+        assert read(m) == read(demo.ref_sam) and read(mo) == read(demo.ref_ori)
+        r, ro = os.path.join(demo.wd, "r100_ref.sam"), os.path.join(demo.wd, "r100_ref_ori.sam")
+        sp.run_reference_aln(demo.data, r, ro, threads=1, extra=("-R", "100"))
+        fc_aln_emul(demo.data, m, mo, extra=("-S", "-R", "100"), threads=2)
+        assert read(m) == read(r) and read(mo) == read(ro)
     finally:
         demo.cleanup()
 
