@@ -199,10 +199,16 @@ int pansvr_aln_create(const char *index_dir, const char *header_sam, const pansv
 	const bool timing = getenv("PANSVR_TIMING") != nullptr;
 	double t0 = tick();
 	auto lap = [&](const char *what) { if (timing) { const double t = tick(); fprintf(stderr, "[timing] create/%s %.3f s\n", what, t - t0); t0 = t; } };
-	if (!c->idx.load(index_dir, header_sam, err)) { g_aln_err = err; delete c; return PANSVR_E_ARG; }
-	lap("index files");
-	if (pansvr_ksw_create(device, &c->ksw) != 0) { g_aln_err = pansvr_last_error(); delete c; return PANSVR_E_CUDA; }
+	// the index files are read (and the bucket table compacted) while the CUDA runtime starts up
+	bool idx_ok = false;
+	std::string idx_err;
+	std::thread loader([&]() { idx_ok = c->idx.load(index_dir, header_sam, idx_err); });
+	const int ksw_rc = pansvr_ksw_create(device, &c->ksw);
 	lap("ksw context (CUDA init)");
+	loader.join();
+	lap("index files (remainder)");
+	if (!idx_ok) { g_aln_err = idx_err; if (ksw_rc == 0) pansvr_ksw_destroy(c->ksw); delete c; return PANSVR_E_ARG; }
+	if (ksw_rc != 0) { g_aln_err = pansvr_last_error(); delete c; return PANSVR_E_CUDA; }
 	c->seeds = seed_service_create(c->idx, device, err);
 	if (!c->seeds) { g_aln_err = err; pansvr_ksw_destroy(c->ksw); delete c; return PANSVR_E_CUDA; }
 	lap("index upload");
@@ -451,23 +457,10 @@ int pansvr_fc_aln_main(int argc, char **argv)
 		fprintf(stderr, "Usage: fc_aln [Options] <IndexDir> <ReadFiles.fq|-> <ori_header.sam>\n");
 		return 1;
 	}
-	pansvr_aln_ctx *ctx = nullptr;
-	int rc = pansvr_aln_create(argv[optind], argv[optind + 2], &o, device, &ctx);
-	if (rc != 0) { fprintf(stderr, "pansvr_b200 fc_aln: %s\n", pansvr_aln_last_error()); return 1; }
-	FILE *fo = nullptr, *fp = nullptr;
-	pansvr_bam_file *bo = nullptr, *bp = nullptr;
-	if (sam) {
-		fo = fopen(out_path.c_str(), "w"); fp = fopen(ori_path.c_str(), "w");
-		if (!fo || !fp) { fprintf(stderr, "pansvr_b200 fc_aln: cannot open the output files\n"); return 1; }
-		fputs(pansvr_aln_header_text(ctx), fo);
-		fputs(pansvr_aln_header_text(ctx), fp);
-	} else if (pansvr_bam_open(ctx, out_path.c_str(), &bo) != 0 || pansvr_bam_open(ctx, ori_path.c_str(), &bp) != 0) {
-		fprintf(stderr, "pansvr_b200 fc_aln: %s\n", pansvr_aln_last_error());
-		return 1;
-	}
 	gzFile in = strcmp(argv[optind + 1], "-") == 0 ? gzdopen(0, "r") : gzopen(argv[optind + 1], "r");
 	if (!in) { fprintf(stderr, "pansvr_b200 fc_aln: cannot open %s\n", argv[optind + 1]); return 1; }
 	gzbuffer(in, 1 << 20);
+	// The input is opened first: the reader fills its queue while the context is created (CUDA start-up, index files).
 	// Three overlapping steps like the reference's kt_pipeline (RR:110-119): a reader thread cuts the input into blocks at
 	// pair boundaries, this thread aligns them in order, a writer thread puts the records out.  The block size is ours
 	// (512 k pairs): the output does not depend on it.
@@ -504,6 +497,22 @@ int pansvr_fc_aln_main(int argc, char **argv)
 		}
 		hand_over(cur.size(), true);                            // whatever is left (an unterminated last line included)
 	});
+	pansvr_aln_ctx *ctx = nullptr;
+	int rc = pansvr_aln_create(argv[optind], argv[optind + 2], &o, device, &ctx);
+	auto stop_reader = [&]() { failed = true; for (;;) { Job j = jobs.pop(); if (j.last) break; } reader.join(); gzclose(in); };
+	if (rc != 0) { fprintf(stderr, "pansvr_b200 fc_aln: %s\n", pansvr_aln_last_error()); stop_reader(); return 1; }
+	FILE *fo = nullptr, *fp = nullptr;
+	pansvr_bam_file *bo = nullptr, *bp = nullptr;
+	if (sam) {
+		fo = fopen(out_path.c_str(), "w"); fp = fopen(ori_path.c_str(), "w");
+		if (!fo || !fp) { fprintf(stderr, "pansvr_b200 fc_aln: cannot open the output files\n"); stop_reader(); return 1; }
+		fputs(pansvr_aln_header_text(ctx), fo);
+		fputs(pansvr_aln_header_text(ctx), fp);
+	} else if (pansvr_bam_open(ctx, out_path.c_str(), &bo) != 0 || pansvr_bam_open(ctx, ori_path.c_str(), &bp) != 0) {
+		fprintf(stderr, "pansvr_b200 fc_aln: %s\n", pansvr_aln_last_error());
+		stop_reader();
+		return 1;
+	}
 	std::thread writer([&]() {
 		for (;;) {
 			Result r = results.pop();
