@@ -156,7 +156,7 @@ def main():
     ap.add_argument("--tasks", type=int, default=1_000_000, help="tasks (reads) per GPU per step")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--ref-sample", type=int, default=200_000, help="tasks per step of the CPU reference arm")
-    ap.add_argument("--cpu-sample", type=int, default=150_000, help="tasks of the cpu_baseline leg")
+    ap.add_argument("--cpu-sample", type=int, default=600_000, help="tasks of the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
