@@ -55,11 +55,15 @@ def _revcomp(a: np.ndarray) -> np.ndarray:
 def make_demo(workdir: str, seed: int = 7, genome_len: int = 200_000, n_sv: int = 25, sv_step: int = 7000,
               sv_lens=(60, 150, 400, 1000), alleles_per_locus: int = 1, pairs_per_sv: int = 40, read_len: int = 150,
               sub_rate: float = 0.01, frag=(300, 500), edge_len: int = 500, build_index: bool = True,
-              n_frac: float = 0.0, n_chrom: int = 1, mate_elsewhere: float = 0.0) -> PipelineData:
+              n_frac: float = 0.0, n_chrom: int = 1, mate_elsewhere: float = 0.0, str_every: int = 0,
+              shared_insert: int = 0) -> PipelineData:
     """SURVEY.md 8d config 1 with the defaults; alleles_per_locus > 1 gives config-3-like shared flanks
     (several INS alleles at one locus => multi-candidate reads and exact score ties).  n_chrom > 1 spreads the loci
     round-robin over chromosomes "1", "2", ...; mate_elsewhere is the fraction of pairs whose ORIGINAL alignment had the
-    mate on another chromosome (RNEXT / MATE_ fields of the -p output)."""
+    mate on another chromosome (RNEXT / MATE_ fields of the -p output).  str_every = k makes every k-th inserted allele a
+    short tandem repeat (unit 2-6 bp) so that reads from it take the STR branch of the seeding loop (RR:553-598);
+    shared_insert = L puts one common L-bp element into every inserted allele, so its unipath has as many reference
+    positions as there are INS alleles (> 500 of them switch expand_seed to its random_r sampling, IDX:219-258)."""
     os.makedirs(workdir, exist_ok=True)
     rng = np.random.default_rng(seed)
     genomes = [ACGT[rng.integers(0, 4, genome_len)] for _ in range(n_chrom)]
@@ -82,6 +86,13 @@ def make_demo(workdir: str, seed: int = 7, genome_len: int = 200_000, n_sv: int 
         for a in range(alleles_per_locus if kind == "INS" else 1):
             if kind == "INS":
                 ins = ACGT[rng.integers(0, 4, L + 37 * a)]
+                if str_every and (k // 2) % str_every == 0:
+                    unit = ACGT[rng.integers(0, 4, int(rng.integers(2, 7)))]
+                    ins = np.tile(unit, (L + 37 * a) // unit.size + 1)[:L + 37 * a]
+                if shared_insert:
+                    if k == 0 and a == 0:
+                        make_demo._common = ACGT[np.random.default_rng(seed + 1000).integers(0, 4, shared_insert)]
+                    ins = np.concatenate([ins[:ins.size // 2], make_demo._common, ins[ins.size // 2:]])
                 svs.append((pos, "INS", base.tobytes(), base.tobytes() + ins.tobytes(), f"sv{k}a{a}", ci))
             else:
                 svs.append((pos, "DEL", genome[pos - 1:pos + L].tobytes(), base.tobytes(), f"sv{k}a{a}", ci))

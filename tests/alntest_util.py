@@ -18,6 +18,11 @@ DATASETS = {
     # three chromosomes, a fifth of the original mates elsewhere (RNAME / RNEXT ids), 250 bp reads (BASELINE configs[3] shape)
     "chroms_250bp": dict(seed=23, genome_len=120_000, n_sv=24, alleles_per_locus=2, pairs_per_sv=25, read_len=250, frag=(500, 700),
                          n_chrom=3, mate_elsewhere=0.2, n_frac=0.0005),
+    # inserted alleles that are short tandem repeats: the STR branch of the seeding loop and of the chain parameters
+    "tandem_repeats": dict(seed=24, genome_len=160_000, n_sv=40, sv_lens=(120, 200, 300, 500), str_every=2, pairs_per_sv=30),
+    # one 150 bp element shared by 520 inserted alleles: its unipath has > 500 positions, expand_seed samples them with random_r
+    "shared_element": dict(seed=25, genome_len=5000 + 7000 * 520 + 4000, n_sv=520, alleles_per_locus=2, pairs_per_sv=2,
+                           shared_insert=150, sv_lens=(200, 300, 400)),
 }
 
 
