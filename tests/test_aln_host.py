@@ -111,6 +111,23 @@ def test_edge_inputs_match_reference(fc_aln_emul):
         demo.cleanup()
 
 
+@pytest.mark.parametrize("opts", [("-Q",), ("-M", "1", "-m", "4", "-O", "6", "-E", "2", "-P", "24", "-F", "1", "-z", "200"),
+                                  ("-M", "3", "-m", "9", "-O", "20", "-E", "3", "-P", "40", "-F", "1", "-z", "100", "-Q", "-w", "50")],
+                         ids=["not_ori", "soft_scoring", "hard_scoring"])
+def test_command_line_options_match_reference(fc_aln_emul, opts):
+    """MAP_PARA::get_option (read_realignment.hpp:82-128): scoring, z-drop, -Q and the ignored -w."""
+    need_ref_tools()
+    demo = Demo("n_bases")
+    try:
+        r, ro = os.path.join(demo.wd, "opt_ref.sam"), os.path.join(demo.wd, "opt_ref_ori.sam")
+        m, mo = os.path.join(demo.wd, "opt_my.sam"), os.path.join(demo.wd, "opt_my_ori.sam")
+        sp.run_reference_aln(demo.data, r, ro, threads=1, extra=opts)
+        fc_aln_emul(demo.data, m, mo, extra=("-S",) + tuple(opts), threads=3)
+        assert read(m) == read(r) and read(mo) == read(ro)
+    finally:
+        demo.cleanup()
+
+
 def test_bam_records_and_writer_across_calls(fc_aln_emul):
     """pansvr_aln_block_bam + pansvr_bam_open/write/close through the C ABI of the host build: records written in several
     calls (open BGZF block carried over) give the reference's BAM file; every record equals its SAM line re-encoded."""
