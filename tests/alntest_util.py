@@ -46,6 +46,18 @@ class Demo:
         shutil.rmtree(self.wd, ignore_errors=True)
 
 
+_DEMOS = {}
+
+
+def get_demo(name):
+    """One shared Demo per data set and test session (index build + reference run are the expensive part)."""
+    import atexit
+    if name not in _DEMOS:
+        _DEMOS[name] = Demo(name)
+        atexit.register(_DEMOS[name].cleanup)
+    return _DEMOS[name]
+
+
 def read(path):
     with open(path, "rb") as f:
         return f.read()

@@ -6,7 +6,7 @@ import os
 import pytest
 
 from pansvr_b200 import aln, synth_pipeline as sp
-from tests.alntest_util import DATASETS, Demo, first_diff, golden, need_ref_tools, read
+from tests.alntest_util import DATASETS, get_demo, first_diff, golden, need_ref_tools, read
 
 pytestmark = pytest.mark.gpu
 
@@ -14,7 +14,7 @@ pytestmark = pytest.mark.gpu
 @pytest.mark.parametrize("name", list(DATASETS))
 def test_block_api_matches_reference_sam(name):
     need_ref_tools()
-    demo = Demo(name)
+    demo = get_demo(name)
     try:
         ctx = aln.AlnContext(demo.data.index_dir, demo.data.header_sam)
         sam, ori = ctx.align_fastq(read(demo.data.reads_fq))
@@ -27,14 +27,14 @@ def test_block_api_matches_reference_sam(name):
         if name == "demo":
             assert hdr + sam == golden("aln_demo.sam.gz")
     finally:
-        demo.cleanup()
+        pass
 
 
 def test_command_line_and_block_boundaries():
     """fc_aln command line of the product; and two half-blocks must give the same bytes as one block (the rand() replay and
     the per-handler random_r streams carry over between blocks)."""
     need_ref_tools()
-    demo = Demo("multi_allele")
+    demo = get_demo("multi_allele")
     try:
         out, ori = os.path.join(demo.wd, "cli.sam"), os.path.join(demo.wd, "cli_ori.sam")
         rc = aln.fc_aln_main(["-t", "1", "-S", "-o", out, "-p", ori, demo.data.index_dir, demo.data.reads_fq, demo.data.header_sam])
@@ -63,4 +63,4 @@ def test_command_line_and_block_boundaries():
         ctx.close()
         assert read(mb) == read(rb)
     finally:
-        demo.cleanup()
+        pass
