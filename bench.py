@@ -38,7 +38,7 @@ OPS_PER_CELL = 55               # int ops per DP cell with traceba
 CIGAR_CAP = 16
 
 
-NCU_DRAM_BYTES_PER_TASK = 65840       # profiles/r1h_ksw_team_full.md
+NCU_DRAM_BYTES_PER_TASK = 56400       # profiles/r1h_ksw_team_full.md (r1o addendum: 20.68 GB read + 35.72 GB written per 1 M tasks)
 
 
 def env_int(name, default):
@@ -289,8 +289,8 @@ def main():
         "gpu_launches": int(launches + e_launches),
         "roofline": {"bound": "int_alu", "achieved": achieved_gops, "peak": int_peak, "unit": "Gop/s",
                      "frac": achieved_gops / int_peak if int_peak else None,
-                     # DRAM bytes per launch of this kernel from the ncu --set full capture in profiles/r1h_ksw_team_full.md
-                     # (65.84 GB at 1 M tasks: dram__bytes_read 30.13 GB + dram__bytes_write 35.71 GB), scaled to this launch
+                     # DRAM bytes per launch of this kernel from ncu (profiles/r1h_ksw_team_full.md, r1o addendum:
+                     # 56.40 GB at 1 M tasks = dram__bytes_read 20.68 GB + dram__bytes_write 35.72 GB), scaled to this launch
                      "traffic": NCU_DRAM_BYTES_PER_TASK * n, "traffic_unit": "bytes/launch",
                      "algorithmic_bytes": bytes_per_task * n,
                      "kernel": "ksw_team_kernel<8,true>", "kernel_ms_per_launch": kern_ms / args.steps,

@@ -194,6 +194,7 @@ LANE_DEV void align_team(const Params &P, bool have_task, int qlen, const uint8_
 		uint32_t rcv2 = shfl(MX2[NR - 1], left);                      // hi half = MX2 of the neighbour's last cell
 		bool active = false;
 		int lmax = INT32_MIN, Hen8 = 0, Hst8 = 0, Mx = INT32_MIN;
+		uint32_t pk4[4] = {0u, 0u, 0u, 0u};                       // this diagonal's 16 traceback bytes of the lane
 
 		if (live) {
 			const int nbk = ((en0 - st0) >> 4) + 1;                   // 16-byte chunks of the score refresh
@@ -280,7 +281,7 @@ LANE_DEV void align_team(const Params &P, bool have_task, int qlen, const uint8_
 			// -- the 16 cells of this lane, right to left so that [i-1] is still last diagonal's
 			active = blk >= bs && blk <= be;
 			if (active) {
-				uint32_t pk4[4], tb_hi = 0;
+				uint32_t tb_hi = 0;
 #pragma unroll
 				for (int i = NR - 1; i >= 0; --i) {
 					const uint32_t mxt1 = i > 0 ? prmt(MX[i > 0 ? i - 1 : 0], MX[i], 0x5432) : prmt(rcv1, MX[0], 0x5410);
@@ -317,8 +318,6 @@ LANE_DEV void align_team(const Params &P, bool have_task, int qlen, const uint8_
 						if (i & 1) tb_hi = tw; else pk4[i >> 1] = prmt(tw, tb_hi, 0x6420);
 					}
 				}
-				if (with_cigar)                                       // one traceback byte per cell, column = t mod W
-					kswfast::store_cells<16>(tb + (size_t)r * W + 16 * tl, pk4);
 			}
 
 			// -- exact H row (KSW:316-351), scaled by 8, in shared memory at column t mod W.  Cells outside
@@ -357,6 +356,14 @@ LANE_DEV void align_team(const Params &P, bool have_task, int qlen, const uint8_
 					hp[ken] = Hprev + d;
 				}
 			} else if (blk == 0) hp[0] = (int)lo16u(V[0]) - bV - P.qe_as_passed * 8;   // r == 0 (KSW:351)
+		}
+		// -- one traceback byte per cell, row = diagonal, column = t mod W.  Two neighbouring lanes share a 32-byte sector: when only
+		//    one of them is in the band the other one stores too (zeros, for cells no backtrack ever visits), so that DRAM sees
+		//    whole sectors and never has to read one back to merge half of it.
+		if (with_cigar) {
+			const bool mine = live && active;
+			const int partner = shfl_xor((int)mine, 1);                  // every lane takes part in the exchange
+			if (mine || partner != 0) kswfast::store_cells<16>(tb + (size_t)r * W + 16 * tl, pk4);
 		}
 		wsync();
 		Mx = team_max<TEAM>(lmax);
