@@ -264,14 +264,14 @@ LANE_DEV void align_team(const Params &P, bool have_task, int qlen, const uint8_
 						for (int i = 0; i < NR; ++i) {
 							const uint32_t x = TB[i] ^ QB[i];
 							const uint32_t sn = SBASE + minu(x, ONE2) * (uint32_t)D1 + minu(x & 0x00300030u, ONE2) * (uint32_t)E2;
-							const uint32_t rm = (MA[i] ^ XM) | YM;
+							const uint32_t rm = xor_or(MA[i], XM, YM);
 							S[i] = (S[i] & ~rm) | (sn & rm);
 						}
 					} else {
 #pragma unroll
 						for (int i = 0; i < NR; ++i) {
 							const uint32_t sn = SBASE + minu(TB[i] ^ QB[i], ONE2) * (uint32_t)D1;
-							const uint32_t rm = (MA[i] ^ XM) | YM;
+							const uint32_t rm = xor_or(MA[i], XM, YM);
 							S[i] = (S[i] & ~rm) | (sn & rm);
 						}
 					}

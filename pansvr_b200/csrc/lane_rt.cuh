@@ -38,7 +38,14 @@ LANE_FN uint32_t minu(uint32_t a, uint32_t b) { return __vminu2(a, b); }        
 LANE_FN uint32_t maxu(uint32_t a, uint32_t b) { return __vmaxu2(a, b); }                          // VIMNMX.U16x2
 LANE_FN uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) { return __byte_perm(a, b, sel); }    // PRMT
 LANE_FN int max3s(int a, int b, int c) { return __vimax3_s32(a, b, c); }                          // VIMNMX3.S32
+LANE_FN uint32_t xor_or(uint32_t a, uint32_t b, uint32_t c)                                       // (a ^ b) | c as one LOP3
+{
+	uint32_t r;
+	asm("lop3.b32 %0, %1, %2, %3, 0xBE;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+	return r;
+}
 #else
+LANE_FN uint32_t xor_or(uint32_t a, uint32_t b, uint32_t c) { return (a ^ b) | c; }
 LANE_FN uint32_t max3u(uint32_t a, uint32_t b, uint32_t c)
 {
 	uint32_t lo = a & 0xffff, hi = a >> 16;
