@@ -476,11 +476,8 @@ LANE_DEV void align_team(const Params &P, bool have_task, int qlen, const uint8_
 					if (li < (lo0 & ~15)) forced = 2;
 					if (li > (hi0 | 15)) forced = 1;
 					if (forced < 0) {
-#ifdef PANSVR_HOST_EMUL
+						// a plain load: the bytes were stored by lanes of this same warp before the __syncwarp above
 						const uint32_t b = tb_t[(size_t)rr * W + (li & (W - 1))];
-#else
-						const uint32_t b = __ldcg(tb_t + (size_t)rr * W + (li & (W - 1)));
-#endif
 						tmp = (b & 0x78u) | (4u - (b & 7u));
 					}
 					clean = forced < 0 && (state == 0 ? (tmp & 7u) == 0 : ((tmp >> (state + 2)) & 1u) != 0);
