@@ -61,9 +61,12 @@ template <class T> bool upload(const std::vector<T> &h, T *&d, std::string &err)
 
 } // namespace
 
+static int g_staging_device = 0;      // device of the (last created) seed service: helper threads allocate on it, not on device 0
+
 void *staging_alloc(size_t bytes)
 {
 	void *p = nullptr;
+	cudaSetDevice(g_staging_device);
 	return cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) == cudaSuccess ? p : nullptr;
 }
 void staging_free(void *p) { if (p) cudaFreeHost(p); }
@@ -86,6 +89,7 @@ SeedService *seed_service_create(const DebgaIndex &idx, int device, std::string 
 		return nullptr;
 	}
 	cudaSetDevice(device);
+	g_staging_device = device;
 	SeedService *s = new SeedService();
 	s->device = device;
 	auto fail = [&]() -> SeedService* { seed_service_destroy(s); return nullptr; };
