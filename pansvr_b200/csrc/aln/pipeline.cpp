@@ -258,11 +258,26 @@ struct KswTaskList {
 // The process-wide rand() stream as the replay sees it: the real generator, or a probe that only records that it
 // was asked (a pair that never asks is independent of the stream position and can be finished on any thread).
 struct RandTap {
+	enum { MAX_SCRIPT = 12 };
 	GlibcRandom *real = nullptr;
 	uint32_t calls = 0;
-	int32_t next() { ++calls; return real ? real->next() : 0; }
+	// probe mode: the outcome of call k is script[k] (0 beyond the script) and its modulus is recorded, so that every
+	// combination of outcomes of a read can be enumerated (explore_read)
+	uint8_t script[MAX_SCRIPT], moduli[MAX_SCRIPT];
+	uint32_t script_len = 0;
+	bool too_deep = false;
+	int32_t draw(int32_t m)                                  // rand() % m
+	{
+		const uint32_t k = calls++;
+		if (real) return real->next() % m;
+		if (k >= MAX_SCRIPT || m > 255) { too_deep = true; return 0; }
+		moduli[k] = (uint8_t)m;
+		return k < script_len ? (int32_t)script[k] : 0;
+	}
+	void restart(uint32_t len) { calls = 0; script_len = len; too_deep = false; }
 	std::vector<CigarPath> cigar_scratch;                    // (per-thread scratch of finish_read rides along)
 };
+struct PairEvent { int8_t i, j; uint8_t tie; };             // store_pair reached with fin >= max_score: candidates i/j (-1 = none)
 
 struct AlnPipeline::Impl {
 	AlnPipeline &P;
@@ -675,7 +690,7 @@ struct AlnPipeline::Impl {
 			if (g.max_index == U32MAX) return 0;
 			int used = 0, fresh = 0;
 			const uint32_t same = (uint32_t)g.same_top.size();
-			if (same > 1) g.max_index = (uint32_t)g.same_top[rnd.next() % (int32_t)same];
+			if (same > 1) g.max_index = (uint32_t)g.same_top[rnd.draw((int32_t)same)];
 			int node = (int)g.max_index;
 			const int first = node;
 			for (; node != -1;) {
@@ -839,7 +854,7 @@ struct AlnPipeline::Impl {
 		if ((v = get_isize(a2, b2, a->direction, b->direction)) > 0) return v;
 		return 0;
 	}
-	void store_pair(PE &pe, Result *a, Result *b, RandTap &rnd)
+	void store_pair(PE &pe, Result *a, Result *b, RandTap &rnd, std::vector<PairEvent> *ev = nullptr, int ci = -1, int cj = -1)
 	{
 		const int isize = proper_mated(a, b);
 		const int basic = (a ? (int)a->align_score : 0) + (b ? (int)b->align_score : 0);
@@ -847,22 +862,80 @@ struct AlnPipeline::Impl {
 		const int fin = basic + (isize > 0 ? 0 : -60) + (one_new ? 0 : 1);
 		if (fin >= pe.max_score) {
 			bool store = true;
+			if (ev) { PairEvent e; e.i = (int8_t)ci; e.j = (int8_t)cj; e.tie = fin == pe.max_score; ev->push_back(e); }
 			if (fin > pe.max_score) pe.max_same = 1;
-			else if (fin == pe.max_score) { ++pe.max_same; if (rnd.next() % pe.max_same != 0) store = false; }
+			else if (fin == pe.max_score) { ++pe.max_same; if (rnd.draw(pe.max_same) != 0) store = false; }
 			if (store) { pe.m1 = a; pe.m2 = b; pe.max_score = fin; pe.cur_isize = isize; pe.proper = isize > 0; }
 		}
 	}
-	void pair_up(ReadState *se, PE &pe, RandTap &rnd)
+	static Result *pick(ReadState &r, int i) { return i < 0 ? nullptr : (i < r.result_num ? &r.result[i] : &r.ori); }
+	// `ev`: also record every candidate combination that reaches `fin >= max_score`, in order.  Which of them wins the ties
+	// is the only thing the random stream decides (the running maximum does not depend on it), so the replay can redraw
+	// a pair's ties from the events alone (replay_pairing) without touching the candidates.
+	void pair_up(ReadState *se, PE &pe, RandTap &rnd, std::vector<PairEvent> *ev = nullptr)
 	{
 		pe = PE();
 		int n0 = se[0].result_num, n1 = se[1].result_num;
 		if (!se[0].ori_unmapped) ++n0;
 		if (!se[1].ori_unmapped) ++n1;
-		auto pick = [](ReadState &r, int i) -> Result* { return i < r.result_num ? &r.result[i] : &r.ori; };
-		for (int i = 0; i < n0; ++i) store_pair(pe, pick(se[0], i), nullptr, rnd);
-		for (int j = 0; j < n1; ++j) store_pair(pe, nullptr, pick(se[1], j), rnd);
-		for (int i = 0; i < n0; ++i) for (int j = 0; j < n1; ++j) store_pair(pe, pick(se[0], i), pick(se[1], j), rnd);
+		for (int i = 0; i < n0; ++i) store_pair(pe, pick(se[0], i), nullptr, rnd, ev, i, -1);
+		for (int j = 0; j < n1; ++j) store_pair(pe, nullptr, pick(se[1], j), rnd, ev, -1, j);
+		for (int i = 0; i < n0; ++i) for (int j = 0; j < n1; ++j) store_pair(pe, pick(se[0], i), pick(se[1], j), rnd, ev, i, j);
 		pe.gain = pe.max_score > 0 && ((pe.m1 && !pe.m1->is_ori) || (pe.m2 && !pe.m2->is_ori));
+	}
+	// the pairing decided by the winner (i, j) of the events; max_score is what pair_up already found
+	void apply_pairing(ReadState *se, PE &pe, int i, int j)
+	{
+		pe.m1 = pick(se[0], i); pe.m2 = pick(se[1], j);
+		pe.cur_isize = proper_mated(pe.m1, pe.m2);
+		pe.proper = pe.cur_isize > 0;
+		pe.gain = pe.max_score > 0 && ((pe.m1 && !pe.m1->is_ori) || (pe.m2 && !pe.m2->is_ori));
+	}
+	// what finish_read left in r, as far as anything downstream can see it
+	static void result_signature(const ReadState &r, std::vector<uint32_t> &sig)
+	{
+		sig.clear();
+		sig.push_back((uint32_t)r.result_num);
+		for (int k = 0; k < r.result_num; ++k) {
+			const Result &c = r.result[k];
+			sig.push_back(c.align_score); sig.push_back(c.chain_score); sig.push_back(c.max_index); sig.push_back(c.read_bg);
+			sig.push_back(c.chr); sig.push_back(c.ref_bg); sig.push_back((uint32_t)c.direction); sig.push_back(c.mapq);
+			sig.push_back((uint32_t)(c.sv ? c.sv->id : 0xffffffffu)); sig.push_back((uint32_t)c.cigar.size());
+			for (const CigarPath &ci : c.cigar) sig.push_back((uint32_t)ci.type << 16 | (uint16_t)ci.size);
+		}
+	}
+	// A read whose candidate list had ties: run finish_read for every combination of tie outcomes.  If all of them leave the
+	// same candidates and make the same number of draws, the read does not depend on the stream at all -- the replay only
+	// has to advance the stream by that number.  Returns the number of draws, or -1 (too many combinations, or they differ).
+	int explore_read(ReadState &r, const KswView &tasks, RandTap &probe, std::vector<uint32_t> &sig0, std::vector<uint32_t> &sig)
+	{
+		enum { MAX_LEAVES = 24 };
+		probe.restart(0);
+		finish_read(r, tasks, probe);
+		if (probe.too_deep) return -1;
+		const uint32_t c0 = probe.calls;
+		if (c0 == 0) return 0;
+		result_signature(r, sig0);
+		uint8_t choice[RandTap::MAX_SCRIPT] = {0}, mod[RandTap::MAX_SCRIPT];
+		memcpy(mod, probe.moduli, c0);
+		uint32_t c = c0;
+		for (int leaves = 1; ; ++leaves) {
+			int p = (int)c - 1;                                   // next combination: odometer over the moduli of the last run
+			while (p >= 0 && choice[p] + 1 >= mod[p]) --p;
+			if (p < 0) break;
+			if (leaves >= MAX_LEAVES) return -1;
+			++choice[p];
+			for (uint32_t k = (uint32_t)p + 1; k < RandTap::MAX_SCRIPT; ++k) choice[k] = 0;
+			probe.restart((uint32_t)p + 1);
+			memcpy(probe.script, choice, (size_t)p + 1);
+			finish_read(r, tasks, probe);
+			if (probe.too_deep || probe.calls != c0) return -1;
+			c = probe.calls;
+			memcpy(mod, probe.moduli, c);
+			result_signature(r, sig);
+			if (sig != sig0) return -1;
+		}
+		return (int)c0;
 	}
 	void set_primary(ReadState *se, PE &pe)                      // set_primary_secondary_mate, RRH:501-534
 	{
@@ -1298,24 +1371,48 @@ bool AlnPipeline::align_block(const FastqRec *recs, size_t n_reads_in, BlockOutp
 	// pair is first finished on a worker thread against a probe; pairs that asked for a random number, and the deferred
 	// pairs, are then replayed in input order against the real stream -- the stream sees exactly the reference's calls.
 	std::vector<Impl::PE> pes(n_pairs);
-	std::vector<uint8_t> redo(n_pairs, 0);
-	parallel(n_pairs, [&](size_t pb, size_t pe_, int) {
+	// what the in-order pass has to do for a pair:
+	//   0  nothing: no random number is drawn anywhere
+	//   1  advance the stream by the pair's draws: the candidate lists have ties, but every outcome of them gives the same lists
+	//      (explore_read) and the pairing has no ties
+	//   2  the same, then redraw the pairing ties from the recorded events; the winner is applied on the helper threads afterwards
+	//   4 + bits  finish read 0 (bit 0) / read 1 (bit 1) against the real stream (their outcomes differ, or are too many to
+	//      enumerate), then pair up
+	//   16 a pair with 'N' (see below)
+	std::vector<uint8_t> redo(n_pairs, 0), draws0(n_pairs, 0), draws1(n_pairs, 0), ev_cnt(n_pairs, 0), ev_chunk(n_pairs, 0);
+	std::vector<uint32_t> ev_off(n_pairs, 0);
+	std::vector<int8_t> win_i(n_pairs, -1), win_j(n_pairs, -1);
+	std::vector<std::vector<PairEvent>> events((size_t)std::max(1, opt.threads));
+	parallel(n_pairs, [&](size_t pb, size_t pe_, int t) {
 		RandTap probe;
+		std::vector<uint32_t> sig0, sig;
+		std::vector<PairEvent> ev, &evs = events[(size_t)t];
 		for (size_t pi = pb; pi < pe_; ++pi) {
 			ReadState *se = &rs[2 * pi];
 			if (se[0].has_n || se[1].has_n) { redo[pi] = 16; continue; }
-			probe.calls = 0;
-			I.finish_read(se[0], tasks_view, probe);
-			const uint32_t c0 = probe.calls;
-			I.finish_read(se[1], tasks_view, probe);
-			if (probe.calls) { redo[pi] = (uint8_t)(4 | (c0 ? 1 : 0) | (probe.calls > c0 ? 2 : 0)); continue; }   // which read's candidate list has ties
-			I.pair_up(se, pes[pi], probe);
-			if (probe.calls) { redo[pi] = 8; continue; }                     // the candidate lists stand, only the pairing tie is redrawn
-			if (pes[pi].gain) I.set_primary(se, pes[pi]);
+			const int c0 = I.explore_read(se[0], tasks_view, probe, sig0, sig);
+			const int c1 = I.explore_read(se[1], tasks_view, probe, sig0, sig);
+			if (c0 < 0 || c1 < 0 || c0 > 250 || c1 > 250) {
+				redo[pi] = (uint8_t)(4 | (c0 < 0 || c0 > 250 ? 1 : 0) | (c1 < 0 || c1 > 250 ? 2 : 0));
+				draws0[pi] = (uint8_t)(c0 < 0 || c0 > 250 ? 0 : c0); draws1[pi] = (uint8_t)(c1 < 0 || c1 > 250 ? 0 : c1);
+				continue;
+			}
+			draws0[pi] = (uint8_t)c0; draws1[pi] = (uint8_t)c1;
+			probe.restart(0);
+			ev.clear();
+			I.pair_up(se, pes[pi], probe, &ev);
+			if (probe.calls == 0) {                                          // the pairing is decided
+				redo[pi] = c0 + c1 ? 1 : 0;
+				if (pes[pi].gain) I.set_primary(se, pes[pi]);
+			} else if (ev.size() <= 255) {
+				redo[pi] = 2;
+				ev_chunk[pi] = (uint8_t)t; ev_off[pi] = (uint32_t)evs.size(); ev_cnt[pi] = (uint8_t)ev.size();
+				evs.insert(evs.end(), ev.begin(), ev.end());
+			} else redo[pi] = 4;                                             // (cannot happen with <= 13 x 13 candidates; stay safe)
 		}
 	});
 	const double t_probe = now() - t0;
-	size_t n_redo = 0, n_in_order = 0, n_deferred = 0, n_mems_late = 0;
+	size_t n_redo = 0, n_full = 0, n_in_order = 0, n_deferred = 0, n_mems_late = 0;
 	RandTap real; real.real = &rand_;
 	// the replay walks cold per-read data on one thread: pull the state of the pairs a few steps ahead into the cache
 	std::vector<uint32_t> redo_list;
@@ -1337,7 +1434,7 @@ bool AlnPipeline::align_block(const FastqRec *recs, size_t n_reads_in, BlockOutp
 	};
 	for (size_t ri = 0; ri < redo_list.size(); ++ri) {
 		const size_t pi = redo_list[ri];
-		prefetch_state(ri + 8); prefetch_arrays(ri + 3);
+		if (redo[pi] >= 4) { prefetch_state(ri + 8); prefetch_arrays(ri + 3); ++n_full; }
 		++n_redo;
 		ReadState *se = &rs[2 * pi];
 		if (se[0].has_n || se[1].has_n) {                                 // deferred pair: its rand() draws happen now
@@ -1373,16 +1470,36 @@ bool AlnPipeline::align_block(const FastqRec *recs, size_t n_reads_in, BlockOutp
 				I.finish_read(r, own[k] ? local.view() : tasks_view, real);
 			}
 		} else if (redo[pi] & 4) {
-			for (int k = 0; k < 2; ++k) if (redo[pi] & (1 << k)) I.finish_read(se[k], tasks_view, real);   // a tie-free list is final already
+			if (redo[pi] & 1) I.finish_read(se[0], tasks_view, real); else for (int k = 0; k < draws0[pi]; ++k) rand_.next();
+			if (redo[pi] & 2) I.finish_read(se[1], tasks_view, real); else for (int k = 0; k < draws1[pi]; ++k) rand_.next();
+		} else {                                                          // 1 or 2: the candidate lists stand whatever is drawn
+			for (int k = 0, n = draws0[pi] + draws1[pi]; k < n; ++k) rand_.next();
+			if (redo[pi] == 2) {                                           // store_pair's tie rule over the recorded events (RRH:553)
+				const PairEvent *e = events[ev_chunk[pi]].data() + ev_off[pi];
+				int max_same = 1, wi = -1, wj = -1;
+				for (int k = 0; k < ev_cnt[pi]; ++k) {
+					if (!e[k].tie) { max_same = 1; wi = e[k].i; wj = e[k].j; }
+					else { ++max_same; if (rand_.next() % max_same == 0) { wi = e[k].i; wj = e[k].j; } }
+				}
+				win_i[pi] = (int8_t)wi; win_j[pi] = (int8_t)wj;
+			}
+			continue;
 		}
 		I.pair_up(se, pes[pi], real);
 		if (pes[pi].gain) I.set_primary(se, pes[pi]);
 	}
 	turn.pass();                                                          // the next block may replay now
+	parallel(n_pairs, [&](size_t pb, size_t pe_, int) {                    // winners of the redrawn pairings
+		for (size_t pi = pb; pi < pe_; ++pi) {
+			if (redo[pi] != 2) continue;
+			I.apply_pairing(&rs[2 * pi], pes[pi], win_i[pi], win_j[pi]);
+			if (pes[pi].gain) I.set_primary(&rs[2 * pi], pes[pi]);
+		}
+	});
 	{ std::lock_guard<std::mutex> lk(stats_m_); stats.reads += 2 * n_pairs; stats.deferred_pairs += n_deferred; stats.mems += n_mems_late; }
 	if (getenv("PANSVR_TIMING"))
-		fprintf(stderr, "[timing] finish: probe %.3f s, in-order replay of %zu/%zu pairs %.3f s (%zu variant states for reads with N, %zu reads prepared in order)\n",
-		        t_probe, n_redo, n_pairs, now() - t0 - t_probe, n_var, n_in_order);
+		fprintf(stderr, "[timing] finish: probe %.3f s, in-order pass over %zu/%zu pairs (%zu of them re-finished) %.3f s (%zu variant states for reads with N, %zu reads prepared in order)\n",
+		        t_probe, n_redo, n_pairs, n_full, now() - t0 - t_probe, n_var, n_in_order);
 	const double t_text = now();
 	// ---- SAM text of every pair (no random numbers involved any more: parallel)
 	parallel(n_pairs, [&](size_t pb, size_t pe_, int t) {                 // chunk t writes its pairs, in order, into buffer t
