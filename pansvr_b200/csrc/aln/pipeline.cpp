@@ -97,11 +97,12 @@ struct Dna5Table {                                              // charToDna5n, 
 };
 const Dna5Table g_dna5;
 inline uint8_t dna5(unsigned char c) { return g_dna5.t[c]; }
-char rev_char(char c)                                           // getReverseChar, clib/bam_file.c:320-328
-{
-	switch (c) { case 'A': case 'a': return 'T'; case 'C': case 'c': return 'G'; case 'G': case 'g': return 'C'; case 'T': case 't': return 'A'; }
-	return 'N';
-}
+struct RevTable {                                               // getReverseChar, clib/bam_file.c:320-328, as a table
+	char t[256];
+	RevTable() { memset(t, 'N', sizeof t); t['A'] = t['a'] = 'T'; t['C'] = t['c'] = 'G'; t['G'] = t['g'] = 'C'; t['T'] = t['t'] = 'A'; }
+};
+const RevTable g_rev;
+inline char rev_char(char c) { return g_rev.t[(unsigned char)c]; }
 void rev_str(char *s, int len)                                  // getReverseStr_char, clib/bam_file.c:330-340
 {
 	const int half = len >> 1;
@@ -356,8 +357,18 @@ struct AlnPipeline::Impl {
 		for (size_t k = n >> 5; k < words; ++k) out[off + k] = 0;
 		size_t i = 0;
 		for (; i + 32 <= n; i += 32) {
-			uint64_t w = 0;
-			for (int k = 0; k < 32; ++k) w = (w << 2) | b[i + k];
+			uint64_t w = 0, any = 0;
+			for (int k = 0; k < 32; k += 8) {                      // eight codes at a time: x * 0x40100401 gathers four 2-bit codes into one byte
+				uint64_t x;
+				memcpy(&x, b.data() + i + k, 8);
+				any |= x;
+				const uint32_t lo = (uint32_t)x, hi = (uint32_t)(x >> 32);
+				w = (w << 16) | (uint64_t)(((lo * 0x40100401u) >> 24) << 8) | (uint64_t)((hi * 0x40100401u) >> 24);
+			}
+			if (any & 0xfcfcfcfcfcfcfcfcull) {                     // a code 4 (lower-case 'n') spills into its neighbour in the reference: literal path
+				w = 0;
+				for (int k = 0; k < 32; ++k) w = (w << 2) | b[i + k];
+			}
 			out[off + (i >> 5)] = w;
 		}
 		if (i < n) {
