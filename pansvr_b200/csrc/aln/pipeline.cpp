@@ -1214,6 +1214,7 @@ bool AlnPipeline::align_block(const FastqRec *recs, size_t n_reads_in, BlockOutp
 			for (const VertexU &u : r.vu[s]) if (u.pos_n > POS_N_MAX) r.needs_rand = true;
 		}
 	};
+	// `i` = index of the (real) read: reads 2p draw from the first handler's random_r stream, reads 2p+1 from the second's
 	auto chain_read = [&](ReadState &r, size_t i, std::vector<Edge> &edges) {   // stage C, part 2: expand + chain
 		for (int s = 0; s < 2; ++s) {
 			Graph &g = r.g[s];
@@ -1284,14 +1285,52 @@ bool AlnPipeline::align_block(const FastqRec *recs, size_t n_reads_in, BlockOutp
 	});
 	std::vector<Edge> edges_main;
 	Impl::PlanScratch plan_main;
+	// Reads whose seeds include a unipath with more than 500 positions sample them with their handler's random_r stream
+	// (expand_seed, IDX:219-258): those streams are consumed in input order, one stream per mate.  So these reads are chained
+	// here one after the other; a read with 'N' runs every variant from the same stream position (the variants must leave the
+	// stream at one position, otherwise the read waits for the replay); and once a read of a handler has to wait for the
+	// replay -- where it draws in its turn -- every later read of that handler that needs the stream waits too.
 	{
 		bool any = false;
-		for (size_t i = 0; i < n_reads && !any; ++i) any = rs[i].batched && rs[i].needs_rand;
-		if (any) wait_turn();                                              // random_r draws: after every earlier block's replay
-		for (size_t i = 0; i < n_reads; ++i) if (rs[i].batched && rs[i].needs_rand) chain_read(rs[i], i, edges_main);
+		for (size_t i = 0; i < n_all && !any; ++i) any = rs[i].batched && rs[i].needs_rand;
+		for (size_t i = 0; i < n_reads && !any; ++i) any = rs[i].in_order_only;
+		if (any) {
+			wait_turn();                                                   // after every earlier block's replay
+			bool tainted[2] = {false, false};
+			for (size_t i = 0; i < n_reads; ++i) {
+				ReadState &r = rs[i];
+				const int h = (int)(i & 1);
+				if (r.skip || r.read_l < LEN_KMER) continue;
+				if (r.in_order_only) { tainted[h] = true; continue; }         // (too many N: what it will draw is not known yet)
+				if (!r.has_n) {
+					if (!r.needs_rand) continue;
+					if (tainted[h]) { r.in_order_only = true; r.batched = false; continue; }
+					chain_read(r, i, edges_main);
+					continue;
+				}
+				if (r.var_base < 0) continue;
+				const size_t nv = (size_t)1 << (2 * r.n_draws);
+				bool needs = false;
+				for (size_t c = 0; c < nv; ++c) needs |= rs[(size_t)r.var_base + c].needs_rand;
+				if (!needs) continue;
+				bool same = !tainted[h];
+				const GlibcRandom start = rand_r_[h];
+				GlibcRandom after = start;
+				for (size_t c = 0; c < nv && same; ++c) {
+					ReadState &v = rs[(size_t)r.var_base + c];
+					rand_r_[h] = start;
+					chain_read(v, i, edges_main);                            // (a variant that does not need the stream leaves it where it was)
+					if (c == 0) after = rand_r_[h]; else same = rand_r_[h] == after;
+				}
+				if (same) rand_r_[h] = after;
+				else {                                                       // the variants disagree (or the handler already waits)
+					rand_r_[h] = start;
+					r.in_order_only = true; tainted[h] = true;
+					for (size_t c = 0; c < nv; ++c) rs[(size_t)r.var_base + c].batched = false;
+				}
+			}
+		}
 	}
-	for (size_t i = n_reads; i < n_all; ++i)                               // a variant that needs random_r: its read waits for its turn
-		if (rs[i].batched && rs[i].needs_rand) { rs[rs[i].var_of].in_order_only = true; rs[i].batched = false; }
 	add_time(2, now() - t0); t0 = now();
 	// ---- stage D: per-thread task lists, concatenated afterwards
 	KswBatchBuf &tasks = ksw_main_[seq & 1];
@@ -1400,7 +1439,7 @@ bool AlnPipeline::align_block(const FastqRec *recs, size_t n_reads_in, BlockOutp
 		std::vector<PairEvent> ev, &evs = events[(size_t)t];
 		for (size_t pi = pb; pi < pe_; ++pi) {
 			ReadState *se = &rs[2 * pi];
-			if (se[0].has_n || se[1].has_n) { redo[pi] = 16; continue; }
+			if (se[0].has_n || se[1].has_n || se[0].in_order_only || se[1].in_order_only) { redo[pi] = 16; continue; }
 			const int c0 = I.explore_read(se[0], tasks_view, probe, sig0, sig);
 			const int c1 = I.explore_read(se[1], tasks_view, probe, sig0, sig);
 			if (c0 < 0 || c1 < 0 || c0 > 250 || c1 > 250) {
@@ -1448,14 +1487,14 @@ bool AlnPipeline::align_block(const FastqRec *recs, size_t n_reads_in, BlockOutp
 		if (redo[pi] >= 4) { prefetch_state(ri + 8); prefetch_arrays(ri + 3); ++n_full; }
 		++n_redo;
 		ReadState *se = &rs[2 * pi];
-		if (se[0].has_n || se[1].has_n) {                                 // deferred pair: its rand() draws happen now
+		if (redo[pi] == 16) {                                             // deferred pair: its rand() / random_r draws happen now
 			++n_deferred;
 			KswTaskList local;
 			bool own[2] = {false, false};
 			for (int k = 0; k < 2; ++k) {
 				ReadState &r = se[k];
-				if (r.skip || r.read_l < LEN_KMER || !r.has_n) { /* nothing drawn: skipped, too short, or prepared in the batch */ }
-				else if (r.var_base >= 0 && !r.in_order_only) {                // draw the substitutions, adopt the variant prepared for them
+				if (r.skip || r.read_l < LEN_KMER || (!r.has_n && !r.in_order_only)) { /* nothing drawn: skipped, too short, or prepared in the batch */ }
+				else if (r.has_n && r.var_base >= 0 && !r.in_order_only) {     // draw the substitutions, adopt the variant prepared for them
 					uint32_t code = 0;
 					for (int j = 0; j < r.n_draws; ++j) code |= (uint32_t)(rand_.next() % 4) << (2 * j);
 					ReadState &v = rs[(size_t)r.var_base + code];

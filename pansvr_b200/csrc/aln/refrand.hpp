@@ -37,6 +37,11 @@ public:
 		if (++b_ >= 31) b_ = 0;
 		return (int32_t)(v >> 1);
 	}
+	bool operator==(const GlibcRandom &o) const                // same position of the same stream
+	{
+		for (int i = 0; i < 31; ++i) if (r_[i] != o.r_[i]) return false;
+		return f_ == o.f_ && b_ == o.b_;
+	}
 private:
 	int32_t r_[31];
 	int f_, b_;

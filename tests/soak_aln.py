@@ -1,0 +1,56 @@
+"""One-off randomized soak of the whole aln stage (not collected by pytest): random synthetic data sets (alleles per locus,
+N rate, tandem repeats, read length, substitution rate, chromosomes, mates elsewhere) through the product library on the GPU
+with random helper-thread counts and sub-block cuts, against the reference's own `panSVR fc_aln -t 1` (SAM and BAM files, byte
+for byte).  `python tests/soak_aln.py [n_sets]` on a GPU box with oracle/_ref built; last result in profiles/r1t_soak.md."""
+import os
+import shutil
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from pansvr_b200 import aln, synth_pipeline as sp  # noqa: E402
+
+
+def main():
+    n_sets = int(sys.argv[1]) if len(sys.argv) > 1 else 8
+    rng = np.random.default_rng(777)
+    bad = 0
+    for k in range(n_sets):
+        read_len = int(rng.choice([100, 150, 250]))
+        kw = dict(seed=int(rng.integers(1, 10_000)), n_sv=int(rng.integers(30, 90)), alleles_per_locus=int(rng.integers(1, 5)),
+                  pairs_per_sv=int(rng.integers(10, 40)), read_len=read_len, frag=(2 * read_len, 2 * read_len + int(rng.integers(100, 400))),
+                  sub_rate=float(rng.choice([0.005, 0.01, 0.03])), n_frac=float(rng.choice([0.0, 0.0005, 0.003])),
+                  str_every=int(rng.choice([0, 0, 2, 3])), n_chrom=int(rng.integers(1, 4)), mate_elsewhere=float(rng.choice([0.0, 0.1, 0.3])),
+                  sv_lens=tuple(int(x) for x in rng.choice([50, 80, 150, 300, 600, 1000, 3000], size=4)))
+        kw["genome_len"] = 5000 + 7000 * ((kw["n_sv"] + kw["n_chrom"] - 1) // kw["n_chrom"]) + 4000
+        threads = int(rng.choice([1, 3, 8, 16]))
+        sub = int(rng.choice([0, 1, 64, 1000]))
+        wd = tempfile.mkdtemp(prefix="pansvr_soak_")
+        t0 = time.time()
+        try:
+            d = sp.make_demo(wd, **kw)
+            p = lambda n: os.path.join(wd, n)
+            sp.run_reference_aln(d, p("r.sam"), p("ro.sam"), threads=1)
+            sp.run_reference_aln(d, p("r.bam"), p("ro.bam"), threads=1, bam=True)
+            if sub:
+                os.environ["PANSVR_SUB_PAIRS"] = str(sub)
+            else:
+                os.environ.pop("PANSVR_SUB_PAIRS", None)
+            rc1 = aln.fc_aln_main(["-t", str(threads), "-S", "-o", p("m.sam"), "-p", p("mo.sam"), d.index_dir, d.reads_fq, d.header_sam])
+            rc2 = aln.fc_aln_main(["-t", str(threads), "-o", p("m.bam"), "-p", p("mo.bam"), d.index_dir, d.reads_fq, d.header_sam])
+            rd = lambda n: open(p(n), "rb").read()
+            same = rc1 == 0 and rc2 == 0 and all(rd("m" + s) == rd("r" + s) for s in (".sam", "o.sam", ".bam", "o.bam"))
+            bad += not same
+            print(f"set {k}: pairs={d.n_pairs} anchors={d.n_sv} threads={threads} sub_pairs={sub} {kw} identical={same} ({time.time() - t0:.1f} s)", flush=True)
+        finally:
+            shutil.rmtree(wd, ignore_errors=True)
+    print("sets", n_sets, "failures", bad)
+    return 1 if bad else 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())
