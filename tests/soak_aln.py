@@ -1,7 +1,7 @@
 """One-off randomized soak of the whole aln stage (not collected by pytest): random synthetic data sets (alleles per locus,
 N rate, tandem repeats, read length, substitution rate, chromosomes, mates elsewhere) through the product library on the GPU
 with random helper-thread counts and sub-block cuts, against the reference's own `panSVR fc_aln -t 1` (SAM and BAM files, byte
-for byte).  `python tests/soak_aln.py [n_sets]` on a GPU box with oracle/_ref built; last result in profiles/r1t_soak.md."""
+for byte).  `python tests/soak_aln.py [n_sets [seed]]` on a GPU box with oracle/_ref built; last result in profiles/r1t_soak.md."""
 import os
 import shutil
 import sys
@@ -17,7 +17,7 @@ from pansvr_b200 import aln, synth_pipeline as sp  # noqa: E402
 
 def main():
     n_sets = int(sys.argv[1]) if len(sys.argv) > 1 else 8
-    rng = np.random.default_rng(777)
+    rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 777)
     bad = 0
     for k in range(n_sets):
         read_len = int(rng.choice([100, 150, 250]))
