@@ -20,6 +20,10 @@ DATASETS = {
                          n_chrom=3, mate_elsewhere=0.2, n_frac=0.0005),
     # inserted alleles that are short tandem repeats: the STR branch of the seeding loop and of the chain parameters
     "tandem_repeats": dict(seed=24, genome_len=160_000, n_sv=40, sv_lens=(120, 200, 300, 500), str_every=2, pairs_per_sv=30),
+    # 3 kb tandem-repeat alleles (one unipath with > 500 positions -> random_r) together with N bases: the random_r streams must be
+    # consumed in input order across batched reads, N variants and reads prepared during the replay (found by tests/soak_aln.py)
+    "repeat_with_n": dict(seed=481, n_sv=16, pairs_per_sv=24, sub_rate=0.01, n_frac=0.001, str_every=1, sv_lens=(3000, 3000),
+                          genome_len=5000 + 7000 * 16 + 4000, frag=(300, 464)),
     # one 150 bp element shared by 520 inserted alleles: its unipath has > 500 positions, expand_seed samples them with random_r
     "shared_element": dict(seed=25, genome_len=5000 + 7000 * 520 + 4000, n_sv=520, alleles_per_locus=2, pairs_per_sv=2,
                            shared_insert=150, sv_lens=(200, 300, 400)),
