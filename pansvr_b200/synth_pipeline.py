@@ -141,6 +141,7 @@ def make_demo(workdir: str, seed: int = 7, genome_len: int = 200_000, n_sv: int 
                 isize = flen
                 soft1 = int(rng.integers(0, 70)) if rng.random() < 0.5 else 0
                 soft2 = int(rng.integers(0, 70)) if rng.random() < 0.5 else 0
+                soft1, soft2 = min(soft1, read_len - 25), min(soft2, read_len - 25)   # a clip never exceeds the read (fc_signal copies a real CIGAR)
                 sc1 = 2 * (read_len - soft1) - int(rng.integers(10, 90))
                 sc2 = 2 * (read_len - soft2) - int(rng.integers(10, 90))
                 name = f"r{si}x{p}"

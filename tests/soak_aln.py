@@ -1,7 +1,7 @@
 """One-off randomized soak of the whole aln stage (not collected by pytest): random synthetic data sets (alleles per locus,
 N rate, tandem repeats, read length, substitution rate, chromosomes, mates elsewhere) through the product library on the GPU
 with random helper-thread counts and sub-block cuts, against the reference's own `panSVR fc_aln -t 1` (SAM and BAM files, byte
-for byte).  `python tests/soak_aln.py [n_sets [seed]]` on a GPU box with oracle/_ref built; last result in profiles/r1t_soak.md."""
+for byte).  `python tests/soak_aln.py [n_sets [seed [harsh]]]` on a GPU box with oracle/_ref built; last result in profiles/r1t_soak.md."""
 import os
 import shutil
 import sys
@@ -26,6 +26,13 @@ def main():
                   sub_rate=float(rng.choice([0.005, 0.01, 0.03])), n_frac=float(rng.choice([0.0, 0.0005, 0.003])),
                   str_every=int(rng.choice([0, 0, 2, 3])), n_chrom=int(rng.integers(1, 4)), mate_elsewhere=float(rng.choice([0.0, 0.1, 0.3])),
                   sv_lens=tuple(int(x) for x in rng.choice([50, 80, 150, 300, 600, 1000, 3000], size=4)))
+        if len(sys.argv) > 3 and sys.argv[3] == "harsh":                  # many N per read, a widely shared element, short reads
+            kw["n_frac"] = float(rng.choice([0.0, 0.003, 0.01, 0.03]))
+            kw["read_len"] = read_len = int(rng.choice([60, 100, 150]))
+            kw["frag"] = (2 * read_len, 2 * read_len + int(rng.integers(50, 300)))
+            if rng.random() < 0.3:
+                kw.update(n_sv=int(rng.integers(510, 560)), alleles_per_locus=2, pairs_per_sv=3, shared_insert=int(rng.choice([60, 150])),
+                          sv_lens=(200, 300, 400))
         kw["genome_len"] = 5000 + 7000 * ((kw["n_sv"] + kw["n_chrom"] - 1) // kw["n_chrom"]) + 4000
         threads = int(rng.choice([1, 3, 8, 16]))
         sub = int(rng.choice([0, 1, 64, 1000]))
