@@ -1,7 +1,7 @@
 """One-off randomized soak of the whole aln stage (not collected by pytest): random synthetic data sets (alleles per locus,
 N rate, tandem repeats, read length, substitution rate, chromosomes, mates elsewhere) through the product library on the GPU
 with random helper-thread counts and sub-block cuts, against the reference's own `panSVR fc_aln -t 1` (SAM and BAM files, byte
-for byte).  `python tests/soak_aln.py [n_sets [seed [harsh]]]` on a GPU box with oracle/_ref built; last result in profiles/r1t_soak.md."""
+for byte).  `python tests/soak_aln.py [n_sets [seed [harsh|options]]]` on a GPU box with oracle/_ref built; last result in profiles/r1t_soak.md."""
 import os
 import shutil
 import sys
@@ -34,6 +34,11 @@ def main():
                 kw.update(n_sv=int(rng.integers(510, 560)), alleles_per_locus=2, pairs_per_sv=3, shared_insert=int(rng.choice([60, 150])),
                           sv_lens=(200, 300, 400))
         kw["genome_len"] = 5000 + 7000 * ((kw["n_sv"] + kw["n_chrom"] - 1) // kw["n_chrom"]) + 4000
+        opts = []
+        if len(sys.argv) > 3 and sys.argv[3] == "options":               # random scoring / z-drop / -Q on both sides
+            opts = ["-M", str(int(rng.integers(1, 4))), "-m", str(int(rng.integers(4, 13))), "-O", str(int(rng.integers(4, 31))),
+                    "-E", str(int(rng.integers(1, 5))), "-P", str(int(rng.integers(13, 61))), "-F", str(int(rng.integers(0, 3))),
+                    "-z", str(int(rng.integers(50, 401)))] + (["-Q"] if rng.random() < 0.3 else [])
         threads = int(rng.choice([1, 3, 8, 16]))
         sub = int(rng.choice([0, 1, 64, 1000]))
         wd = tempfile.mkdtemp(prefix="pansvr_soak_")
@@ -41,18 +46,28 @@ def main():
         try:
             d = sp.make_demo(wd, **kw)
             p = lambda n: os.path.join(wd, n)
-            sp.run_reference_aln(d, p("r.sam"), p("ro.sam"), threads=1)
-            sp.run_reference_aln(d, p("r.bam"), p("ro.bam"), threads=1, bam=True)
+            sp.run_reference_aln(d, p("r.sam"), p("ro.sam"), threads=1, extra=opts)
+            sp.run_reference_aln(d, p("r.bam"), p("ro.bam"), threads=1, bam=True, extra=opts)
             if sub:
                 os.environ["PANSVR_SUB_PAIRS"] = str(sub)
             else:
                 os.environ.pop("PANSVR_SUB_PAIRS", None)
-            rc1 = aln.fc_aln_main(["-t", str(threads), "-S", "-o", p("m.sam"), "-p", p("mo.sam"), d.index_dir, d.reads_fq, d.header_sam])
-            rc2 = aln.fc_aln_main(["-t", str(threads), "-o", p("m.bam"), "-p", p("mo.bam"), d.index_dir, d.reads_fq, d.header_sam])
+            run = aln.fc_aln_main
+            if os.environ.get("PANSVR_SOAK_EMUL"):                       # host build of the pipeline (tests/emul): no GPU needed, much slower
+                import subprocess
+                env = dict(os.environ, PANSVR_ORACLE_SO=os.path.join(ROOT, "oracle", "libksw_oracle.so"))
+                run = lambda argv: subprocess.run([os.path.join(ROOT, "tests", "emul", "fc_aln_emul"), *argv], env=env, stderr=subprocess.DEVNULL).returncode
+            rc1 = run(["-t", str(threads), "-S", *opts, "-o", p("m.sam"), "-p", p("mo.sam"), d.index_dir, d.reads_fq, d.header_sam])
+            rc2 = run(["-t", str(threads), *opts, "-o", p("m.bam"), "-p", p("mo.bam"), d.index_dir, d.reads_fq, d.header_sam])
             rd = lambda n: open(p(n), "rb").read()
             same = rc1 == 0 and rc2 == 0 and all(rd("m" + s) == rd("r" + s) for s in (".sam", "o.sam", ".bam", "o.bam"))
-            bad += not same
-            print(f"set {k}: pairs={d.n_pairs} anchors={d.n_sv} threads={threads} sub_pairs={sub} {kw} identical={same} ({time.time() - t0:.1f} s)", flush=True)
+            # With a small z-drop the reference can build a CIGAR shorter than the read; htslib then rejects the record
+            # ("CIGAR and query sequence are of different length") and the reference writes the half-parsed bam1_t with whatever
+            # the reused buffer held.  Such a run has no defined output to compare with.
+            if not same and b"different length" in rd("fc_aln.log"):
+                same = None
+            bad += same is False
+            print(f"set {k}: identical={same} pairs={d.n_pairs} anchors={d.n_sv} threads={threads} sub_pairs={sub} opts={" ".join(opts)} {kw} identical={same} ({time.time() - t0:.1f} s)", flush=True)
         finally:
             shutil.rmtree(wd, ignore_errors=True)
     print("sets", n_sets, "failures", bad)
