@@ -64,7 +64,11 @@ static inline Plan make_plan(int m, const int8_t *mat, int q, int e, int q2, int
 	const int allowed = kswfast::F_SCORE_ONLY | kswfast::F_EXTZ_ONLY | kswfast::F_REV_CIGAR;
 	const int smin = std::min(P.sc_mch, std::min(P.sc_mis, P.sc_N)), smax = std::max(P.sc_mch, std::max(P.sc_mis, P.sc_N));
 	pl.fast_params = !(flag & ~allowed) && m <= 16 && q >= 0 && e >= 0 && q2 >= 0 && e2 >= 0 && q + e <= 127 && q2 + e2 <= 127;
-	pl.nowrap_ok = pl.fast_params && P.sc_mch >= 0 && int8_bounds_hold(P.sc_mch, smin, smax, q, e, q2, e2, P.long_diff);
+	// The bounds of int8_bounds_hold assume first-row / first-column values that are consistent with the recurrence.  With
+	// e < e2 the reference's long_thres is negative and its boundary steps by -e2 where the recurrence extends by -e
+	// (KSW:151,155): the differences then leave those bounds inside the band, the reference wraps, and only the WRAP variant
+	// reproduces it (found by tests/soak_aln.py with -O 22 -E 3 -P 14 -F 0).
+	pl.nowrap_ok = pl.fast_params && P.sc_mch >= 0 && e >= e2 && int8_bounds_hold(P.sc_mch, smin, smax, q, e, q2, e2, P.long_diff);
 	return pl;
 }
 

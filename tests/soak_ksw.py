@@ -15,7 +15,8 @@ for i in range(24):
     w = int(rng.choice([2, 8, 30, 50, 100, 132, 200, 500, -1]))
     zd = int(rng.choice([20, 100, 132, 400, -1]))
     flag = int(rng.choice([0, 0, 0, 0x40, 0x80, 0x01, 0xC0]))
-    sc = [(2, 12, 16, 1, 32, 0), (2, 10, 24, 2, 32, 1), (1, 4, 6, 2, 24, 1), (4, 24, 60, 8, 100, 20), (1, 1, 1, 1, 2, 1), (2, 4, 4, 2, 13, 1)][int(rng.integers(0, 6))]
+    sc = [(2, 12, 16, 1, 32, 0), (2, 10, 24, 2, 32, 1), (1, 4, 6, 2, 24, 1), (4, 24, 60, 8, 100, 20), (1, 1, 1, 1, 2, 1), (2, 4, 4, 2, 13, 1),
+              (2, 11, 22, 3, 14, 0), (2, 12, 16, 0, 32, 1), (2, 11, 14, 1, 22, 3), (3, 5, 4, 3, 19, 2), (1, 9, 30, 1, 13, 4)][int(rng.integers(0, 11))]
     p = synth.KswParams(mat=synth.dna_matrix(sc[0], sc[1], sc_ambi=int(rng.choice([0, -1]))), q=sc[2], e=sc[3], q2=sc[4], e2=sc[5], w=w, zdrop=zd, flag=flag,
                         end_bonus=int(rng.choice([-1, 0, 5])))
     ml = int(rng.choice([60, 160, 260, 400, 700]))

@@ -45,6 +45,8 @@ CASES = [
     ("zdrop_tight", lambda: synth.fuzz_batch(60, 36, params=synth.KswParams(w=30, zdrop=20)), 0, 0),
     ("tiny_bands", lambda: synth.fuzz_batch(60, 37, max_len=120, params=synth.KswParams(w=2, zdrop=400)), 0, 0),
     ("fc_sv_contigs", lambda: synth.fcsv_batch(3, pool_bases=1 << 16), 0, 0),
+    ("swapped_e_lt_e2", lambda: synth.fuzz_batch(60, 77, max_len=200, params=synth.KswParams(mat=synth.dna_matrix(2, 11), q=22, e=3, q2=14, e2=0, w=200, zdrop=384)), 0, 0),
+    ("e_lt_e2", lambda: synth.fuzz_batch(60, 78, max_len=200, params=synth.KswParams(q=16, e=0, q2=32, e2=1, w=200, zdrop=400)), 0, 0),
     ("wide_w500", lambda: synth.fuzz_batch(6, 35, max_len=460, params=synth.KswParams(w=500)), 0, 0),
 ]
 

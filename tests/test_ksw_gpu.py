@@ -39,7 +39,11 @@ def test_other_scoring_sets(ksw_ctx):
     sets = [synth.KswParams(mat=synth.dna_matrix(2, 10), q=24, e=2, q2=32, e2=1, w=132, zdrop=132),      # fc_sv (SignalAssembly.hpp:411-421)
             synth.KswParams(mat=synth.dna_matrix(1, 4, sc_ambi=-1), q=24, e=1, q2=6, e2=2, w=60, zdrop=80),  # swapped pieces
             synth.KswParams(mat=synth.dna_matrix(4, 24), q=60, e=8, q2=100, e2=20, w=50, zdrop=300),        # gap costs near the int8 edge
-            synth.KswParams(mat=synth.dna_matrix(1, 1), q=1, e=1, q2=2, e2=1, w=40, zdrop=20)]
+            synth.KswParams(mat=synth.dna_matrix(1, 1), q=1, e=1, q2=2, e2=1, w=40, zdrop=20),
+            # first piece with the smaller extension (e < e2 after the swap): inconsistent boundary, wraps inside unclipped bands
+            synth.KswParams(mat=synth.dna_matrix(2, 11), q=22, e=3, q2=14, e2=0, w=200, zdrop=384),
+            synth.KswParams(q=16, e=0, q2=32, e2=1, w=200, zdrop=400),
+            synth.KswParams(mat=synth.dna_matrix(2, 11), q=14, e=1, q2=22, e2=3, w=300, zdrop=400)]
     for k, p in enumerate(sets):
         b = synth.fuzz_batch(2000, 70 + k, max_len=300, params=p)
         res, cig = ksw_ctx.extd2_batch(b, cigar_cap=160)
