@@ -543,6 +543,9 @@ int pansvr_fc_aln_main(int argc, char **argv)
 	gzclose(in);
 	if (sam) { fclose(fo); fclose(fp); }
 	else if (pansvr_bam_close(bo) != 0 || pansvr_bam_close(bp) != 0) { fprintf(stderr, "pansvr_b200 fc_aln: %s\n", pansvr_aln_last_error()); ok = false; }
+	if (const uint64_t nbad = ctx->pipe->bad_cigar_records_.load())
+		fprintf(stderr, "pansvr_b200 fc_aln: %llu records left out: their CIGAR does not span the read (z-dropped extension; the reference writes such "
+		        "records as rejected by htslib, with undefined content)\n", (unsigned long long)nbad);
 	pansvr_aln_stats_t st;
 	pansvr_aln_last_stats(ctx, &st);
 	fprintf(stderr, "pansvr_b200 fc_aln: %ld reads, %ld MEMs, %ld ksw tasks; stage seconds A %.3f B %.3f C %.3f D %.3f E %.3f F %.3f parse %.3f emit %.3f\n",

@@ -22,6 +22,7 @@
 #pragma once
 #include <stdint.h>
 #include <string.h>
+#include <atomic>
 #include <condition_variable>
 #include <functional>
 #include <mutex>
@@ -139,6 +140,7 @@ public:
 	// rest (stages A-E, the probe, the record text) of one block overlaps the in-order replay of the other.
 	bool align_block(const FastqRec *recs, size_t n_reads, BlockOutput &out, std::string &err, uint64_t seq);
 	uint64_t next_seq() { return seq_issued_++; }
+	std::atomic<uint64_t> bad_cigar_records_{0};   // records left out because their CIGAR does not span the read (see output_bam)
 	void ensure_read_stats(const FastqRec &first);   // STAT_ fields of the input's first comment; call before overlapping blocks
 	void reset();                     // back to the state of a freshly started `fc_aln` (rand() streams, counters)
 	struct Stats { uint64_t reads = 0, probes_reads = 0, mems = 0, ksw_tasks = 0, ksw_cells = 0, deferred_pairs = 0;

@@ -64,8 +64,11 @@ def main():
             # With a small z-drop the reference can build a CIGAR shorter than the read; htslib then rejects the record
             # ("CIGAR and query sequence are of different length") and the reference writes the half-parsed bam1_t with whatever
             # the reused buffer held.  Such a run has no defined output to compare with.
-            if not same and b"different length" in rd("fc_aln.log"):
-                same = None
+            if not same and b"different length" in rd("fc_aln.log"):     # compare what is defined: the well-formed records, the -p file
+                good = [ln for ln in rd("r.sam").split(b"\n") if ln and not ln.startswith(b"@") and len(ln.split(b"\t")) > 11
+                        and ln.split(b"\t")[11].startswith(b"AS:i:")]
+                mine = [ln for ln in rd("m.sam").split(b"\n") if ln and not ln.startswith(b"@")]
+                same = None if (rc1 == 0 and rc2 == 0 and mine == good and rd("mo.sam") == rd("ro.sam")) else False
             bad += same is False
             print(f"set {k}: identical={same} pairs={d.n_pairs} anchors={d.n_sv} threads={threads} sub_pairs={sub} opts={" ".join(opts)} {kw} identical={same} ({time.time() - t0:.1f} s)", flush=True)
         finally:

@@ -128,6 +128,29 @@ def test_command_line_options_match_reference(fc_aln_emul, opts):
         pass
 
 
+def test_short_cigar_records_are_left_out(fc_aln_emul):
+    """With a z-drop far below the default an extension can stop early and leave a CIGAR shorter than the read.  The reference
+    logs an error, htslib rejects the record and the reference writes the half-parsed record with stale buffer bytes; we leave
+    such records out.  Every well-formed record of the reference and its whole -p file must still be ours, and BAM mode must
+    not fail on them."""
+    need_ref_tools()
+    demo = get_demo("chroms_250bp")
+    opts = ("-z", "60", "-O", "10", "-E", "2")
+    r, ro = os.path.join(demo.wd, "z_ref.sam"), os.path.join(demo.wd, "z_ref_ori.sam")
+    m, mo = os.path.join(demo.wd, "z_my.sam"), os.path.join(demo.wd, "z_my_ori.sam")
+    sp.run_reference_aln(demo.data, r, ro, threads=1, extra=opts)
+    n_bad = read(os.path.join(demo.wd, "fc_aln.log")).count(b"different length")
+    assert n_bad > 0                                     # the data set does hit the case
+    fc_aln_emul(demo.data, m, mo, extra=("-S",) + opts, threads=3)
+    well_formed = [ln for ln in read(r).split(b"\n") if ln and not ln.startswith(b"@") and len(ln.split(b"\t")) > 11
+                   and ln.split(b"\t")[11].startswith(b"AS:i:")]
+    mine = [ln for ln in read(m).split(b"\n") if ln and not ln.startswith(b"@")]
+    assert mine == well_formed
+    assert read(mo) == read(ro)
+    fc_aln_emul(demo.data, os.path.join(demo.wd, "z_my.bam"), os.path.join(demo.wd, "z_my_ori.bam"), extra=opts, threads=3)
+    assert gzip.decompress(read(os.path.join(demo.wd, "z_my.bam")))[:4] == b"BAM\x01"
+
+
 def test_bam_records_and_writer_across_calls(fc_aln_emul):
     """pansvr_aln_block_bam + pansvr_bam_open/write/close through the C ABI of the host build: records written in several
     calls (open BGZF block carried over) give the reference's BAM file; every record equals its SAM line re-encoded."""
