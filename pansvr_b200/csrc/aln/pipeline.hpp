@@ -10,13 +10,16 @@
 //   C  host   merge MEMs per unipath, expand to reference positions, chain DP   (deBGA_index.cpp:151-305, graph.cpp:53-150)
 //   D  host   plan the ksw windows of every chain end that can still be chosen  (RR:308-400, 910-986)
 //   E  GPU    ksw_extd2 batch                                                   (ksw_team.cuh)
-//   F  host   sequential replay in input order: chain selection, result sort, pairing, SAM text,
-//             consuming the libc rand() stream exactly as the reference does   (RR:212-293, 406-476, 479-536, 745-799; RRH:434-628)
+//   F  host   chain selection, result sort, pairing, SAM text                   (RR:212-293, 406-476, 479-536, 745-799; RRH:434-628)
 //
-// Stage D works on a superset because which chain ends get extended depends on rand() tie-breaks
-// whose stream position depends on the ksw results of earlier pairs:
-// get_ksw_score is a pure function of (strand, end node), so every node with
-// dist >= max(30, best-30) is planned and the replay picks from the table.
+// Everything runs on the helper threads except what has to see the reference's libc random streams in the reference's
+// order.  rand(): stage D plans a superset because which chain ends get extended depends on rand() tie-breaks whose stream
+// position depends on the results of earlier pairs (get_ksw_score is a pure function of (strand, end node), so every node
+// with dist >= max(30, best-30) is planned); stage F finishes every pair against a probe first, enumerates the outcomes of
+// the ties of a read (usually they all give the same candidates, and the read then only advances the stream), records the
+// pairing ties as events, and a short in-order pass redraws those from the real stream; reads with 'N' (rand()%4 per base)
+// are prepared once per possible substitution.  random_r(): reads that sample a repeat's positions are chained one after
+// the other in stage C.  DESIGN.md section 4.5 has the details.
 //
 // The output is defined against `panSVR fc_aln -t 1` (the only deterministic mode).
 #pragma once
