@@ -73,6 +73,7 @@ def make_demo(workdir: str, seed: int = 7, genome_len: int = 200_000, n_sv: int 
         for chrom, genome in zip(chroms, genomes):
             f.write(f">{chrom}\n{_wrap(genome.tobytes())}\n")
     # ---- variants
+    common = ACGT[np.random.default_rng(seed + 1000).integers(0, 4, shared_insert)] if shared_insert else None
     svs = []   # (pos1 (1-based, anchor base), type, ref_bytes, alt_bytes, id, chromosome index)
     for k in range(n_sv):
         ci = k % n_chrom
@@ -90,9 +91,7 @@ def make_demo(workdir: str, seed: int = 7, genome_len: int = 200_000, n_sv: int 
                     unit = ACGT[rng.integers(0, 4, int(rng.integers(2, 7)))]
                     ins = np.tile(unit, (L + 37 * a) // unit.size + 1)[:L + 37 * a]
                 if shared_insert:
-                    if k == 0 and a == 0:
-                        make_demo._common = ACGT[np.random.default_rng(seed + 1000).integers(0, 4, shared_insert)]
-                    ins = np.concatenate([ins[:ins.size // 2], make_demo._common, ins[ins.size // 2:]])
+                    ins = np.concatenate([ins[:ins.size // 2], common, ins[ins.size // 2:]])
                 svs.append((pos, "INS", base.tobytes(), base.tobytes() + ins.tobytes(), f"sv{k}a{a}", ci))
             else:
                 svs.append((pos, "DEL", genome[pos - 1:pos + L].tobytes(), base.tobytes(), f"sv{k}a{a}", ci))
