@@ -102,6 +102,17 @@ struct RevTable {                                               // getReverseCha
 	RevTable() { memset(t, 'N', sizeof t); t['A'] = t['a'] = 'T'; t['C'] = t['c'] = 'G'; t['G'] = t['g'] = 'C'; t['T'] = t['t'] = 'A'; }
 };
 const RevTable g_rev;
+struct Nt16Norm {                                               // a base after htslib's sam_parse1 -> sam_format1 round trip:
+	char t[256];                                                // seq_nt16_str[seq_nt16_table[c]] (upper case, IUPAC kept, anything else 'N')
+	Nt16Norm()
+	{
+		memset(t, 'N', sizeof t);
+		const char *code = "=ACMGRSVTWYHKDBN";
+		for (int i = 0; i < 16; ++i) { t[(unsigned char)code[i]] = code[i]; if (code[i] >= 'A') t[(unsigned char)(code[i] + 32)] = code[i]; }
+		t['0'] = 'A'; t['1'] = 'C'; t['2'] = 'G'; t['3'] = 'T';
+	}
+};
+const Nt16Norm g_nt16_norm;
 inline char rev_char(char c) { return g_rev.t[(unsigned char)c]; }
 void rev_str(char *s, int len)                                  // getReverseStr_char, clib/bam_file.c:330-340
 {
@@ -983,6 +994,7 @@ struct AlnPipeline::Impl {
 		const size_t at = out.size();
 		out.append(r.rec->seq, r.rec->seq_l); out += '\t'; out.append(r.rec->qual, r.rec->qual_l);
 		if (reversed) { rev_str(&out[at], r.read_l); rev_qual(&out[at + r.rec->seq_l + 1], r.read_l); }
+		for (size_t i = at, e = at + r.rec->seq_l; i < e; ++i) out[i] = g_nt16_norm.t[(unsigned char)out[i]];   // 4-bit round trip of SEQ
 	}
 	std::string target_name(uint32_t id) const { return id < idx.target_names.size() ? idx.target_names[id] : std::string("*"); }
 

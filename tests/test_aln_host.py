@@ -94,6 +94,23 @@ def test_edge_inputs_match_reference(fc_aln_emul):
             sp.run_reference_aln(d, r, ro, threads=1)
             fc_aln_emul(d, m, mo, threads=2)
             assert read(m) == read(r) and read(mo) == read(ro), name
+        # lower-case bases (incl. 'n', which the reference encodes as 4 and lets spill into the neighbouring base), IUPAC codes
+        # and a junk character: SEQ comes back through htslib's 4-bit round trip
+        import random
+        rnd = random.Random(3)
+        lc = list(fq)
+        for i in range(1, len(lc), 4):
+            lc[i] = "".join((c.lower() if rnd.random() < 0.05 else ("NRy."[rnd.randrange(4)] if rnd.random() < 0.004 else c)) for c in lc[i])
+        path = os.path.join(demo.wd, "lower.fq")
+        with open(path, "w") as f:
+            f.write("\n".join(lc))
+        d = sp.PipelineData(demo.data.workdir, demo.data.ref_fa, demo.data.vcf, demo.data.anchors_fa, demo.data.index_dir, path,
+                            demo.data.header_sam, 0, 0)
+        r, ro = os.path.join(demo.wd, "lc_ref.sam"), os.path.join(demo.wd, "lc_ref_ori.sam")
+        m, mo = os.path.join(demo.wd, "lc_my.sam"), os.path.join(demo.wd, "lc_my_ori.sam")
+        sp.run_reference_aln(d, r, ro, threads=1)
+        fc_aln_emul(d, m, mo, threads=2)
+        assert read(m) == read(r) and read(mo) == read(ro)
         # gzip-compressed input, and -R (max_use_read) cutting the input after 100 pairs
         gz = os.path.join(demo.wd, "reads.fq.gz")
         with open(demo.data.reads_fq, "rb") as f, gzip.open(gz, "wb", compresslevel=1) as g:
