@@ -50,7 +50,7 @@ void parse_fastq(const char *p, size_t n, std::vector<FastqRec> &out)
 		const char *nl = (const char*)memchr(p + i, '\n', n - i);
 		const size_t e = nl ? (size_t)(nl - p) : n;
 		size_t len = e - i;
-		if (len && p[i + len - 1] == '\r') --len;
+		// (a '\r' before the newline stays part of the line: the reference's reader keeps it, clib/utils.c:953-990)
 		b = p + i; l = (uint32_t)len;
 		i = e + 1;
 		return true;
@@ -116,7 +116,7 @@ bool parse_fastq_parallel(const char *p, size_t n, AlnPipeline &pipe, int thread
 					const char *x = q < n ? (const char*)memchr(p + q, '\n', n - q) : nullptr;
 					const size_t e2 = x ? (size_t)(x - p) : n;
 					size_t len = e2 - q;
-					if (len && p[q + len - 1] == '\r') --len;
+					// (a '\r' stays part of the line, like in parse_fastq)
 					ln[k] = p + q; ll[k] = (uint32_t)len;
 					q = e2 + 1;
 				}
@@ -329,12 +329,18 @@ int pansvr_aln_block_bam(pansvr_aln_ctx *c, const char *fastq, size_t n, uint8_t
 	const size_t np = text_sam.size();
 	std::vector<std::vector<uint8_t>> part_s(np), part_o(np);
 	std::vector<std::string> errs(np);
-	auto encode_lines = [&](const std::string &text, std::vector<uint8_t> &dst, std::string &err) {
+	// A record htslib's sam_parse1 would reject (the reference then writes a half-parsed bam1_t with undefined content, e.g. the
+	// -p record of a read whose original CIGAR does not match its sequence) is left out and counted, not fatal.
+	auto encode_lines = [&](const std::string &text, std::vector<uint8_t> &dst, std::string &) {
 		dst.reserve(text.size() / 2);
-		for (size_t p = 0; p < text.size() && err.empty();) {
+		for (size_t p = 0; p < text.size();) {
 			const char *nl = (const char*)memchr(text.data() + p, '\n', text.size() - p);
 			const size_t e = nl ? (size_t)(nl - text.data()) : text.size();
-			if (e > p) bam_encode_record(text.data() + p, e - p, c->bam_hdr, dst, err);
+			if (e > p) {
+				const size_t at = dst.size();
+				std::string why;
+				if (!bam_encode_record(text.data() + p, e - p, c->bam_hdr, dst, why)) { dst.resize(at); ++c->pipe->bad_cigar_records_; }
+			}
 			p = e + 1;
 		}
 	};
@@ -544,8 +550,9 @@ int pansvr_fc_aln_main(int argc, char **argv)
 	if (sam) { fclose(fo); fclose(fp); }
 	else if (pansvr_bam_close(bo) != 0 || pansvr_bam_close(bp) != 0) { fprintf(stderr, "pansvr_b200 fc_aln: %s\n", pansvr_aln_last_error()); ok = false; }
 	if (const uint64_t nbad = ctx->pipe->bad_cigar_records_.load())
-		fprintf(stderr, "pansvr_b200 fc_aln: %llu records left out: their CIGAR does not span the read (z-dropped extension; the reference writes such "
-		        "records as rejected by htslib, with undefined content)\n", (unsigned long long)nbad);
+		fprintf(stderr, "pansvr_b200 fc_aln: %llu records left out: htslib would reject them (a CIGAR that does not span the read after a z-dropped "
+		        "extension, or an original CIGAR that does not match the sequence); the reference writes such records with undefined content\n",
+		        (unsigned long long)nbad);
 	pansvr_aln_stats_t st;
 	pansvr_aln_last_stats(ctx, &st);
 	fprintf(stderr, "pansvr_b200 fc_aln: %ld reads, %ld MEMs, %ld ksw tasks; stage seconds A %.3f B %.3f C %.3f D %.3f E %.3f F %.3f parse %.3f emit %.3f\n",
