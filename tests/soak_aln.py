@@ -45,6 +45,14 @@ def main():
         t0 = time.time()
         try:
             d = sp.make_demo(wd, **kw)
+            if rng.random() < 0.4:                                       # lower-case bases, IUPAC codes and junk characters in the reads
+                import random
+                rnd = random.Random(int(rng.integers(1, 1 << 30)))
+                lines = open(d.reads_fq).read().split("\n")
+                for li in range(1, len(lines), 4):
+                    lines[li] = "".join((c.lower() if rnd.random() < 0.05 else ("nRy."[rnd.randrange(4)] if rnd.random() < 0.003 else c)) for c in lines[li])
+                with open(d.reads_fq, "w") as f:
+                    f.write("\n".join(lines))
             p = lambda n: os.path.join(wd, n)
             sp.run_reference_aln(d, p("r.sam"), p("ro.sam"), threads=1, extra=opts)
             sp.run_reference_aln(d, p("r.bam"), p("ro.bam"), threads=1, bam=True, extra=opts)
