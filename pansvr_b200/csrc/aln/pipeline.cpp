@@ -223,6 +223,8 @@ struct ReadState {
 	const FastqRec *rec = nullptr;
 	std::string comment;                       // mutable copy (the reference edits its kseq_t in place)
 	int read_l = 0;
+	bool seq_twice_reversed = false;           // the reference reverse-complemented its kseq_t in place and back (output_BAM on a
+	                                           // reverse-strand record): anything but ACGT is 'N' from then on, e.g. in the -p record
 	bool has_n = false, skip = false;          // skip: early-out of single_end_handler::align (RR:413-414)
 	// original alignment (parse_ori_mapping_rst)
 	Result ori;
@@ -993,6 +995,7 @@ struct AlnPipeline::Impl {
 	{
 		const size_t at = out.size();
 		out.append(r.rec->seq, r.rec->seq_l); out += '\t'; out.append(r.rec->qual, r.rec->qual_l);
+		if (r.seq_twice_reversed) for (size_t i = at, e = at + r.rec->seq_l; i < e; ++i) out[i] = rev_char(rev_char(out[i]));
 		if (reversed) { rev_str(&out[at], r.read_l); rev_qual(&out[at + r.rec->seq_l + 1], r.read_l); }
 		for (size_t i = at, e = at + r.rec->seq_l; i < e; ++i) out[i] = g_nt16_norm.t[(unsigned char)out[i]];   // 4-bit round trip of SEQ
 	}
@@ -1006,7 +1009,7 @@ struct AlnPipeline::Impl {
 		// A z-dropped extension (only with -z well below the default) can leave a CIGAR shorter than the read.  The reference
 		// logs "ERROR cigar", htslib rejects the record and the reference then writes the half-parsed bam1_t with stale buffer
 		// bytes; there is nothing defined to reproduce, so the record is left out and counted.
-		if (!p->is_ori && !p->cigar_ok) { ++P.bad_cigar_records_; return; }
+		if (!p->is_ori && !p->cigar_ok) { ++P.bad_cigar_records_; if (p->direction == REVERSE) r.seq_twice_reversed = true; return; }
 		const int dir = p->direction;
 		const uint8_t flag = (uint8_t)((first ? 0x40 : 0) + (dir == REVERSE ? 0x10 : 0) + (p->has_mate ? 0 : 0x08));
 		out.append(r.rec->name, r.rec->name_l); out += '\t'; append_int(out, flag); out += '\t';
@@ -1020,6 +1023,7 @@ struct AlnPipeline::Impl {
 			out += '\t'; append_int(out, (int)p->mate_ref_bg); out += '\t'; append_int(out, isize); out += '\t';
 		} else out += "*\t0\t0\t";
 		append_seq_qual(out, r, dir == REVERSE); out += '\t';
+		if (dir == REVERSE) r.seq_twice_reversed = true;
 		out += "AS:i:"; append_int(out, (int)p->align_score);
 		out += "\tOS:i:"; append_int(out, (int)r.ori.align_score);
 		out += "\tOA:Z:"; append_int(out, (int)r.ori.chr); out += ','; append_int(out, (int)r.ori.ref_bg); out += ',';

@@ -79,8 +79,12 @@ def main():
                 same = None if (rc1 == 0 and rc2 == 0 and mine == good and rd("mo.sam") == rd("ro.sam")) else False
             bad += same is False
             print(f"set {k}: identical={same} pairs={d.n_pairs} anchors={d.n_sv} threads={threads} sub_pairs={sub} opts={" ".join(opts)} {kw} identical={same} ({time.time() - t0:.1f} s)", flush=True)
+            if same is False and os.environ.get("PANSVR_SOAK_KEEP"):
+                print("kept", wd, flush=True)
+                wd = None
         finally:
-            shutil.rmtree(wd, ignore_errors=True)
+            if wd:
+                shutil.rmtree(wd, ignore_errors=True)
     print("sets", n_sets, "failures", bad)
     return 1 if bad else 0
 
