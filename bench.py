@@ -1,31 +1,35 @@
 #!/usr/bin/env python
-"""bench.py -- the hot-path benchmark of pansvr_b200 (BASELINE.json metric: realigned reads/s and GCUPS).
+"""bench.py -- the hot-path benchmark of pansvr_b200: the whole `fc_aln` stage (BASELINE.json metric: realigned reads/s and
+GCUPS at 1/2/4/8 B200 vs the CPU `panSVR aln`), on SURVEY.md section 8d "Config 3" = BASELINE.json configs[2]:
+10 M x 150 bp signal reads vs 10 500 anchors with 50 bp - 10 kb INS/DEL alleles, 2-4 alleles per locus (multi-candidate reads,
+exact score ties), FASTQ text in -> SAM text out through the C ABI (pansvr_aln_block, include/pansvr_b200.h).
 
-One "step" = one pass of the ksw extension stage over one batch of synthetic tasks of
-BASELINE.json configs[1] ("1 M x 150 bp signal reads vs ~1.1 kb anchor windows, band 100", SURVEY.md
-section 8d "Config 2"): every read is one ksw_extd2 task (qlen 150, tlen 1100, w 100, zdrop 400,
-flag 0, 2/-12, gaps min(16+k, 32)) = 25 100 in-band DP cells, with traceback and CIGAR.
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--pairs P]
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--tasks T] [--impl reference]
-
-value   : whole-job reads/s with the batch already resident in HBM (pansvr_ksw_extd2_batch_device),
-          CUDA-event time of the call on its own stream (host planning gap + plan upload + kernels).
-e2e     : the same metric through the host-buffer C-ABI call (pansvr_ksw_extd2_batch): pinned host
-          buffers in, H2D + kernels + D2H of results and CIGARs inside the timed region.
-N > 1   : one process per GPU (torchrun), every rank runs its own T tasks (weak scaling), no
-          collective on the data path; time = max over ranks.
---impl reference : the reference's own ksw2_extd2_sse.c (oracle/_ref, else the oracle port) on all
-          host cores, one bounded sample of the same workload per step.
+step    : one pass of the stage over the whole input (all ranks together).  ctx.reset() between steps puts the rand() replay
+          back to the state of a freshly started fc_aln, so every step produces the same bytes.
+value   : whole-job realigned reads/s with the FASTQ text of the rank's shard already staged in pinned host memory
+          (what step 0 of the reference's pipeline hands to step 1) -- every stage of the path runs, host and device.
+e2e     : the same through the plain host-buffer call: pageable FASTQ text in, malloc'ed SAM text out; h2d/d2h bytes are what
+          the library copied (counted where the copies are issued).
+N > 1   : one process per GPU (torchrun); ONE input, cut into N contiguous ranges of pairs (strong scaling); no collective on
+          the data path.  The only state that flows between pairs is the reference's process-wide rand() stream: rank r hands
+          the stream state to rank r+1 through a small file when its replay is done (pansvr_aln_publish_state /
+          pansvr_aln_await_state); every rank runs all other stages of its shard without waiting.  time = max over ranks.
+roofline: the DP kernel (ksw_team, integer ALU: cells x 55 ops / kernel time / measured integer peak) as it runs inside the
+          stage, and "roofline_seed": the seeding kernels against HBM (SURVEY.md section 8d byte model / kernel time / hbm_gbs).
+ksw_config2: the kernel-level line of BASELINE.json configs[1] (1 M x 150 bp vs 1.1 kb windows, w=100), from bench_ksw.py.
+--impl reference : the reference's own `panSVR fc_aln -t <cores> -S` (oracle/_ref, built from the unmodified reference) on a
+          bounded prefix of the same input per step, start-up (`-R 1`: the 2 GiB index read) subtracted.
 """
 from __future__ import annotations
 
 import argparse
+import ctypes as C
+import hashlib
 import json
 import os
-import statistics
-import subprocess
 import sys
-import tempfile
 import time
 
 import numpy as np
@@ -33,283 +37,339 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-CELLS_PER_TASK = 25100          # band_cells(150, 1100, 100), SURVEY.md 8d
+import bench_ksw  # noqa: E402
+from bench_ksw import ClockSampler, env_int, measured_peaks  # noqa: E402
+
 OPS_PER_CELL = 55               # int ops per DP cell with traceback
-CIGAR_CAP = 16
+SEED_BYTES_MISS, SEED_BYTES_HIT = 64, 290      # SURVEY.md 8d seeding byte model: per miss probe / per hit
+METRIC = "realigned reads/s (fc_aln stage: FASTQ text in, SAM text out; config 3)"
 
 
-NCU_DRAM_BYTES_PER_TASK = 56400       # profiles/r1h_ksw_team_full.md (r1o addendum: 20.68 GB read + 35.72 GB written per 1 M tasks)
+def workload_name(d):
+    return (f"config3: {2 * d.n_pairs} x {d.read_len} bp signal reads vs {d.n_anchors} anchors, 50 bp-10 kb INS/DEL alleles, 2-4 alleles "
+            "per locus sharing flanks (BASELINE.json configs[2], SURVEY.md 8d)")
 
 
-def env_int(name, default):
-    try:
-        return int(os.environ.get(name, default))
-    except ValueError:
-        return default
+def ref_threads():
+    return min(48, os.cpu_count() or 1)          # the reference caps -t at 48 (read_realignment.hpp:121)
 
 
-def measured_peaks():
-    try:
-        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
-            return json.load(f), "MEASURED_PEAKS.json"
-    except Exception:
-        return {"hbm_gbs": 6650.0}, "fallback (B200_PROFILING.md)"
+def reference_startup(d, cache=True):
+    """Wall seconds of `fc_aln -R 1` (index load etc.), min of 2."""
+    from benchdata import config3
+    return min(config3.run_reference_aln(d, 1, max_pairs=1) for _ in range(2))
 
 
-class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
-
-    def __init__(self, gpu_index):
-        self.gpu = gpu_index
-        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
-        self.p = None
-
-    def start(self):
-        try:
-            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                                       "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
-        except Exception:
-            self.p = None
-
-    def stop(self):
-        if self.p is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.p.terminate()
-        try:
-            self.p.wait(timeout=5)
-        except Exception:
-            self.p.kill()
-        self.f.flush()
-        sm, smax, reasons = [], [], set()
-        with open(self.f.name) as f:
-            for line in f:
-                c = [x.strip() for x in line.split(",")]
-                if len(c) < 9:
-                    continue
-                try:
-                    sm.append(float(c[1])); smax.append(float(c[2]))
-                except ValueError:
-                    continue
-                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
-                    if v.lower().startswith("active"):
-                        reasons.add(name)
-        os.unlink(self.f.name)
-        if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
-        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(smax), "reasons": sorted(reasons), "samples": len(sm)}
-
-
-def cpu_reference_rate(batch, sample_tasks, threads):
-    """reads/s of the reference's CPU ksw on `threads` host threads over a bounded sample."""
-    from oracle import pyoracle
-    pyoracle.build()
-    kind, impl = ("reference", "ref") if pyoracle.have_ref() else ("port", "oracle")
-    sub = batch.head(sample_tasks)
-    pyoracle.run(sub.head(min(2000, sub.n)), impl, threads=threads, cigar_cap=CIGAR_CAP)      # page in / warm
-    _, _, secs = pyoracle.run(sub, impl, threads=threads, cigar_cap=CIGAR_CAP)
-    return sub.n / secs, kind, secs, sub.n
-
-
-def run_reference_arm(args, rank, world):
+def run_reference_arm(args, rank):
     if rank != 0:
         return
-    from pansvr_b200 import synth
-    threads = min(48, os.cpu_count() or 1)          # the reference caps -t at 48 (read_realignment.hpp:121)
-    sample = args.ref_sample
-    batch = synth.config2_batch(sample, seed=11)
-    from oracle import pyoracle
-    pyoracle.build()
-    kind, impl = ("reference", "ref") if pyoracle.have_ref() else ("port", "oracle")
-    for _ in range(args.warmup):
-        pyoracle.run(batch.head(max(1000, sample // 10)), impl, threads=threads, cigar_cap=CIGAR_CAP)
+    from benchdata import config3
+    d = config3.prepare(pairs=args.pairs, loci=args.loci)
+    threads = ref_threads()
+    sample = min(args.ref_sample_pairs, d.n_pairs)
+    t_start = reference_startup(d)
+    for _ in range(min(args.warmup, 2)):
+        config3.run_reference_aln(d, threads, max_pairs=min(sample, 50_000))
     secs = []
     for _ in range(args.steps):
-        _, _, s = pyoracle.run(batch, impl, threads=threads, cigar_cap=CIGAR_CAP)
-        secs.append(s)
+        secs.append(max(config3.run_reference_aln(d, threads, max_pairs=sample) - t_start, 1e-6))
     tot = sum(secs)
-    rate = sample * args.steps / tot
+    rate = 2 * sample * args.steps / tot
     line = {
-        "impl": "reference", "metric": "realigned reads/s (ksw extension stage, config 2)", "value": rate, "unit": "reads/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int8 differences / int32 H (SSE2)",
-        "data": "synthetic", "gcups": rate * CELLS_PER_TASK / 1e9,
-        "config": {"workload": "config2: 150 bp reads vs 1.1 kb anchor windows, w=100, zdrop=400, flag=0, with CIGAR",
-                   "tasks_per_step": sample, "cells_per_task": CELLS_PER_TASK},
-        "cpu_baseline": {"value": rate, "unit": "reads/s", "cores": threads, "kind": kind,
-                         "sample": f"{sample} tasks of the same workload per step, ksw_extd2_sse from "
-                                   f"{'oracle/_ref/libksw_ref.so (reference source, -O3, SSE2 as shipped)' if kind == 'reference' else 'oracle port'}"
-                                   f" on a pthread pool, one ksw_extz_t per thread"},
+        "impl": "reference", "metric": METRIC, "value": rate, "unit": "reads/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * tot / args.steps, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "int8 differences / int32 H (SSE2 ksw), host C++", "data": "synthetic",
+        "config": {"workload": workload_name(d), "reads_per_step": 2 * sample,
+                   "sample": f"first {sample} pairs of the same input per step"},
+        "cpu_baseline": {"value": rate, "unit": "reads/s", "cores": threads, "kind": "reference",
+                         "sample": f"`panSVR fc_aln -t {threads} -S -R {sample}` (oracle/_ref: the unmodified reference) on the first {sample} pairs "
+                                   f"of the same input, wall minus the {t_start:.2f} s start-up measured with -R 1; SAM written to /dev/null"},
         "e2e": {"value": rate, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0,
+        "gpu_launches": 0, "startup_seconds": t_start,
     }
     print(json.dumps(line), flush=True)
+
+
+def reference_t1_md5(d, pairs):
+    """md5 of the SAM / -p files of `fc_aln -t 1 -S -R pairs` (the deterministic mode = the output oracle), cached per box."""
+    from benchdata import config3
+    cache = os.path.join(d.workdir, f"ref_t1_{pairs}.json")
+    if os.path.exists(cache):
+        with open(cache) as f:
+            return json.load(f)
+    out, ori = os.path.join(d.workdir, f"ref_t1_{pairs}.sam"), os.path.join(d.workdir, f"ref_t1_{pairs}_ori.sam")
+    t0 = time.time()
+    config3.run_reference_aln(d, 1, max_pairs=pairs, out_sam=out, ori_sam=ori)
+    secs = time.time() - t0
+    res = {"seconds": secs}
+    for k, p in (("sam", out), ("ori", ori)):
+        h = hashlib.md5()
+        with open(p, "rb") as f:
+            for chunk in iter(lambda: f.read(64 << 20), b""):
+                h.update(chunk)
+        res[k] = h.hexdigest()
+        res[k + "_bytes"] = os.path.getsize(p)
+        os.unlink(p)
+    with open(cache, "w") as f:
+        json.dump(res, f)
+    return res
+
+
+def md5_of(header: bytes, addr: int, n: int) -> str:
+    h = hashlib.md5(header)
+    if n:
+        h.update((C.c_char * n).from_address(addr))
+    return h.hexdigest()
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--tasks", type=int, default=1_000_000, help="tasks (reads) per GPU per step")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--ref-sample", type=int, default=200_000, help="tasks per step of the CPU reference arm")
-    ap.add_argument("--cpu-sample", type=int, default=600_000, help="tasks of the cpu_baseline leg")
+    ap.add_argument("--pairs", type=int, default=5_000_000, help="read pairs of the input (config 3: 5 M pairs = 10 M reads)")
+    ap.add_argument("--loci", type=int, default=5250, help="SV loci of the anchor set (config 3: 5250 loci = 10 500 anchors)")
+    ap.add_argument("--block-pairs", type=int, default=491_520, help="pairs per pansvr_aln_block call at N=1 (multiple of 4096)")
+    ap.add_argument("--ref-sample-pairs", type=int, default=250_000, help="pairs per step of the CPU reference arm / cpu_baseline")
+    ap.add_argument("--parity-pairs", type=int, default=491_520, help="prefix checked against `fc_aln -t 1` in the run (0 = off)")
+    ap.add_argument("--threads", type=int, default=0, help="host helper threads per rank (0 = cores / ranks)")
+    ap.add_argument("--no-ksw", action="store_true", help="skip the config-2 kernel line")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
     args.warmup = max(args.warmup, 0)
-
     if args.impl == "reference":
-        run_reference_arm(args, rank, world)
+        run_reference_arm(args, rank)
         return
 
     import torch
-    from pansvr_b200 import ksw, shard, synth
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device; the B200 path has no CPU fallback (use --impl reference for the CPU arm)")
-    torch.cuda.set_device(local)
+    from benchdata import config3
+    from pansvr_b200 import aln, ksw, shard
+    # PANSVR_BENCH_EMUL=1 (tests only): dry run of this script's flow on the host-emulated pipeline of tests/emul, gloo instead of
+    # nccl; the line it prints is marked "emulated" and its numbers mean nothing.  The product path needs a B200.
+    emul = bool(os.environ.get("PANSVR_BENCH_EMUL"))
+    emul_lib = None
+    if emul:
+        os.environ.setdefault("PANSVR_ORACLE_SO", os.path.join(ROOT, "oracle", "libksw_oracle.so"))
+        emul_lib = C.CDLL(os.path.join(ROOT, "tests", "emul", "libaln_emul.so"))
+        args.no_ksw = args.no_cpu_baseline = True
+        dev = torch.device("cpu")
+    else:
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py: no CUDA device; the B200 path has no CPU fallback (use --impl reference for the CPU arm)")
+        torch.cuda.set_device(local)
+        dev = torch.device("cuda", local)
     dist = None
     if world > 1:
         import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    dev = torch.device("cuda", local)
-    ctx = ksw.KswContext(local)
+        if emul:
+            dist.init_process_group("gloo")
+        else:
+            dist.init_process_group("nccl", device_id=dev)
 
-    # ---- synthetic workload (every rank its own seed: weak scaling, reads shard trivially)
-    n = args.tasks
-    batch = synth.config2_batch(n, seed=shard.shard_seed(11, rank))
-    p = batch.params
-    cells = CELLS_PER_TASK * n
-    # pinned host staging (the batcher's buffers) and the device-resident copy
-    pins = {}
-    for k, dt in (("qseq", np.uint8), ("tseq", np.uint8), ("qoff", np.int64), ("toff", np.int64), ("qlen", np.int32), ("tlen", np.int32)):
-        a = np.ascontiguousarray(getattr(batch, k), dt)
-        pa = ksw.PinnedArray(a.shape, dt)
-        pa.array[...] = a
-        pins[k] = pa
-    hb = synth.KswBatch(pins["qseq"].array, pins["qoff"].array, pins["qlen"].array, pins["tseq"].array, pins["toff"].array,
-                        pins["tlen"].array, p, batch.name)
-    out_res = ksw.PinnedArray((n, ksw.RES_WORDS), np.int32)
-    out_cig = ksw.PinnedArray((n, CIGAR_CAP), np.uint32)
-    d = {k: torch.from_numpy(pins[k].array).to(dev) for k in pins}
-    d_res = torch.zeros((n, ksw.RES_WORDS), dtype=torch.int32, device=dev)
-    d_cig = torch.zeros((n, CIGAR_CAP), dtype=torch.int32, device=dev)
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
-    torch.cuda.synchronize()
-
-    def step_resident():
-        ctx.extd2_batch_device(n, d["qseq"].data_ptr(), d["qoff"].data_ptr(), d["qlen"].data_ptr(), d["tseq"].data_ptr(),
-                               d["toff"].data_ptr(), d["tlen"].data_ptr(), hb.qlen, hb.tlen, p, d_res.data_ptr(), d_cig.data_ptr(),
-                               CIGAR_CAP)
-        return ctx.stats()
-
-    def step_e2e():
-        ctx.extd2_batch(hb, cigar_cap=CIGAR_CAP, out=(out_res.array, out_cig.array))
-        return ctx.stats()
+    d = config3.prepare(pairs=args.pairs, loci=args.loci)
+    # ---- this rank's contiguous range of pairs, cut at multiples of IDX_STRIDE (results are merged by pair index)
+    S = config3.IDX_STRIDE
+    units = (d.n_pairs + S - 1) // S
+    ub, ue = shard.shard_range(units, rank, world)
+    pb, pe = ub * S, min(ue * S, d.n_pairs)
+    b0, b1 = d.byte_range(pb, pe)
+    nbytes = b1 - b0
+    pin = ksw.PinnedArray((max(nbytes, 1),), np.uint8) if not emul else argparse.Namespace(array=np.empty(max(nbytes, 1), np.uint8))
+    with open(d.reads_fq, "rb") as f:
+        f.seek(b0)
+        got = f.readinto(memoryview(pin.array)[:nbytes]) if nbytes else 0
+    assert got == nbytes
+    pageable = bytes(memoryview(pin.array)[:nbytes])                     # the e2e leg's input: ordinary host memory
+    with open(d.reads_fq, "rb") as f:
+        head = f.read(4096)                                              # first record of the input (STAT_ fields, RR:134-148)
+    # calls of one step: at N=1 blocks of --block-pairs (the first one doubles as the parity prefix); a rank of an N>1 run hands
+    # its whole shard over in one call so that nothing of it waits for the upstream rank's stream state but the in-order passes
+    if world == 1:
+        bp = max(S, args.block_pairs // S * S)
+        cuts = list(range(pb, pe, bp)) + [pe]
+    else:
+        cuts = [pb, pe]
+    calls = []
+    for c0, c1 in zip(cuts[:-1], cuts[1:]):
+        o0, o1 = d.byte_range(c0, c1)
+        calls.append((o0 - b0, o1 - o0, c1 - c0))
+    threads = args.threads or max(1, min(48, (os.cpu_count() or 1) // world))
+    ctx = aln.AlnContext(d.index_dir, d.header_sam, device=local, threads=threads, lib=emul_lib)
+    ctx.prime_read_stats(head)
+    header = ctx.header_text().encode()
+    run_id = [f"{os.getpid()}_{int(time.time())}"]
+    if dist is not None:
+        dist.broadcast_object_list(run_id, src=0)      # stream-state files of this run only
+    run_id = run_id[0]
+    state_dir = os.path.join("/dev/shm" if os.path.isdir("/dev/shm") else d.workdir, f"pansvr_state_{run_id}")
+    os.makedirs(state_dir, exist_ok=True)
+    step_no = [0]
 
     def barrier():
         if dist is not None:
             dist.barrier()
-        torch.cuda.synchronize()
+        if not emul:
+            torch.cuda.synchronize()
 
-    def timed(step, k_steps):
-        tot_ms, kern_ms, launches, last = 0.0, 0.0, 0, None
+    def one_step(kind, keep_first=False):
+        """One pass over this rank's shard.  Returns (stats, md5 of the first call's output or None)."""
+        k = step_no[0]; step_no[0] += 1
+        ctx.reset()
+        ctx.prime_read_stats(head)
+        if world > 1 and rank > 0:
+            ctx.await_state(os.path.join(state_dir, f"s{k}_r{rank}"))
+        first = None
+        base = pin.array.ctypes.data
+        for i, (off, n, _) in enumerate(calls):
+            if kind == "resident":
+                sam, ori, release = ctx.align_ptr(base + off, n)
+            else:
+                (sam, ori, release) = ctx.align_bytes_at(pageable, off, n)
+            if keep_first and i == 0:
+                first = (md5_of(header, *sam), md5_of(header, *ori), sam[1], ori[1])
+            release()
+        if world > 1 and rank + 1 < world:
+            ctx.publish_state(os.path.join(state_dir, f"s{k}_r{rank + 1}"))
+        return ctx.stats(), first
+
+    def timed(kind, k_steps):
+        acc = None
         barrier()
+        if not emul:
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record()
         t0 = time.perf_counter()
         for _ in range(k_steps):
-            flush.zero_()                      # L2 flush between timed iterations (outside the event brackets)
-            torch.cuda.synchronize()
-            last = step()
-            tot_ms += last["total_ms"]; kern_ms += last["kernel_ms"]; launches += last["kernel_launches"]
+            st, _ = one_step(kind)
+            if acc is None:
+                acc = {k: (list(v) if isinstance(v, list) else v) for k, v in st.items()}
+            else:
+                for k, v in st.items():
+                    acc[k] = [a + b for a, b in zip(acc[k], v)] if isinstance(v, list) else acc[k] + v
+        if not emul:
+            ev1.record()
         barrier()
         wall_ms = (time.perf_counter() - t0) * 1e3
-        tot_ms, kern_ms, wall_ms = shard.max_over_ranks([tot_ms, kern_ms, wall_ms], dist, dev)
-        return tot_ms, kern_ms, launches, wall_ms, last
+        ev_ms = ev0.elapsed_time(ev1) if not emul else wall_ms
+        wall_ms, ev_ms = shard.max_over_ranks([wall_ms, ev_ms], dist, dev)
+        return wall_ms, ev_ms, acc
 
     for _ in range(args.warmup):
-        step_resident()
-    for _ in range(min(args.warmup, 2)):
-        step_e2e()
-
+        one_step("resident")
+    for _ in range(min(args.warmup, 1)):
+        one_step("e2e")
     sampler = ClockSampler(local)
-    if rank == 0:
+    if rank == 0 and not emul:
         sampler.start()
-    tot_ms, kern_ms, launches, wall_ms, last = timed(step_resident, args.steps)
-    e_tot_ms, e_kern_ms, e_launches, e_wall_ms, e_last = timed(step_e2e, args.steps)
-    clocks = sampler.stop() if rank == 0 else None
+    wall_ms, ev_ms, st = timed("resident", args.steps)
+    e_wall_ms, e_ev_ms, e_st = timed("e2e", args.steps)
+    clocks = sampler.stop() if rank == 0 and not emul else None
 
-    # parity spot check of what was just timed (result of the e2e pass, sample vs the oracle) -- rank 0
+    # ---- parity in the run: the first call's output against `panSVR fc_aln -t 1 -S -R <pairs>` (md5 of both files)
     parity = None
-    if rank == 0:
-        from oracle import pyoracle
-        idx = np.random.default_rng(1).choice(n, min(n, 2000), replace=False)
-        r0, c0, _ = pyoracle.run(hb.take(idx), "oracle", threads=min(16, os.cpu_count() or 1), cigar_cap=CIGAR_CAP)
-        parity = bool(np.array_equal(r0[:, :11], out_res.array[idx][:, :11]) and np.array_equal(c0, out_cig.array[idx])
-                      and np.array_equal(d_res.cpu().numpy()[idx][:, :11], r0[:, :11]))
+    if args.parity_pairs > 0:
+        _, first = one_step("resident", keep_first=(rank == 0))           # (every rank: the state files are per step)
+        if rank == 0 and os.access(os.path.join(config3.REF_BIN, "panSVR"), os.X_OK):
+            pp = calls[0][2]
+            ref = reference_t1_md5(d, pp)
+            parity = {"pairs": pp, "sam_md5_equal": first[0] == ref["sam"], "ori_md5_equal": first[1] == ref["ori"],
+                      "sam_bytes": first[2], "ori_bytes": first[3], "reference": f"oracle/_ref/panSVR fc_aln -t 1 -S -R {pp}",
+                      "reference_t1_seconds": ref.get("seconds")}
+    barrier()
 
-    int_peak = ctx.int_alu_peak_gops() if rank == 0 else 0.0
+    # ---- gather the per-rank device counters (sums) on rank 0
+    keys = ("reads", "mems", "ksw_tasks", "ksw_cells", "kernel_launches", "h2d_bytes", "d2h_bytes", "seed_probes")
+    vec = [float(st[k]) for k in keys] + [float(e_st[k]) for k in keys]
+    mx = [st["seed_kernel_ms"], st["ksw_kernel_ms"], st["stage_kernel_ms"]] + list(st["stage_seconds"])
+    if dist is not None:
+        t = torch.tensor(vec, dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        vec = [float(x) for x in t.cpu()]
+        mx = shard.max_over_ranks(mx, dist, dev)
+    tot = dict(zip(keys, vec[:len(keys)]))
+    e_tot = dict(zip(keys, vec[len(keys):]))
+    seed_ms, ksw_ms, stage_ms = mx[0], mx[1], mx[2]
+    stage_seconds = mx[3:]
+
+    ksw_line = None
+    if not args.no_ksw:
+        ctx.close()
+        ka = bench_ksw.parse_args(["--steps", "3", "--warmup", "3", "--no-cpu-baseline"])
+        ksw_line = bench_ksw.measure(ka, rank, world, local, dist)
+        ctx = None
+    pipes = {}
+    if rank == 0 and ksw_line is not None:
+        pipes = ksw_line["roofline"].get("pipe_peaks_gops", {})
+    elif rank == 0 and not emul:
+        kc = ksw.KswContext(local)
+        pipes = kc.int_pipe_peaks_gops()
+        kc.close()
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
         return
 
     peaks, peak_src = measured_peaks()
-    reads_s = shard.whole_job_rate(n, args.steps, world, tot_ms)
-    e2e_reads_s = shard.whole_job_rate(n, args.steps, world, e_tot_ms)
-    kernel_gcups = cells * args.steps / (kern_ms * 1e-3) / 1e9                  # per GPU, dominant kernel only
-    achieved_gops = kernel_gcups * OPS_PER_CELL
-    # HBM view of the same kernel: bytes it must move per task (query + touched target + traceback written
-    # + results), SURVEY 8d: 1 B per computed cell of traceback dominates
-    tb_bytes = 0
-    for r in range(150 + 1100 - 1):
-        lo = max(0, r - 149, (r - 100 + 1) >> 1); hi = min(1099, r, (r + 100) >> 1)
-        if lo > hi:
-            break
-        tb_bytes += (hi | 15) - (lo & ~15) + 1
-    bytes_per_task = 150 + 272 + tb_bytes + 48 + 4 * CIGAR_CAP
-    hbm_gbs = bytes_per_task * n * args.steps / (kern_ms * 1e-3) / 1e9
-
+    n_reads = 2 * d.n_pairs
+    reads_s = n_reads * args.steps / (ev_ms * 1e-3)
+    e_reads_s = n_reads * args.steps / (e_ev_ms * 1e-3)
+    cells_s = tot["ksw_cells"] / (ev_ms * 1e-3)
+    # DP kernel as it runs inside the stage: cells of the emitted tasks / CUDA-event time of the ksw kernels (slowest rank)
+    int_peak = pipes.get("mixed", 0.0)
+    ksw_gcups = (tot["ksw_cells"] / world) / (ksw_ms * 1e-3) / 1e9 if ksw_ms > 0 else 0.0
+    ksw_gops = ksw_gcups * OPS_PER_CELL
+    # seeding: SURVEY 8d byte model; the two passes (count, fill) each make every probe
+    hits = tot["mems"]
+    seed_bytes = 2 * ((tot["seed_probes"] - min(hits, tot["seed_probes"])) * SEED_BYTES_MISS + hits * SEED_BYTES_HIT)
+    seed_gbs = (seed_bytes / world) / (seed_ms * 1e-3) / 1e9 if seed_ms > 0 else 0.0
     line = {
-        "metric": "realigned reads/s (ksw extension stage, config 2)",
-        "value": reads_s, "unit": "reads/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": tot_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "u16x2 (exact int8 emulation) / int32 H", "data": "synthetic",
-        "gcups": reads_s * CELLS_PER_TASK / 1e9, "kernel_gcups_per_gpu": kernel_gcups,
-        "config": {"workload": "config2: 1 M x 150 bp reads vs 1.1 kb anchor windows, w=100, zdrop=400, flag=0, with traceback/CIGAR "
-                               "(BASELINE.json configs[1])",
-                   "tasks_per_gpu_per_step": n, "cells_per_task": CELLS_PER_TASK, "cigar_cap": CIGAR_CAP,
-                   "l2": "explicit 256 MB L2 flush between timed iterations; inputs 167 MB + traceback scratch also exceed L2",
-                   "parallelism": f"reads sharded over {world} GPU(s), no collective on the data path"},
-        "e2e": {"value": e2e_reads_s, "unit": "reads/s", "h2d_bytes_per_step": int(e_last["h2d_bytes"]) * world,
-                "d2h_bytes_per_step": int(e_last["d2h_bytes"]) * world, "ms_per_step": e_tot_ms / args.steps,
-                "gcups": e2e_reads_s * CELLS_PER_TASK / 1e9},
-        "gpu_launches": int(launches + e_launches),
-        "roofline": {"bound": "int_alu", "achieved": achieved_gops, "peak": int_peak, "unit": "Gop/s",
-                     "frac": achieved_gops / int_peak if int_peak else None,
-                     # DRAM bytes per launch of this kernel from ncu (profiles/r1h_ksw_team_full.md, r1o addendum:
-                     # 56.40 GB at 1 M tasks = dram__bytes_read 20.68 GB + dram__bytes_write 35.72 GB), scaled to this launch
-                     "traffic": NCU_DRAM_BYTES_PER_TASK * n, "traffic_unit": "bytes/launch",
-                     "algorithmic_bytes": bytes_per_task * n,
-                     "kernel": "ksw_team_kernel<8,true>", "kernel_ms_per_launch": kern_ms / args.steps,
-                     "ops_per_cell": OPS_PER_CELL, "gcups": kernel_gcups,
-                     "peak_source": "pansvr_int_alu_peak measured live on this GPU (IADD3/LOP3/VIMNMX chains)",
-                     "hbm": {"achieved": hbm_gbs, "peak": peaks.get("hbm_gbs"), "unit": "GB/s",
-                             "frac": hbm_gbs / peaks["hbm_gbs"] if peaks.get("hbm_gbs") else None,
-                             "bytes_per_task": bytes_per_task, "peak_source": peak_src}},
+        "metric": METRIC, "value": reads_s, "unit": "reads/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ev_ms / args.steps, "higher_is_better": True, "scaling": "strong" if world > 1 else "weak", "vs_baseline": None,
+        "dtype": "u16x2 (exact int8 emulation) / int32 H in the DP kernel; uint64 2-bit words in seeding", "data": "synthetic",
+        "gcups": cells_s / 1e9,
+        "config": {"workload": workload_name(d), "reads_per_step": n_reads, "pairs_per_rank": pe - pb, "calls_per_step_per_rank": len(calls),
+                   "host_threads_per_rank": threads, "host_cores": os.cpu_count(),
+                   "l2": "inputs exceed L2: every call streams hundreds of MB of packed reads, MEMs, ksw tasks and traceback (no reuse between steps)",
+                   "parallelism": (f"one input cut into {world} contiguous pair ranges, one process per GPU, no collective on the data path; "
+                                   "rand() stream state handed from rank to rank through a file") if world > 1 else "1 GPU",
+                   "timing": "CUDA events on the rank's current stream around the K steps after a barrier + synchronize, max over ranks (wall clock agrees: see wall_ms_per_step)"},
+        "e2e": {"value": e_reads_s, "unit": "reads/s", "h2d_bytes_per_step": int(e_tot["h2d_bytes"] / args.steps),
+                "d2h_bytes_per_step": int(e_tot["d2h_bytes"] / args.steps), "ms_per_step": e_ev_ms / args.steps,
+                "host_in_bytes_per_step": int(d.pair_offsets[-1]), "note": "pageable FASTQ text in, malloc'ed SAM text out through pansvr_aln_block"},
+        "gpu_launches": int(tot["kernel_launches"] + e_tot["kernel_launches"]),
+        "roofline": {"bound": "int_alu", "kernel": "ksw_team_kernel (stage E, all variants of the fc_aln task mix, w=200)",
+                     "achieved": ksw_gops, "peak": int_peak, "unit": "Gop/s", "frac": ksw_gops / int_peak if int_peak else None,
+                     "gcups": ksw_gcups, "ops_per_cell": OPS_PER_CELL, "kernel_ms_per_step": ksw_ms / args.steps,
+                     "cells_per_step": tot["ksw_cells"] / args.steps, "tasks_per_step": tot["ksw_tasks"] / args.steps,
+                     "pipe_peaks_gops": pipes, "frac_of": {k: (ksw_gops / v if v else None) for k, v in pipes.items()},
+                     "peak_source": "pansvr_int_pipe_peaks measured live on this GPU ('mixed' = IADD3/LOP3/VIMNMX chains; ALU pipe, FMA pipe and both together alongside)",
+                     "traffic": None},
+        "roofline_seed": {"bound": "hbm", "kernel": "seed_count_kernel_probes + seed_fill_kernel (stage B)", "achieved": seed_gbs,
+                          "peak": peaks.get("hbm_gbs"), "unit": "GB/s", "frac": seed_gbs / peaks["hbm_gbs"] if peaks.get("hbm_gbs") else None,
+                          "kernel_ms_per_step": seed_ms / args.steps, "probes_per_step": tot["seed_probes"] / args.steps,
+                          "hits_per_step": hits / args.steps, "bytes_model": f"{SEED_BYTES_MISS} B per miss probe, {SEED_BYTES_HIT} B per hit, both passes (SURVEY.md 8d)",
+                          "peak_source": peak_src, "traffic": None},
         "clocks": clocks,
         "wall_ms_per_step": {"resident": wall_ms / args.steps, "e2e": e_wall_ms / args.steps},
-        "parity_sample_ok": parity,
-        "resident_warps": int(last["resident_warps"]), "tb_bytes_per_warp": int(last["tb_bytes_per_warp"]),
+        "stage_seconds_per_step": {k: v / args.steps for k, v in zip(("A_encode_census", "B_seeding_gpu", "C_merge_chain", "D_plan", "E_ksw_gpu",
+                                                                       "F_replay_text", "fastq_parse", "output_join"), stage_seconds)},
+        "device_busy_ms_per_step": {"seed_kernels": seed_ms / args.steps, "ksw_kernels": ksw_ms / args.steps, "stage_kernels": stage_ms / args.steps},
+        "parity": parity,
     }
+    if emul:
+        line["emulated"] = "PANSVR_BENCH_EMUL dry run on the CPU emulation of tests/emul: NOT a measurement"
+    if ksw_line is not None:
+        line["ksw_config2"] = ksw_line
     if world == 1 and not args.no_cpu_baseline:
-        threads = min(48, os.cpu_count() or 1)
-        rate, kind, secs, ns = cpu_reference_rate(batch, args.cpu_sample, threads)
-        line["cpu_baseline"] = {"value": rate, "unit": "reads/s", "cores": threads, "kind": kind,
-                                "sample": f"first {ns} tasks of the same workload, {secs:.1f} s wall on {threads} threads",
-                                "gcups": rate * CELLS_PER_TASK / 1e9}
+        thr = ref_threads()
+        sample = min(args.ref_sample_pairs, d.n_pairs)
+        t_start = reference_startup(d)
+        t = config3.run_reference_aln(d, thr, max_pairs=sample) - t_start
+        line["cpu_baseline"] = {"value": 2 * sample / max(t, 1e-6), "unit": "reads/s", "cores": thr, "kind": "reference",
+                                "sample": f"`panSVR fc_aln -t {thr} -S -R {sample}` (oracle/_ref) on the first {sample} pairs of the same input: "
+                                          f"{t:.2f} s after subtracting the {t_start:.2f} s start-up (-R 1)"}
     print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()

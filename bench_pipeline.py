@@ -34,7 +34,8 @@ def main():
     ap.add_argument("--out", default="")
     ap.add_argument("--keep", action="store_true")
     a = ap.parse_args()
-    from pansvr_b200 import aln, synth_pipeline as sp
+    from pansvr_b200 import aln
+    from oracle import synth_pipeline as sp
     threads = a.threads or min(48, os.cpu_count() or 1)
     wd = tempfile.mkdtemp(prefix="pansvr_pipe_")
     try:

@@ -116,6 +116,10 @@ int pansvr_ksw_last_stats(const pansvr_ksw_ctx *ctx, pansvr_ksw_stats_t *out);
 /* Measured 32-bit integer-ALU throughput of the device in Gop/s (IADD3/LOP3/VIMNMX chains, no
  * memory): the denominator of the DP kernel's roofline (cells/s x 55 ops per cell). */
 int pansvr_int_alu_peak(pansvr_ksw_ctx *ctx, double *gops);
+/* The same measurement per pipe, so that the yardstick can be read against the hardware: out[0] = the mixed chain above,
+ * out[1] = ALU pipe only (LOP3 / VIMNMX chains), out[2] = FMA pipe only (IMAD chains), out[3] = both pipes fed at once
+ * (independent LOP3 and IMAD chains: the issue limit).  Gop/s, one op = one 32-bit lane operation. */
+int pansvr_int_pipe_peaks(pansvr_ksw_ctx *ctx, double out[4]);
 
 /* In-band DP cells of one task, the work unit GCUPS is quoted in (ksw2_extd2_sse.c:131-138). */
 int64_t pansvr_ksw_band_cells(int32_t qlen, int32_t tlen, int32_t w);
@@ -153,6 +157,11 @@ typedef struct {
 	int64_t reads, mems, ksw_tasks, ksw_cells, deferred_pairs;
 	double stage_seconds[8];    /* A encode/census, B seeding (GPU), C merge/expand/chain, D ksw planning, E ksw (GPU), F replay + SAM text,
 	                               FASTQ parse, output assembly */
+	/* device side, summed over all GPUs of the context since the last reset */
+	int64_t kernel_launches;    /* our kernels launched */
+	int64_t h2d_bytes, d2h_bytes;
+	int64_t seed_probes;        /* k-mer lookups made by the seeding kernels */
+	double seed_kernel_ms, ksw_kernel_ms, stage_kernel_ms;   /* CUDA-event time of the seeding / ksw / other stage kernels */
 } pansvr_aln_stats_t;
 
 typedef struct pansvr_aln_ctx pansvr_aln_ctx;
@@ -183,6 +192,17 @@ int  pansvr_aln_last_stats(const pansvr_aln_ctx *ctx, pansvr_aln_stats_t *out);
 /* Puts the replay back to the state of a freshly started `fc_aln` (rand() streams, counters); the index stays resident. */
 int  pansvr_aln_reset(pansvr_aln_ctx *ctx);
 void pansvr_free(void *p);
+/* ---- one input sharded over several processes / GPUs (reads shard trivially; results are merged by pair index, like the
+ * reference's kt_for fan-out and ordered write, read_realignment.cpp:114,160,165-176).  A process that realigns pairs [b, e) of an
+ * input must see (1) the STAT_ fields of the input's FIRST record, which the reference parses once (read_realignment.cpp:134-148):
+ * pansvr_aln_prime_read_stats with the head of the input; (2) the libc random streams (rand(), random_r()) as the process
+ * handling the pairs before b left them: pansvr_aln_await_state(path) makes the context's first in-order pass wait for the file
+ * `path` and continue from the state in it -- all other stages of its blocks run meanwhile -- and pansvr_aln_publish_state(path)
+ * writes the state after the context's last in-order pass (atomically: readers never see a partial file).  No collective, no
+ * device traffic between processes. */
+int  pansvr_aln_prime_read_stats(pansvr_aln_ctx *ctx, const char *fastq_head, size_t bytes);
+int  pansvr_aln_await_state(pansvr_aln_ctx *ctx, const char *path);
+int  pansvr_aln_publish_state(pansvr_aln_ctx *ctx, const char *path);
 /* Same command line as `panSVR fc_aln` (classify_main, src/main.cpp:18-25): [options] <IndexDir> <reads.fq|-> <header.sam>.
  * Writes BAM, or SAM text with -S, like the reference; -d <gpu> selects the device; -t is the number of host helper threads
  * (the output is that of the reference's `-t 1`, the only deterministic mode). */

@@ -21,7 +21,7 @@ from dataclasses import dataclass
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-REF_BIN = os.path.join(os.path.dirname(HERE), "oracle", "_ref")
+REF_BIN = os.path.join(HERE, "_ref")
 ACGT = np.frombuffer(b"ACGT", dtype=np.uint8)
 COMP = np.zeros(256, dtype=np.uint8)
 COMP[list(b"ACGTN")] = list(b"TGCAN")

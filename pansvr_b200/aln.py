@@ -20,7 +20,9 @@ class AlnOptionsC(C.Structure):
 
 class AlnStatsC(C.Structure):
     _fields_ = [("reads", C.c_int64), ("mems", C.c_int64), ("ksw_tasks", C.c_int64), ("ksw_cells", C.c_int64),
-                ("deferred_pairs", C.c_int64), ("stage_seconds", C.c_double * 8)]
+                ("deferred_pairs", C.c_int64), ("stage_seconds", C.c_double * 8),
+                ("kernel_launches", C.c_int64), ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64), ("seed_probes", C.c_int64),
+                ("seed_kernel_ms", C.c_double), ("ksw_kernel_ms", C.c_double), ("stage_kernel_ms", C.c_double)]
 
 
 def _bind(lib):
@@ -39,6 +41,9 @@ def _bind(lib):
     lib.pansvr_aln_reset.argtypes = [C.c_void_p]
     lib.pansvr_free.argtypes = [C.c_void_p]
     lib.pansvr_fc_aln_main.argtypes = [C.c_int, C.POINTER(C.c_char_p)]
+    lib.pansvr_aln_prime_read_stats.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t]
+    lib.pansvr_aln_await_state.argtypes = [C.c_void_p, C.c_char_p]
+    lib.pansvr_aln_publish_state.argtypes = [C.c_void_p, C.c_char_p]
     return lib
 
 
@@ -82,6 +87,36 @@ class AlnContext:
             self.lib.pansvr_free(s); self.lib.pansvr_free(o)
         return sam, ori, release
 
+    def align_ptr(self, addr: int, nbytes: int):
+        """pansvr_aln_block on a raw host buffer (e.g. pinned memory): returns ((sam_addr, sam_bytes), (ori_addr, ori_bytes), release)."""
+        s, o = C.c_void_p(), C.c_void_p()
+        sl, ol = C.c_size_t(), C.c_size_t()
+        rc = self.lib.pansvr_aln_block(self.h, C.cast(C.c_void_p(addr), C.c_char_p), nbytes, C.byref(s), C.byref(sl), C.byref(o), C.byref(ol))
+        if rc != 0:
+            raise RuntimeError(f"pansvr_aln_block failed ({rc}): {self.lib.pansvr_aln_last_error().decode()}")
+
+        def release():
+            self.lib.pansvr_free(s); self.lib.pansvr_free(o)
+        return (s.value, sl.value), (o.value, ol.value), release
+
+    def align_bytes_at(self, fastq: bytes, offset: int, nbytes: int):
+        """pansvr_aln_block on fastq[offset : offset + nbytes] without slicing (no copy); same returns as align_ptr."""
+        base = C.cast(C.c_char_p(fastq), C.c_void_p).value
+        return self.align_ptr(base + offset, nbytes)
+
+    def prime_read_stats(self, fastq_head: bytes) -> None:
+        """Show the context the first record of the whole input (STAT_ fields); needed when its own blocks start later in the input."""
+        if self.lib.pansvr_aln_prime_read_stats(self.h, fastq_head, len(fastq_head)) != 0:
+            raise RuntimeError(self.lib.pansvr_aln_last_error().decode())
+
+    def await_state(self, path: str) -> None:
+        if self.lib.pansvr_aln_await_state(self.h, path.encode()) != 0:
+            raise RuntimeError(self.lib.pansvr_aln_last_error().decode())
+
+    def publish_state(self, path: str) -> None:
+        if self.lib.pansvr_aln_publish_state(self.h, path.encode()) != 0:
+            raise RuntimeError(self.lib.pansvr_aln_last_error().decode())
+
     def align_fastq_bam(self, fastq: bytes):
         """Like align_fastq, records in uncompressed BAM form (what htslib's bam_write1 hands to BGZF)."""
         s, o = C.c_void_p(), C.c_void_p()
@@ -113,7 +148,8 @@ class AlnContext:
     def stats(self) -> dict:
         st = AlnStatsC()
         self.lib.pansvr_aln_last_stats(self.h, C.byref(st))
-        d = {k: getattr(st, k) for k in ("reads", "mems", "ksw_tasks", "ksw_cells", "deferred_pairs")}
+        d = {k: getattr(st, k) for k in ("reads", "mems", "ksw_tasks", "ksw_cells", "deferred_pairs", "kernel_launches", "h2d_bytes",
+                                         "d2h_bytes", "seed_probes", "seed_kernel_ms", "ksw_kernel_ms", "stage_kernel_ms")}
         d["stage_seconds"] = list(st.stage_seconds)
         return d
 

@@ -261,12 +261,15 @@ int run_block(pansvr_aln_ctx *c, const char *fastq, size_t n, std::vector<const 
 	};
 	if (n_sub == 1) run_sub(0);
 	else {
+		// two in flight; all of them while the context waits for another process's stream state (pansvr_aln_await_state), so that
+		// only the in-order passes wait and every other stage of the shard is done by the time the state arrives
+		const size_t flight = c->pipe->awaiting_streams() ? n_sub : 2;
 		std::vector<std::thread> th(n_sub);
 		for (size_t k = 0; k < n_sub; ++k) {
-			if (k >= 2) th[k - 2].join();                       // two in flight
+			if (k >= flight) th[k - flight].join();
 			th[k] = std::thread(run_sub, k);
 		}
-		for (size_t k = n_sub >= 2 ? n_sub - 2 : 0; k < n_sub; ++k) th[k].join();
+		for (size_t k = n_sub >= flight ? n_sub - flight : 0; k < n_sub; ++k) th[k].join();
 	}
 	for (size_t k = 0; k < n_sub; ++k) if (!ok[k]) { g_aln_err = errs[k]; return PANSVR_E_CUDA; }
 	sam.clear(); ori.clear();
@@ -410,10 +413,40 @@ int pansvr_aln_last_stats(const pansvr_aln_ctx *c, pansvr_aln_stats_t *out)
 	out->reads = (int64_t)s.reads; out->mems = (int64_t)s.mems; out->ksw_tasks = (int64_t)s.ksw_tasks; out->ksw_cells = (int64_t)s.ksw_cells;
 	out->deferred_pairs = (int64_t)s.deferred_pairs;
 	for (int i = 0; i < 8; ++i) out->stage_seconds[i] = s.t_stage[i];
+	out->kernel_launches = s.dev.launches; out->h2d_bytes = s.dev.h2d_bytes; out->d2h_bytes = s.dev.d2h_bytes;
+	out->seed_probes = s.dev.seed_probes;
+	out->seed_kernel_ms = s.dev.seed_kernel_ms; out->ksw_kernel_ms = s.dev.ksw_kernel_ms; out->stage_kernel_ms = s.dev.stage_kernel_ms;
 	return 0;
 }
 
 void pansvr_free(void *p) { free(p); }
+
+int pansvr_aln_prime_read_stats(pansvr_aln_ctx *c, const char *fastq_head, size_t n)
+{
+	if (!c || !fastq_head) return PANSVR_E_ARG;
+	std::vector<FastqRec> recs;
+	const char *nl = fastq_head;
+	int lines = 0;
+	for (size_t i = 0; i < n && lines < 4; ++i) if (fastq_head[i] == '\n') { ++lines; nl = fastq_head + i + 1; }
+	parse_fastq(fastq_head, lines == 4 ? (size_t)(nl - fastq_head) : n, recs);
+	if (recs.empty()) { g_aln_err = "no FASTQ record in the given text"; return PANSVR_E_ARG; }
+	c->pipe->ensure_read_stats(recs[0]);
+	return 0;
+}
+
+int pansvr_aln_await_state(pansvr_aln_ctx *c, const char *path)
+{
+	if (!c || !path || !*path) return PANSVR_E_ARG;
+	c->pipe->await_streams(path);
+	return 0;
+}
+
+int pansvr_aln_publish_state(pansvr_aln_ctx *c, const char *path)
+{
+	if (!c || !path || !*path) return PANSVR_E_ARG;
+	if (!c->pipe->publish_streams(path)) { g_aln_err = std::string("cannot write ") + path; return PANSVR_E_ARG; }
+	return 0;
+}
 
 int pansvr_aln_reset(pansvr_aln_ctx *c)
 {

@@ -1118,9 +1118,36 @@ void AlnPipeline::ensure_read_stats(const FastqRec &first)
 	opt.stat_set = true;
 }
 
+AlnPipeline::StreamState AlnPipeline::export_streams()
+{
+	std::unique_lock<std::mutex> lk(turn_m_);
+	turn_cv_.wait(lk, [&]() { return replay_turn_ == seq_issued_; });
+	StreamState s;
+	memset(&s, 0, sizeof s);
+	s.magic = 0x70535652u;
+	s.rand = rand_; s.rand_r[0] = rand_r_[0]; s.rand_r[1] = rand_r_[1];
+	return s;
+}
+
+void AlnPipeline::import_streams(const StreamState &s) { rand_ = s.rand; rand_r_[0] = s.rand_r[0]; rand_r_[1] = s.rand_r[1]; }
+
+void AlnPipeline::await_streams(const std::string &path) { std::lock_guard<std::mutex> lk(turn_m_); await_path_ = path; }
+
+bool AlnPipeline::publish_streams(const std::string &path)
+{
+	const StreamState s = export_streams();
+	const std::string tmp = path + ".part";
+	FILE *f = fopen(tmp.c_str(), "wb");
+	if (!f) return false;
+	const bool ok = fwrite(&s, sizeof s, 1, f) == 1;
+	if (fclose(f) != 0 || !ok) { remove(tmp.c_str()); return false; }
+	return rename(tmp.c_str(), path.c_str()) == 0;
+}
+
 void AlnPipeline::reset()
 {
 	replay_turn_ = 0; seq_issued_ = 0;
+	await_path_.clear();
 	bad_cigar_records_ = 0;
 	rand_.reseed(1);
 	stats = Stats();
@@ -1134,7 +1161,25 @@ bool AlnPipeline::align_block(const FastqRec *recs, size_t n_reads_in, BlockOutp
 	Impl I(*this);
 	const size_t n_reads = n_reads_in & ~(size_t)1, n_pairs = n_reads / 2;
 	// in-order sections: wait until every earlier block has finished its replay; leave by passing the turn on
-	auto wait_turn = [&]() { std::unique_lock<std::mutex> lk(turn_m_); turn_cv_.wait(lk, [&]() { return replay_turn_ == seq; }); };
+	auto wait_turn = [&]() {
+		std::unique_lock<std::mutex> lk(turn_m_);
+		turn_cv_.wait(lk, [&]() { return replay_turn_ == seq; });
+		if (await_path_.empty()) return;
+		// this process continues another one's input (await_streams): take the random streams where that one left them
+		const std::string path = await_path_;
+		await_path_.clear();
+		lk.unlock();
+		for (uint64_t spins = 0;; ++spins) {
+			if (spins == 6000000) { fprintf(stderr, "pansvr_b200: still no stream state at %s after 10 minutes (did the process before this one fail?)\n", path.c_str()); abort(); }
+			if (FILE *f = fopen(path.c_str(), "rb")) {
+				StreamState s;
+				const bool ok = fread(&s, sizeof s, 1, f) == 1 && s.magic == 0x70535652u;
+				fclose(f);
+				if (ok) { import_streams(s); remove(path.c_str()); return; }
+			}
+			std::this_thread::sleep_for(std::chrono::microseconds(100));
+		}
+	};
 	struct TurnGuard {                                                    // whatever happens, the next block must not wait for ever
 		AlnPipeline &P; uint64_t seq; bool passed = false;
 		void pass() { if (passed) return; passed = true; { std::lock_guard<std::mutex> lk(P.turn_m_); if (P.replay_turn_ == seq) P.replay_turn_ = seq + 1; } P.turn_cv_.notify_all(); }
@@ -1295,7 +1340,7 @@ bool AlnPipeline::align_block(const FastqRec *recs, size_t n_reads_in, BlockOutp
 		std::lock_guard<std::mutex> dev(dev_m_);
 		if (!sb.jobs.empty() && !seed_service_run(seeds_, sb, err)) return false;
 	}
-	{ std::lock_guard<std::mutex> lk(stats_m_); stats.mems += sb.mems.size(); }
+	{ std::lock_guard<std::mutex> lk(stats_m_); stats.mems += sb.mems.size(); stats.dev.add(sb.dev); sb.dev = DevCounters(); }
 	add_time(1, now() - t0); t0 = now();
 	// ---- stage C: reads whose expansion draws from the per-handler random_r stream go in input order, the rest in parallel
 	par_all([&](size_t b, size_t e, int) {
@@ -1409,6 +1454,12 @@ bool AlnPipeline::align_block(const FastqRec *recs, size_t n_reads_in, BlockOutp
 			std::unique_lock<std::mutex> dev(dev_m_);
 			const int rc = pansvr_ksw_extd2_batch((pansvr_ksw_ctx*)ksw_, (int64_t)n, q, (int64_t)q_bytes, qoff, qlen, t, (int64_t)t_bytes, toff, tlen, &kp, res, cig, cap);
 			if (rc != 0) { err = std::string("ksw batch: ") + pansvr_last_error(); return false; }
+			pansvr_ksw_stats_t ks;
+			if (pansvr_ksw_last_stats((pansvr_ksw_ctx*)ksw_, &ks) == 0) {
+				std::lock_guard<std::mutex> lk(stats_m_);
+				stats.dev.launches += ks.kernel_launches; stats.dev.h2d_bytes += ks.h2d_bytes; stats.dev.d2h_bytes += ks.d2h_bytes;
+				stats.dev.ksw_kernel_ms += ks.kernel_ms;
+			}
 			dev.unlock();
 			std::atomic<int> need(0);
 			std::atomic<uint64_t> cells(0);
@@ -1536,6 +1587,7 @@ bool AlnPipeline::align_block(const FastqRec *recs, size_t n_reads_in, BlockOutp
 						if (!seed_service_run(seeds_, one, err)) return false;
 					}
 					n_mems_late += one.mems.size();
+					{ std::lock_guard<std::mutex> lk(stats_m_); stats.dev.add(one.dev); one.dev = DevCounters(); }
 					merge_read(r, one);
 					chain_read(r, 2 * pi + k, edges_main);
 					I.plan_read(r, local, plan_main);

@@ -96,6 +96,17 @@ private:
 	size_t n_ = 0, cap_ = 0;
 };
 
+struct DevCounters {                  // what the device services did for a block (bench.py: gpu_launches, e2e bytes, rooflines)
+	int64_t launches = 0, h2d_bytes = 0, d2h_bytes = 0;
+	int64_t seed_probes = 0;          // k-mer lookups of the seeding kernels (fill pass; the count pass repeats them)
+	double seed_kernel_ms = 0, ksw_kernel_ms = 0, stage_kernel_ms = 0;   // CUDA-event time of our kernels on their streams
+	void add(const DevCounters &o)
+	{
+		launches += o.launches; h2d_bytes += o.h2d_bytes; d2h_bytes += o.d2h_bytes; seed_probes += o.seed_probes;
+		seed_kernel_ms += o.seed_kernel_ms; ksw_kernel_ms += o.ksw_kernel_ms; stage_kernel_ms += o.stage_kernel_ms;
+	}
+};
+
 struct SeedJob {                      // one read strand
 	uint32_t bits_off, read_len;      // word offset into SeedBatch::bits
 	uint32_t list_off;                // offset into SeedBatch::seed_list (STR reads only)
@@ -107,6 +118,7 @@ struct SeedBatch {
 	HostVec<SeedJob> jobs;
 	HostVec<Mem> mems;                // out: MEMs of job i are mems[mem_off[i] .. mem_off[i+1])
 	HostVec<uint32_t> mem_off;
+	DevCounters dev;                  // out: added to by seed_service_run
 	void clear() { bits.clear(); seed_list.clear(); jobs.clear(); mems.clear(); mem_off.clear(); }
 };
 struct KswBatchBuf {                  // the ksw tasks of one block, joined (stage D -> E -> F)
@@ -146,8 +158,17 @@ public:
 	std::atomic<uint64_t> bad_cigar_records_{0};   // records left out because their CIGAR does not span the read (see output_bam)
 	void ensure_read_stats(const FastqRec &first);   // STAT_ fields of the input's first comment; call before overlapping blocks
 	void reset();                     // back to the state of a freshly started `fc_aln` (rand() streams, counters)
+	// ---- one input sharded over several processes: the only state that flows from pair to pair are the libc
+	// random streams the replay consumes in input order.  A process that handles pairs [b, e) of the input takes the streams as the
+	// process before it left them and hands them on when its own in-order passes are done; everything else runs without waiting.
+	struct StreamState { uint32_t magic; GlibcRandom rand, rand_r[2]; };
+	StreamState export_streams();                       // waits for every block issued so far to finish its in-order pass
+	void import_streams(const StreamState &s);           // before any block since the last reset
+	void await_streams(const std::string &path);         // the first in-order section from now on waits for `path` and imports it
+	bool publish_streams(const std::string &path);       // export_streams() into `path` (written beside it and renamed: readers never see a part)
+	bool awaiting_streams() { std::lock_guard<std::mutex> lk(turn_m_); return !await_path_.empty(); }
 	struct Stats { uint64_t reads = 0, probes_reads = 0, mems = 0, ksw_tasks = 0, ksw_cells = 0, deferred_pairs = 0;
-	               double t_stage[8] = {0, 0, 0, 0, 0, 0, 0, 0}; } stats;   // A..F, FASTQ parse, output assembly
+	               double t_stage[8] = {0, 0, 0, 0, 0, 0, 0, 0}; DevCounters dev; } stats;   // A..F, FASTQ parse, output assembly
 	AlnOptions opt;                   // stat_set / read_len / isize_* are filled from the first comment
 private:
 	struct Impl;
@@ -166,6 +187,7 @@ private:
 	GlibcRandom rand_;                // the process-global rand() of the reference
 	GlibcRandom rand_r_[2];           // per-handler random_r states (RRH:339-340), seeded from rand_ at start-up
 	int min_filter_score_ = 0;
+	std::string await_path_;              // guarded by turn_m_
 	friend struct Impl;
 };
 

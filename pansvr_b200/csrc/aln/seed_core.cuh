@@ -186,17 +186,20 @@ SEED_HD void unitig_mem(const IndexView &ix, uint64_t kmer_index, const uint64_t
 }
 
 // All MEMs of one read strand, in the reference's order.  seed_list (only read when is_str) marks the seed
-// positions an STR read may use.  Returns the number of MEMs found; only the first `cap` are stored.
+// positions an STR read may use.  Returns the number of MEMs found; only the first `cap` are stored.  *n_probes (optional)
+// receives the number of k-mer lookups made (the unit of the seeding roofline).
 SEED_HD int seed_read_strand(const IndexView &ix, const uint64_t *read_bit, uint32_t read_l, bool is_str, const uint8_t *seed_list,
-                             Mem *out, int cap)
+                             Mem *out, int cap, uint32_t *n_probes = nullptr)
 {
 	int n = 0;
+	uint32_t probes = 0;
 	const uint32_t kmer_number = read_l - LEN_KMER + 1;
 	uint32_t max_search_right = 0;
 	for (uint32_t read_off = 0; read_off < kmer_number; read_off += SEED_STEP) {
 		if (read_off + LEN_KMER - 1 <= max_search_right) continue;          // still inside the last MEM
 		if (is_str && seed_list[read_off] == 0) continue;
 		int64_t range[2];
+		++probes;
 		if (!search_kmer(ix, get_kmer(read_off, read_bit), range)) continue;
 		if ((uint64_t)(range[1] - range[0] + 1) > UNI_POS_N_MAX) continue;
 		uint32_t max_right_i = 1;
@@ -208,6 +211,7 @@ SEED_HD int seed_read_strand(const IndexView &ix, const uint64_t *read_bit, uint
 		}
 		max_search_right = read_off + LEN_KMER + max_right_i - 1;
 	}
+	if (n_probes) *n_probes = probes;
 	return n;
 }
 

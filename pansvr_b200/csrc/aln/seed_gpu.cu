@@ -18,14 +18,6 @@ namespace {
 
 #define SCU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { err = std::string(#call) + ": " + cudaGetErrorString(e_); return false; } } while (0)
 
-__global__ void seed_count_kernel(IndexView ix, const uint64_t *bits, const uint8_t *seed_list, const SeedJob *jobs, int n, uint32_t *count)
-{
-	const int i = blockIdx.x * blockDim.x + threadIdx.x;
-	if (i >= n) return;
-	const SeedJob j = jobs[i];
-	count[i] = (uint32_t)seed_read_strand(ix, bits + j.bits_off, j.read_len, j.is_str != 0, seed_list + j.list_off, (Mem*)nullptr, 0);
-}
-
 __global__ void seed_fill_kernel(IndexView ix, const uint64_t *bits, const uint8_t *seed_list, const SeedJob *jobs, int n,
                                  const uint32_t *off, Mem *mems)
 {
@@ -34,6 +26,20 @@ __global__ void seed_fill_kernel(IndexView ix, const uint64_t *bits, const uint8
 	const SeedJob j = jobs[i];
 	const int cap = (int)(off[i + 1] - off[i]);
 	if (cap > 0) seed_read_strand(ix, bits + j.bits_off, j.read_len, j.is_str != 0, seed_list + j.list_off, mems + off[i], cap);
+}
+
+// number of k-mer lookups of the batch (the work unit of the seeding roofline): warp-aggregated
+__global__ void seed_count_kernel_probes(IndexView ix, const uint64_t *bits, const uint8_t *seed_list, const SeedJob *jobs, int n, uint32_t *count,
+                                         unsigned long long *probes)
+{
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	uint32_t p = 0;
+	if (i < n) {
+		const SeedJob j = jobs[i];
+		count[i] = (uint32_t)seed_read_strand(ix, bits + j.bits_off, j.read_len, j.is_str != 0, seed_list + j.list_off, (Mem*)nullptr, 0, &p);
+	}
+	for (int o = 16; o > 0; o >>= 1) p += __shfl_down_sync(0xffffffffu, p, o);
+	if ((threadIdx.x & 31) == 0 && p) atomicAdd(probes, (unsigned long long)p);
 }
 
 struct Buf {
@@ -74,6 +80,8 @@ void staging_free(void *p) { if (p) cudaFreeHost(p); }
 struct SeedService {
 	int device = 0;
 	cudaStream_t stream = nullptr;
+	cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+	unsigned long long *d_probes = nullptr;
 	uint64_t *seqb = nullptr, *seqf = nullptr, *posp = nullptr, *bkt_start = nullptr, *off_g = nullptr;
 	uint32_t *kmer_g = nullptr, *bkt_dir = nullptr, *bkt_key = nullptr;
 	IndexView view;
@@ -94,6 +102,8 @@ SeedService *seed_service_create(const DebgaIndex &idx, int device, std::string 
 	s->device = device;
 	auto fail = [&]() -> SeedService* { seed_service_destroy(s); return nullptr; };
 	if (cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking) != cudaSuccess) { err = "cudaStreamCreate failed"; return fail(); }
+	for (cudaEvent_t &e : s->ev) if (cudaEventCreate(&e) != cudaSuccess) { err = "cudaEventCreate failed"; return fail(); }
+	if (cudaMalloc((void**)&s->d_probes, 8) != cudaSuccess) { err = "cudaMalloc failed"; return fail(); }
 	if (!upload(idx.seqb, s->seqb, err) || !upload(idx.seqf, s->seqf, err) || !upload(idx.posp, s->posp, err) ||
 	    !upload(idx.bkt_dir, s->bkt_dir, err) || !upload(idx.bkt_key, s->bkt_key, err) || !upload(idx.bkt_start, s->bkt_start, err) ||
 	    !upload(idx.off_g, s->off_g, err) || !upload(idx.kmer_g, s->kmer_g, err)) return fail();
@@ -110,6 +120,8 @@ void seed_service_destroy(SeedService *s)
 	if (!s) return;
 	cudaSetDevice(s->device);
 	for (void *p : {(void*)s->seqb, (void*)s->seqf, (void*)s->posp, (void*)s->bkt_dir, (void*)s->bkt_key, (void*)s->bkt_start, (void*)s->off_g, (void*)s->kmer_g}) if (p) cudaFree(p);
+	for (cudaEvent_t e : s->ev) if (e) cudaEventDestroy(e);
+	if (s->d_probes) cudaFree(s->d_probes);
 	if (s->stream) cudaStreamDestroy(s->stream);
 	delete s;
 }
@@ -129,25 +141,44 @@ bool seed_service_run(SeedService *s, SeedBatch &b, std::string &err)
 	if (!b.seed_list.empty()) SCU(cudaMemcpyAsync(s->list.p, b.seed_list.data(), b.seed_list.size(), cudaMemcpyHostToDevice, st));
 	SCU(cudaMemcpyAsync(s->jobs.p, b.jobs.data(), (size_t)n * sizeof(SeedJob), cudaMemcpyHostToDevice, st));
 	SCU(cudaMemsetAsync(s->count.p, 0, ((size_t)n + 1) * 4, st));
+	SCU(cudaMemsetAsync(s->d_probes, 0, 8, st));
 	const int threads = 128, blocks = (n + threads - 1) / threads;
-	seed_count_kernel<<<blocks, threads, 0, st>>>(s->view, (const uint64_t*)s->bits.p, (const uint8_t*)s->list.p, (const SeedJob*)s->jobs.p, n,
-	                                              (uint32_t*)s->count.p);
+	SCU(cudaEventRecord(s->ev[0], st));
+	seed_count_kernel_probes<<<blocks, threads, 0, st>>>(s->view, (const uint64_t*)s->bits.p, (const uint8_t*)s->list.p, (const SeedJob*)s->jobs.p, n,
+	                                                     (uint32_t*)s->count.p, s->d_probes);
 	SCU(cudaGetLastError());
+	SCU(cudaEventRecord(s->ev[1], st));
+	unsigned long long probes = 0;
+	SCU(cudaMemcpyAsync(&probes, s->d_probes, 8, cudaMemcpyDeviceToHost, st));
+	b.dev.launches += 1;
+	b.dev.h2d_bytes += (int64_t)(b.bits.size() * 8 + b.seed_list.size() + (size_t)n * sizeof(SeedJob));
 	size_t tmp_bytes = 0;
 	SCU(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, (const uint32_t*)s->count.p, (uint32_t*)s->off.p, n + 1, st));
 	if (!s->tmp.reserve(tmp_bytes, err)) return false;
 	SCU(cub::DeviceScan::ExclusiveSum(s->tmp.p, tmp_bytes, (const uint32_t*)s->count.p, (uint32_t*)s->off.p, n + 1, st));
 	SCU(cudaMemcpyAsync(b.mem_off.data(), s->off.p, ((size_t)n + 1) * 4, cudaMemcpyDeviceToHost, st));
 	SCU(cudaStreamSynchronize(st));
+	{
+		float ms = 0;
+		SCU(cudaEventElapsedTime(&ms, s->ev[0], s->ev[1]));
+		b.dev.seed_kernel_ms += ms; b.dev.seed_probes += (int64_t)probes; b.dev.d2h_bytes += (int64_t)((size_t)n + 1) * 4 + 8;
+	}
 	const size_t total = b.mem_off[n];
 	b.mems.resize(total);
 	if (total == 0) return true;
 	if (!s->mems.reserve(total * sizeof(Mem), err)) return false;
+	SCU(cudaEventRecord(s->ev[2], st));
 	seed_fill_kernel<<<blocks, threads, 0, st>>>(s->view, (const uint64_t*)s->bits.p, (const uint8_t*)s->list.p, (const SeedJob*)s->jobs.p, n,
 	                                             (const uint32_t*)s->off.p, (Mem*)s->mems.p);
 	SCU(cudaGetLastError());
+	SCU(cudaEventRecord(s->ev[3], st));
 	SCU(cudaMemcpyAsync(b.mems.data(), s->mems.p, total * sizeof(Mem), cudaMemcpyDeviceToHost, st));
 	SCU(cudaStreamSynchronize(st));
+	{
+		float ms = 0;
+		SCU(cudaEventElapsedTime(&ms, s->ev[2], s->ev[3]));
+		b.dev.seed_kernel_ms += ms; b.dev.launches += 1; b.dev.d2h_bytes += (int64_t)(total * sizeof(Mem));
+	}
 	return true;
 }
 

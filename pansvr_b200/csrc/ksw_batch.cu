@@ -109,6 +109,39 @@ __global__ void __launch_bounds__(256) int_alu_peak_kernel(uint32_t *out, int it
 	if (r == 0x12345678u) out[blockIdx.x * blockDim.x + threadIdx.x] = r;   // keeps the chains alive
 }
 
+// The same per pipe (the mixed chain above is a compiler-chosen blend of both integer pipes).
+// MODE 1: LOP3 + VIMNMX only (ALU pipe).  MODE 2: IMAD only (FMA pipe; the multiplier is opaque so that the adds stay IMAD).
+// MODE 3: eight LOP3/VIMNMX chains and eight IMAD chains side by side (both pipes, the issue limit).
+template <int MODE>
+__global__ void __launch_bounds__(256) int_pipe_peak_kernel(uint32_t *out, int iters, uint32_t seed, uint32_t one)
+{
+	uint32_t a[16];
+#pragma unroll
+	for (int k = 0; k < 16; ++k) a[k] = seed * (threadIdx.x + 1) + k * 0x9e3779b9u;
+	const uint32_t c1 = seed | 1u, c2 = seed ^ 0x5bd1e995u;
+	for (int it = 0; it < iters; ++it) {
+#pragma unroll
+		for (int k = 0; k < 16; ++k) {
+			const bool alu = MODE == 1 || (MODE == 3 && (k & 1));
+			if (alu) {
+				a[k] = (a[k] ^ c2) & ~c1;                             // LOP3
+				a[k] = (uint32_t)max((int)a[k], (int)c2);             // VIMNMX.S32
+				a[k] = (a[k] | c1) ^ (uint32_t)it;                    // LOP3
+				a[k] = (uint32_t)min((int)a[k], (int)c1);             // VIMNMX.S32
+			} else {
+				a[k] = a[k] * one + c1;                               // IMAD
+				a[k] = a[k] * one + c2;
+				a[k] = a[k] * one + (uint32_t)it;
+				a[k] = a[k] * one + c1;
+			}
+		}
+	}
+	uint32_t r = 0;
+#pragma unroll
+	for (int k = 0; k < 16; ++k) r ^= a[k];
+	if (r == 0x12345678u) out[blockIdx.x * blockDim.x + threadIdx.x] = r;
+}
+
 struct DevBuf {
 	void *p = nullptr; size_t cap = 0;
 	cudaError_t reserve(size_t bytes)
@@ -470,6 +503,33 @@ int pansvr_int_alu_peak(pansvr_ksw_ctx *ctx, double *gops)
 		if (rep > 0 && g > best) best = g;
 	}
 	*gops = best;
+	return 0;
+}
+
+int pansvr_int_pipe_peaks(pansvr_ksw_ctx *ctx, double out[4])
+{
+	if (!ctx || !out) return fail(PANSVR_E_ARG, "bad argument");
+	int rc = pansvr_int_alu_peak(ctx, &out[0]);
+	if (rc) return rc;
+	const int iters = 4096, grid = ctx->sm_count * 8, ops_per_iter = 16 * 4;
+	for (int mode = 1; mode <= 3; ++mode) {
+		double best = 0;
+		for (int rep = 0; rep < 4; ++rep) {
+			CU(cudaEventRecord(ctx->ev[0], ctx->stream));
+			const uint32_t seed = 0x2545f491u + rep, one = (uint32_t)(rep >= 0);
+			if (mode == 1) int_pipe_peak_kernel<1><<<grid, 256, 0, ctx->stream>>>((uint32_t*)ctx->counters.p, iters, seed, one);
+			else if (mode == 2) int_pipe_peak_kernel<2><<<grid, 256, 0, ctx->stream>>>((uint32_t*)ctx->counters.p, iters, seed, one);
+			else int_pipe_peak_kernel<3><<<grid, 256, 0, ctx->stream>>>((uint32_t*)ctx->counters.p, iters, seed, one);
+			CU(cudaGetLastError());
+			CU(cudaEventRecord(ctx->ev[3], ctx->stream));
+			CU(cudaStreamSynchronize(ctx->stream));
+			float ms = 0;
+			CU(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[3]));
+			const double g = (double)grid * 256 * iters * ops_per_iter / (ms * 1e-3) * 1e-9;
+			if (rep > 0 && g > best) best = g;
+		}
+		out[mode] = best;
+	}
 	return 0;
 }
 

@@ -21,9 +21,10 @@ RES_WORDS = 12
 RES_COLS = ("max", "zdropped", "max_q", "max_t", "mqe", "mqe_t", "mte", "mte_q", "score", "n_cigar", "reach_end", "status")
 EXPORTS = ("pansvr_ksw_create", "pansvr_ksw_destroy", "pansvr_last_error", "pansvr_host_alloc", "pansvr_host_free",
            "pansvr_ksw_extd2_batch", "pansvr_ksw_extd2_batch_device", "pansvr_ksw_last_stats", "pansvr_ksw_band_cells",
-           "pansvr_ksw_extd2", "ksw_extd2_sse", "pansvr_int_alu_peak",
+           "pansvr_ksw_extd2", "ksw_extd2_sse", "pansvr_int_alu_peak", "pansvr_int_pipe_peaks",
            "pansvr_aln_create", "pansvr_aln_destroy", "pansvr_aln_header_text", "pansvr_aln_last_error", "pansvr_aln_block",
-           "pansvr_aln_block_bam", "pansvr_bam_open", "pansvr_bam_write", "pansvr_bam_close", "pansvr_aln_last_stats", "pansvr_aln_reset", "pansvr_free", "pansvr_fc_aln_main")
+           "pansvr_aln_block_bam", "pansvr_bam_open", "pansvr_bam_write", "pansvr_bam_close", "pansvr_aln_last_stats", "pansvr_aln_reset", "pansvr_free", "pansvr_fc_aln_main",
+           "pansvr_aln_prime_read_stats", "pansvr_aln_await_state", "pansvr_aln_publish_state")
 
 
 class KswParamsC(C.Structure):
@@ -71,6 +72,7 @@ def load_library():
                                                   C.c_void_p, C.c_void_p, C.c_int32]
     lib.pansvr_ksw_last_stats.argtypes = [C.c_void_p, C.POINTER(KswStatsC)]
     lib.pansvr_int_alu_peak.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
+    lib.pansvr_int_pipe_peaks.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
     lib.pansvr_ksw_band_cells.restype = C.c_int64
     lib.pansvr_ksw_band_cells.argtypes = [C.c_int32, C.c_int32, C.c_int32]
     sse_args = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int8, C.c_void_p, C.c_int8, C.c_int8, C.c_int8,
@@ -145,6 +147,12 @@ class KswContext:
         g = C.c_double()
         _check(self.lib, self.lib.pansvr_int_alu_peak(self.h, C.byref(g)), "pansvr_int_alu_peak")
         return g.value
+
+    def int_pipe_peaks_gops(self) -> dict:
+        """Integer throughput per pipe (Gop/s): the mixed yardstick, ALU pipe only, FMA pipe only, both pipes at once."""
+        g = (C.c_double * 4)()
+        _check(self.lib, self.lib.pansvr_int_pipe_peaks(self.h, g), "pansvr_int_pipe_peaks")
+        return {"mixed": g[0], "alu_pipe": g[1], "fma_pipe": g[2], "both_pipes": g[3]}
 
     def extd2_batch(self, b: KswBatch, cigar_cap: int = 64, out=None):
         """Host buffers in, host buffers out: results[n,12] int32, cigar[n,cigar_cap] uint32."""

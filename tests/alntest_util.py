@@ -6,7 +6,7 @@ import tempfile
 
 import pytest
 
-from pansvr_b200 import synth_pipeline as sp
+from oracle import synth_pipeline as sp
 
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 

@@ -67,6 +67,7 @@ extern "C" {
 const char *pansvr_last_error(void) { return g_err.c_str(); }
 int pansvr_ksw_create(int, pansvr_ksw_ctx **out) { *out = (pansvr_ksw_ctx*)1; return load_oracle() ? 0 : PANSVR_E_CUDA; }
 void pansvr_ksw_destroy(pansvr_ksw_ctx*) {}
+int pansvr_ksw_last_stats(const pansvr_ksw_ctx*, pansvr_ksw_stats_t *out) { memset(out, 0, sizeof *out); return 0; }
 int64_t pansvr_ksw_band_cells(int32_t q, int32_t t, int32_t w) { return load_oracle() ? g_cells(q, t, w) : 0; }
 int pansvr_ksw_extd2_batch(pansvr_ksw_ctx*, int64_t n, const uint8_t *qseq, int64_t, const int64_t *qoff, const int32_t *qlen, const uint8_t *tseq,
                            int64_t, const int64_t *toff, const int32_t *tlen, const pansvr_ksw_params_t *p, int32_t *res, uint32_t *cig, int32_t cap)

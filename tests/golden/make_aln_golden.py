@@ -1,5 +1,5 @@
 """Generates tests/golden/aln_demo.sam.gz / aln_demo_ori.sam.gz: the REFERENCE's own `panSVR fc_aln -t 1 -S` output on the
-seeded synthetic demo (pansvr_b200/synth_pipeline.make_demo defaults).  Needs oracle/_ref/panSVR and
+seeded synthetic demo (oracle/synth_pipeline.make_demo defaults).  Needs oracle/_ref/panSVR and
 oracle/_ref/deBGA (oracle/build_ref_pipeline.sh, build container only).  The inputs are regenerated from the seed by the
 tests; only the reference's output is stored."""
 import gzip
@@ -10,7 +10,7 @@ import tempfile
 
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
-from pansvr_b200 import synth_pipeline as sp  # noqa: E402
+from oracle import synth_pipeline as sp  # noqa: E402
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 

@@ -12,7 +12,8 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from pansvr_b200 import aln, synth_pipeline as sp  # noqa: E402
+from pansvr_b200 import aln
+from oracle import synth_pipeline as sp  # noqa: E402
 
 
 def main():

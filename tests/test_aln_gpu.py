@@ -5,7 +5,8 @@ import os
 
 import pytest
 
-from pansvr_b200 import aln, synth_pipeline as sp
+from pansvr_b200 import aln
+from oracle import synth_pipeline as sp
 from tests.alntest_util import DATASETS, get_demo, first_diff, golden, need_ref_tools, read
 
 pytestmark = pytest.mark.gpu

@@ -8,7 +8,7 @@ import subprocess
 
 import pytest
 
-from pansvr_b200 import synth_pipeline as sp
+from oracle import synth_pipeline as sp
 from tests.alntest_util import DATASETS, get_demo, first_diff, golden, need_ref_tools, read
 
 HERE = os.path.dirname(os.path.abspath(__file__))

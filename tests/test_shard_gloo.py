@@ -64,12 +64,83 @@ def test_two_ranks_gloo_max_and_ranges(tmp_path):
     assert abs(line["rate"] - 2 * 1000 * 5 / 15e-3) < 1e-6
 
 
-def test_reference_arm_two_ranks_prints_once():
-    """bench.py --impl reference under torchrun: rank 0 alone runs the CPU arm and prints one JSON line, rank 1 exits 0."""
-    p = _torchrun(["bench.py", "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0", "--ref-sample", "3000"])
+def test_reference_arm_two_ranks_prints_once(tmp_path):
+    """bench.py --impl reference under torchrun: rank 0 alone runs the CPU arm (the reference's own `panSVR fc_aln`) and prints one
+    JSON line, rank 1 exits 0."""
+    from tests.alntest_util import need_ref_tools
+    need_ref_tools()
+    os.environ["PANSVR_BENCH_CACHE"] = str(tmp_path)
+    try:
+        p = _torchrun(["bench.py", "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0", "--loci", "24", "--pairs", "4096",
+                       "--ref-sample-pairs", "1500"], timeout=600)
+    finally:
+        del os.environ["PANSVR_BENCH_CACHE"]
     assert p.returncode == 0, p.stderr[-2000:]
     lines = [ln for ln in p.stdout.splitlines() if ln.startswith("{")]
     assert len(lines) == 1
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["n_gpus"] == 2 and d["value"] > 0 and d["e2e"]["h2d_bytes_per_step"] == 0
-    assert d["cpu_baseline"]["kind"] in ("reference", "port")
+    assert d["cpu_baseline"]["kind"] == "reference" and "fc_aln" in d["metric"]
+
+
+SHARD_WORKER = r"""
+# one input, two processes: rank r realigns its contiguous range of pairs on the host-emulated pipeline (tests/emul), takes the
+# reference's rand()/random_r() streams where rank r-1 left them (pansvr_aln_await_state / publish_state) and rank 0 joins the
+# outputs in rank order = input order
+import ctypes, json, os, sys
+sys.path.insert(0, sys.argv[1])
+import torch.distributed as dist
+from pansvr_b200 import aln, shard
+root, index_dir, header_sam, reads_fq, state_dir, out_path = sys.argv[1:7]
+rank, local, world = shard.rank_env()
+dist.init_process_group("gloo")
+os.environ["PANSVR_ORACLE_SO"] = os.path.join(root, "oracle", "libksw_oracle.so")
+lib = ctypes.CDLL(os.path.join(root, "tests", "emul", "libaln_emul.so"))
+fq = open(reads_fq, "rb").read()
+lines = fq.split(b"\n")
+n_pairs = len([1 for x in lines if x]) // 8
+pb, pe = shard.shard_range(n_pairs, rank, world)
+mine = b"\n".join(lines[8 * pb:8 * pe]) + b"\n"
+head = b"\n".join(lines[:4]) + b"\n"
+ctx = aln.AlnContext(index_dir, header_sam, lib=lib, threads=2)
+outs = []
+for step in range(2):                                 # two passes: reset() must give the same bytes again
+    ctx.reset()
+    ctx.prime_read_stats(head)
+    if rank > 0:
+        ctx.await_state(os.path.join(state_dir, f"s{step}_r{rank}"))
+    sam, ori = ctx.align_fastq(mine)
+    if rank + 1 < world:
+        ctx.publish_state(os.path.join(state_dir, f"s{step}_r{rank + 1}"))
+    outs.append((sam, ori))
+assert outs[0] == outs[1]
+got = [None] * world
+dist.all_gather_object(got, outs[0])
+if rank == 0:
+    hdr = ctx.header_text().encode()
+    open(out_path + ".sam", "wb").write(hdr + b"".join(g[0] for g in got))
+    open(out_path + "_ori.sam", "wb").write(hdr + b"".join(g[1] for g in got))
+    print(json.dumps({"pairs": n_pairs, "ranges": [shard.shard_range(n_pairs, r, world) for r in range(world)]}))
+dist.barrier()
+dist.destroy_process_group()
+"""
+
+
+@pytest.mark.parametrize("name", ["multi_allele", "n_bases"])
+def test_sharded_aln_two_ranks_equals_reference_t1(tmp_path, name):
+    """one input cut into two contiguous pair ranges, one process each; the joined SAM equals `fc_aln -t 1` --
+    with exact score ties (rand() draws at almost every pair) and with N bases (draws whose number depends on the stream)."""
+    from tests.alntest_util import get_demo, need_ref_tools, read, first_diff
+    need_ref_tools()
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "tests", "emul"), os.path.join(ROOT, "tests", "emul", "fc_aln_emul")])
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle"), os.path.join(ROOT, "oracle", "libksw_oracle.so")])
+    demo = get_demo(name)
+    w = tmp_path / "shard_worker.py"
+    w.write_text(SHARD_WORKER)
+    state = tmp_path / "state"
+    state.mkdir()
+    out = str(tmp_path / "joined")
+    p = _torchrun([str(w), ROOT, demo.data.index_dir, demo.data.header_sam, demo.data.reads_fq, str(state), out], timeout=900)
+    assert p.returncode == 0, p.stderr[-3000:]
+    assert first_diff(read(out + ".sam"), read(demo.ref_sam)) is None
+    assert read(out + "_ori.sam") == read(demo.ref_ori)
