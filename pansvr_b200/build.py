@@ -9,7 +9,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libpansvr_b200.so")
-SOURCES = ["ksw_batch.cu", "aln/seed_gpu.cu", "aln/pipeline.cpp", "aln/index.cpp", "aln/aln_capi.cpp", "aln/bam_out.cpp"]
+SOURCES = ["ksw_batch.cu", "aln/seed_gpu.cu", "aln/stages_gpu.cu", "aln/pipeline.cpp", "aln/index.cpp", "aln/aln_capi.cpp", "aln/bam_out.cpp"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 

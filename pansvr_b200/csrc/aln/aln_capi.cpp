@@ -17,6 +17,7 @@
 #include "../../../include/pansvr_b200.h"
 #include "bam_out.hpp"
 #include "pipeline.hpp"
+#include "stages_run.hpp"
 
 using namespace pansvr;
 
@@ -26,6 +27,7 @@ struct pansvr_aln_ctx {
 	DebgaIndex idx;
 	AlnOptions opt;
 	SeedService *seeds = nullptr;
+	StageService *stages = nullptr;
 	pansvr_ksw_ctx *ksw = nullptr;
 	AlnPipeline *pipe = nullptr;
 	BamHeaderInfo bam_hdr;
@@ -211,8 +213,10 @@ int pansvr_aln_create(const char *index_dir, const char *header_sam, const pansv
 	if (ksw_rc != 0) { g_aln_err = pansvr_last_error(); delete c; return PANSVR_E_CUDA; }
 	c->seeds = seed_service_create(c->idx, device, err);
 	if (!c->seeds) { g_aln_err = err; pansvr_ksw_destroy(c->ksw); delete c; return PANSVR_E_CUDA; }
+	c->stages = stage_service_create(c->idx, c->seeds, c->ksw, device, err);
+	if (!c->stages) { g_aln_err = err; seed_service_destroy(c->seeds); pansvr_ksw_destroy(c->ksw); delete c; return PANSVR_E_CUDA; }
 	lap("index upload");
-	c->pipe = new AlnPipeline(c->idx, c->opt, c->seeds, c->ksw);
+	c->pipe = new AlnPipeline(c->idx, c->opt, c->seeds, c->ksw, c->stages);
 	c->bam_hdr.parse(c->idx.header_text);
 	lap("pipeline");
 	*out = c;
@@ -223,6 +227,7 @@ void pansvr_aln_destroy(pansvr_aln_ctx *c)
 {
 	if (!c) return;
 	delete c->pipe;
+	stage_service_destroy(c->stages);
 	seed_service_destroy(c->seeds);
 	pansvr_ksw_destroy(c->ksw);
 	delete c;

@@ -12,8 +12,15 @@
 #include <thread>
 
 #include "../../../include/pansvr_b200.h"
+#include "stages_run.hpp"
 
 namespace pansvr {
+
+struct AlnPipeline::DevBuffers {                                  // host side of one block's trip through the device stages
+	HostVec<DevRead> reads;
+	HostVec<uint8_t> seq;                                         // the bases of the block's device reads, gathered (pinned)
+	DevStageOut out;
+};
 
 namespace {
 
@@ -242,6 +249,8 @@ struct ReadState {
 	uint32_t var_code = 0;                     // variant: substitution of the j-th N = (var_code >> 2j) & 3
 	bool in_order_only = false;                // real read: must be prepared during the replay (too many N, or random_r needed)
 	bool batched = false, needs_rand = false;  // needs_rand: a unipath with > 500 positions draws from random_r (expand_seed)
+	bool dev = false;                          // stages A..F1 of this read state ran on the device (stages_run.hpp)
+	int64_t dev_index = -1;                    // its row in the block's device read table
 	std::vector<VertexU> vu[2];
 	int job[2] = {-1, -1};
 	Graph g[2];
@@ -1096,14 +1105,20 @@ struct AlnPipeline::Impl {
 };
 
 // ================================================================================================ public
-AlnPipeline::AlnPipeline(const DebgaIndex &idx, const AlnOptions &o, SeedService *seeds, void *ksw_ctx)
-	: opt(o), idx_(idx), seeds_(seeds), ksw_(ksw_ctx), rand_(1)
+AlnPipeline::AlnPipeline(const DebgaIndex &idx, const AlnOptions &o, SeedService *seeds, void *ksw_ctx, StageService *stages)
+	: opt(o), idx_(idx), seeds_(seeds), ksw_(ksw_ctx), stages_(stages), rand_(1)
 {
 	if (opt.threads > 1) workers_ = new Workers(opt.threads);
+	if (getenv("PANSVR_HOST_STAGES")) stages_ = nullptr;          // differential runs: stages A, C, D on the host (the round-1 path)
+	if (stages_) {
+		AlnScores sc{opt.match, opt.mismatch, opt.gap_open, opt.gap_ex, opt.gap_open2, opt.gap_ex2};
+		stage_service_set_scoring(stages_, sc, opt.zdrop);
+		for (DevBuffers *&b : devbuf_) b = new DevBuffers();
+	}
 	reset();
 }
 
-AlnPipeline::~AlnPipeline() { delete workers_; }
+AlnPipeline::~AlnPipeline() { delete workers_; for (DevBuffers *b : devbuf_) delete b; }
 
 // read statistics from the first comment of the input (load_reads, RR:134-148); must have run before two blocks are in flight
 void AlnPipeline::ensure_read_stats(const FastqRec &first)
@@ -1205,13 +1220,14 @@ bool AlnPipeline::align_block(const FastqRec *recs, size_t n_reads_in, BlockOutp
 	double ta = now();
 	auto lap = [&](const char *what) { if (timing) { const double t = now(); fprintf(stderr, "[timing]   A/%s %.3f s\n", what, t - ta); ta = t; } };
 	enum { MAX_VARIANT_DRAWS = 3 };
-	std::vector<uint8_t> n_count(n_reads, 0);
+	std::vector<uint8_t> n_count(n_reads, 0), lower_n(n_reads, 0);
 	par_reads([&](size_t b, size_t e, int) {
 		for (size_t i = b; i < e; ++i) {
 			uint32_t c = 0;
 			const char *q = recs[i].seq, *qe = q + recs[i].seq_l;
 			while ((q = (const char*)memchr(q, 'N', (size_t)(qe - q))) != nullptr) { ++c; ++q; }
 			n_count[i] = (uint8_t)std::min<uint32_t>(c, 255);
+			lower_n[i] = memchr(recs[i].seq, 'n', recs[i].seq_l) != nullptr;     // code 4 spills into the packed neighbour: such a read stays on the host
 		}
 	});
 	std::vector<std::pair<size_t, size_t>> var_src;                       // (real read, first variant index) of reads with variants
@@ -1292,14 +1308,111 @@ bool AlnPipeline::align_block(const FastqRec *recs, size_t n_reads_in, BlockOutp
 			I.chain(g, edges);
 		}
 	};
+	// a real read with N is not encoded here (its bases depend on the draws); the N-free mate of such a read is
+	for (size_t i = 0; i < n_all; ++i) { ReadState &r = rs[i]; r.batched = !(r.skip || r.has_n || r.read_l < LEN_KMER); }
+	// ---- device path: stages A..F1 of every read state the host does not have to keep run on the GPU in one trip
+	// (stages_run.hpp); what comes back are the sorted seeds and chain tables of both strands and the candidate alignments
+	// (score + final CIGAR) of every chain end that can still be chosen.  Reads the device hands back (a unipath with more than
+	// 500 positions: expand_seed draws from random_r) and reads with a lower-case 'n' go through the host stages below.
+	if (stages_) {
+		DevBuffers &db = *devbuf_[seq & 1];
+		std::vector<uint32_t> ids;
+		ids.reserve(n_all);
+		for (size_t i = 0; i < n_all; ++i) {
+			const ReadState &r = rs[i];
+			const size_t real = r.var_of >= 0 ? (size_t)r.var_of : i;
+			if (r.batched && !lower_n[real]) ids.push_back((uint32_t)i);
+		}
+		const size_t nd = ids.size();
+		db.reads.resize(nd);
+		size_t seq_bytes = 0, words = 0, list_bytes = 0;
+		for (size_t k = 0; k < nd; ++k) {
+			const ReadState &r = rs[ids[k]];
+			DevRead &d = db.reads[k];
+			d.seq_off = (uint32_t)seq_bytes; d.len = (uint32_t)r.read_l; d.var_code = r.var_of >= 0 ? r.var_code : 0u;
+			d.bits_off = (uint32_t)words; d.list_off = (uint32_t)list_bytes;
+			seq_bytes += (size_t)r.read_l; words += 2 * (size_t)((r.read_l >> 5) + 2); list_bytes += 2 * (size_t)(r.read_l - LEN_KMER + 1);
+		}
+		if (seq_bytes >= 0xffffffffull || words >= 0xffffffffull || list_bytes >= 0xffffffffull) { err = "block too large for the device stages (cut it into smaller blocks)"; return false; }
+		db.seq.resize(seq_bytes + 1);
+		parallel(nd, [&](size_t b, size_t e, int) { for (size_t k = b; k < e; ++k) memcpy(db.seq.data() + db.reads[k].seq_off, rs[ids[k]].rec->seq, db.reads[k].len); });
+		lap("device read table + gather");
+		add_time(0, now() - t0); t0 = now();
+		DevStageIn in;
+		in.text = db.seq.data(); in.text_bytes = seq_bytes; in.reads = db.reads.data(); in.n_reads = nd; in.bits_words = words; in.list_bytes = list_bytes;
+		in.scores = AlnScores{opt.match, opt.mismatch, opt.gap_open, opt.gap_ex, opt.gap_open2, opt.gap_ex2};
+		{
+			std::lock_guard<std::mutex> dev(dev_m_);
+			if (nd && !stage_service_run(stages_, in, db.out, err)) return false;
+		}
+		add_time(1, now() - t0); t0 = now();
+		const DevStageOut &o = db.out;
+		if (const char *dump = getenv("PANSVR_DUMP_STAGES")) {                  // tests: what the device stages returned, for the differential
+			const std::string path = std::string(dump) + "." + std::to_string(seq);   // between the CUDA backend and the host-stepped one
+			if (FILE *f = fopen(path.c_str(), "wb")) {
+				const uint64_t hdr[4] = {nd, nd ? o.seed_off[2 * nd] : 0, o.cands.size(), nd ? o.mem_off[2 * nd] : 0};
+				fwrite(hdr, 8, 4, f);
+				if (nd) {
+					fwrite(o.flags.data(), 1, nd, f); fwrite(o.mem_off.data(), 4, 2 * nd + 1, f); fwrite(o.seed_off.data(), 4, 2 * nd + 1, f);
+					fwrite(o.seeds.data(), sizeof(DevSeed), o.seeds.size(), f); fwrite(o.dist.data(), 4, o.dist.size(), f); fwrite(o.pre.data(), 4, o.pre.size(), f);
+					fwrite(o.cand_off.data(), 4, nd + 1, f);
+					for (size_t c = 0; c < o.cands.size(); ++c) {
+						DevCand cd = o.cands[c];
+						fwrite(o.cigs.data() + cd.cig_off, sizeof(DevCigar), cd.n_cig, f);
+						cd.piece_off = cd.cig_off = cd.cig_cap = 0;                     // (layout details that may differ between backends)
+						fwrite(&cd, sizeof cd, 1, f);
+					}
+				}
+				fclose(f);
+			}
+		}
+		static_assert(sizeof(UniSeed) == sizeof(DevSeed) && sizeof(CigarPath) == sizeof(DevCigar), "device records mirror the host's");
+		std::atomic<uint64_t> kept(0);
+		if (nd) parallel(nd, [&](size_t b, size_t e, int) {
+			uint64_t k_mems = 0;
+			for (size_t k = b; k < e; ++k) {
+				ReadState &r = rs[ids[k]];
+				r.dev_index = (int64_t)k;
+				if (o.flags[k] & ST_FLAG_NEEDS_RAND) continue;             // stays `batched`: host stages below
+				r.dev = true; r.batched = false;
+				r.is_str = (o.flags[k] & ST_FLAG_STR) != 0;
+				k_mems += o.mem_off[2 * k + 2] - o.mem_off[2 * k];
+				for (int s = 0; s < 2; ++s) {
+					const uint32_t sb0 = o.seed_off[2 * k + s], n = o.seed_off[2 * k + s + 1] - sb0;
+					Graph &g = r.g[s];
+					g.is_str = r.is_str;
+					g.v.resize(n); g.path.resize(n);
+					if (n) memcpy((void*)g.v.data(), o.seeds.data() + sb0, (size_t)n * sizeof(UniSeed));
+					for (uint32_t x = 0; x < n; ++x) { g.path[x].dist = o.dist[sb0 + x]; g.path[x].pre_node = o.pre[sb0 + x]; g.path[x].used = 0; }
+				}
+				r.node_aln.clear();
+				for (uint32_t c = o.cand_off[k]; c < o.cand_off[k + 1]; ++c) {
+					const DevCand &cd = o.cands[c];
+					r.node_aln.emplace_back((uint64_t)cd.strand << 32 | cd.node, NodeAln());
+					NodeAln &na = r.node_aln.back().second;
+					na.planned = na.resolved = true;
+					na.fixed_score = cd.fixed_score; na.read_begin_alignment = cd.read_begin_alignment;
+					na.align_score = cd.align_score; na.cigar_ok = cd.cigar_ok != 0;
+					na.cigar.resize(cd.n_cig);
+					if (cd.n_cig) memcpy((void*)na.cigar.data(), o.cigs.data() + cd.cig_off, (size_t)cd.n_cig * sizeof(CigarPath));
+				}
+			}
+			kept += k_mems;
+		});
+		{
+			std::lock_guard<std::mutex> lk(stats_m_);
+			stats.mems += kept.load(); stats.ksw_tasks += o.n_tasks; stats.ksw_cells += o.n_cells;
+			stats.dev.add(o.dev); stats.dev.seed_probes += (int64_t)o.probes;
+			db.out.dev = DevCounters();
+		}
+		lap("read states from the device results");
+	}
 	SeedBatch &sb = seed_main_[seq & 1];
 	sb.clear();
 	{
 		std::vector<uint32_t> word_off(n_all + 1, 0), job_of(n_all + 1, 0);
 		for (size_t i = 0; i < n_all; ++i) {                                 // layout of the packed-read pool (two strands per read)
 			ReadState &r = rs[i];
-			// a real read with N is not encoded here (its bases depend on the draws); the N-free mate of such a read is
-			r.batched = !(r.skip || r.has_n || r.read_l < LEN_KMER);
 			word_off[i + 1] = word_off[i] + (r.batched ? 2u * (uint32_t)((r.read_l >> 5) + 2) : 0u);
 			job_of[i + 1] = job_of[i] + (r.batched ? 2u : 0u);
 		}

@@ -128,6 +128,7 @@ struct KswBatchBuf {                  // the ksw tasks of one block, joined (sta
 	HostVec<uint32_t> cig;
 	int cap = 16;                     // CIGAR words per task; a block whose longest CIGAR does not fit is run again with room
 };
+struct StageService;                  // opaque; the device stages (stages_run.hpp)
 struct SeedService;                   // opaque; owns the device-resident index
 SeedService *seed_service_create(const DebgaIndex &idx, int device, std::string &err);
 void seed_service_destroy(SeedService *s);
@@ -143,7 +144,8 @@ struct CigarPath { uint8_t type; int16_t size; };
 
 class AlnPipeline {
 public:
-	AlnPipeline(const DebgaIndex &idx, const AlnOptions &opt, SeedService *seeds, void *ksw_ctx);
+	// `stages` (may be null): the device stages A..F1 (stages_run.hpp); without them every stage but seeding and ksw runs on the host
+	AlnPipeline(const DebgaIndex &idx, const AlnOptions &opt, SeedService *seeds, void *ksw_ctx, StageService *stages = nullptr);
 	~AlnPipeline();
 	AlnPipeline(const AlnPipeline&) = delete;
 	AlnPipeline &operator=(const AlnPipeline&) = delete;
@@ -177,6 +179,9 @@ private:
 	const DebgaIndex &idx_;
 	SeedService *seeds_;
 	void *ksw_;
+	StageService *stages_;
+	struct DevBuffers;
+	DevBuffers *devbuf_[2] = {nullptr, nullptr};   // host side of the device stages' transfers, kept across blocks; slot = seq & 1
 	SeedBatch seed_main_[2], seed_small_; // batch buffers live across blocks (staging memory is pinned once); slot = seq & 1
 	KswBatchBuf ksw_main_[2];
 	std::mutex dev_m_;                    // the two device services take one batch at a time

@@ -115,6 +115,8 @@ SeedService *seed_service_create(const DebgaIndex &idx, int device, std::string 
 	return s;
 }
 
+const IndexView &seed_service_view(const SeedService *s) { return s->view; }
+
 void seed_service_destroy(SeedService *s)
 {
 	if (!s) return;

@@ -1,0 +1,174 @@
+// stages_gpu.cu -- CUDA backend of the device stages (stages_run.hpp): one thread per read / strand / candidate, grow-only
+// buffers in HBM, cub prefix sums, everything of one block on one stream.  The per-read work of these stages is a few hundred
+// dependent integer operations over a few hundred bytes, so the kernels are bound by HBM/L2 latency with every SM full of
+// reads in flight -- the layout goal is that a read's data is touched once per stage and never leaves the device in between.
+#include <cuda_runtime.h>
+#include <cub/device/device_scan.cuh>
+#include <string>
+#include <vector>
+
+#include "../../../include/pansvr_b200.h"
+#include "stages_run.hpp"
+
+namespace pansvr {
+
+// device pointers of the seed service (seed_gpu.cu)
+const IndexView &seed_service_view(const SeedService *s);
+
+namespace {
+
+template <class F> __global__ void __launch_bounds__(128) for_each_kernel(F f, size_t n)
+{
+	const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n) f(i);
+}
+
+struct CudaBackend {
+	cudaStream_t st = nullptr;
+	void *p[SL_COUNT]; size_t cap[SL_COUNT];
+	bool failed = false; std::string why;
+	std::vector<cudaEvent_t> ev_pool; size_t ev_used = 0;
+	struct Lap { cudaEvent_t a, b; int stage; };
+	std::vector<Lap> laps;
+	pansvr_ksw_ctx *ksw_ctx = nullptr; pansvr_ksw_params_t kp; int8_t mat[25];
+	HostVec<int32_t> h_qlen, h_tlen;
+	DevCounters dev;
+	CudaBackend() { for (int i = 0; i < SL_COUNT; ++i) { p[i] = nullptr; cap[i] = 0; } }
+	void check(cudaError_t e, const char *what) { if (e != cudaSuccess && !failed) { failed = true; why = std::string(what) + ": " + cudaGetErrorString(e); } }
+	template <class T> T *buf(int slot, size_t n)
+	{
+		const size_t bytes = n * sizeof(T);
+		if (bytes <= cap[slot]) return (T*)p[slot];
+		check(cudaStreamSynchronize(st), "cudaStreamSynchronize");
+		if (p[slot]) cudaFree(p[slot]);
+		p[slot] = nullptr; cap[slot] = 0;
+		const size_t want = bytes + bytes / 4 + 4096;
+		cudaError_t e = cudaMalloc(&p[slot], want);
+		if (e != cudaSuccess) { check(e, "cudaMalloc"); return nullptr; }
+		cap[slot] = want;
+		return (T*)p[slot];
+	}
+	void h2d(void *d, const void *h, size_t bytes) { if (bytes) { check(cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, st), "cudaMemcpyAsync H2D"); dev.h2d_bytes += (int64_t)bytes; } }
+	void d2h(void *h, const void *d, size_t bytes) { if (bytes) { check(cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, st), "cudaMemcpyAsync D2H"); dev.d2h_bytes += (int64_t)bytes; } }
+	void zero(void *d, size_t bytes) { if (bytes) check(cudaMemsetAsync(d, 0, bytes, st), "cudaMemsetAsync"); }
+	void sync() { check(cudaStreamSynchronize(st), "cudaStreamSynchronize"); }
+	cudaEvent_t event()
+	{
+		if (ev_used == ev_pool.size()) { cudaEvent_t e; check(cudaEventCreate(&e), "cudaEventCreate"); ev_pool.push_back(e); }
+		return ev_pool[ev_used++];
+	}
+	template <class F> void for_each(size_t n, const F &f, int stage)
+	{
+		if (n == 0 || failed) return;
+		Lap l; l.a = event(); l.b = event(); l.stage = stage;
+		check(cudaEventRecord(l.a, st), "cudaEventRecord");
+		const unsigned threads = 128;
+		for_each_kernel<F><<<(unsigned)((n + threads - 1) / threads), threads, 0, st>>>(f, n);
+		check(cudaGetLastError(), "kernel launch");
+		check(cudaEventRecord(l.b, st), "cudaEventRecord");
+		laps.push_back(l);
+		++dev.launches;
+	}
+	void scan(const uint32_t *in, uint32_t *out, size_t n)
+	{
+		size_t tmp_bytes = 0;
+		check(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, in, out, (int)n, st), "cub scan size");
+		void *tmp = buf<uint8_t>(SL_SCAN_TMP, tmp_bytes + 256);
+		if (!tmp) return;
+		check(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, in, out, (int)n, st), "cub scan");
+	}
+	bool ksw(size_t n, const uint8_t *q, const int64_t *qoff, const int32_t *qlen, const uint8_t *t, const int64_t *toff, const int32_t *tlen,
+	         int32_t *res, uint32_t *cig, int cigar_cap, std::string &err)
+	{
+		h_qlen.resize(n); h_tlen.resize(n);
+		d2h(h_qlen.data(), qlen, n * 4);
+		d2h(h_tlen.data(), tlen, n * 4);
+		sync();
+		if (failed) { err = why; return false; }
+		// (the ksw context has its own stream; everything it reads was produced before the sync above, and the call returns
+		// after its kernels have finished)
+		const int rc = pansvr_ksw_extd2_batch_device(ksw_ctx, (int64_t)n, q, qoff, qlen, t, toff, tlen, h_qlen.data(), h_tlen.data(), &kp, res, cig, cigar_cap);
+		if (rc != 0) { err = std::string("ksw batch: ") + pansvr_last_error(); return false; }
+		pansvr_ksw_stats_t ks;
+		if (pansvr_ksw_last_stats(ksw_ctx, &ks) == 0) { dev.launches += ks.kernel_launches; dev.h2d_bytes += ks.h2d_bytes; dev.ksw_kernel_ms += ks.kernel_ms; }
+		return true;
+	}
+	void collect_laps()
+	{
+		for (const Lap &l : laps) {
+			float ms = 0;
+			if (cudaEventElapsedTime(&ms, l.a, l.b) != cudaSuccess) continue;
+			if (l.stage == 1) dev.seed_kernel_ms += ms; else dev.stage_kernel_ms += ms;
+		}
+		laps.clear(); ev_used = 0;
+	}
+};
+
+} // namespace
+
+struct StageService {
+	int device = 0;
+	CudaBackend be;
+	void *scan_tmp = nullptr; size_t scan_cap = 0;
+	IndexView view;
+	uint64_t *d_pos = nullptr, *d_ref = nullptr;
+	RefView rf;
+};
+
+StageService *stage_service_create(const DebgaIndex &idx, SeedService *seeds, void *ksw_ctx, int device, std::string &err)
+{
+	if (cudaSetDevice(device) != cudaSuccess) { err = "stage service: no usable CUDA device (the device stages have no CPU fallback)"; return nullptr; }
+	StageService *s = new StageService();
+	s->device = device;
+	s->view = seed_service_view(seeds);
+	s->be.ksw_ctx = (pansvr_ksw_ctx*)ksw_ctx;
+	auto up = [&](const std::vector<uint64_t> &h, uint64_t *&d) -> bool {
+		if (cudaMalloc((void**)&d, (h.size() + 2) * 8) != cudaSuccess) return false;
+		if (cudaMemset(d, 0, (h.size() + 2) * 8) != cudaSuccess) return false;
+		return cudaMemcpy(d, h.data(), h.size() * 8, cudaMemcpyHostToDevice) == cudaSuccess;
+	};
+	if (cudaStreamCreateWithFlags(&s->be.st, cudaStreamNonBlocking) != cudaSuccess || !up(idx.pos, s->d_pos) || !up(idx.ref_seq, s->d_ref)) {
+		err = "stage service: CUDA set-up failed";
+		stage_service_destroy(s);
+		return nullptr;
+	}
+	s->rf.ref_seq = s->d_ref;
+	return s;
+}
+
+void stage_service_destroy(StageService *s)
+{
+	if (!s) return;
+	cudaSetDevice(s->device);
+	if (s->be.st) cudaStreamSynchronize(s->be.st);
+	for (int i = 0; i < SL_COUNT; ++i) if (s->be.p[i]) cudaFree(s->be.p[i]);
+	for (cudaEvent_t e : s->be.ev_pool) cudaEventDestroy(e);
+	if (s->d_pos) cudaFree(s->d_pos);
+	if (s->d_ref) cudaFree(s->d_ref);
+	if (s->be.st) cudaStreamDestroy(s->be.st);
+	delete s;
+}
+
+void stage_service_set_scoring(StageService *s, const AlnScores &o, int zdrop)
+{
+	CudaBackend &be = s->be;
+	const int8_t m = (int8_t)o.match, x = (int8_t)-o.mismatch;
+	for (int a = 0, k = 0; a < 5; ++a) for (int b = 0; b < 5; ++b, ++k) be.mat[k] = (a == 4 || b == 4) ? 0 : (a == b ? m : x);   // ksw_gen_mat_D, RR:829-844
+	be.kp.m = 5; be.kp.mat = be.mat; be.kp.gapo = (int8_t)o.gap_open; be.kp.gape = (int8_t)o.gap_ex; be.kp.gapo2 = (int8_t)o.gap_open2; be.kp.gape2 = (int8_t)o.gap_ex2;
+	be.kp.w = 200; be.kp.zdrop = (uint16_t)zdrop; be.kp.end_bonus = -1; be.kp.flag = 0;               // copy_option, RR:817-827
+}
+
+bool stage_service_run(StageService *s, const DevStageIn &in, DevStageOut &out, std::string &err)
+{
+	if (cudaSetDevice(s->device) != cudaSuccess) { err = "cudaSetDevice failed"; return false; }
+	CudaBackend &be = s->be;
+	be.failed = false; be.why.clear(); be.dev = DevCounters();
+	const bool ok = run_device_stages(be, s->view, s->d_pos, s->rf, in, out, err);
+	be.sync();
+	be.collect_laps();
+	out.dev.add(be.dev);
+	if (be.failed) { err = "device stages: " + be.why; return false; }
+	return ok;
+}
+
+} // namespace pansvr

@@ -1,0 +1,282 @@
+// stages_run.hpp -- one block of read states through the device stages A..F1 (stages_core.cuh), written once against a small
+// backend interface: the CUDA backend of the product (stages_gpu.cu: kernels on a stream, buffers in HBM, cub scans) and the
+// host backend of the CPU-only test build (tests/emul: the same functors stepped by a loop).  Everything between the FASTQ
+// text and the candidate alignments stays in device memory; the host gets back what stage F needs.
+//
+//   text + read table --H2D--> A encode/census -> B seed count | scan | fill -> (MEMs --D2H--> for reads the host keeps)
+//     -> C merge | scan | expand + chain -> D plan count | scans | fill -> E ksw (ksw_team kernels) -> F1 resolve
+//     --D2H--> per strand: sorted seeds + chain table; per read: candidates with score and final CIGAR
+//
+// Backend concept:
+//   template <class T> T *buf(int slot, size_t n)        grow-only device buffer `slot`, at least n elements
+//   void h2d(void *d, const void *h, size_t bytes)  /  void d2h(void *h, const void *d, size_t bytes)   (stream order)
+//   void zero(void *d, size_t bytes)
+//   void sync()                                           wait for everything issued so far
+//   template <class F> void for_each(size_t n, const F &f, int stage)    f(i) for i in [0, n); `stage` labels the timing
+//   void scan(const uint32_t *in, uint32_t *out, size_t n)               exclusive prefix sums, n elements
+//   bool ksw(n, q, qoff, qlen, t, toff, tlen, res, cig, cap, err)        ksw_extd2 batch (w=200, the stage's scoring) over device arrays
+#pragma once
+#include <string>
+
+#include "pipeline.hpp"
+#include "stages_core.cuh"
+
+namespace pansvr {
+
+enum DevSlot {
+	SL_TEXT, SL_READS, SL_BITS, SL_LIST, SL_FLAGS, SL_MEM_CNT, SL_MEM_OFF, SL_MEMS, SL_MEMS_TMP, SL_NVU, SL_SEED_CNT, SL_SEED_OFF,
+	SL_SEEDS, SL_SEEDS_TMP, SL_DIST, SL_PRE, SL_PLAN_CNT, SL_PLAN_OFF, SL_CANDS, SL_PIECES, SL_QLEN, SL_TLEN, SL_QOFF, SL_TOFF,
+	SL_Q, SL_T, SL_RES, SL_KCIG, SL_CIGS, SL_MISC, SL_SCAN_TMP, SL_COUNT
+};
+
+// ---- functors (one element of work each; plain data members only, so they can be passed to a kernel by value)
+struct FnEncode {
+	const uint8_t *text; const DevRead *reads; uint64_t *bits; uint8_t *list; uint8_t *flags;
+	SEED_HD void operator()(size_t i) const { flags[i] = encode_read(text, reads[i], bits, list) ? (uint8_t)ST_FLAG_STR : (uint8_t)0; }
+};
+struct FnSeed {                                                    // strand j = 2 * read + strand; fill == false: count only
+	IndexView ix; const DevRead *reads; const uint64_t *bits; const uint8_t *list; const uint8_t *flags;
+	uint32_t *count; const uint32_t *off; Mem *mems; unsigned long long *probes; bool fill;
+	SEED_HD void operator()(size_t j) const
+	{
+		const DevRead &rd = reads[j >> 1];
+		const uint32_t s = (uint32_t)(j & 1), words = (rd.len >> 5) + 2, kn = rd.len - LEN_KMER + 1;
+		const uint64_t *b = bits + rd.bits_off + (size_t)s * words;
+		const bool is_str = (flags[j >> 1] & ST_FLAG_STR) != 0;
+		const uint8_t *sl = list + rd.list_off + (size_t)s * kn;
+		if (!fill) {
+			uint32_t p = 0;
+			count[j] = (uint32_t)seed_read_strand(ix, b, rd.len, is_str, sl, (Mem*)nullptr, 0, &p);
+#if defined(__CUDA_ARCH__)
+			if (p) atomicAdd(probes, (unsigned long long)p);
+#else
+			*probes += p;
+#endif
+		} else {
+			const int cap = (int)(off[j + 1] - off[j]);
+			if (cap > 0) seed_read_strand(ix, b, rd.len, is_str, sl, mems + off[j], cap);
+		}
+	}
+};
+struct FnMerge {                                                   // per read: both strands
+	const uint32_t *mem_off; Mem *mems, *tmp; uint8_t *flags; uint32_t *nvu, *seed_cnt;
+	SEED_HD void operator()(size_t i) const
+	{
+		const uint32_t b = mem_off[2 * i], e = mem_off[2 * i + 2];
+		bool needs_rand = false;
+		for (uint32_t k = b; k < e; ++k) needs_rand |= mems[k].pos_n > (uint32_t)ST_POS_N_MAX;
+		if (needs_rand) {                                           // expand_seed would draw from random_r: the host keeps this read
+			flags[i] |= (uint8_t)ST_FLAG_NEEDS_RAND;
+			nvu[2 * i] = nvu[2 * i + 1] = 0; seed_cnt[2 * i] = seed_cnt[2 * i + 1] = 0;
+			return;
+		}
+		for (int s = 0; s < 2; ++s) {
+			const uint32_t mb = mem_off[2 * i + s], me = mem_off[2 * i + s + 1];
+			uint32_t ns = 0;
+			nvu[2 * i + s] = merge_strand(mems + mb, tmp + mb, me - mb, &ns);
+			seed_cnt[2 * i + s] = ns;
+		}
+	}
+};
+struct FnChain {
+	const uint32_t *mem_off, *nvu, *seed_off; const Mem *mems; const uint64_t *pos, *posp; const uint8_t *flags;
+	DevSeed *seeds, *tmp; float *dist; int32_t *pre;
+	SEED_HD void operator()(size_t i) const
+	{
+		for (int s = 0; s < 2; ++s) {
+			const uint32_t sb = seed_off[2 * i + s], n = seed_off[2 * i + s + 1] - sb;
+			if (n == 0) continue;
+			chain_strand((const DevVertex*)(mems + mem_off[2 * i + s]), nvu[2 * i + s], pos, posp, (flags[i] & ST_FLAG_STR) != 0,
+			             seeds + sb, tmp + sb, n, dist + sb, pre + sb);
+		}
+	}
+};
+enum { PLAN_FIELDS = 6 };                                          // cands, pieces, tasks, q bytes, t bytes, CIGAR room
+struct FnPlan {
+	AlnScores o; RefView rf; const DevRead *reads; const uint64_t *bits; const uint32_t *seed_off; const DevSeed *seeds; const float *dist; const int32_t *pre;
+	size_t n_reads; uint32_t *cnt; const uint32_t *off;              // cnt / off: PLAN_FIELDS planes of (n_reads + 1)
+	DevCand *cands; DevPiece *pieces; int32_t *qlen, *tlen; int64_t *qoff, *toff; uint8_t *q, *t; uint32_t ksw_cig_cap; bool fill;
+	SEED_HD void operator()(size_t i) const
+	{
+		const DevRead &rd = reads[i];
+		const DevSeed *v[2]; const float *d[2]; const int32_t *p[2]; uint32_t n[2];
+		for (int s = 0; s < 2; ++s) {
+			const uint32_t sb = seed_off[2 * i + s];
+			v[s] = seeds + sb; d[s] = dist + sb; p[s] = pre + sb; n[s] = seed_off[2 * i + s + 1] - sb;
+		}
+		PlanSink S;
+		S.fill = fill; S.n_cand = S.n_piece = S.n_task = S.q_bytes = S.t_bytes = S.cig_cap = 0; S.ksw_cig_cap = ksw_cig_cap;
+		S.cand = nullptr; S.piece = nullptr; S.task_qlen = S.task_tlen = nullptr; S.task_qoff = S.task_toff = nullptr; S.q = S.t = nullptr;
+		S.piece_base = S.task_base = S.cig_base = 0; S.q_base = S.t_base = 0;
+		const size_t P = n_reads + 1;
+		if (fill) {
+			const uint32_t c0 = off[i], p0 = off[P + i], k0 = off[2 * P + i], q0 = off[3 * P + i], t0 = off[4 * P + i], g0 = off[5 * P + i];
+			S.cand = cands + c0; S.piece = pieces + p0; S.task_qlen = qlen + k0; S.task_tlen = tlen + k0; S.task_qoff = qoff + k0; S.task_toff = toff + k0;
+			S.q = q + q0; S.t = t + t0; S.piece_base = p0; S.task_base = k0; S.cig_base = g0; S.q_base = (int64_t)q0; S.t_base = (int64_t)t0;
+		}
+		if (n[0] + n[1] != 0) plan_read(o, rf, (uint32_t)i, bits + rd.bits_off, rd.len, v, d, p, n, S);
+		if (!fill) { cnt[i] = S.n_cand; cnt[P + i] = S.n_piece; cnt[2 * P + i] = S.n_task; cnt[3 * P + i] = S.q_bytes; cnt[4 * P + i] = S.t_bytes; cnt[5 * P + i] = S.cig_cap; }
+	}
+};
+struct FnResolve {
+	DevCand *cands; const DevPiece *pieces; const int32_t *res; const uint32_t *kcig; int cap; const DevRead *reads; DevCigar *cigs; uint32_t *overflow;
+	SEED_HD void operator()(size_t c) const
+	{
+		if (!resolve_cand(cands[c], pieces, res, kcig, cap, reads[cands[c].read].len, cigs)) *overflow = 1;     // (benign race: every writer stores 1)
+	}
+};
+
+struct FnCells {                                                   // in-band DP cells of the tasks (the unit GCUPS is quoted in, KSW:131-138)
+	const int32_t *qlen, *tlen; int w; unsigned long long *cells;
+	SEED_HD void operator()(size_t k) const
+	{
+		const int ql = qlen[k], tl = tlen[k];
+		if (ql <= 0 || tl <= 0) return;
+		unsigned long long c = 0;
+		for (int r = 0; r < ql + tl - 1; ++r) {
+			int lo = 0, hi = tl - 1;
+			if (lo < r - ql + 1) lo = r - ql + 1;
+			if (hi > r) hi = r;
+			if (lo < ((r - w + 1) >> 1)) lo = (r - w + 1) >> 1;
+			if (hi > ((r + w) >> 1)) hi = (r + w) >> 1;
+			if (lo > hi) break;
+			c += (unsigned long long)(hi - lo + 1);
+		}
+#if defined(__CUDA_ARCH__)
+		atomicAdd(cells, c);
+#else
+		*cells += c;
+#endif
+	}
+};
+
+struct DevStageIn {
+	const uint8_t *text; size_t text_bytes;                        // host: the block's FASTQ text (seq_off of the read table points into it)
+	const DevRead *reads; size_t n_reads;                          // host: the read table; bits_off / list_off laid out by the caller
+	size_t bits_words, list_bytes;                                 // pool sizes implied by the table
+	AlnScores scores;
+};
+struct DevStageOut {                                               // host side, kept across blocks (pinned in the product)
+	HostVec<uint8_t> flags;                                        // per read state: ST_FLAG_*
+	HostVec<uint32_t> mem_off;                                     // 2 n + 1: MEM counts (the MEMs themselves never leave the device)
+	HostVec<uint32_t> seed_off;                                    // 2 n + 1: seeds of strand s of read i = [seed_off[2i+s], seed_off[2i+s+1])
+	HostVec<DevSeed> seeds; HostVec<float> dist; HostVec<int32_t> pre;
+	HostVec<uint32_t> cand_off;                                    // n + 1
+	HostVec<DevCand> cands; HostVec<DevCigar> cigs;
+	uint64_t n_tasks = 0, n_cells = 0, probes = 0;
+	DevCounters dev;
+};
+
+template <class BE>
+bool run_device_stages(BE &be, const IndexView &ix, const uint64_t *d_pos, const RefView &rf, const DevStageIn &in, DevStageOut &out, std::string &err)
+{
+	const size_t n = in.n_reads;
+	out.n_tasks = out.n_cells = out.probes = 0;
+	out.flags.resize(n); out.mem_off.resize(2 * n + 1); out.seed_off.resize(2 * n + 1); out.cand_off.resize(n + 1);
+	out.seeds.clear(); out.dist.clear(); out.pre.clear(); out.cands.clear(); out.cigs.clear();
+	if (n == 0) { out.mem_off[0] = out.seed_off[0] = out.cand_off[0] = 0; return true; }
+	// ---- upload
+	uint8_t *d_text = be.template buf<uint8_t>(SL_TEXT, in.text_bytes + 16);
+	DevRead *d_reads = be.template buf<DevRead>(SL_READS, n);
+	uint64_t *d_bits = be.template buf<uint64_t>(SL_BITS, in.bits_words + 2);
+	uint8_t *d_list = be.template buf<uint8_t>(SL_LIST, in.list_bytes + 16);
+	uint8_t *d_flags = be.template buf<uint8_t>(SL_FLAGS, n);
+	uint32_t *d_mem_cnt = be.template buf<uint32_t>(SL_MEM_CNT, 2 * n + 1), *d_mem_off = be.template buf<uint32_t>(SL_MEM_OFF, 2 * n + 1);
+	uint32_t *d_misc = be.template buf<uint32_t>(SL_MISC, 16);
+	if (!d_text || !d_reads || !d_bits || !d_list || !d_flags || !d_mem_cnt || !d_mem_off || !d_misc) { err = "device stages: out of device memory"; return false; }
+	be.h2d(d_text, in.text, in.text_bytes);
+	be.h2d(d_reads, in.reads, n * sizeof(DevRead));
+	be.zero(d_misc, 64);
+	be.zero(d_mem_cnt + 2 * n, 4);
+	// ---- A
+	be.for_each(n, FnEncode{d_text, d_reads, d_bits, d_list, d_flags}, 0);
+	// ---- B
+	unsigned long long *d_probes = (unsigned long long*)(d_misc + 2);
+	FnSeed fs{ix, d_reads, d_bits, d_list, d_flags, d_mem_cnt, d_mem_off, nullptr, d_probes, false};
+	be.for_each(2 * n, fs, 1);
+	be.scan(d_mem_cnt, d_mem_off, 2 * n + 1);
+	be.d2h(out.mem_off.data(), d_mem_off, (2 * n + 1) * 4);
+	be.sync();
+	const size_t n_mems = out.mem_off[2 * n];
+	Mem *d_mems = be.template buf<Mem>(SL_MEMS, n_mems + 1), *d_mems_tmp = be.template buf<Mem>(SL_MEMS_TMP, n_mems + 1);
+	uint32_t *d_nvu = be.template buf<uint32_t>(SL_NVU, 2 * n), *d_seed_cnt = be.template buf<uint32_t>(SL_SEED_CNT, 2 * n + 1);
+	uint32_t *d_seed_off = be.template buf<uint32_t>(SL_SEED_OFF, 2 * n + 1);
+	if (!d_mems || !d_mems_tmp || !d_nvu || !d_seed_cnt || !d_seed_off) { err = "device stages: out of device memory"; return false; }
+	fs.mems = d_mems; fs.fill = true;
+	be.for_each(2 * n, fs, 1);
+	// ---- C
+	be.zero(d_seed_cnt + 2 * n, 4);
+	be.for_each(n, FnMerge{d_mem_off, d_mems, d_mems_tmp, d_flags, d_nvu, d_seed_cnt}, 2);
+	be.scan(d_seed_cnt, d_seed_off, 2 * n + 1);
+	be.d2h(out.seed_off.data(), d_seed_off, (2 * n + 1) * 4);
+	be.d2h(out.flags.data(), d_flags, n);
+	uint64_t probes = 0;
+	be.d2h(&probes, d_probes, 8);
+	be.sync();
+	out.probes = probes;
+	const size_t n_seeds = out.seed_off[2 * n];
+	DevSeed *d_seeds = be.template buf<DevSeed>(SL_SEEDS, n_seeds + 1), *d_seeds_tmp = be.template buf<DevSeed>(SL_SEEDS_TMP, n_seeds + 1);
+	float *d_dist = be.template buf<float>(SL_DIST, n_seeds + 1);
+	int32_t *d_pre = be.template buf<int32_t>(SL_PRE, n_seeds + 1);
+	const size_t P = n + 1;
+	uint32_t *d_plan_cnt = be.template buf<uint32_t>(SL_PLAN_CNT, PLAN_FIELDS * P), *d_plan_off = be.template buf<uint32_t>(SL_PLAN_OFF, PLAN_FIELDS * P);
+	if (!d_seeds || !d_seeds_tmp || !d_dist || !d_pre || !d_plan_cnt || !d_plan_off) { err = "device stages: out of device memory"; return false; }
+	be.for_each(n, FnChain{d_mem_off, d_nvu, d_seed_off, d_mems, d_pos, ix.posp, d_flags, d_seeds, d_seeds_tmp, d_dist, d_pre}, 2);
+	out.seeds.resize(n_seeds); out.dist.resize(n_seeds); out.pre.resize(n_seeds);
+	be.d2h(out.seeds.data(), d_seeds, n_seeds * sizeof(DevSeed));
+	be.d2h(out.dist.data(), d_dist, n_seeds * 4);
+	be.d2h(out.pre.data(), d_pre, n_seeds * 4);
+	// ---- D: count, offsets, fill
+	int cap = 16;
+	for (;;) {                                                     // (again with more room if a ksw CIGAR does not fit `cap` words)
+		be.zero(d_plan_cnt, PLAN_FIELDS * P * 4);
+		FnPlan fp{in.scores, rf, d_reads, d_bits, d_seed_off, d_seeds, d_dist, d_pre, n, d_plan_cnt, d_plan_off,
+		          nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, (uint32_t)cap, false};
+		be.for_each(n, fp, 3);
+		for (int f = 0; f < PLAN_FIELDS; ++f) be.scan(d_plan_cnt + f * P, d_plan_off + f * P, P);
+		uint32_t tot[PLAN_FIELDS];
+		for (int f = 0; f < PLAN_FIELDS; ++f) be.d2h(&tot[f], d_plan_off + f * P + n, 4);
+		be.d2h(out.cand_off.data(), d_plan_off, P * 4);
+		be.sync();
+		const size_t n_cand = tot[0], n_piece = tot[1], n_task = tot[2], q_bytes = tot[3], t_bytes = tot[4], n_cig = tot[5];
+		DevCand *d_cands = be.template buf<DevCand>(SL_CANDS, n_cand + 1);
+		DevPiece *d_pieces = be.template buf<DevPiece>(SL_PIECES, n_piece + 1);
+		int32_t *d_qlen = be.template buf<int32_t>(SL_QLEN, n_task + 1), *d_tlen = be.template buf<int32_t>(SL_TLEN, n_task + 1);
+		int64_t *d_qoff = be.template buf<int64_t>(SL_QOFF, n_task + 1), *d_toff = be.template buf<int64_t>(SL_TOFF, n_task + 1);
+		uint8_t *d_q = be.template buf<uint8_t>(SL_Q, q_bytes + 16), *d_t = be.template buf<uint8_t>(SL_T, t_bytes + 16);
+		int32_t *d_res = be.template buf<int32_t>(SL_RES, (n_task + 1) * 12);
+		uint32_t *d_kcig = be.template buf<uint32_t>(SL_KCIG, (n_task + 1) * (size_t)cap);
+		DevCigar *d_cigs = be.template buf<DevCigar>(SL_CIGS, n_cig + 1);
+		if (!d_cands || !d_pieces || !d_qlen || !d_tlen || !d_qoff || !d_toff || !d_q || !d_t || !d_res || !d_kcig || !d_cigs) { err = "device stages: out of device memory"; return false; }
+		fp.cands = d_cands; fp.pieces = d_pieces; fp.qlen = d_qlen; fp.tlen = d_tlen; fp.qoff = d_qoff; fp.toff = d_toff; fp.q = d_q; fp.t = d_t; fp.fill = true;
+		be.for_each(n, fp, 3);
+		unsigned long long *d_cells = (unsigned long long*)(d_misc + 4);
+		be.zero(d_cells, 8);
+		if (n_task) be.for_each(n_task, FnCells{d_qlen, d_tlen, 200, d_cells}, 5);
+		// ---- E
+		if (n_task && !be.ksw(n_task, d_q, d_qoff, d_qlen, d_t, d_toff, d_tlen, d_res, d_kcig, cap, err)) return false;
+		// ---- F1
+		be.zero(d_misc, 4);
+		if (n_cand) be.for_each(n_cand, FnResolve{d_cands, d_pieces, d_res, d_kcig, cap, d_reads, d_cigs, d_misc}, 4);
+		uint32_t overflow = 0;
+		uint64_t cells = 0;
+		be.d2h(&overflow, d_misc, 4);
+		be.d2h(&cells, d_cells, 8);
+		out.cands.resize(n_cand); out.cigs.resize(n_cig);
+		be.d2h(out.cands.data(), d_cands, n_cand * sizeof(DevCand));
+		be.d2h(out.cigs.data(), d_cigs, n_cig * sizeof(DevCigar));
+		be.sync();
+		if (!overflow) { out.n_tasks = n_task; out.n_cells = cells; break; }
+		cap *= 4;
+	}
+	return true;
+}
+
+// ---- the link-time service (CUDA in the product library, the host backend in tests/emul)
+struct StageService;
+StageService *stage_service_create(const DebgaIndex &idx, SeedService *seeds, void *ksw_ctx, int device, std::string &err);
+void stage_service_destroy(StageService *s);
+void stage_service_set_scoring(StageService *s, const AlnScores &o, int zdrop);   // ksw parameters of stage E (copy_option, RR:817-827)
+bool stage_service_run(StageService *s, const DevStageIn &in, DevStageOut &out, std::string &err);
+
+} // namespace pansvr

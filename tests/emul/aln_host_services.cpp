@@ -11,6 +11,7 @@
 
 #include "../../include/pansvr_b200.h"
 #include "../../pansvr_b200/csrc/aln/pipeline.hpp"
+#include "../../pansvr_b200/csrc/aln/stages_run.hpp"
 
 namespace pansvr {
 
@@ -44,6 +45,56 @@ bool seed_service_run(SeedService *s, SeedBatch &b, std::string &)
 	return true;
 }
 
+// ---- host backend of the device stages (stages_run.hpp): the same functors, stepped by a loop over plain memory
+struct HostBackend {
+	void *p[SL_COUNT]; size_t cap[SL_COUNT];
+	pansvr_ksw_params_t kp; int8_t mat[25];
+	HostBackend() { for (int i = 0; i < SL_COUNT; ++i) { p[i] = nullptr; cap[i] = 0; } }
+	~HostBackend() { for (int i = 0; i < SL_COUNT; ++i) free(p[i]); }
+	template <class T> T *buf(int slot, size_t n)
+	{
+		const size_t bytes = n * sizeof(T) + 64;
+		if (bytes > cap[slot]) { free(p[slot]); p[slot] = malloc(bytes); cap[slot] = bytes; }
+		return (T*)p[slot];
+	}
+	void h2d(void *d, const void *h, size_t bytes) { if (bytes) memcpy(d, h, bytes); }
+	void d2h(void *h, const void *d, size_t bytes) { if (bytes) memcpy(h, d, bytes); }
+	void zero(void *d, size_t bytes) { if (bytes) memset(d, 0, bytes); }
+	void sync() {}
+	template <class F> void for_each(size_t n, const F &f, int) { for (size_t i = 0; i < n; ++i) f(i); }
+	void scan(const uint32_t *in, uint32_t *out, size_t n) { uint32_t run = 0; for (size_t i = 0; i < n; ++i) { const uint32_t v = in[i]; out[i] = run; run += v; } }
+	bool ksw(size_t n, const uint8_t *q, const int64_t *qoff, const int32_t *qlen, const uint8_t *t, const int64_t *toff, const int32_t *tlen,
+	         int32_t *res, uint32_t *cig, int cigar_cap, std::string &err)
+	{
+		int64_t qb = 0, tb = 0;
+		for (size_t i = 0; i < n; ++i) { qb = std::max<int64_t>(qb, qoff[i] + qlen[i]); tb = std::max<int64_t>(tb, toff[i] + tlen[i]); }
+		if (pansvr_ksw_extd2_batch((pansvr_ksw_ctx*)1, (int64_t)n, q, qb, qoff, qlen, t, tb, toff, tlen, &kp, res, cig, cigar_cap) != 0) { err = pansvr_last_error(); return false; }
+		return true;
+	}
+};
+
+struct StageService { HostBackend be; IndexView view; const uint64_t *pos; RefView rf; };
+
+StageService *stage_service_create(const DebgaIndex &idx, SeedService *seeds, void *, int, std::string &)
+{
+	StageService *s = new StageService();
+	s->view = seeds->view; s->pos = idx.pos.data(); s->rf.ref_seq = idx.ref_seq.data();
+	return s;
+}
+void stage_service_destroy(StageService *s) { delete s; }
+void stage_service_set_scoring(StageService *s, const AlnScores &o, int zdrop)
+{
+	HostBackend &be = s->be;
+	const int8_t m = (int8_t)o.match, x = (int8_t)-o.mismatch;
+	for (int a = 0, k = 0; a < 5; ++a) for (int b = 0; b < 5; ++b, ++k) be.mat[k] = (a == 4 || b == 4) ? 0 : (a == b ? m : x);
+	be.kp.m = 5; be.kp.mat = be.mat; be.kp.gapo = (int8_t)o.gap_open; be.kp.gape = (int8_t)o.gap_ex; be.kp.gapo2 = (int8_t)o.gap_open2; be.kp.gape2 = (int8_t)o.gap_ex2;
+	be.kp.w = 200; be.kp.zdrop = (uint16_t)zdrop; be.kp.end_bonus = -1; be.kp.flag = 0;
+}
+bool stage_service_run(StageService *s, const DevStageIn &in, DevStageOut &out, std::string &err)
+{
+	return run_device_stages(s->be, s->view, s->pos, s->rf, in, out, err);
+}
+
 } // namespace pansvr
 
 // ---- ksw through the oracle
@@ -63,6 +114,7 @@ static bool load_oracle()
 	g_cells = (cells_fn)dlsym(h, "ksw_extd2_oracle_cells");
 	return g_batch && g_cells;
 }
+extern "C" const char *pansvr_last_error(void);
 extern "C" {
 const char *pansvr_last_error(void) { return g_err.c_str(); }
 int pansvr_ksw_create(int, pansvr_ksw_ctx **out) { *out = (pansvr_ksw_ctx*)1; return load_oracle() ? 0 : PANSVR_E_CUDA; }

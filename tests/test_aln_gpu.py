@@ -2,6 +2,7 @@
 host replay), called through the C ABI, must write the same SAM as the reference's `panSVR fc_aln -t 1 -S` run on the same
 box on the same synthetic inputs (byte for byte, main and `-p` outputs)."""
 import os
+import subprocess
 
 import pytest
 
@@ -10,6 +11,7 @@ from oracle import synth_pipeline as sp
 from tests.alntest_util import DATASETS, get_demo, first_diff, golden, need_ref_tools, read
 
 pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 @pytest.mark.parametrize("name", list(DATASETS))
@@ -65,3 +67,29 @@ def test_command_line_and_block_boundaries():
         assert read(mb) == read(rb)
     finally:
         pass
+
+
+@pytest.mark.parametrize("name", ["demo", "multi_allele", "tandem_repeats", "shared_element", "chroms_250bp"])
+def test_device_stages_equal_host_stepped_stages(name, tmp_path):
+    """Stage-level differential (SURVEY.md 4 ii): what the CUDA stages A..F1 hand back for a block -- STR flags, MEM counts, the
+    sorted seeds and chain tables of every strand, every candidate with its score and final CIGAR -- equals, byte for byte, what the
+    same stage functions produce when stepped on the host (tests/emul), whose SAM in turn equals the reference's (CPU tests)."""
+    need_ref_tools()
+    demo = get_demo(name)
+    emul = os.path.join(ROOT, "tests", "emul")
+    subprocess.check_call(["make", "-s", "-C", emul, os.path.join(emul, "fc_aln_emul")])
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle"), os.path.join(ROOT, "oracle", "libksw_oracle.so")])
+    env = dict(os.environ, PANSVR_DUMP_STAGES=str(tmp_path / "emul"), PANSVR_ORACLE_SO=os.path.join(ROOT, "oracle", "libksw_oracle.so"))
+    subprocess.check_call([os.path.join(emul, "fc_aln_emul"), "-t", "2", "-S", "-o", str(tmp_path / "e.sam"), "-p", str(tmp_path / "eo.sam"),
+                           demo.data.index_dir, demo.data.reads_fq, demo.data.header_sam], env=env, stderr=subprocess.DEVNULL)
+    os.environ["PANSVR_DUMP_STAGES"] = str(tmp_path / "cuda")
+    try:
+        ctx = aln.AlnContext(demo.data.index_dir, demo.data.header_sam, threads=2)
+        ctx.align_fastq(read(demo.data.reads_fq))
+        st = ctx.stats()
+        ctx.close()
+    finally:
+        del os.environ["PANSVR_DUMP_STAGES"]
+    a, b = read(str(tmp_path / "cuda.0")), read(str(tmp_path / "emul.0"))
+    assert len(a) > 64 and a == b
+    assert st["stage_kernel_ms"] > 0 and st["seed_kernel_ms"] > 0 and st["seed_probes"] > 0
