@@ -1138,7 +1138,7 @@ AlnPipeline::StreamState AlnPipeline::export_streams()
 	std::unique_lock<std::mutex> lk(turn_m_);
 	turn_cv_.wait(lk, [&]() { return replay_turn_ == seq_issued_; });
 	StreamState s;
-	memset(&s, 0, sizeof s);
+	memset((void*)&s, 0, sizeof s);
 	s.magic = 0x70535652u;
 	s.rand = rand_; s.rand_r[0] = rand_r_[0]; s.rand_r[1] = rand_r_[1];
 	return s;

@@ -164,6 +164,7 @@ constexpr int N_VARIANTS = V_FAST0 + 10;
 
 struct pansvr_ksw_ctx {
 	int device = 0, sm_count = 0;
+	int smem_optin = 227 * 1024;      // cudaDevAttrMaxSharedMemoryPerBlockOptin
 	cudaStream_t stream = nullptr;
 	cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
 	DevBuf qseq, tseq, qoff, toff, qlen, tlen, res, cigar, order, counters, tb, gscratch;
@@ -176,6 +177,15 @@ struct pansvr_ksw_ctx {
 namespace {
 
 struct Shape { int rows, team; };
+
+// Dynamic shared memory of a team-kernel launch whose longest query is `qlen` (launch_team_wc): a long query against a
+// narrow band (few lanes per alignment, so many alignments and query copies per warp) can exceed what a CTA may have; such
+// tasks go to the generic kernel instead.
+inline bool team_fits(int team, int qlen, int smem_optin)
+{
+	const long per_cta = ((long)kswteam::team_smem_bytes(team, qlen) * (32 / team) + 32 * 32) * WARPS_PER_CTA + 512;
+	return per_cta <= (long)smem_optin;
+}
 
 // Builds ctx->h_order (task ids grouped by kernel variant, most anti-diagonals first inside a
 // group) and returns per-variant [begin,end) plus the largest row count / query length per variant.
@@ -195,7 +205,7 @@ void plan_batch(pansvr_ksw_ctx *ctx, const kswhost::Plan &pl, int64_t n, const i
 		while (i < n && qlen[i] == q0 && tlen[i] == t0) ++i;
 		if (i == n && !pl.trivial && q0 > 0 && t0 > 0 && pl.fast_params && q0 <= 8000) {
 			const int team = kswhost::pick_team(q0, t0, w);
-			if (team != 0) {
+			if (team != 0 && team_fits(team, q0, ctx->smem_optin)) {
 				const bool wrap = !pl.nowrap_ok || kswhost::band_clips(q0, t0, w);
 				int lg = 0;
 				while ((2 << lg) < team) ++lg;
@@ -233,7 +243,7 @@ void plan_batch(pansvr_ksw_ctx *ctx, const kswhost::Plan &pl, int64_t n, const i
 				} else sh = it->second;
 				last_key = key; last = sh;
 			}
-			if (!pl.fast_params || sh.team == 0 || ql > 8000) v = V_GENERIC;
+			if (!pl.fast_params || sh.team == 0 || ql > 8000 || !team_fits(sh.team, ql, ctx->smem_optin)) v = V_GENERIC;
 			else {
 				const bool wrap = !pl.nowrap_ok || kswhost::band_clips(ql, tl, w);
 				int lg = 0;
@@ -387,6 +397,7 @@ int pansvr_ksw_create(int device, pansvr_ksw_ctx **out)
 	if (prop.major < 10) return fail(PANSVR_E_CUDA, std::string("device is not sm_100 class: ") + prop.name);
 	pansvr_ksw_ctx *c = new pansvr_ksw_ctx();
 	c->device = device; c->sm_count = prop.multiProcessorCount;
+	if (cudaDeviceGetAttribute(&c->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device) != cudaSuccess) c->smem_optin = 227 * 1024;
 	memset(&c->stats, 0, sizeof(c->stats));
 	CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
 	for (auto &e : c->ev) CU(cudaEventCreate(&e));

@@ -150,3 +150,21 @@ def test_config2_full_size_properties(ksw_ctx):
     # determinism: a second pass gives the same bytes
     res2, cig2 = ksw_ctx.extd2_batch(b, cigar_cap=16)
     assert np.array_equal(res, res2) and np.array_equal(cig, cig2)
+
+
+def test_long_query_narrow_band_goes_generic(ksw_ctx):
+    """a long query against a tiny target / narrow band picks a narrow team, whose shared memory (one query copy per
+    alignment of the warp) would exceed the per-CTA limit; the planner must route such tasks to the generic kernel, not fail."""
+    rng = np.random.default_rng(91)
+    n = 24
+    qlen = rng.integers(4000, 8001, n).astype(np.int32)
+    tlen = rng.integers(1, 17, n).astype(np.int32)
+    qoff = np.concatenate([[0], np.cumsum(qlen[:-1])]).astype(np.int64)
+    toff = np.concatenate([[0], np.cumsum(tlen[:-1])]).astype(np.int64)
+    qseq = rng.integers(0, 4, int(qlen.sum()), dtype=np.uint8)
+    tseq = rng.integers(0, 4, int(tlen.sum()), dtype=np.uint8)
+    for w in (3, 15, 47):
+        b = synth.KswBatch(qseq, qoff, qlen, tseq, toff, tlen, synth.KswParams(w=w, zdrop=400, flag=0), f"long query w={w}")
+        res, cig = ksw_ctx.extd2_batch(b, cigar_cap=64)
+        r0, c0, _ = pyoracle.run(b, "oracle", threads=4, cigar_cap=64)
+        assert_same(r0, c0, res, cig, b.name)
