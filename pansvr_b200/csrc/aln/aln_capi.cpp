@@ -216,7 +216,7 @@ int pansvr_aln_create(const char *index_dir, const char *header_sam, const pansv
 	c->stages = stage_service_create(c->idx, c->seeds, c->ksw, device, err);
 	if (!c->stages) { g_aln_err = err; seed_service_destroy(c->seeds); pansvr_ksw_destroy(c->ksw); delete c; return PANSVR_E_CUDA; }
 	lap("index upload");
-	c->pipe = new AlnPipeline(c->idx, c->opt, c->seeds, c->ksw, c->stages);
+	c->pipe = new AlnPipeline(c->idx, c->opt, c->seeds, c->ksw, c->stages, device);
 	c->bam_hdr.parse(c->idx.header_text);
 	lap("pipeline");
 	*out = c;

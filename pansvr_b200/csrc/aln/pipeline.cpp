@@ -16,9 +16,12 @@
 
 namespace pansvr {
 
-struct AlnPipeline::DevBuffers {                                  // host side of one block's trip through the device stages
+struct AlnPipeline::DevBuffers {                                  // one block's trip through the device stages
+	StageService *svc = nullptr; bool owned = false;
 	HostVec<DevRead> reads;
+	HostVec<DevOri> ori;
 	HostVec<uint8_t> seq;                                         // the bases of the block's device reads, gathered (pinned)
+	HostVec<int8_t> win;
 	DevStageOut out;
 };
 
@@ -1102,23 +1105,69 @@ struct AlnPipeline::Impl {
 		}
 		clip_or_unmapped = ops.empty() || clip >= 25;
 	}
+
+	// the `-p` records of a pair (RR:776-797): both originals, unless the pair turned out proper after all
+	void output_ori_pair(ReadState *se, const PE &pe, std::string &, std::string &ori, int min_filter_score)
+	{
+		if (!(pe.max_score <= min_filter_score && (int)se[0].ori.chr != -1 && (int)se[1].ori.chr != -1)) return;
+		bool clip[2] = {true, true};
+		const size_t ori_mark = ori.size();
+		for (int k = 0; k < 2; ++k) output_ori(se[k], ori, pe.max_score, clip[k]);
+		bool proper = pe.proper;
+		for (int k = 0; proper && k < 2; ++k) {
+			const Result *c = k == 0 ? pe.m1 : pe.m2;
+			if (!c) { proper = false; break; }
+			if (c->is_ori && clip[k]) proper = false;
+			if (proper && !c->is_ori) {
+				int ins = 0;
+				for (const CigarPath &ci : c->cigar) if (ci.type == 1) ins += ci.size;
+				if (c->cigar.empty() || ins >= 25) proper = false;
+			}
+		}
+		if (proper) ori.resize(ori_mark);                              // a proper pair after all: nothing goes to the -p file
+	}
 };
 
 // ================================================================================================ public
-AlnPipeline::AlnPipeline(const DebgaIndex &idx, const AlnOptions &o, SeedService *seeds, void *ksw_ctx, StageService *stages)
-	: opt(o), idx_(idx), seeds_(seeds), ksw_(ksw_ctx), stages_(stages), rand_(1)
+AlnPipeline::AlnPipeline(const DebgaIndex &idx, const AlnOptions &o, SeedService *seeds, void *ksw_ctx, StageService *stages, int device)
+	: opt(o), idx_(idx), seeds_(seeds), ksw_(ksw_ctx), stages_(stages), device_(device), rand_(1)
 {
 	if (opt.threads > 1) workers_ = new Workers(opt.threads);
 	if (getenv("PANSVR_HOST_STAGES")) stages_ = nullptr;          // differential runs: stages A, C, D on the host (the round-1 path)
 	if (stages_) {
 		AlnScores sc{opt.match, opt.mismatch, opt.gap_open, opt.gap_ex, opt.gap_open2, opt.gap_ex2};
 		stage_service_set_scoring(stages_, sc, opt.zdrop);
-		for (DevBuffers *&b : devbuf_) b = new DevBuffers();
+		DevBuffers *b = new DevBuffers();
+		b->svc = stages_;
+		dev_all_.push_back(b); dev_free_.push_back(b);
 	}
 	reset();
 }
 
-AlnPipeline::~AlnPipeline() { delete workers_; for (DevBuffers *b : devbuf_) delete b; }
+AlnPipeline::~AlnPipeline()
+{
+	delete workers_;
+	for (DevBuffers *b : dev_all_) { if (b->owned) stage_service_destroy(b->svc); delete b; }
+}
+
+AlnPipeline::DevBuffers *AlnPipeline::acquire_dev(std::string &err)
+{
+	{
+		std::lock_guard<std::mutex> lk(dev_pool_m_);
+		if (!dev_free_.empty()) { DevBuffers *b = dev_free_.back(); dev_free_.pop_back(); return b; }
+	}
+	StageService *svc = stage_service_create(idx_, seeds_, ksw_, device_, err);   // another block in flight: its own device state
+	if (!svc) return nullptr;
+	AlnScores sc{opt.match, opt.mismatch, opt.gap_open, opt.gap_ex, opt.gap_open2, opt.gap_ex2};
+	stage_service_set_scoring(svc, sc, opt.zdrop);
+	DevBuffers *b = new DevBuffers();
+	b->svc = svc; b->owned = true;
+	std::lock_guard<std::mutex> lk(dev_pool_m_);
+	dev_all_.push_back(b);
+	return b;
+}
+
+void AlnPipeline::release_dev(DevBuffers *b) { std::lock_guard<std::mutex> lk(dev_pool_m_); dev_free_.push_back(b); }
 
 // read statistics from the first comment of the input (load_reads, RR:134-148); must have run before two blocks are in flight
 void AlnPipeline::ensure_read_stats(const FastqRec &first)
@@ -1171,7 +1220,17 @@ void AlnPipeline::reset()
 	for (int i = 0; i < 2; ++i) rand_r_[i].reseed((unsigned)rand_.next());
 }
 
-bool AlnPipeline::align_block(const FastqRec *recs, size_t n_reads_in, BlockOutput &out, std::string &err, uint64_t seq)
+// The host path: every stage but seeding and ksw on the helper threads (round 1's pipeline).  It finishes what the device path
+// leaves to it -- pairs with 'N' or a lower-case 'n', pairs whose unipaths need random_r sampling, pairs whose rand() ties change
+// the outcome -- and, without a stage service, whole blocks.  With hooks, `recs` are the pairs left to it out of a larger block:
+// the in-order pass and the record text are merged with the device path's pairs in input order.
+struct BlockHooks {
+	const uint32_t *global_pair = nullptr;                            // pair k of `recs` is pair global_pair[k] of the whole block
+	std::function<void(uint64_t)> fast_until;                         // in-order work of the device path's pairs below this block index
+	std::function<bool(const std::function<void(size_t, std::string&, std::string&)>&, std::string&)> emit;   // record text of the whole block
+};
+
+bool AlnPipeline::align_block_host(const FastqRec *recs, size_t n_reads_in, BlockOutput &out, std::string &err, uint64_t seq, BlockHooks *H)
 {
 	Impl I(*this);
 	const size_t n_reads = n_reads_in & ~(size_t)1, n_pairs = n_reads / 2;
@@ -1205,10 +1264,10 @@ bool AlnPipeline::align_block(const FastqRec *recs, size_t n_reads_in, BlockOutp
 	out.ori.resize((size_t)std::max(1, opt.threads));
 	for (std::string &x : out.sam) x.clear();
 	for (std::string &x : out.ori) x.clear();
-	if (n_pairs == 0) return true;
+	if (n_pairs == 0 && !H) return true;
 	double t0 = now();
 
-	ensure_read_stats(recs[0]);
+	if (n_pairs) ensure_read_stats(recs[0]);
 
 	// ---- stage A (parallel over reads; reads of a pair with an 'N' are left for the replay, see below)
 	const int T = std::max(1, opt.threads);
@@ -1310,103 +1369,6 @@ bool AlnPipeline::align_block(const FastqRec *recs, size_t n_reads_in, BlockOutp
 	};
 	// a real read with N is not encoded here (its bases depend on the draws); the N-free mate of such a read is
 	for (size_t i = 0; i < n_all; ++i) { ReadState &r = rs[i]; r.batched = !(r.skip || r.has_n || r.read_l < LEN_KMER); }
-	// ---- device path: stages A..F1 of every read state the host does not have to keep run on the GPU in one trip
-	// (stages_run.hpp); what comes back are the sorted seeds and chain tables of both strands and the candidate alignments
-	// (score + final CIGAR) of every chain end that can still be chosen.  Reads the device hands back (a unipath with more than
-	// 500 positions: expand_seed draws from random_r) and reads with a lower-case 'n' go through the host stages below.
-	if (stages_) {
-		DevBuffers &db = *devbuf_[seq & 1];
-		std::vector<uint32_t> ids;
-		ids.reserve(n_all);
-		for (size_t i = 0; i < n_all; ++i) {
-			const ReadState &r = rs[i];
-			const size_t real = r.var_of >= 0 ? (size_t)r.var_of : i;
-			if (r.batched && !lower_n[real]) ids.push_back((uint32_t)i);
-		}
-		const size_t nd = ids.size();
-		db.reads.resize(nd);
-		size_t seq_bytes = 0, words = 0, list_bytes = 0;
-		for (size_t k = 0; k < nd; ++k) {
-			const ReadState &r = rs[ids[k]];
-			DevRead &d = db.reads[k];
-			d.seq_off = (uint32_t)seq_bytes; d.len = (uint32_t)r.read_l; d.var_code = r.var_of >= 0 ? r.var_code : 0u;
-			d.bits_off = (uint32_t)words; d.list_off = (uint32_t)list_bytes;
-			seq_bytes += (size_t)r.read_l; words += 2 * (size_t)((r.read_l >> 5) + 2); list_bytes += 2 * (size_t)(r.read_l - LEN_KMER + 1);
-		}
-		if (seq_bytes >= 0xffffffffull || words >= 0xffffffffull || list_bytes >= 0xffffffffull) { err = "block too large for the device stages (cut it into smaller blocks)"; return false; }
-		db.seq.resize(seq_bytes + 1);
-		parallel(nd, [&](size_t b, size_t e, int) { for (size_t k = b; k < e; ++k) memcpy(db.seq.data() + db.reads[k].seq_off, rs[ids[k]].rec->seq, db.reads[k].len); });
-		lap("device read table + gather");
-		add_time(0, now() - t0); t0 = now();
-		DevStageIn in;
-		in.text = db.seq.data(); in.text_bytes = seq_bytes; in.reads = db.reads.data(); in.n_reads = nd; in.bits_words = words; in.list_bytes = list_bytes;
-		in.scores = AlnScores{opt.match, opt.mismatch, opt.gap_open, opt.gap_ex, opt.gap_open2, opt.gap_ex2};
-		{
-			std::lock_guard<std::mutex> dev(dev_m_);
-			if (nd && !stage_service_run(stages_, in, db.out, err)) return false;
-		}
-		add_time(1, now() - t0); t0 = now();
-		const DevStageOut &o = db.out;
-		if (const char *dump = getenv("PANSVR_DUMP_STAGES")) {                  // tests: what the device stages returned, for the differential
-			const std::string path = std::string(dump) + "." + std::to_string(seq);   // between the CUDA backend and the host-stepped one
-			if (FILE *f = fopen(path.c_str(), "wb")) {
-				const uint64_t hdr[4] = {nd, nd ? o.seed_off[2 * nd] : 0, o.cands.size(), nd ? o.mem_off[2 * nd] : 0};
-				fwrite(hdr, 8, 4, f);
-				if (nd) {
-					fwrite(o.flags.data(), 1, nd, f); fwrite(o.mem_off.data(), 4, 2 * nd + 1, f); fwrite(o.seed_off.data(), 4, 2 * nd + 1, f);
-					fwrite(o.seeds.data(), sizeof(DevSeed), o.seeds.size(), f); fwrite(o.dist.data(), 4, o.dist.size(), f); fwrite(o.pre.data(), 4, o.pre.size(), f);
-					fwrite(o.cand_off.data(), 4, nd + 1, f);
-					for (size_t c = 0; c < o.cands.size(); ++c) {
-						DevCand cd = o.cands[c];
-						fwrite(o.cigs.data() + cd.cig_off, sizeof(DevCigar), cd.n_cig, f);
-						cd.piece_off = cd.cig_off = cd.cig_cap = 0;                     // (layout details that may differ between backends)
-						fwrite(&cd, sizeof cd, 1, f);
-					}
-				}
-				fclose(f);
-			}
-		}
-		static_assert(sizeof(UniSeed) == sizeof(DevSeed) && sizeof(CigarPath) == sizeof(DevCigar), "device records mirror the host's");
-		std::atomic<uint64_t> kept(0);
-		if (nd) parallel(nd, [&](size_t b, size_t e, int) {
-			uint64_t k_mems = 0;
-			for (size_t k = b; k < e; ++k) {
-				ReadState &r = rs[ids[k]];
-				r.dev_index = (int64_t)k;
-				if (o.flags[k] & ST_FLAG_NEEDS_RAND) continue;             // stays `batched`: host stages below
-				r.dev = true; r.batched = false;
-				r.is_str = (o.flags[k] & ST_FLAG_STR) != 0;
-				k_mems += o.mem_off[2 * k + 2] - o.mem_off[2 * k];
-				for (int s = 0; s < 2; ++s) {
-					const uint32_t sb0 = o.seed_off[2 * k + s], n = o.seed_off[2 * k + s + 1] - sb0;
-					Graph &g = r.g[s];
-					g.is_str = r.is_str;
-					g.v.resize(n); g.path.resize(n);
-					if (n) memcpy((void*)g.v.data(), o.seeds.data() + sb0, (size_t)n * sizeof(UniSeed));
-					for (uint32_t x = 0; x < n; ++x) { g.path[x].dist = o.dist[sb0 + x]; g.path[x].pre_node = o.pre[sb0 + x]; g.path[x].used = 0; }
-				}
-				r.node_aln.clear();
-				for (uint32_t c = o.cand_off[k]; c < o.cand_off[k + 1]; ++c) {
-					const DevCand &cd = o.cands[c];
-					r.node_aln.emplace_back((uint64_t)cd.strand << 32 | cd.node, NodeAln());
-					NodeAln &na = r.node_aln.back().second;
-					na.planned = na.resolved = true;
-					na.fixed_score = cd.fixed_score; na.read_begin_alignment = cd.read_begin_alignment;
-					na.align_score = cd.align_score; na.cigar_ok = cd.cigar_ok != 0;
-					na.cigar.resize(cd.n_cig);
-					if (cd.n_cig) memcpy((void*)na.cigar.data(), o.cigs.data() + cd.cig_off, (size_t)cd.n_cig * sizeof(CigarPath));
-				}
-			}
-			kept += k_mems;
-		});
-		{
-			std::lock_guard<std::mutex> lk(stats_m_);
-			stats.mems += kept.load(); stats.ksw_tasks += o.n_tasks; stats.ksw_cells += o.n_cells;
-			stats.dev.add(o.dev); stats.dev.seed_probes += (int64_t)o.probes;
-			db.out.dev = DevCounters();
-		}
-		lap("read states from the device results");
-	}
 	SeedBatch &sb = seed_main_[seq & 1];
 	sb.clear();
 	{
@@ -1670,7 +1632,9 @@ bool AlnPipeline::align_block(const FastqRec *recs, size_t n_reads_in, BlockOutp
 			__builtin_prefetch(r.result.data());
 		}
 	};
-	for (size_t ri = 0; ri < redo_list.size(); ++ri) {
+	for (size_t ri = 0; ri <= redo_list.size(); ++ri) {
+		if (H) H->fast_until(ri < redo_list.size() ? (uint64_t)H->global_pair[redo_list[ri]] : ~(uint64_t)0);   // the device path's pairs before this one
+		if (ri == redo_list.size()) break;
 		const size_t pi = redo_list[ri];
 		if (redo[pi] >= 4) { prefetch_state(ri + 8); prefetch_arrays(ri + 3); ++n_full; }
 		++n_redo;
@@ -1741,40 +1705,245 @@ bool AlnPipeline::align_block(const FastqRec *recs, size_t n_reads_in, BlockOutp
 		        t_probe, n_redo, n_pairs, n_full, now() - t0 - t_probe, n_var, n_in_order);
 	const double t_text = now();
 	// ---- SAM text of every pair (no random numbers involved any more: parallel)
-	parallel(n_pairs, [&](size_t pb, size_t pe_, int t) {                 // chunk t writes its pairs, in order, into buffer t
+	auto text_pair = [&](size_t pi, std::string &sam, std::string &ori) {
+		ReadState *se = &rs[2 * pi];
+		const Impl::PE &pe = pes[pi];
+		if (pe.gain)
+			for (int k = 0; k < 2; ++k) I.output_bam(se[k], sam, k == 0, pe.cur_isize);
+		I.output_ori_pair(se, pe, sam, ori, min_filter_score_);
+	};
+	if (H) { if (!H->emit(text_pair, err)) return false; }
+	else parallel(n_pairs, [&](size_t pb, size_t pe_, int t) {            // chunk t writes its pairs, in order, into buffer t
 		// the string headers of neighbouring chunks share cache lines and every append updates the length: work on locals
 		std::string sam, ori;
 		sam.swap(out.sam[(size_t)t]); ori.swap(out.ori[(size_t)t]);
 		sam.reserve((pe_ - pb) * 2 * (2 * (size_t)opt.read_len + 400));
-		for (size_t pi = pb; pi < pe_; ++pi) {
-			ReadState *se = &rs[2 * pi];
-			const Impl::PE &pe = pes[pi];
-			if (pe.gain)
-				for (int k = 0; k < 2; ++k) I.output_bam(se[k], sam, k == 0, pe.cur_isize);
-			if (pe.max_score <= min_filter_score_ && (int)se[0].ori.chr != -1 && (int)se[1].ori.chr != -1) {   // RR:776-797
-				bool clip[2] = {true, true};
-				const size_t ori_mark = ori.size();
-				for (int k = 0; k < 2; ++k) I.output_ori(se[k], ori, pe.max_score, clip[k]);
-				bool proper = pe.proper;
-				for (int k = 0; proper && k < 2; ++k) {
-					const Result *c = k == 0 ? pe.m1 : pe.m2;
-					if (!c) { proper = false; break; }
-					if (c->is_ori && clip[k]) proper = false;
-					if (proper && !c->is_ori) {
-						int ins = 0;
-						for (const CigarPath &ci : c->cigar) if (ci.type == 1) ins += ci.size;
-						if (c->cigar.empty() || ins >= 25) proper = false;
-					}
-				}
-				if (proper) ori.resize(ori_mark);                          // a proper pair after all: nothing goes to the -p file
-			}
-		}
+		for (size_t pi = pb; pi < pe_; ++pi) text_pair(pi, sam, ori);
 		sam.swap(out.sam[(size_t)t]); ori.swap(out.ori[(size_t)t]);
 	});
 	add_time(5, now() - t0);
 	if (timing) fprintf(stderr, "[timing]   F/record text %.3f s\n", now() - t_text);
 	if (getenv("PANSVR_TIMING")) { double a = 0; for (int i = 0; i < 6; ++i) a += stats.t_stage[i]; fprintf(stderr, "[timing] align_block body done, stages A-F %.3f s\n", a); }
 	return true;
+}
+
+
+// ================================================================================================ the device path
+namespace {
+
+// parse_ori_mapping_rst (RRH:392-429) without touching the comment: the numbers and flags of the original alignment
+void parse_ori_light(const FastqRec &rec, int match, DevOri &o)
+{
+	const char *c = rec.comment; const size_t n = rec.comment_l;
+	const char *tok[10]; size_t tok_l[10];
+	int nt = 0;
+	size_t i = 0;
+	while (nt < 10 && i < n) {
+		while (i < n && c[i] == '_') ++i;
+		if (i >= n) break;
+		size_t j = i;
+		while (j < n && c[j] != '_') ++j;
+		tok[nt] = c + i; tok_l[nt] = j - i; ++nt;
+		i = j + 1;
+	}
+	auto num = [&](int k) -> int {
+		if (k >= nt) return 0;
+		const char *p = tok[k], *e = p + tok_l[k];
+		while (p < e && (*p == ' ' || *p == '\t')) ++p;
+		bool neg = false;
+		if (p < e && (*p == '-' || *p == '+')) { neg = *p == '-'; ++p; }
+		long v = 0;
+		while (p < e && *p >= '0' && *p <= '9') v = v * 10 + (*p++ - '0');
+		return (int)(neg ? -v : v);
+	};
+	o.chr = (uint32_t)num(0); o.ref_bg = (uint32_t)num(1); o.read_bg = (uint32_t)num(2); o.align_score = (uint32_t)num(3); o.mapq = (uint8_t)num(4);
+	o.direction = (nt > 9 && tok_l[9] > 0 && tok[9][0] == 'F') ? FORWARD : REVERSE;
+	o.unmapped = (nt > 9 && tok_l[9] > 1 && tok[9][1] == 'Y') || o.chr > 24;                       // RR:413
+	if (o.ref_bg >= (uint32_t)I32MAX) o.ref_bg = 1;
+	o.skip = !o.unmapped && o.align_score == (uint32_t)((int)rec.seq_l * match);                  // RR:414
+}
+
+} // namespace
+
+bool AlnPipeline::align_block(const FastqRec *recs, size_t n_reads_in, BlockOutput &out, std::string &err, uint64_t seq)
+{
+	const size_t n_pairs = n_reads_in / 2;
+	if (!stages_ || n_pairs == 0) return align_block_host(recs, n_reads_in, out, err, seq, nullptr);
+	Impl I(*this);
+	const DebgaIndex &idx = idx_;
+	auto add_time = [&](int stage, double dt) { std::lock_guard<std::mutex> lk(stats_m_); stats.t_stage[stage] += dt; };
+	double t0 = now();
+	ensure_read_stats(recs[0]);
+	DevBuffers *db = acquire_dev(err);
+	if (!db) return false;
+	struct Release { AlnPipeline &P; DevBuffers *b; ~Release() { P.release_dev(b); } } release{*this, db};
+	// ---- which pairs the device takes: no 'N' (its substitution draws rand()), no lower-case 'n' (code 4 spills into the packed
+	// neighbour).  Read 2k, 2k+1 of the device table are the mates of the k-th such pair.
+	std::vector<uint8_t> host_pair(n_pairs, 0);
+	parallel(n_pairs, [&](size_t b, size_t e, int) {
+		for (size_t pi = b; pi < e; ++pi) {
+			bool host = false;
+			for (int k = 0; k < 2; ++k) { const FastqRec &r = recs[2 * pi + k]; host |= memchr(r.seq, 'N', r.seq_l) != nullptr || memchr(r.seq, 'n', r.seq_l) != nullptr; }
+			host_pair[pi] = host;
+		}
+	});
+	std::vector<uint32_t> fast;                                           // block indices of the device path's pairs
+	fast.reserve(n_pairs);
+	for (size_t pi = 0; pi < n_pairs; ++pi) if (!host_pair[pi]) fast.push_back((uint32_t)pi);
+	const size_t nf = fast.size(), nd = 2 * nf;
+	db->reads.resize(nd); db->ori.resize(nd);
+	parallel(nf, [&](size_t b, size_t e, int) {
+		for (size_t k = b; k < e; ++k) for (int m = 0; m < 2; ++m) parse_ori_light(recs[2 * (size_t)fast[k] + m], opt.match, db->ori[2 * k + m]);
+	});
+	size_t seq_bytes = 0, words = 0, list_bytes = 0;
+	for (size_t t = 0; t < nd; ++t) {
+		const FastqRec &r = recs[2 * (size_t)fast[t >> 1] + (t & 1)];
+		DevRead &d = db->reads[t];
+		const bool seeded = !db->ori[t].skip && r.seq_l >= LEN_KMER;      // (not seeded: full-score original, RR:414, or shorter than a k-mer)
+		d.seq_off = (uint32_t)seq_bytes; d.len = seeded ? r.seq_l : 0u; d.var_code = 0; d.bits_off = (uint32_t)words; d.list_off = (uint32_t)list_bytes;
+		if (seeded) { seq_bytes += r.seq_l; words += 2 * (size_t)((r.seq_l >> 5) + 2); list_bytes += 2 * (size_t)(r.seq_l - LEN_KMER + 1); }
+	}
+	if (seq_bytes >= 0xffffffffull || words >= 0xffffffffull || list_bytes >= 0xffffffffull) { err = "block too large for the device stages (cut it into smaller blocks)"; return false; }
+	db->seq.resize(seq_bytes + 1);
+	parallel(nd, [&](size_t b, size_t e, int) {
+		for (size_t t = b; t < e; ++t) if (db->reads[t].len) memcpy(db->seq.data() + db->reads[t].seq_off, recs[2 * (size_t)fast[t >> 1] + (t & 1)].seq, db->reads[t].len);
+	});
+	add_time(0, now() - t0); t0 = now();
+	// ---- first trip: stages A..F1 and the probe of stage F
+	DevStageIn in;
+	in.text = db->seq.data(); in.text_bytes = seq_bytes; in.reads = db->reads.data(); in.n_reads = nd; in.bits_words = words; in.list_bytes = list_bytes;
+	in.scores = AlnScores{opt.match, opt.mismatch, opt.gap_open, opt.gap_ex, opt.gap_open2, opt.gap_ex2};
+	in.ori = db->ori.data(); in.pair_opts = PairOpts{opt.isize_max, opt.isize_min, opt.read_len};
+	const char *dump = getenv("PANSVR_DUMP_STAGES");
+	in.want_tables = dump != nullptr;
+	if (nd && !stage_service_run(db->svc, in, db->out, err)) return false;
+	DevStageOut &o = db->out;
+	if (nd == 0) o.pair_probe.clear();
+	add_time(1, now() - t0); t0 = now();
+	if (dump) {                                                           // tests: what the device stages returned, for the differential
+		const std::string path = std::string(dump) + "." + std::to_string(seq);   // between the CUDA backend and the host-stepped one
+		if (FILE *f = fopen(path.c_str(), "wb")) {
+			const uint64_t hdr[4] = {nd, nd ? o.seed_off[2 * nd] : 0, o.cands.size(), nd ? o.mem_off[2 * nd] : 0};
+			fwrite(hdr, 8, 4, f);
+			if (nd) {
+				fwrite(o.flags.data(), 1, nd, f); fwrite(o.mem_off.data(), 4, 2 * nd + 1, f); fwrite(o.seed_off.data(), 4, 2 * nd + 1, f);
+				fwrite(o.seeds.data(), sizeof(DevSeed), o.seeds.size(), f); fwrite(o.dist.data(), 4, o.dist.size(), f); fwrite(o.pre.data(), 4, o.pre.size(), f);
+				fwrite(o.cand_off.data(), 4, nd + 1, f);
+				for (size_t c = 0; c < o.cands.size(); ++c) {
+					DevCand cd = o.cands[c];
+					fwrite(o.cigs.data() + cd.cig_off, sizeof(DevCigar), cd.n_cig, f);
+					cd.piece_off = cd.cig_off = cd.cig_cap = 0;
+					fwrite(&cd, sizeof cd, 1, f);
+				}
+				fwrite(o.pair_probe.data(), sizeof(DevProbe), o.pair_probe.size(), f);
+			}
+			fclose(f);
+		}
+	}
+	// ---- the pairs the host path finishes: those it kept, and those the device hands back
+	std::vector<uint32_t> host_list;
+	for (size_t k = 0; k < nf; ++k) if (o.pair_probe[k].redo == PR_REDO_HOST) host_pair[fast[k]] = 1;
+	for (size_t pi = 0; pi < n_pairs; ++pi) if (host_pair[pi]) host_list.push_back((uint32_t)pi);
+	std::vector<FastqRec> hrecs(2 * host_list.size());
+	for (size_t s = 0; s < host_list.size(); ++s) { hrecs[2 * s] = recs[2 * (size_t)host_list[s]]; hrecs[2 * s + 1] = recs[2 * (size_t)host_list[s] + 1]; }
+	db->win.resize(2 * nf + 2);
+	for (size_t t = 0; t < 2 * nf; ++t) db->win[t] = -1;
+	size_t cursor = 0;
+	uint64_t n_fast_done = 0;
+	BlockHooks H;
+	H.global_pair = host_list.data();
+	// in-order pass of the device path's pairs: advance the stream by a read's draws, redraw the pairing ties (RRH:553)
+	H.fast_until = [&](uint64_t upto) {
+		for (; cursor < nf && (uint64_t)fast[cursor] < upto; ++cursor) {
+			const DevProbe &pr = o.pair_probe[cursor];
+			if (pr.redo == 0 || pr.redo == PR_REDO_HOST) continue;
+			for (int k = 0, n = pr.draws0 + pr.draws1; k < n; ++k) rand_.next();
+			if (pr.redo == 2) {
+				int max_same = 1, wi = -1, wj = -1;
+				for (int k = 0; k < pr.ev_cnt; ++k) {
+					if (!((pr.tie_mask >> k) & 1)) { max_same = 1; wi = pr.ev_i[k]; wj = pr.ev_j[k]; }
+					else { ++max_same; if (rand_.next() % max_same == 0) { wi = pr.ev_i[k]; wj = pr.ev_j[k]; } }
+				}
+				db->win[2 * cursor] = (int8_t)wi; db->win[2 * cursor + 1] = (int8_t)wj;
+			}
+		}
+	};
+	H.emit = [&](const std::function<void(size_t, std::string&, std::string&)> &text_host, std::string &e2) -> bool {
+		double t1 = now();
+		// ---- second trip: the winners go up, primary / secondary / mate of every read come back
+		if (nf && !stage_service_finalize(db->svc, in.pair_opts, nf, db->win.data(), o, e2)) return false;
+		add_time(2, now() - t1); t1 = now();
+		std::vector<int32_t> slot_of(n_pairs, -1), fast_of(n_pairs, -1);
+		for (size_t s = 0; s < host_list.size(); ++s) slot_of[host_list[s]] = (int32_t)s;
+		for (size_t k = 0; k < nf; ++k) fast_of[fast[k]] = (int32_t)k;
+		std::atomic<uint64_t> done(0);
+		parallel(n_pairs, [&](size_t pb, size_t pe_, int t) {             // chunk t writes its pairs, in order, into buffer t
+			std::string sam, ori;
+			sam.swap(out.sam[(size_t)t]); ori.swap(out.ori[(size_t)t]);
+			sam.reserve((pe_ - pb) * 2 * (2 * (size_t)opt.read_len + 400));
+			uint64_t mine = 0;
+			for (size_t pi = pb; pi < pe_; ++pi) {
+				if (slot_of[pi] >= 0) { text_host((size_t)slot_of[pi], sam, ori); continue; }
+				// a pair of the device path: rebuild what output_BAM / output_ori_bam read of the handlers (RR:479-536, 656-717)
+				const size_t k = (size_t)fast_of[pi];
+				const DevPairFinal &pf = o.pfin[k];
+				++mine;
+				ReadState se[2];
+				Result prim[2], sec[2];
+				Impl::PE pe;
+				pe.max_score = pf.max_score; pe.cur_isize = pf.cur_isize; pe.gain = pf.gain != 0; pe.proper = pf.proper != 0;
+				for (int m = 0; m < 2; ++m) {
+					ReadState &r = se[m];
+					r.rec = &recs[2 * pi + m];
+					r.comment.assign(r.rec->comment, r.rec->comment_l);
+					r.read_l = (int)r.rec->seq_l;
+					I.parse_ori(r);
+					if (r.ori.chr > 24) r.ori_unmapped = true;
+					const DevFinal &f = o.fin[2 * k + m];
+					if (!(f.flags & FIN_PRIMARY)) continue;
+					Result *c;
+					if (f.flags & FIN_P_ORI) c = &r.ori;
+					else {
+						c = &prim[m];
+						c->is_ori = false; c->chr = f.p_chr; c->ref_bg = f.p_ref_bg; c->align_score = f.p_align; c->chain_score = f.p_chain;
+						c->mapq = (uint8_t)f.p_mapq; c->direction = (f.flags & FIN_P_FWD) ? FORWARD : REVERSE; c->cigar_ok = (f.flags & FIN_P_CIGAR_OK) != 0;
+						const DevCand &cd = o.cands[(size_t)f.p_cand];
+						c->cigar.resize(cd.n_cig);
+						if (cd.n_cig) memcpy((void*)c->cigar.data(), o.cigs.data() + cd.cig_off, (size_t)cd.n_cig * sizeof(CigarPath));
+					}
+					c->sv = f.p_sv >= 0 ? &idx.sv_info[(size_t)f.p_sv] : nullptr;
+					c->has_mate = (f.flags & FIN_HAS_MATE) != 0; c->mate_chr = f.mate_chr; c->mate_ref_bg = f.mate_ref_bg;
+					c->mate_sv = f.p_mate_sv >= 0 ? &idx.sv_info[(size_t)f.p_mate_sv] : nullptr;
+					(m == 0 ? pe.m1 : pe.m2) = c;
+					if (!pe.gain) continue;
+					r.primary = c;
+					if (f.flags & FIN_SECONDARY) {
+						Result &s2 = sec[m];
+						s2.chr = f.s_chr; s2.ref_bg = f.s_ref_bg; s2.read_bg = f.s_read_bg; s2.align_score = f.s_align;
+						s2.direction = (f.flags & FIN_S_FWD) ? FORWARD : REVERSE; s2.sv = f.s_sv >= 0 ? &idx.sv_info[(size_t)f.s_sv] : nullptr;
+						r.secondary = &s2;
+					}
+				}
+				if (pe.gain)
+					for (int m = 0; m < 2; ++m) I.output_bam(se[m], sam, m == 0, pe.cur_isize);
+				I.output_ori_pair(se, pe, sam, ori, min_filter_score_);
+			}
+			done += mine;
+			sam.swap(out.sam[(size_t)t]); ori.swap(out.ori[(size_t)t]);
+		});
+		n_fast_done = done.load();
+		add_time(5, now() - t1);
+		return true;
+	};
+	const bool ok = align_block_host(hrecs.data(), hrecs.size(), out, err, seq, &H);
+	if (ok) {
+		std::lock_guard<std::mutex> lk(stats_m_);
+		stats.reads += 2 * n_fast_done;
+		stats.mems += nd ? o.mem_off[2 * nd] : 0; stats.ksw_tasks += o.n_tasks; stats.ksw_cells += o.n_cells;
+		stats.dev.add(o.dev); stats.dev.seed_probes += (int64_t)o.probes;
+		o.dev = DevCounters();
+	}
+	return ok;
 }
 
 } // namespace pansvr

@@ -129,6 +129,7 @@ struct KswBatchBuf {                  // the ksw tasks of one block, joined (sta
 	int cap = 16;                     // CIGAR words per task; a block whose longest CIGAR does not fit is run again with room
 };
 struct StageService;                  // opaque; the device stages (stages_run.hpp)
+struct BlockHooks;
 struct SeedService;                   // opaque; owns the device-resident index
 SeedService *seed_service_create(const DebgaIndex &idx, int device, std::string &err);
 void seed_service_destroy(SeedService *s);
@@ -145,7 +146,7 @@ struct CigarPath { uint8_t type; int16_t size; };
 class AlnPipeline {
 public:
 	// `stages` (may be null): the device stages A..F1 (stages_run.hpp); without them every stage but seeding and ksw runs on the host
-	AlnPipeline(const DebgaIndex &idx, const AlnOptions &opt, SeedService *seeds, void *ksw_ctx, StageService *stages = nullptr);
+	AlnPipeline(const DebgaIndex &idx, const AlnOptions &opt, SeedService *seeds, void *ksw_ctx, StageService *stages = nullptr, int device = 0);
 	~AlnPipeline();
 	AlnPipeline(const AlnPipeline&) = delete;
 	AlnPipeline &operator=(const AlnPipeline&) = delete;
@@ -156,6 +157,7 @@ public:
 	// may be in flight on two threads: everything that consumes a random stream is serialised in `seq` order inside, the
 	// rest (stages A-E, the probe, the record text) of one block overlaps the in-order replay of the other.
 	bool align_block(const FastqRec *recs, size_t n_reads, BlockOutput &out, std::string &err, uint64_t seq);
+	bool align_block_host(const FastqRec *recs, size_t n_reads, BlockOutput &out, std::string &err, uint64_t seq, BlockHooks *hooks);
 	uint64_t next_seq() { return seq_issued_++; }
 	std::atomic<uint64_t> bad_cigar_records_{0};   // records left out because their CIGAR does not span the read (see output_bam)
 	void ensure_read_stats(const FastqRec &first);   // STAT_ fields of the input's first comment; call before overlapping blocks
@@ -180,8 +182,14 @@ private:
 	SeedService *seeds_;
 	void *ksw_;
 	StageService *stages_;
+	int device_ = 0;
+	// one block's trip through the device stages: a stage service instance (device buffers, stream, ksw context) plus the host
+	// side of its transfers; blocks in flight at the same time hold different ones, instances are created on demand and kept
 	struct DevBuffers;
-	DevBuffers *devbuf_[2] = {nullptr, nullptr};   // host side of the device stages' transfers, kept across blocks; slot = seq & 1
+	std::vector<DevBuffers*> dev_free_, dev_all_;
+	std::mutex dev_pool_m_;
+	DevBuffers *acquire_dev(std::string &err);
+	void release_dev(DevBuffers *d);
 	SeedBatch seed_main_[2], seed_small_; // batch buffers live across blocks (staging memory is pinned once); slot = seq & 1
 	KswBatchBuf ksw_main_[2];
 	std::mutex dev_m_;                    // the two device services take one batch at a time

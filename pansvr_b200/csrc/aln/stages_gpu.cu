@@ -112,7 +112,10 @@ struct StageService {
 	void *scan_tmp = nullptr; size_t scan_cap = 0;
 	IndexView view;
 	uint64_t *d_pos = nullptr, *d_ref = nullptr;
+	uint32_t *d_csi = nullptr, *d_cen = nullptr; DevSv *d_sv = nullptr;
 	RefView rf;
+	PairIndexView pix;
+	pansvr_ksw_ctx *own_ksw = nullptr;                            // every instance has its own ksw context (stream + scratch): no lock between blocks
 };
 
 StageService *stage_service_create(const DebgaIndex &idx, SeedService *seeds, void *ksw_ctx, int device, std::string &err)
@@ -121,18 +124,29 @@ StageService *stage_service_create(const DebgaIndex &idx, SeedService *seeds, vo
 	StageService *s = new StageService();
 	s->device = device;
 	s->view = seed_service_view(seeds);
-	s->be.ksw_ctx = (pansvr_ksw_ctx*)ksw_ctx;
+	(void)ksw_ctx;
+	if (pansvr_ksw_create(device, &s->own_ksw) != 0) { err = std::string("stage service: ") + pansvr_last_error(); delete s; return nullptr; }
+	s->be.ksw_ctx = s->own_ksw;
+	std::vector<DevSv> svs(idx.sv_info.size());
+	for (size_t i = 0; i < svs.size(); ++i) { svs[i].chr_id = idx.sv_info[i].chr_id; svs[i].st_pos = (uint32_t)idx.sv_info[i].st_pos; svs[i].end_offset = idx.sv_info[i].end_offset; svs[i].pad = 0; }
+	auto up32 = [&](const void *h, size_t bytes, void **d) -> bool {
+		if (cudaMalloc(d, bytes + 16) != cudaSuccess) return false;
+		return cudaMemcpy(*d, h, bytes, cudaMemcpyHostToDevice) == cudaSuccess;
+	};
 	auto up = [&](const std::vector<uint64_t> &h, uint64_t *&d) -> bool {
 		if (cudaMalloc((void**)&d, (h.size() + 2) * 8) != cudaSuccess) return false;
 		if (cudaMemset(d, 0, (h.size() + 2) * 8) != cudaSuccess) return false;
 		return cudaMemcpy(d, h.data(), h.size() * 8, cudaMemcpyHostToDevice) == cudaSuccess;
 	};
-	if (cudaStreamCreateWithFlags(&s->be.st, cudaStreamNonBlocking) != cudaSuccess || !up(idx.pos, s->d_pos) || !up(idx.ref_seq, s->d_ref)) {
+	if (cudaStreamCreateWithFlags(&s->be.st, cudaStreamNonBlocking) != cudaSuccess || !up(idx.pos, s->d_pos) || !up(idx.ref_seq, s->d_ref) ||
+	    !up32(idx.chr_search_index.data(), idx.chr_search_index.size() * 4, (void**)&s->d_csi) || !up32(idx.chr_end_n.data(), idx.chr_end_n.size() * 4, (void**)&s->d_cen) ||
+	    !up32(svs.data(), svs.size() * sizeof(DevSv), (void**)&s->d_sv)) {
 		err = "stage service: CUDA set-up failed";
 		stage_service_destroy(s);
 		return nullptr;
 	}
 	s->rf.ref_seq = s->d_ref;
+	s->pix.chr_search_index = s->d_csi; s->pix.chr_end_n = s->d_cen; s->pix.sv = s->d_sv;
 	return s;
 }
 
@@ -145,6 +159,8 @@ void stage_service_destroy(StageService *s)
 	for (cudaEvent_t e : s->be.ev_pool) cudaEventDestroy(e);
 	if (s->d_pos) cudaFree(s->d_pos);
 	if (s->d_ref) cudaFree(s->d_ref);
+	for (void *q : {(void*)s->d_csi, (void*)s->d_cen, (void*)s->d_sv}) if (q) cudaFree(q);
+	if (s->own_ksw) pansvr_ksw_destroy(s->own_ksw);
 	if (s->be.st) cudaStreamDestroy(s->be.st);
 	delete s;
 }
@@ -163,7 +179,20 @@ bool stage_service_run(StageService *s, const DevStageIn &in, DevStageOut &out, 
 	if (cudaSetDevice(s->device) != cudaSuccess) { err = "cudaSetDevice failed"; return false; }
 	CudaBackend &be = s->be;
 	be.failed = false; be.why.clear(); be.dev = DevCounters();
-	const bool ok = run_device_stages(be, s->view, s->d_pos, s->rf, in, out, err);
+	const bool ok = run_device_stages(be, s->view, s->d_pos, s->rf, s->pix, in, out, err);
+	be.sync();
+	be.collect_laps();
+	out.dev.add(be.dev);
+	if (be.failed) { err = "device stages: " + be.why; return false; }
+	return ok;
+}
+
+bool stage_service_finalize(StageService *s, const PairOpts &o, size_t n_pairs, const int8_t *win, DevStageOut &out, std::string &err)
+{
+	if (cudaSetDevice(s->device) != cudaSuccess) { err = "cudaSetDevice failed"; return false; }
+	CudaBackend &be = s->be;
+	be.failed = false; be.why.clear(); be.dev = DevCounters();
+	const bool ok = run_device_finalize(be, s->pix, o, n_pairs, win, out, err);
 	be.sync();
 	be.collect_laps();
 	out.dev.add(be.dev);

@@ -20,19 +20,21 @@
 
 #include "pipeline.hpp"
 #include "stages_core.cuh"
+#include "pair_core.cuh"
 
 namespace pansvr {
 
 enum DevSlot {
 	SL_TEXT, SL_READS, SL_BITS, SL_LIST, SL_FLAGS, SL_MEM_CNT, SL_MEM_OFF, SL_MEMS, SL_MEMS_TMP, SL_NVU, SL_SEED_CNT, SL_SEED_OFF,
 	SL_SEEDS, SL_SEEDS_TMP, SL_DIST, SL_PRE, SL_PLAN_CNT, SL_PLAN_OFF, SL_CANDS, SL_PIECES, SL_QLEN, SL_TLEN, SL_QOFF, SL_TOFF,
-	SL_Q, SL_T, SL_RES, SL_KCIG, SL_CIGS, SL_MISC, SL_SCAN_TMP, SL_COUNT
+	SL_Q, SL_T, SL_RES, SL_KCIG, SL_CIGS, SL_MISC, SL_SCAN_TMP, SL_USED, SL_ORI, SL_PSTATE, SL_PROBE, SL_WIN, SL_FINAL, SL_PFINAL, SL_COUNT
 };
 
 // ---- functors (one element of work each; plain data members only, so they can be passed to a kernel by value)
 struct FnEncode {
 	const uint8_t *text; const DevRead *reads; uint64_t *bits; uint8_t *list; uint8_t *flags;
-	SEED_HD void operator()(size_t i) const { flags[i] = encode_read(text, reads[i], bits, list) ? (uint8_t)ST_FLAG_STR : (uint8_t)0; }
+	SEED_HD void operator()(size_t i) const   // (len 0: a read that is not seeded -- skipped by RR:413-414, or shorter than a k-mer)
+	{ flags[i] = reads[i].len >= LEN_KMER && encode_read(text, reads[i], bits, list) ? (uint8_t)ST_FLAG_STR : (uint8_t)0; }
 };
 struct FnSeed {                                                    // strand j = 2 * read + strand; fill == false: count only
 	IndexView ix; const DevRead *reads; const uint64_t *bits; const uint8_t *list; const uint8_t *flags;
@@ -40,6 +42,7 @@ struct FnSeed {                                                    // strand j =
 	SEED_HD void operator()(size_t j) const
 	{
 		const DevRead &rd = reads[j >> 1];
+		if (rd.len < LEN_KMER) { if (!fill) count[j] = 0; return; }
 		const uint32_t s = (uint32_t)(j & 1), words = (rd.len >> 5) + 2, kn = rd.len - LEN_KMER + 1;
 		const uint64_t *b = bits + rd.bits_off + (size_t)s * words;
 		const bool is_str = (flags[j >> 1] & ST_FLAG_STR) != 0;
@@ -126,6 +129,30 @@ struct FnResolve {
 	}
 };
 
+struct FnProbe {                                                   // one pair = reads 2p, 2p + 1 of the table
+	PairIndexView ix; PairOpts o; const uint8_t *flags; const uint32_t *seed_off; const DevSeed *seeds; const float *dist; const int32_t *pre; uint8_t *used;
+	const uint32_t *cand_off; const DevCand *cands; const DevOri *ori; DevPairState *state; DevProbe *probe;
+	SEED_HD void operator()(size_t p) const
+	{
+		DevProbe &pr = probe[p];
+		if ((flags[2 * p] | flags[2 * p + 1]) & ST_FLAG_NEEDS_RAND) { pr.redo = PR_REDO_HOST; pr.draws0 = pr.draws1 = pr.ev_cnt = 0; pr.tie_mask = 0; return; }
+		ReadView R[2];
+		for (int k = 0; k < 2; ++k) {
+			const size_t i = 2 * p + k;
+			for (int s = 0; s < 2; ++s) {
+				const uint32_t sb = seed_off[2 * i + s];
+				R[k].v[s] = seeds + sb; R[k].dist[s] = dist + sb; R[k].pre[s] = pre + sb; R[k].used[s] = used + sb; R[k].n[s] = seed_off[2 * i + s + 1] - sb;
+			}
+			R[k].cands = cands; R[k].cand_b = cand_off[i]; R[k].cand_e = cand_off[i + 1]; R[k].ori = ori[i];
+		}
+		dev_probe_pair(ix, o, R, state[p], pr);
+	}
+};
+struct FnFinalize {
+	PairIndexView ix; PairOpts o; const DevOri *ori; DevPairState *state; const DevProbe *probe; const int8_t *win; DevFinal *fin; DevPairFinal *pfin;
+	SEED_HD void operator()(size_t p) const { dev_finalize_pair(ix, o, ori + 2 * p, state[p], probe[p].redo, win[2 * p], win[2 * p + 1], fin + 2 * p, pfin[p]); }
+};
+
 struct FnCells {                                                   // in-band DP cells of the tasks (the unit GCUPS is quoted in, KSW:131-138)
 	const int32_t *qlen, *tlen; int w; unsigned long long *cells;
 	SEED_HD void operator()(size_t k) const
@@ -155,6 +182,9 @@ struct DevStageIn {
 	const DevRead *reads; size_t n_reads;                          // host: the read table; bits_off / list_off laid out by the caller
 	size_t bits_words, list_bytes;                                 // pool sizes implied by the table
 	AlnScores scores;
+	// stage F on the device: reads 2p, 2p + 1 of the table are the mates of pair p (n_reads even); ori = their original alignments
+	const DevOri *ori = nullptr; PairOpts pair_opts = {0, 0, 0};
+	bool want_tables = false;                                      // also bring the sorted seeds and chain tables back (tests)
 };
 struct DevStageOut {                                               // host side, kept across blocks (pinned in the product)
 	HostVec<uint8_t> flags;                                        // per read state: ST_FLAG_*
@@ -163,12 +193,14 @@ struct DevStageOut {                                               // host side,
 	HostVec<DevSeed> seeds; HostVec<float> dist; HostVec<int32_t> pre;
 	HostVec<uint32_t> cand_off;                                    // n + 1
 	HostVec<DevCand> cands; HostVec<DevCigar> cigs;
+	HostVec<DevProbe> pair_probe;                                  // n / 2: what the in-order pass has to do for each pair
+	HostVec<DevFinal> fin; HostVec<DevPairFinal> pfin;             // after run_device_finalize: n and n / 2
 	uint64_t n_tasks = 0, n_cells = 0, probes = 0;
 	DevCounters dev;
 };
 
 template <class BE>
-bool run_device_stages(BE &be, const IndexView &ix, const uint64_t *d_pos, const RefView &rf, const DevStageIn &in, DevStageOut &out, std::string &err)
+bool run_device_stages(BE &be, const IndexView &ix, const uint64_t *d_pos, const RefView &rf, const PairIndexView &pix, const DevStageIn &in, DevStageOut &out, std::string &err)
 {
 	const size_t n = in.n_reads;
 	out.n_tasks = out.n_cells = out.probes = 0;
@@ -222,10 +254,12 @@ bool run_device_stages(BE &be, const IndexView &ix, const uint64_t *d_pos, const
 	uint32_t *d_plan_cnt = be.template buf<uint32_t>(SL_PLAN_CNT, PLAN_FIELDS * P), *d_plan_off = be.template buf<uint32_t>(SL_PLAN_OFF, PLAN_FIELDS * P);
 	if (!d_seeds || !d_seeds_tmp || !d_dist || !d_pre || !d_plan_cnt || !d_plan_off) { err = "device stages: out of device memory"; return false; }
 	be.for_each(n, FnChain{d_mem_off, d_nvu, d_seed_off, d_mems, d_pos, ix.posp, d_flags, d_seeds, d_seeds_tmp, d_dist, d_pre}, 2);
-	out.seeds.resize(n_seeds); out.dist.resize(n_seeds); out.pre.resize(n_seeds);
-	be.d2h(out.seeds.data(), d_seeds, n_seeds * sizeof(DevSeed));
-	be.d2h(out.dist.data(), d_dist, n_seeds * 4);
-	be.d2h(out.pre.data(), d_pre, n_seeds * 4);
+	if (in.want_tables) {
+		out.seeds.resize(n_seeds); out.dist.resize(n_seeds); out.pre.resize(n_seeds);
+		be.d2h(out.seeds.data(), d_seeds, n_seeds * sizeof(DevSeed));
+		be.d2h(out.dist.data(), d_dist, n_seeds * 4);
+		be.d2h(out.pre.data(), d_pre, n_seeds * 4);
+	}
 	// ---- D: count, offsets, fill
 	int cap = 16;
 	for (;;) {                                                     // (again with more room if a ksw CIGAR does not fit `cap` words)
@@ -269,6 +303,40 @@ bool run_device_stages(BE &be, const IndexView &ix, const uint64_t *d_pos, const
 		if (!overflow) { out.n_tasks = n_task; out.n_cells = cells; break; }
 		cap *= 4;
 	}
+	// ---- F (probe): chain selection, candidate sort and pairing of every pair against a scripted generator
+	out.pair_probe.clear();
+	if (in.ori && (n & 1) == 0) {
+		const size_t np = n / 2;
+		uint8_t *d_used = be.template buf<uint8_t>(SL_USED, n_seeds + 16);
+		DevOri *d_ori = be.template buf<DevOri>(SL_ORI, n);
+		DevPairState *d_state = be.template buf<DevPairState>(SL_PSTATE, np);
+		DevProbe *d_probe = be.template buf<DevProbe>(SL_PROBE, np);
+		if (!d_used || !d_ori || !d_state || !d_probe) { err = "device stages: out of device memory"; return false; }
+		be.h2d(d_ori, in.ori, n * sizeof(DevOri));
+		be.for_each(np, FnProbe{pix, in.pair_opts, d_flags, d_seed_off, d_seeds, d_dist, d_pre, d_used, d_plan_off, be.template buf<DevCand>(SL_CANDS, 0), d_ori, d_state, d_probe}, 6);
+		out.pair_probe.resize(np);
+		be.d2h(out.pair_probe.data(), d_probe, np * sizeof(DevProbe));
+		be.sync();
+	}
+	return true;
+}
+
+// Second trip of a block whose pairs were probed: the winners the in-order pass drew for the pairs with pairing ties go up,
+// primary / secondary / mate of every read come back.  win: 2 entries per pair (candidate index of each mate, -1 = none).
+template <class BE>
+bool run_device_finalize(BE &be, const PairIndexView &pix, const PairOpts &o, size_t n_pairs, const int8_t *win, DevStageOut &out, std::string &err)
+{
+	out.fin.resize(2 * n_pairs); out.pfin.resize(n_pairs);
+	if (n_pairs == 0) return true;
+	int8_t *d_win = be.template buf<int8_t>(SL_WIN, 2 * n_pairs);
+	DevFinal *d_fin = be.template buf<DevFinal>(SL_FINAL, 2 * n_pairs);
+	DevPairFinal *d_pfin = be.template buf<DevPairFinal>(SL_PFINAL, n_pairs);
+	if (!d_win || !d_fin || !d_pfin) { err = "device stages: out of device memory"; return false; }
+	be.h2d(d_win, win, 2 * n_pairs);
+	be.for_each(n_pairs, FnFinalize{pix, o, be.template buf<DevOri>(SL_ORI, 0), be.template buf<DevPairState>(SL_PSTATE, 0), be.template buf<DevProbe>(SL_PROBE, 0), d_win, d_fin, d_pfin}, 6);
+	be.d2h(out.fin.data(), d_fin, 2 * n_pairs * sizeof(DevFinal));
+	be.d2h(out.pfin.data(), d_pfin, n_pairs * sizeof(DevPairFinal));
+	be.sync();
 	return true;
 }
 
@@ -277,6 +345,9 @@ struct StageService;
 StageService *stage_service_create(const DebgaIndex &idx, SeedService *seeds, void *ksw_ctx, int device, std::string &err);
 void stage_service_destroy(StageService *s);
 void stage_service_set_scoring(StageService *s, const AlnScores &o, int zdrop);   // ksw parameters of stage E (copy_option, RR:817-827)
+// A service instance holds one block's device state from stage_service_run to stage_service_finalize (two trips with the host's
+// in-order pass in between); blocks in flight at the same time use different instances.
 bool stage_service_run(StageService *s, const DevStageIn &in, DevStageOut &out, std::string &err);
+bool stage_service_finalize(StageService *s, const PairOpts &o, size_t n_pairs, const int8_t *win, DevStageOut &out, std::string &err);
 
 } // namespace pansvr

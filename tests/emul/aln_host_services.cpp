@@ -73,12 +73,15 @@ struct HostBackend {
 	}
 };
 
-struct StageService { HostBackend be; IndexView view; const uint64_t *pos; RefView rf; };
+struct StageService { HostBackend be; IndexView view; const uint64_t *pos; RefView rf; std::vector<DevSv> svs; PairIndexView pix; };
 
 StageService *stage_service_create(const DebgaIndex &idx, SeedService *seeds, void *, int, std::string &)
 {
 	StageService *s = new StageService();
 	s->view = seeds->view; s->pos = idx.pos.data(); s->rf.ref_seq = idx.ref_seq.data();
+	s->svs.resize(idx.sv_info.size());
+	for (size_t i = 0; i < s->svs.size(); ++i) { s->svs[i].chr_id = idx.sv_info[i].chr_id; s->svs[i].st_pos = (uint32_t)idx.sv_info[i].st_pos; s->svs[i].end_offset = idx.sv_info[i].end_offset; s->svs[i].pad = 0; }
+	s->pix.chr_search_index = idx.chr_search_index.data(); s->pix.chr_end_n = idx.chr_end_n.data(); s->pix.sv = s->svs.data();
 	return s;
 }
 void stage_service_destroy(StageService *s) { delete s; }
@@ -92,7 +95,11 @@ void stage_service_set_scoring(StageService *s, const AlnScores &o, int zdrop)
 }
 bool stage_service_run(StageService *s, const DevStageIn &in, DevStageOut &out, std::string &err)
 {
-	return run_device_stages(s->be, s->view, s->pos, s->rf, in, out, err);
+	return run_device_stages(s->be, s->view, s->pos, s->rf, s->pix, in, out, err);
+}
+bool stage_service_finalize(StageService *s, const PairOpts &o, size_t n_pairs, const int8_t *win, DevStageOut &out, std::string &err)
+{
+	return run_device_finalize(s->be, s->pix, o, n_pairs, win, out, err);
 }
 
 } // namespace pansvr
