@@ -31,7 +31,7 @@ struct pansvr_aln_ctx {
 	pansvr_ksw_ctx *ksw = nullptr;
 	AlnPipeline *pipe = nullptr;
 	BamHeaderInfo bam_hdr;
-	std::vector<BlockOutput> outs;    // chunk buffers of the record text of every sub-block, kept across calls
+	std::deque<BlockOutput> outs;     // chunk buffers of the record text of every sub-block, kept across calls
 };
 
 struct pansvr_bam_file {
@@ -242,7 +242,22 @@ namespace {
 // parse + align one block; `text` receives, in input order, the buffers that hold the record text.
 // A large block is cut into sub-blocks and two of them are in flight at a time: the single-threaded in-order replay of one
 // overlaps the parallel stages of the next (AlnPipeline::align_block keeps the random streams in sequence).
-int run_block(pansvr_aln_ctx *c, const char *fastq, size_t n, std::vector<const std::string*> &sam, std::vector<const std::string*> &ori)
+struct Part { const char *p; size_t n; };                    // a piece of record text; pieces end at line ends
+
+// cuts [p, p + n) into pieces of about 4 MB at line ends, so that whoever consumes the text can do so on all helper threads
+void add_parts(std::vector<Part> &parts, const char *p, size_t n)
+{
+	const size_t want = (size_t)4 << 20;
+	size_t at = 0;
+	while (at < n) {
+		size_t e = std::min(n, at + want);
+		if (e < n) { const char *nl = (const char*)memchr(p + e, '\n', n - e); e = nl ? (size_t)(nl - p) + 1 : n; }
+		parts.push_back(Part{p + at, e - at});
+		at = e;
+	}
+}
+
+int run_block(pansvr_aln_ctx *c, const char *fastq, size_t n, std::vector<Part> &sam, std::vector<Part> &ori)
 {
 	const auto tick = []() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
 	const double t0 = tick();
@@ -279,8 +294,9 @@ int run_block(pansvr_aln_ctx *c, const char *fastq, size_t n, std::vector<const 
 	for (size_t k = 0; k < n_sub; ++k) if (!ok[k]) { g_aln_err = errs[k]; return PANSVR_E_CUDA; }
 	sam.clear(); ori.clear();
 	for (size_t k = 0; k < n_sub; ++k) {
-		for (const std::string &x : c->outs[k].sam) sam.push_back(&x);
-		for (const std::string &x : c->outs[k].ori) ori.push_back(&x);
+		if (c->outs[k].sam_text.size()) add_parts(sam, c->outs[k].sam_text.data(), c->outs[k].sam_text.size());     // device path: one text per sub-block
+		for (const std::string &x : c->outs[k].sam) if (!x.empty()) add_parts(sam, x.data(), x.size());
+		for (const std::string &x : c->outs[k].ori) if (!x.empty()) add_parts(ori, x.data(), x.size());
 	}
 	return 0;
 }
@@ -304,17 +320,17 @@ int pansvr_aln_block(pansvr_aln_ctx *c, const char *fastq, size_t n, char **sam,
 {
 	if (!c || !fastq || !sam || !ori) return PANSVR_E_ARG;
 	CallReport report(c);
-	std::vector<const std::string*> text_sam, text_ori;
+	std::vector<Part> text_sam, text_ori;
 	const int rc = run_block(c, fastq, n, text_sam, text_ori);
 	if (rc != 0) return rc;
 	const double t0 = CallReport::now();
-	auto join = [&](const std::vector<const std::string*> &parts, char **out, size_t *bytes) -> bool {     // chunk buffers -> one malloc'ed text
+	auto join = [&](const std::vector<Part> &parts, char **out, size_t *bytes) -> bool {     // chunk buffers -> one malloc'ed text
 		const size_t np = parts.size();
 		std::vector<size_t> off(np + 1, 0);
-		for (size_t i = 0; i < np; ++i) off[i + 1] = off[i] + parts[i]->size();
+		for (size_t i = 0; i < np; ++i) off[i + 1] = off[i] + parts[i].n;
 		char *buf = (char*)malloc(off[np] + 1);
 		if (!buf) return false;
-		c->pipe->parallel(np, [&](size_t b, size_t e, int) { for (size_t i = b; i < e; ++i) if (!parts[i]->empty()) memcpy(buf + off[i], parts[i]->data(), parts[i]->size()); }, 2);
+		c->pipe->parallel(np, [&](size_t b, size_t e, int) { for (size_t i = b; i < e; ++i) if (parts[i].n) memcpy(buf + off[i], parts[i].p, parts[i].n); }, 2);
 		buf[off[np]] = 0;
 		*out = buf;
 		if (bytes) *bytes = off[np];
@@ -330,30 +346,30 @@ int pansvr_aln_block_bam(pansvr_aln_ctx *c, const char *fastq, size_t n, uint8_t
 {
 	if (!c || !fastq || !bam || !ori) return PANSVR_E_ARG;
 	CallReport report(c);
-	std::vector<const std::string*> text_sam, text_ori;
+	std::vector<Part> text_sam, text_ori;
 	const int rc = run_block(c, fastq, n, text_sam, text_ori);
 	if (rc != 0) return rc;
 	const double t0 = CallReport::now();
-	const size_t np = text_sam.size();
-	std::vector<std::vector<uint8_t>> part_s(np), part_o(np);
-	std::vector<std::string> errs(np);
+	const size_t np = text_sam.size(), npo = text_ori.size();
+	std::vector<std::vector<uint8_t>> part_s(np), part_o(npo);
+	std::vector<std::string> errs(np + npo);
 	// A record htslib's sam_parse1 would reject (the reference then writes a half-parsed bam1_t with undefined content, e.g. the
 	// -p record of a read whose original CIGAR does not match its sequence) is left out and counted, not fatal.
-	auto encode_lines = [&](const std::string &text, std::vector<uint8_t> &dst, std::string &) {
-		dst.reserve(text.size() / 2);
-		for (size_t p = 0; p < text.size();) {
-			const char *nl = (const char*)memchr(text.data() + p, '\n', text.size() - p);
-			const size_t e = nl ? (size_t)(nl - text.data()) : text.size();
+	auto encode_lines = [&](const Part &text, std::vector<uint8_t> &dst, std::string &) {
+		dst.reserve(text.n / 2);
+		for (size_t p = 0; p < text.n;) {
+			const char *nl = (const char*)memchr(text.p + p, '\n', text.n - p);
+			const size_t e = nl ? (size_t)(nl - text.p) : text.n;
 			if (e > p) {
 				const size_t at = dst.size();
 				std::string why;
-				if (!bam_encode_record(text.data() + p, e - p, c->bam_hdr, dst, why)) { dst.resize(at); ++c->pipe->bad_cigar_records_; }
+				if (!bam_encode_record(text.p + p, e - p, c->bam_hdr, dst, why)) { dst.resize(at); ++c->pipe->bad_cigar_records_; }
 			}
 			p = e + 1;
 		}
 	};
-	c->pipe->parallel(np, [&](size_t b, size_t e, int) {
-		for (size_t i = b; i < e; ++i) { encode_lines(*text_sam[i], part_s[i], errs[i]); if (errs[i].empty()) encode_lines(*text_ori[i], part_o[i], errs[i]); }
+	c->pipe->parallel(np + npo, [&](size_t b, size_t e, int) {
+		for (size_t i = b; i < e; ++i) { if (i < np) encode_lines(text_sam[i], part_s[i], errs[i]); else encode_lines(text_ori[i - np], part_o[i - np], errs[i]); }
 	}, 2);
 	for (const std::string &e : errs) if (!e.empty()) { g_aln_err = e; return PANSVR_E_ARG; }
 	auto join = [&](std::vector<std::vector<uint8_t>> &parts, uint8_t **out, size_t *bytes) -> bool {

@@ -18,10 +18,11 @@ namespace pansvr {
 
 struct AlnPipeline::DevBuffers {                                  // one block's trip through the device stages
 	StageService *svc = nullptr; bool owned = false;
+	HostVec<uint8_t> text;                                        // the block's FASTQ text (pinned staging)
 	HostVec<DevRead> reads;
-	HostVec<DevOri> ori;
-	HostVec<uint8_t> seq;                                         // the bases of the block's device reads, gathered (pinned)
+	HostVec<DevRec> recs;
 	HostVec<int8_t> win;
+	HostVec<uint32_t> host_len;
 	DevStageOut out;
 };
 
@@ -310,6 +311,7 @@ struct PairEvent { int8_t i, j; uint8_t tie; };             // store_pair reache
 struct AlnPipeline::Impl {
 	AlnPipeline &P;
 	const DebgaIndex &idx;
+	bool count_bad = true;                                       // output_bam counts the records it leaves out (off for scratch runs)
 	explicit Impl(AlnPipeline &p) : P(p), idx(p.idx_) {}
 
 	// ---------------------------------------------------------------- stage A
@@ -1021,7 +1023,7 @@ struct AlnPipeline::Impl {
 		// A z-dropped extension (only with -z well below the default) can leave a CIGAR shorter than the read.  The reference
 		// logs "ERROR cigar", htslib rejects the record and the reference then writes the half-parsed bam1_t with stale buffer
 		// bytes; there is nothing defined to reproduce, so the record is left out and counted.
-		if (!p->is_ori && !p->cigar_ok) { ++P.bad_cigar_records_; if (p->direction == REVERSE) r.seq_twice_reversed = true; return; }
+		if (!p->is_ori && !p->cigar_ok) { if (count_bad) ++P.bad_cigar_records_; if (p->direction == REVERSE) r.seq_twice_reversed = true; return; }
 		const int dir = p->direction;
 		const uint8_t flag = (uint8_t)((first ? 0x40 : 0) + (dir == REVERSE ? 0x10 : 0) + (p->has_mate ? 0 : 0x08));
 		out.append(r.rec->name, r.rec->name_l); out += '\t'; append_int(out, flag); out += '\t';
@@ -1729,45 +1731,10 @@ bool AlnPipeline::align_block_host(const FastqRec *recs, size_t n_reads_in, Bloc
 
 
 // ================================================================================================ the device path
-namespace {
-
-// parse_ori_mapping_rst (RRH:392-429) without touching the comment: the numbers and flags of the original alignment
-void parse_ori_light(const FastqRec &rec, int match, DevOri &o)
-{
-	const char *c = rec.comment; const size_t n = rec.comment_l;
-	const char *tok[10]; size_t tok_l[10];
-	int nt = 0;
-	size_t i = 0;
-	while (nt < 10 && i < n) {
-		while (i < n && c[i] == '_') ++i;
-		if (i >= n) break;
-		size_t j = i;
-		while (j < n && c[j] != '_') ++j;
-		tok[nt] = c + i; tok_l[nt] = j - i; ++nt;
-		i = j + 1;
-	}
-	auto num = [&](int k) -> int {
-		if (k >= nt) return 0;
-		const char *p = tok[k], *e = p + tok_l[k];
-		while (p < e && (*p == ' ' || *p == '\t')) ++p;
-		bool neg = false;
-		if (p < e && (*p == '-' || *p == '+')) { neg = *p == '-'; ++p; }
-		long v = 0;
-		while (p < e && *p >= '0' && *p <= '9') v = v * 10 + (*p++ - '0');
-		return (int)(neg ? -v : v);
-	};
-	o.chr = (uint32_t)num(0); o.ref_bg = (uint32_t)num(1); o.read_bg = (uint32_t)num(2); o.align_score = (uint32_t)num(3); o.mapq = (uint8_t)num(4);
-	o.direction = (nt > 9 && tok_l[9] > 0 && tok[9][0] == 'F') ? FORWARD : REVERSE;
-	o.unmapped = (nt > 9 && tok_l[9] > 1 && tok[9][1] == 'Y') || o.chr > 24;                       // RR:413
-	if (o.ref_bg >= (uint32_t)I32MAX) o.ref_bg = 1;
-	o.skip = !o.unmapped && o.align_score == (uint32_t)((int)rec.seq_l * match);                  // RR:414
-}
-
-} // namespace
-
 bool AlnPipeline::align_block(const FastqRec *recs, size_t n_reads_in, BlockOutput &out, std::string &err, uint64_t seq)
 {
-	const size_t n_pairs = n_reads_in / 2;
+	const size_t n_pairs = n_reads_in / 2, nd = 2 * n_pairs;
+	out.sam_text.clear();
 	if (!stages_ || n_pairs == 0) return align_block_host(recs, n_reads_in, out, err, seq, nullptr);
 	Impl I(*this);
 	const DebgaIndex &idx = idx_;
@@ -1777,84 +1744,76 @@ bool AlnPipeline::align_block(const FastqRec *recs, size_t n_reads_in, BlockOutp
 	DevBuffers *db = acquire_dev(err);
 	if (!db) return false;
 	struct Release { AlnPipeline &P; DevBuffers *b; ~Release() { P.release_dev(b); } } release{*this, db};
-	// ---- which pairs the device takes: no 'N' (its substitution draws rand()), no lower-case 'n' (code 4 spills into the packed
-	// neighbour).  Read 2k, 2k+1 of the device table are the mates of the k-th such pair.
-	std::vector<uint8_t> host_pair(n_pairs, 0);
-	parallel(n_pairs, [&](size_t b, size_t e, int) {
-		for (size_t pi = b; pi < e; ++pi) {
-			bool host = false;
-			for (int k = 0; k < 2; ++k) { const FastqRec &r = recs[2 * pi + k]; host |= memchr(r.seq, 'N', r.seq_l) != nullptr || memchr(r.seq, 'n', r.seq_l) != nullptr; }
-			host_pair[pi] = host;
-		}
-	});
-	std::vector<uint32_t> fast;                                           // block indices of the device path's pairs
-	fast.reserve(n_pairs);
-	for (size_t pi = 0; pi < n_pairs; ++pi) if (!host_pair[pi]) fast.push_back((uint32_t)pi);
-	const size_t nf = fast.size(), nd = 2 * nf;
-	db->reads.resize(nd); db->ori.resize(nd);
-	parallel(nf, [&](size_t b, size_t e, int) {
-		for (size_t k = b; k < e; ++k) for (int m = 0; m < 2; ++m) parse_ori_light(recs[2 * (size_t)fast[k] + m], opt.match, db->ori[2 * k + m]);
-	});
-	size_t seq_bytes = 0, words = 0, list_bytes = 0;
-	for (size_t t = 0; t < nd; ++t) {
-		const FastqRec &r = recs[2 * (size_t)fast[t >> 1] + (t & 1)];
-		DevRead &d = db->reads[t];
-		const bool seeded = !db->ori[t].skip && r.seq_l >= LEN_KMER;      // (not seeded: full-score original, RR:414, or shorter than a k-mer)
-		d.seq_off = (uint32_t)seq_bytes; d.len = seeded ? r.seq_l : 0u; d.var_code = 0; d.bits_off = (uint32_t)words; d.list_off = (uint32_t)list_bytes;
-		if (seeded) { seq_bytes += r.seq_l; words += 2 * (size_t)((r.seq_l >> 5) + 2); list_bytes += 2 * (size_t)(r.seq_l - LEN_KMER + 1); }
+	// ---- the block's text and record table go up as they are: records are views into one buffer, in input order
+	const char *base = recs[0].name;
+	const char *end = recs[nd - 1].qual + recs[nd - 1].qual_l;
+	for (size_t t = 0; t < nd; t += 1 + (nd > 2 ? nd - 2 : 0)) {          // (first and last suffice for a parsed buffer; be safe about odd callers)
+		base = std::min(base, recs[t].name); end = std::max(end, recs[t].qual + recs[t].qual_l);
 	}
-	if (seq_bytes >= 0xffffffffull || words >= 0xffffffffull || list_bytes >= 0xffffffffull) { err = "block too large for the device stages (cut it into smaller blocks)"; return false; }
-	db->seq.resize(seq_bytes + 1);
-	parallel(nd, [&](size_t b, size_t e, int) {
-		for (size_t t = b; t < e; ++t) if (db->reads[t].len) memcpy(db->seq.data() + db->reads[t].seq_off, recs[2 * (size_t)fast[t >> 1] + (t & 1)].seq, db->reads[t].len);
-	});
+	const size_t text_bytes = (size_t)(end - base);
+	if (text_bytes >= 0xfffffff0ull) { err = "block too large for the device stages (cut it into smaller blocks)"; return false; }
+	db->text.resize(text_bytes + 1);
+	{
+		const size_t piece = (size_t)4 << 20, n_piece = (text_bytes + piece - 1) / piece;
+		parallel(n_piece, [&](size_t b, size_t e, int) { for (size_t k = b; k < e; ++k) memcpy(db->text.data() + k * piece, base + k * piece, std::min(piece, text_bytes - k * piece)); }, 2);
+	}
+	db->reads.resize(nd); db->recs.resize(nd);
+	size_t words = 0, list_bytes = 0;
+	for (size_t t = 0; t < nd; ++t) {
+		const FastqRec &r = recs[t];
+		DevRec &dr = db->recs[t];
+		dr.name_off = (uint32_t)(r.name - base); dr.comment_off = (uint32_t)(r.comment - base); dr.seq_off = (uint32_t)(r.seq - base); dr.qual_off = (uint32_t)(r.qual - base);
+		dr.name_l = r.name_l; dr.comment_l = r.comment_l; dr.seq_l = r.seq_l; dr.qual_l = r.qual_l;
+		DevRead &d = db->reads[t];
+		d.seq_off = dr.seq_off; d.len = r.seq_l; d.var_code = 0; d.bits_off = (uint32_t)words; d.list_off = (uint32_t)list_bytes;
+		if (r.seq_l >= LEN_KMER) { words += 2 * (size_t)((r.seq_l >> 5) + 2); list_bytes += 2 * (size_t)(r.seq_l - LEN_KMER + 1); }
+	}
+	if (words >= 0xffffffffull || list_bytes >= 0xffffffffull) { err = "block too large for the device stages (cut it into smaller blocks)"; return false; }
 	add_time(0, now() - t0); t0 = now();
-	// ---- first trip: stages A..F1 and the probe of stage F
+	// ---- first trip: the original alignments, stages A..F1 and the probe of stage F
 	DevStageIn in;
-	in.text = db->seq.data(); in.text_bytes = seq_bytes; in.reads = db->reads.data(); in.n_reads = nd; in.bits_words = words; in.list_bytes = list_bytes;
+	in.text = db->text.data(); in.text_bytes = text_bytes; in.reads = db->reads.data(); in.n_reads = nd; in.bits_words = words; in.list_bytes = list_bytes;
 	in.scores = AlnScores{opt.match, opt.mismatch, opt.gap_open, opt.gap_ex, opt.gap_open2, opt.gap_ex2};
-	in.ori = db->ori.data(); in.pair_opts = PairOpts{opt.isize_max, opt.isize_min, opt.read_len};
+	in.recs = db->recs.data(); in.pair_opts = PairOpts{opt.isize_max, opt.isize_min, opt.read_len};
 	const char *dump = getenv("PANSVR_DUMP_STAGES");
 	in.want_tables = dump != nullptr;
-	if (nd && !stage_service_run(db->svc, in, db->out, err)) return false;
+	if (!stage_service_run(db->svc, in, db->out, err)) return false;
 	DevStageOut &o = db->out;
-	if (nd == 0) o.pair_probe.clear();
 	add_time(1, now() - t0); t0 = now();
 	if (dump) {                                                           // tests: what the device stages returned, for the differential
 		const std::string path = std::string(dump) + "." + std::to_string(seq);   // between the CUDA backend and the host-stepped one
 		if (FILE *f = fopen(path.c_str(), "wb")) {
-			const uint64_t hdr[4] = {nd, nd ? o.seed_off[2 * nd] : 0, o.cands.size(), nd ? o.mem_off[2 * nd] : 0};
+			const uint64_t hdr[4] = {nd, o.seed_off[2 * nd], o.cands.size(), o.mem_off[2 * nd]};
 			fwrite(hdr, 8, 4, f);
-			if (nd) {
-				fwrite(o.flags.data(), 1, nd, f); fwrite(o.mem_off.data(), 4, 2 * nd + 1, f); fwrite(o.seed_off.data(), 4, 2 * nd + 1, f);
-				fwrite(o.seeds.data(), sizeof(DevSeed), o.seeds.size(), f); fwrite(o.dist.data(), 4, o.dist.size(), f); fwrite(o.pre.data(), 4, o.pre.size(), f);
-				fwrite(o.cand_off.data(), 4, nd + 1, f);
-				for (size_t c = 0; c < o.cands.size(); ++c) {
-					DevCand cd = o.cands[c];
-					fwrite(o.cigs.data() + cd.cig_off, sizeof(DevCigar), cd.n_cig, f);
-					cd.piece_off = cd.cig_off = cd.cig_cap = 0;
-					fwrite(&cd, sizeof cd, 1, f);
-				}
-				fwrite(o.pair_probe.data(), sizeof(DevProbe), o.pair_probe.size(), f);
+			fwrite(o.flags.data(), 1, nd, f); fwrite(o.mem_off.data(), 4, 2 * nd + 1, f); fwrite(o.seed_off.data(), 4, 2 * nd + 1, f);
+			fwrite(o.seeds.data(), sizeof(DevSeed), o.seeds.size(), f); fwrite(o.dist.data(), 4, o.dist.size(), f); fwrite(o.pre.data(), 4, o.pre.size(), f);
+			fwrite(o.cand_off.data(), 4, nd + 1, f);
+			for (size_t c = 0; c < o.cands.size(); ++c) {
+				DevCand cd = o.cands[c];
+				fwrite(o.cigs.data() + cd.cig_off, sizeof(DevCigar), cd.n_cig, f);
+				cd.piece_off = cd.cig_off = cd.cig_cap = 0;
+				fwrite(&cd, sizeof cd, 1, f);
+			}
+			for (size_t k = 0; k < o.pair_probe.size(); ++k) {             // (only what the probe defines: events beyond ev_cnt are not written by it)
+				const DevProbe &pr = o.pair_probe[k];
+				fwrite(&pr, 4, 1, f); fwrite(pr.ev_i, 1, pr.ev_cnt, f); fwrite(pr.ev_j, 1, pr.ev_cnt, f); fwrite(&pr.tie_mask, 4, 1, f);
 			}
 			fclose(f);
 		}
 	}
-	// ---- the pairs the host path finishes: those it kept, and those the device hands back
+	// ---- the pairs the host path finishes: 'N' / 'n' in a read, a unipath that needs random_r, ties that change the outcome
 	std::vector<uint32_t> host_list;
-	for (size_t k = 0; k < nf; ++k) if (o.pair_probe[k].redo == PR_REDO_HOST) host_pair[fast[k]] = 1;
-	for (size_t pi = 0; pi < n_pairs; ++pi) if (host_pair[pi]) host_list.push_back((uint32_t)pi);
+	for (size_t p = 0; p < n_pairs; ++p) if (o.pair_probe[p].redo == PR_REDO_HOST) host_list.push_back((uint32_t)p);
 	std::vector<FastqRec> hrecs(2 * host_list.size());
 	for (size_t s = 0; s < host_list.size(); ++s) { hrecs[2 * s] = recs[2 * (size_t)host_list[s]]; hrecs[2 * s + 1] = recs[2 * (size_t)host_list[s] + 1]; }
-	db->win.resize(2 * nf + 2);
-	for (size_t t = 0; t < 2 * nf; ++t) db->win[t] = -1;
+	db->win.resize(nd + 2);
+	for (size_t t = 0; t < nd; ++t) db->win[t] = -1;
 	size_t cursor = 0;
-	uint64_t n_fast_done = 0;
 	BlockHooks H;
 	H.global_pair = host_list.data();
 	// in-order pass of the device path's pairs: advance the stream by a read's draws, redraw the pairing ties (RRH:553)
 	H.fast_until = [&](uint64_t upto) {
-		for (; cursor < nf && (uint64_t)fast[cursor] < upto; ++cursor) {
+		for (; cursor < n_pairs && (uint64_t)cursor < upto; ++cursor) {
 			const DevProbe &pr = o.pair_probe[cursor];
 			if (pr.redo == 0 || pr.redo == PR_REDO_HOST) continue;
 			for (int k = 0, n = pr.draws0 + pr.draws1; k < n; ++k) rand_.next();
@@ -1870,24 +1829,31 @@ bool AlnPipeline::align_block(const FastqRec *recs, size_t n_reads_in, BlockOutp
 	};
 	H.emit = [&](const std::function<void(size_t, std::string&, std::string&)> &text_host, std::string &e2) -> bool {
 		double t1 = now();
-		// ---- second trip: the winners go up, primary / secondary / mate of every read come back
-		if (nf && !stage_service_finalize(db->svc, in.pair_opts, nf, db->win.data(), o, e2)) return false;
+		// the host path's pairs first: the device leaves room for their records
+		const size_t nh = host_list.size();
+		std::vector<std::string> h_sam(nh), h_ori(nh);
+		parallel(nh, [&](size_t b, size_t e, int) { for (size_t s = b; s < e; ++s) text_host(s, h_sam[s], h_ori[s]); }, 64);
+		db->host_len.resize(n_pairs + 1);
+		for (size_t p = 0; p < n_pairs; ++p) db->host_len[p] = 0;
+		for (size_t s = 0; s < nh; ++s) db->host_len[host_list[s]] = (uint32_t)h_sam[s].size();
+		// ---- second trip: the winners go up; primary / secondary / mate of every read and the block's SAM text come back
+		if (!stage_service_finalize(db->svc, in.pair_opts, opt.not_ori ? 1 : 0, n_pairs, db->win.data(), db->host_len.data(), o, out.sam_text, e2)) return false;
+		for (size_t s = 0; s < nh; ++s) if (!h_sam[s].empty()) memcpy(out.sam_text.data() + o.txt_off[2 * (size_t)host_list[s]], h_sam[s].data(), h_sam[s].size());
+		bad_cigar_records_ += o.bad_records;
 		add_time(2, now() - t1); t1 = now();
-		std::vector<int32_t> slot_of(n_pairs, -1), fast_of(n_pairs, -1);
-		for (size_t s = 0; s < host_list.size(); ++s) slot_of[host_list[s]] = (int32_t)s;
-		for (size_t k = 0; k < nf; ++k) fast_of[fast[k]] = (int32_t)k;
-		std::atomic<uint64_t> done(0);
+		// ---- the `-p` records (output_ori_bam, RR:656-717, 776-797) are rare: written here from what came back
+		std::vector<int32_t> slot_of(n_pairs, -1);
+		for (size_t s = 0; s < nh; ++s) slot_of[host_list[s]] = (int32_t)s;
+		Impl Iq(*this);
+		Iq.count_bad = false;
 		parallel(n_pairs, [&](size_t pb, size_t pe_, int t) {             // chunk t writes its pairs, in order, into buffer t
-			std::string sam, ori;
-			sam.swap(out.sam[(size_t)t]); ori.swap(out.ori[(size_t)t]);
-			sam.reserve((pe_ - pb) * 2 * (2 * (size_t)opt.read_len + 400));
-			uint64_t mine = 0;
+			std::string ori, scratch;
+			ori.swap(out.ori[(size_t)t]);
 			for (size_t pi = pb; pi < pe_; ++pi) {
-				if (slot_of[pi] >= 0) { text_host((size_t)slot_of[pi], sam, ori); continue; }
-				// a pair of the device path: rebuild what output_BAM / output_ori_bam read of the handlers (RR:479-536, 656-717)
-				const size_t k = (size_t)fast_of[pi];
-				const DevPairFinal &pf = o.pfin[k];
-				++mine;
+				if (slot_of[pi] >= 0) { ori += h_ori[(size_t)slot_of[pi]]; continue; }
+				const DevPairFinal &pf = o.pfin[pi];
+				if (!(pf.max_score <= min_filter_score_)) continue;
+				// rebuild what output_BAM / output_ori_bam read of the two handlers
 				ReadState se[2];
 				Result prim[2], sec[2];
 				Impl::PE pe;
@@ -1897,9 +1863,9 @@ bool AlnPipeline::align_block(const FastqRec *recs, size_t n_reads_in, BlockOutp
 					r.rec = &recs[2 * pi + m];
 					r.comment.assign(r.rec->comment, r.rec->comment_l);
 					r.read_l = (int)r.rec->seq_l;
-					I.parse_ori(r);
+					Iq.parse_ori(r);
 					if (r.ori.chr > 24) r.ori_unmapped = true;
-					const DevFinal &f = o.fin[2 * k + m];
+					const DevFinal &f = o.fin[2 * pi + m];
 					if (!(f.flags & FIN_PRIMARY)) continue;
 					Result *c;
 					if (f.flags & FIN_P_ORI) c = &r.ori;
@@ -1924,22 +1890,22 @@ bool AlnPipeline::align_block(const FastqRec *recs, size_t n_reads_in, BlockOutp
 						r.secondary = &s2;
 					}
 				}
-				if (pe.gain)
-					for (int m = 0; m < 2; ++m) I.output_bam(se[m], sam, m == 0, pe.cur_isize);
-				I.output_ori_pair(se, pe, sam, ori, min_filter_score_);
+				if (pe.gain) {                                                 // (the main records came from the device; this run only leaves the handlers
+					scratch.clear();                                            // in the state output_ori_bam finds them in, and must not count twice)
+					for (int m = 0; m < 2; ++m) Iq.output_bam(se[m], scratch, m == 0, pe.cur_isize);
+				}
+				Iq.output_ori_pair(se, pe, scratch, ori, min_filter_score_);
 			}
-			done += mine;
-			sam.swap(out.sam[(size_t)t]); ori.swap(out.ori[(size_t)t]);
+			ori.swap(out.ori[(size_t)t]);
 		});
-		n_fast_done = done.load();
 		add_time(5, now() - t1);
 		return true;
 	};
 	const bool ok = align_block_host(hrecs.data(), hrecs.size(), out, err, seq, &H);
 	if (ok) {
 		std::lock_guard<std::mutex> lk(stats_m_);
-		stats.reads += 2 * n_fast_done;
-		stats.mems += nd ? o.mem_off[2 * nd] : 0; stats.ksw_tasks += o.n_tasks; stats.ksw_cells += o.n_cells;
+		stats.reads += 2 * (n_pairs - host_list.size());
+		stats.mems += o.mem_off[2 * nd]; stats.ksw_tasks += o.n_tasks; stats.ksw_cells += o.n_cells;
 		stats.dev.add(o.dev); stats.dev.seed_probes += (int64_t)o.probes;
 		o.dev = DevCounters();
 	}

@@ -139,6 +139,7 @@ bool seed_service_run(SeedService *s, SeedBatch &b, std::string &err);
 struct BlockOutput {                  // record text of one block: buffer t holds the lines ("...\n") of the t-th chunk of pairs,
 	std::vector<std::string> sam;     // concatenating the buffers in order gives the block's output in input order
 	std::vector<std::string> ori;     // `-p` output: pairs still poorly aligned
+	HostVec<char> sam_text;           // device path: the block's main output as one text, straight from the device (then `sam` is empty)
 };
 
 struct CigarPath { uint8_t type; int16_t size; };

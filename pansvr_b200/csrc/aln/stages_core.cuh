@@ -22,7 +22,7 @@ namespace pansvr {
 enum { ST_POS_N_MAX = 500, ST_POS_N_MAX_LEVEL2 = 8000, ST_WAITING_LEN = 3 };
 enum { ST_MIN_CHAIN_SCORE = 20, ST_MAX_CHAIN_SCORE_DIFF = 30, ST_MIN_CHAIN_SCORE2 = 30 };
 enum { ST_ALN_LEFT = 0, ST_ALN_RIGHT = 1, ST_ALN_E2E = 2 };
-enum { ST_FLAG_NEEDS_RAND = 1, ST_FLAG_STR = 2 };
+enum { ST_FLAG_NEEDS_RAND = 1, ST_FLAG_STR = 2, ST_FLAG_HOST = 4, ST_FLAG_NOSEED = 8 };
 const int ST_NEG_INF = -0x40000000;
 
 struct DevRead {                  // one read state of the device path: a read, or one substitution variant of a read with 1..3 'N'

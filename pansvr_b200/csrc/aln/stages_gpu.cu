@@ -115,6 +115,8 @@ struct StageService {
 	uint32_t *d_csi = nullptr, *d_cen = nullptr; DevSv *d_sv = nullptr;
 	RefView rf;
 	PairIndexView pix;
+	TextTables tt;                                                // target names and the anchors' tag strings, in device memory
+	std::vector<void*> tt_mem;
 	pansvr_ksw_ctx *own_ksw = nullptr;                            // every instance has its own ksw context (stream + scratch): no lock between blocks
 };
 
@@ -147,6 +149,26 @@ StageService *stage_service_create(const DebgaIndex &idx, SeedService *seeds, vo
 	}
 	s->rf.ref_seq = s->d_ref;
 	s->pix.chr_search_index = s->d_csi; s->pix.chr_end_n = s->d_cen; s->pix.sv = s->d_sv;
+	auto table = [&](const std::vector<std::string> &v, StrTable &t) -> bool {
+		std::vector<uint32_t> off(v.size() + 1, 0);
+		std::string pool;
+		for (size_t i = 0; i < v.size(); ++i) { pool += v[i]; off[i + 1] = (uint32_t)pool.size(); }
+		void *dp = nullptr, *dof = nullptr;
+		if (!up32(pool.data(), pool.size(), &dp)) return false;
+		s->tt_mem.push_back(dp);
+		if (!up32(off.data(), off.size() * 4, &dof)) return false;
+		s->tt_mem.push_back(dof);
+		t.pool = (const char*)dp; t.off = (const uint32_t*)dof; t.n = (uint32_t)v.size();
+		return true;
+	};
+	std::vector<std::string> prints(idx.sv_info.size()), ids(idx.sv_info.size());
+	for (size_t i = 0; i < idx.sv_info.size(); ++i) { prints[i] = idx.sv_info[i].vcf_print; ids[i] = idx.sv_info[i].vcf_id; }
+	if (!table(idx.target_names, s->tt.target_names) || !table(prints, s->tt.sv_print) || !table(ids, s->tt.sv_id)) {
+		err = "stage service: CUDA set-up failed";
+		stage_service_destroy(s);
+		return nullptr;
+	}
+	s->tt.not_ori = 0;
 	return s;
 }
 
@@ -160,6 +182,7 @@ void stage_service_destroy(StageService *s)
 	if (s->d_pos) cudaFree(s->d_pos);
 	if (s->d_ref) cudaFree(s->d_ref);
 	for (void *q : {(void*)s->d_csi, (void*)s->d_cen, (void*)s->d_sv}) if (q) cudaFree(q);
+	for (void *q : s->tt_mem) if (q) cudaFree(q);
 	if (s->own_ksw) pansvr_ksw_destroy(s->own_ksw);
 	if (s->be.st) cudaStreamDestroy(s->be.st);
 	delete s;
@@ -187,12 +210,15 @@ bool stage_service_run(StageService *s, const DevStageIn &in, DevStageOut &out, 
 	return ok;
 }
 
-bool stage_service_finalize(StageService *s, const PairOpts &o, size_t n_pairs, const int8_t *win, DevStageOut &out, std::string &err)
+bool stage_service_finalize(StageService *s, const PairOpts &o, int not_ori, size_t n_pairs, const int8_t *win, const uint32_t *host_len, DevStageOut &out,
+                            HostVec<char> &text_out, std::string &err)
 {
 	if (cudaSetDevice(s->device) != cudaSuccess) { err = "cudaSetDevice failed"; return false; }
 	CudaBackend &be = s->be;
 	be.failed = false; be.why.clear(); be.dev = DevCounters();
-	const bool ok = run_device_finalize(be, s->pix, o, n_pairs, win, out, err);
+	TextTables T = s->tt;
+	T.not_ori = not_ori;
+	const bool ok = run_device_finalize(be, s->pix, o, T, n_pairs, win, host_len, out, text_out, err);
 	be.sync();
 	be.collect_laps();
 	out.dev.add(be.dev);

@@ -21,20 +21,34 @@
 #include "pipeline.hpp"
 #include "stages_core.cuh"
 #include "pair_core.cuh"
+#include "text_core.cuh"
 
 namespace pansvr {
 
 enum DevSlot {
 	SL_TEXT, SL_READS, SL_BITS, SL_LIST, SL_FLAGS, SL_MEM_CNT, SL_MEM_OFF, SL_MEMS, SL_MEMS_TMP, SL_NVU, SL_SEED_CNT, SL_SEED_OFF,
 	SL_SEEDS, SL_SEEDS_TMP, SL_DIST, SL_PRE, SL_PLAN_CNT, SL_PLAN_OFF, SL_CANDS, SL_PIECES, SL_QLEN, SL_TLEN, SL_QOFF, SL_TOFF,
-	SL_Q, SL_T, SL_RES, SL_KCIG, SL_CIGS, SL_MISC, SL_SCAN_TMP, SL_USED, SL_ORI, SL_PSTATE, SL_PROBE, SL_WIN, SL_FINAL, SL_PFINAL, SL_COUNT
+	SL_Q, SL_T, SL_RES, SL_KCIG, SL_CIGS, SL_MISC, SL_SCAN_TMP, SL_USED, SL_ORI, SL_PSTATE, SL_PROBE, SL_WIN, SL_FINAL, SL_PFINAL, SL_RECS, SL_HOSTLEN, SL_TXT_LEN, SL_TXT_OFF, SL_TXT, SL_COUNT
 };
 
 // ---- functors (one element of work each; plain data members only, so they can be passed to a kernel by value)
+struct FnOri {                                                     // original alignment of every read, out of its comment
+	const uint8_t *text; const DevRec *recs; int match; DevOri *ori;
+	SEED_HD void operator()(size_t i) const { dev_parse_ori((const char*)text + recs[i].comment_off, recs[i].comment_l, recs[i].seq_l, match, ori[i]); }
+};
 struct FnEncode {
-	const uint8_t *text; const DevRead *reads; uint64_t *bits; uint8_t *list; uint8_t *flags;
-	SEED_HD void operator()(size_t i) const   // (len 0: a read that is not seeded -- skipped by RR:413-414, or shorter than a k-mer)
-	{ flags[i] = reads[i].len >= LEN_KMER && encode_read(text, reads[i], bits, list) ? (uint8_t)ST_FLAG_STR : (uint8_t)0; }
+	const uint8_t *text; const DevRead *reads; const DevOri *ori; uint64_t *bits; uint8_t *list; uint8_t *flags;
+	SEED_HD void operator()(size_t i) const
+	{
+		const DevRead &rd = reads[i];
+		uint8_t f = 0;
+		// 'N' (its substitution draws rand()) or a lower-case 'n' (code 4 spills into the packed neighbour): the host path keeps the pair
+		for (uint32_t k = 0; k < rd.len; ++k) { const uint8_t c = text[rd.seq_off + k]; if (c == 'N' || c == 'n') { f = ST_FLAG_HOST; break; } }
+		// not seeded: skipped by RR:413-414 (full-score original alignment), or shorter than a k-mer
+		if (!f && (rd.len < LEN_KMER || (ori && ori[i].skip))) f = ST_FLAG_NOSEED;
+		if (!f && encode_read(text, rd, bits, list)) f = ST_FLAG_STR;
+		flags[i] = f;
+	}
 };
 struct FnSeed {                                                    // strand j = 2 * read + strand; fill == false: count only
 	IndexView ix; const DevRead *reads; const uint64_t *bits; const uint8_t *list; const uint8_t *flags;
@@ -42,7 +56,7 @@ struct FnSeed {                                                    // strand j =
 	SEED_HD void operator()(size_t j) const
 	{
 		const DevRead &rd = reads[j >> 1];
-		if (rd.len < LEN_KMER) { if (!fill) count[j] = 0; return; }
+		if (flags[j >> 1] & (ST_FLAG_HOST | ST_FLAG_NOSEED)) { if (!fill) count[j] = 0; return; }
 		const uint32_t s = (uint32_t)(j & 1), words = (rd.len >> 5) + 2, kn = rd.len - LEN_KMER + 1;
 		const uint64_t *b = bits + rd.bits_off + (size_t)s * words;
 		const bool is_str = (flags[j >> 1] & ST_FLAG_STR) != 0;
@@ -135,7 +149,7 @@ struct FnProbe {                                                   // one pair =
 	SEED_HD void operator()(size_t p) const
 	{
 		DevProbe &pr = probe[p];
-		if ((flags[2 * p] | flags[2 * p + 1]) & ST_FLAG_NEEDS_RAND) { pr.redo = PR_REDO_HOST; pr.draws0 = pr.draws1 = pr.ev_cnt = 0; pr.tie_mask = 0; return; }
+		if ((flags[2 * p] | flags[2 * p + 1]) & (ST_FLAG_NEEDS_RAND | ST_FLAG_HOST)) { pr.redo = PR_REDO_HOST; pr.draws0 = pr.draws1 = pr.ev_cnt = 0; pr.tie_mask = 0; return; }
 		ReadView R[2];
 		for (int k = 0; k < 2; ++k) {
 			const size_t i = 2 * p + k;
@@ -182,8 +196,9 @@ struct DevStageIn {
 	const DevRead *reads; size_t n_reads;                          // host: the read table; bits_off / list_off laid out by the caller
 	size_t bits_words, list_bytes;                                 // pool sizes implied by the table
 	AlnScores scores;
-	// stage F on the device: reads 2p, 2p + 1 of the table are the mates of pair p (n_reads even); ori = their original alignments
-	const DevOri *ori = nullptr; PairOpts pair_opts = {0, 0, 0};
+	// stage F on the device: reads 2p, 2p + 1 of the table are the mates of pair p (n_reads even); recs = their FASTQ records
+	// (offsets into `text`): the original alignments are parsed out of the comments, the SAM records written from them
+	const DevRec *recs = nullptr; PairOpts pair_opts = {0, 0, 0};
 	bool want_tables = false;                                      // also bring the sorted seeds and chain tables back (tests)
 };
 struct DevStageOut {                                               // host side, kept across blocks (pinned in the product)
@@ -195,6 +210,8 @@ struct DevStageOut {                                               // host side,
 	HostVec<DevCand> cands; HostVec<DevCigar> cigs;
 	HostVec<DevProbe> pair_probe;                                  // n / 2: what the in-order pass has to do for each pair
 	HostVec<DevFinal> fin; HostVec<DevPairFinal> pfin;             // after run_device_finalize: n and n / 2
+	HostVec<uint32_t> txt_off;                                     // n + 1: place of every read's record in the block's SAM text
+	uint64_t bad_records = 0;                                      // records left out because htslib would reject them (CIGAR does not span the read)
 	uint64_t n_tasks = 0, n_cells = 0, probes = 0;
 	DevCounters dev;
 };
@@ -220,8 +237,17 @@ bool run_device_stages(BE &be, const IndexView &ix, const uint64_t *d_pos, const
 	be.h2d(d_reads, in.reads, n * sizeof(DevRead));
 	be.zero(d_misc, 64);
 	be.zero(d_mem_cnt + 2 * n, 4);
+	// ---- the original alignments (comment fields), when the block came with its record table
+	DevOri *d_ori = nullptr;
+	if (in.recs) {
+		DevRec *d_recs = be.template buf<DevRec>(SL_RECS, n);
+		d_ori = be.template buf<DevOri>(SL_ORI, n);
+		if (!d_recs || !d_ori) { err = "device stages: out of device memory"; return false; }
+		be.h2d(d_recs, in.recs, n * sizeof(DevRec));
+		be.for_each(n, FnOri{d_text, d_recs, in.scores.match, d_ori}, 0);
+	}
 	// ---- A
-	be.for_each(n, FnEncode{d_text, d_reads, d_bits, d_list, d_flags}, 0);
+	be.for_each(n, FnEncode{d_text, d_reads, d_ori, d_bits, d_list, d_flags}, 0);
 	// ---- B
 	unsigned long long *d_probes = (unsigned long long*)(d_misc + 2);
 	FnSeed fs{ix, d_reads, d_bits, d_list, d_flags, d_mem_cnt, d_mem_off, nullptr, d_probes, false};
@@ -305,14 +331,12 @@ bool run_device_stages(BE &be, const IndexView &ix, const uint64_t *d_pos, const
 	}
 	// ---- F (probe): chain selection, candidate sort and pairing of every pair against a scripted generator
 	out.pair_probe.clear();
-	if (in.ori && (n & 1) == 0) {
+	if (d_ori && (n & 1) == 0) {
 		const size_t np = n / 2;
 		uint8_t *d_used = be.template buf<uint8_t>(SL_USED, n_seeds + 16);
-		DevOri *d_ori = be.template buf<DevOri>(SL_ORI, n);
 		DevPairState *d_state = be.template buf<DevPairState>(SL_PSTATE, np);
 		DevProbe *d_probe = be.template buf<DevProbe>(SL_PROBE, np);
-		if (!d_used || !d_ori || !d_state || !d_probe) { err = "device stages: out of device memory"; return false; }
-		be.h2d(d_ori, in.ori, n * sizeof(DevOri));
+		if (!d_used || !d_state || !d_probe) { err = "device stages: out of device memory"; return false; }
 		be.for_each(np, FnProbe{pix, in.pair_opts, d_flags, d_seed_off, d_seeds, d_dist, d_pre, d_used, d_plan_off, be.template buf<DevCand>(SL_CANDS, 0), d_ori, d_state, d_probe}, 6);
 		out.pair_probe.resize(np);
 		be.d2h(out.pair_probe.data(), d_probe, np * sizeof(DevProbe));
@@ -321,21 +345,73 @@ bool run_device_stages(BE &be, const IndexView &ix, const uint64_t *d_pos, const
 	return true;
 }
 
-// Second trip of a block whose pairs were probed: the winners the in-order pass drew for the pairs with pairing ties go up,
-// primary / secondary / mate of every read come back.  win: 2 entries per pair (candidate index of each mate, -1 = none).
+struct FnText {                                                    // the SAM record of read i; len[i] = its length (count pass), or written at off[i]
+	const uint8_t *text; const DevRec *recs; const DevOri *ori; const DevFinal *fin; const DevPairFinal *pfin; const DevCand *cands; const DevCigar *cigs;
+	TextTables T; const uint32_t *host_len; uint32_t *len; const uint32_t *off; char *out; uint32_t *bad; bool write;
+	SEED_HD void operator()(size_t i) const
+	{
+		const size_t p = i >> 1; const int m = (int)(i & 1);
+		if (!write) {
+			if (!pfin[p].valid) { len[i] = m == 0 ? host_len[p] : 0u; return; }       // a pair the host path finished: room for its text
+			CountSink s; s.n = 0;
+			const int b = dev_sam_record(s, (const char*)text, recs[i], ori[i], fin[i], pfin[p], m, cands, cigs, T);
+			len[i] = s.n;
+#if defined(__CUDA_ARCH__)
+			if (b) atomicAdd(bad, 1u);
+#else
+			if (b) ++*bad;
+#endif
+		} else {
+			if (!pfin[p].valid) return;
+			WriteSink s; s.p = out + off[i]; s.n = 0;
+			dev_sam_record(s, (const char*)text, recs[i], ori[i], fin[i], pfin[p], m, cands, cigs, T);
+		}
+	}
+};
+
+// Second trip of a block whose pairs were probed: the winners the in-order pass drew for the pairs with pairing ties go up
+// (win: 2 entries per pair, the candidate index of each mate, -1 = none), with the length of the text the host path produced for
+// each of its pairs (host_len, 0 elsewhere); primary / secondary / mate of every read come back, and the block's SAM text with
+// every record in its place (gaps of host_len bytes where the host's pairs go: out.txt_off[2p] is the place of pair p).
 template <class BE>
-bool run_device_finalize(BE &be, const PairIndexView &pix, const PairOpts &o, size_t n_pairs, const int8_t *win, DevStageOut &out, std::string &err)
+bool run_device_finalize(BE &be, const PairIndexView &pix, const PairOpts &o, const TextTables &T, size_t n_pairs, const int8_t *win, const uint32_t *host_len,
+                         DevStageOut &out, HostVec<char> &text_out, std::string &err)
 {
-	out.fin.resize(2 * n_pairs); out.pfin.resize(n_pairs);
-	if (n_pairs == 0) return true;
-	int8_t *d_win = be.template buf<int8_t>(SL_WIN, 2 * n_pairs);
-	DevFinal *d_fin = be.template buf<DevFinal>(SL_FINAL, 2 * n_pairs);
+	out.fin.resize(2 * n_pairs); out.pfin.resize(n_pairs); out.txt_off.resize(2 * n_pairs + 1);
+	out.bad_records = 0;
+	text_out.clear();
+	if (n_pairs == 0) { out.txt_off[0] = 0; return true; }
+	const size_t n = 2 * n_pairs;
+	int8_t *d_win = be.template buf<int8_t>(SL_WIN, n);
+	DevFinal *d_fin = be.template buf<DevFinal>(SL_FINAL, n);
 	DevPairFinal *d_pfin = be.template buf<DevPairFinal>(SL_PFINAL, n_pairs);
-	if (!d_win || !d_fin || !d_pfin) { err = "device stages: out of device memory"; return false; }
-	be.h2d(d_win, win, 2 * n_pairs);
-	be.for_each(n_pairs, FnFinalize{pix, o, be.template buf<DevOri>(SL_ORI, 0), be.template buf<DevPairState>(SL_PSTATE, 0), be.template buf<DevProbe>(SL_PROBE, 0), d_win, d_fin, d_pfin}, 6);
-	be.d2h(out.fin.data(), d_fin, 2 * n_pairs * sizeof(DevFinal));
+	uint32_t *d_hl = be.template buf<uint32_t>(SL_HOSTLEN, n_pairs), *d_len = be.template buf<uint32_t>(SL_TXT_LEN, n + 1), *d_off = be.template buf<uint32_t>(SL_TXT_OFF, n + 1);
+	uint32_t *d_misc = be.template buf<uint32_t>(SL_MISC, 16);
+	if (!d_win || !d_fin || !d_pfin || !d_hl || !d_len || !d_off) { err = "device stages: out of device memory"; return false; }
+	be.h2d(d_win, win, n);
+	be.h2d(d_hl, host_len, n_pairs * 4);
+	be.zero(d_misc, 64);
+	be.zero(d_len + n, 4);
+	const DevOri *d_ori = be.template buf<DevOri>(SL_ORI, 0);
+	be.for_each(n_pairs, FnFinalize{pix, o, d_ori, be.template buf<DevPairState>(SL_PSTATE, 0), be.template buf<DevProbe>(SL_PROBE, 0), d_win, d_fin, d_pfin}, 6);
+	FnText ft{be.template buf<uint8_t>(SL_TEXT, 0), be.template buf<DevRec>(SL_RECS, 0), d_ori, d_fin, d_pfin, be.template buf<DevCand>(SL_CANDS, 0), be.template buf<DevCigar>(SL_CIGS, 0),
+	          T, d_hl, d_len, d_off, nullptr, d_misc, false};
+	be.for_each(n, ft, 7);
+	be.scan(d_len, d_off, n + 1);
+	be.d2h(out.txt_off.data(), d_off, (n + 1) * 4);
+	be.d2h(out.fin.data(), d_fin, n * sizeof(DevFinal));
 	be.d2h(out.pfin.data(), d_pfin, n_pairs * sizeof(DevPairFinal));
+	uint32_t bad = 0;
+	be.d2h(&bad, d_misc, 4);
+	be.sync();
+	out.bad_records = bad;
+	const size_t total = out.txt_off[n];
+	char *d_txt = be.template buf<char>(SL_TXT, total + 16);
+	if (!d_txt) { err = "device stages: out of device memory"; return false; }
+	ft.out = d_txt; ft.write = true;
+	be.for_each(n, ft, 7);
+	text_out.resize(total);
+	be.d2h(text_out.data(), d_txt, total);
 	be.sync();
 	return true;
 }
@@ -348,6 +424,7 @@ void stage_service_set_scoring(StageService *s, const AlnScores &o, int zdrop); 
 // A service instance holds one block's device state from stage_service_run to stage_service_finalize (two trips with the host's
 // in-order pass in between); blocks in flight at the same time use different instances.
 bool stage_service_run(StageService *s, const DevStageIn &in, DevStageOut &out, std::string &err);
-bool stage_service_finalize(StageService *s, const PairOpts &o, size_t n_pairs, const int8_t *win, DevStageOut &out, std::string &err);
+bool stage_service_finalize(StageService *s, const PairOpts &o, int not_ori, size_t n_pairs, const int8_t *win, const uint32_t *host_len, DevStageOut &out,
+                            HostVec<char> &text_out, std::string &err);
 
 } // namespace pansvr

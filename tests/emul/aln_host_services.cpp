@@ -73,7 +73,12 @@ struct HostBackend {
 	}
 };
 
-struct StageService { HostBackend be; IndexView view; const uint64_t *pos; RefView rf; std::vector<DevSv> svs; PairIndexView pix; };
+struct HostStrTable {
+	std::string pool; std::vector<uint32_t> off;
+	void build(const std::vector<std::string> &v) { off.assign(v.size() + 1, 0); pool.clear(); for (size_t i = 0; i < v.size(); ++i) { pool += v[i]; off[i + 1] = (uint32_t)pool.size(); } }
+	StrTable view() const { StrTable t; t.pool = pool.data(); t.off = off.data(); t.n = (uint32_t)off.size() - 1; return t; }
+};
+struct StageService { HostBackend be; IndexView view; const uint64_t *pos; RefView rf; std::vector<DevSv> svs; PairIndexView pix; HostStrTable names, prints, ids; };
 
 StageService *stage_service_create(const DebgaIndex &idx, SeedService *seeds, void *, int, std::string &)
 {
@@ -82,6 +87,9 @@ StageService *stage_service_create(const DebgaIndex &idx, SeedService *seeds, vo
 	s->svs.resize(idx.sv_info.size());
 	for (size_t i = 0; i < s->svs.size(); ++i) { s->svs[i].chr_id = idx.sv_info[i].chr_id; s->svs[i].st_pos = (uint32_t)idx.sv_info[i].st_pos; s->svs[i].end_offset = idx.sv_info[i].end_offset; s->svs[i].pad = 0; }
 	s->pix.chr_search_index = idx.chr_search_index.data(); s->pix.chr_end_n = idx.chr_end_n.data(); s->pix.sv = s->svs.data();
+	std::vector<std::string> prints(idx.sv_info.size()), ids(idx.sv_info.size());
+	for (size_t i = 0; i < idx.sv_info.size(); ++i) { prints[i] = idx.sv_info[i].vcf_print; ids[i] = idx.sv_info[i].vcf_id; }
+	s->names.build(idx.target_names); s->prints.build(prints); s->ids.build(ids);
 	return s;
 }
 void stage_service_destroy(StageService *s) { delete s; }
@@ -97,9 +105,12 @@ bool stage_service_run(StageService *s, const DevStageIn &in, DevStageOut &out, 
 {
 	return run_device_stages(s->be, s->view, s->pos, s->rf, s->pix, in, out, err);
 }
-bool stage_service_finalize(StageService *s, const PairOpts &o, size_t n_pairs, const int8_t *win, DevStageOut &out, std::string &err)
+bool stage_service_finalize(StageService *s, const PairOpts &o, int not_ori, size_t n_pairs, const int8_t *win, const uint32_t *host_len, DevStageOut &out,
+                            HostVec<char> &text_out, std::string &err)
 {
-	return run_device_finalize(s->be, s->pix, o, n_pairs, win, out, err);
+	TextTables T;
+	T.target_names = s->names.view(); T.sv_print = s->prints.view(); T.sv_id = s->ids.view(); T.not_ori = not_ori;
+	return run_device_finalize(s->be, s->pix, o, T, n_pairs, win, host_len, out, text_out, err);
 }
 
 } // namespace pansvr
