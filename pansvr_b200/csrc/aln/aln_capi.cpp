@@ -9,6 +9,7 @@
 #include <chrono>
 #include <condition_variable>
 #include <deque>
+#include <functional>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -257,42 +258,111 @@ void add_parts(std::vector<Part> &parts, const char *p, size_t n)
 	}
 }
 
-int run_block(pansvr_aln_ctx *c, const char *fastq, size_t n, std::vector<Part> &sam, std::vector<Part> &ori)
+// Where the sub-blocks of a text start, without parsing it: strict 4-line FASTQ (what fc_signal writes) has 8 lines per pair, so the
+// helper threads count the line ends of their slices and the cuts are the line ends whose number is a multiple of 8 * per.
+// false = the text is not of that form (no final newline, a line count that is not a multiple of 8): the host parser decides.
+bool cut_text(const char *p, size_t n, AlnPipeline &pipe, int threads, size_t &n_pairs, size_t &per, std::vector<size_t> &cuts)
+{
+	if (n == 0 || p[n - 1] != '\n') return false;
+	const size_t T = (size_t)std::max(1, threads), slice = (n + T - 1) / T;
+	std::vector<size_t> nl(T + 1, 0);
+	pipe.parallel(T, [&](size_t b, size_t e, int) {
+		for (size_t t = b; t < e; ++t) {
+			const size_t s0 = std::min(n, slice * t), s1 = std::min(n, slice * (t + 1));
+			size_t c = 0;
+			for (const char *q = p + s0, *qe = p + s1; (q = (const char*)memchr(q, '\n', (size_t)(qe - q))) != nullptr; ++q) ++c;
+			nl[t + 1] = c;
+		}
+	}, 2);
+	for (size_t t = 0; t < T; ++t) nl[t + 1] += nl[t];
+	if (nl[T] % 8 != 0) return false;
+	n_pairs = nl[T] / 8;
+	per = n_pairs;
+	if (threads > 1 && n_pairs >= 65536) per = std::min<size_t>(262144, std::max<size_t>(32768, (n_pairs + 3) / 4));
+	if (const char *e = getenv("PANSVR_SUB_PAIRS")) { const long v = atol(e); if (v > 0) per = (size_t)v; }   // tests: force the cut
+	const size_t n_sub = n_pairs ? (n_pairs + per - 1) / per : 1;
+	cuts.assign(n_sub + 1, n);
+	cuts[0] = 0;
+	for (size_t k = 1; k < n_sub; ++k) {
+		const size_t want = 8 * per * k;                           // the cut is right after line end number `want` (1-based)
+		size_t t = 0;
+		while (nl[t + 1] < want) ++t;
+		size_t seen = nl[t];
+		const char *q = p + std::min(n, slice * t);
+		for (;;) { q = (const char*)memchr(q, '\n', (size_t)(p + n - q)); ++seen; ++q; if (seen == want) break; }
+		cuts[k] = (size_t)(q - p);
+	}
+	return true;
+}
+
+int run_block(pansvr_aln_ctx *c, const char *fastq, size_t n, std::vector<Part> &sam, std::vector<Part> &ori,
+              const std::function<void(const BlockOutput&)> *on_done = nullptr)
 {
 	const auto tick = []() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
 	const double t0 = tick();
 	std::vector<FastqRec> recs;
-	if (!parse_fastq_parallel(fastq, n, *c->pipe, c->opt.threads, recs)) parse_fastq(fastq, n, recs);
+	size_t n_pairs = 0, per = 0;
+	std::vector<size_t> cuts;
+	// device path: the text goes up as it is and the records are found there; the host only needs to know where to cut
+	bool as_text = c->pipe->has_device_stages() && cut_text(fastq, n, *c->pipe, c->opt.threads, n_pairs, per, cuts);
+	if (as_text) {
+		std::vector<FastqRec> first;
+		const char *q = fastq; int lines = 0;
+		while (lines < 4 && q < fastq + n) { q = (const char*)memchr(q, '\n', (size_t)(fastq + n - q)); if (!q) break; ++q; ++lines; }
+		if (lines == 4) parse_fastq(fastq, (size_t)(q - fastq), first);
+		if (first.empty()) as_text = false; else c->pipe->ensure_read_stats(first[0]);
+	}
+	if (!as_text) {
+		if (!parse_fastq_parallel(fastq, n, *c->pipe, c->opt.threads, recs)) parse_fastq(fastq, n, recs);
+		n_pairs = recs.size() / 2;
+		per = n_pairs;                                            // pairs per sub-block
+		if (c->opt.threads > 1 && n_pairs >= 65536) per = std::min<size_t>(262144, std::max<size_t>(32768, (n_pairs + 3) / 4));
+		if (const char *e = getenv("PANSVR_SUB_PAIRS")) { const long v = atol(e); if (v > 0) per = (size_t)v; }   // tests: force the cut
+		if (!recs.empty()) c->pipe->ensure_read_stats(recs[0]);
+	}
 	c->pipe->stats.t_stage[6] += tick() - t0;
-	const size_t n_pairs = recs.size() / 2;
-	size_t per = n_pairs;                                     // pairs per sub-block
-	if (c->opt.threads > 1 && n_pairs >= 65536) per = std::min<size_t>(262144, std::max<size_t>(32768, (n_pairs + 3) / 4));
-	if (const char *e = getenv("PANSVR_SUB_PAIRS")) { const long v = atol(e); if (v > 0) per = (size_t)v; }   // tests: force the cut
 	const size_t n_sub = n_pairs ? (n_pairs + per - 1) / per : 1;
 	if (c->outs.size() < n_sub) c->outs.resize(n_sub);
-	if (!recs.empty()) c->pipe->ensure_read_stats(recs[0]);
 	std::vector<std::string> errs(n_sub);
 	std::vector<uint8_t> ok(n_sub, 1);
 	std::vector<uint64_t> seqs(n_sub);
 	for (size_t k = 0; k < n_sub; ++k) seqs[k] = c->pipe->next_seq();
 	auto run_sub = [&](size_t k) {
 		const size_t pb = std::min(n_pairs, per * k), pe = std::min(n_pairs, per * (k + 1));
+		if (as_text) {
+			bool reparse = false;
+			ok[k] = c->pipe->align_block_text(fastq + cuts[k], cuts[k + 1] - cuts[k], pe - pb, c->outs[k], errs[k], seqs[k], &reparse) ? 1 : 0;
+			if (!ok[k] || !reparse) return;
+			std::vector<FastqRec> mine;                             // not what it looked like (a header line without '@', ...): the host parser's records
+			parse_fastq(fastq + cuts[k], cuts[k + 1] - cuts[k], mine);
+			ok[k] = c->pipe->align_block(mine.data(), mine.size(), c->outs[k], errs[k], seqs[k]) ? 1 : 0;
+			return;
+		}
 		ok[k] = c->pipe->align_block(recs.data() + 2 * pb, 2 * (pe - pb), c->outs[k], errs[k], seqs[k]) ? 1 : 0;
 	};
+	// on_done: the caller takes every sub-block's output as soon as it and all earlier ones are finished, while later ones still run
+	size_t handed = 0;
+	auto hand_over = [&](size_t upto) { if (on_done) for (; handed < upto; ++handed) if (ok[handed]) (*on_done)(c->outs[handed]); };
 	if (n_sub == 1) run_sub(0);
 	else {
-		// two in flight; all of them while the context waits for another process's stream state (pansvr_aln_await_state), so that
-		// only the in-order passes wait and every other stage of the shard is done by the time the state arrives
-		const size_t flight = c->pipe->awaiting_streams() ? n_sub : 2;
+		// a few in flight (their device trips and host passes overlap); all of them while the context waits for another process's
+		// stream state (pansvr_aln_await_state), so that only the in-order passes wait and every other stage of the shard is done by
+		// the time the state arrives
+		size_t flight = c->pipe->has_device_stages() ? 3 : 2;
+		if (const char *e = getenv("PANSVR_FLIGHT")) { const long v = atol(e); if (v > 0) flight = (size_t)v; }
+		if (c->pipe->awaiting_streams()) flight = n_sub;
 		std::vector<std::thread> th(n_sub);
 		for (size_t k = 0; k < n_sub; ++k) {
-			if (k >= flight) th[k - flight].join();
+			if (k >= flight) { th[k - flight].join(); }
 			th[k] = std::thread(run_sub, k);
+			if (k >= flight) hand_over(k - flight + 1);
 		}
-		for (size_t k = n_sub >= flight ? n_sub - flight : 0; k < n_sub; ++k) th[k].join();
+		for (size_t k = n_sub >= flight ? n_sub - flight : 0; k < n_sub; ++k) { th[k].join(); hand_over(k + 1); }
 	}
 	for (size_t k = 0; k < n_sub; ++k) if (!ok[k]) { g_aln_err = errs[k]; return PANSVR_E_CUDA; }
+	hand_over(n_sub);
 	sam.clear(); ori.clear();
+	if (on_done) return 0;
 	for (size_t k = 0; k < n_sub; ++k) {
 		if (c->outs[k].sam_text.size()) add_parts(sam, c->outs[k].sam_text.data(), c->outs[k].sam_text.size());     // device path: one text per sub-block
 		for (const std::string &x : c->outs[k].sam) if (!x.empty()) add_parts(sam, x.data(), x.size());
@@ -320,24 +390,43 @@ int pansvr_aln_block(pansvr_aln_ctx *c, const char *fastq, size_t n, char **sam,
 {
 	if (!c || !fastq || !sam || !ori) return PANSVR_E_ARG;
 	CallReport report(c);
-	std::vector<Part> text_sam, text_ori;
-	const int rc = run_block(c, fastq, n, text_sam, text_ori);
-	if (rc != 0) return rc;
-	const double t0 = CallReport::now();
-	auto join = [&](const std::vector<Part> &parts, char **out, size_t *bytes) -> bool {     // chunk buffers -> one malloc'ed text
-		const size_t np = parts.size();
-		std::vector<size_t> off(np + 1, 0);
-		for (size_t i = 0; i < np; ++i) off[i + 1] = off[i] + parts[i].n;
-		char *buf = (char*)malloc(off[np] + 1);
-		if (!buf) return false;
-		c->pipe->parallel(np, [&](size_t b, size_t e, int) { for (size_t i = b; i < e; ++i) if (parts[i].n) memcpy(buf + off[i], parts[i].p, parts[i].n); }, 2);
-		buf[off[np]] = 0;
-		*out = buf;
-		if (bytes) *bytes = off[np];
-		return true;
+	// The output text is assembled while the block is still being aligned: every finished sub-block is copied to its place behind the
+	// earlier ones.  Room for 2.5 x the input (a record grows by its fixed fields and tags) is only address space until it is written;
+	// it grows if that should not be enough.
+	struct Grow {
+		char *p = nullptr; size_t cap = 0, used = 0;
+		bool room(size_t more) { if (used + more + 1 <= cap) return true; const size_t want = std::max(cap * 2, used + more + 1); char *q = (char*)realloc(p, want); if (!q) return false; p = q; cap = want; return true; }
+	} gs, go;
+	gs.cap = n / 2 * 5 + (1 << 16); gs.p = (char*)malloc(gs.cap);
+	go.cap = 1 << 16; go.p = (char*)malloc(go.cap);
+	bool oom = !gs.p || !go.p;
+	double t_join = 0;
+	const std::function<void(const BlockOutput&)> take = [&](const BlockOutput &o) {
+		const double t0 = CallReport::now();
+		std::vector<Part> ps, po;
+		if (o.sam_text.size()) add_parts(ps, o.sam_text.data(), o.sam_text.size());
+		for (const std::string &x : o.sam) if (!x.empty()) add_parts(ps, x.data(), x.size());
+		for (const std::string &x : o.ori) if (!x.empty()) add_parts(po, x.data(), x.size());
+		auto append = [&](Grow &g, const std::vector<Part> &parts) {
+			size_t tot = 0;
+			for (const Part &q : parts) tot += q.n;
+			if (oom || !g.room(tot)) { oom = true; return; }
+			std::vector<size_t> off(parts.size() + 1, g.used);
+			for (size_t i = 0; i < parts.size(); ++i) off[i + 1] = off[i] + parts[i].n;
+			c->pipe->parallel(parts.size(), [&](size_t b, size_t e, int) { for (size_t i = b; i < e; ++i) memcpy(g.p + off[i], parts[i].p, parts[i].n); }, 2);
+			g.used += tot;
+		};
+		append(gs, ps); append(go, po);
+		t_join += CallReport::now() - t0;
 	};
-	if (!join(text_sam, sam, sam_bytes) || !join(text_ori, ori, ori_bytes)) { g_aln_err = "out of memory"; return PANSVR_E_ARG; }
-	c->pipe->stats.t_stage[7] += CallReport::now() - t0;
+	std::vector<Part> unused_s, unused_o;
+	const int rc = run_block(c, fastq, n, unused_s, unused_o, &take);
+	if (rc != 0 || oom) { free(gs.p); free(go.p); if (rc == 0) { g_aln_err = "out of memory"; return PANSVR_E_ARG; } return rc; }
+	gs.p[gs.used] = 0; go.p[go.used] = 0;
+	*sam = gs.p; *ori = go.p;
+	if (sam_bytes) *sam_bytes = gs.used;
+	if (ori_bytes) *ori_bytes = go.used;
+	c->pipe->stats.t_stage[7] += t_join;
 	return 0;
 }
 

@@ -320,14 +320,17 @@ SEED_HD void dev_probe_pair(const PairIndexView &ix, const PairOpts &o, const Re
 	pr.redo = 0; pr.draws0 = pr.draws1 = 0; pr.ev_cnt = 0; pr.tie_mask = 0;
 	DevTap probe;
 	int n0 = 0, n1 = 0;
-	const int c0 = dev_explore_read(ix, R[0], st.res[0], &n0, probe);
-	const int c1 = c0 < 0 ? -1 : dev_explore_read(ix, R[1], st.res[1], &n1, probe);
+	DevRes res0[PR_MAX_RES], res1[PR_MAX_RES];                     // (worked on locally; only the candidates that exist go to the pair's state)
+	const int c0 = dev_explore_read(ix, R[0], res0, &n0, probe);
+	const int c1 = c0 < 0 ? -1 : dev_explore_read(ix, R[1], res1, &n1, probe);
 	if (c0 < 0 || c1 < 0 || c0 > 250 || c1 > 250) { pr.redo = PR_REDO_HOST; return; }
 	st.n[0] = (uint8_t)n0; st.n[1] = (uint8_t)n1;
+	for (int k = 0; k < n0; ++k) st.res[0][k] = res0[k];
+	for (int k = 0; k < n1; ++k) st.res[1][k] = res1[k];
 	pr.draws0 = (uint8_t)c0; pr.draws1 = (uint8_t)c1;
 	PairSide S[2];
-	S[0].res = st.res[0]; S[0].n = n0; S[0].ori = R[0].ori;
-	S[1].res = st.res[1]; S[1].n = n1; S[1].ori = R[1].ori;
+	S[0].res = res0; S[0].n = n0; S[0].ori = R[0].ori;
+	S[1].res = res1; S[1].n = n1; S[1].ori = R[1].ori;
 	probe.restart(0);
 	EventSink ev; ev.pr = &pr; ev.overflow = false;
 	dev_pair_up(ix, o, S, st.pe, probe, &ev);

@@ -1150,6 +1150,7 @@ AlnPipeline::~AlnPipeline()
 {
 	delete workers_;
 	for (DevBuffers *b : dev_all_) { if (b->owned) stage_service_destroy(b->svc); delete b; }
+	for (HostSlot *h : host_all_) delete h;
 }
 
 AlnPipeline::DevBuffers *AlnPipeline::acquire_dev(std::string &err)
@@ -1170,6 +1171,17 @@ AlnPipeline::DevBuffers *AlnPipeline::acquire_dev(std::string &err)
 }
 
 void AlnPipeline::release_dev(DevBuffers *b) { std::lock_guard<std::mutex> lk(dev_pool_m_); dev_free_.push_back(b); }
+
+AlnPipeline::HostSlot *AlnPipeline::acquire_host()
+{
+	std::lock_guard<std::mutex> lk(dev_pool_m_);
+	if (!host_free_.empty()) { HostSlot *h = host_free_.back(); host_free_.pop_back(); return h; }
+	HostSlot *h = new HostSlot();
+	host_all_.push_back(h);
+	return h;
+}
+
+void AlnPipeline::release_host(HostSlot *h) { std::lock_guard<std::mutex> lk(dev_pool_m_); host_free_.push_back(h); }
 
 // read statistics from the first comment of the input (load_reads, RR:134-148); must have run before two blocks are in flight
 void AlnPipeline::ensure_read_stats(const FastqRec &first)
@@ -1371,7 +1383,9 @@ bool AlnPipeline::align_block_host(const FastqRec *recs, size_t n_reads_in, Bloc
 	};
 	// a real read with N is not encoded here (its bases depend on the draws); the N-free mate of such a read is
 	for (size_t i = 0; i < n_all; ++i) { ReadState &r = rs[i]; r.batched = !(r.skip || r.has_n || r.read_l < LEN_KMER); }
-	SeedBatch &sb = seed_main_[seq & 1];
+	HostSlot *hslot = acquire_host();
+	struct HostRelease { AlnPipeline &P; HostSlot *h; ~HostRelease() { P.release_host(h); } } host_release{*this, hslot};
+	SeedBatch &sb = hslot->seeds;
 	sb.clear();
 	{
 		std::vector<uint32_t> word_off(n_all + 1, 0), job_of(n_all + 1, 0);
@@ -1479,7 +1493,7 @@ bool AlnPipeline::align_block_host(const FastqRec *recs, size_t n_reads_in, Bloc
 	}
 	add_time(2, now() - t0); t0 = now();
 	// ---- stage D: per-thread task lists, concatenated afterwards
-	KswBatchBuf &tasks = ksw_main_[seq & 1];
+	KswBatchBuf &tasks = hslot->ksw;
 	{
 		std::vector<KswTaskList> part((size_t)T + 1);                      // one list per chunk of reads, the last one for the variants
 		std::vector<size_t> lo((size_t)T, 0), hi((size_t)T, 0);
@@ -1736,49 +1750,78 @@ bool AlnPipeline::align_block(const FastqRec *recs, size_t n_reads_in, BlockOutp
 	const size_t n_pairs = n_reads_in / 2, nd = 2 * n_pairs;
 	out.sam_text.clear();
 	if (!stages_ || n_pairs == 0) return align_block_host(recs, n_reads_in, out, err, seq, nullptr);
-	Impl I(*this);
-	const DebgaIndex &idx = idx_;
-	auto add_time = [&](int stage, double dt) { std::lock_guard<std::mutex> lk(stats_m_); stats.t_stage[stage] += dt; };
-	double t0 = now();
 	ensure_read_stats(recs[0]);
-	DevBuffers *db = acquire_dev(err);
-	if (!db) return false;
-	struct Release { AlnPipeline &P; DevBuffers *b; ~Release() { P.release_dev(b); } } release{*this, db};
-	// ---- the block's text and record table go up as they are: records are views into one buffer, in input order
+	// records are views into one buffer, in input order: the text they span goes up as it is
 	const char *base = recs[0].name;
 	const char *end = recs[nd - 1].qual + recs[nd - 1].qual_l;
 	for (size_t t = 0; t < nd; t += 1 + (nd > 2 ? nd - 2 : 0)) {          // (first and last suffice for a parsed buffer; be safe about odd callers)
 		base = std::min(base, recs[t].name); end = std::max(end, recs[t].qual + recs[t].qual_l);
 	}
-	const size_t text_bytes = (size_t)(end - base);
+	return align_block_dev(base, (size_t)(end - base), recs, n_pairs, out, err, seq, nullptr);
+}
+
+// A block given as text: strict 4-line FASTQ of n_pairs interleaved pairs (the caller counted the lines).  The record table is
+// made on the device; *reparse = true (and nothing done) if the text turns out not to be what it was taken for.
+bool AlnPipeline::align_block_text(const char *text, size_t bytes, size_t n_pairs, BlockOutput &out, std::string &err, uint64_t seq, bool *reparse)
+{
+	*reparse = false;
+	out.sam_text.clear();
+	if (!stages_ || n_pairs == 0) { *reparse = true; return true; }
+	return align_block_dev(text, bytes, nullptr, n_pairs, out, err, seq, reparse);
+}
+
+bool AlnPipeline::align_block_dev(const char *base, size_t text_bytes, const FastqRec *recs, size_t n_pairs, BlockOutput &out, std::string &err, uint64_t seq, bool *reparse)
+{
+	const size_t nd = 2 * n_pairs;
+	Impl I(*this);
+	const DebgaIndex &idx = idx_;
+	auto add_time = [&](int stage, double dt) { std::lock_guard<std::mutex> lk(stats_m_); stats.t_stage[stage] += dt; };
+	double t0 = now();
+	DevBuffers *db = acquire_dev(err);
+	if (!db) return false;
+	struct Release { AlnPipeline &P; DevBuffers *b; ~Release() { P.release_dev(b); } } release{*this, db};
 	if (text_bytes >= 0xfffffff0ull) { err = "block too large for the device stages (cut it into smaller blocks)"; return false; }
 	db->text.resize(text_bytes + 1);
 	{
 		const size_t piece = (size_t)4 << 20, n_piece = (text_bytes + piece - 1) / piece;
 		parallel(n_piece, [&](size_t b, size_t e, int) { for (size_t k = b; k < e; ++k) memcpy(db->text.data() + k * piece, base + k * piece, std::min(piece, text_bytes - k * piece)); }, 2);
 	}
-	db->reads.resize(nd); db->recs.resize(nd);
 	size_t words = 0, list_bytes = 0;
-	for (size_t t = 0; t < nd; ++t) {
-		const FastqRec &r = recs[t];
-		DevRec &dr = db->recs[t];
-		dr.name_off = (uint32_t)(r.name - base); dr.comment_off = (uint32_t)(r.comment - base); dr.seq_off = (uint32_t)(r.seq - base); dr.qual_off = (uint32_t)(r.qual - base);
-		dr.name_l = r.name_l; dr.comment_l = r.comment_l; dr.seq_l = r.seq_l; dr.qual_l = r.qual_l;
-		DevRead &d = db->reads[t];
-		d.seq_off = dr.seq_off; d.len = r.seq_l; d.var_code = 0; d.bits_off = (uint32_t)words; d.list_off = (uint32_t)list_bytes;
-		if (r.seq_l >= LEN_KMER) { words += 2 * (size_t)((r.seq_l >> 5) + 2); list_bytes += 2 * (size_t)(r.seq_l - LEN_KMER + 1); }
+	if (recs) {
+		db->reads.resize(nd); db->recs.resize(nd);
+		for (size_t t = 0; t < nd; ++t) {
+			const FastqRec &r = recs[t];
+			DevRec &dr = db->recs[t];
+			dr.name_off = (uint32_t)(r.name - base); dr.comment_off = (uint32_t)(r.comment - base); dr.seq_off = (uint32_t)(r.seq - base); dr.qual_off = (uint32_t)(r.qual - base);
+			dr.name_l = r.name_l; dr.comment_l = r.comment_l; dr.seq_l = r.seq_l; dr.qual_l = r.qual_l;
+			DevRead &d = db->reads[t];
+			d.seq_off = dr.seq_off; d.len = r.seq_l; d.var_code = 0; d.bits_off = (uint32_t)words; d.list_off = (uint32_t)list_bytes;
+			if (r.seq_l >= LEN_KMER) { words += 2 * (size_t)((r.seq_l >> 5) + 2); list_bytes += 2 * (size_t)(r.seq_l - LEN_KMER + 1); }
+		}
+		if (words >= 0xffffffffull || list_bytes >= 0xffffffffull) { err = "block too large for the device stages (cut it into smaller blocks)"; return false; }
 	}
-	if (words >= 0xffffffffull || list_bytes >= 0xffffffffull) { err = "block too large for the device stages (cut it into smaller blocks)"; return false; }
 	add_time(0, now() - t0); t0 = now();
 	// ---- first trip: the original alignments, stages A..F1 and the probe of stage F
 	DevStageIn in;
 	in.text = db->text.data(); in.text_bytes = text_bytes; in.reads = db->reads.data(); in.n_reads = nd; in.bits_words = words; in.list_bytes = list_bytes;
 	in.scores = AlnScores{opt.match, opt.mismatch, opt.gap_open, opt.gap_ex, opt.gap_open2, opt.gap_ex2};
-	in.recs = db->recs.data(); in.pair_opts = PairOpts{opt.isize_max, opt.isize_min, opt.read_len};
+	in.recs = recs ? db->recs.data() : nullptr; in.parse_text = recs == nullptr;
+	in.pair_opts = PairOpts{opt.isize_max, opt.isize_min, opt.read_len};
 	const char *dump = getenv("PANSVR_DUMP_STAGES");
 	in.want_tables = dump != nullptr;
 	if (!stage_service_run(db->svc, in, db->out, err)) return false;
 	DevStageOut &o = db->out;
+	if (!o.parse_ok) { if (reparse) { *reparse = true; return true; } err = "internal error: record table rejected"; return false; }
+	// a record of the block as the host path sees it
+	const DevRec *drecs = recs ? db->recs.data() : o.recs.data();
+	auto rec_at = [&](size_t t) -> FastqRec {
+		if (recs) return recs[t];
+		const DevRec &d = drecs[t];
+		FastqRec r;
+		r.name = base + d.name_off; r.comment = base + d.comment_off; r.seq = base + d.seq_off; r.qual = base + d.qual_off;
+		r.name_l = d.name_l; r.comment_l = d.comment_l; r.seq_l = d.seq_l; r.qual_l = d.qual_l;
+		return r;
+	};
 	add_time(1, now() - t0); t0 = now();
 	if (dump) {                                                           // tests: what the device stages returned, for the differential
 		const std::string path = std::string(dump) + "." + std::to_string(seq);   // between the CUDA backend and the host-stepped one
@@ -1805,7 +1848,7 @@ bool AlnPipeline::align_block(const FastqRec *recs, size_t n_reads_in, BlockOutp
 	std::vector<uint32_t> host_list;
 	for (size_t p = 0; p < n_pairs; ++p) if (o.pair_probe[p].redo == PR_REDO_HOST) host_list.push_back((uint32_t)p);
 	std::vector<FastqRec> hrecs(2 * host_list.size());
-	for (size_t s = 0; s < host_list.size(); ++s) { hrecs[2 * s] = recs[2 * (size_t)host_list[s]]; hrecs[2 * s + 1] = recs[2 * (size_t)host_list[s] + 1]; }
+	for (size_t s = 0; s < host_list.size(); ++s) { hrecs[2 * s] = rec_at(2 * (size_t)host_list[s]); hrecs[2 * s + 1] = rec_at(2 * (size_t)host_list[s] + 1); }
 	db->win.resize(nd + 2);
 	for (size_t t = 0; t < nd; ++t) db->win[t] = -1;
 	size_t cursor = 0;
@@ -1857,10 +1900,11 @@ bool AlnPipeline::align_block(const FastqRec *recs, size_t n_reads_in, BlockOutp
 				ReadState se[2];
 				Result prim[2], sec[2];
 				Impl::PE pe;
+				const FastqRec two[2] = {rec_at(2 * pi), rec_at(2 * pi + 1)};
 				pe.max_score = pf.max_score; pe.cur_isize = pf.cur_isize; pe.gain = pf.gain != 0; pe.proper = pf.proper != 0;
 				for (int m = 0; m < 2; ++m) {
 					ReadState &r = se[m];
-					r.rec = &recs[2 * pi + m];
+					r.rec = &two[m];
 					r.comment.assign(r.rec->comment, r.rec->comment_l);
 					r.read_l = (int)r.rec->seq_l;
 					Iq.parse_ori(r);

@@ -159,6 +159,10 @@ public:
 	// rest (stages A-E, the probe, the record text) of one block overlaps the in-order replay of the other.
 	bool align_block(const FastqRec *recs, size_t n_reads, BlockOutput &out, std::string &err, uint64_t seq);
 	bool align_block_host(const FastqRec *recs, size_t n_reads, BlockOutput &out, std::string &err, uint64_t seq, BlockHooks *hooks);
+	// the same block given as text (strict 4-line FASTQ of n_pairs interleaved pairs): the records are found on the device
+	bool align_block_text(const char *text, size_t bytes, size_t n_pairs, BlockOutput &out, std::string &err, uint64_t seq, bool *reparse);
+	bool align_block_dev(const char *text, size_t bytes, const FastqRec *recs, size_t n_pairs, BlockOutput &out, std::string &err, uint64_t seq, bool *reparse);
+	bool has_device_stages() const { return stages_ != nullptr; }
 	uint64_t next_seq() { return seq_issued_++; }
 	std::atomic<uint64_t> bad_cigar_records_{0};   // records left out because their CIGAR does not span the read (see output_bam)
 	void ensure_read_stats(const FastqRec &first);   // STAT_ fields of the input's first comment; call before overlapping blocks
@@ -191,8 +195,12 @@ private:
 	std::mutex dev_pool_m_;
 	DevBuffers *acquire_dev(std::string &err);
 	void release_dev(DevBuffers *d);
-	SeedBatch seed_main_[2], seed_small_; // batch buffers live across blocks (staging memory is pinned once); slot = seq & 1
-	KswBatchBuf ksw_main_[2];
+	// batch buffers of the host path live across blocks (staging memory is pinned once); every block in flight holds one set
+	struct HostSlot { SeedBatch seeds; KswBatchBuf ksw; };
+	std::vector<HostSlot*> host_free_, host_all_;
+	HostSlot *acquire_host();
+	void release_host(HostSlot *h);
+	SeedBatch seed_small_;
 	std::mutex dev_m_;                    // the two device services take one batch at a time
 	std::mutex stats_m_;
 	std::mutex turn_m_;                   // blocks take their in-order sections by sequence number

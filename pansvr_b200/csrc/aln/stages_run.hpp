@@ -28,10 +28,45 @@ namespace pansvr {
 enum DevSlot {
 	SL_TEXT, SL_READS, SL_BITS, SL_LIST, SL_FLAGS, SL_MEM_CNT, SL_MEM_OFF, SL_MEMS, SL_MEMS_TMP, SL_NVU, SL_SEED_CNT, SL_SEED_OFF,
 	SL_SEEDS, SL_SEEDS_TMP, SL_DIST, SL_PRE, SL_PLAN_CNT, SL_PLAN_OFF, SL_CANDS, SL_PIECES, SL_QLEN, SL_TLEN, SL_QOFF, SL_TOFF,
-	SL_Q, SL_T, SL_RES, SL_KCIG, SL_CIGS, SL_MISC, SL_SCAN_TMP, SL_USED, SL_ORI, SL_PSTATE, SL_PROBE, SL_WIN, SL_FINAL, SL_PFINAL, SL_RECS, SL_HOSTLEN, SL_TXT_LEN, SL_TXT_OFF, SL_TXT, SL_COUNT
+	SL_Q, SL_T, SL_RES, SL_KCIG, SL_CIGS, SL_MISC, SL_SCAN_TMP, SL_USED, SL_ORI, SL_PSTATE, SL_PROBE, SL_WIN, SL_FINAL, SL_PFINAL, SL_RECS, SL_HOSTLEN, SL_TXT_LEN, SL_TXT_OFF, SL_TXT, SL_NL_CNT, SL_NL_OFF, SL_LINES, SL_LAY_CNT, SL_LAY_OFF, SL_COUNT
 };
 
 // ---- functors (one element of work each; plain data members only, so they can be passed to a kernel by value)
+enum { NL_PIECE = 64 };
+struct FnLines {                                                   // line ends of one 64-byte piece of the text: counted, then placed
+	const uint8_t *text; uint32_t bytes; uint32_t *cnt; const uint32_t *off; uint32_t *lines; uint32_t max_lines; bool fill;
+	SEED_HD void operator()(size_t k) const
+	{
+		const uint32_t b = (uint32_t)k * NL_PIECE, e = b + NL_PIECE < bytes ? b + NL_PIECE : bytes;
+		uint32_t c = 0;
+		if (!fill) { for (uint32_t i = b; i < e; ++i) c += text[i] == '\n'; cnt[k] = c; return; }
+		uint32_t at = off[k];
+		for (uint32_t i = b; i < e; ++i) if (text[i] == '\n') { if (at < max_lines) lines[at] = i; ++at; }
+	}
+};
+struct FnRecord {                                                  // record r = lines 4r .. 4r+3: "@name comment", bases, "+...", qualities
+	const uint8_t *text; const uint32_t *lines; DevRec *recs; uint32_t *words, *list; uint32_t *bad;
+	SEED_HD void operator()(size_t r) const
+	{
+		uint32_t s[4], e[4];
+		for (int k = 0; k < 4; ++k) { const size_t l = 4 * r + k; s[k] = l == 0 ? 0u : lines[l - 1] + 1; e[k] = lines[l]; }
+		if (e[0] == s[0] || (text[s[0]] != '@' && text[s[0]] != '>') || e[2] == s[2] || text[s[2]] != '+') *bad = 1;
+		uint32_t sp = s[0] + 1;
+		while (sp < e[0] && text[sp] != ' ' && text[sp] != '\t') ++sp;
+		DevRec d;
+		d.name_off = s[0] + 1; d.name_l = e[0] > s[0] ? sp - (s[0] + 1) : 0;
+		while (sp < e[0] && (text[sp] == ' ' || text[sp] == '\t')) ++sp;
+		d.comment_off = sp; d.comment_l = e[0] > sp ? e[0] - sp : 0;
+		d.seq_off = s[1]; d.seq_l = e[1] - s[1]; d.qual_off = s[3]; d.qual_l = e[3] - s[3];
+		recs[r] = d;
+		words[r] = d.seq_l >= LEN_KMER ? 2 * ((d.seq_l >> 5) + 2) : 0;
+		list[r] = d.seq_l >= LEN_KMER ? 2 * (d.seq_l - LEN_KMER + 1) : 0;
+	}
+};
+struct FnReadTable {
+	const DevRec *recs; const uint32_t *words_off, *list_off; DevRead *reads;
+	SEED_HD void operator()(size_t i) const { DevRead d; d.seq_off = recs[i].seq_off; d.len = recs[i].seq_l; d.var_code = 0; d.bits_off = words_off[i]; d.list_off = list_off[i]; reads[i] = d; }
+};
 struct FnOri {                                                     // original alignment of every read, out of its comment
 	const uint8_t *text; const DevRec *recs; int match; DevOri *ori;
 	SEED_HD void operator()(size_t i) const { dev_parse_ori((const char*)text + recs[i].comment_off, recs[i].comment_l, recs[i].seq_l, match, ori[i]); }
@@ -199,6 +234,10 @@ struct DevStageIn {
 	// stage F on the device: reads 2p, 2p + 1 of the table are the mates of pair p (n_reads even); recs = their FASTQ records
 	// (offsets into `text`): the original alignments are parsed out of the comments, the SAM records written from them
 	const DevRec *recs = nullptr; PairOpts pair_opts = {0, 0, 0};
+	// ... or parse_text: `text` is strict 4-line FASTQ of n_reads records, and the record and read tables are made from it on the
+	// device (reads / recs / bits_words / list_bytes are not read); out.recs brings the record table back, out.parse_ok says whether
+	// the text was what it was taken for (if not, nothing else was done: the host parses the block)
+	bool parse_text = false;
 	bool want_tables = false;                                      // also bring the sorted seeds and chain tables back (tests)
 };
 struct DevStageOut {                                               // host side, kept across blocks (pinned in the product)
@@ -210,6 +249,7 @@ struct DevStageOut {                                               // host side,
 	HostVec<DevCand> cands; HostVec<DevCigar> cigs;
 	HostVec<DevProbe> pair_probe;                                  // n / 2: what the in-order pass has to do for each pair
 	HostVec<DevFinal> fin; HostVec<DevPairFinal> pfin;             // after run_device_finalize: n and n / 2
+	HostVec<DevRec> recs; bool parse_ok = true;                     // parse_text: the record table the device made
 	HostVec<uint32_t> txt_off;                                     // n + 1: place of every read's record in the block's SAM text
 	uint64_t bad_records = 0;                                      // records left out because htslib would reject them (CIGAR does not span the read)
 	uint64_t n_tasks = 0, n_cells = 0, probes = 0;
@@ -225,27 +265,64 @@ bool run_device_stages(BE &be, const IndexView &ix, const uint64_t *d_pos, const
 	out.seeds.clear(); out.dist.clear(); out.pre.clear(); out.cands.clear(); out.cigs.clear();
 	if (n == 0) { out.mem_off[0] = out.seed_off[0] = out.cand_off[0] = 0; return true; }
 	// ---- upload
+	out.parse_ok = true;
 	uint8_t *d_text = be.template buf<uint8_t>(SL_TEXT, in.text_bytes + 16);
 	DevRead *d_reads = be.template buf<DevRead>(SL_READS, n);
-	uint64_t *d_bits = be.template buf<uint64_t>(SL_BITS, in.bits_words + 2);
-	uint8_t *d_list = be.template buf<uint8_t>(SL_LIST, in.list_bytes + 16);
 	uint8_t *d_flags = be.template buf<uint8_t>(SL_FLAGS, n);
 	uint32_t *d_mem_cnt = be.template buf<uint32_t>(SL_MEM_CNT, 2 * n + 1), *d_mem_off = be.template buf<uint32_t>(SL_MEM_OFF, 2 * n + 1);
 	uint32_t *d_misc = be.template buf<uint32_t>(SL_MISC, 16);
-	if (!d_text || !d_reads || !d_bits || !d_list || !d_flags || !d_mem_cnt || !d_mem_off || !d_misc) { err = "device stages: out of device memory"; return false; }
+	if (!d_text || !d_reads || !d_flags || !d_mem_cnt || !d_mem_off || !d_misc) { err = "device stages: out of device memory"; return false; }
 	be.h2d(d_text, in.text, in.text_bytes);
-	be.h2d(d_reads, in.reads, n * sizeof(DevRead));
 	be.zero(d_misc, 64);
 	be.zero(d_mem_cnt + 2 * n, 4);
-	// ---- the original alignments (comment fields), when the block came with its record table
+	size_t bits_words = in.bits_words, list_bytes = in.list_bytes;
 	DevOri *d_ori = nullptr;
-	if (in.recs) {
+	if (in.parse_text) {
+		// ---- the record table from the text itself (kseq_read of strict 4-line FASTQ, clib/utils.c:953-990): line ends per 64-byte
+		// piece, counted then placed; one thread per record cuts name / comment / sequence / quality and sizes the read's pools
+		const size_t n_piece = (in.text_bytes + NL_PIECE - 1) / NL_PIECE;
+		uint32_t *d_nl_cnt = be.template buf<uint32_t>(SL_NL_CNT, n_piece + 1), *d_nl_off = be.template buf<uint32_t>(SL_NL_OFF, n_piece + 1);
+		uint32_t *d_lines = be.template buf<uint32_t>(SL_LINES, 4 * n + 16);
 		DevRec *d_recs = be.template buf<DevRec>(SL_RECS, n);
+		uint32_t *d_lay_cnt = be.template buf<uint32_t>(SL_LAY_CNT, 2 * (n + 1)), *d_lay_off = be.template buf<uint32_t>(SL_LAY_OFF, 2 * (n + 1));
 		d_ori = be.template buf<DevOri>(SL_ORI, n);
-		if (!d_recs || !d_ori) { err = "device stages: out of device memory"; return false; }
-		be.h2d(d_recs, in.recs, n * sizeof(DevRec));
+		if (!d_nl_cnt || !d_nl_off || !d_lines || !d_recs || !d_lay_cnt || !d_lay_off || !d_ori) { err = "device stages: out of device memory"; return false; }
+		be.zero(d_nl_cnt + n_piece, 4);
+		FnLines fl{d_text, (uint32_t)in.text_bytes, d_nl_cnt, d_nl_off, d_lines, (uint32_t)(4 * n), false};
+		be.for_each(n_piece, fl, 0);
+		be.scan(d_nl_cnt, d_nl_off, n_piece + 1);
+		uint32_t n_lines = 0;
+		be.d2h(&n_lines, d_nl_off + n_piece, 4);
+		be.sync();
+		if (n_lines != 4 * n) { out.parse_ok = false; return true; }      // not the strict 4-line format this block was cut for: the host parses it
+		fl.fill = true;
+		be.for_each(n_piece, fl, 0);
+		be.zero(d_lay_cnt, 2 * (n + 1) * 4);
+		be.for_each(n, FnRecord{d_text, d_lines, d_recs, d_lay_cnt, d_lay_cnt + (n + 1), d_misc + 8}, 0);
+		be.scan(d_lay_cnt, d_lay_off, n + 1);
+		be.scan(d_lay_cnt + (n + 1), d_lay_off + (n + 1), n + 1);
+		be.for_each(n, FnReadTable{d_recs, d_lay_off, d_lay_off + (n + 1), d_reads}, 0);
+		uint32_t tot[2], bad = 0;
+		be.d2h(&tot[0], d_lay_off + n, 4); be.d2h(&tot[1], d_lay_off + (n + 1) + n, 4); be.d2h(&bad, d_misc + 8, 4);
+		out.recs.resize(n);
+		be.d2h(out.recs.data(), d_recs, n * sizeof(DevRec));
+		be.sync();
+		if (bad) { out.parse_ok = false; return true; }
+		bits_words = tot[0]; list_bytes = tot[1];
 		be.for_each(n, FnOri{d_text, d_recs, in.scores.match, d_ori}, 0);
+	} else {
+		be.h2d(d_reads, in.reads, n * sizeof(DevRead));
+		if (in.recs) {                                             // the original alignments (comment fields), when the block came with its record table
+			DevRec *d_recs = be.template buf<DevRec>(SL_RECS, n);
+			d_ori = be.template buf<DevOri>(SL_ORI, n);
+			if (!d_recs || !d_ori) { err = "device stages: out of device memory"; return false; }
+			be.h2d(d_recs, in.recs, n * sizeof(DevRec));
+			be.for_each(n, FnOri{d_text, d_recs, in.scores.match, d_ori}, 0);
+		}
 	}
+	uint64_t *d_bits = be.template buf<uint64_t>(SL_BITS, bits_words + 2);
+	uint8_t *d_list = be.template buf<uint8_t>(SL_LIST, list_bytes + 16);
+	if (!d_bits || !d_list) { err = "device stages: out of device memory"; return false; }
 	// ---- A
 	be.for_each(n, FnEncode{d_text, d_reads, d_ori, d_bits, d_list, d_flags}, 0);
 	// ---- B
