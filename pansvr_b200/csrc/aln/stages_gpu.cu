@@ -23,6 +23,32 @@ template <class F> __global__ void __launch_bounds__(128) for_each_kernel(F f, s
 	if (i < n) f(i);
 }
 
+// SAM text, write pass: every thread formats the short fields of its record and sets its (up to four) long copies aside; the
+// warp then runs the 32 x 4 copies with all lanes on one copy at a time, so that a 150-byte field is read and written as
+// contiguous segments instead of one byte per lane at 32 different places.
+__global__ void __launch_bounds__(128) text_write_kernel(FnText f, size_t n)
+{
+	__shared__ CopyJob jobs[4][32][4];
+	const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	JobSink s;
+	s.p = nullptr; s.n = 0; s.nj = 0; s.np = 0;
+	if (i < n) f.prepare(i, s);
+	for (int j = 0; j < 4; ++j) {
+		CopyJob J;
+		if (j < s.nj) J = s.job[j]; else { J.src = nullptr; J.dst = nullptr; J.len = 0; J.mode = 0; }
+		jobs[warp][lane][j] = J;
+	}
+	__syncwarp();
+	for (int l = 0; l < 32; ++l)
+		for (int j = 0; j < 4; ++j) {
+			const CopyJob J = jobs[warp][l][j];
+			for (uint32_t k = (uint32_t)lane; k < J.len; k += 32) J.dst[k] = copy_byte(J.mode, J.src, k, J.len);
+		}
+	__syncwarp();
+	for (int k = 0; k < s.np; ++k) s.p[s.patches[k]] = ',';
+}
+
 struct CudaBackend {
 	cudaStream_t st = nullptr;
 	void *p[SL_COUNT]; size_t cap[SL_COUNT];
@@ -64,6 +90,17 @@ struct CudaBackend {
 		check(cudaEventRecord(l.a, st), "cudaEventRecord");
 		const unsigned threads = 128;
 		for_each_kernel<F><<<(unsigned)((n + threads - 1) / threads), threads, 0, st>>>(f, n);
+		check(cudaGetLastError(), "kernel launch");
+		check(cudaEventRecord(l.b, st), "cudaEventRecord");
+		laps.push_back(l);
+		++dev.launches;
+	}
+	void text_write(size_t n, const FnText &f)
+	{
+		if (n == 0 || failed) return;
+		Lap l; l.a = event(); l.b = event(); l.stage = 7;
+		check(cudaEventRecord(l.a, st), "cudaEventRecord");
+		text_write_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(f, n);
 		check(cudaGetLastError(), "kernel launch");
 		check(cudaEventRecord(l.b, st), "cudaEventRecord");
 		laps.push_back(l);

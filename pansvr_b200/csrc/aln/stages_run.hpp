@@ -444,6 +444,14 @@ struct FnText {                                                    // the SAM re
 			dev_sam_record(s, (const char*)text, recs[i], ori[i], fin[i], pfin[p], m, cands, cigs, T);
 		}
 	}
+	// write pass with the long copies (name, bases, qualities, comment) set aside as jobs for the backend's text_write()
+	SEED_HD void prepare(size_t i, JobSink &s) const
+	{
+		const size_t p = i >> 1;
+		s.p = out + off[i]; s.n = 0; s.nj = 0; s.np = 0;
+		if (!pfin[p].valid) return;
+		dev_sam_record(s, (const char*)text, recs[i], ori[i], fin[i], pfin[p], (int)(i & 1), cands, cigs, T);
+	}
 };
 
 // Second trip of a block whose pairs were probed: the winners the in-order pass drew for the pairs with pairing ties go up
@@ -486,7 +494,7 @@ bool run_device_finalize(BE &be, const PairIndexView &pix, const PairOpts &o, co
 	char *d_txt = be.template buf<char>(SL_TXT, total + 16);
 	if (!d_txt) { err = "device stages: out of device memory"; return false; }
 	ft.out = d_txt; ft.write = true;
-	be.for_each(n, ft, 7);
+	be.text_write(n, ft);
 	text_out.resize(total);
 	be.d2h(text_out.data(), d_txt, total);
 	be.sync();

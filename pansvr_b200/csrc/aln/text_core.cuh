@@ -49,25 +49,6 @@ SEED_HD void dev_parse_ori(const char *c, uint32_t n, uint32_t seq_l, int match,
 	o.skip = (!o.unmapped && o.align_score == (uint32_t)((int)seq_l * match)) ? 1 : 0;      // RR:414
 }
 
-// ---- sinks
-struct CountSink { uint32_t n; SEED_HD void put(char) { ++n; } SEED_HD void copy(const char *, uint32_t l) { n += l; } SEED_HD char *here() { return nullptr; } };
-struct WriteSink {
-	char *p; uint32_t n;
-	SEED_HD void put(char c) { p[n++] = c; }
-	SEED_HD void copy(const char *s, uint32_t l) { for (uint32_t i = 0; i < l; ++i) p[n + i] = s[i]; n += l; }
-	SEED_HD char *here() { return p + n; }
-};
-template <class S> SEED_HD void put_int(S &s, long v)
-{
-	char b[24]; int n = 24;
-	unsigned long u = v < 0 ? 0ul - (unsigned long)v : (unsigned long)v;
-	do { b[--n] = (char)('0' + u % 10); u /= 10; } while (u);
-	if (v < 0) b[--n] = '-';
-	for (int i = n; i < 24; ++i) s.put(b[i]);
-}
-template <class S> SEED_HD void put_str(S &s, const StrTable &t, uint32_t i) { if (i < t.n) s.copy(t.pool + t.off[i], t.off[i + 1] - t.off[i]); else s.put('*'); }
-template <class S> SEED_HD void put_lit(S &s, const char *z) { while (*z) s.put(*z++); }
-
 SEED_HD char dev_rev_char(char c)                                  // getReverseChar, clib/bam_file.c:320-328
 {
 	switch (c) { case 'A': case 'a': return 'T'; case 'C': case 'c': return 'G'; case 'G': case 'g': return 'C'; case 'T': case 't': return 'A'; default: return 'N'; }
@@ -84,6 +65,66 @@ SEED_HD char dev_nt16_norm(char c)                                 // seq_nt16_s
 	}
 }
 
+// The long fields of a record (name, bases, qualities, comment) are copies with a per-byte rule:
+//   COPY_PLAIN   out[i] = src[i]
+//   COPY_SEQ     out[i] = nt16(src[i])                               SEQ after htslib's 4-bit round trip
+//   COPY_SEQ_RC  out[i] = nt16(complement(src[len-1-i]))             getReverseStr_char, clib/bam_file.c:330-340
+//   COPY_QUAL_R  out[i] = src[len-1-i], except that an even length keeps its middle pair in place: getReverseStr_qual swaps up to
+//                and including i = len/2, which swaps that pair twice (clib/bam_file.c:342-360)
+enum { COPY_PLAIN = 0, COPY_SEQ = 1, COPY_SEQ_RC = 2, COPY_QUAL_R = 3 };
+SEED_HD char copy_byte(uint32_t mode, const char *src, uint32_t i, uint32_t len)
+{
+	switch (mode) {
+	case COPY_SEQ: return dev_nt16_norm(src[i]);
+	case COPY_SEQ_RC: return dev_nt16_norm(dev_rev_char(src[len - 1 - i]));
+	case COPY_QUAL_R: return (!(len & 1) && (i == (len >> 1) - 1 || i == (len >> 1))) ? src[i] : src[len - 1 - i];
+	default: return src[i];
+	}
+}
+struct CopyJob { const char *src; char *dst; uint32_t len, mode; };
+
+// ---- sinks: counting, writing byte by byte, and writing with the long copies set aside as jobs (the CUDA text kernel runs
+// the jobs of a warp's 32 records with all lanes on one job at a time, so that its loads and stores are contiguous)
+struct CountSink {
+	uint32_t n;
+	SEED_HD void put(char) { ++n; }
+	SEED_HD void copy(const char *, uint32_t l) { n += l; }
+	SEED_HD void big(const char *, uint32_t l, uint32_t) { n += l; }
+	SEED_HD void patch(uint32_t) {}
+	SEED_HD char *here() { return nullptr; }
+};
+struct WriteSink {
+	char *p; uint32_t n;
+	SEED_HD void put(char c) { p[n++] = c; }
+	SEED_HD void copy(const char *s, uint32_t l) { for (uint32_t i = 0; i < l; ++i) p[n + i] = s[i]; n += l; }
+	SEED_HD void big(const char *s, uint32_t l, uint32_t mode) { for (uint32_t i = 0; i < l; ++i) p[n + i] = copy_byte(mode, s, i, l); n += l; }
+	SEED_HD void patch(uint32_t at) { p[at] = ','; }
+	SEED_HD char *here() { return p + n; }
+};
+struct JobSink {
+	char *p; uint32_t n; CopyJob job[4]; int nj; uint32_t patches[10]; int np;
+	SEED_HD void put(char c) { p[n++] = c; }
+	SEED_HD void copy(const char *s, uint32_t l) { for (uint32_t i = 0; i < l; ++i) p[n + i] = s[i]; n += l; }
+	SEED_HD void big(const char *s, uint32_t l, uint32_t mode)
+	{
+		if (nj < 4) { CopyJob j; j.src = s; j.dst = p + n; j.len = l; j.mode = mode; job[nj++] = j; }
+		else for (uint32_t i = 0; i < l; ++i) p[n + i] = copy_byte(mode, s, i, l);
+		n += l;
+	}
+	SEED_HD void patch(uint32_t at) { if (np < 10) patches[np++] = at; }       // applied after the jobs have run
+	SEED_HD char *here() { return p + n; }
+};
+template <class S> SEED_HD void put_int(S &s, long v)
+{
+	char b[24]; int n = 24;
+	unsigned long u = v < 0 ? 0ul - (unsigned long)v : (unsigned long)v;
+	do { b[--n] = (char)('0' + u % 10); u /= 10; } while (u);
+	if (v < 0) b[--n] = '-';
+	for (int i = n; i < 24; ++i) s.put(b[i]);
+}
+template <class S> SEED_HD void put_str(S &s, const StrTable &t, uint32_t i) { if (i < t.n) s.copy(t.pool + t.off[i], t.off[i + 1] - t.off[i]); else s.put('*'); }
+template <class S> SEED_HD void put_lit(S &s, const char *z) { while (*z) s.put(*z++); }
+
 // The SAM record of read `m` (0 / 1) of a pair, or nothing.  Returns 1 if a record htslib would reject was left out (bad CIGAR).
 template <class S>
 SEED_HD int dev_sam_record(S &s, const char *text, const DevRec &rec, const DevOri &ori, const DevFinal &f, const DevPairFinal &pf, int m,
@@ -96,7 +137,7 @@ SEED_HD int dev_sam_record(S &s, const char *text, const DevRec &rec, const DevO
 	if (!is_ori && !(f.flags & FIN_P_CIGAR_OK)) return 1;
 	const bool fwd = (f.flags & FIN_P_FWD) != 0, has_mate = (f.flags & FIN_HAS_MATE) != 0;
 	const uint8_t flag = (uint8_t)((m == 0 ? 0x40 : 0) + (fwd ? 0 : 0x10) + (has_mate ? 0 : 0x08));
-	s.copy(text + rec.name_off, rec.name_l); s.put('\t'); put_int(s, flag); s.put('\t');
+	s.big(text + rec.name_off, rec.name_l, COPY_PLAIN); s.put('\t'); put_int(s, flag); s.put('\t');
 	put_str(s, T.target_names, f.p_chr); s.put('\t'); put_int(s, (int)f.p_ref_bg); s.put('\t'); put_int(s, (long)(f.p_mapq & 0xff)); s.put('\t');
 	if (is_ori) {                                                  // the original alignment as a candidate: [S] M (RRH:421-424)
 		if (ori.read_bg > 0) { put_int(s, (int16_t)(uint16_t)(int)ori.read_bg); s.put('S'); }
@@ -117,21 +158,23 @@ SEED_HD int dev_sam_record(S &s, const char *text, const DevRec &rec, const DevO
 	{
 		const char *sq = text + rec.seq_off, *ql = text + rec.qual_off;
 		const uint32_t L = rec.seq_l, QL = rec.qual_l, RL = rec.seq_l;   // read_l = seq.l
-		char *out = s.here();
-		if (out) {
-			for (uint32_t i = 0; i < L; ++i) out[i] = sq[i];
-			out[L] = '\t';
-			for (uint32_t i = 0; i < QL; ++i) out[L + 1 + i] = ql[i];
-			if (!fwd) {
+		if (fwd || QL == RL) {
+			s.big(sq, L, fwd ? COPY_SEQ : COPY_SEQ_RC); s.put('\t'); s.big(ql, QL, fwd ? COPY_PLAIN : COPY_QUAL_R);
+		} else {                                                   // (qualities of another length than the bases: the reference's in-place loops, literally)
+			char *out = s.here();
+			if (out) {
+				for (uint32_t i = 0; i < L; ++i) out[i] = sq[i];
+				out[L] = '\t';
+				for (uint32_t i = 0; i < QL; ++i) out[L + 1 + i] = ql[i];
 				const uint32_t half = RL >> 1;
 				for (uint32_t i = 0; i < half; ++i) { const char t = out[i]; out[i] = dev_rev_char(out[RL - 1 - i]); out[RL - 1 - i] = dev_rev_char(t); }
 				if (RL & 1) out[half] = dev_rev_char(out[half]);
 				char *q = out + L + 1;
 				for (uint32_t i = 0; i < half + 1; ++i) { const uint32_t ri = RL - 1 - i; const char t = q[i]; q[i] = q[ri]; q[ri] = t; }
+				for (uint32_t i = 0; i < L; ++i) out[i] = dev_nt16_norm(out[i]);
 			}
-			for (uint32_t i = 0; i < L; ++i) out[i] = dev_nt16_norm(out[i]);
+			s.n += L + 1 + QL;
 		}
-		s.n += L + 1 + QL;
 	}
 	s.put('\t');
 	put_lit(s, "AS:i:"); put_int(s, (int)f.p_align);
@@ -151,23 +194,19 @@ SEED_HD int dev_sam_record(S &s, const char *text, const DevRec &rec, const DevO
 	put_lit(s, "\tRC:Z:");
 	{
 		const char *c = text + rec.comment_off;
-		const uint32_t n = rec.comment_l;
-		char *out = s.here();
-		if (out) {
-			for (uint32_t i = 0; i < n; ++i) out[i] = c[i];
-			int nt = 0;
-			uint32_t i = 0;
-			while (nt < 10 && i < n) {
-				while (i < n && c[i] == '_') ++i;
-				if (i >= n) break;
-				uint32_t j = i;
-				while (j < n && c[j] != '_') ++j;
-				++nt;
-				if (j < n && j + 1 < n) out[j] = ',';
-				i = j + 1;
-			}
+		const uint32_t n = rec.comment_l, at = s.n;
+		s.big(c, n, COPY_PLAIN);
+		int nt = 0;
+		uint32_t i = 0;
+		while (nt < 10 && i < n) {
+			while (i < n && c[i] == '_') ++i;
+			if (i >= n) break;
+			uint32_t j = i;
+			while (j < n && c[j] != '_') ++j;
+			++nt;
+			if (j < n && j + 1 < n) s.patch(at + j);
+			i = j + 1;
 		}
-		s.n += n;
 	}
 	s.put('\n');
 	return 0;

@@ -62,6 +62,15 @@ struct HostBackend {
 	void zero(void *d, size_t bytes) { if (bytes) memset(d, 0, bytes); }
 	void sync() {}
 	template <class F> void for_each(size_t n, const F &f, int) { for (size_t i = 0; i < n; ++i) f(i); }
+	void text_write(size_t n, const FnText &f)                    // the text kernel's three steps, one record at a time
+	{
+		for (size_t i = 0; i < n; ++i) {
+			JobSink s;
+			f.prepare(i, s);
+			for (int j = 0; j < s.nj; ++j) for (uint32_t k = 0; k < s.job[j].len; ++k) s.job[j].dst[k] = copy_byte(s.job[j].mode, s.job[j].src, k, s.job[j].len);
+			for (int k = 0; k < s.np; ++k) s.p[s.patches[k]] = ',';
+		}
+	}
 	void scan(const uint32_t *in, uint32_t *out, size_t n) { uint32_t run = 0; for (size_t i = 0; i < n; ++i) { const uint32_t v = in[i]; out[i] = run; run += v; } }
 	bool ksw(size_t n, const uint8_t *q, const int64_t *qoff, const int32_t *qlen, const uint8_t *t, const int64_t *toff, const int32_t *tlen,
 	         int32_t *res, uint32_t *cig, int cigar_cap, std::string &err)
