@@ -150,7 +150,8 @@ typedef struct {                /* MAP_PARA, read_realignment.hpp:43-128; 0 in e
 	int32_t match, mismatch, gap_open, gap_ex, gap_open2, gap_ex2, zdrop, band_width;
 	int32_t not_ori;            /* -Q */
 	int32_t max_use_read;       /* -R */
-	int32_t threads;            /* -t: host helper threads of the parallel stages; 0 = all cores (max 32).  The output is that of `-t 1`. */
+	int32_t threads;            /* -t: host helper threads of the parallel stages; 0 = all cores (max 48, the reference's limit).  The output is that of `-t 1`. */
+	int32_t explicit_mask;      /* bit k set: field k of this struct (match = 0, mismatch = 1, ...) is meant as given even when it is 0 */
 } pansvr_aln_options_t;
 
 typedef struct {
@@ -162,6 +163,8 @@ typedef struct {
 	int64_t h2d_bytes, d2h_bytes;
 	int64_t seed_probes;        /* k-mer lookups made by the seeding kernels */
 	double seed_kernel_ms, ksw_kernel_ms, stage_kernel_ms;   /* CUDA-event time of the seeding / ksw / other stage kernels */
+	double stage_kernel_ms_by[8];   /* the stage kernels by group: 0 records + original alignments + encode/census, 1 seeding, 2 merge + chain,
+	                                   3 ksw planning, 4 candidate resolution, 5 cell count, 6 pairing probe + finalize, 7 SAM text */
 } pansvr_aln_stats_t;
 
 typedef struct pansvr_aln_ctx pansvr_aln_ctx;

@@ -15,14 +15,15 @@ from .ksw import load_library
 
 class AlnOptionsC(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ("match", "mismatch", "gap_open", "gap_ex", "gap_open2", "gap_ex2", "zdrop", "band_width",
-                                         "not_ori", "max_use_read", "threads")]
+                                         "not_ori", "max_use_read", "threads", "explicit_mask")]
 
 
 class AlnStatsC(C.Structure):
     _fields_ = [("reads", C.c_int64), ("mems", C.c_int64), ("ksw_tasks", C.c_int64), ("ksw_cells", C.c_int64),
                 ("deferred_pairs", C.c_int64), ("stage_seconds", C.c_double * 8),
                 ("kernel_launches", C.c_int64), ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64), ("seed_probes", C.c_int64),
-                ("seed_kernel_ms", C.c_double), ("ksw_kernel_ms", C.c_double), ("stage_kernel_ms", C.c_double)]
+                ("seed_kernel_ms", C.c_double), ("ksw_kernel_ms", C.c_double), ("stage_kernel_ms", C.c_double),
+                ("stage_kernel_ms_by", C.c_double * 8)]
 
 
 def _bind(lib):
@@ -151,6 +152,7 @@ class AlnContext:
         d = {k: getattr(st, k) for k in ("reads", "mems", "ksw_tasks", "ksw_cells", "deferred_pairs", "kernel_launches", "h2d_bytes",
                                          "d2h_bytes", "seed_probes", "seed_kernel_ms", "ksw_kernel_ms", "stage_kernel_ms")}
         d["stage_seconds"] = list(st.stage_seconds)
+        d["stage_kernel_ms_by"] = list(st.stage_kernel_ms_by)
         return d
 
     def close(self):

@@ -172,16 +172,19 @@ AlnOptions from_c(const pansvr_aln_options_t *o)
 	AlnOptions a;
 	a.threads = 0;
 	if (!o) return a;
-	if (o->match) a.match = o->match;
-	if (o->mismatch) a.mismatch = o->mismatch;
-	if (o->gap_open) a.gap_open = o->gap_open;
-	if (o->gap_ex) a.gap_ex = o->gap_ex;
-	if (o->gap_open2) a.gap_open2 = o->gap_open2;
+	// a zero means "the reference's default" unless the field's bit in explicit_mask says the caller meant zero (`-E 0` on the
+	// command line is honoured by the reference's option parser)
+	auto given = [&](int bit, int32_t v) { return v != 0 || ((o->explicit_mask >> bit) & 1); };
+	if (given(0, o->match)) a.match = o->match;
+	if (given(1, o->mismatch)) a.mismatch = o->mismatch;
+	if (given(2, o->gap_open)) a.gap_open = o->gap_open;
+	if (given(3, o->gap_ex)) a.gap_ex = o->gap_ex;
+	if (given(4, o->gap_open2)) a.gap_open2 = o->gap_open2;
 	a.gap_ex2 = o->gap_ex2;
-	if (o->zdrop) a.zdrop = o->zdrop;
-	if (o->band_width) a.bw = o->band_width;
+	if (given(6, o->zdrop)) a.zdrop = o->zdrop;
+	if (given(7, o->band_width)) a.bw = o->band_width;
 	a.not_ori = o->not_ori != 0;
-	if (o->max_use_read > 0) a.max_use_read = o->max_use_read;
+	if (o->max_use_read > 0 || ((o->explicit_mask >> 9) & 1)) a.max_use_read = o->max_use_read;
 	a.threads = o->threads;
 	return a;
 }
@@ -196,7 +199,7 @@ int pansvr_aln_create(const char *index_dir, const char *header_sam, const pansv
 	*out = nullptr;
 	pansvr_aln_ctx *c = new pansvr_aln_ctx();
 	c->opt = from_c(opt);
-	if (c->opt.threads <= 0) c->opt.threads = (int)std::min(32u, std::max(1u, std::thread::hardware_concurrency()));
+	if (c->opt.threads <= 0) c->opt.threads = (int)std::min(48u, std::max(1u, std::thread::hardware_concurrency()));   // the reference's -t limit (RRH:121)
 	std::string err;
 	const auto tick = []() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
 	const bool timing = getenv("PANSVR_TIMING") != nullptr;
@@ -526,6 +529,7 @@ int pansvr_aln_last_stats(const pansvr_aln_ctx *c, pansvr_aln_stats_t *out)
 	out->kernel_launches = s.dev.launches; out->h2d_bytes = s.dev.h2d_bytes; out->d2h_bytes = s.dev.d2h_bytes;
 	out->seed_probes = s.dev.seed_probes;
 	out->seed_kernel_ms = s.dev.seed_kernel_ms; out->ksw_kernel_ms = s.dev.ksw_kernel_ms; out->stage_kernel_ms = s.dev.stage_kernel_ms;
+	for (int i = 0; i < 8; ++i) out->stage_kernel_ms_by[i] = s.dev.by_stage_ms[i];
 	return 0;
 }
 
@@ -583,19 +587,19 @@ int pansvr_fc_aln_main(int argc, char **argv)
 	while ((ch = getopt_long(argc, argv, "t:O:P:E:F:M:m:z:w:o:p:QSR:d:", lo, 0)) != -1) {
 		switch (ch) {
 		case 't': threads = atoi(optarg); o.threads = threads; break;
-		case 'O': o.gap_open = atoi(optarg); break;
-		case 'P': o.gap_open2 = atoi(optarg); break;
-		case 'E': o.gap_ex = atoi(optarg); break;
+		case 'O': o.gap_open = atoi(optarg); o.explicit_mask |= 1 << 2; break;
+		case 'P': o.gap_open2 = atoi(optarg); o.explicit_mask |= 1 << 4; break;
+		case 'E': o.gap_ex = atoi(optarg); o.explicit_mask |= 1 << 3; break;
 		case 'F': o.gap_ex2 = atoi(optarg); f_given = true; break;
-		case 'M': o.match = atoi(optarg); break;
-		case 'm': o.mismatch = atoi(optarg); break;
-		case 'z': o.zdrop = atoi(optarg); break;
-		case 'w': o.band_width = atoi(optarg); break;     // parsed and ignored, like the reference (RR:817-827)
+		case 'M': o.match = atoi(optarg); o.explicit_mask |= 1 << 0; break;
+		case 'm': o.mismatch = atoi(optarg); o.explicit_mask |= 1 << 1; break;
+		case 'z': o.zdrop = atoi(optarg); o.explicit_mask |= 1 << 6; break;
+		case 'w': o.band_width = atoi(optarg); o.explicit_mask |= 1 << 7; break;     // parsed and ignored, like the reference (RR:817-827)
 		case 'o': out_path = optarg; break;
 		case 'p': ori_path = optarg; break;
 		case 'Q': o.not_ori = 1; break;
 		case 'S': sam = true; break;
-		case 'R': o.max_use_read = atoi(optarg); break;
+		case 'R': o.max_use_read = atoi(optarg); o.explicit_mask |= 1 << 9; break;
 		case 'd': device = atoi(optarg); break;
 		default: return 1;
 		}
@@ -615,7 +619,7 @@ int pansvr_fc_aln_main(int argc, char **argv)
 	// (512 k pairs): the output does not depend on it.
 	struct Job { std::string fastq; bool last = false; };
 	struct Result { void *main = nullptr, *ori = nullptr; size_t main_n = 0, ori_n = 0; bool last = false; };
-	const long max_pairs = o.max_use_read > 0 ? o.max_use_read : 0x7fffffff;
+	const long max_pairs = (o.explicit_mask >> 9) & 1 ? std::max(0, o.max_use_read) : (o.max_use_read > 0 ? o.max_use_read : 0x7fffffff);   // (-R 0 reads nothing, like the reference)
 	Queue<Job> jobs(2);
 	Queue<Result> results(2);
 	std::atomic<bool> failed(false);
@@ -624,7 +628,7 @@ int pansvr_fc_aln_main(int argc, char **argv)
 		std::vector<char> chunk(4 << 20);
 		long lines = 0, total_pairs = 0, pairs_in_block = 0;
 		size_t boundary = 0;                                    // end of the last complete pair in `cur`
-		bool stop = false;
+		bool stop = max_pairs <= 0;
 		auto hand_over = [&](size_t upto, bool last) {
 			Job j; j.fastq.assign(cur, 0, upto); j.last = last;
 			cur.erase(0, upto); boundary = 0; pairs_in_block = 0;

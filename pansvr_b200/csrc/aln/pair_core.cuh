@@ -36,7 +36,7 @@ struct DevRes {                                                    // MAX_IDX_OU
 	uint8_t direction, mapq, cigar_ok, rst_idx;
 };
 struct DevPE { int32_t max_same, max_score, cur_isize; int8_t m1, m2; uint8_t proper, gain; };   // m1/m2: index into pick() (-1 none)
-struct DevPairState { DevRes res[2][PR_MAX_RES]; uint8_t n[2]; uint8_t pad[2]; DevPE pe; };
+struct DevPairState { DevRes res[2][PR_MAX_RES]; uint8_t n[2]; uint8_t pad[2]; int16_t draws[2]; DevPE pe; };   // draws: rand() calls of each read (-1: outcomes differ)
 struct DevProbe { uint8_t redo, draws0, draws1, ev_cnt; int8_t ev_i[PR_MAX_EVENTS], ev_j[PR_MAX_EVENTS]; uint32_t tie_mask; };
 struct DevFinal {                                                  // what the record text of one read needs
 	uint32_t flags;                                                // FIN_*
@@ -312,25 +312,31 @@ SEED_HD void dev_pair_up(const PairIndexView &ix, const PairOpts &o, const PairS
 	pe.gain = pe.max_score > 0 && (dev_is_new(S[0], pe.m1) || dev_is_new(S[1], pe.m2));
 }
 
-// One pair through the probe.  Returns what the in-order pass has to do for it in pr.redo:
-//   0 nothing; 1 advance the stream by draws0 + draws1; 2 the same, then redraw the pairing ties from the events;
-//   PR_REDO_HOST: the host path finishes this pair (outcomes of a read's ties differ, too many events, a read the device handed back)
-SEED_HD void dev_probe_pair(const PairIndexView &ix, const PairOpts &o, const ReadView *R, DevPairState &st, DevProbe &pr)
+// The probe of one pair, in two steps so that the two reads of a pair are explored by two threads:
+//   dev_explore_store   one read: its candidates and the number of rand() draws its ties make (-1: the outcomes differ)
+//   dev_probe_pair      the pair: pairing against the scripted generator.  pr.redo = what the in-order pass has to do for it:
+//     0 nothing; 1 advance the stream by draws0 + draws1; 2 the same, then redraw the pairing ties from the events;
+//     PR_REDO_HOST: the host path finishes this pair (outcomes of a read's ties differ, too many events, a read the device handed back)
+SEED_HD void dev_explore_store(const PairIndexView &ix, const ReadView &R, DevPairState &st, int k)
+{
+	DevTap probe;
+	DevRes res[PR_MAX_RES];                                        // (worked on locally; only the candidates that exist go to the pair's state)
+	int n = 0;
+	const int c = dev_explore_read(ix, R, res, &n, probe);
+	st.draws[k] = (int16_t)((c < 0 || c > 250) ? -1 : c);
+	st.n[k] = (uint8_t)(c < 0 ? 0 : n);
+	if (c >= 0) for (int x = 0; x < n; ++x) st.res[k][x] = res[x];
+}
+SEED_HD void dev_probe_pair(const PairIndexView &ix, const PairOpts &o, const DevOri *ori, DevPairState &st, DevProbe &pr)
 {
 	pr.redo = 0; pr.draws0 = pr.draws1 = 0; pr.ev_cnt = 0; pr.tie_mask = 0;
-	DevTap probe;
-	int n0 = 0, n1 = 0;
-	DevRes res0[PR_MAX_RES], res1[PR_MAX_RES];                     // (worked on locally; only the candidates that exist go to the pair's state)
-	const int c0 = dev_explore_read(ix, R[0], res0, &n0, probe);
-	const int c1 = c0 < 0 ? -1 : dev_explore_read(ix, R[1], res1, &n1, probe);
-	if (c0 < 0 || c1 < 0 || c0 > 250 || c1 > 250) { pr.redo = PR_REDO_HOST; return; }
-	st.n[0] = (uint8_t)n0; st.n[1] = (uint8_t)n1;
-	for (int k = 0; k < n0; ++k) st.res[0][k] = res0[k];
-	for (int k = 0; k < n1; ++k) st.res[1][k] = res1[k];
+	const int c0 = st.draws[0], c1 = st.draws[1];
+	if (c0 < 0 || c1 < 0) { pr.redo = PR_REDO_HOST; return; }
 	pr.draws0 = (uint8_t)c0; pr.draws1 = (uint8_t)c1;
 	PairSide S[2];
-	S[0].res = res0; S[0].n = n0; S[0].ori = R[0].ori;
-	S[1].res = res1; S[1].n = n1; S[1].ori = R[1].ori;
+	S[0].res = st.res[0]; S[0].n = st.n[0]; S[0].ori = ori[0];
+	S[1].res = st.res[1]; S[1].n = st.n[1]; S[1].ori = ori[1];
+	DevTap probe;
 	probe.restart(0);
 	EventSink ev; ev.pr = &pr; ev.overflow = false;
 	dev_pair_up(ix, o, S, st.pe, probe, &ev);

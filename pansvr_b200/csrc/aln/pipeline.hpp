@@ -100,10 +100,13 @@ struct DevCounters {                  // what the device services did for a bloc
 	int64_t launches = 0, h2d_bytes = 0, d2h_bytes = 0;
 	int64_t seed_probes = 0;          // k-mer lookups of the seeding kernels (fill pass; the count pass repeats them)
 	double seed_kernel_ms = 0, ksw_kernel_ms = 0, stage_kernel_ms = 0;   // CUDA-event time of our kernels on their streams
+	double by_stage_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // the same by group: 0 records / original alignments / encode + census, 1 seeding,
+	                                                    // 2 merge + chain, 3 ksw planning, 4 candidate resolution, 5 cell count, 6 pairing probe + finalize, 7 SAM text
 	void add(const DevCounters &o)
 	{
 		launches += o.launches; h2d_bytes += o.h2d_bytes; d2h_bytes += o.d2h_bytes; seed_probes += o.seed_probes;
 		seed_kernel_ms += o.seed_kernel_ms; ksw_kernel_ms += o.ksw_kernel_ms; stage_kernel_ms += o.stage_kernel_ms;
+		for (int i = 0; i < 8; ++i) by_stage_ms[i] += o.by_stage_ms[i];
 	}
 };
 

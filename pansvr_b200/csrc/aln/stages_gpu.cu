@@ -136,6 +136,7 @@ struct CudaBackend {
 			float ms = 0;
 			if (cudaEventElapsedTime(&ms, l.a, l.b) != cudaSuccess) continue;
 			if (l.stage == 1) dev.seed_kernel_ms += ms; else dev.stage_kernel_ms += ms;
+			if (l.stage >= 0 && l.stage < 8) dev.by_stage_ms[l.stage] += ms;
 		}
 		laps.clear(); ev_used = 0;
 	}

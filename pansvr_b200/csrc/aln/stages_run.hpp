@@ -178,23 +178,29 @@ struct FnResolve {
 	}
 };
 
-struct FnProbe {                                                   // one pair = reads 2p, 2p + 1 of the table
-	PairIndexView ix; PairOpts o; const uint8_t *flags; const uint32_t *seed_off; const DevSeed *seeds; const float *dist; const int32_t *pre; uint8_t *used;
-	const uint32_t *cand_off; const DevCand *cands; const DevOri *ori; DevPairState *state; DevProbe *probe;
+struct FnExplore {                                                 // one read: chain selection and candidate sort under every outcome of its ties
+	PairIndexView ix; const uint8_t *flags; const uint32_t *seed_off; const DevSeed *seeds; const float *dist; const int32_t *pre; uint8_t *used;
+	const uint32_t *cand_off; const DevCand *cands; const DevOri *ori; DevPairState *state;
+	SEED_HD void operator()(size_t i) const
+	{
+		const size_t p = i >> 1;
+		if ((flags[2 * p] | flags[2 * p + 1]) & (ST_FLAG_NEEDS_RAND | ST_FLAG_HOST)) return;      // the host path keeps the pair
+		ReadView R;
+		for (int s = 0; s < 2; ++s) {
+			const uint32_t sb = seed_off[2 * i + s];
+			R.v[s] = seeds + sb; R.dist[s] = dist + sb; R.pre[s] = pre + sb; R.used[s] = used + sb; R.n[s] = seed_off[2 * i + s + 1] - sb;
+		}
+		R.cands = cands; R.cand_b = cand_off[i]; R.cand_e = cand_off[i + 1]; R.ori = ori[i];
+		dev_explore_store(ix, R, state[p], (int)(i & 1));
+	}
+};
+struct FnProbe {                                                   // one pair = reads 2p, 2p + 1 of the table: pairing
+	PairIndexView ix; PairOpts o; const uint8_t *flags; const DevOri *ori; DevPairState *state; DevProbe *probe;
 	SEED_HD void operator()(size_t p) const
 	{
 		DevProbe &pr = probe[p];
 		if ((flags[2 * p] | flags[2 * p + 1]) & (ST_FLAG_NEEDS_RAND | ST_FLAG_HOST)) { pr.redo = PR_REDO_HOST; pr.draws0 = pr.draws1 = pr.ev_cnt = 0; pr.tie_mask = 0; return; }
-		ReadView R[2];
-		for (int k = 0; k < 2; ++k) {
-			const size_t i = 2 * p + k;
-			for (int s = 0; s < 2; ++s) {
-				const uint32_t sb = seed_off[2 * i + s];
-				R[k].v[s] = seeds + sb; R[k].dist[s] = dist + sb; R[k].pre[s] = pre + sb; R[k].used[s] = used + sb; R[k].n[s] = seed_off[2 * i + s + 1] - sb;
-			}
-			R[k].cands = cands; R[k].cand_b = cand_off[i]; R[k].cand_e = cand_off[i + 1]; R[k].ori = ori[i];
-		}
-		dev_probe_pair(ix, o, R, state[p], pr);
+		dev_probe_pair(ix, o, ori + 2 * p, state[p], pr);
 	}
 };
 struct FnFinalize {
@@ -414,7 +420,8 @@ bool run_device_stages(BE &be, const IndexView &ix, const uint64_t *d_pos, const
 		DevPairState *d_state = be.template buf<DevPairState>(SL_PSTATE, np);
 		DevProbe *d_probe = be.template buf<DevProbe>(SL_PROBE, np);
 		if (!d_used || !d_state || !d_probe) { err = "device stages: out of device memory"; return false; }
-		be.for_each(np, FnProbe{pix, in.pair_opts, d_flags, d_seed_off, d_seeds, d_dist, d_pre, d_used, d_plan_off, be.template buf<DevCand>(SL_CANDS, 0), d_ori, d_state, d_probe}, 6);
+		be.for_each(n, FnExplore{pix, d_flags, d_seed_off, d_seeds, d_dist, d_pre, d_used, d_plan_off, be.template buf<DevCand>(SL_CANDS, 0), d_ori, d_state}, 6);
+		be.for_each(np, FnProbe{pix, in.pair_opts, d_flags, d_ori, d_state, d_probe}, 6);
 		out.pair_probe.resize(np);
 		be.d2h(out.pair_probe.data(), d_probe, np * sizeof(DevProbe));
 		be.sync();

@@ -129,8 +129,9 @@ def test_edge_inputs_match_reference(fc_aln_emul):
 
 
 @pytest.mark.parametrize("opts", [("-Q",), ("-M", "1", "-m", "4", "-O", "6", "-E", "2", "-P", "24", "-F", "1", "-z", "200"),
-                                  ("-M", "3", "-m", "9", "-O", "20", "-E", "3", "-P", "40", "-F", "1", "-z", "100", "-Q", "-w", "50")],
-                         ids=["not_ori", "soft_scoring", "hard_scoring"])
+                                  ("-M", "3", "-m", "9", "-O", "20", "-E", "3", "-P", "40", "-F", "1", "-z", "100", "-Q", "-w", "50"),
+                                  ("-E", "0", "-O", "12"), ("-R", "0")],
+                         ids=["not_ori", "soft_scoring", "hard_scoring", "explicit_zero", "no_reads"])
 def test_command_line_options_match_reference(fc_aln_emul, opts):
     """MAP_PARA::get_option (read_realignment.hpp:82-128): scoring, z-drop, -Q and the ignored -w."""
     need_ref_tools()
