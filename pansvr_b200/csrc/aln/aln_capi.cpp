@@ -24,6 +24,39 @@ using namespace pansvr;
 
 namespace { thread_local std::string g_aln_err; }
 
+// Output buffers the device writes the SAM text into directly (page-locked staging memory, so the copy from the device is one
+// DMA per sub-block and nothing is copied on the host afterwards).  They are handed to the caller as the result of
+// pansvr_aln_block and come back through pansvr_free; a few are kept for reuse, since page-locking is not cheap.
+namespace {
+struct OutPool {
+	struct Buf { char *p; size_t cap; bool busy; };
+	std::mutex m;
+	std::vector<Buf> bufs;
+	char *acquire(size_t cap)
+	{
+		std::lock_guard<std::mutex> lk(m);
+		for (Buf &b : bufs) if (!b.busy && b.cap >= cap) { b.busy = true; return b.p; }
+		for (size_t i = 0; i < bufs.size(); ++i) if (!bufs[i].busy) { staging_free(bufs[i].p); bufs.erase(bufs.begin() + (long)i); break; }   // one too small: replace it
+		char *p = (char*)staging_alloc(cap);
+		if (!p) return nullptr;
+		bufs.push_back(Buf{p, cap, true});
+		return p;
+	}
+	bool release(void *p)                                     // false: not one of ours
+	{
+		std::lock_guard<std::mutex> lk(m);
+		size_t idle = 0;
+		for (Buf &b : bufs) idle += !b.busy;
+		for (size_t i = 0; i < bufs.size(); ++i) if (bufs[i].p == p) {
+			if (idle >= 3) { staging_free(bufs[i].p); bufs.erase(bufs.begin() + (long)i); } else bufs[i].busy = false;
+			return true;
+		}
+		return false;
+	}
+};
+OutPool g_out_pool;
+}
+
 struct pansvr_aln_ctx {
 	DebgaIndex idx;
 	AlnOptions opt;
@@ -298,8 +331,12 @@ bool cut_text(const char *p, size_t n, AlnPipeline &pipe, int threads, size_t &n
 	return true;
 }
 
+// `room`: a buffer the sub-blocks' SAM text goes into directly, one behind the other in input order (device path); *room_used =
+// how much of it was filled.  A sub-block whose text does not fit keeps it in its own buffer (and so do all later ones).
+struct TextRoom { char *p = nullptr; size_t cap = 0, used = 0; size_t next = 0; bool full = false; std::mutex m; std::condition_variable cv; };
+
 int run_block(pansvr_aln_ctx *c, const char *fastq, size_t n, std::vector<Part> &sam, std::vector<Part> &ori,
-              const std::function<void(const BlockOutput&)> *on_done = nullptr)
+              const std::function<void(const BlockOutput&)> *on_done = nullptr, TextRoom *room = nullptr)
 {
 	const auto tick = []() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
 	const double t0 = tick();
@@ -332,6 +369,20 @@ int run_block(pansvr_aln_ctx *c, const char *fastq, size_t n, std::vector<Part> 
 	for (size_t k = 0; k < n_sub; ++k) seqs[k] = c->pipe->next_seq();
 	auto run_sub = [&](size_t k) {
 		const size_t pb = std::min(n_pairs, per * k), pe = std::min(n_pairs, per * (k + 1));
+		BlockOutput &bo = c->outs[k];
+		bo.place = nullptr;
+		if (room) bo.place = [room, k](size_t total) -> char* {      // sub-block k's text goes behind that of 0 .. k-1
+			std::unique_lock<std::mutex> lk(room->m);
+			room->cv.wait(lk, [&]() { return room->next == k; });
+			char *at = nullptr;
+			if (!room->full && room->used + total + 1 <= room->cap) { at = room->p + room->used; room->used += total; }
+			else if (total) room->full = true;
+			room->next = k + 1;
+			lk.unlock();
+			room->cv.notify_all();
+			return at;
+		};
+		struct Always { BlockOutput &b; ~Always() { if (b.place && !b.place_called) b.place(0); b.place = nullptr; } } always{bo};
 		if (as_text) {
 			bool reparse = false;
 			ok[k] = c->pipe->align_block_text(fastq + cuts[k], cuts[k + 1] - cuts[k], pe - pb, c->outs[k], errs[k], seqs[k], &reparse) ? 1 : 0;
@@ -400,13 +451,30 @@ int pansvr_aln_block(pansvr_aln_ctx *c, const char *fastq, size_t n, char **sam,
 		char *p = nullptr; size_t cap = 0, used = 0;
 		bool room(size_t more) { if (used + more + 1 <= cap) return true; const size_t want = std::max(cap * 2, used + more + 1); char *q = (char*)realloc(p, want); if (!q) return false; p = q; cap = want; return true; }
 	} gs, go;
-	gs.cap = n / 2 * 5 + (1 << 16); gs.p = (char*)malloc(gs.cap);
+	TextRoom room;
+	const bool direct = c->pipe->has_device_stages();            // device path: the text comes straight into a page-locked buffer
+	gs.cap = n / 2 * 5 + (1 << 16);
+	if (direct) { room.cap = gs.cap; if (const char *e = getenv("PANSVR_ROOM_BYTES")) room.cap = (size_t)std::max(1L, atol(e)); room.p = g_out_pool.acquire(room.cap); }   // (the variable: tests force the spill)
+	if (!room.p) gs.p = (char*)malloc(gs.cap);
 	go.cap = 1 << 16; go.p = (char*)malloc(go.cap);
-	bool oom = !gs.p || !go.p;
+	bool oom = (!gs.p && !room.p) || !go.p;
+	bool spilled = false;                                         // some text did not go into the room (did not fit)
+	size_t placed_prefix = 0;                                     // text of the sub-blocks handed over so far that sits in the room, contiguous from its start
 	double t_join = 0;
 	const std::function<void(const BlockOutput&)> take = [&](const BlockOutput &o) {
 		const double t0 = CallReport::now();
 		std::vector<Part> ps, po;
+		if (room.p && !o.placed && !spilled) {
+			// this sub-block's text is not in the room (no room left): from here on the text is assembled by copying; what the earlier
+			// sub-blocks put into the room moves over first
+			spilled = true;
+			gs.p = (char*)malloc(gs.cap);
+			if (!gs.p || !gs.room(placed_prefix)) { oom = true; return; }
+			memcpy(gs.p, room.p, placed_prefix);
+			gs.used = placed_prefix;
+		}
+		if (o.placed && !spilled) placed_prefix += o.placed_bytes;
+		if (o.placed && spilled) add_parts(ps, o.placed_ptr, o.placed_bytes);
 		if (o.sam_text.size()) add_parts(ps, o.sam_text.data(), o.sam_text.size());
 		for (const std::string &x : o.sam) if (!x.empty()) add_parts(ps, x.data(), x.size());
 		for (const std::string &x : o.ori) if (!x.empty()) add_parts(po, x.data(), x.size());
@@ -423,8 +491,10 @@ int pansvr_aln_block(pansvr_aln_ctx *c, const char *fastq, size_t n, char **sam,
 		t_join += CallReport::now() - t0;
 	};
 	std::vector<Part> unused_s, unused_o;
-	const int rc = run_block(c, fastq, n, unused_s, unused_o, &take);
-	if (rc != 0 || oom) { free(gs.p); free(go.p); if (rc == 0) { g_aln_err = "out of memory"; return PANSVR_E_ARG; } return rc; }
+	const int rc = run_block(c, fastq, n, unused_s, unused_o, &take, room.p ? &room : nullptr);
+	if (rc != 0 || oom) { free(gs.p); free(go.p); if (room.p) g_out_pool.release(room.p); if (rc == 0) { g_aln_err = "out of memory"; return PANSVR_E_ARG; } return rc; }
+	if (room.p && !spilled) { gs.p = room.p; gs.used = placed_prefix; }  // the usual case: everything is already in place
+	else if (room.p) g_out_pool.release(room.p);
 	gs.p[gs.used] = 0; go.p[go.used] = 0;
 	*sam = gs.p; *ori = go.p;
 	if (sam_bytes) *sam_bytes = gs.used;
@@ -533,7 +603,7 @@ int pansvr_aln_last_stats(const pansvr_aln_ctx *c, pansvr_aln_stats_t *out)
 	return 0;
 }
 
-void pansvr_free(void *p) { free(p); }
+void pansvr_free(void *p) { if (p && !g_out_pool.release(p)) free(p); }
 
 int pansvr_aln_prime_read_stats(pansvr_aln_ctx *c, const char *fastq_head, size_t n)
 {

@@ -28,7 +28,7 @@ const uint32_t PR_U32MAX = 0xffffffffu;
 struct DevOri { uint32_t chr, ref_bg, read_bg, align_score; uint8_t mapq, direction, unmapped, skip; };   // parse_ori_mapping_rst + RR:413-414
 struct DevSv { uint32_t chr_id, st_pos; int32_t end_offset; uint32_t pad; };                                  // SV_chr_info, per anchor id
 struct PairIndexView { const uint32_t *chr_search_index, *chr_end_n; const DevSv *sv; };
-struct PairOpts { int isize_max, isize_min, read_len; };
+struct PairOpts { int isize_max, isize_min, read_len, min_filter_score; };   // (min_filter_score: pairs scoring at most this go to the `-p` output, RR:776)
 
 struct DevRes {                                                    // MAX_IDX_OUTPUT, RRH:232-318 (what stage F needs of it)
 	uint32_t align_score, chain_score, max_index, read_bg, chr, ref_bg;
@@ -42,6 +42,7 @@ struct DevFinal {                                                  // what the r
 	uint32_t flags;                                                // FIN_*
 	uint32_t p_chr, p_ref_bg, p_align, p_chain, p_mapq; int32_t p_cand, p_sv, p_mate_sv; uint32_t mate_chr, mate_ref_bg;
 	uint32_t s_chr, s_ref_bg, s_read_bg, s_align; int32_t s_sv;
+	uint32_t p_ins, p_ncig;                                        // inserted bases / entries of the primary's CIGAR (the `-p` decision reads them, RR:788-792)
 };
 enum { FIN_PRIMARY = 1, FIN_P_ORI = 2, FIN_HAS_MATE = 4, FIN_SECONDARY = 8, FIN_P_FWD = 16, FIN_S_FWD = 32, FIN_P_CIGAR_OK = 64 };
 struct DevPairFinal { int32_t max_score, cur_isize; uint8_t gain, proper, valid, pad; };
@@ -348,9 +349,9 @@ SEED_HD void dev_probe_pair(const PairIndexView &ix, const PairOpts &o, const De
 // Primary / secondary / mate of both reads once the pairing is decided (win_i / win_j: the in-order pass's winner for a
 // pair with redo == 2).  set_primary_secondary_mate, RRH:501-534, and what output_BAM reads of the results.
 SEED_HD void dev_finalize_pair(const PairIndexView &ix, const PairOpts &o, const DevOri *ori, DevPairState &st, uint8_t redo, int win_i, int win_j,
-                               DevFinal *fin, DevPairFinal &pf)
+                               const DevCand *cands, const DevCigar *cigs, DevFinal *fin, DevPairFinal &pf)
 {
-	for (int k = 0; k < 2; ++k) { DevFinal &f = fin[k]; f.flags = 0; f.p_chr = f.p_ref_bg = f.p_align = f.p_chain = f.p_mapq = 0; f.p_cand = f.p_sv = f.p_mate_sv = -1; f.mate_chr = f.mate_ref_bg = 0; f.s_chr = f.s_ref_bg = f.s_read_bg = f.s_align = 0; f.s_sv = -1; }
+	for (int k = 0; k < 2; ++k) { DevFinal &f = fin[k]; f.flags = 0; f.p_ins = f.p_ncig = 0; f.p_chr = f.p_ref_bg = f.p_align = f.p_chain = f.p_mapq = 0; f.p_cand = f.p_sv = f.p_mate_sv = -1; f.mate_chr = f.mate_ref_bg = 0; f.s_chr = f.s_ref_bg = f.s_read_bg = f.s_align = 0; f.s_sv = -1; }
 	pf.max_score = 0; pf.cur_isize = 0; pf.gain = pf.proper = 0; pf.valid = 0; pf.pad = 0;
 	if (redo == PR_REDO_HOST) return;
 	PairSide S[2];
@@ -377,7 +378,16 @@ SEED_HD void dev_finalize_pair(const PairIndexView &ix, const PairOpts &o, const
 		if (c.is_ori) f.flags |= FIN_P_ORI;
 		if (c.direction == PR_FORWARD) f.flags |= FIN_P_FWD;
 		f.p_chr = c.chr; f.p_ref_bg = c.ref_bg; f.p_align = c.align_score; f.p_sv = c.sv;
-		if (!c.is_ori) { const DevRes &r = S[k].res[mi]; f.p_chain = r.chain_score; f.p_mapq = r.mapq; f.p_cand = r.cand; if (r.cigar_ok) f.flags |= FIN_P_CIGAR_OK; }
+		if (!c.is_ori) {
+			const DevRes &r = S[k].res[mi];
+			f.p_chain = r.chain_score; f.p_mapq = r.mapq; f.p_cand = r.cand;
+			if (r.cigar_ok) f.flags |= FIN_P_CIGAR_OK;
+			const DevCand &cd = cands[r.cand];
+			f.p_ncig = cd.n_cig;
+			int ins = 0;
+			for (uint32_t x = 0; x < cd.n_cig; ++x) if (cigs[cd.cig_off + x].type == 1) ins += cigs[cd.cig_off + x].size;
+			f.p_ins = (uint32_t)ins;
+		}
 		else { f.p_mapq = S[k].ori.mapq; f.flags |= FIN_P_CIGAR_OK; }
 		const DevRes *sec = nullptr;
 		if (c.is_ori && S[k].n > 0) sec = &S[k].res[0];

@@ -1748,7 +1748,7 @@ bool AlnPipeline::align_block_host(const FastqRec *recs, size_t n_reads_in, Bloc
 bool AlnPipeline::align_block(const FastqRec *recs, size_t n_reads_in, BlockOutput &out, std::string &err, uint64_t seq)
 {
 	const size_t n_pairs = n_reads_in / 2, nd = 2 * n_pairs;
-	out.sam_text.clear();
+	out.sam_text.clear(); out.placed = false; out.placed_bytes = 0; out.place_called = false;
 	if (!stages_ || n_pairs == 0) return align_block_host(recs, n_reads_in, out, err, seq, nullptr);
 	ensure_read_stats(recs[0]);
 	// records are views into one buffer, in input order: the text they span goes up as it is
@@ -1765,7 +1765,7 @@ bool AlnPipeline::align_block(const FastqRec *recs, size_t n_reads_in, BlockOutp
 bool AlnPipeline::align_block_text(const char *text, size_t bytes, size_t n_pairs, BlockOutput &out, std::string &err, uint64_t seq, bool *reparse)
 {
 	*reparse = false;
-	out.sam_text.clear();
+	out.sam_text.clear(); out.placed = false; out.placed_bytes = 0; out.place_called = false;
 	if (!stages_ || n_pairs == 0) { *reparse = true; return true; }
 	return align_block_dev(text, bytes, nullptr, n_pairs, out, err, seq, reparse);
 }
@@ -1781,8 +1781,10 @@ bool AlnPipeline::align_block_dev(const char *base, size_t text_bytes, const Fas
 	if (!db) return false;
 	struct Release { AlnPipeline &P; DevBuffers *b; ~Release() { P.release_dev(b); } } release{*this, db};
 	if (text_bytes >= 0xfffffff0ull) { err = "block too large for the device stages (cut it into smaller blocks)"; return false; }
-	db->text.resize(text_bytes + 1);
-	{
+	// the text goes up from page-locked memory: the caller's own buffer if it is (pansvr_host_alloc), else a staging copy of it
+	const bool pinned_input = staging_is_pinned(base);
+	if (!pinned_input) {
+		db->text.resize(text_bytes + 1);
 		const size_t piece = (size_t)4 << 20, n_piece = (text_bytes + piece - 1) / piece;
 		parallel(n_piece, [&](size_t b, size_t e, int) { for (size_t k = b; k < e; ++k) memcpy(db->text.data() + k * piece, base + k * piece, std::min(piece, text_bytes - k * piece)); }, 2);
 	}
@@ -1803,10 +1805,10 @@ bool AlnPipeline::align_block_dev(const char *base, size_t text_bytes, const Fas
 	add_time(0, now() - t0); t0 = now();
 	// ---- first trip: the original alignments, stages A..F1 and the probe of stage F
 	DevStageIn in;
-	in.text = db->text.data(); in.text_bytes = text_bytes; in.reads = db->reads.data(); in.n_reads = nd; in.bits_words = words; in.list_bytes = list_bytes;
+	in.text = pinned_input ? (const uint8_t*)base : db->text.data(); in.text_bytes = text_bytes; in.reads = db->reads.data(); in.n_reads = nd; in.bits_words = words; in.list_bytes = list_bytes;
 	in.scores = AlnScores{opt.match, opt.mismatch, opt.gap_open, opt.gap_ex, opt.gap_open2, opt.gap_ex2};
 	in.recs = recs ? db->recs.data() : nullptr; in.parse_text = recs == nullptr;
-	in.pair_opts = PairOpts{opt.isize_max, opt.isize_min, opt.read_len};
+	in.pair_opts = PairOpts{opt.isize_max, opt.isize_min, opt.read_len, min_filter_score_};
 	const char *dump = getenv("PANSVR_DUMP_STAGES");
 	in.want_tables = dump != nullptr;
 	if (!stage_service_run(db->svc, in, db->out, err)) return false;
@@ -1880,8 +1882,14 @@ bool AlnPipeline::align_block_dev(const char *base, size_t text_bytes, const Fas
 		for (size_t p = 0; p < n_pairs; ++p) db->host_len[p] = 0;
 		for (size_t s = 0; s < nh; ++s) db->host_len[host_list[s]] = (uint32_t)h_sam[s].size();
 		// ---- second trip: the winners go up; primary / secondary / mate of every read and the block's SAM text come back
-		if (!stage_service_finalize(db->svc, in.pair_opts, opt.not_ori ? 1 : 0, n_pairs, db->win.data(), db->host_len.data(), o, out.sam_text, e2)) return false;
-		for (size_t s = 0; s < nh; ++s) if (!h_sam[s].empty()) memcpy(out.sam_text.data() + o.txt_off[2 * (size_t)host_list[s]], h_sam[s].data(), h_sam[s].size());
+		bool got = false;
+		o.text_dest = [&](size_t total) -> char* { char *p = out.place ? out.place(total) : nullptr; out.place_called = true; got = p != nullptr; return p; };
+		const bool fin_ok = stage_service_finalize(db->svc, in.pair_opts, opt.not_ori ? 1 : 0, n_pairs, db->win.data(), db->host_len.data(), o, out.sam_text, e2);
+		o.text_dest = nullptr;
+		if (!fin_ok) return false;
+		out.placed = got;
+		if (out.placed) { out.placed_bytes = o.text_total; out.placed_ptr = o.text_ptr; }
+		for (size_t s = 0; s < nh; ++s) if (!h_sam[s].empty()) memcpy(o.text_ptr + o.txt_off[2 * (size_t)host_list[s]], h_sam[s].data(), h_sam[s].size());
 		bad_cigar_records_ += o.bad_records;
 		add_time(2, now() - t1); t1 = now();
 		// ---- the `-p` records (output_ori_bam, RR:656-717, 776-797) are rare: written here from what came back
@@ -1889,14 +1897,34 @@ bool AlnPipeline::align_block_dev(const char *base, size_t text_bytes, const Fas
 		for (size_t s = 0; s < nh; ++s) slot_of[host_list[s]] = (int32_t)s;
 		Impl Iq(*this);
 		Iq.count_bad = false;
+		// the device selected the pairs that may qualify (score at most min_filter_score, both originals on a chromosome)
+		std::vector<uint32_t> sel_order(o.sel_pair.size());
+		for (size_t k = 0; k < sel_order.size(); ++k) sel_order[k] = (uint32_t)k;
+		std::sort(sel_order.begin(), sel_order.end(), [&](uint32_t x, uint32_t y) { return o.sel_pair[x] < o.sel_pair[y]; });
 		parallel(n_pairs, [&](size_t pb, size_t pe_, int t) {             // chunk t writes its pairs, in order, into buffer t
 			std::string ori, scratch;
 			ori.swap(out.ori[(size_t)t]);
-			for (size_t pi = pb; pi < pe_; ++pi) {
-				if (slot_of[pi] >= 0) { ori += h_ori[(size_t)slot_of[pi]]; continue; }
-				const DevPairFinal &pf = o.pfin[pi];
-				if (!(pf.max_score <= min_filter_score_)) continue;
-				// rebuild what output_BAM / output_ori_bam read of the two handlers
+			// what this chunk has to look at, in pair order: the host path's pairs and the selected ones
+			size_t hi = std::lower_bound(host_list.begin(), host_list.end(), (uint32_t)pb) - host_list.begin();
+			size_t si = std::lower_bound(sel_order.begin(), sel_order.end(), (uint32_t)pb, [&](uint32_t x, uint32_t v) { return o.sel_pair[x] < v; }) - sel_order.begin();
+			size_t pi_all = pb;                                               // (sel_all: every pair is looked at)
+			for (;;) {
+				size_t pi; const DevFinal *f2 = nullptr; const DevPairFinal *pfp = nullptr; bool host = false;
+				if (o.sel_all) {
+					if (pi_all >= pe_) break;
+					pi = pi_all++;
+					if (slot_of[pi] >= 0) host = true; else { f2 = &o.fin[2 * pi]; pfp = &o.pfin[pi]; }
+				} else {
+					const size_t hp = hi < host_list.size() ? host_list[hi] : (size_t)-1, sp_ = si < sel_order.size() ? o.sel_pair[sel_order[si]] : (size_t)-1;
+					pi = std::min(hp, sp_);
+					if (pi >= pe_) break;
+					if (hp == pi) { host = true; ++hi; if (sp_ == pi) ++si; }
+					else { f2 = &o.sel_fin[2 * (size_t)sel_order[si]]; pfp = &o.sel_pfin[sel_order[si]]; ++si; }
+				}
+				if (host) { ori += h_ori[(size_t)slot_of[pi]]; continue; }
+				const DevPairFinal &pf = *pfp;
+				if (!pf.valid || !(pf.max_score <= min_filter_score_)) continue;
+				// rebuild what output_ori_bam reads of the two handlers
 				ReadState se[2];
 				Result prim[2], sec[2];
 				Impl::PE pe;
@@ -1909,7 +1937,7 @@ bool AlnPipeline::align_block_dev(const char *base, size_t text_bytes, const Fas
 					r.read_l = (int)r.rec->seq_l;
 					Iq.parse_ori(r);
 					if (r.ori.chr > 24) r.ori_unmapped = true;
-					const DevFinal &f = o.fin[2 * pi + m];
+					const DevFinal &f = f2[m];
 					if (!(f.flags & FIN_PRIMARY)) continue;
 					Result *c;
 					if (f.flags & FIN_P_ORI) c = &r.ori;
@@ -1917,26 +1945,16 @@ bool AlnPipeline::align_block_dev(const char *base, size_t text_bytes, const Fas
 						c = &prim[m];
 						c->is_ori = false; c->chr = f.p_chr; c->ref_bg = f.p_ref_bg; c->align_score = f.p_align; c->chain_score = f.p_chain;
 						c->mapq = (uint8_t)f.p_mapq; c->direction = (f.flags & FIN_P_FWD) ? FORWARD : REVERSE; c->cigar_ok = (f.flags & FIN_P_CIGAR_OK) != 0;
-						const DevCand &cd = o.cands[(size_t)f.p_cand];
-						c->cigar.resize(cd.n_cig);
-						if (cd.n_cig) memcpy((void*)c->cigar.data(), o.cigs.data() + cd.cig_off, (size_t)cd.n_cig * sizeof(CigarPath));
+						c->cigar.clear();                                       // (stand-in with the two properties the `-p` decision reads: empty or not, inserted bases)
+						if (f.p_ncig) { c->cigar.push_back(CigarPath{0, 1}); if (f.p_ins) c->cigar.push_back(CigarPath{1, (int16_t)std::min<uint32_t>(f.p_ins, 32767)}); }
 					}
 					c->sv = f.p_sv >= 0 ? &idx.sv_info[(size_t)f.p_sv] : nullptr;
 					c->has_mate = (f.flags & FIN_HAS_MATE) != 0; c->mate_chr = f.mate_chr; c->mate_ref_bg = f.mate_ref_bg;
 					c->mate_sv = f.p_mate_sv >= 0 ? &idx.sv_info[(size_t)f.p_mate_sv] : nullptr;
 					(m == 0 ? pe.m1 : pe.m2) = c;
-					if (!pe.gain) continue;
-					r.primary = c;
-					if (f.flags & FIN_SECONDARY) {
-						Result &s2 = sec[m];
-						s2.chr = f.s_chr; s2.ref_bg = f.s_ref_bg; s2.read_bg = f.s_read_bg; s2.align_score = f.s_align;
-						s2.direction = (f.flags & FIN_S_FWD) ? FORWARD : REVERSE; s2.sv = f.s_sv >= 0 ? &idx.sv_info[(size_t)f.s_sv] : nullptr;
-						r.secondary = &s2;
-					}
-				}
-				if (pe.gain) {                                                 // (the main records came from the device; this run only leaves the handlers
-					scratch.clear();                                            // in the state output_ori_bam finds them in, and must not count twice)
-					for (int m = 0; m < 2; ++m) Iq.output_bam(se[m], scratch, m == 0, pe.cur_isize);
+					// the main record (written by the device) came first: a reverse-strand record leaves the read reverse-complemented
+					// in place and back (RR:502-510), after which anything but ACGT reads 'N'
+					if (pe.gain && c->chr != U32MAX && !(opt.not_ori && c->is_ori) && c->direction == REVERSE) r.seq_twice_reversed = true;
 				}
 				Iq.output_ori_pair(se, pe, scratch, ori, min_filter_score_);
 			}

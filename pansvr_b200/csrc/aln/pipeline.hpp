@@ -61,6 +61,7 @@ struct FastqRec {                     // views into the caller's FASTQ text (no 
 // copies of a block are direct DMA; plain malloc in the host test build.
 void *staging_alloc(size_t bytes);
 void staging_free(void *p);
+bool staging_is_pinned(const void *p);   // page-locked memory the device can copy from directly (a caller's buffer from pansvr_host_alloc)
 
 // The part of std::vector the pipeline needs, for trivially copyable T, on staging memory; grow-only, contents are
 // not initialised by resize().  The pipeline keeps its batch buffers across blocks, so they are pinned once.
@@ -143,6 +144,11 @@ struct BlockOutput {                  // record text of one block: buffer t hold
 	std::vector<std::string> sam;     // concatenating the buffers in order gives the block's output in input order
 	std::vector<std::string> ori;     // `-p` output: pairs still poorly aligned
 	HostVec<char> sam_text;           // device path: the block's main output as one text, straight from the device (then `sam` is empty)
+	// ... or straight into the caller's buffer: place(total) is asked once per block for room for `total` bytes (nullptr = none: the
+	// text goes to sam_text); placed_bytes = what went there.  A block that has no text for it calls place(0) all the same, so
+	// that callers can hand the room out block by block, in order.
+	std::function<char*(size_t)> place;
+	size_t placed_bytes = 0; const char *placed_ptr = nullptr; bool placed = false, place_called = false;
 };
 
 struct CigarPath { uint8_t type; int16_t size; };

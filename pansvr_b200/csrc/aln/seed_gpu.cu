@@ -76,6 +76,12 @@ void *staging_alloc(size_t bytes)
 	return cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) == cudaSuccess ? p : nullptr;
 }
 void staging_free(void *p) { if (p) cudaFreeHost(p); }
+bool staging_is_pinned(const void *p)
+{
+	cudaPointerAttributes a;
+	if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+	return a.type == cudaMemoryTypeHost;
+}
 
 struct SeedService {
 	int device = 0;

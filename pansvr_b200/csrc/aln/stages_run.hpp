@@ -28,7 +28,7 @@ namespace pansvr {
 enum DevSlot {
 	SL_TEXT, SL_READS, SL_BITS, SL_LIST, SL_FLAGS, SL_MEM_CNT, SL_MEM_OFF, SL_MEMS, SL_MEMS_TMP, SL_NVU, SL_SEED_CNT, SL_SEED_OFF,
 	SL_SEEDS, SL_SEEDS_TMP, SL_DIST, SL_PRE, SL_PLAN_CNT, SL_PLAN_OFF, SL_CANDS, SL_PIECES, SL_QLEN, SL_TLEN, SL_QOFF, SL_TOFF,
-	SL_Q, SL_T, SL_RES, SL_KCIG, SL_CIGS, SL_MISC, SL_SCAN_TMP, SL_USED, SL_ORI, SL_PSTATE, SL_PROBE, SL_WIN, SL_FINAL, SL_PFINAL, SL_RECS, SL_HOSTLEN, SL_TXT_LEN, SL_TXT_OFF, SL_TXT, SL_NL_CNT, SL_NL_OFF, SL_LINES, SL_LAY_CNT, SL_LAY_OFF, SL_COUNT
+	SL_Q, SL_T, SL_RES, SL_KCIG, SL_CIGS, SL_MISC, SL_SCAN_TMP, SL_USED, SL_ORI, SL_PSTATE, SL_PROBE, SL_WIN, SL_FINAL, SL_PFINAL, SL_RECS, SL_HOSTLEN, SL_TXT_LEN, SL_TXT_OFF, SL_TXT, SL_NL_CNT, SL_NL_OFF, SL_LINES, SL_LAY_CNT, SL_LAY_OFF, SL_SEL_PAIR, SL_SEL_FIN, SL_SEL_PFIN, SL_COUNT
 };
 
 // ---- functors (one element of work each; plain data members only, so they can be passed to a kernel by value)
@@ -204,8 +204,23 @@ struct FnProbe {                                                   // one pair =
 	}
 };
 struct FnFinalize {
-	PairIndexView ix; PairOpts o; const DevOri *ori; DevPairState *state; const DevProbe *probe; const int8_t *win; DevFinal *fin; DevPairFinal *pfin;
-	SEED_HD void operator()(size_t p) const { dev_finalize_pair(ix, o, ori + 2 * p, state[p], probe[p].redo, win[2 * p], win[2 * p + 1], fin + 2 * p, pfin[p]); }
+	PairIndexView ix; PairOpts o; const DevOri *ori; DevPairState *state; const DevProbe *probe; const int8_t *win; const DevCand *cands; const DevCigar *cigs;
+	DevFinal *fin; DevPairFinal *pfin;
+	SEED_HD void operator()(size_t p) const { dev_finalize_pair(ix, o, ori + 2 * p, state[p], probe[p].redo, win[2 * p], win[2 * p + 1], cands, cigs, fin + 2 * p, pfin[p]); }
+};
+struct FnOriSelect {                                               // the (few) pairs whose originals may go to the `-p` output: their results go back to the host
+	PairOpts o; const DevOri *ori; const DevFinal *fin; const DevPairFinal *pfin; uint32_t *count; uint32_t cap; uint32_t *sel_pair; DevFinal *sel_fin; DevPairFinal *sel_pfin;
+	SEED_HD void operator()(size_t p) const
+	{
+		if (!pfin[p].valid || pfin[p].max_score > o.min_filter_score || ori[2 * p].chr == PR_U32MAX || ori[2 * p + 1].chr == PR_U32MAX) return;
+#if defined(__CUDA_ARCH__)
+		const uint32_t k = atomicAdd(count, 1u);
+#else
+		const uint32_t k = (*count)++;
+#endif
+		if (k >= cap) return;
+		sel_pair[k] = (uint32_t)p; sel_fin[2 * k] = fin[2 * p]; sel_fin[2 * k + 1] = fin[2 * p + 1]; sel_pfin[k] = pfin[p];
+	}
 };
 
 struct FnCells {                                                   // in-band DP cells of the tasks (the unit GCUPS is quoted in, KSW:131-138)
@@ -254,10 +269,15 @@ struct DevStageOut {                                               // host side,
 	HostVec<uint32_t> cand_off;                                    // n + 1
 	HostVec<DevCand> cands; HostVec<DevCigar> cigs;
 	HostVec<DevProbe> pair_probe;                                  // n / 2: what the in-order pass has to do for each pair
-	HostVec<DevFinal> fin; HostVec<DevPairFinal> pfin;             // after run_device_finalize: n and n / 2
+	// after run_device_finalize: the results of the pairs that may go to the `-p` output (pair index, both reads, pair) -- or, if
+	// sel_all, of every pair (fin: n, pfin: n / 2)
+	HostVec<uint32_t> sel_pair; HostVec<DevFinal> sel_fin; HostVec<DevPairFinal> sel_pfin; bool sel_all = false;
+	HostVec<DevFinal> fin; HostVec<DevPairFinal> pfin;
 	HostVec<DevRec> recs; bool parse_ok = true;                     // parse_text: the record table the device made
 	HostVec<uint32_t> txt_off;                                     // n + 1: place of every read's record in the block's SAM text
 	uint64_t bad_records = 0;                                      // records left out because htslib would reject them (CIGAR does not span the read)
+	std::function<char*(size_t)> text_dest;                        // optional: called once with the size of the block's SAM text, returns where it goes
+	char *text_ptr = nullptr; size_t text_total = 0;               // where it went
 	uint64_t n_tasks = 0, n_cells = 0, probes = 0;
 	DevCounters dev;
 };
@@ -405,9 +425,11 @@ bool run_device_stages(BE &be, const IndexView &ix, const uint64_t *d_pos, const
 		uint64_t cells = 0;
 		be.d2h(&overflow, d_misc, 4);
 		be.d2h(&cells, d_cells, 8);
-		out.cands.resize(n_cand); out.cigs.resize(n_cig);
-		be.d2h(out.cands.data(), d_cands, n_cand * sizeof(DevCand));
-		be.d2h(out.cigs.data(), d_cigs, n_cig * sizeof(DevCigar));
+		out.cands.resize(in.want_tables ? n_cand : 0); out.cigs.resize(in.want_tables ? n_cig : 0);
+		if (in.want_tables) {
+			be.d2h(out.cands.data(), d_cands, n_cand * sizeof(DevCand));
+			be.d2h(out.cigs.data(), d_cigs, n_cig * sizeof(DevCigar));
+		}
 		be.sync();
 		if (!overflow) { out.n_tasks = n_task; out.n_cells = cells; break; }
 		cap *= 4;
@@ -485,25 +507,46 @@ bool run_device_finalize(BE &be, const PairIndexView &pix, const PairOpts &o, co
 	be.zero(d_misc, 64);
 	be.zero(d_len + n, 4);
 	const DevOri *d_ori = be.template buf<DevOri>(SL_ORI, 0);
-	be.for_each(n_pairs, FnFinalize{pix, o, d_ori, be.template buf<DevPairState>(SL_PSTATE, 0), be.template buf<DevProbe>(SL_PROBE, 0), d_win, d_fin, d_pfin}, 6);
+	be.for_each(n_pairs, FnFinalize{pix, o, d_ori, be.template buf<DevPairState>(SL_PSTATE, 0), be.template buf<DevProbe>(SL_PROBE, 0), d_win,
+	                                be.template buf<DevCand>(SL_CANDS, 0), be.template buf<DevCigar>(SL_CIGS, 0), d_fin, d_pfin}, 6);
+	// the `-p` candidates: selected on the device, a short list for the host (all of it if the list overflows its room)
+	const uint32_t sel_cap = (uint32_t)(n_pairs / 8 + 1024);
+	uint32_t *d_sel_pair = be.template buf<uint32_t>(SL_SEL_PAIR, sel_cap);
+	DevFinal *d_sel_fin = be.template buf<DevFinal>(SL_SEL_FIN, 2 * (size_t)sel_cap);
+	DevPairFinal *d_sel_pfin = be.template buf<DevPairFinal>(SL_SEL_PFIN, sel_cap);
+	if (!d_sel_pair || !d_sel_fin || !d_sel_pfin) { err = "device stages: out of device memory"; return false; }
+	be.for_each(n_pairs, FnOriSelect{o, d_ori, d_fin, d_pfin, d_misc + 2, sel_cap, d_sel_pair, d_sel_fin, d_sel_pfin}, 6);
 	FnText ft{be.template buf<uint8_t>(SL_TEXT, 0), be.template buf<DevRec>(SL_RECS, 0), d_ori, d_fin, d_pfin, be.template buf<DevCand>(SL_CANDS, 0), be.template buf<DevCigar>(SL_CIGS, 0),
 	          T, d_hl, d_len, d_off, nullptr, d_misc, false};
 	be.for_each(n, ft, 7);
 	be.scan(d_len, d_off, n + 1);
 	be.d2h(out.txt_off.data(), d_off, (n + 1) * 4);
-	be.d2h(out.fin.data(), d_fin, n * sizeof(DevFinal));
-	be.d2h(out.pfin.data(), d_pfin, n_pairs * sizeof(DevPairFinal));
-	uint32_t bad = 0;
+	uint32_t bad = 0, n_sel = 0;
 	be.d2h(&bad, d_misc, 4);
+	be.d2h(&n_sel, d_misc + 2, 4);
 	be.sync();
 	out.bad_records = bad;
+	out.sel_all = n_sel > sel_cap;
+	if (out.sel_all) {                                             // (more than an eighth of the pairs: everything comes back)
+		be.d2h(out.fin.data(), d_fin, n * sizeof(DevFinal));
+		be.d2h(out.pfin.data(), d_pfin, n_pairs * sizeof(DevPairFinal));
+		out.sel_pair.clear(); out.sel_fin.clear(); out.sel_pfin.clear();
+	} else {
+		out.sel_pair.resize(n_sel); out.sel_fin.resize(2 * (size_t)n_sel); out.sel_pfin.resize(n_sel);
+		be.d2h(out.sel_pair.data(), d_sel_pair, (size_t)n_sel * 4);
+		be.d2h(out.sel_fin.data(), d_sel_fin, 2 * (size_t)n_sel * sizeof(DevFinal));
+		be.d2h(out.sel_pfin.data(), d_sel_pfin, (size_t)n_sel * sizeof(DevPairFinal));
+	}
 	const size_t total = out.txt_off[n];
 	char *d_txt = be.template buf<char>(SL_TXT, total + 16);
 	if (!d_txt) { err = "device stages: out of device memory"; return false; }
 	ft.out = d_txt; ft.write = true;
 	be.text_write(n, ft);
-	text_out.resize(total);
-	be.d2h(text_out.data(), d_txt, total);
+	// where the text goes: the place the caller hands out for it (e.g. behind the earlier blocks' text in one output buffer), else text_out
+	char *dst = out.text_dest ? out.text_dest(total) : nullptr;
+	if (!dst) { text_out.resize(total); dst = text_out.data(); } else text_out.clear();
+	out.text_ptr = dst; out.text_total = total;
+	be.d2h(dst, d_txt, total);
 	be.sync();
 	return true;
 }

@@ -221,7 +221,11 @@ void plan_batch(pansvr_ksw_ctx *ctx, const kswhost::Plan &pl, int64_t n, const i
 	ctx->h_variant.resize(n);
 	ctx->h_rows.resize(n);
 	ctx->h_order.resize(n);
-	std::unordered_map<uint64_t, Shape> memo;
+	std::unordered_map<uint64_t, Shape> memo;                  // shapes beyond the direct table
+	enum { DIRECT = 512 };                                     // (qlen, tlen) below this: one table look-up per task (the fc_aln task mix)
+	static thread_local std::vector<Shape> direct;
+	static thread_local int direct_w = -0x7fffffff;
+	if (direct.empty() || direct_w != w) { direct.assign((size_t)DIRECT * DIRECT, Shape{-1, 0}); direct_w = w; }
 	uint64_t last_key = ~0ull; Shape last{0, 0};
 	int64_t count[N_VARIANTS];
 	memset(count, 0, sizeof(count));

@@ -17,6 +17,7 @@ namespace pansvr {
 
 void *staging_alloc(size_t bytes) { return malloc(bytes ? bytes : 1); }
 void staging_free(void *p) { free(p); }
+bool staging_is_pinned(const void *) { return false; }
 
 struct SeedService { IndexView view; };
 

@@ -22,7 +22,9 @@ def fc_aln_emul():
     env = dict(os.environ, PANSVR_ORACLE_SO=os.path.join(ROOT, "oracle", "libksw_oracle.so"))
 
     def run(d, out, ori, extra=("-S",), threads=1, sub_pairs=0):
-        e = dict(env, PANSVR_SUB_PAIRS=str(sub_pairs)) if sub_pairs else env
+        e = dict(os.environ, **{k: env[k] for k in ("PANSVR_ORACLE_SO",)})      # (the environment as it is at the call)
+        if sub_pairs:
+            e["PANSVR_SUB_PAIRS"] = str(sub_pairs)
         subprocess.check_call([os.path.join(HERE, "emul", "fc_aln_emul"), "-t", str(threads), "-o", out, "-p", ori, *extra,
                                d.index_dir, d.reads_fq, d.header_sam], env=e, stderr=subprocess.DEVNULL)
     return run
@@ -73,6 +75,22 @@ def test_host_pipeline_matches_reference_sam(fc_aln_emul, name):
         assert gzip.decompress(read(mb))[:4] == b"BAM\x01"
     finally:
         pass
+
+
+def test_output_room_spill(fc_aln_emul):
+    """The device path writes every sub-block's SAM text straight behind the previous one's in one output buffer; when that
+    buffer is too small (forced here) the remaining text is assembled by copying -- same bytes either way."""
+    need_ref_tools()
+    demo = get_demo("multi_allele")
+    out, ori = os.path.join(demo.wd, "spill.sam"), os.path.join(demo.wd, "spill_ori.sam")
+    for room in ("150000", "1"):
+        os.environ["PANSVR_ROOM_BYTES"] = room
+        try:
+            fc_aln_emul(demo.data, out, ori, threads=4, sub_pairs=97)
+        finally:
+            del os.environ["PANSVR_ROOM_BYTES"]
+        assert first_diff(read(out), read(demo.ref_sam)) is None
+        assert read(ori) == read(demo.ref_ori)
 
 
 def test_edge_inputs_match_reference(fc_aln_emul):
