@@ -402,7 +402,7 @@ int run_block(pansvr_aln_ctx *c, const char *fastq, size_t n, std::vector<Part> 
 		// a few in flight (their device trips and host passes overlap); all of them while the context waits for another process's
 		// stream state (pansvr_aln_await_state), so that only the in-order passes wait and every other stage of the shard is done by
 		// the time the state arrives
-		size_t flight = c->pipe->has_device_stages() ? 3 : 2;
+		size_t flight = c->pipe->has_device_stages() ? 5 : 2;
 		if (const char *e = getenv("PANSVR_FLIGHT")) { const long v = atol(e); if (v > 0) flight = (size_t)v; }
 		if (c->pipe->awaiting_streams()) flight = n_sub;
 		std::vector<std::thread> th(n_sub);
