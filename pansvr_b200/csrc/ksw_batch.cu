@@ -166,8 +166,13 @@ struct pansvr_ksw_ctx {
 	int device = 0, sm_count = 0;
 	int smem_optin = 227 * 1024;      // cudaDevAttrMaxSharedMemoryPerBlockOptin
 	cudaStream_t stream = nullptr;
+	// the team variants of one batch run side by side on their own streams (each launch fills the device with persistent CTAs, so
+	// what overlaps are their tails: a batch of a few hundred thousand short tasks is otherwise four launches with four tails)
+	cudaStream_t vstream[4] = {nullptr, nullptr, nullptr, nullptr};
+	cudaEvent_t vev_in = nullptr, vev_done[4] = {nullptr, nullptr, nullptr, nullptr};
 	cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
 	DevBuf qseq, tseq, qoff, toff, qlen, tlen, res, cigar, order, counters, tb, gscratch;
+	DevBuf tb_v[16];                 // traceback scratch per variant (they run concurrently)
 	std::vector<int> h_order;
 	std::vector<uint8_t> h_variant;
 	std::vector<int> h_rows;
@@ -277,7 +282,7 @@ void plan_batch(pansvr_ksw_ctx *ctx, const kswhost::Plan &pl, int64_t n, const i
 }
 
 template <int TEAM, bool WRAP, bool WC>
-int launch_team_wc(pansvr_ksw_ctx *ctx, KArgs a, int max_rows, int max_qlen)
+int launch_team_wc(pansvr_ksw_ctx *ctx, KArgs a, int max_rows, int max_qlen, cudaStream_t st, DevBuf &tbuf)
 {
 	constexpr int W = 16 * TEAM, NT = 32 / TEAM;
 	a.smem_per_team = kswteam::team_smem_bytes(TEAM, max_qlen);
@@ -292,21 +297,21 @@ int launch_team_wc(pansvr_ksw_ctx *ctx, KArgs a, int max_rows, int max_qlen)
 	a.tb_per_team = (a.P.flag & kswfast::F_SCORE_ONLY) ? 0 : (((size_t)max_rows + 1) * W + 255) & ~(size_t)255;
 	const size_t tb_cap = (size_t)24 << 30;               // keep the traceback scratch under 24 GiB
 	while (grid > 1 && a.tb_per_team * (size_t)grid * WARPS_PER_CTA * NT > tb_cap) grid = (grid + 1) / 2;
-	CU(ctx->tb.reserve(a.tb_per_team * (size_t)grid * WARPS_PER_CTA * NT + 256));
-	a.tb = (uint8_t*)ctx->tb.p;
+	CU(tbuf.reserve(a.tb_per_team * (size_t)grid * WARPS_PER_CTA * NT + 256));
+	a.tb = (uint8_t*)tbuf.p;
 	ctx->stats.tb_bytes_per_warp = (int64_t)a.tb_per_team * NT;
 	ctx->stats.resident_warps = (int64_t)grid * WARPS_PER_CTA;
-	kern<<<grid, THREADS, smem, ctx->stream>>>(a);
+	kern<<<grid, THREADS, smem, st>>>(a);
 	CU(cudaGetLastError());
 	++ctx->stats.kernel_launches;
 	return 0;
 }
 
 template <int TEAM, bool WRAP>
-int launch_team(pansvr_ksw_ctx *ctx, const KArgs &a, int max_rows, int max_qlen)
+int launch_team(pansvr_ksw_ctx *ctx, const KArgs &a, int max_rows, int max_qlen, cudaStream_t st, DevBuf &tbuf)
 {
-	return (a.P.flag & kswfast::F_SCORE_ONLY) ? launch_team_wc<TEAM, WRAP, false>(ctx, a, max_rows, max_qlen)
-	                                          : launch_team_wc<TEAM, WRAP, true>(ctx, a, max_rows, max_qlen);
+	return (a.P.flag & kswfast::F_SCORE_ONLY) ? launch_team_wc<TEAM, WRAP, false>(ctx, a, max_rows, max_qlen, st, tbuf)
+	                                          : launch_team_wc<TEAM, WRAP, true>(ctx, a, max_rows, max_qlen, st, tbuf);
 }
 
 // everything after the inputs are on the device: plan, launch each variant, leave results on the device
@@ -327,6 +332,8 @@ int run_device(pansvr_ksw_ctx *ctx, int64_t n, const uint8_t *d_qseq, const int6
 	}
 	CU(cudaMemsetAsync(ctx->counters.p, 0, sizeof(int) * N_VARIANTS, ctx->stream));
 	CU(cudaEventRecord(ctx->ev[1], ctx->stream));
+	CU(cudaEventRecord(ctx->vev_in, ctx->stream));               // inputs and plan are in place: the variant streams start from here
+	int n_side = 0;
 	KArgs a;
 	a.P = pl.P;
 	a.qseq = d_qseq; a.qoff = d_qoff; a.qlen = d_qlen; a.tseq = d_tseq; a.toff = d_toff; a.tlen = d_tlen;
@@ -351,22 +358,29 @@ int run_device(pansvr_ksw_ctx *ctx, int64_t n, const uint8_t *d_qseq, const int6
 		} else {
 			const int lg = (v - V_FAST0) >> 1, wrap = (v - V_FAST0) & 1;
 			const int mr = bp.max_rows[v], mq = bp.max_qlen[v];
+			const int side = n_side++ & 3;
+			cudaStream_t st = ctx->vstream[side];
+			if (n_side > 4) CU(cudaStreamWaitEvent(st, ctx->vev_done[side], 0));      // (more than four variants: queue behind the earlier one)
+			else CU(cudaStreamWaitEvent(st, ctx->vev_in, 0));
+			DevBuf &tbuf = ctx->tb_v[v];
 			switch (lg * 2 + wrap) {
-			case 0: rc = launch_team<2, false>(ctx, a, mr, mq); break;
-			case 1: rc = launch_team<2, true>(ctx, a, mr, mq); break;
-			case 2: rc = launch_team<4, false>(ctx, a, mr, mq); break;
-			case 3: rc = launch_team<4, true>(ctx, a, mr, mq); break;
-			case 4: rc = launch_team<8, false>(ctx, a, mr, mq); break;
-			case 5: rc = launch_team<8, true>(ctx, a, mr, mq); break;
-			case 6: rc = launch_team<16, false>(ctx, a, mr, mq); break;
-			case 7: rc = launch_team<16, true>(ctx, a, mr, mq); break;
-			case 8: rc = launch_team<32, false>(ctx, a, mr, mq); break;
-			default: rc = launch_team<32, true>(ctx, a, mr, mq); break;
+			case 0: rc = launch_team<2, false>(ctx, a, mr, mq, st, tbuf); break;
+			case 1: rc = launch_team<2, true>(ctx, a, mr, mq, st, tbuf); break;
+			case 2: rc = launch_team<4, false>(ctx, a, mr, mq, st, tbuf); break;
+			case 3: rc = launch_team<4, true>(ctx, a, mr, mq, st, tbuf); break;
+			case 4: rc = launch_team<8, false>(ctx, a, mr, mq, st, tbuf); break;
+			case 5: rc = launch_team<8, true>(ctx, a, mr, mq, st, tbuf); break;
+			case 6: rc = launch_team<16, false>(ctx, a, mr, mq, st, tbuf); break;
+			case 7: rc = launch_team<16, true>(ctx, a, mr, mq, st, tbuf); break;
+			case 8: rc = launch_team<32, false>(ctx, a, mr, mq, st, tbuf); break;
+			default: rc = launch_team<32, true>(ctx, a, mr, mq, st, tbuf); break;
 			}
+			if (rc == 0) CU(cudaEventRecord(ctx->vev_done[side], st));
 			(wrap ? ctx->stats.tasks_fast_wrap : ctx->stats.tasks_fast_nowrap) += cnt;
 		}
 		if (rc) return rc;
 	}
+	for (int k = 0; k < std::min(n_side, 4); ++k) CU(cudaStreamWaitEvent(ctx->stream, ctx->vev_done[k], 0));     // join
 	CU(cudaEventRecord(ctx->ev[2], ctx->stream));
 	return 0;
 }
@@ -404,6 +418,9 @@ int pansvr_ksw_create(int device, pansvr_ksw_ctx **out)
 	if (cudaDeviceGetAttribute(&c->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device) != cudaSuccess) c->smem_optin = 227 * 1024;
 	memset(&c->stats, 0, sizeof(c->stats));
 	CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+	for (auto &vs : c->vstream) CU(cudaStreamCreateWithFlags(&vs, cudaStreamNonBlocking));
+	CU(cudaEventCreateWithFlags(&c->vev_in, cudaEventDisableTiming));
+	for (auto &e : c->vev_done) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
 	for (auto &e : c->ev) CU(cudaEventCreate(&e));
 	*out = c;
 	return 0;
@@ -414,6 +431,10 @@ void pansvr_ksw_destroy(pansvr_ksw_ctx *c)
 	if (!c) return;
 	cudaSetDevice(c->device);
 	cudaStreamSynchronize(c->stream);
+	for (auto &vs : c->vstream) if (vs) { cudaStreamSynchronize(vs); cudaStreamDestroy(vs); }
+	if (c->vev_in) cudaEventDestroy(c->vev_in);
+	for (auto &e : c->vev_done) if (e) cudaEventDestroy(e);
+	for (DevBuf &b : c->tb_v) b.release();
 	for (DevBuf *b : {&c->qseq, &c->tseq, &c->qoff, &c->toff, &c->qlen, &c->tlen, &c->res, &c->cigar, &c->order, &c->counters,
 	                  &c->tb, &c->gscratch}) b->release();
 	for (auto &e : c->ev) if (e) cudaEventDestroy(e);
