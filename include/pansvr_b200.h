@@ -172,6 +172,10 @@ typedef struct pansvr_aln_ctx pansvr_aln_ctx;
 /* Loads the deBGA index directory (the 8 files `deBGA index -k 22` writes + unipath.chr) and the header SAM of the
  * original BAM, uploads the index to `device`.  Replaces deBGA_INDEX::load_index_file (deBGA_index.cpp:33-80). */
 int  pansvr_aln_create(const char *index_dir, const char *header_sam, const pansvr_aln_options_t *opt, int device, pansvr_aln_ctx **out);
+/* The same on several GPUs of one box: every device gets a replica of the index, the sub-blocks of a block are dealt to the devices
+ * round robin (each on its own host thread and stream), the results are merged by pair index as on one device -- the reference's
+ * kt_for fan-out over a block and its ordered write (read_realignment.cpp:114,160,165-176).  `-d 0,1,2,3` on the command line. */
+int  pansvr_aln_create_multi(const char *index_dir, const char *header_sam, const pansvr_aln_options_t *opt, const int *devices, int n_devices, pansvr_aln_ctx **out);
 void pansvr_aln_destroy(pansvr_aln_ctx *ctx);
 /* Header text the reference writes in front of its output (the original header, verbatim). */
 const char *pansvr_aln_header_text(const pansvr_aln_ctx *ctx);
@@ -207,7 +211,7 @@ int  pansvr_aln_prime_read_stats(pansvr_aln_ctx *ctx, const char *fastq_head, si
 int  pansvr_aln_await_state(pansvr_aln_ctx *ctx, const char *path);
 int  pansvr_aln_publish_state(pansvr_aln_ctx *ctx, const char *path);
 /* Same command line as `panSVR fc_aln` (classify_main, src/main.cpp:18-25): [options] <IndexDir> <reads.fq|-> <header.sam>.
- * Writes BAM, or SAM text with -S, like the reference; -d <gpu> selects the device; -t is the number of host helper threads
+ * Writes BAM, or SAM text with -S, like the reference; -d <gpu>[,<gpu>...] selects the device(s); -t is the number of host helper threads
  * (the output is that of the reference's `-t 1`, the only deterministic mode). */
 int  pansvr_fc_aln_main(int argc, char **argv);
 

@@ -28,6 +28,7 @@ class AlnStatsC(C.Structure):
 
 def _bind(lib):
     lib.pansvr_aln_create.argtypes = [C.c_char_p, C.c_char_p, C.POINTER(AlnOptionsC), C.c_int, C.POINTER(C.c_void_p)]
+    lib.pansvr_aln_create_multi.argtypes = [C.c_char_p, C.c_char_p, C.POINTER(AlnOptionsC), C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_void_p)]
     lib.pansvr_aln_destroy.argtypes = [C.c_void_p]
     lib.pansvr_aln_header_text.restype = C.c_char_p
     lib.pansvr_aln_header_text.argtypes = [C.c_void_p]
@@ -53,7 +54,11 @@ class AlnContext:
         self.lib = _bind(lib or load_library())
         o = AlnOptionsC(**options)
         h = C.c_void_p()
-        rc = self.lib.pansvr_aln_create(index_dir.encode(), header_sam.encode(), C.byref(o), device, C.byref(h))
+        if isinstance(device, (list, tuple)):                     # several GPUs of one box
+            arr = (C.c_int * len(device))(*device)
+            rc = self.lib.pansvr_aln_create_multi(index_dir.encode(), header_sam.encode(), C.byref(o), arr, len(device), C.byref(h))
+        else:
+            rc = self.lib.pansvr_aln_create(index_dir.encode(), header_sam.encode(), C.byref(o), device, C.byref(h))
         if rc != 0:
             raise RuntimeError(f"pansvr_aln_create failed ({rc}): {self.lib.pansvr_aln_last_error().decode()}")
         self.h = h

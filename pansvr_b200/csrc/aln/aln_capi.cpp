@@ -61,6 +61,7 @@ struct pansvr_aln_ctx {
 	DebgaIndex idx;
 	AlnOptions opt;
 	SeedService *seeds = nullptr;
+	std::vector<SeedService*> more_seeds;   // index replicas on the further GPUs of a device list
 	StageService *stages = nullptr;
 	pansvr_ksw_ctx *ksw = nullptr;
 	AlnPipeline *pipe = nullptr;
@@ -260,10 +261,27 @@ int pansvr_aln_create(const char *index_dir, const char *header_sam, const pansv
 	return 0;
 }
 
+int pansvr_aln_create_multi(const char *index_dir, const char *header_sam, const pansvr_aln_options_t *opt, const int *devices, int n_devices, pansvr_aln_ctx **out)
+{
+	if (!devices || n_devices < 1) return PANSVR_E_ARG;
+	const int rc = pansvr_aln_create(index_dir, header_sam, opt, devices[0], out);
+	if (rc != 0) return rc;
+	pansvr_aln_ctx *c = *out;
+	for (int k = 1; k < n_devices; ++k) {                          // an index replica per further GPU; stage services are made on demand
+		std::string err;
+		SeedService *s = seed_service_create(c->idx, devices[k], err);
+		if (!s) { g_aln_err = err; pansvr_aln_destroy(c); *out = nullptr; return PANSVR_E_CUDA; }
+		c->more_seeds.push_back(s);
+		c->pipe->add_device(devices[k], s);
+	}
+	return 0;
+}
+
 void pansvr_aln_destroy(pansvr_aln_ctx *c)
 {
 	if (!c) return;
 	delete c->pipe;
+	for (SeedService *s : c->more_seeds) seed_service_destroy(s);
 	stage_service_destroy(c->stages);
 	seed_service_destroy(c->seeds);
 	pansvr_ksw_destroy(c->ksw);
@@ -402,7 +420,7 @@ int run_block(pansvr_aln_ctx *c, const char *fastq, size_t n, std::vector<Part> 
 		// a few in flight (their device trips and host passes overlap); all of them while the context waits for another process's
 		// stream state (pansvr_aln_await_state), so that only the in-order passes wait and every other stage of the shard is done by
 		// the time the state arrives
-		size_t flight = c->pipe->has_device_stages() ? 5 : 2;
+		size_t flight = c->pipe->has_device_stages() ? 5 * c->pipe->n_devices() : 2;
 		if (const char *e = getenv("PANSVR_FLIGHT")) { const long v = atol(e); if (v > 0) flight = (size_t)v; }
 		if (c->pipe->awaiting_streams()) flight = n_sub;
 		std::vector<std::thread> th(n_sub);
@@ -646,7 +664,8 @@ int pansvr_fc_aln_main(int argc, char **argv)
 	memset(&o, 0, sizeof o);
 	std::string out_path = "./output.bam", ori_path = "./output_ori.bam";
 	bool sam = false;
-	int threads = 4, device = 0;
+	int threads = 4;
+	std::vector<int> devices;
 	static const struct option lo[] = {
 		{"thread", 1, 0, 't'}, {"gap-open1", 1, 0, 'O'}, {"gap-open2", 1, 0, 'P'}, {"gap-extension1", 1, 0, 'E'}, {"gap-extension2", 1, 0, 'F'},
 		{"match-score", 1, 0, 'M'}, {"mis-score", 1, 0, 'm'}, {"zdrop", 1, 0, 'z'}, {"band-width", 1, 0, 'w'}, {"output", 1, 0, 'o'},
@@ -670,7 +689,7 @@ int pansvr_fc_aln_main(int argc, char **argv)
 		case 'Q': o.not_ori = 1; break;
 		case 'S': sam = true; break;
 		case 'R': o.max_use_read = atoi(optarg); o.explicit_mask |= 1 << 9; break;
-		case 'd': device = atoi(optarg); break;
+		case 'd': for (const char *q = optarg; *q;) { devices.push_back(atoi(q)); while (*q && *q != ',') ++q; if (*q == ',') ++q; } break;
 		default: return 1;
 		}
 	}
@@ -721,7 +740,8 @@ int pansvr_fc_aln_main(int argc, char **argv)
 		hand_over(cur.size(), true);                            // whatever is left (an unterminated last line included)
 	});
 	pansvr_aln_ctx *ctx = nullptr;
-	int rc = pansvr_aln_create(argv[optind], argv[optind + 2], &o, device, &ctx);
+	if (devices.empty()) devices.push_back(0);
+	int rc = pansvr_aln_create_multi(argv[optind], argv[optind + 2], &o, devices.data(), (int)devices.size(), &ctx);
 	auto stop_reader = [&]() { failed = true; for (;;) { Job j = jobs.pop(); if (j.last) break; } reader.join(); gzclose(in); };
 	if (rc != 0) { fprintf(stderr, "pansvr_b200 fc_aln: %s\n", pansvr_aln_last_error()); stop_reader(); return 1; }
 	FILE *fo = nullptr, *fp = nullptr;

@@ -17,7 +17,7 @@
 namespace pansvr {
 
 struct AlnPipeline::DevBuffers {                                  // one block's trip through the device stages
-	StageService *svc = nullptr; bool owned = false;
+	StageService *svc = nullptr; bool owned = false; size_t site = 0;
 	HostVec<uint8_t> text;                                        // the block's FASTQ text (pinned staging)
 	HostVec<DevRead> reads;
 	HostVec<DevRec> recs;
@@ -1143,6 +1143,7 @@ AlnPipeline::AlnPipeline(const DebgaIndex &idx, const AlnOptions &o, SeedService
 		b->svc = stages_;
 		dev_all_.push_back(b); dev_free_.push_back(b);
 	}
+	sites_.push_back(DevSite{device_, seeds_});
 	reset();
 }
 
@@ -1153,18 +1154,19 @@ AlnPipeline::~AlnPipeline()
 	for (HostSlot *h : host_all_) delete h;
 }
 
-AlnPipeline::DevBuffers *AlnPipeline::acquire_dev(std::string &err)
+AlnPipeline::DevBuffers *AlnPipeline::acquire_dev(std::string &err, uint64_t seq)
 {
+	const size_t site = (size_t)(seq % sites_.size());               // sub-blocks are dealt to the GPUs round robin
 	{
 		std::lock_guard<std::mutex> lk(dev_pool_m_);
-		if (!dev_free_.empty()) { DevBuffers *b = dev_free_.back(); dev_free_.pop_back(); return b; }
+		for (size_t k = 0; k < dev_free_.size(); ++k) if (dev_free_[k]->site == site) { DevBuffers *b = dev_free_[k]; dev_free_.erase(dev_free_.begin() + (long)k); return b; }
 	}
-	StageService *svc = stage_service_create(idx_, seeds_, ksw_, device_, err);   // another block in flight: its own device state
+	StageService *svc = stage_service_create(idx_, sites_[site].seeds, ksw_, sites_[site].device, err);   // another block in flight: its own device state
 	if (!svc) return nullptr;
 	AlnScores sc{opt.match, opt.mismatch, opt.gap_open, opt.gap_ex, opt.gap_open2, opt.gap_ex2};
 	stage_service_set_scoring(svc, sc, opt.zdrop);
 	DevBuffers *b = new DevBuffers();
-	b->svc = svc; b->owned = true;
+	b->svc = svc; b->owned = true; b->site = site;
 	std::lock_guard<std::mutex> lk(dev_pool_m_);
 	dev_all_.push_back(b);
 	return b;
@@ -1777,7 +1779,7 @@ bool AlnPipeline::align_block_dev(const char *base, size_t text_bytes, const Fas
 	const DebgaIndex &idx = idx_;
 	auto add_time = [&](int stage, double dt) { std::lock_guard<std::mutex> lk(stats_m_); stats.t_stage[stage] += dt; };
 	double t0 = now();
-	DevBuffers *db = acquire_dev(err);
+	DevBuffers *db = acquire_dev(err, seq);
 	if (!db) return false;
 	struct Release { AlnPipeline &P; DevBuffers *b; ~Release() { P.release_dev(b); } } release{*this, db};
 	if (text_bytes >= 0xfffffff0ull) { err = "block too large for the device stages (cut it into smaller blocks)"; return false; }

@@ -202,7 +202,14 @@ private:
 	struct DevBuffers;
 	std::vector<DevBuffers*> dev_free_, dev_all_;
 	std::mutex dev_pool_m_;
-	DevBuffers *acquire_dev(std::string &err);
+	DevBuffers *acquire_dev(std::string &err, uint64_t seq = 0);
+	// further GPUs of the same box: sub-block k goes to site k mod (1 + extra sites); each site has its own index replica
+	struct DevSite { int device; SeedService *seeds; };
+	std::vector<DevSite> sites_;          // [0] = the context's first device
+public:
+	void add_device(int device, SeedService *seeds) { sites_.push_back(DevSite{device, seeds}); }
+	size_t n_devices() const { return sites_.size(); }
+private:
 	void release_dev(DevBuffers *d);
 	// batch buffers of the host path live across blocks (staging memory is pinned once); every block in flight holds one set
 	struct HostSlot { SeedBatch seeds; KswBatchBuf ksw; };

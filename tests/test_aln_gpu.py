@@ -93,3 +93,23 @@ def test_device_stages_equal_host_stepped_stages(name, tmp_path):
     a, b = read(str(tmp_path / "cuda.0")), read(str(tmp_path / "emul.0"))
     assert len(a) > 64 and a == b
     assert st["stage_kernel_ms"] > 0 and st["seed_kernel_ms"] > 0 and st["seed_probes"] > 0
+
+
+def test_device_list_one_process_same_bytes():
+    """SURVEY.md 8e in one process: a context over several GPUs deals the sub-blocks of a block to the devices round robin; the
+    output does not depend on it (needs a box with at least two GPUs)."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("one GPU on this box")
+    need_ref_tools()
+    demo = get_demo("multi_allele")
+    os.environ["PANSVR_SUB_PAIRS"] = "101"
+    try:
+        ctx = aln.AlnContext(demo.data.index_dir, demo.data.header_sam, device=list(range(min(4, torch.cuda.device_count()))), threads=4)
+        sam, ori = ctx.align_fastq(read(demo.data.reads_fq))
+        hdr = ctx.header_text().encode()
+        ctx.close()
+    finally:
+        del os.environ["PANSVR_SUB_PAIRS"]
+    assert first_diff(hdr + sam, read(demo.ref_sam)) is None
+    assert hdr + ori == read(demo.ref_ori)

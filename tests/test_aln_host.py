@@ -77,6 +77,17 @@ def test_host_pipeline_matches_reference_sam(fc_aln_emul, name):
         pass
 
 
+def test_device_list_round_robin(fc_aln_emul):
+    """`-d 0,1,2`: the sub-blocks of a block are dealt to the devices of the list round robin, each with its own stage service
+    (on the host-stepped build the device numbers are only labels); same bytes as one device."""
+    need_ref_tools()
+    demo = get_demo("multi_allele")
+    out, ori = os.path.join(demo.wd, "dl.sam"), os.path.join(demo.wd, "dl_ori.sam")
+    fc_aln_emul(demo.data, out, ori, extra=("-S", "-d", "0,1,2"), threads=4, sub_pairs=97)
+    assert first_diff(read(out), read(demo.ref_sam)) is None
+    assert read(ori) == read(demo.ref_ori)
+
+
 def test_output_room_spill(fc_aln_emul):
     """The device path writes every sub-block's SAM text straight behind the previous one's in one output buffer; when that
     buffer is too small (forced here) the remaining text is assembled by copying -- same bytes either way."""
