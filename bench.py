@@ -12,10 +12,11 @@ value   : whole-job realigned reads/s with the FASTQ text of the rank's shard al
           (what step 0 of the reference's pipeline hands to step 1) -- every stage of the path runs, host and device.
 e2e     : the same through the plain host-buffer call: pageable FASTQ text in, malloc'ed SAM text out; h2d/d2h bytes are what
           the library copied (counted where the copies are issued).
-N > 1   : one process per GPU (torchrun); ONE input, cut into N contiguous ranges of pairs (strong scaling); no collective on
-          the data path.  The only state that flows between pairs is the reference's process-wide rand() stream: rank r hands
-          the stream state to rank r+1 through a small file when its replay is done (pansvr_aln_publish_state /
-          pansvr_aln_await_state); every rank runs all other stages of its shard without waiting.  time = max over ranks.
+N > 1   : one process per GPU (torchrun); ONE input, dealt to the ranks piece by piece (piece b of --piece-pairs pairs goes to
+          rank b mod N: strong scaling); no collective on the data path.  Every rank realigns its pieces in one
+          pansvr_aln_pieces call.  The only state that flows between pairs is the reference's process-wide rand() stream: the
+          in-order pass of piece b takes the stream state from piece b-1's through a 400-byte file in /dev/shm and hands it on the
+          moment it is done; all other stages of all pieces overlap.  time = max over ranks.
 roofline: the DP kernel (ksw_team, integer ALU: cells x 55 ops / kernel time / measured integer peak) as it runs inside the
           stage, and "roofline_seed": the seeding kernels against HBM (SURVEY.md section 8d byte model / kernel time / hbm_gbs).
 ksw_config2: the kernel-level line of BASELINE.json configs[1] (1 M x 150 bp vs 1.1 kb windows, w=100), from bench_ksw.py.
@@ -130,7 +131,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--pairs", type=int, default=5_000_000, help="read pairs of the input (config 3: 5 M pairs = 10 M reads)")
     ap.add_argument("--loci", type=int, default=5250, help="SV loci of the anchor set (config 3: 5250 loci = 10 500 anchors)")
-    ap.add_argument("--block-pairs", type=int, default=491_520, help="pairs per pansvr_aln_block call at N=1 (multiple of 4096)")
+    ap.add_argument("--block-pairs", type=int, default=0, help="pairs per pansvr_aln_block call at N=1 (multiple of 4096; 0 = the whole input in one call)")
+    ap.add_argument("--piece-pairs", type=int, default=131_072, help="N>1: pairs per piece of the block-cyclic deal (multiple of 4096)")
     ap.add_argument("--ref-sample-pairs", type=int, default=250_000, help="pairs per step of the CPU reference arm / cpu_baseline")
     ap.add_argument("--parity-pairs", type=int, default=491_520, help="prefix checked against `fc_aln -t 1` in the run (0 = off)")
     ap.add_argument("--threads", type=int, default=0, help="host helper threads per rank (0 = cores / ranks)")
@@ -169,32 +171,34 @@ def main():
             dist.init_process_group("nccl", device_id=dev)
 
     d = config3.prepare(pairs=args.pairs, loci=args.loci)
-    # ---- this rank's contiguous range of pairs, cut at multiples of IDX_STRIDE (results are merged by pair index)
+    # ---- this rank's pieces of the input, cut at multiples of IDX_STRIDE pairs (results are merged by piece index = input order)
     S = config3.IDX_STRIDE
-    units = (d.n_pairs + S - 1) // S
-    ub, ue = shard.shard_range(units, rank, world)
-    pb, pe = ub * S, min(ue * S, d.n_pairs)
-    b0, b1 = d.byte_range(pb, pe)
-    nbytes = b1 - b0
+    if world == 1:
+        bp = max(S, args.block_pairs // S * S) if args.block_pairs > 0 else d.n_pairs
+        cuts = list(range(0, d.n_pairs, bp)) + [d.n_pairs]
+        mine = list(range(len(cuts) - 1))
+    else:
+        pp = max(S, args.piece_pairs // S * S)
+        cuts = list(range(0, d.n_pairs, pp)) + [d.n_pairs]
+        mine = [b for b in range(len(cuts) - 1) if b % world == rank]
+    n_pieces_total = len(cuts) - 1
+    spans = [d.byte_range(cuts[b], cuts[b + 1]) for b in mine]
+    nbytes = sum(e - b for b, e in spans)
+    my_pairs = sum(cuts[b + 1] - cuts[b] for b in mine)
     pin = ksw.PinnedArray((max(nbytes, 1),), np.uint8) if not emul else argparse.Namespace(array=np.empty(max(nbytes, 1), np.uint8))
+    offs = []
     with open(d.reads_fq, "rb") as f:
-        f.seek(b0)
-        got = f.readinto(memoryview(pin.array)[:nbytes]) if nbytes else 0
-    assert got == nbytes
+        at = 0
+        for b0, b1 in spans:
+            f.seek(b0)
+            got = f.readinto(memoryview(pin.array)[at:at + (b1 - b0)])
+            assert got == b1 - b0
+            offs.append((at, b1 - b0))
+            at += b1 - b0
     pageable = bytes(memoryview(pin.array)[:nbytes])                     # the e2e leg's input: ordinary host memory
     with open(d.reads_fq, "rb") as f:
         head = f.read(4096)                                              # first record of the input (STAT_ fields, RR:134-148)
-    # calls of one step: at N=1 blocks of --block-pairs (the first one doubles as the parity prefix); a rank of an N>1 run hands
-    # its whole shard over in one call so that nothing of it waits for the upstream rank's stream state but the in-order passes
-    if world == 1:
-        bp = max(S, args.block_pairs // S * S)
-        cuts = list(range(pb, pe, bp)) + [pe]
-    else:
-        cuts = [pb, pe]
-    calls = []
-    for c0, c1 in zip(cuts[:-1], cuts[1:]):
-        o0, o1 = d.byte_range(c0, c1)
-        calls.append((o0 - b0, o1 - o0, c1 - c0))
+    parity_pairs = min(args.parity_pairs // S * S, cuts[1]) if args.parity_pairs > 0 else 0
     threads = args.threads or max(1, min(48, (os.cpu_count() or 1) // world))
     ctx = aln.AlnContext(d.index_dir, d.header_sam, device=local, threads=threads, lib=emul_lib)
     ctx.prime_read_stats(head)
@@ -213,25 +217,30 @@ def main():
         if not emul:
             torch.cuda.synchronize()
 
-    def one_step(kind, keep_first=False):
-        """One pass over this rank's shard.  Returns (stats, md5 of the first call's output or None)."""
+    def one_step(kind, prefix_pairs=0):
+        """One pass over this rank's pieces (prefix_pairs: only the first pairs of the input, on rank 0 -- the parity check).
+        Returns (stats, (md5 sam, md5 ori, bytes, bytes) of the output when prefix_pairs)."""
         k = step_no[0]; step_no[0] += 1
         ctx.reset()
         ctx.prime_read_stats(head)
-        if world > 1 and rank > 0:
-            ctx.await_state(os.path.join(state_dir, f"s{k}_r{rank}"))
+        base = pin.array.ctypes.data if kind == "resident" else C.cast(C.c_char_p(pageable), C.c_void_p).value
         first = None
-        base = pin.array.ctypes.data
-        for i, (off, n, _) in enumerate(calls):
-            if kind == "resident":
-                sam, ori, release = ctx.align_ptr(base + off, n)
-            else:
-                (sam, ori, release) = ctx.align_bytes_at(pageable, off, n)
-            if keep_first and i == 0:
+        if prefix_pairs:
+            if rank == 0:
+                o0, o1 = d.byte_range(0, prefix_pairs)
+                sam, ori, release = ctx.align_ptr(base, o1 - o0)
                 first = (md5_of(header, *sam), md5_of(header, *ori), sam[1], ori[1])
+                release()
+            return ctx.stats(), first
+        if world == 1:
+            for off, n in offs:
+                sam, ori, release = ctx.align_ptr(base + off, n)
+                release()
+        elif mine:
+            pieces = [(base + off, n, os.path.join(state_dir, f"s{k}_b{b}") if b > 0 else None,
+                       os.path.join(state_dir, f"s{k}_b{b + 1}") if b + 1 < n_pieces_total else None) for b, (off, n) in zip(mine, offs)]
+            sam, ori, _, release = ctx.align_pieces(pieces)
             release()
-        if world > 1 and rank + 1 < world:
-            ctx.publish_state(os.path.join(state_dir, f"s{k}_r{rank + 1}"))
         return ctx.stats(), first
 
     def timed(kind, k_steps):
@@ -269,10 +278,10 @@ def main():
 
     # ---- parity in the run: the first call's output against `panSVR fc_aln -t 1 -S -R <pairs>` (md5 of both files)
     parity = None
-    if args.parity_pairs > 0:
-        _, first = one_step("resident", keep_first=(rank == 0))           # (every rank: the state files are per step)
+    if parity_pairs > 0:
+        _, first = one_step("resident", prefix_pairs=parity_pairs)
         if rank == 0 and os.access(os.path.join(config3.REF_BIN, "panSVR"), os.X_OK):
-            pp = calls[0][2]
+            pp = parity_pairs
             ref = reference_t1_md5(d, pp)
             parity = {"pairs": pp, "sam_md5_equal": first[0] == ref["sam"], "ori_md5_equal": first[1] == ref["ori"],
                       "sam_bytes": first[2], "ori_bytes": first[3], "reference": f"oracle/_ref/panSVR fc_aln -t 1 -S -R {pp}",
@@ -286,7 +295,8 @@ def main():
     barrier()
 
     # ---- gather the per-rank device counters (sums) on rank 0
-    keys = ("reads", "mems", "ksw_tasks", "ksw_cells", "kernel_launches", "h2d_bytes", "d2h_bytes", "seed_probes")
+    keys = ("reads", "mems", "ksw_tasks", "ksw_cells", "kernel_launches", "h2d_bytes", "d2h_bytes", "seed_probes",
+            "in_order_seconds", "in_order_pairs", "in_order_draws", "host_pairs")
     vec = [float(st[k]) for k in keys] + [float(e_st[k]) for k in keys]
     mx = [st["seed_kernel_ms"], st["ksw_kernel_ms"], st["stage_kernel_ms"]] + list(st["stage_seconds"])
     pmx = [pst["seed_kernel_ms"], pst["ksw_kernel_ms"], pst["stage_kernel_ms"], float(pst["ksw_cells"]), float(pst["seed_probes"]), float(pst["mems"])] + list(pst["stage_kernel_ms_by"])
@@ -339,11 +349,11 @@ def main():
         "ms_per_step": ev_ms / args.steps, "higher_is_better": True, "scaling": "strong" if world > 1 else "weak", "vs_baseline": None,
         "dtype": "u16x2 (exact int8 emulation) / int32 H in the DP kernel; uint64 2-bit words in seeding", "data": "synthetic",
         "gcups": cells_s / 1e9,
-        "config": {"workload": workload_name(d), "reads_per_step": n_reads, "pairs_per_rank": pe - pb, "calls_per_step_per_rank": len(calls),
+        "config": {"workload": workload_name(d), "reads_per_step": n_reads, "pairs_per_rank": my_pairs, "calls_per_step_per_rank": len(offs) if world == 1 else 1, "pieces": n_pieces_total,
                    "host_threads_per_rank": threads, "host_cores": os.cpu_count(),
                    "l2": "inputs exceed L2: every call streams hundreds of MB of packed reads, MEMs, ksw tasks and traceback (no reuse between steps)",
-                   "parallelism": (f"one input cut into {world} contiguous pair ranges, one process per GPU, no collective on the data path; "
-                                   "rand() stream state handed from rank to rank through a file") if world > 1 else "1 GPU",
+                   "parallelism": (f"one input dealt to {world} processes (one per GPU) in {n_pieces_total} pieces of {cuts[1] - cuts[0]} pairs, round robin; no collective "
+                                   "on the data path; the rand() stream state goes from piece to piece through files in /dev/shm") if world > 1 else "1 GPU",
                    "timing": "CUDA events on the rank's current stream around the K steps after a barrier + synchronize, max over ranks (wall clock agrees: see wall_ms_per_step)"},
         "e2e": {"value": e_reads_s, "unit": "reads/s", "h2d_bytes_per_step": int(e_tot["h2d_bytes"] / args.steps),
                 "d2h_bytes_per_step": int(e_tot["d2h_bytes"] / args.steps), "ms_per_step": e_ev_ms / args.steps,
@@ -370,6 +380,10 @@ def main():
                                     "note": "summed CUDA-event times of the timed passes; kernels of the sub-blocks in flight overlap, so these exceed the busy time"},
         "kernel_ms_alone_per_step": {"seeding": p_seed_ms, "ksw": p_ksw_ms,
                                      **dict(zip(("records_ori_encode", "seeding_", "merge_chain", "ksw_plan", "resolve", "cell_count", "pair_probe_finalize", "sam_text"), pmx[6:14]))},
+        "in_order_chain": {"seconds_per_step": tot["in_order_seconds"] / args.steps, "pairs_with_draws_per_step": tot["in_order_pairs"] / args.steps,
+                           "draws_per_step": tot["in_order_draws"] / args.steps, "host_path_pairs_per_step": tot["host_pairs"] / args.steps,
+                           "note": "the in-order passes over the reference's rand() stream, summed over all ranks: the one part of the stage that is sequential "
+                                   "from pair to pair (one piece after the other, across ranks); everything else overlaps -- the lower bound of a step at any N"},
         "parity": parity,
     }
     if emul:

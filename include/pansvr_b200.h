@@ -165,6 +165,11 @@ typedef struct {
 	double seed_kernel_ms, ksw_kernel_ms, stage_kernel_ms;   /* CUDA-event time of the seeding / ksw / other stage kernels */
 	double stage_kernel_ms_by[8];   /* the stage kernels by group: 0 records + original alignments + encode/census, 1 seeding, 2 merge + chain,
 	                                   3 ksw planning, 4 candidate resolution, 5 cell count, 6 pairing probe + finalize, 7 SAM text */
+	/* the in-order passes (the only part of a block that waits for the block before it: the reference's rand() stream) */
+	double in_order_seconds;    /* time inside the in-order sections, waiting for the turn not included */
+	int64_t in_order_pairs;     /* pairs that drew at least one random number */
+	int64_t in_order_draws;     /* rand() calls replayed */
+	int64_t host_pairs;         /* pairs the device path handed to the host path ('N', random_r sampling, ties that change the outcome) */
 } pansvr_aln_stats_t;
 
 typedef struct pansvr_aln_ctx pansvr_aln_ctx;
@@ -208,6 +213,18 @@ void pansvr_free(void *p);
  * writes the state after the context's last in-order pass (atomically: readers never see a partial file).  No collective, no
  * device traffic between processes. */
 int  pansvr_aln_prime_read_stats(pansvr_aln_ctx *ctx, const char *fastq_head, size_t bytes);
+/* Block-cyclic form of the same, for one input dealt to N processes piece by piece (piece b goes to process b mod N): one call
+ * realigns all pieces this process owns, a few sub-blocks in flight across piece boundaries.  A piece's first in-order pass waits
+ * for `await_path` (NULL: none -- the first piece of the input) and its last one writes `publish_path` (NULL: none) the moment it
+ * is done, before the piece's remaining stages: the in-order passes of consecutive pieces follow each other through the files while
+ * everything else of every piece overlaps.  *sam / *ori: the texts of the pieces one behind the other; sam_bytes / ori_bytes of
+ * each piece = its share.  (pansvr_aln_block = one piece without files.) */
+typedef struct {
+	const char *fastq; size_t fastq_bytes;
+	const char *await_path, *publish_path;
+	size_t sam_bytes, ori_bytes;                /* out */
+} pansvr_aln_piece_t;
+int  pansvr_aln_pieces(pansvr_aln_ctx *ctx, pansvr_aln_piece_t *pieces, int n_pieces, char **sam, size_t *sam_bytes, char **ori, size_t *ori_bytes);
 int  pansvr_aln_await_state(pansvr_aln_ctx *ctx, const char *path);
 int  pansvr_aln_publish_state(pansvr_aln_ctx *ctx, const char *path);
 /* Same command line as `panSVR fc_aln` (classify_main, src/main.cpp:18-25): [options] <IndexDir> <reads.fq|-> <header.sam>.

@@ -18,12 +18,18 @@ class AlnOptionsC(C.Structure):
                                          "not_ori", "max_use_read", "threads", "explicit_mask")]
 
 
+class AlnPieceC(C.Structure):
+    _fields_ = [("fastq", C.c_void_p), ("fastq_bytes", C.c_size_t), ("await_path", C.c_char_p), ("publish_path", C.c_char_p),
+                ("sam_bytes", C.c_size_t), ("ori_bytes", C.c_size_t)]
+
+
 class AlnStatsC(C.Structure):
     _fields_ = [("reads", C.c_int64), ("mems", C.c_int64), ("ksw_tasks", C.c_int64), ("ksw_cells", C.c_int64),
                 ("deferred_pairs", C.c_int64), ("stage_seconds", C.c_double * 8),
                 ("kernel_launches", C.c_int64), ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64), ("seed_probes", C.c_int64),
                 ("seed_kernel_ms", C.c_double), ("ksw_kernel_ms", C.c_double), ("stage_kernel_ms", C.c_double),
-                ("stage_kernel_ms_by", C.c_double * 8)]
+                ("stage_kernel_ms_by", C.c_double * 8),
+                ("in_order_seconds", C.c_double), ("in_order_pairs", C.c_int64), ("in_order_draws", C.c_int64), ("host_pairs", C.c_int64)]
 
 
 def _bind(lib):
@@ -46,6 +52,8 @@ def _bind(lib):
     lib.pansvr_aln_prime_read_stats.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t]
     lib.pansvr_aln_await_state.argtypes = [C.c_void_p, C.c_char_p]
     lib.pansvr_aln_publish_state.argtypes = [C.c_void_p, C.c_char_p]
+    lib.pansvr_aln_pieces.argtypes = [C.c_void_p, C.POINTER(AlnPieceC), C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t),
+                                      C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
     return lib
 
 
@@ -110,6 +118,24 @@ class AlnContext:
         base = C.cast(C.c_char_p(fastq), C.c_void_p).value
         return self.align_ptr(base + offset, nbytes)
 
+    def align_pieces(self, pieces):
+        """pansvr_aln_pieces: pieces = [(addr, nbytes, await_path or None, publish_path or None), ...] of one input, in input order.
+        Returns ((sam_addr, sam_bytes), (ori_addr, ori_bytes), [(sam_bytes, ori_bytes) per piece], release)."""
+        arr = (AlnPieceC * len(pieces))()
+        for a, (addr, n, aw, pb) in zip(arr, pieces):
+            a.fastq = addr; a.fastq_bytes = n
+            a.await_path = aw.encode() if aw else None
+            a.publish_path = pb.encode() if pb else None
+        s, o = C.c_void_p(), C.c_void_p()
+        sl, ol = C.c_size_t(), C.c_size_t()
+        rc = self.lib.pansvr_aln_pieces(self.h, arr, len(pieces), C.byref(s), C.byref(sl), C.byref(o), C.byref(ol))
+        if rc != 0:
+            raise RuntimeError(f"pansvr_aln_pieces failed ({rc}): {self.lib.pansvr_aln_last_error().decode()}")
+
+        def release():
+            self.lib.pansvr_free(s); self.lib.pansvr_free(o)
+        return (s.value, sl.value), (o.value, ol.value), [(a.sam_bytes, a.ori_bytes) for a in arr], release
+
     def prime_read_stats(self, fastq_head: bytes) -> None:
         """Show the context the first record of the whole input (STAT_ fields); needed when its own blocks start later in the input."""
         if self.lib.pansvr_aln_prime_read_stats(self.h, fastq_head, len(fastq_head)) != 0:
@@ -155,7 +181,8 @@ class AlnContext:
         st = AlnStatsC()
         self.lib.pansvr_aln_last_stats(self.h, C.byref(st))
         d = {k: getattr(st, k) for k in ("reads", "mems", "ksw_tasks", "ksw_cells", "deferred_pairs", "kernel_launches", "h2d_bytes",
-                                         "d2h_bytes", "seed_probes", "seed_kernel_ms", "ksw_kernel_ms", "stage_kernel_ms")}
+                                         "d2h_bytes", "seed_probes", "seed_kernel_ms", "ksw_kernel_ms", "stage_kernel_ms",
+                                         "in_order_seconds", "in_order_pairs", "in_order_draws", "host_pairs")}
         d["stage_seconds"] = list(st.stage_seconds)
         d["stage_kernel_ms_by"] = list(st.stage_kernel_ms_by)
         return d

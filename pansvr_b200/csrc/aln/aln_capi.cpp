@@ -312,126 +312,207 @@ void add_parts(std::vector<Part> &parts, const char *p, size_t n)
 	}
 }
 
-// Where the sub-blocks of a text start, without parsing it: strict 4-line FASTQ (what fc_signal writes) has 8 lines per pair, so the
-// helper threads count the line ends of their slices and the cuts are the line ends whose number is a multiple of 8 * per.
-// false = the text is not of that form (no final newline, a line count that is not a multiple of 8): the host parser decides.
-bool cut_text(const char *p, size_t n, AlnPipeline &pipe, int threads, size_t &n_pairs, size_t &per, std::vector<size_t> &cuts)
+// One piece of an input handed to a block call: whole pairs as 4-line FASTQ text.  await / publish: files through which the
+// reference's random streams are handed from the piece before it (realigned by another process) and to the piece after it.
+struct Piece { const char *p = nullptr; size_t n = 0; const char *await_path = nullptr, *publish_path = nullptr; size_t sam_bytes = 0, ori_bytes = 0; };
+
+size_t count_line_ends(const char *b, const char *e)
 {
-	if (n == 0 || p[n - 1] != '\n') return false;
-	const size_t T = (size_t)std::max(1, threads), slice = (n + T - 1) / T;
-	std::vector<size_t> nl(T + 1, 0);
-	pipe.parallel(T, [&](size_t b, size_t e, int) {
-		for (size_t t = b; t < e; ++t) {
-			const size_t s0 = std::min(n, slice * t), s1 = std::min(n, slice * (t + 1));
-			size_t c = 0;
-			for (const char *q = p + s0, *qe = p + s1; (q = (const char*)memchr(q, '\n', (size_t)(qe - q))) != nullptr; ++q) ++c;
-			nl[t + 1] = c;
+	size_t c = 0;
+	for (const char *q = b; (q = (const char*)memchr(q, '\n', (size_t)(e - q))) != nullptr; ++q) ++c;
+	return c;
+}
+
+// Position just behind line end number `want` counted from `at`, found on all helper threads by counting the line ends of slices of
+// a window that probably holds it (`guess` bytes); lines = `want`, or how many line ends there were if the text ends first (then n
+// is returned).  Strict 4-line FASTQ (what fc_signal writes) has 8 lines per pair, so this is where a run of pairs ends without
+// looking at the records.
+size_t line_end_after(const char *p, size_t n, size_t at, size_t want, size_t guess, AlnPipeline &pipe, int threads, size_t &lines)
+{
+	lines = 0;
+	const size_t T = (size_t)std::max(1, threads);
+	std::vector<size_t> nl(T + 1);
+	while (at < n) {
+		const size_t win = std::min(n - at, std::max<size_t>(guess, (size_t)1 << 16)), slice = (win + T - 1) / T;
+		std::fill(nl.begin(), nl.end(), 0);
+		pipe.parallel(T, [&](size_t b, size_t e, int) {
+			for (size_t t = b; t < e; ++t) nl[t + 1] = count_line_ends(p + at + std::min(win, slice * t), p + at + std::min(win, slice * (t + 1)));
+		}, 2);
+		for (size_t t = 0; t < T; ++t) nl[t + 1] += nl[t];
+		if (lines + nl[T] < want) {                                // not in this window: go on behind it
+			lines += nl[T]; at += win;
+			guess = std::max<size_t>(guess / 8, (size_t)1 << 20);
+			continue;
 		}
-	}, 2);
-	for (size_t t = 0; t < T; ++t) nl[t + 1] += nl[t];
-	if (nl[T] % 8 != 0) return false;
-	n_pairs = nl[T] / 8;
-	per = n_pairs;
+		const size_t need = want - lines;
+		size_t t = 0;
+		while (nl[t + 1] < need) ++t;
+		size_t seen = nl[t];
+		const char *q = p + at + std::min(win, slice * t);
+		for (;;) { q = (const char*)memchr(q, '\n', (size_t)(p + n - q)); ++seen; ++q; if (seen == need) break; }
+		lines = want;
+		return (size_t)(q - p);
+	}
+	return n;
+}
+
+size_t pairs_per_sub_block(size_t n_pairs, int threads)
+{
+	size_t per = std::max<size_t>(n_pairs, 1);
 	if (threads > 1 && n_pairs >= 65536) per = std::min<size_t>(262144, std::max<size_t>(32768, (n_pairs + 3) / 4));
 	if (const char *e = getenv("PANSVR_SUB_PAIRS")) { const long v = atol(e); if (v > 0) per = (size_t)v; }   // tests: force the cut
-	const size_t n_sub = n_pairs ? (n_pairs + per - 1) / per : 1;
-	cuts.assign(n_sub + 1, n);
-	cuts[0] = 0;
-	for (size_t k = 1; k < n_sub; ++k) {
-		const size_t want = 8 * per * k;                           // the cut is right after line end number `want` (1-based)
-		size_t t = 0;
-		while (nl[t + 1] < want) ++t;
-		size_t seen = nl[t];
-		const char *q = p + std::min(n, slice * t);
-		for (;;) { q = (const char*)memchr(q, '\n', (size_t)(p + n - q)); ++seen; ++q; if (seen == want) break; }
-		cuts[k] = (size_t)(q - p);
-	}
-	return true;
+	return per;
 }
 
 // `room`: a buffer the sub-blocks' SAM text goes into directly, one behind the other in input order (device path); *room_used =
 // how much of it was filled.  A sub-block whose text does not fit keeps it in its own buffer (and so do all later ones).
 struct TextRoom { char *p = nullptr; size_t cap = 0, used = 0; size_t next = 0; bool full = false; std::mutex m; std::condition_variable cv; };
 
-int run_block(pansvr_aln_ctx *c, const char *fastq, size_t n, std::vector<Part> &sam, std::vector<Part> &ori,
-              const std::function<void(const BlockOutput&)> *on_done = nullptr, TextRoom *room = nullptr)
+// The pieces of a call, cut into sub-blocks that go through the pipeline a few at a time.  On the device path the text goes up as
+// it is and the records are found there, so the host only has to know where to cut: sub-block after sub-block, just before each
+// one is started (the first one is on its way after a look at a few MB, not after a pass over the whole text).
+int run_block(pansvr_aln_ctx *c, Piece *pieces, size_t n_pieces, std::vector<Part> &sam, std::vector<Part> &ori,
+              const std::function<void(const BlockOutput&, size_t)> *on_done = nullptr, TextRoom *room = nullptr)
 {
 	const auto tick = []() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
-	const double t0 = tick();
-	std::vector<FastqRec> recs;
-	size_t n_pairs = 0, per = 0;
-	std::vector<size_t> cuts;
-	// device path: the text goes up as it is and the records are found there; the host only needs to know where to cut
-	bool as_text = c->pipe->has_device_stages() && cut_text(fastq, n, *c->pipe, c->opt.threads, n_pairs, per, cuts);
-	if (as_text) {
-		std::vector<FastqRec> first;
-		const char *q = fastq; int lines = 0;
-		while (lines < 4 && q < fastq + n) { q = (const char*)memchr(q, '\n', (size_t)(fastq + n - q)); if (!q) break; ++q; ++lines; }
-		if (lines == 4) parse_fastq(fastq, (size_t)(q - fastq), first);
-		if (first.empty()) as_text = false; else c->pipe->ensure_read_stats(first[0]);
-	}
-	if (!as_text) {
-		if (!parse_fastq_parallel(fastq, n, *c->pipe, c->opt.threads, recs)) parse_fastq(fastq, n, recs);
-		n_pairs = recs.size() / 2;
-		per = n_pairs;                                            // pairs per sub-block
-		if (c->opt.threads > 1 && n_pairs >= 65536) per = std::min<size_t>(262144, std::max<size_t>(32768, (n_pairs + 3) / 4));
-		if (const char *e = getenv("PANSVR_SUB_PAIRS")) { const long v = atol(e); if (v > 0) per = (size_t)v; }   // tests: force the cut
+	const int threads = c->opt.threads;
+	struct Sub {
+		size_t piece = 0; const char *p = nullptr; size_t n = 0, pairs = 0; bool as_text = false;
+		const FastqRec *recs = nullptr;                             // host-parsed piece: this sub-block's records
+		uint64_t seq = 0; std::thread th; std::string err; uint8_t ok = 1;
+	};
+	std::deque<Sub> subs;
+	std::deque<std::vector<FastqRec>> parsed;                       // records of the pieces the host parser took
+	bool chained = false;
+	for (size_t i = 0; i < n_pieces; ++i) { pieces[i].sam_bytes = pieces[i].ori_bytes = 0; chained |= pieces[i].await_path || pieces[i].publish_path; }
+	// ---- the cutter: next_sub() describes the next sub-block, in input order
+	size_t pi = 0, at = 0, per = 0, rec_at = 0, guess = 0;
+	bool open = false, text_mode = false, piece_first = true;
+	const std::vector<FastqRec> *cur_recs = nullptr;
+	auto open_host = [&](const Piece &P) {
+		text_mode = false;
+		parsed.emplace_back();
+		std::vector<FastqRec> &recs = parsed.back();
+		if (!parse_fastq_parallel(P.p, P.n, *c->pipe, threads, recs)) parse_fastq(P.p, P.n, recs);
+		cur_recs = &recs; rec_at = 0;
+		per = pairs_per_sub_block(recs.size() / 2, threads);
+		if (chained && recs.size() / 2 <= 262144 && !getenv("PANSVR_SUB_PAIRS")) per = std::max<size_t>(recs.size() / 2, 1);   // pieces of a dealt input are the caller's sub-blocks
 		if (!recs.empty()) c->pipe->ensure_read_stats(recs[0]);
-	}
-	c->pipe->stats.t_stage[6] += tick() - t0;
-	const size_t n_sub = n_pairs ? (n_pairs + per - 1) / per : 1;
-	if (c->outs.size() < n_sub) c->outs.resize(n_sub);
-	std::vector<std::string> errs(n_sub);
-	std::vector<uint8_t> ok(n_sub, 1);
-	std::vector<uint64_t> seqs(n_sub);
-	for (size_t k = 0; k < n_sub; ++k) seqs[k] = c->pipe->next_seq();
-	auto run_sub = [&](size_t k) {
-		const size_t pb = std::min(n_pairs, per * k), pe = std::min(n_pairs, per * (k + 1));
-		BlockOutput &bo = c->outs[k];
+	};
+	auto open_piece = [&]() {
+		const Piece &P = pieces[pi];
+		open = true; at = 0; piece_first = true;
+		text_mode = c->pipe->has_device_stages() && P.n > 0 && P.p[P.n - 1] == '\n';
+		if (text_mode) {
+			const size_t head = std::min(P.n, (size_t)4 << 20);
+			const size_t lines = count_line_ends(P.p, P.p + head);
+			std::vector<FastqRec> first;
+			const char *q = P.p; int l4 = 0;
+			while (l4 < 4 && q < P.p + P.n) { q = (const char*)memchr(q, '\n', (size_t)(P.p + P.n - q)); if (!q) break; ++q; ++l4; }
+			if (l4 == 4) parse_fastq(P.p, (size_t)(q - P.p), first);
+			if (first.empty() || lines < 8) text_mode = false;
+			else {
+				c->pipe->ensure_read_stats(first[0]);
+				const double bytes_per_pair = 8.0 * (double)head / (double)lines;
+				const size_t est_pairs = (size_t)((double)P.n / bytes_per_pair);
+				per = pairs_per_sub_block(est_pairs, threads);
+				if ((per >= est_pairs || (chained && est_pairs <= 262144)) && !getenv("PANSVR_SUB_PAIRS")) per = (size_t)-1 / 16;   // one sub-block, however far the estimate is off
+				guess = per < (size_t)1 << 40 ? (size_t)((double)per * bytes_per_pair * 1.02) + 4096 : P.n;
+			}
+		}
+		if (!text_mode) open_host(P);
+	};
+	auto next_sub = [&](Sub &S) -> bool {
+		for (;;) {
+			if (!open) { if (pi >= n_pieces) return false; open_piece(); }
+			const Piece &P = pieces[pi];
+			S.piece = pi;
+			if (text_mode) {
+				if (at < P.n) {
+					size_t lines = 0;
+					const size_t e = line_end_after(P.p, P.n, at, 8 * per, guess, *c->pipe, threads, lines);
+					if (lines % 8 != 0 && at == 0) { open_host(P); continue; }      // not whole pairs of 4-line records: the host parser decides
+					S.p = P.p + at; S.n = e - at; S.pairs = lines / 8; S.as_text = lines % 8 == 0; S.recs = nullptr;
+					if (!S.as_text) {                                               // (an odd tail behind sub-blocks already on their way)
+						parsed.emplace_back();
+						parse_fastq(S.p, S.n, parsed.back());
+						S.recs = parsed.back().data(); S.pairs = parsed.back().size() / 2;
+					}
+					at = e; piece_first = false;
+					return true;
+				}
+			} else {
+				const size_t n_pairs = cur_recs->size() / 2;
+				if (rec_at < n_pairs || piece_first) {
+					const size_t pe = std::min(n_pairs, rec_at + per);
+					S.p = nullptr; S.n = 0; S.as_text = false; S.recs = cur_recs->data() + 2 * rec_at; S.pairs = pe - rec_at;
+					rec_at = pe; piece_first = false;
+					return true;
+				}
+			}
+			open = false; ++pi;
+		}
+	};
+	// on_done: the caller takes every sub-block's output as soon as it and all earlier ones are finished, while later ones still run
+	size_t handed = 0;
+	auto hand_over = [&](size_t upto) { if (on_done) for (; handed < upto; ++handed) if (subs[handed].ok) (*on_done)(c->outs[handed], subs[handed].piece); };
+	auto run_sub = [&](Sub *sp, BlockOutput *bop, size_t k) {          // (pointers: the deques grow while sub-blocks run)
+		Sub &S = *sp;
+		BlockOutput &bo = *bop;
 		bo.place = nullptr;
 		if (room) bo.place = [room, k](size_t total) -> char* {      // sub-block k's text goes behind that of 0 .. k-1
 			std::unique_lock<std::mutex> lk(room->m);
 			room->cv.wait(lk, [&]() { return room->next == k; });
-			char *at = nullptr;
-			if (!room->full && room->used + total + 1 <= room->cap) { at = room->p + room->used; room->used += total; }
+			char *at2 = nullptr;
+			if (!room->full && room->used + total + 1 <= room->cap) { at2 = room->p + room->used; room->used += total; }
 			else if (total) room->full = true;
 			room->next = k + 1;
 			lk.unlock();
 			room->cv.notify_all();
-			return at;
+			return at2;
 		};
 		struct Always { BlockOutput &b; ~Always() { if (b.place && !b.place_called) b.place(0); b.place = nullptr; } } always{bo};
-		if (as_text) {
+		if (S.as_text) {
 			bool reparse = false;
-			ok[k] = c->pipe->align_block_text(fastq + cuts[k], cuts[k + 1] - cuts[k], pe - pb, c->outs[k], errs[k], seqs[k], &reparse) ? 1 : 0;
-			if (!ok[k] || !reparse) return;
+			S.ok = c->pipe->align_block_text(S.p, S.n, S.pairs, bo, S.err, S.seq, &reparse) ? 1 : 0;
+			if (!S.ok || !reparse) return;
 			std::vector<FastqRec> mine;                             // not what it looked like (a header line without '@', ...): the host parser's records
-			parse_fastq(fastq + cuts[k], cuts[k + 1] - cuts[k], mine);
-			ok[k] = c->pipe->align_block(mine.data(), mine.size(), c->outs[k], errs[k], seqs[k]) ? 1 : 0;
+			parse_fastq(S.p, S.n, mine);
+			S.ok = c->pipe->align_block(mine.data(), mine.size(), bo, S.err, S.seq) ? 1 : 0;
 			return;
 		}
-		ok[k] = c->pipe->align_block(recs.data() + 2 * pb, 2 * (pe - pb), c->outs[k], errs[k], seqs[k]) ? 1 : 0;
+		S.ok = c->pipe->align_block(S.recs, 2 * S.pairs, bo, S.err, S.seq) ? 1 : 0;
 	};
-	// on_done: the caller takes every sub-block's output as soon as it and all earlier ones are finished, while later ones still run
-	size_t handed = 0;
-	auto hand_over = [&](size_t upto) { if (on_done) for (; handed < upto; ++handed) if (ok[handed]) (*on_done)(c->outs[handed]); };
-	if (n_sub == 1) run_sub(0);
-	else {
-		// a few in flight (their device trips and host passes overlap); all of them while the context waits for another process's
-		// stream state (pansvr_aln_await_state), so that only the in-order passes wait and every other stage of the shard is done by
-		// the time the state arrives
-		size_t flight = c->pipe->has_device_stages() ? 5 * c->pipe->n_devices() : 2;
-		if (const char *e = getenv("PANSVR_FLIGHT")) { const long v = atol(e); if (v > 0) flight = (size_t)v; }
-		if (c->pipe->awaiting_streams()) flight = n_sub;
-		std::vector<std::thread> th(n_sub);
-		for (size_t k = 0; k < n_sub; ++k) {
-			if (k >= flight) { th[k - flight].join(); }
-			th[k] = std::thread(run_sub, k);
-			if (k >= flight) hand_over(k - flight + 1);
-		}
-		for (size_t k = n_sub >= flight ? n_sub - flight : 0; k < n_sub; ++k) { th[k].join(); hand_over(k + 1); }
+	// a few in flight (their device trips and host passes overlap); all of them while the context waits for another process's
+	// stream state (pansvr_aln_await_state), so that only the in-order passes wait and every other stage of the shard is done by
+	// the time the state arrives
+	size_t flight = c->pipe->has_device_stages() ? (chained ? 8 : 5) * c->pipe->n_devices() : 2;
+	if (const char *e = getenv("PANSVR_FLIGHT")) { const long v = atol(e); if (v > 0) flight = (size_t)v; }
+	if (c->pipe->awaiting_streams()) flight = (size_t)-1;
+	double t_cut = 0;
+	for (size_t k = 0;; ++k) {
+		const double t0 = tick();
+		Sub next;
+		const bool more = next_sub(next);
+		t_cut += tick() - t0;
+		if (!more) break;
+		if (k >= flight) { subs[k - flight].th.join(); hand_over(k - flight + 1); }
+		subs.emplace_back(std::move(next));
+		Sub &S = subs.back();
+		S.seq = c->pipe->next_seq();
+		const Piece &P = pieces[S.piece];
+		const bool first_of_piece = k == 0 || subs[k - 1].piece != S.piece;
+		// (the last sub-block of a piece is the one after which the cutter moves on: at == P.n in text mode, rec_at == all in host mode)
+		const bool last_of_piece = text_mode ? at >= P.n : rec_at >= cur_recs->size() / 2;
+		if ((first_of_piece && P.await_path) || (last_of_piece && P.publish_path))
+			c->pipe->chain_at(S.seq, first_of_piece ? P.await_path : nullptr, last_of_piece ? P.publish_path : nullptr);
+		if (c->outs.size() <= k) c->outs.emplace_back();
+		S.th = std::thread(run_sub, &S, &c->outs[k], k);
 	}
-	for (size_t k = 0; k < n_sub; ++k) if (!ok[k]) { g_aln_err = errs[k]; return PANSVR_E_CUDA; }
+	c->pipe->stats.t_stage[6] += t_cut;
+	const size_t n_sub = subs.size();
+	for (size_t k = 0; k < n_sub; ++k) if (subs[k].th.joinable()) { subs[k].th.join(); hand_over(k + 1); }
+	for (size_t k = 0; k < n_sub; ++k) if (!subs[k].ok) { g_aln_err = subs[k].err; return PANSVR_E_CUDA; }
 	hand_over(n_sub);
 	sam.clear(); ori.clear();
 	if (on_done) return 0;
@@ -458,10 +539,12 @@ struct CallReport {                                           // PANSVR_TIMING=1
 
 } // namespace
 
-int pansvr_aln_block(pansvr_aln_ctx *c, const char *fastq, size_t n, char **sam, size_t *sam_bytes, char **ori, size_t *ori_bytes)
+namespace {
+int block_of_pieces(pansvr_aln_ctx *c, Piece *pieces, size_t n_pieces, char **sam, size_t *sam_bytes, char **ori, size_t *ori_bytes)
 {
-	if (!c || !fastq || !sam || !ori) return PANSVR_E_ARG;
 	CallReport report(c);
+	size_t n = 0;
+	for (size_t i = 0; i < n_pieces; ++i) n += pieces[i].n;
 	// The output text is assembled while the block is still being aligned: every finished sub-block is copied to its place behind the
 	// earlier ones.  Room for 2.5 x the input (a record grows by its fixed fields and tags) is only address space until it is written;
 	// it grows if that should not be enough.
@@ -479,7 +562,7 @@ int pansvr_aln_block(pansvr_aln_ctx *c, const char *fastq, size_t n, char **sam,
 	bool spilled = false;                                         // some text did not go into the room (did not fit)
 	size_t placed_prefix = 0;                                     // text of the sub-blocks handed over so far that sits in the room, contiguous from its start
 	double t_join = 0;
-	const std::function<void(const BlockOutput&)> take = [&](const BlockOutput &o) {
+	const std::function<void(const BlockOutput&, size_t)> take = [&](const BlockOutput &o, size_t piece) {
 		const double t0 = CallReport::now();
 		std::vector<Part> ps, po;
 		if (room.p && !o.placed && !spilled) {
@@ -505,11 +588,14 @@ int pansvr_aln_block(pansvr_aln_ctx *c, const char *fastq, size_t n, char **sam,
 			c->pipe->parallel(parts.size(), [&](size_t b, size_t e, int) { for (size_t i = b; i < e; ++i) memcpy(g.p + off[i], parts[i].p, parts[i].n); }, 2);
 			g.used += tot;
 		};
+		for (const Part &q : ps) pieces[piece].sam_bytes += q.n;
+		if (o.placed && !spilled) pieces[piece].sam_bytes += o.placed_bytes;
+		for (const Part &q : po) pieces[piece].ori_bytes += q.n;
 		append(gs, ps); append(go, po);
 		t_join += CallReport::now() - t0;
 	};
 	std::vector<Part> unused_s, unused_o;
-	const int rc = run_block(c, fastq, n, unused_s, unused_o, &take, room.p ? &room : nullptr);
+	const int rc = run_block(c, pieces, n_pieces, unused_s, unused_o, &take, room.p ? &room : nullptr);
 	if (rc != 0 || oom) { free(gs.p); free(go.p); if (room.p) g_out_pool.release(room.p); if (rc == 0) { g_aln_err = "out of memory"; return PANSVR_E_ARG; } return rc; }
 	if (room.p && !spilled) { gs.p = room.p; gs.used = placed_prefix; }  // the usual case: everything is already in place
 	else if (room.p) g_out_pool.release(room.p);
@@ -520,6 +606,30 @@ int pansvr_aln_block(pansvr_aln_ctx *c, const char *fastq, size_t n, char **sam,
 	c->pipe->stats.t_stage[7] += t_join;
 	return 0;
 }
+} // namespace
+
+int pansvr_aln_block(pansvr_aln_ctx *c, const char *fastq, size_t n, char **sam, size_t *sam_bytes, char **ori, size_t *ori_bytes)
+{
+	if (!c || !fastq || !sam || !ori) return PANSVR_E_ARG;
+	Piece one;
+	one.p = fastq; one.n = n;
+	return block_of_pieces(c, &one, 1, sam, sam_bytes, ori, ori_bytes);
+}
+
+int pansvr_aln_pieces(pansvr_aln_ctx *c, pansvr_aln_piece_t *pieces, int n_pieces, char **sam, size_t *sam_bytes, char **ori, size_t *ori_bytes)
+{
+	if (!c || !pieces || n_pieces < 1 || !sam || !ori) return PANSVR_E_ARG;
+	std::vector<Piece> ps((size_t)n_pieces);
+	for (int i = 0; i < n_pieces; ++i) {
+		if (!pieces[i].fastq) return PANSVR_E_ARG;
+		ps[(size_t)i].p = pieces[i].fastq; ps[(size_t)i].n = pieces[i].fastq_bytes;
+		ps[(size_t)i].await_path = pieces[i].await_path && *pieces[i].await_path ? pieces[i].await_path : nullptr;
+		ps[(size_t)i].publish_path = pieces[i].publish_path && *pieces[i].publish_path ? pieces[i].publish_path : nullptr;
+	}
+	const int rc = block_of_pieces(c, ps.data(), ps.size(), sam, sam_bytes, ori, ori_bytes);
+	for (int i = 0; i < n_pieces; ++i) { pieces[i].sam_bytes = ps[(size_t)i].sam_bytes; pieces[i].ori_bytes = ps[(size_t)i].ori_bytes; }
+	return rc;
+}
 
 // Same block, records in BAM form: every record as bam_write1 hands it to BGZF ([block_size][core][name][cigar][seq][qual][aux]).
 int pansvr_aln_block_bam(pansvr_aln_ctx *c, const char *fastq, size_t n, uint8_t **bam, size_t *bam_bytes, uint8_t **ori, size_t *ori_bytes)
@@ -527,7 +637,9 @@ int pansvr_aln_block_bam(pansvr_aln_ctx *c, const char *fastq, size_t n, uint8_t
 	if (!c || !fastq || !bam || !ori) return PANSVR_E_ARG;
 	CallReport report(c);
 	std::vector<Part> text_sam, text_ori;
-	const int rc = run_block(c, fastq, n, text_sam, text_ori);
+	Piece one;
+	one.p = fastq; one.n = n;
+	const int rc = run_block(c, &one, 1, text_sam, text_ori);
 	if (rc != 0) return rc;
 	const double t0 = CallReport::now();
 	const size_t np = text_sam.size(), npo = text_ori.size();
@@ -613,6 +725,7 @@ int pansvr_aln_last_stats(const pansvr_aln_ctx *c, pansvr_aln_stats_t *out)
 	const AlnPipeline::Stats &s = c->pipe->stats;
 	out->reads = (int64_t)s.reads; out->mems = (int64_t)s.mems; out->ksw_tasks = (int64_t)s.ksw_tasks; out->ksw_cells = (int64_t)s.ksw_cells;
 	out->deferred_pairs = (int64_t)s.deferred_pairs;
+	out->in_order_seconds = s.t_in_order; out->in_order_pairs = (int64_t)s.in_order_pairs; out->in_order_draws = (int64_t)s.in_order_draws; out->host_pairs = (int64_t)s.host_pairs;
 	for (int i = 0; i < 8; ++i) out->stage_seconds[i] = s.t_stage[i];
 	out->kernel_launches = s.dev.launches; out->h2d_bytes = s.dev.h2d_bytes; out->d2h_bytes = s.dev.d2h_bytes;
 	out->seed_probes = s.dev.seed_probes;

@@ -346,18 +346,36 @@ SEED_HD void dev_probe_pair(const PairIndexView &ix, const PairOpts &o, const De
 	else pr.redo = PR_REDO_HOST;
 }
 
-// Primary / secondary / mate of both reads once the pairing is decided (win_i / win_j: the in-order pass's winner for a
-// pair with redo == 2).  set_primary_secondary_mate, RRH:501-534, and what output_BAM reads of the results.
-SEED_HD void dev_finalize_pair(const PairIndexView &ix, const PairOpts &o, const DevOri *ori, DevPairState &st, uint8_t redo, int win_i, int win_j,
+// What a pair takes from the reference's rand() stream when nothing about it depends on the numbers but the pairing winner:
+// the draws of its two reads, then one draw per tied pairing event (RRH:553).
+SEED_HD uint32_t dev_pair_draws(const DevProbe &pr)
+{
+	if (pr.redo != 1 && pr.redo != 2) return 0;
+	uint32_t n = (uint32_t)pr.draws0 + pr.draws1;
+	for (uint32_t m = pr.tie_mask; m; m &= m - 1) ++n;
+	return n;
+}
+
+// Primary / secondary / mate of both reads once the pairing is decided.  A pair with redo == 2 redraws its pairing ties here from
+// `drawn`, the numbers the in-order pass took from the stream for this pair (store_pair's rule over the recorded events).
+// set_primary_secondary_mate, RRH:501-534, and what output_BAM reads of the results.
+SEED_HD void dev_finalize_pair(const PairIndexView &ix, const PairOpts &o, const DevOri *ori, DevPairState &st, const DevProbe &pr, const int32_t *drawn,
                                const DevCand *cands, const DevCigar *cigs, DevFinal *fin, DevPairFinal &pf)
 {
 	for (int k = 0; k < 2; ++k) { DevFinal &f = fin[k]; f.flags = 0; f.p_ins = f.p_ncig = 0; f.p_chr = f.p_ref_bg = f.p_align = f.p_chain = f.p_mapq = 0; f.p_cand = f.p_sv = f.p_mate_sv = -1; f.mate_chr = f.mate_ref_bg = 0; f.s_chr = f.s_ref_bg = f.s_read_bg = f.s_align = 0; f.s_sv = -1; }
 	pf.max_score = 0; pf.cur_isize = 0; pf.gain = pf.proper = 0; pf.valid = 0; pf.pad = 0;
+	const uint8_t redo = pr.redo;
 	if (redo == PR_REDO_HOST) return;
 	PairSide S[2];
 	for (int k = 0; k < 2; ++k) { S[k].res = st.res[k]; S[k].n = st.n[k]; S[k].ori = ori[k]; }
 	DevPE pe = st.pe;
-	if (redo == 2) {                                               // apply_pairing
+	if (redo == 2) {                                               // the tie rule over the events, then apply_pairing
+		const int32_t *r = drawn + pr.draws0 + pr.draws1;
+		int max_same = 1, win_i = -1, win_j = -1;
+		for (int k = 0; k < pr.ev_cnt; ++k) {
+			if (!((pr.tie_mask >> k) & 1)) { max_same = 1; win_i = pr.ev_i[k]; win_j = pr.ev_j[k]; }
+			else { ++max_same; if (*r++ % max_same == 0) { win_i = pr.ev_i[k]; win_j = pr.ev_j[k]; } }
+		}
 		pe.m1 = (int8_t)win_i; pe.m2 = (int8_t)win_j;
 		const Picked a = dev_pick(S[0], win_i), b = dev_pick(S[1], win_j);
 		pe.cur_isize = dev_proper_mated(ix, o, a, b);

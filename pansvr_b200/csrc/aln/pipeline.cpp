@@ -21,7 +21,7 @@ struct AlnPipeline::DevBuffers {                                  // one block's
 	HostVec<uint8_t> text;                                        // the block's FASTQ text (pinned staging)
 	HostVec<DevRead> reads;
 	HostVec<DevRec> recs;
-	HostVec<int8_t> win;
+	HostVec<int32_t> drawn;                                       // what the in-order pass took from the rand() stream for the block's device pairs
 	HostVec<uint32_t> host_len;
 	DevStageOut out;
 };
@@ -1213,9 +1213,16 @@ void AlnPipeline::import_streams(const StreamState &s) { rand_ = s.rand; rand_r_
 
 void AlnPipeline::await_streams(const std::string &path) { std::lock_guard<std::mutex> lk(turn_m_); await_path_ = path; }
 
-bool AlnPipeline::publish_streams(const std::string &path)
+void AlnPipeline::chain_at(uint64_t seq, const char *await, const char *publish)
 {
-	const StreamState s = export_streams();
+	std::lock_guard<std::mutex> lk(turn_m_);
+	chain_[seq] = std::make_pair(std::string(await ? await : ""), std::string(publish ? publish : ""));
+}
+
+bool AlnPipeline::publish_streams(const std::string &path) { return write_streams(path, export_streams()); }
+
+bool AlnPipeline::write_streams(const std::string &path, const StreamState &s)
+{
 	const std::string tmp = path + ".part";
 	FILE *f = fopen(tmp.c_str(), "wb");
 	if (!f) return false;
@@ -1227,7 +1234,7 @@ bool AlnPipeline::publish_streams(const std::string &path)
 void AlnPipeline::reset()
 {
 	replay_turn_ = 0; seq_issued_ = 0;
-	await_path_.clear();
+	await_path_.clear(); chain_.clear();
 	bad_cigar_records_ = 0;
 	rand_.reseed(1);
 	stats = Stats();
@@ -1251,13 +1258,17 @@ bool AlnPipeline::align_block_host(const FastqRec *recs, size_t n_reads_in, Bloc
 	Impl I(*this);
 	const size_t n_reads = n_reads_in & ~(size_t)1, n_pairs = n_reads / 2;
 	// in-order sections: wait until every earlier block has finished its replay; leave by passing the turn on
+	double t_turn = -1;                                                   // when this block's in-order section began
 	auto wait_turn = [&]() {
 		std::unique_lock<std::mutex> lk(turn_m_);
 		turn_cv_.wait(lk, [&]() { return replay_turn_ == seq; });
-		if (await_path_.empty()) return;
-		// this process continues another one's input (await_streams): take the random streams where that one left them
-		const std::string path = await_path_;
-		await_path_.clear();
+		struct Mark { double &t; ~Mark() { if (t < 0) t = now(); } } mark{t_turn};
+		// this process continues another one's input (await_streams, chain_at): take the random streams where that one left them
+		std::string path;
+		if (!await_path_.empty()) { path = await_path_; await_path_.clear(); }
+		auto ch = chain_.find(seq);
+		if (ch != chain_.end() && !ch->second.first.empty()) { path = ch->second.first; ch->second.first.clear(); }
+		if (path.empty()) return;
 		lk.unlock();
 		for (uint64_t spins = 0;; ++spins) {
 			if (spins == 6000000) { fprintf(stderr, "pansvr_b200: still no stream state at %s after 10 minutes (did the process before this one fail?)\n", path.c_str()); abort(); }
@@ -1272,7 +1283,21 @@ bool AlnPipeline::align_block_host(const FastqRec *recs, size_t n_reads_in, Bloc
 	};
 	struct TurnGuard {                                                    // whatever happens, the next block must not wait for ever
 		AlnPipeline &P; uint64_t seq; bool passed = false;
-		void pass() { if (passed) return; passed = true; { std::lock_guard<std::mutex> lk(P.turn_m_); if (P.replay_turn_ == seq) P.replay_turn_ = seq + 1; } P.turn_cv_.notify_all(); }
+		void pass()
+		{
+			if (passed) return;
+			passed = true;
+			std::string pub;
+			{ std::lock_guard<std::mutex> lk(P.turn_m_); auto ch = P.chain_.find(seq); if (ch != P.chain_.end()) { pub = ch->second.second; P.chain_.erase(ch); } }
+			if (!pub.empty()) {                                               // the process that has the next piece of the input goes on from here
+				StreamState s;
+				memset((void*)&s, 0, sizeof s);
+				s.magic = 0x70535652u; s.rand = P.rand_; s.rand_r[0] = P.rand_r_[0]; s.rand_r[1] = P.rand_r_[1];
+				if (!P.write_streams(pub, s)) { fprintf(stderr, "pansvr_b200: cannot write the stream state to %s\n", pub.c_str()); abort(); }
+			}
+			{ std::lock_guard<std::mutex> lk(P.turn_m_); if (P.replay_turn_ == seq) P.replay_turn_ = seq + 1; }
+			P.turn_cv_.notify_all();
+		}
 		~TurnGuard() { if (!passed) { std::unique_lock<std::mutex> lk(P.turn_m_); P.turn_cv_.wait(lk, [&]() { return P.replay_turn_ == seq; }); lk.unlock(); pass(); } }
 	} turn{*this, seq};
 	auto add_time = [&](int stage, double dt) { std::lock_guard<std::mutex> lk(stats_m_); stats.t_stage[stage] += dt; };
@@ -1280,7 +1305,12 @@ bool AlnPipeline::align_block_host(const FastqRec *recs, size_t n_reads_in, Bloc
 	out.ori.resize((size_t)std::max(1, opt.threads));
 	for (std::string &x : out.sam) x.clear();
 	for (std::string &x : out.ori) x.clear();
-	if (n_pairs == 0 && !H) return true;
+	if (n_pairs == 0 && !H) {
+		bool chained;
+		{ std::lock_guard<std::mutex> lk(turn_m_); chained = chain_.count(seq) != 0; }
+		if (chained) wait_turn();                                          // an empty piece still takes the streams over and hands them on
+		return true;
+	}
 	double t0 = now();
 
 	if (n_pairs) ensure_read_stats(recs[0]);
@@ -1710,6 +1740,7 @@ bool AlnPipeline::align_block_host(const FastqRec *recs, size_t n_reads_in, Bloc
 		if (pes[pi].gain) I.set_primary(se, pes[pi]);
 	}
 	turn.pass();                                                          // the next block may replay now
+	{ std::lock_guard<std::mutex> lk(stats_m_); stats.t_in_order += now() - t_turn; stats.in_order_pairs += n_redo; }
 	parallel(n_pairs, [&](size_t pb, size_t pe_, int) {                    // winners of the redrawn pairings
 		for (size_t pi = pb; pi < pe_; ++pi) {
 			if (redo[pi] != 2) continue;
@@ -1850,29 +1881,22 @@ bool AlnPipeline::align_block_dev(const char *base, size_t text_bytes, const Fas
 	}
 	// ---- the pairs the host path finishes: 'N' / 'n' in a read, a unipath that needs random_r, ties that change the outcome
 	std::vector<uint32_t> host_list;
-	for (size_t p = 0; p < n_pairs; ++p) if (o.pair_probe[p].redo == PR_REDO_HOST) host_list.push_back((uint32_t)p);
+	size_t io_pairs = 0;
+	for (size_t p = 0; p < n_pairs; ++p) { if (o.redo[p] == PR_REDO_HOST) host_list.push_back((uint32_t)p); else io_pairs += o.redo[p] != 0; }
 	std::vector<FastqRec> hrecs(2 * host_list.size());
 	for (size_t s = 0; s < host_list.size(); ++s) { hrecs[2 * s] = rec_at(2 * (size_t)host_list[s]); hrecs[2 * s + 1] = rec_at(2 * (size_t)host_list[s] + 1); }
-	db->win.resize(nd + 2);
-	for (size_t t = 0; t < nd; ++t) db->win[t] = -1;
-	size_t cursor = 0;
+	// in-order pass of the device path's pairs: each advances the stream by a count the probe knows (its reads' draws, one per tied
+	// pairing event), so the pass only takes the numbers -- draw_off[p] of them before pair p -- and the second trip redraws the
+	// pairing winners from them on the device (RRH:553); the host path's pairs take their turn in between, against the stream itself
+	const size_t n_drawn = n_pairs ? o.draw_off[n_pairs] : 0;
+	db->drawn.resize(n_drawn + 1);
+	size_t taken = 0;
 	BlockHooks H;
 	H.global_pair = host_list.data();
-	// in-order pass of the device path's pairs: advance the stream by a read's draws, redraw the pairing ties (RRH:553)
 	H.fast_until = [&](uint64_t upto) {
-		for (; cursor < n_pairs && (uint64_t)cursor < upto; ++cursor) {
-			const DevProbe &pr = o.pair_probe[cursor];
-			if (pr.redo == 0 || pr.redo == PR_REDO_HOST) continue;
-			for (int k = 0, n = pr.draws0 + pr.draws1; k < n; ++k) rand_.next();
-			if (pr.redo == 2) {
-				int max_same = 1, wi = -1, wj = -1;
-				for (int k = 0; k < pr.ev_cnt; ++k) {
-					if (!((pr.tie_mask >> k) & 1)) { max_same = 1; wi = pr.ev_i[k]; wj = pr.ev_j[k]; }
-					else { ++max_same; if (rand_.next() % max_same == 0) { wi = pr.ev_i[k]; wj = pr.ev_j[k]; } }
-				}
-				db->win[2 * cursor] = (int8_t)wi; db->win[2 * cursor + 1] = (int8_t)wj;
-			}
-		}
+		const size_t to = o.draw_off[(size_t)std::min<uint64_t>(upto, n_pairs)];
+		int32_t *r = db->drawn.data();
+		for (; taken < to; ++taken) r[taken] = rand_.next();
 	};
 	H.emit = [&](const std::function<void(size_t, std::string&, std::string&)> &text_host, std::string &e2) -> bool {
 		double t1 = now();
@@ -1886,7 +1910,7 @@ bool AlnPipeline::align_block_dev(const char *base, size_t text_bytes, const Fas
 		// ---- second trip: the winners go up; primary / secondary / mate of every read and the block's SAM text come back
 		bool got = false;
 		o.text_dest = [&](size_t total) -> char* { char *p = out.place ? out.place(total) : nullptr; out.place_called = true; got = p != nullptr; return p; };
-		const bool fin_ok = stage_service_finalize(db->svc, in.pair_opts, opt.not_ori ? 1 : 0, n_pairs, db->win.data(), db->host_len.data(), o, out.sam_text, e2);
+		const bool fin_ok = stage_service_finalize(db->svc, in.pair_opts, opt.not_ori ? 1 : 0, n_pairs, db->drawn.data(), n_drawn, db->host_len.data(), o, out.sam_text, e2);
 		o.text_dest = nullptr;
 		if (!fin_ok) return false;
 		out.placed = got;
@@ -1969,6 +1993,7 @@ bool AlnPipeline::align_block_dev(const char *base, size_t text_bytes, const Fas
 	if (ok) {
 		std::lock_guard<std::mutex> lk(stats_m_);
 		stats.reads += 2 * (n_pairs - host_list.size());
+		stats.in_order_pairs += io_pairs; stats.in_order_draws += n_drawn; stats.host_pairs += host_list.size();
 		stats.mems += o.mem_off[2 * nd]; stats.ksw_tasks += o.n_tasks; stats.ksw_cells += o.n_cells;
 		stats.dev.add(o.dev); stats.dev.seed_probes += (int64_t)o.probes;
 		o.dev = DevCounters();

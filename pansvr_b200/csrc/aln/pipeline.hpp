@@ -185,7 +185,11 @@ public:
 	void await_streams(const std::string &path);         // the first in-order section from now on waits for `path` and imports it
 	bool publish_streams(const std::string &path);       // export_streams() into `path` (written beside it and renamed: readers never see a part)
 	bool awaiting_streams() { std::lock_guard<std::mutex> lk(turn_m_); return !await_path_.empty(); }
-	struct Stats { uint64_t reads = 0, probes_reads = 0, mems = 0, ksw_tasks = 0, ksw_cells = 0, deferred_pairs = 0;
+	// the same per block: the in-order section of block `seq` first waits for the file `await` and imports it, and writes `publish`
+	// the moment it is done (before the block's later stages) -- pieces of one input dealt to several processes in turn
+	void chain_at(uint64_t seq, const char *await, const char *publish);
+	struct Stats { uint64_t reads = 0, probes_reads = 0, mems = 0, ksw_tasks = 0, ksw_cells = 0, deferred_pairs = 0, in_order_pairs = 0, in_order_draws = 0, host_pairs = 0;
+	               double t_in_order = 0;
 	               double t_stage[8] = {0, 0, 0, 0, 0, 0, 0, 0}; DevCounters dev; } stats;   // A..F, FASTQ parse, output assembly
 	AlnOptions opt;                   // stat_set / read_len / isize_* are filled from the first comment
 private:
@@ -226,6 +230,8 @@ private:
 	GlibcRandom rand_r_[2];           // per-handler random_r states (RRH:339-340), seeded from rand_ at start-up
 	int min_filter_score_ = 0;
 	std::string await_path_;              // guarded by turn_m_
+	std::map<uint64_t, std::pair<std::string, std::string>> chain_;   // seq -> (await, publish); guarded by turn_m_
+	bool write_streams(const std::string &path, const StreamState &s);
 	friend struct Impl;
 };
 

@@ -28,7 +28,7 @@ namespace pansvr {
 enum DevSlot {
 	SL_TEXT, SL_READS, SL_BITS, SL_LIST, SL_FLAGS, SL_MEM_CNT, SL_MEM_OFF, SL_MEMS, SL_MEMS_TMP, SL_NVU, SL_SEED_CNT, SL_SEED_OFF,
 	SL_SEEDS, SL_SEEDS_TMP, SL_DIST, SL_PRE, SL_PLAN_CNT, SL_PLAN_OFF, SL_CANDS, SL_PIECES, SL_QLEN, SL_TLEN, SL_QOFF, SL_TOFF,
-	SL_Q, SL_T, SL_RES, SL_KCIG, SL_CIGS, SL_MISC, SL_SCAN_TMP, SL_USED, SL_ORI, SL_PSTATE, SL_PROBE, SL_WIN, SL_FINAL, SL_PFINAL, SL_RECS, SL_HOSTLEN, SL_TXT_LEN, SL_TXT_OFF, SL_TXT, SL_NL_CNT, SL_NL_OFF, SL_LINES, SL_LAY_CNT, SL_LAY_OFF, SL_SEL_PAIR, SL_SEL_FIN, SL_SEL_PFIN, SL_COUNT
+	SL_Q, SL_T, SL_RES, SL_KCIG, SL_CIGS, SL_MISC, SL_SCAN_TMP, SL_USED, SL_ORI, SL_PSTATE, SL_PROBE, SL_WIN, SL_FINAL, SL_PFINAL, SL_RECS, SL_HOSTLEN, SL_TXT_LEN, SL_TXT_OFF, SL_TXT, SL_NL_CNT, SL_NL_OFF, SL_LINES, SL_LAY_CNT, SL_LAY_OFF, SL_SEL_PAIR, SL_SEL_FIN, SL_SEL_PFIN, SL_DRAW_CNT, SL_DRAW_OFF, SL_REDO, SL_DRAWN, SL_COUNT
 };
 
 // ---- functors (one element of work each; plain data members only, so they can be passed to a kernel by value)
@@ -195,18 +195,20 @@ struct FnExplore {                                                 // one read: 
 	}
 };
 struct FnProbe {                                                   // one pair = reads 2p, 2p + 1 of the table: pairing
-	PairIndexView ix; PairOpts o; const uint8_t *flags; const DevOri *ori; DevPairState *state; DevProbe *probe;
+	PairIndexView ix; PairOpts o; const uint8_t *flags; const DevOri *ori; DevPairState *state; DevProbe *probe; uint32_t *draw_cnt; uint8_t *redo;
 	SEED_HD void operator()(size_t p) const
 	{
 		DevProbe &pr = probe[p];
-		if ((flags[2 * p] | flags[2 * p + 1]) & (ST_FLAG_NEEDS_RAND | ST_FLAG_HOST)) { pr.redo = PR_REDO_HOST; pr.draws0 = pr.draws1 = pr.ev_cnt = 0; pr.tie_mask = 0; return; }
-		dev_probe_pair(ix, o, ori + 2 * p, state[p], pr);
+		if ((flags[2 * p] | flags[2 * p + 1]) & (ST_FLAG_NEEDS_RAND | ST_FLAG_HOST)) { pr.redo = PR_REDO_HOST; pr.draws0 = pr.draws1 = pr.ev_cnt = 0; pr.tie_mask = 0; }
+		else dev_probe_pair(ix, o, ori + 2 * p, state[p], pr);
+		draw_cnt[p] = dev_pair_draws(pr);                           // how far the pair advances the stream (0: not at all, or the host path's business)
+		redo[p] = pr.redo;
 	}
 };
 struct FnFinalize {
-	PairIndexView ix; PairOpts o; const DevOri *ori; DevPairState *state; const DevProbe *probe; const int8_t *win; const DevCand *cands; const DevCigar *cigs;
+	PairIndexView ix; PairOpts o; const DevOri *ori; DevPairState *state; const DevProbe *probe; const uint32_t *draw_off; const int32_t *drawn; const DevCand *cands; const DevCigar *cigs;
 	DevFinal *fin; DevPairFinal *pfin;
-	SEED_HD void operator()(size_t p) const { dev_finalize_pair(ix, o, ori + 2 * p, state[p], probe[p].redo, win[2 * p], win[2 * p + 1], cands, cigs, fin + 2 * p, pfin[p]); }
+	SEED_HD void operator()(size_t p) const { dev_finalize_pair(ix, o, ori + 2 * p, state[p], probe[p], drawn + draw_off[p], cands, cigs, fin + 2 * p, pfin[p]); }
 };
 struct FnOriSelect {                                               // the (few) pairs whose originals may go to the `-p` output: their results go back to the host
 	PairOpts o; const DevOri *ori; const DevFinal *fin; const DevPairFinal *pfin; uint32_t *count; uint32_t cap; uint32_t *sel_pair; DevFinal *sel_fin; DevPairFinal *sel_pfin;
@@ -268,7 +270,9 @@ struct DevStageOut {                                               // host side,
 	HostVec<DevSeed> seeds; HostVec<float> dist; HostVec<int32_t> pre;
 	HostVec<uint32_t> cand_off;                                    // n + 1
 	HostVec<DevCand> cands; HostVec<DevCigar> cigs;
-	HostVec<DevProbe> pair_probe;                                  // n / 2: what the in-order pass has to do for each pair
+	HostVec<DevProbe> pair_probe;                                  // n / 2: the probe's record of each pair (want_tables only; it stays on the device)
+	HostVec<uint8_t> redo;                                         // n / 2: 0 nothing drawn, 1 / 2 advances the stream by a known count, PR_REDO_HOST: the host path's pair
+	HostVec<uint32_t> draw_off;                                    // n / 2 + 1: prefix sums of the pairs' draw counts = each pair's place in the block's drawn numbers
 	// after run_device_finalize: the results of the pairs that may go to the `-p` output (pair index, both reads, pair) -- or, if
 	// sel_all, of every pair (fin: n, pfin: n / 2)
 	HostVec<uint32_t> sel_pair; HostVec<DevFinal> sel_fin; HostVec<DevPairFinal> sel_pfin; bool sel_all = false;
@@ -288,7 +292,7 @@ bool run_device_stages(BE &be, const IndexView &ix, const uint64_t *d_pos, const
 	const size_t n = in.n_reads;
 	out.n_tasks = out.n_cells = out.probes = 0;
 	out.flags.resize(n); out.mem_off.resize(2 * n + 1); out.seed_off.resize(2 * n + 1); out.cand_off.resize(n + 1);
-	out.seeds.clear(); out.dist.clear(); out.pre.clear(); out.cands.clear(); out.cigs.clear();
+	out.seeds.clear(); out.dist.clear(); out.pre.clear(); out.cands.clear(); out.cigs.clear(); out.redo.clear(); out.draw_off.clear();
 	if (n == 0) { out.mem_off[0] = out.seed_off[0] = out.cand_off[0] = 0; return true; }
 	// ---- upload
 	out.parse_ok = true;
@@ -443,9 +447,16 @@ bool run_device_stages(BE &be, const IndexView &ix, const uint64_t *d_pos, const
 		DevProbe *d_probe = be.template buf<DevProbe>(SL_PROBE, np);
 		if (!d_used || !d_state || !d_probe) { err = "device stages: out of device memory"; return false; }
 		be.for_each(n, FnExplore{pix, d_flags, d_seed_off, d_seeds, d_dist, d_pre, d_used, d_plan_off, be.template buf<DevCand>(SL_CANDS, 0), d_ori, d_state}, 6);
-		be.for_each(np, FnProbe{pix, in.pair_opts, d_flags, d_ori, d_state, d_probe}, 6);
-		out.pair_probe.resize(np);
-		be.d2h(out.pair_probe.data(), d_probe, np * sizeof(DevProbe));
+		uint32_t *d_dcnt = be.template buf<uint32_t>(SL_DRAW_CNT, np + 1), *d_doff = be.template buf<uint32_t>(SL_DRAW_OFF, np + 1);
+		uint8_t *d_redo = be.template buf<uint8_t>(SL_REDO, np);
+		if (!d_dcnt || !d_doff || !d_redo) { err = "device stages: out of device memory"; return false; }
+		be.zero(d_dcnt + np, 4);
+		be.for_each(np, FnProbe{pix, in.pair_opts, d_flags, d_ori, d_state, d_probe, d_dcnt, d_redo}, 6);
+		be.scan(d_dcnt, d_doff, np + 1);
+		out.redo.resize(np); out.draw_off.resize(np + 1);
+		be.d2h(out.redo.data(), d_redo, np);
+		be.d2h(out.draw_off.data(), d_doff, (np + 1) * 4);
+		if (in.want_tables) { out.pair_probe.resize(np); be.d2h(out.pair_probe.data(), d_probe, np * sizeof(DevProbe)); }
 		be.sync();
 	}
 	return true;
@@ -483,12 +494,12 @@ struct FnText {                                                    // the SAM re
 	}
 };
 
-// Second trip of a block whose pairs were probed: the winners the in-order pass drew for the pairs with pairing ties go up
-// (win: 2 entries per pair, the candidate index of each mate, -1 = none), with the length of the text the host path produced for
+// Second trip of a block whose pairs were probed: the numbers the in-order pass took from the stream for the block's pairs go up
+// (drawn: draw_off[n_pairs] of them, pair p's at draw_off[p]), with the length of the text the host path produced for
 // each of its pairs (host_len, 0 elsewhere); primary / secondary / mate of every read come back, and the block's SAM text with
 // every record in its place (gaps of host_len bytes where the host's pairs go: out.txt_off[2p] is the place of pair p).
 template <class BE>
-bool run_device_finalize(BE &be, const PairIndexView &pix, const PairOpts &o, const TextTables &T, size_t n_pairs, const int8_t *win, const uint32_t *host_len,
+bool run_device_finalize(BE &be, const PairIndexView &pix, const PairOpts &o, const TextTables &T, size_t n_pairs, const int32_t *drawn, size_t n_drawn, const uint32_t *host_len,
                          DevStageOut &out, HostVec<char> &text_out, std::string &err)
 {
 	out.fin.resize(2 * n_pairs); out.pfin.resize(n_pairs); out.txt_off.resize(2 * n_pairs + 1);
@@ -496,18 +507,18 @@ bool run_device_finalize(BE &be, const PairIndexView &pix, const PairOpts &o, co
 	text_out.clear();
 	if (n_pairs == 0) { out.txt_off[0] = 0; return true; }
 	const size_t n = 2 * n_pairs;
-	int8_t *d_win = be.template buf<int8_t>(SL_WIN, n);
+	int32_t *d_drawn = be.template buf<int32_t>(SL_DRAWN, n_drawn + 1);
 	DevFinal *d_fin = be.template buf<DevFinal>(SL_FINAL, n);
 	DevPairFinal *d_pfin = be.template buf<DevPairFinal>(SL_PFINAL, n_pairs);
 	uint32_t *d_hl = be.template buf<uint32_t>(SL_HOSTLEN, n_pairs), *d_len = be.template buf<uint32_t>(SL_TXT_LEN, n + 1), *d_off = be.template buf<uint32_t>(SL_TXT_OFF, n + 1);
 	uint32_t *d_misc = be.template buf<uint32_t>(SL_MISC, 16);
-	if (!d_win || !d_fin || !d_pfin || !d_hl || !d_len || !d_off) { err = "device stages: out of device memory"; return false; }
-	be.h2d(d_win, win, n);
+	if (!d_drawn || !d_fin || !d_pfin || !d_hl || !d_len || !d_off) { err = "device stages: out of device memory"; return false; }
+	be.h2d(d_drawn, drawn, n_drawn * 4);
 	be.h2d(d_hl, host_len, n_pairs * 4);
 	be.zero(d_misc, 64);
 	be.zero(d_len + n, 4);
 	const DevOri *d_ori = be.template buf<DevOri>(SL_ORI, 0);
-	be.for_each(n_pairs, FnFinalize{pix, o, d_ori, be.template buf<DevPairState>(SL_PSTATE, 0), be.template buf<DevProbe>(SL_PROBE, 0), d_win,
+	be.for_each(n_pairs, FnFinalize{pix, o, d_ori, be.template buf<DevPairState>(SL_PSTATE, 0), be.template buf<DevProbe>(SL_PROBE, 0), be.template buf<uint32_t>(SL_DRAW_OFF, 0), d_drawn,
 	                                be.template buf<DevCand>(SL_CANDS, 0), be.template buf<DevCigar>(SL_CIGS, 0), d_fin, d_pfin}, 6);
 	// the `-p` candidates: selected on the device, a short list for the host (all of it if the list overflows its room)
 	const uint32_t sel_cap = (uint32_t)(n_pairs / 8 + 1024);
@@ -559,7 +570,7 @@ void stage_service_set_scoring(StageService *s, const AlnScores &o, int zdrop); 
 // A service instance holds one block's device state from stage_service_run to stage_service_finalize (two trips with the host's
 // in-order pass in between); blocks in flight at the same time use different instances.
 bool stage_service_run(StageService *s, const DevStageIn &in, DevStageOut &out, std::string &err);
-bool stage_service_finalize(StageService *s, const PairOpts &o, int not_ori, size_t n_pairs, const int8_t *win, const uint32_t *host_len, DevStageOut &out,
+bool stage_service_finalize(StageService *s, const PairOpts &o, int not_ori, size_t n_pairs, const int32_t *drawn, size_t n_drawn, const uint32_t *host_len, DevStageOut &out,
                             HostVec<char> &text_out, std::string &err);
 
 } // namespace pansvr

@@ -24,7 +24,7 @@ EXPORTS = ("pansvr_ksw_create", "pansvr_ksw_destroy", "pansvr_last_error", "pans
            "pansvr_ksw_extd2", "ksw_extd2_sse", "pansvr_int_alu_peak", "pansvr_int_pipe_peaks",
            "pansvr_aln_create", "pansvr_aln_create_multi", "pansvr_aln_destroy", "pansvr_aln_header_text", "pansvr_aln_last_error", "pansvr_aln_block",
            "pansvr_aln_block_bam", "pansvr_bam_open", "pansvr_bam_write", "pansvr_bam_close", "pansvr_aln_last_stats", "pansvr_aln_reset", "pansvr_free", "pansvr_fc_aln_main",
-           "pansvr_aln_prime_read_stats", "pansvr_aln_await_state", "pansvr_aln_publish_state")
+           "pansvr_aln_prime_read_stats", "pansvr_aln_await_state", "pansvr_aln_publish_state", "pansvr_aln_pieces")
 
 
 class KswParamsC(C.Structure):

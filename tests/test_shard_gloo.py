@@ -144,3 +144,79 @@ def test_sharded_aln_two_ranks_equals_reference_t1(tmp_path, name):
     assert p.returncode == 0, p.stderr[-3000:]
     assert first_diff(read(out + ".sam"), read(demo.ref_sam)) is None
     assert read(out + "_ori.sam") == read(demo.ref_ori)
+
+
+PIECES_WORKER = r"""
+# one input dealt to two processes piece by piece (piece b goes to rank b mod 2): every rank realigns its pieces in ONE
+# pansvr_aln_pieces call; the random streams go from piece to piece through files, rank 0 joins the outputs in piece order
+import ctypes, json, os, sys
+sys.path.insert(0, sys.argv[1])
+import torch.distributed as dist
+from pansvr_b200 import aln, shard
+root, index_dir, header_sam, reads_fq, state_dir, out_path, piece_pairs = sys.argv[1:8]
+piece_pairs = int(piece_pairs)
+rank, local, world = shard.rank_env()
+dist.init_process_group("gloo")
+os.environ["PANSVR_ORACLE_SO"] = os.path.join(root, "oracle", "libksw_oracle.so")
+lib = ctypes.CDLL(os.path.join(root, "tests", "emul", "libaln_emul.so"))
+fq = open(reads_fq, "rb").read()
+lines = fq.split(b"\n")
+n_pairs = len([1 for x in lines if x]) // 8
+cuts = list(range(0, n_pairs, piece_pairs)) + [n_pairs]
+texts = [b"\n".join(lines[8 * b:8 * e]) + b"\n" for b, e in zip(cuts[:-1], cuts[1:])]
+head = b"\n".join(lines[:4]) + b"\n"
+ctx = aln.AlnContext(index_dir, header_sam, lib=lib, threads=2)
+outs = []
+for step in range(2):                                 # two passes: reset() must give the same bytes again
+    ctx.reset()
+    ctx.prime_read_stats(head)
+    mine = [b for b in range(len(texts)) if b % world == rank]
+    bufs = [ctypes.create_string_buffer(texts[b], len(texts[b])) for b in mine]
+    pieces = [(ctypes.addressof(buf), len(texts[b]),
+               os.path.join(state_dir, f"s{step}_b{b}") if b > 0 else None,
+               os.path.join(state_dir, f"s{step}_b{b + 1}") if b + 1 < len(texts) else None) for b, buf in zip(mine, bufs)]
+    if pieces:
+        (sa, sn), (oa, on), per, release = ctx.align_pieces(pieces)
+        sam, ori = ctypes.string_at(sa, sn), ctypes.string_at(oa, on)
+        release()
+        assert sum(p[0] for p in per) == sn and sum(p[1] for p in per) == on
+        parts, so, oo = [], 0, 0
+        for b, (ps, po) in zip(mine, per):
+            parts.append((b, sam[so:so + ps], ori[oo:oo + po])); so += ps; oo += po
+    else:
+        parts = []
+    outs.append(parts)
+assert outs[0] == outs[1]
+got = [None] * world
+dist.all_gather_object(got, outs[0])
+if rank == 0:
+    allp = sorted(p for g in got for p in g)
+    hdr = ctx.header_text().encode()
+    open(out_path + ".sam", "wb").write(hdr + b"".join(p[1] for p in allp))
+    open(out_path + "_ori.sam", "wb").write(hdr + b"".join(p[2] for p in allp))
+    print(json.dumps({"pairs": n_pairs, "pieces": len(texts)}))
+dist.barrier()
+dist.destroy_process_group()
+"""
+
+
+@pytest.mark.parametrize("name,piece_pairs", [("multi_allele", 37), ("n_bases", 64)])
+def test_pieces_dealt_to_two_ranks_equal_reference_t1(tmp_path, name, piece_pairs):
+    """SURVEY.md 8e, block-cyclic: the input is dealt to two processes piece by piece, each realigns its pieces in one
+    pansvr_aln_pieces call and the in-order passes follow each other from process to process through the state files; the SAM
+    joined in piece order equals `fc_aln -t 1`."""
+    from tests.alntest_util import get_demo, need_ref_tools, read, first_diff
+    need_ref_tools()
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "tests", "emul"), os.path.join(ROOT, "tests", "emul", "fc_aln_emul")])
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle"), os.path.join(ROOT, "oracle", "libksw_oracle.so")])
+    demo = get_demo(name)
+    w = tmp_path / "pieces_worker.py"
+    w.write_text(PIECES_WORKER)
+    state = tmp_path / "state"
+    state.mkdir()
+    out = str(tmp_path / "joined")
+    p = _torchrun([str(w), ROOT, demo.data.index_dir, demo.data.header_sam, demo.data.reads_fq, str(state), out, str(piece_pairs)], timeout=900)
+    assert p.returncode == 0, p.stderr[-3000:]
+    assert json.loads([ln for ln in p.stdout.splitlines() if ln.startswith("{")][-1])["pieces"] >= 4
+    assert first_diff(read(out + ".sam"), read(demo.ref_sam)) is None
+    assert read(out + "_ori.sam") == read(demo.ref_ori)
