@@ -17,6 +17,7 @@
 
 #include "../../../include/pansvr_b200.h"
 #include "bam_out.hpp"
+#include "text_in.hpp"
 #include "pipeline.hpp"
 #include "stages_run.hpp"
 
@@ -812,9 +813,12 @@ int pansvr_fc_aln_main(int argc, char **argv)
 		fprintf(stderr, "Usage: fc_aln [Options] <IndexDir> <ReadFiles.fq|-> <ori_header.sam>\n");
 		return 1;
 	}
-	gzFile in = strcmp(argv[optind + 1], "-") == 0 ? gzdopen(0, "r") : gzopen(argv[optind + 1], "r");
-	if (!in) { fprintf(stderr, "pansvr_b200 fc_aln: cannot open %s\n", argv[optind + 1]); return 1; }
-	gzbuffer(in, 1 << 20);
+	// plain text, gzip (one inflate stream, as in the reference) or BGZF (blocks inflated on all helper threads): text_in.hpp
+	TextInput in;
+	{
+		std::string why;
+		if (!in.open(argv[optind + 1], std::max(1, threads), why)) { fprintf(stderr, "pansvr_b200 fc_aln: %s\n", why.c_str()); return 1; }
+	}
 	// The input is opened first: the reader fills its queue while the context is created (CUDA start-up, index files).
 	// Three overlapping steps like the reference's kt_pipeline (RR:110-119): a reader thread cuts the input into blocks at
 	// pair boundaries, this thread aligns them in order, a writer thread puts the records out.  The block size is ours
@@ -837,8 +841,9 @@ int pansvr_fc_aln_main(int argc, char **argv)
 			jobs.push(std::move(j));
 		};
 		while (!stop && !failed) {
-			const int got = gzread(in, chunk.data(), (unsigned)chunk.size());
-			if (got <= 0) break;
+			const long got = in.read(chunk.data(), chunk.size());
+			if (got < 0) { fprintf(stderr, "pansvr_b200 fc_aln: %s\n", in.why().c_str()); failed = true; break; }
+			if (got == 0) break;
 			const size_t base = cur.size();
 			cur.append(chunk.data(), (size_t)got);
 			for (const char *q = cur.data() + base, *e = cur.data() + cur.size(); (q = (const char*)memchr(q, '\n', (size_t)(e - q))) != nullptr; ++q) {
@@ -855,7 +860,7 @@ int pansvr_fc_aln_main(int argc, char **argv)
 	pansvr_aln_ctx *ctx = nullptr;
 	if (devices.empty()) devices.push_back(0);
 	int rc = pansvr_aln_create_multi(argv[optind], argv[optind + 2], &o, devices.data(), (int)devices.size(), &ctx);
-	auto stop_reader = [&]() { failed = true; for (;;) { Job j = jobs.pop(); if (j.last) break; } reader.join(); gzclose(in); };
+	auto stop_reader = [&]() { failed = true; for (;;) { Job j = jobs.pop(); if (j.last) break; } reader.join(); in.close(); };
 	if (rc != 0) { fprintf(stderr, "pansvr_b200 fc_aln: %s\n", pansvr_aln_last_error()); stop_reader(); return 1; }
 	FILE *fo = nullptr, *fp = nullptr;
 	pansvr_bam_file *bo = nullptr, *bp = nullptr;
@@ -896,7 +901,7 @@ int pansvr_fc_aln_main(int argc, char **argv)
 	reader.join();
 	writer.join();
 	if (failed && ok) { fprintf(stderr, "pansvr_b200 fc_aln: writing the output failed: %s\n", pansvr_aln_last_error()); ok = false; }
-	gzclose(in);
+	in.close();
 	if (sam) { fclose(fo); fclose(fp); }
 	else if (pansvr_bam_close(bo) != 0 || pansvr_bam_close(bp) != 0) { fprintf(stderr, "pansvr_b200 fc_aln: %s\n", pansvr_aln_last_error()); ok = false; }
 	if (const uint64_t nbad = ctx->pipe->bad_cigar_records_.load())

@@ -88,52 +88,67 @@ SEED_HD uint8_t dna5_code(uint8_t c)                               // charToDna5
 SEED_HD uint32_t packed_base(const uint64_t *bits, uint32_t i) { return (uint32_t)(bits[i >> 5] >> ((31 - (i & 31)) << 1)) & 3u; }
 
 // ---------------------------------------------------------------------------------------------------------- stage A
-// Packs both strands of read state `rd` and runs the STR census of the forward strand.  Returns true for an STR read (whose
-// seed lists are then written).  Reads with a lower-case 'n' never come here (the host keeps them).
-SEED_HD bool encode_read(const uint8_t *text, const DevRead &rd, uint64_t *bits_pool, uint8_t *list_pool)
+// Packs both strands of read state `rd` and runs the STR census of the forward strand.  Returns ENC_STR for an STR read (whose
+// seed lists are then written), ENC_HAS_N if the read holds an 'N' or a lower-case 'n' (then nothing else about the result is
+// defined: the host keeps such a pair), else ENC_PLAIN.
+// filter: ENC_FILTER_WORDS words of scratch, word k at filter[k * fstride] (the CUDA backend keeps them in shared memory,
+// interleaved over the threads of a CTA so that the census's random accesses never conflict).
+enum { ENC_PLAIN = 0, ENC_STR = 1, ENC_HAS_N = 2, ENC_FILTER_WORDS = 64 };
+SEED_HD uint64_t revcomp_word(uint64_t x)                          // the 32 bases of a word in reverse order, complemented
+{
+	x = (x >> 32) | (x << 32);
+	x = ((x >> 16) & 0x0000ffff0000ffffull) | ((x & 0x0000ffff0000ffffull) << 16);
+	x = ((x >> 8) & 0x00ff00ff00ff00ffull) | ((x & 0x00ff00ff00ff00ffull) << 8);
+	x = ((x >> 4) & 0x0f0f0f0f0f0f0f0full) | ((x & 0x0f0f0f0f0f0f0f0full) << 4);
+	x = ((x >> 2) & 0x3333333333333333ull) | ((x & 0x3333333333333333ull) << 2);
+	return ~x;
+}
+SEED_HD int encode_read(const uint8_t *text, const DevRead &rd, uint64_t *bits_pool, uint8_t *list_pool, uint32_t *filter, uint32_t fstride)
 {
 	const uint32_t L = rd.len, words = (L >> 5) + 2;
 	uint64_t *fw = bits_pool + rd.bits_off, *rv = fw + words;
-	const uint8_t *seq = text + rd.seq_off;
 	for (uint32_t k = 0; k < words; ++k) { fw[k] = 0; rv[k] = 0; }
-	uint32_t nth = 0;
-	{
-		uint64_t w = 0;
-		for (uint32_t i = 0; i < L; ++i) {
-			uint8_t ch = seq[i];
-			uint32_t c;
-			if (ch == 'N') { c = (rd.var_code >> (2 * nth)) & 3u; ++nth; }       // "ACGT"[k] encodes to k
-			else c = dna5_code(ch) & 3u;
-			w = (w << 2) | c;
-			if ((i & 31) == 31) { fw[i >> 5] = w; w = 0; }
-		}
-		if (L & 31) fw[L >> 5] = w << ((32 - (L & 31)) << 1);
-	}
-	{                                                              // reverse complement: base j of rv = 3 - base (L-1-j) of fw
-		uint64_t w = 0;
-		for (uint32_t j = 0; j < L; ++j) {
-			w = (w << 2) | (3u - packed_base(fw, L - 1 - j));
-			if ((j & 31) == 31) { rv[j >> 5] = w; w = 0; }
-		}
-		if (L & 31) rv[L >> 5] = w << ((32 - (L & 31)) << 1);
-	}
-	// ---- STR census (RR:553-598): the read is an STR read when fewer than kn - 15 of its kn 20-mers are distinct.
-	// Duplicates are counted through a 4096-bit filter first: a k-mer whose bit is already set MAY be a duplicate, so fewer than
-	// 16 such events prove the read is not STR (almost every read); otherwise the multiplicities are counted exactly.
-	const uint32_t kn = L - LEN_KMER + 1;
+	for (uint32_t k = 0; k < ENC_FILTER_WORDS; ++k) filter[k * fstride] = 0;
+	// ---- one pass over the bases (read a word of text at a time): forward strand packed, and the STR census (RR:553-598) on the
+	// fly.  The read is an STR read when fewer than kn - 15 of its kn 20-mers are distinct; duplicates are counted through a
+	// 2048-bit filter first: a k-mer whose bit is already set MAY be a duplicate, so fewer than 16 such events prove the read is
+	// not STR (almost every read); otherwise the multiplicities are counted exactly below.
 	const uint64_t kmask = (1ull << (2 * LEN_KMER)) - 1;
-	uint32_t filter[128];
-	for (int k = 0; k < 128; ++k) filter[k] = 0;
-	uint32_t maybe_dup = 0;
-	uint64_t roll = 0;
-	for (uint32_t i = 0; i + 1 < LEN_KMER; ++i) roll = (roll << 2) | packed_base(fw, i);
-	for (uint32_t i = 0; i < kn; ++i) {
-		roll = ((roll << 2) | packed_base(fw, i + LEN_KMER - 1)) & kmask;
-		const uint32_t h = (uint32_t)((roll * 0x9E3779B97F4A7C15ull) >> 52);
-		const uint32_t bit = 1u << (h & 31);
-		if (filter[h >> 5] & bit) ++maybe_dup; else filter[h >> 5] |= bit;
+	const uint32_t *tw = (const uint32_t*)(text + (rd.seq_off & ~3u));
+	uint32_t cur = tw[0] >> (8 * (rd.seq_off & 3u)), have = 4 - (rd.seq_off & 3u), next = 1;
+	uint32_t nth = 0, maybe_dup = 0;
+	bool has_n = false;
+	uint64_t w = 0, roll = 0;
+	for (uint32_t i = 0; i < L; ++i) {
+		if (have == 0) { cur = tw[next++]; have = 4; }
+		const uint8_t ch = (uint8_t)(cur & 0xffu);
+		cur >>= 8; --have;
+		uint32_t c;
+		if (ch == 'N') { c = (rd.var_code >> (2 * nth)) & 3u; ++nth; has_n = true; }      // "ACGT"[k] encodes to k
+		else { c = dna5_code(ch) & 3u; has_n |= ch == 'n'; }
+		w = (w << 2) | c;
+		if ((i & 31) == 31) { fw[i >> 5] = w; w = 0; }
+		roll = ((roll << 2) | c) & kmask;
+		if (i + 1 >= LEN_KMER) {
+			const uint32_t x = (uint32_t)roll ^ (uint32_t)(roll >> 19);
+			const uint32_t h = (x * 0x9E3779B1u) >> 21, bit = 1u << (h & 31);
+			uint32_t &slot = filter[(h >> 5) * fstride];
+			if (slot & bit) ++maybe_dup; else slot |= bit;
+		}
 	}
-	if (maybe_dup <= 15) return false;
+	if (L & 31) fw[L >> 5] = w << ((32 - (L & 31)) << 1);
+	if (has_n && rd.var_code == 0) return ENC_HAS_N;
+	{                                                              // reverse complement, a word at a time: base j of rv = 3 - base (L-1-j) of fw
+		const uint32_t nw = (L + 31) >> 5, pad2 = 2 * (32 * nw - L);  // the packed string ends pad2 bits before the end of its last word
+		uint64_t prev = nw ? revcomp_word(fw[nw - 1]) : 0;
+		for (uint32_t k = 0; k < nw; ++k) {
+			const uint64_t nxt = k + 1 < nw ? revcomp_word(fw[nw - 2 - k]) : 0;
+			rv[k] = pad2 ? (prev << pad2) | (nxt >> (64 - pad2)) : prev;
+			prev = nxt;
+		}
+	}
+	const uint32_t kn = L - LEN_KMER + 1;
+	if (maybe_dup <= 15) return ENC_PLAIN;
 	uint32_t distinct = 0;
 	for (uint32_t i = 0; i < kn; ++i) {
 		const uint64_t k = get_kmer(i, fw);
@@ -141,7 +156,7 @@ SEED_HD bool encode_read(const uint8_t *text, const DevRead &rd, uint64_t *bits_
 		for (uint32_t j = 0; j < i && !seen; ++j) seen = get_kmer(j, fw) == k;
 		distinct += !seen;
 	}
-	if (!(distinct < kn - 15)) return false;
+	if (!(distinct < kn - 15)) return ENC_PLAIN;
 	// multiplicity mask, forced seeds at both ends (RR:575-598), reversed copy for the other strand (RR:601)
 	uint8_t *sl = list_pool + rd.list_off, *sr = sl + kn;
 	for (uint32_t i = 0; i < kn; ++i) {
@@ -161,7 +176,7 @@ SEED_HD bool encode_read(const uint8_t *text, const DevRead &rd, uint64_t *bits_
 	}
 	for (uint32_t i = 0; i < kn; ++i) sr[i] = sl[i];
 	for (uint32_t i = 0; i < (kn >> 1) + 1; ++i) { const uint32_t ri = kn - 1 - i; const uint8_t t = sr[i]; sr[i] = sr[ri]; sr[ri] = t; }   // getReverseStr_qual (sic)
-	return true;
+	return ENC_STR;
 }
 
 // ---------------------------------------------------------------------------------------------------------- stage C

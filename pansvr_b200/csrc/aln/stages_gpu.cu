@@ -49,6 +49,15 @@ __global__ void __launch_bounds__(128) text_write_kernel(FnText f, size_t n)
 	for (int k = 0; k < s.np; ++k) s.p[s.patches[k]] = ',';
 }
 
+// Stage A: the census filter of every thread lives in shared memory, word k of thread t at [k * 128 + t]: whatever words the threads
+// of a warp touch, they are in 32 different banks (a per-thread local array would put 32 random words in 32 different cache lines).
+__global__ void __launch_bounds__(128) encode_kernel(FnEncode f, size_t n)
+{
+	__shared__ uint32_t filter[ENC_FILTER_WORDS * 128];
+	const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n) f.run(i, filter + threadIdx.x, 128);
+}
+
 struct CudaBackend {
 	cudaStream_t st = nullptr;
 	void *p[SL_COUNT]; size_t cap[SL_COUNT];
@@ -90,6 +99,17 @@ struct CudaBackend {
 		check(cudaEventRecord(l.a, st), "cudaEventRecord");
 		const unsigned threads = 128;
 		for_each_kernel<F><<<(unsigned)((n + threads - 1) / threads), threads, 0, st>>>(f, n);
+		check(cudaGetLastError(), "kernel launch");
+		check(cudaEventRecord(l.b, st), "cudaEventRecord");
+		laps.push_back(l);
+		++dev.launches;
+	}
+	void encode(size_t n, const FnEncode &f)
+	{
+		if (n == 0 || failed) return;
+		Lap l; l.a = event(); l.b = event(); l.stage = 0;
+		check(cudaEventRecord(l.a, st), "cudaEventRecord");
+		encode_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(f, n);
 		check(cudaGetLastError(), "kernel launch");
 		check(cudaEventRecord(l.b, st), "cudaEventRecord");
 		laps.push_back(l);

@@ -13,6 +13,7 @@
 //   void zero(void *d, size_t bytes)
 //   void sync()                                           wait for everything issued so far
 //   template <class F> void for_each(size_t n, const F &f, int stage)    f(i) for i in [0, n); `stage` labels the timing
+//   void encode(size_t n, const FnEncode &f)                             f.run(i, scratch, stride) for i in [0, n) (stage A; the backend owns the scratch)
 //   void scan(const uint32_t *in, uint32_t *out, size_t n)               exclusive prefix sums, n elements
 //   bool ksw(n, q, qoff, qlen, t, toff, tlen, res, cig, cap, err)        ksw_extd2 batch (w=200, the stage's scoring) over device arrays
 #pragma once
@@ -33,12 +34,44 @@ enum DevSlot {
 
 // ---- functors (one element of work each; plain data members only, so they can be passed to a kernel by value)
 enum { NL_PIECE = 64 };
+// bit 7 of every byte of w that is '\n' (exact: no borrow runs into a neighbour)
+SEED_HD uint32_t newline_bits(uint32_t w)
+{
+	const uint32_t x = w ^ 0x0a0a0a0au;
+	return ~(((x & 0x7f7f7f7fu) + 0x7f7f7f7fu) | x | 0x7f7f7f7fu);
+}
+SEED_HD uint32_t popc32(uint32_t x)
+{
+#if defined(__CUDA_ARCH__)
+	return (uint32_t)__popc(x);
+#else
+	return (uint32_t)__builtin_popcount(x);
+#endif
+}
+struct alignas(16) TextWords { uint32_t w[4]; };
 struct FnLines {                                                   // line ends of one 64-byte piece of the text: counted, then placed
 	const uint8_t *text; uint32_t bytes; uint32_t *cnt; const uint32_t *off; uint32_t *lines; uint32_t max_lines; bool fill;
 	SEED_HD void operator()(size_t k) const
 	{
 		const uint32_t b = (uint32_t)k * NL_PIECE, e = b + NL_PIECE < bytes ? b + NL_PIECE : bytes;
 		uint32_t c = 0;
+		if (e - b == NL_PIECE) {                                    // a whole piece: four 16-byte loads, line ends found a word at a time
+			TextWords q[4];
+			for (int i = 0; i < 4; ++i) q[i] = ((const TextWords*)(text + b))[i];
+			if (!fill) {
+				for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) c += popc32(newline_bits(q[i].w[j]));
+				cnt[k] = c;
+				return;
+			}
+			uint32_t at = off[k];
+			for (int i = 0; i < 4; ++i)
+				for (int j = 0; j < 4; ++j)
+					for (uint32_t m = newline_bits(q[i].w[j]); m; m &= m - 1) {
+						if (at < max_lines) lines[at] = b + 16 * i + 4 * j + ((uint32_t)ctz64(m) >> 3);
+						++at;
+					}
+			return;
+		}
 		if (!fill) { for (uint32_t i = b; i < e; ++i) c += text[i] == '\n'; cnt[k] = c; return; }
 		uint32_t at = off[k];
 		for (uint32_t i = b; i < e; ++i) if (text[i] == '\n') { if (at < max_lines) lines[at] = i; ++at; }
@@ -73,17 +106,23 @@ struct FnOri {                                                     // original a
 };
 struct FnEncode {
 	const uint8_t *text; const DevRead *reads; const DevOri *ori; uint64_t *bits; uint8_t *list; uint8_t *flags;
-	SEED_HD void operator()(size_t i) const
+	// filter: the census's scratch (stages_core.cuh: encode_read), word k at filter[k * fstride]
+	SEED_HD void run(size_t i, uint32_t *filter, uint32_t fstride) const
 	{
 		const DevRead &rd = reads[i];
 		uint8_t f = 0;
-		// 'N' (its substitution draws rand()) or a lower-case 'n' (code 4 spills into the packed neighbour): the host path keeps the pair
-		for (uint32_t k = 0; k < rd.len; ++k) { const uint8_t c = text[rd.seq_off + k]; if (c == 'N' || c == 'n') { f = ST_FLAG_HOST; break; } }
-		// not seeded: skipped by RR:413-414 (full-score original alignment), or shorter than a k-mer
-		if (!f && (rd.len < LEN_KMER || (ori && ori[i].skip))) f = ST_FLAG_NOSEED;
-		if (!f && encode_read(text, rd, bits, list)) f = ST_FLAG_STR;
+		if (rd.len < LEN_KMER || (ori && ori[i].skip)) {
+			// not seeded: skipped by RR:413-414 (full-score original alignment), or shorter than a k-mer -- unless the host path keeps
+			// the pair: 'N' (its substitution draws rand()) or a lower-case 'n' (code 4 spills into the packed neighbour)
+			f = ST_FLAG_NOSEED;
+			for (uint32_t k = 0; k < rd.len; ++k) { const uint8_t c = text[rd.seq_off + k]; if (c == 'N' || c == 'n') { f = ST_FLAG_HOST; break; } }
+		} else {
+			const int r = encode_read(text, rd, bits, list, filter, fstride);
+			f = r == ENC_HAS_N ? (uint8_t)ST_FLAG_HOST : r == ENC_STR ? (uint8_t)ST_FLAG_STR : (uint8_t)0;
+		}
 		flags[i] = f;
 	}
+	SEED_HD void operator()(size_t i) const { uint32_t filter[ENC_FILTER_WORDS]; run(i, filter, 1); }
 };
 struct FnSeed {                                                    // strand j = 2 * read + strand; fill == false: count only
 	IndexView ix; const DevRead *reads; const uint64_t *bits; const uint8_t *list; const uint8_t *flags;
@@ -354,7 +393,7 @@ bool run_device_stages(BE &be, const IndexView &ix, const uint64_t *d_pos, const
 	uint8_t *d_list = be.template buf<uint8_t>(SL_LIST, list_bytes + 16);
 	if (!d_bits || !d_list) { err = "device stages: out of device memory"; return false; }
 	// ---- A
-	be.for_each(n, FnEncode{d_text, d_reads, d_ori, d_bits, d_list, d_flags}, 0);
+	be.encode(n, FnEncode{d_text, d_reads, d_ori, d_bits, d_list, d_flags});
 	// ---- B
 	unsigned long long *d_probes = (unsigned long long*)(d_misc + 2);
 	FnSeed fs{ix, d_reads, d_bits, d_list, d_flags, d_mem_cnt, d_mem_off, nullptr, d_probes, false};

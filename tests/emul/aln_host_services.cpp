@@ -63,6 +63,11 @@ struct HostBackend {
 	void zero(void *d, size_t bytes) { if (bytes) memset(d, 0, bytes); }
 	void sync() {}
 	template <class F> void for_each(size_t n, const F &f, int) { for (size_t i = 0; i < n; ++i) f(i); }
+	void encode(size_t n, const FnEncode &f)                      // strided scratch like the CUDA kernel's (word k of "thread" t at [k * 4 + t])
+	{
+		uint32_t filter[ENC_FILTER_WORDS * 4];
+		for (size_t i = 0; i < n; ++i) f.run(i, filter + (i & 3), 4);
+	}
 	void text_write(size_t n, const FnText &f)                    // the text kernel's three steps, one record at a time
 	{
 		for (size_t i = 0; i < n; ++i) {

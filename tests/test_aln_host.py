@@ -252,3 +252,48 @@ def test_anchor_zero_one_collapse_is_reproduced():
     """the reference's calloc'ed loader merges anchors 0 and 1; the fixture shows it, and so must we."""
     g = golden("aln_demo.sam.gz")
     assert b"SV:Z:0_" not in g and g.count(b"SV:Z:1_") > 60
+
+
+def _bgzf(data: bytes, block=60000) -> bytes:
+    """BGZF as htslib's bgzip writes it: independent gzip members with a 'BC' extra field holding the member size, then the
+    empty end-of-file member (SAM specification 4.1)."""
+    import struct, zlib
+    out = []
+    for at in list(range(0, len(data), block)) + [None]:
+        chunk = b"" if at is None else data[at:at + block]
+        co = zlib.compressobj(6, zlib.DEFLATED, -15)
+        body = co.compress(chunk) + co.flush()
+        bsize = 18 + len(body) + 8 - 1
+        out.append(b"\x1f\x8b\x08\x04\0\0\0\0\0\xff\x06\0BC\x02\0" + struct.pack("<H", bsize) + body + struct.pack("<II", zlib.crc32(chunk), len(chunk)))
+    return b"".join(out)
+
+
+def test_bgzf_gzip_and_pipe_inputs(fc_aln_emul):
+    """the command line takes plain text, gzip or BGZF, from a file or from standard input; BGZF members are
+    inflated on all helper threads (text_in.hpp).  Same files as the reference's for each."""
+    need_ref_tools()
+    demo = get_demo("multi_allele")
+    text = read(demo.data.reads_fq)
+    exe = os.path.join(HERE, "emul", "fc_aln_emul")
+    env = dict(os.environ, PANSVR_ORACLE_SO=os.path.join(ROOT, "oracle", "libksw_oracle.so"))
+    forms = {"bgzf": _bgzf(text, 7001), "gzip": gzip.compress(text, 1), "gzip2": gzip.compress(text[:len(text) // 2]) + gzip.compress(text[len(text) // 2:]),
+             "plain": text}
+    for name, blob in forms.items():
+        path = os.path.join(demo.wd, "in_" + name)
+        with open(path, "wb") as f:
+            f.write(blob)
+        for how in ("file", "pipe"):
+            out, ori = os.path.join(demo.wd, f"tin_{name}_{how}.sam"), os.path.join(demo.wd, f"tin_{name}_{how}_ori.sam")
+            argv = [exe, "-t", "3", "-S", "-o", out, "-p", ori, demo.data.index_dir, path if how == "file" else "-", demo.data.header_sam]
+            with open(path, "rb") as f:
+                subprocess.check_call(argv, env=env, stdin=f if how == "pipe" else subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+            assert first_diff(read(out), read(demo.ref_sam)) is None, (name, how)
+            assert read(ori) == read(demo.ref_ori), (name, how)
+    # a damaged BGZF member is an error, not silently shorter input
+    bad = bytearray(forms["bgzf"]); bad[len(bad) // 2] ^= 0x55
+    path = os.path.join(demo.wd, "in_bad")
+    with open(path, "wb") as f:
+        f.write(bytes(bad))
+    p = subprocess.run([exe, "-t", "2", "-S", "-o", os.path.join(demo.wd, "bad.sam"), "-p", os.path.join(demo.wd, "bad_ori.sam"), demo.data.index_dir, path,
+                        demo.data.header_sam], env=env, capture_output=True)
+    assert p.returncode != 0 and b"BGZF" in p.stderr
