@@ -340,9 +340,10 @@ def main():
     p_seed_ms, p_ksw_ms, p_stage_ms, p_cells, p_probes, p_hits = pmx[:6]
     ksw_gcups = p_cells / (p_ksw_ms * 1e-3) / 1e9 if p_ksw_ms > 0 else 0.0
     ksw_gops = ksw_gcups * OPS_PER_CELL
-    # seeding: SURVEY 8d byte model; the two passes (count, fill) each make every probe
+    # seeding: SURVEY 8d byte model (every probe made once: the counting pass keeps the MEMs it finds), plus the copy of each MEM
+    # (32 B read + 32 B written) to its place in the dense list
     hits = tot["mems"]
-    seed_bytes = 2 * ((p_probes - min(p_hits, p_probes)) * SEED_BYTES_MISS + p_hits * SEED_BYTES_HIT)
+    seed_bytes = (p_probes - min(p_hits, p_probes)) * SEED_BYTES_MISS + p_hits * (SEED_BYTES_HIT + 64)
     seed_gbs = seed_bytes / (p_seed_ms * 1e-3) / 1e9 if p_seed_ms > 0 else 0.0
     line = {
         "metric": METRIC, "value": reads_s, "unit": "reads/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -367,10 +368,10 @@ def main():
                      "pipe_peaks_gops": pipes, "frac_of": {k: (ksw_gops / v if v else None) for k, v in pipes.items()},
                      "peak_source": "pansvr_int_pipe_peaks measured live on this GPU ('mixed' = IADD3/LOP3/VIMNMX chains; ALU pipe, FMA pipe and both together alongside)",
                      "traffic": None},
-        "roofline_seed": {"bound": "hbm", "kernel": "seed_count_kernel_probes + seed_fill_kernel (stage B)", "achieved": seed_gbs,
+        "roofline_seed": {"bound": "hbm", "kernel": "for_each_kernel<FnSeed> + for_each_kernel<FnSeedPlace> (stage B)", "achieved": seed_gbs,
                           "peak": peaks.get("hbm_gbs"), "unit": "GB/s", "frac": seed_gbs / peaks["hbm_gbs"] if peaks.get("hbm_gbs") else None,
                           "kernel_ms_per_step": p_seed_ms, "probes_per_step": tot["seed_probes"] / args.steps,
-                          "hits_per_step": hits / args.steps, "bytes_model": f"{SEED_BYTES_MISS} B per miss probe, {SEED_BYTES_HIT} B per hit, both passes (SURVEY.md 8d)",
+                          "hits_per_step": hits / args.steps, "bytes_model": f"{SEED_BYTES_MISS} B per miss probe, {SEED_BYTES_HIT} B per hit (SURVEY.md 8d), 64 B per MEM moved to the dense list",
                           "peak_source": peak_src, "traffic": None},
         "clocks": clocks,
         "wall_ms_per_step": {"resident": wall_ms / args.steps, "e2e": e_wall_ms / args.steps},

@@ -101,9 +101,9 @@ int pansvr_ksw_extd2_batch(pansvr_ksw_ctx *ctx, int64_t n,
                            int32_t *results, uint32_t *cigar, int32_t cigar_cap);
 
 /* Same, with every array already resident in device memory (DEVICE pointers) and the results
- * left there; only the small per-task plan is built on the host from host copies of the
- * lengths.  Used when the sequences were produced on the GPU (seed/chain stage) and for
- * kernel-only timing. */
+ * left there.  The per-task plan (kernel variant, order) is made on the device from the lengths
+ * there; h_qlen / h_tlen (host copies of the lengths) are not read any more and may be NULL.
+ * Used when the sequences were produced on the GPU (seed/chain stage) and for kernel-only timing. */
 int pansvr_ksw_extd2_batch_device(pansvr_ksw_ctx *ctx, int64_t n,
                                   const uint8_t *d_qseq, const int64_t *d_qoff, const int32_t *d_qlen,
                                   const uint8_t *d_tseq, const int64_t *d_toff, const int32_t *d_tlen,

@@ -58,6 +58,8 @@ struct OutPool {
 OutPool g_out_pool;
 }
 
+extern "C" int pansvr_ksw_create_prio(int device, int high_priority, pansvr_ksw_ctx **out);   // ksw_batch.cu (not in the public header)
+
 struct pansvr_aln_ctx {
 	DebgaIndex idx;
 	AlnOptions opt;
@@ -244,7 +246,7 @@ int pansvr_aln_create(const char *index_dir, const char *header_sam, const pansv
 	bool idx_ok = false;
 	std::string idx_err;
 	std::thread loader([&]() { idx_ok = c->idx.load(index_dir, header_sam, idx_err); });
-	const int ksw_rc = pansvr_ksw_create(device, &c->ksw);
+	const int ksw_rc = pansvr_ksw_create_prio(device, 1, &c->ksw);     // the host path's context: its few tasks go ahead of the bulk kernels
 	lap("ksw context (CUDA init)");
 	loader.join();
 	lap("index files (remainder)");
@@ -484,10 +486,11 @@ int run_block(pansvr_aln_ctx *c, Piece *pieces, size_t n_pieces, std::vector<Par
 		}
 		S.ok = c->pipe->align_block(S.recs, 2 * S.pairs, bo, S.err, S.seq) ? 1 : 0;
 	};
-	// a few in flight (their device trips and host passes overlap); all of them while the context waits for another process's
+	// eight in flight per device (their device trips and host passes overlap; at most three of them in their first trip at a time,
+	// pipeline.hpp: trip1_cap_); all of them while the context waits for another process's
 	// stream state (pansvr_aln_await_state), so that only the in-order passes wait and every other stage of the shard is done by
 	// the time the state arrives
-	size_t flight = c->pipe->has_device_stages() ? (chained ? 8 : 5) * c->pipe->n_devices() : 2;
+	size_t flight = c->pipe->has_device_stages() ? 8 * c->pipe->n_devices() : 2;
 	if (const char *e = getenv("PANSVR_FLIGHT")) { const long v = atol(e); if (v > 0) flight = (size_t)v; }
 	if (c->pipe->awaiting_streams()) flight = (size_t)-1;
 	double t_cut = 0;

@@ -150,10 +150,10 @@ SEED_HD void dev_msort(DevRes *b, DevRes *tmp, int n, After after)
 struct AfterChain { SEED_HD int operator()(const DevRes &x, const DevRes &y) const { return x.chain_score != y.chain_score ? x.chain_score < y.chain_score : x.max_index > y.max_index; } };
 struct AfterAlign { SEED_HD int operator()(const DevRes &x, const DevRes &y) const { return x.align_score != y.align_score ? x.align_score < y.align_score : x.max_index > y.max_index; } };
 
-// Returns the number of candidates left in res[] (sorted by alignment score), or -1 if a chain end was not planned (cannot happen).
-SEED_HD int dev_finish_read(const PairIndexView &ix, const ReadView &R, DevRes *res, DevTap &rnd)
+// The part of single_end_handler::align that draws (RR:416-437): up to six chain ends per strand, sorted by chain score.  Returns
+// their number; everything behind it (dev_align_chains) is a function of this list.
+SEED_HD int dev_select_chains(const PairIndexView &ix, const ReadView &R, DevRes *res, DevTap &rnd, uint32_t *max_chain_out)
 {
-	if (R.ori.skip) return 0;
 	for (int s = 0; s < 2; ++s) for (uint32_t i = 0; i < R.n[s]; ++i) R.used[s][i] = 0;
 	int result_num = 0;
 	uint32_t max_chain = 0;
@@ -171,6 +171,14 @@ SEED_HD int dev_finish_read(const PairIndexView &ix, const ReadView &R, DevRes *
 	}
 	DevRes tmp[PR_MAX_RES];
 	dev_msort<4>(res, tmp, result_num, AfterChain());
+	*max_chain_out = max_chain;
+	return result_num;
+}
+
+// The rest of it (RR:438-475): alignment scores of the chosen chain ends, sort, anchor coordinates, mapq.  Returns the number of
+// candidates left in res[] (sorted by alignment score), or -1 if a chain end was not planned (cannot happen).
+SEED_HD int dev_align_chains(const PairIndexView &ix, const ReadView &R, DevRes *res, int result_num, uint32_t max_chain)
+{
 	if (result_num == 0 || max_chain < (uint32_t)ST_MIN_CHAIN_SCORE) return result_num;
 	for (int k = 0; k < result_num; ++k) {
 		DevRes &c = res[k];
@@ -189,6 +197,7 @@ SEED_HD int dev_finish_read(const PairIndexView &ix, const ReadView &R, DevRes *
 		c.cigar_ok = (uint8_t)cd.cigar_ok;
 		c.cand = (int32_t)lo;
 	}
+	DevRes tmp[PR_MAX_RES];
 	dev_msort<4>(res, tmp, result_num, AfterAlign());
 	if (result_num == 0) return 0;
 	if (res[0].align_score < (uint32_t)PR_MIN_ALN_SCORE) return 0;
@@ -206,6 +215,14 @@ SEED_HD int dev_finish_read(const PairIndexView &ix, const ReadView &R, DevRes *
 	return result_num;
 }
 
+SEED_HD int dev_finish_read(const PairIndexView &ix, const ReadView &R, DevRes *res, DevTap &rnd)
+{
+	if (R.ori.skip) return 0;
+	uint32_t max_chain = 0;
+	const int n = dev_select_chains(ix, R, res, rnd, &max_chain);
+	return dev_align_chains(ix, R, res, n, max_chain);
+}
+
 SEED_HD bool dev_same_results(const DevRes *a, int na, const DevRes *b, int nb)
 {
 	if (na != nb) return false;
@@ -217,35 +234,43 @@ SEED_HD bool dev_same_results(const DevRes *a, int na, const DevRes *b, int nb)
 	return true;
 }
 
-// explore_read of pipeline.cpp: the number of draws the read makes if every outcome of its ties leaves the same candidates,
-// else -1.  res / *n_res = the candidates.
+// explore_read of pipeline.cpp: the number of draws the read makes if every outcome of its ties chooses the same chain ends (then
+// everything behind the choice is the same too), else -1.  res / *n_res = the candidates.  Only the drawing part of the read's
+// finish is run again for the other outcomes.
 SEED_HD int dev_explore_read(const PairIndexView &ix, const ReadView &R, DevRes *res, int *n_res, DevTap &probe)
 {
 	probe.restart(0);
-	int n0 = dev_finish_read(ix, R, res, probe);
-	if (n0 < 0 || probe.too_deep) return -1;
-	*n_res = n0;
+	*n_res = 0;
+	if (R.ori.skip) return 0;
+	uint32_t max_chain = 0;
+	const int n_sel = dev_select_chains(ix, R, res, probe, &max_chain);
+	if (probe.too_deep) return -1;
 	const uint32_t c0 = probe.calls;
-	if (c0 == 0) return 0;
-	uint8_t choice[PR_MAX_SCRIPT], mod[PR_MAX_SCRIPT];
-	for (int k = 0; k < PR_MAX_SCRIPT; ++k) { choice[k] = 0; mod[k] = k < (int)c0 ? probe.moduli[k] : 0; }
-	uint32_t c = c0;
-	DevRes alt[PR_MAX_RES];
-	for (int leaves = 1; ; ++leaves) {
-		int p = (int)c - 1;
-		while (p >= 0 && choice[p] + 1 >= mod[p]) --p;
-		if (p < 0) break;
-		if (leaves >= PR_MAX_LEAVES) return -1;
-		++choice[p];
-		for (int k = p + 1; k < PR_MAX_SCRIPT; ++k) choice[k] = 0;
-		probe.restart((uint32_t)p + 1);
-		for (int k = 0; k <= p; ++k) probe.script[k] = choice[k];
-		const int na = dev_finish_read(ix, R, alt, probe);
-		if (na < 0 || probe.too_deep || probe.calls != c0) return -1;
-		c = probe.calls;
-		for (uint32_t k = 0; k < c; ++k) mod[k] = probe.moduli[k];
-		if (!dev_same_results(res, n0, alt, na)) return -1;
+	if (c0 != 0) {
+		uint8_t choice[PR_MAX_SCRIPT], mod[PR_MAX_SCRIPT];
+		for (int k = 0; k < PR_MAX_SCRIPT; ++k) { choice[k] = 0; mod[k] = k < (int)c0 ? probe.moduli[k] : 0; }
+		uint32_t c = c0;
+		DevRes alt[PR_MAX_RES];
+		for (int leaves = 1; ; ++leaves) {
+			int p = (int)c - 1;
+			while (p >= 0 && choice[p] + 1 >= mod[p]) --p;
+			if (p < 0) break;
+			if (leaves >= PR_MAX_LEAVES) return -1;
+			++choice[p];
+			for (int k = p + 1; k < PR_MAX_SCRIPT; ++k) choice[k] = 0;
+			probe.restart((uint32_t)p + 1);
+			for (int k = 0; k <= p; ++k) probe.script[k] = choice[k];
+			uint32_t mc = 0;
+			const int na = dev_select_chains(ix, R, alt, probe, &mc);
+			if (probe.too_deep || probe.calls != c0 || mc != max_chain) return -1;
+			c = probe.calls;
+			for (uint32_t k = 0; k < c; ++k) mod[k] = probe.moduli[k];
+			if (!dev_same_results(res, n_sel, alt, na)) return -1;
+		}
 	}
+	const int n0 = dev_align_chains(ix, R, res, n_sel, max_chain);
+	if (n0 < 0) return -1;
+	*n_res = n0;
 	return (int)c0;
 }
 

@@ -1144,6 +1144,7 @@ AlnPipeline::AlnPipeline(const DebgaIndex &idx, const AlnOptions &o, SeedService
 		dev_all_.push_back(b); dev_free_.push_back(b);
 	}
 	sites_.push_back(DevSite{device_, seeds_});
+	if (const char *e = getenv("PANSVR_TRIP1")) { const int v = atoi(e); if (v > 0) trip1_cap_ = v; }
 	reset();
 }
 
@@ -1741,6 +1742,7 @@ bool AlnPipeline::align_block_host(const FastqRec *recs, size_t n_reads_in, Bloc
 	}
 	turn.pass();                                                          // the next block may replay now
 	{ std::lock_guard<std::mutex> lk(stats_m_); stats.t_in_order += now() - t_turn; stats.in_order_pairs += n_redo; }
+	if (getenv("PANSVR_TRACE")) fprintf(stderr, "T %llu in_order %.6f %.6f\n", (unsigned long long)seq, t_turn, now());
 	parallel(n_pairs, [&](size_t pb, size_t pe_, int) {                    // winners of the redrawn pairings
 		for (size_t pi = pb; pi < pe_; ++pi) {
 			if (redo[pi] != 2) continue;
@@ -1803,8 +1805,21 @@ bool AlnPipeline::align_block_text(const char *text, size_t bytes, size_t n_pair
 	return align_block_dev(text, bytes, nullptr, n_pairs, out, err, seq, reparse);
 }
 
+namespace {
+void trace_host(uint64_t seq, const char *what)                       // PANSVR_TRACE=<file>: host-side phase marks of every sub-block (steady clock, s)
+{
+	static const char *path = getenv("PANSVR_TRACE");
+	if (!path) return;
+	static std::mutex m; static FILE *f = nullptr;
+	std::lock_guard<std::mutex> lk(m);
+	if (!f) f = fopen((std::string(path) + ".host").c_str(), "a");
+	if (f) { fprintf(f, "H %llu %s %.6f\n", (unsigned long long)seq, what, now()); fflush(f); }
+}
+}
+
 bool AlnPipeline::align_block_dev(const char *base, size_t text_bytes, const FastqRec *recs, size_t n_pairs, BlockOutput &out, std::string &err, uint64_t seq, bool *reparse)
 {
+	trace_host(seq, "enter");
 	const size_t nd = 2 * n_pairs;
 	Impl I(*this);
 	const DebgaIndex &idx = idx_;
@@ -1844,7 +1859,23 @@ bool AlnPipeline::align_block_dev(const char *base, size_t text_bytes, const Fas
 	in.pair_opts = PairOpts{opt.isize_max, opt.isize_min, opt.read_len, min_filter_score_};
 	const char *dump = getenv("PANSVR_DUMP_STAGES");
 	in.want_tables = dump != nullptr;
-	if (!stage_service_run(db->svc, in, db->out, err)) return false;
+	{
+		const size_t site = db->site;
+		{
+			std::unique_lock<std::mutex> lk(trip1_m_);
+			if (trip1_busy_.size() <= site) { trip1_busy_.resize(site + 1, 0); trip1_wait_.resize(site + 1); }
+			trip1_wait_[site].insert(seq);                              // admitted oldest first
+			trip1_cv_.wait(lk, [&]() { return trip1_busy_[site] < trip1_cap_ && *trip1_wait_[site].begin() == seq; });
+			trip1_wait_[site].erase(seq);
+			++trip1_busy_[site];
+			lk.unlock();
+			trip1_cv_.notify_all();
+		}
+		struct Leave { AlnPipeline &P; size_t site; ~Leave() { { std::lock_guard<std::mutex> lk(P.trip1_m_); --P.trip1_busy_[site]; } P.trip1_cv_.notify_all(); } } leave{*this, site};
+		trace_host(seq, "trip1_begin");
+		if (!stage_service_run(db->svc, in, db->out, err)) return false;
+		trace_host(seq, "trip1_end");
+	}
 	DevStageOut &o = db->out;
 	if (!o.parse_ok) { if (reparse) { *reparse = true; return true; } err = "internal error: record table rejected"; return false; }
 	// a record of the block as the host path sees it
@@ -1910,8 +1941,10 @@ bool AlnPipeline::align_block_dev(const char *base, size_t text_bytes, const Fas
 		// ---- second trip: the winners go up; primary / secondary / mate of every read and the block's SAM text come back
 		bool got = false;
 		o.text_dest = [&](size_t total) -> char* { char *p = out.place ? out.place(total) : nullptr; out.place_called = true; got = p != nullptr; return p; };
+		trace_host(seq, "trip2_begin");
 		const bool fin_ok = stage_service_finalize(db->svc, in.pair_opts, opt.not_ori ? 1 : 0, n_pairs, db->drawn.data(), n_drawn, db->host_len.data(), o, out.sam_text, e2);
 		o.text_dest = nullptr;
+		trace_host(seq, "trip2_end");
 		if (!fin_ok) return false;
 		out.placed = got;
 		if (out.placed) { out.placed_bytes = o.text_total; out.placed_ptr = o.text_ptr; }
@@ -1990,6 +2023,7 @@ bool AlnPipeline::align_block_dev(const char *base, size_t text_bytes, const Fas
 		return true;
 	};
 	const bool ok = align_block_host(hrecs.data(), hrecs.size(), out, err, seq, &H);
+	trace_host(seq, "done");
 	if (ok) {
 		std::lock_guard<std::mutex> lk(stats_m_);
 		stats.reads += 2 * (n_pairs - host_list.size());

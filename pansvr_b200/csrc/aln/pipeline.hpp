@@ -31,6 +31,7 @@
 #include <mutex>
 #include <new>
 #include <map>
+#include <set>
 #include <string>
 #include <vector>
 
@@ -209,6 +210,10 @@ private:
 	DevBuffers *acquire_dev(std::string &err, uint64_t seq = 0);
 	// further GPUs of the same box: sub-block k goes to site k mod (1 + extra sites); each site has its own index replica
 	struct DevSite { int device; SeedService *seeds; };
+	// how many sub-blocks may be in their first trip on one device at a time: the trips of the sub-blocks in flight share the GPU,
+	// so the fewer run side by side the sooner the oldest one is through -- and it is the oldest one every in-order pass (of this
+	// process, and of the process that has the next piece of the input) waits for.  Second trips are not counted.
+	std::mutex trip1_m_; std::condition_variable trip1_cv_; std::vector<int> trip1_busy_; std::vector<std::set<uint64_t>> trip1_wait_; int trip1_cap_ = 3;
 	std::vector<DevSite> sites_;          // [0] = the context's first device
 public:
 	void add_device(int device, SeedService *seeds) { sites_.push_back(DevSite{device, seeds}); }

@@ -107,7 +107,10 @@ SeedService *seed_service_create(const DebgaIndex &idx, int device, std::string 
 	SeedService *s = new SeedService();
 	s->device = device;
 	auto fail = [&]() -> SeedService* { seed_service_destroy(s); return nullptr; };
-	if (cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking) != cudaSuccess) { err = "cudaStreamCreate failed"; return fail(); }
+	// (this service only runs the host path's small batches: its stream goes ahead of the bulk kernels of the sub-blocks in flight)
+	int prio_lo = 0, prio_hi = 0;
+	cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+	if (cudaStreamCreateWithPriority(&s->stream, cudaStreamNonBlocking, prio_hi) != cudaSuccess) { err = "cudaStreamCreate failed"; return fail(); }
 	for (cudaEvent_t &e : s->ev) if (cudaEventCreate(&e) != cudaSuccess) { err = "cudaEventCreate failed"; return fail(); }
 	if (cudaMalloc((void**)&s->d_probes, 8) != cudaSuccess) { err = "cudaMalloc failed"; return fail(); }
 	if (!upload(idx.seqb, s->seqb, err) || !upload(idx.seqf, s->seqf, err) || !upload(idx.posp, s->posp, err) ||

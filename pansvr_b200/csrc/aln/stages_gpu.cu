@@ -4,6 +4,9 @@
 // reads in flight -- the layout goal is that a read's data is touched once per stage and never leaves the device in between.
 #include <cuda_runtime.h>
 #include <cub/device/device_scan.cuh>
+#include <cub/device/device_radix_sort.cuh>
+#include <chrono>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -21,6 +24,12 @@ template <class F> __global__ void __launch_bounds__(128) for_each_kernel(F f, s
 {
 	const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
 	if (i < n) f(i);
+}
+
+template <class F> __global__ void __launch_bounds__(128) for_each_in_kernel(F f, const uint32_t *perm, size_t n)
+{
+	const size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (k < n) f((size_t)perm[k]);
 }
 
 // SAM text, write pass: every thread formats the short fields of its record and sets its (up to four) long copies aside; the
@@ -66,7 +75,6 @@ struct CudaBackend {
 	struct Lap { cudaEvent_t a, b; int stage; };
 	std::vector<Lap> laps;
 	pansvr_ksw_ctx *ksw_ctx = nullptr; pansvr_ksw_params_t kp; int8_t mat[25];
-	HostVec<int32_t> h_qlen, h_tlen;
 	DevCounters dev;
 	CudaBackend() { for (int i = 0; i < SL_COUNT; ++i) { p[i] = nullptr; cap[i] = 0; } }
 	void check(cudaError_t e, const char *what) { if (e != cudaSuccess && !failed) { failed = true; why = std::string(what) + ": " + cudaGetErrorString(e); } }
@@ -104,6 +112,28 @@ struct CudaBackend {
 		laps.push_back(l);
 		++dev.launches;
 	}
+	template <class F> void for_each_in(size_t n, const uint32_t *perm, const F &f, int stage)
+	{
+		if (n == 0 || failed) return;
+		Lap l; l.a = event(); l.b = event(); l.stage = stage;
+		check(cudaEventRecord(l.a, st), "cudaEventRecord");
+		for_each_in_kernel<F><<<(unsigned)((n + 127) / 128), 128, 0, st>>>(f, perm, n);
+		check(cudaGetLastError(), "kernel launch");
+		check(cudaEventRecord(l.b, st), "cudaEventRecord");
+		laps.push_back(l);
+		++dev.launches;
+	}
+	void order_desc(const uint32_t *key, const uint32_t *idx, uint32_t *perm, size_t n)
+	{
+		if (n == 0 || failed) return;
+		uint32_t *key_out = buf<uint32_t>(SL_SORT_KEYS, n);
+		size_t tmp_bytes = 0;
+		check(cub::DeviceRadixSort::SortPairsDescending(nullptr, tmp_bytes, key, key_out, idx, perm, (int)n, 0, 8, st), "cub sort size");
+		void *tmp = buf<uint8_t>(SL_SORT_TMP, tmp_bytes + 256);
+		if (!key_out || !tmp) return;
+		check(cub::DeviceRadixSort::SortPairsDescending(tmp, tmp_bytes, key, key_out, idx, perm, (int)n, 0, 8, st), "cub sort");
+		++dev.launches;
+	}
 	void encode(size_t n, const FnEncode &f)
 	{
 		if (n == 0 || failed) return;
@@ -137,24 +167,45 @@ struct CudaBackend {
 	bool ksw(size_t n, const uint8_t *q, const int64_t *qoff, const int32_t *qlen, const uint8_t *t, const int64_t *toff, const int32_t *tlen,
 	         int32_t *res, uint32_t *cig, int cigar_cap, std::string &err)
 	{
-		h_qlen.resize(n); h_tlen.resize(n);
-		d2h(h_qlen.data(), qlen, n * 4);
-		d2h(h_tlen.data(), tlen, n * 4);
 		sync();
 		if (failed) { err = why; return false; }
 		// (the ksw context has its own stream; everything it reads was produced before the sync above, and the call returns
-		// after its kernels have finished)
-		const int rc = pansvr_ksw_extd2_batch_device(ksw_ctx, (int64_t)n, q, qoff, qlen, t, toff, tlen, h_qlen.data(), h_tlen.data(), &kp, res, cig, cigar_cap);
+		// after its kernels have finished; the per-task plan is made on the device from the lengths there)
+		const double th0 = std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+		const int rc = pansvr_ksw_extd2_batch_device(ksw_ctx, (int64_t)n, q, qoff, qlen, t, toff, tlen, nullptr, nullptr, &kp, res, cig, cigar_cap);
+		{
+			FILE *tf = nullptr;
+			if (trace_ref(st, &tf) && tf) fprintf(tf, "E %p %.6f %.6f %zu\n", (void*)this, th0, std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(), n);
+		}
 		if (rc != 0) { err = std::string("ksw batch: ") + pansvr_last_error(); return false; }
 		pansvr_ksw_stats_t ks;
 		if (pansvr_ksw_last_stats(ksw_ctx, &ks) == 0) { dev.launches += ks.kernel_launches; dev.h2d_bytes += ks.h2d_bytes; dev.ksw_kernel_ms += ks.kernel_ms; }
 		return true;
 	}
+	// PANSVR_TRACE=<file>: every timed kernel of every sub-block with its start and end on one clock (ms since the first use), to see
+	// what the device did when (diagnostics; the events exist anyway)
+	static cudaEvent_t trace_ref(cudaStream_t st, FILE **fp)
+	{
+		static std::mutex m; static cudaEvent_t ref = nullptr; static FILE *f = nullptr; static bool tried = false;
+		std::lock_guard<std::mutex> lk(m);
+		if (!tried) {
+			tried = true;
+			if (const char *path = getenv("PANSVR_TRACE")) {
+				f = fopen(path, "a");
+				if (f && cudaEventCreate(&ref) == cudaSuccess) { cudaEventRecord(ref, st); cudaEventSynchronize(ref); fprintf(f, "# ref %.6f\n", std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count()); }
+			}
+		}
+		*fp = f;
+		return ref;
+	}
 	void collect_laps()
 	{
+		FILE *tf = nullptr;
+		cudaEvent_t ref = trace_ref(st, &tf);
 		for (const Lap &l : laps) {
 			float ms = 0;
 			if (cudaEventElapsedTime(&ms, l.a, l.b) != cudaSuccess) continue;
+			if (ref && tf) { float t0 = 0; if (cudaEventElapsedTime(&t0, ref, l.a) == cudaSuccess) fprintf(tf, "K %p %d %.3f %.3f\n", (void*)this, l.stage, t0, t0 + ms); }
 			if (l.stage == 1) dev.seed_kernel_ms += ms; else dev.stage_kernel_ms += ms;
 			if (l.stage >= 0 && l.stage < 8) dev.by_stage_ms[l.stage] += ms;
 		}

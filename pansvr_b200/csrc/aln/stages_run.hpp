@@ -13,6 +13,8 @@
 //   void zero(void *d, size_t bytes)
 //   void sync()                                           wait for everything issued so far
 //   template <class F> void for_each(size_t n, const F &f, int stage)    f(i) for i in [0, n); `stage` labels the timing
+//   template <class F> void for_each_in(size_t n, const uint32_t *perm, const F &f, int stage)    f(perm[k]) for k in [0, n)
+//   void order_desc(const uint32_t *key, const uint32_t *idx, uint32_t *perm, size_t n)   perm = idx sorted by key (< 256), largest first
 //   void encode(size_t n, const FnEncode &f)                             f.run(i, scratch, stride) for i in [0, n) (stage A; the backend owns the scratch)
 //   void scan(const uint32_t *in, uint32_t *out, size_t n)               exclusive prefix sums, n elements
 //   bool ksw(n, q, qoff, qlen, t, toff, tlen, res, cig, cap, err)        ksw_extd2 batch (w=200, the stage's scoring) over device arrays
@@ -29,7 +31,7 @@ namespace pansvr {
 enum DevSlot {
 	SL_TEXT, SL_READS, SL_BITS, SL_LIST, SL_FLAGS, SL_MEM_CNT, SL_MEM_OFF, SL_MEMS, SL_MEMS_TMP, SL_NVU, SL_SEED_CNT, SL_SEED_OFF,
 	SL_SEEDS, SL_SEEDS_TMP, SL_DIST, SL_PRE, SL_PLAN_CNT, SL_PLAN_OFF, SL_CANDS, SL_PIECES, SL_QLEN, SL_TLEN, SL_QOFF, SL_TOFF,
-	SL_Q, SL_T, SL_RES, SL_KCIG, SL_CIGS, SL_MISC, SL_SCAN_TMP, SL_USED, SL_ORI, SL_PSTATE, SL_PROBE, SL_WIN, SL_FINAL, SL_PFINAL, SL_RECS, SL_HOSTLEN, SL_TXT_LEN, SL_TXT_OFF, SL_TXT, SL_NL_CNT, SL_NL_OFF, SL_LINES, SL_LAY_CNT, SL_LAY_OFF, SL_SEL_PAIR, SL_SEL_FIN, SL_SEL_PFIN, SL_DRAW_CNT, SL_DRAW_OFF, SL_REDO, SL_DRAWN, SL_COUNT
+	SL_Q, SL_T, SL_RES, SL_KCIG, SL_CIGS, SL_MISC, SL_SCAN_TMP, SL_USED, SL_ORI, SL_PSTATE, SL_PROBE, SL_WIN, SL_FINAL, SL_PFINAL, SL_RECS, SL_HOSTLEN, SL_TXT_LEN, SL_TXT_OFF, SL_TXT, SL_NL_CNT, SL_NL_OFF, SL_LINES, SL_LAY_CNT, SL_LAY_OFF, SL_SEL_PAIR, SL_SEL_FIN, SL_SEL_PFIN, SL_DRAW_CNT, SL_DRAW_OFF, SL_REDO, SL_DRAWN, SL_MEMS_KEPT, SL_WORK_KEY, SL_WORK_IDX, SL_WORK_PERM, SL_SORT_KEYS, SL_SORT_TMP, SL_COUNT
 };
 
 // ---- functors (one element of work each; plain data members only, so they can be passed to a kernel by value)
@@ -124,29 +126,38 @@ struct FnEncode {
 	}
 	SEED_HD void operator()(size_t i) const { uint32_t filter[ENC_FILTER_WORDS]; run(i, filter, 1); }
 };
-struct FnSeed {                                                    // strand j = 2 * read + strand; fill == false: count only
+enum { SEED_TMP_CAP = 8 };                                         // MEMs per strand kept by the counting pass (most strands have fewer)
+struct FnSeed {                                                    // strand j = 2 * read + strand: its MEMs counted, the first SEED_TMP_CAP of them kept in tmp
 	IndexView ix; const DevRead *reads; const uint64_t *bits; const uint8_t *list; const uint8_t *flags;
-	uint32_t *count; const uint32_t *off; Mem *mems; unsigned long long *probes; bool fill;
+	uint32_t *count; Mem *tmp; unsigned long long *probes;
 	SEED_HD void operator()(size_t j) const
 	{
 		const DevRead &rd = reads[j >> 1];
-		if (flags[j >> 1] & (ST_FLAG_HOST | ST_FLAG_NOSEED)) { if (!fill) count[j] = 0; return; }
+		if (flags[j >> 1] & (ST_FLAG_HOST | ST_FLAG_NOSEED)) { count[j] = 0; return; }
 		const uint32_t s = (uint32_t)(j & 1), words = (rd.len >> 5) + 2, kn = rd.len - LEN_KMER + 1;
 		const uint64_t *b = bits + rd.bits_off + (size_t)s * words;
 		const bool is_str = (flags[j >> 1] & ST_FLAG_STR) != 0;
 		const uint8_t *sl = list + rd.list_off + (size_t)s * kn;
-		if (!fill) {
-			uint32_t p = 0;
-			count[j] = (uint32_t)seed_read_strand(ix, b, rd.len, is_str, sl, (Mem*)nullptr, 0, &p);
+		uint32_t p = 0;
+		count[j] = (uint32_t)seed_read_strand(ix, b, rd.len, is_str, sl, tmp + j * SEED_TMP_CAP, SEED_TMP_CAP, &p);
 #if defined(__CUDA_ARCH__)
-			if (p) atomicAdd(probes, (unsigned long long)p);
+		if (p) atomicAdd(probes, (unsigned long long)p);
 #else
-			*probes += p;
+		*probes += p;
 #endif
-		} else {
-			const int cap = (int)(off[j + 1] - off[j]);
-			if (cap > 0) seed_read_strand(ix, b, rd.len, is_str, sl, mems + off[j], cap);
-		}
+	}
+};
+struct FnSeedPlace {                                               // the strand's MEMs to their place in the dense list: copied, or found again if there were more than kept
+	IndexView ix; const DevRead *reads; const uint64_t *bits; const uint8_t *list; const uint8_t *flags;
+	const uint32_t *off; const Mem *tmp; Mem *mems;
+	SEED_HD void operator()(size_t j) const
+	{
+		const uint32_t n = off[j + 1] - off[j];
+		if (n == 0) return;
+		if (n <= (uint32_t)SEED_TMP_CAP) { for (uint32_t k = 0; k < n; ++k) mems[off[j] + k] = tmp[j * SEED_TMP_CAP + k]; return; }
+		const DevRead &rd = reads[j >> 1];
+		const uint32_t s = (uint32_t)(j & 1), words = (rd.len >> 5) + 2, kn = rd.len - LEN_KMER + 1;
+		seed_read_strand(ix, bits + rd.bits_off + (size_t)s * words, rd.len, (flags[j >> 1] & ST_FLAG_STR) != 0, list + rd.list_off + (size_t)s * kn, mems + off[j], (int)n);
 	}
 };
 struct FnMerge {                                                   // per read: both strands
@@ -181,6 +192,10 @@ struct FnChain {
 			             seeds + sb, tmp + sb, n, dist + sb, pre + sb);
 		}
 	}
+};
+struct FnWorkKey {                                                 // how much the per-read stages behind chaining have to do for read i: its seeds (at most 255)
+	const uint32_t *seed_off; uint32_t *key, *idx;
+	SEED_HD void operator()(size_t i) const { const uint32_t n = seed_off[2 * i + 2] - seed_off[2 * i]; key[i] = n < 255u ? n : 255u; idx[i] = (uint32_t)i; }
 };
 enum { PLAN_FIELDS = 6 };                                          // cands, pieces, tasks, q bytes, t bytes, CIGAR room
 struct FnPlan {
@@ -396,8 +411,9 @@ bool run_device_stages(BE &be, const IndexView &ix, const uint64_t *d_pos, const
 	be.encode(n, FnEncode{d_text, d_reads, d_ori, d_bits, d_list, d_flags});
 	// ---- B
 	unsigned long long *d_probes = (unsigned long long*)(d_misc + 2);
-	FnSeed fs{ix, d_reads, d_bits, d_list, d_flags, d_mem_cnt, d_mem_off, nullptr, d_probes, false};
-	be.for_each(2 * n, fs, 1);
+	Mem *d_mems_kept = be.template buf<Mem>(SL_MEMS_KEPT, 2 * n * (size_t)SEED_TMP_CAP);
+	if (!d_mems_kept) { err = "device stages: out of device memory"; return false; }
+	be.for_each(2 * n, FnSeed{ix, d_reads, d_bits, d_list, d_flags, d_mem_cnt, d_mems_kept, d_probes}, 1);
 	be.scan(d_mem_cnt, d_mem_off, 2 * n + 1);
 	be.d2h(out.mem_off.data(), d_mem_off, (2 * n + 1) * 4);
 	be.sync();
@@ -406,8 +422,7 @@ bool run_device_stages(BE &be, const IndexView &ix, const uint64_t *d_pos, const
 	uint32_t *d_nvu = be.template buf<uint32_t>(SL_NVU, 2 * n), *d_seed_cnt = be.template buf<uint32_t>(SL_SEED_CNT, 2 * n + 1);
 	uint32_t *d_seed_off = be.template buf<uint32_t>(SL_SEED_OFF, 2 * n + 1);
 	if (!d_mems || !d_mems_tmp || !d_nvu || !d_seed_cnt || !d_seed_off) { err = "device stages: out of device memory"; return false; }
-	fs.mems = d_mems; fs.fill = true;
-	be.for_each(2 * n, fs, 1);
+	be.for_each(2 * n, FnSeedPlace{ix, d_reads, d_bits, d_list, d_flags, d_mem_off, d_mems_kept, d_mems}, 1);
 	// ---- C
 	be.zero(d_seed_cnt + 2 * n, 4);
 	be.for_each(n, FnMerge{d_mem_off, d_mems, d_mems_tmp, d_flags, d_nvu, d_seed_cnt}, 2);
@@ -432,13 +447,20 @@ bool run_device_stages(BE &be, const IndexView &ix, const uint64_t *d_pos, const
 		be.d2h(out.dist.data(), d_dist, n_seeds * 4);
 		be.d2h(out.pre.data(), d_pre, n_seeds * 4);
 	}
+	// the per-read kernels from here on (planning, chain selection) do work that grows with the read's seeds, from nothing to tens of
+	// thousands of instructions: they visit the reads in the order of their seed counts, heaviest first, so that the threads of a warp
+	// have about the same to do (results are written per read: the order changes nothing else)
+	uint32_t *d_wkey = be.template buf<uint32_t>(SL_WORK_KEY, n), *d_widx = be.template buf<uint32_t>(SL_WORK_IDX, n), *d_perm = be.template buf<uint32_t>(SL_WORK_PERM, n);
+	if (!d_wkey || !d_widx || !d_perm) { err = "device stages: out of device memory"; return false; }
+	be.for_each(n, FnWorkKey{d_seed_off, d_wkey, d_widx}, 3);
+	be.order_desc(d_wkey, d_widx, d_perm, n);
 	// ---- D: count, offsets, fill
 	int cap = 16;
 	for (;;) {                                                     // (again with more room if a ksw CIGAR does not fit `cap` words)
 		be.zero(d_plan_cnt, PLAN_FIELDS * P * 4);
 		FnPlan fp{in.scores, rf, d_reads, d_bits, d_seed_off, d_seeds, d_dist, d_pre, n, d_plan_cnt, d_plan_off,
 		          nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, (uint32_t)cap, false};
-		be.for_each(n, fp, 3);
+		be.for_each_in(n, d_perm, fp, 3);
 		for (int f = 0; f < PLAN_FIELDS; ++f) be.scan(d_plan_cnt + f * P, d_plan_off + f * P, P);
 		uint32_t tot[PLAN_FIELDS];
 		for (int f = 0; f < PLAN_FIELDS; ++f) be.d2h(&tot[f], d_plan_off + f * P + n, 4);
@@ -455,7 +477,7 @@ bool run_device_stages(BE &be, const IndexView &ix, const uint64_t *d_pos, const
 		DevCigar *d_cigs = be.template buf<DevCigar>(SL_CIGS, n_cig + 1);
 		if (!d_cands || !d_pieces || !d_qlen || !d_tlen || !d_qoff || !d_toff || !d_q || !d_t || !d_res || !d_kcig || !d_cigs) { err = "device stages: out of device memory"; return false; }
 		fp.cands = d_cands; fp.pieces = d_pieces; fp.qlen = d_qlen; fp.tlen = d_tlen; fp.qoff = d_qoff; fp.toff = d_toff; fp.q = d_q; fp.t = d_t; fp.fill = true;
-		be.for_each(n, fp, 3);
+		be.for_each_in(n, d_perm, fp, 3);
 		unsigned long long *d_cells = (unsigned long long*)(d_misc + 4);
 		be.zero(d_cells, 8);
 		if (n_task) be.for_each(n_task, FnCells{d_qlen, d_tlen, 200, d_cells}, 5);
@@ -485,7 +507,7 @@ bool run_device_stages(BE &be, const IndexView &ix, const uint64_t *d_pos, const
 		DevPairState *d_state = be.template buf<DevPairState>(SL_PSTATE, np);
 		DevProbe *d_probe = be.template buf<DevProbe>(SL_PROBE, np);
 		if (!d_used || !d_state || !d_probe) { err = "device stages: out of device memory"; return false; }
-		be.for_each(n, FnExplore{pix, d_flags, d_seed_off, d_seeds, d_dist, d_pre, d_used, d_plan_off, be.template buf<DevCand>(SL_CANDS, 0), d_ori, d_state}, 6);
+		be.for_each_in(n, d_perm, FnExplore{pix, d_flags, d_seed_off, d_seeds, d_dist, d_pre, d_used, d_plan_off, be.template buf<DevCand>(SL_CANDS, 0), d_ori, d_state}, 6);
 		uint32_t *d_dcnt = be.template buf<uint32_t>(SL_DRAW_CNT, np + 1), *d_doff = be.template buf<uint32_t>(SL_DRAW_OFF, np + 1);
 		uint8_t *d_redo = be.template buf<uint8_t>(SL_REDO, np);
 		if (!d_dcnt || !d_doff || !d_redo) { err = "device stages: out of device memory"; return false; }

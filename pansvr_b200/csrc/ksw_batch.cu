@@ -13,7 +13,6 @@
 #include <string.h>
 #include <algorithm>
 #include <string>
-#include <unordered_map>
 #include <vector>
 
 #include "../../include/pansvr_b200.h"
@@ -171,114 +170,142 @@ struct pansvr_ksw_ctx {
 	cudaStream_t vstream[4] = {nullptr, nullptr, nullptr, nullptr};
 	cudaEvent_t vev_in = nullptr, vev_done[4] = {nullptr, nullptr, nullptr, nullptr};
 	cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
-	DevBuf qseq, tseq, qoff, toff, qlen, tlen, res, cigar, order, counters, tb, gscratch;
+	DevBuf qseq, tseq, qoff, toff, qlen, tlen, res, cigar, order, counters, tb, gscratch, plan_variant, plan_rows, plan_stats;
 	DevBuf tb_v[16];                 // traceback scratch per variant (they run concurrently)
-	std::vector<int> h_order;
-	std::vector<uint8_t> h_variant;
-	std::vector<int> h_rows;
 	pansvr_ksw_stats_t stats;
 };
 
 namespace {
 
-struct Shape { int rows, team; };
+// The per-task plan of a batch, made on the device from the lengths that are there anyway: the kernel variant of every task,
+// task ids grouped by variant and, inside a variant, by anti-diagonal count (most first: 256 levels), per-variant counts and the
+// largest row count / query / target length.  Four small kernels and one 240-byte download; the order inside a level is whatever
+// the atomics give (results do not depend on it: every task writes its own row of the result arrays).
+struct BatchPlan {
+	bool identity;               // every task has the same shape: one variant, tasks in input order, no order[]
+	int begin[N_VARIANTS + 1];
+	int max_rows[N_VARIANTS], max_qlen[N_VARIANTS], max_tlen[N_VARIANTS];
+};
+enum { PS_COUNT = 0, PS_ROWS = N_VARIANTS, PS_QLEN = 2 * N_VARIANTS, PS_TLEN = 3 * N_VARIANTS, PS_UNIFORM = 4 * N_VARIANTS, PS_WORDS = 4 * N_VARIANTS + 4 };
+struct PlanArgs { int n; const int32_t *qlen, *tlen; int w; int trivial, fast_params, nowrap_ok, smem_optin; uint8_t *variant; int *rows; int *stats; int *bins; int *order; };
 
-// Dynamic shared memory of a team-kernel launch whose longest query is `qlen` (launch_team_wc): a long query against a
-// narrow band (few lanes per alignment, so many alignments and query copies per warp) can exceed what a CTA may have; such
-// tasks go to the generic kernel instead.
-inline bool team_fits(int team, int qlen, int smem_optin)
+__device__ __forceinline__ bool d_team_fits(int team, int qlen, int smem_optin)
 {
 	const long per_cta = ((long)kswteam::team_smem_bytes(team, qlen) * (32 / team) + 32 * 32) * WARPS_PER_CTA + 512;
 	return per_cta <= (long)smem_optin;
 }
 
-// Builds ctx->h_order (task ids grouped by kernel variant, most anti-diagonals first inside a
-// group) and returns per-variant [begin,end) plus the largest row count / query length per variant.
-struct BatchPlan {
-	bool identity;               // every task has the same shape: one variant, tasks in input order, no order[] upload
-	int begin[N_VARIANTS + 1];
-	int max_rows[N_VARIANTS], max_qlen[N_VARIANTS], max_tlen[N_VARIANTS];
-};
-
-void plan_batch(pansvr_ksw_ctx *ctx, const kswhost::Plan &pl, int64_t n, const int32_t *qlen, const int32_t *tlen, BatchPlan &bp)
+__global__ void __launch_bounds__(256) plan_classify_kernel(PlanArgs a)
 {
-	const int w = pl.P.w;
-	bp.identity = false;
-	{   // uniform batches (the common benchmark / fixed-read-length case) need no per-task plan at all
-		const int q0 = qlen[0], t0 = tlen[0];
-		int64_t i = 1;
-		while (i < n && qlen[i] == q0 && tlen[i] == t0) ++i;
-		if (i == n && !pl.trivial && q0 > 0 && t0 > 0 && pl.fast_params && q0 <= 8000) {
-			const int team = kswhost::pick_team(q0, t0, w);
-			if (team != 0 && team_fits(team, q0, ctx->smem_optin)) {
-				const bool wrap = !pl.nowrap_ok || kswhost::band_clips(q0, t0, w);
+	__shared__ int s_stat[4 * N_VARIANTS];
+	__shared__ int s_uniform;
+	for (int k = threadIdx.x; k < 4 * N_VARIANTS; k += blockDim.x) s_stat[k] = 0;
+	if (threadIdx.x == 0) s_uniform = 1;
+	__syncthreads();
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < a.n) {
+		const int ql = a.qlen[i], tl = a.tlen[i];
+		int v, rows = 0;
+		if (a.trivial || ql <= 0 || tl <= 0) v = V_TRIVIAL;
+		else {
+			rows = kswhost::n_diagonals(ql, tl, a.w);
+			const int team = kswhost::pick_team(ql, tl, a.w);
+			if (!a.fast_params || team == 0 || ql > 8000 || !d_team_fits(team, ql, a.smem_optin)) v = V_GENERIC;
+			else {
+				const bool wrap = !a.nowrap_ok || kswhost::band_clips(ql, tl, a.w);
 				int lg = 0;
 				while ((2 << lg) < team) ++lg;
-				const int v = V_FAST0 + 2 * lg + (wrap ? 1 : 0);
-				for (int k = 0; k < N_VARIANTS; ++k) { bp.max_rows[k] = bp.max_qlen[k] = bp.max_tlen[k] = 0; bp.begin[k] = k <= v ? 0 : (int)n; }
-				bp.begin[N_VARIANTS] = (int)n;
-				bp.max_rows[v] = kswhost::n_diagonals(q0, t0, w); bp.max_qlen[v] = q0; bp.max_tlen[v] = t0;
-				bp.identity = true;
-				return;
-			}
-		}
-	}
-	ctx->h_variant.resize(n);
-	ctx->h_rows.resize(n);
-	ctx->h_order.resize(n);
-	std::unordered_map<uint64_t, Shape> memo;                  // shapes beyond the direct table
-	enum { DIRECT = 512 };                                     // (qlen, tlen) below this: one table look-up per task (the fc_aln task mix)
-	static thread_local std::vector<Shape> direct;
-	static thread_local int direct_w = -0x7fffffff;
-	if (direct.empty() || direct_w != w) { direct.assign((size_t)DIRECT * DIRECT, Shape{-1, 0}); direct_w = w; }
-	uint64_t last_key = ~0ull; Shape last{0, 0};
-	int64_t count[N_VARIANTS];
-	memset(count, 0, sizeof(count));
-	for (int v = 0; v < N_VARIANTS; ++v) bp.max_rows[v] = bp.max_qlen[v] = bp.max_tlen[v] = 0;
-	for (int64_t i = 0; i < n; ++i) {
-		const int ql = qlen[i], tl = tlen[i];
-		int v;
-		Shape sh{0, 0};
-		if (pl.trivial || ql <= 0 || tl <= 0) v = V_TRIVIAL;
-		else {
-			const uint64_t key = (uint64_t)(uint32_t)ql << 32 | (uint32_t)tl;
-			if (key == last_key) sh = last;
-			else {
-				auto it = memo.find(key);
-				if (it == memo.end()) {
-					sh.rows = kswhost::n_diagonals(ql, tl, w);
-					sh.team = kswhost::pick_team(ql, tl, w);
-					memo.emplace(key, sh);
-				} else sh = it->second;
-				last_key = key; last = sh;
-			}
-			if (!pl.fast_params || sh.team == 0 || ql > 8000 || !team_fits(sh.team, ql, ctx->smem_optin)) v = V_GENERIC;
-			else {
-				const bool wrap = !pl.nowrap_ok || kswhost::band_clips(ql, tl, w);
-				int lg = 0;
-				while ((2 << lg) < sh.team) ++lg;
 				v = V_FAST0 + 2 * lg + (wrap ? 1 : 0);
 			}
 		}
-		ctx->h_variant[i] = (uint8_t)v;
-		ctx->h_rows[i] = sh.rows;
-		++count[v];
-		bp.max_rows[v] = std::max(bp.max_rows[v], sh.rows);
-		bp.max_qlen[v] = std::max(bp.max_qlen[v], ql);
-		bp.max_tlen[v] = std::max(bp.max_tlen[v], tl);
+		a.variant[i] = (uint8_t)v; a.rows[i] = rows;
+		atomicAdd(&s_stat[PS_COUNT + v], 1);
+		atomicMax(&s_stat[PS_ROWS + v], rows); atomicMax(&s_stat[PS_QLEN + v], ql); atomicMax(&s_stat[PS_TLEN + v], tl);
+		if (ql != a.qlen[0] || tl != a.tlen[0]) s_uniform = 0;
 	}
+	__syncthreads();
+	for (int k = threadIdx.x; k < 4 * N_VARIANTS; k += blockDim.x) {
+		const int x = s_stat[k];
+		if (x) { if (k < N_VARIANTS) atomicAdd(&a.stats[k], x); else atomicMax(&a.stats[k], x); }
+	}
+	if (threadIdx.x == 0 && !s_uniform) a.stats[PS_UNIFORM] = 1;       // (1 = the tasks are not all of one shape)
+}
+
+__device__ __forceinline__ int plan_level(const PlanArgs &a, int i, int v)
+{
+	const int mr = a.stats[PS_ROWS + v] > 1 ? a.stats[PS_ROWS + v] : 1;
+	return 255 - (int)((long long)a.rows[i] * 255 / mr);
+}
+
+__global__ void __launch_bounds__(256) plan_hist_kernel(PlanArgs a)          // tasks per (variant, level)
+{
+	__shared__ int s_bin[N_VARIANTS * 256];
+	for (int k = threadIdx.x; k < N_VARIANTS * 256; k += blockDim.x) s_bin[k] = 0;
+	__syncthreads();
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < a.n) { const int v = a.variant[i]; atomicAdd(&s_bin[v * 256 + plan_level(a, i, v)], 1); }
+	__syncthreads();
+	for (int k = threadIdx.x; k < N_VARIANTS * 256; k += blockDim.x) if (s_bin[k]) atomicAdd(&a.bins[k], s_bin[k]);
+}
+
+__global__ void __launch_bounds__(1024) plan_scan_kernel(PlanArgs a)          // bins -> where each (variant, level) starts in order[]
+{
+	__shared__ int s_part[1024];
+	constexpr int NB = N_VARIANTS * 256, PER = (NB + 1023) / 1024;
+	int local[PER], sum = 0;
+	for (int k = 0; k < PER; ++k) { const int b = threadIdx.x * PER + k; local[k] = b < NB ? a.bins[b] : 0; sum += local[k]; }
+	s_part[threadIdx.x] = sum;
+	__syncthreads();
+	for (int o = 1; o < 1024; o <<= 1) {
+		const int x = threadIdx.x >= o ? s_part[threadIdx.x - o] : 0;
+		__syncthreads();
+		s_part[threadIdx.x] += x;
+		__syncthreads();
+	}
+	int run = s_part[threadIdx.x] - sum;
+	for (int k = 0; k < PER; ++k) { const int b = threadIdx.x * PER + k; if (b < NB) { a.bins[b] = run; run += local[k]; } }
+}
+
+__global__ void __launch_bounds__(256) plan_scatter_kernel(PlanArgs a)
+{
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= a.n) return;
+	const int v = a.variant[i];
+	a.order[atomicAdd(&a.bins[v * 256 + plan_level(a, i, v)], 1)] = i;
+}
+
+int plan_batch(pansvr_ksw_ctx *ctx, const kswhost::Plan &pl, int64_t n, const int32_t *d_qlen, const int32_t *d_tlen, BatchPlan &bp)
+{
+	CU(ctx->plan_variant.reserve((size_t)n));
+	CU(ctx->plan_rows.reserve(sizeof(int) * (size_t)n));
+	CU(ctx->plan_stats.reserve(sizeof(int) * (PS_WORDS + N_VARIANTS * 256)));
+	CU(ctx->order.reserve(sizeof(int) * (size_t)n));
+	PlanArgs a;
+	a.n = (int)n; a.qlen = d_qlen; a.tlen = d_tlen; a.w = pl.P.w;
+	a.trivial = pl.trivial; a.fast_params = pl.fast_params; a.nowrap_ok = pl.nowrap_ok; a.smem_optin = ctx->smem_optin;
+	a.variant = (uint8_t*)ctx->plan_variant.p; a.rows = (int*)ctx->plan_rows.p; a.stats = (int*)ctx->plan_stats.p; a.bins = a.stats + PS_WORDS;
+	a.order = (int*)ctx->order.p;
+	const unsigned grid = (unsigned)((n + 255) / 256);
+	CU(cudaMemsetAsync(a.stats, 0, sizeof(int) * (PS_WORDS + N_VARIANTS * 256), ctx->stream));
+	plan_classify_kernel<<<grid, 256, 0, ctx->stream>>>(a);
+	plan_hist_kernel<<<grid, 256, 0, ctx->stream>>>(a);
+	plan_scan_kernel<<<1, 1024, 0, ctx->stream>>>(a);
+	plan_scatter_kernel<<<grid, 256, 0, ctx->stream>>>(a);
+	CU(cudaGetLastError());
+	ctx->stats.kernel_launches += 4;
+	int h[PS_WORDS];
+	CU(cudaMemcpyAsync(h, a.stats, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
+	CU(cudaStreamSynchronize(ctx->stream));
 	bp.begin[0] = 0;
-	for (int v = 0; v < N_VARIANTS; ++v) bp.begin[v + 1] = bp.begin[v] + (int)count[v];
-	// counting sort inside a variant: 256 levels of row count, longest first
-	std::vector<int> pos((size_t)N_VARIANTS * 256, 0);
-	auto level = [&](int64_t i) { int v = ctx->h_variant[i]; int mr = std::max(bp.max_rows[v], 1);
-	                              return 255 - (int)((int64_t)ctx->h_rows[i] * 255 / mr); };
-	for (int64_t i = 0; i < n; ++i) ++pos[(size_t)ctx->h_variant[i] * 256 + level(i)];
+	int used = 0, which = -1;
 	for (int v = 0; v < N_VARIANTS; ++v) {
-		int run = bp.begin[v];
-		for (int l = 0; l < 256; ++l) { int c = pos[(size_t)v * 256 + l]; pos[(size_t)v * 256 + l] = run; run += c; }
+		bp.begin[v + 1] = bp.begin[v] + h[PS_COUNT + v];
+		bp.max_rows[v] = h[PS_ROWS + v]; bp.max_qlen[v] = h[PS_QLEN + v]; bp.max_tlen[v] = h[PS_TLEN + v];
+		if (h[PS_COUNT + v]) { ++used; which = v; }
 	}
-	for (int64_t i = 0; i < n; ++i) ctx->h_order[pos[(size_t)ctx->h_variant[i] * 256 + level(i)]++] = (int)i;
+	// uniform batches (the fixed-read-length case): the tasks run in input order, no indirection
+	bp.identity = h[PS_UNIFORM] == 0 && used == 1 && which >= V_FAST0;
+	return 0;
 }
 
 template <int TEAM, bool WRAP, bool WC>
@@ -322,14 +349,10 @@ int run_device(pansvr_ksw_ctx *ctx, int64_t n, const uint8_t *d_qseq, const int6
 	if (pr->m > 1 && !pr->mat) return fail(PANSVR_E_ARG, "params->mat is NULL");
 	kswhost::Plan pl = kswhost::make_plan(pr->m, pr->mat, pr->gapo, pr->gape, pr->gapo2, pr->gape2, pr->w, pr->zdrop,
 	                                      pr->end_bonus, pr->flag);
+	(void)h_qlen; (void)h_tlen;                                   // (the plan is made on the device)
 	BatchPlan bp;
-	plan_batch(ctx, pl, n, h_qlen, h_tlen, bp);
+	{ const int prc = plan_batch(ctx, pl, n, d_qlen, d_tlen, bp); if (prc) return prc; }
 	CU(ctx->counters.reserve(sizeof(int) * N_VARIANTS));
-	if (!bp.identity) {
-		CU(ctx->order.reserve(sizeof(int) * (size_t)n));
-		CU(cudaMemcpyAsync(ctx->order.p, ctx->h_order.data(), sizeof(int) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
-		ctx->stats.h2d_bytes += (int64_t)sizeof(int) * n;
-	}
 	CU(cudaMemsetAsync(ctx->counters.p, 0, sizeof(int) * N_VARIANTS, ctx->stream));
 	CU(cudaEventRecord(ctx->ev[1], ctx->stream));
 	CU(cudaEventRecord(ctx->vev_in, ctx->stream));               // inputs and plan are in place: the variant streams start from here
@@ -402,7 +425,12 @@ extern "C" {
 
 const char *pansvr_last_error(void) { return g_err.c_str(); }
 
-int pansvr_ksw_create(int device, pansvr_ksw_ctx **out)
+extern "C" int pansvr_ksw_create_prio(int device, int high_priority, pansvr_ksw_ctx **out);
+int pansvr_ksw_create(int device, pansvr_ksw_ctx **out) { return pansvr_ksw_create_prio(device, 0, out); }
+
+// (not part of the ABI in include/: the aln stage makes the context of its host path with high-priority streams, so that the few
+// tasks of the pairs handed back to the host do not queue behind the bulk kernels of the sub-blocks in flight)
+int pansvr_ksw_create_prio(int device, int high_priority, pansvr_ksw_ctx **out)
 {
 	if (!out) return fail(PANSVR_E_ARG, "out is NULL");
 	*out = nullptr;
@@ -417,8 +445,11 @@ int pansvr_ksw_create(int device, pansvr_ksw_ctx **out)
 	c->device = device; c->sm_count = prop.multiProcessorCount;
 	if (cudaDeviceGetAttribute(&c->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device) != cudaSuccess) c->smem_optin = 227 * 1024;
 	memset(&c->stats, 0, sizeof(c->stats));
-	CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-	for (auto &vs : c->vstream) CU(cudaStreamCreateWithFlags(&vs, cudaStreamNonBlocking));
+	int prio_lo = 0, prio_hi = 0;
+	CU(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+	const int prio = high_priority ? prio_hi : prio_lo;
+	CU(cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, prio));
+	for (auto &vs : c->vstream) CU(cudaStreamCreateWithPriority(&vs, cudaStreamNonBlocking, prio));
 	CU(cudaEventCreateWithFlags(&c->vev_in, cudaEventDisableTiming));
 	for (auto &e : c->vev_done) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
 	for (auto &e : c->ev) CU(cudaEventCreate(&e));

@@ -73,11 +73,12 @@ static inline Plan make_plan(int m, const int8_t *mat, int q, int e, int q2, int
 }
 
 // Anti-diagonals the reference executes before its band closes (KSW:124-138); upper bound on
-// traceback rows (a z-drop can only end earlier).
-static inline int n_diagonals(int qlen, int tlen, int w)
+// traceback rows (a z-drop can only end earlier).  (This and the next three run on the host and, for the per-task plan of a
+// batch, on the device.)
+LANE_HD int n_diagonals(int qlen, int tlen, int w)
 {
 	if (qlen <= 0 || tlen <= 0) return 0;
-	if (w < 0) w = std::max(qlen, tlen);
+	if (w < 0) w = qlen > tlen ? qlen : tlen;
 	// lo0 > hi0 first happens where r-qlen+1 > (r+w)>>1 or (r-w+1)>>1 > tlen-1 (the other pairs cannot cross)
 	int n = qlen + tlen - 1;
 	for (int r = 0; r < n; ++r) {
@@ -89,19 +90,20 @@ static inline int n_diagonals(int qlen, int tlen, int w)
 }
 
 // 16-cell blocks per diagonal, as the reference sizes its traceback rows (KSW:86-87)
-static inline int n_col_blocks(int qlen, int tlen, int w)
+LANE_HD int n_col_blocks(int qlen, int tlen, int w)
 {
-	if (w < 0) w = std::max(qlen, tlen);
-	int n = std::min(qlen, tlen);
-	return (std::min(n, w + 1) + 15) / 16 + 1;
+	if (w < 0) w = qlen > tlen ? qlen : tlen;
+	int n = qlen < tlen ? qlen : tlen;
+	if (n > w + 1) n = w + 1;
+	return (n + 15) / 16 + 1;
 }
 
 // does the band ever cut the matrix?  (unclipped iff qlen,tlen <= w+1)
-static inline bool band_clips(int qlen, int tlen, int w) { return w >= 0 && (qlen > w + 1 || tlen > w + 1); }
+LANE_HD bool band_clips(int qlen, int tlen, int w) { return w >= 0 && (qlen > w + 1 || tlen > w + 1); }
 
 // lanes per alignment of the team kernel: one lane per 16-cell block of the widest rounded band
 // (n_col_blocks), rounded up to a power of two.  0 = wider than a warp.
-static inline int pick_team(int qlen, int tlen, int w)
+LANE_HD int pick_team(int qlen, int tlen, int w)
 {
 	const int need = n_col_blocks(qlen, tlen, w);
 	for (int t = 2; t <= 32; t *= 2)

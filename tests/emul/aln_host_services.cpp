@@ -7,6 +7,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <algorithm>
 #include <string>
 
 #include "../../include/pansvr_b200.h"
@@ -63,6 +64,12 @@ struct HostBackend {
 	void zero(void *d, size_t bytes) { if (bytes) memset(d, 0, bytes); }
 	void sync() {}
 	template <class F> void for_each(size_t n, const F &f, int) { for (size_t i = 0; i < n; ++i) f(i); }
+	template <class F> void for_each_in(size_t n, const uint32_t *perm, const F &f, int) { for (size_t k = 0; k < n; ++k) f((size_t)perm[k]); }
+	void order_desc(const uint32_t *key, const uint32_t *idx, uint32_t *perm, size_t n)
+	{
+		for (size_t i = 0; i < n; ++i) perm[i] = idx[i];
+		std::stable_sort(perm, perm + n, [&](uint32_t a, uint32_t b) { return key[a] > key[b]; });   // (idx is the identity here)
+	}
 	void encode(size_t n, const FnEncode &f)                      // strided scratch like the CUDA kernel's (word k of "thread" t at [k * 4 + t])
 	{
 		uint32_t filter[ENC_FILTER_WORDS * 4];
@@ -151,6 +158,7 @@ extern "C" const char *pansvr_last_error(void);
 extern "C" {
 const char *pansvr_last_error(void) { return g_err.c_str(); }
 int pansvr_ksw_create(int, pansvr_ksw_ctx **out) { *out = (pansvr_ksw_ctx*)1; return load_oracle() ? 0 : PANSVR_E_CUDA; }
+int pansvr_ksw_create_prio(int d, int, pansvr_ksw_ctx **out) { return pansvr_ksw_create(d, out); }
 void pansvr_ksw_destroy(pansvr_ksw_ctx*) {}
 int pansvr_ksw_last_stats(const pansvr_ksw_ctx*, pansvr_ksw_stats_t *out) { memset(out, 0, sizeof *out); return 0; }
 int64_t pansvr_ksw_band_cells(int32_t q, int32_t t, int32_t w) { return load_oracle() ? g_cells(q, t, w) : 0; }
