@@ -37,6 +37,8 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# eight sub-blocks in flight with a handful of streams each: give them hardware queues of their own (read when CUDA starts)
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 
 import bench_ksw  # noqa: E402
 from bench_ksw import ClockSampler, env_int, measured_peaks  # noqa: E402
@@ -132,7 +134,8 @@ def main():
     ap.add_argument("--pairs", type=int, default=5_000_000, help="read pairs of the input (config 3: 5 M pairs = 10 M reads)")
     ap.add_argument("--loci", type=int, default=5250, help="SV loci of the anchor set (config 3: 5250 loci = 10 500 anchors)")
     ap.add_argument("--block-pairs", type=int, default=0, help="pairs per pansvr_aln_block call at N=1 (multiple of 4096; 0 = the whole input in one call)")
-    ap.add_argument("--piece-pairs", type=int, default=131_072, help="N>1: pairs per piece of the block-cyclic deal (multiple of 4096)")
+    ap.add_argument("--piece-pairs", type=int, default=0, help="N>1: pairs per piece of the block-cyclic deal (multiple of 4096; 0 = the largest of "
+                    "262144 ... 65536 that gives every rank at least four pieces and keeps the ranks within 8 %% of each other)")
     ap.add_argument("--ref-sample-pairs", type=int, default=250_000, help="pairs per step of the CPU reference arm / cpu_baseline")
     ap.add_argument("--parity-pairs", type=int, default=491_520, help="prefix checked against `fc_aln -t 1` in the run (0 = off)")
     ap.add_argument("--threads", type=int, default=0, help="host helper threads per rank (0 = cores / ranks)")
@@ -178,7 +181,13 @@ def main():
         cuts = list(range(0, d.n_pairs, bp)) + [d.n_pairs]
         mine = list(range(len(cuts) - 1))
     else:
-        pp = max(S, args.piece_pairs // S * S)
+        pp = max(S, args.piece_pairs // S * S) if args.piece_pairs > 0 else 65536
+        if args.piece_pairs <= 0:
+            for cand in (262144, 196608, 131072, 98304, 65536):      # larger pieces = fuller kernels; smaller = better balance
+                n_pc = -(-d.n_pairs // cand)
+                if n_pc >= 4 * world and -(-n_pc // world) * cand <= 1.08 * d.n_pairs / world + cand * 0.0:
+                    pp = cand
+                    break
         cuts = list(range(0, d.n_pairs, pp)) + [d.n_pairs]
         mine = [b for b in range(len(cuts) - 1) if b % world == rank]
     n_pieces_total = len(cuts) - 1

@@ -777,6 +777,7 @@ int pansvr_aln_reset(pansvr_aln_ctx *c)
 // ---- `panSVR fc_aln` command line (MAP_PARA::get_option, read_realignment.hpp:82-128)
 int pansvr_fc_aln_main(int argc, char **argv)
 {
+	setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);               // the sub-blocks in flight use some fifty streams: hardware queues of their own (read when CUDA starts)
 	pansvr_aln_options_t o;
 	memset(&o, 0, sizeof o);
 	std::string out_path = "./output.bam", ori_path = "./output_ori.bam";

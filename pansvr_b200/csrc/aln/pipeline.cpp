@@ -2,6 +2,7 @@
 #include "pipeline.hpp"
 
 #include <stdio.h>
+#include <unistd.h>
 #include <stdlib.h>
 #include <string.h>
 #include <algorithm>
@@ -100,6 +101,17 @@ void AlnPipeline::parallel(size_t n, const std::function<void(size_t, size_t, in
 namespace {
 
 double now() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
+// PANSVR_TRACE=<file>: host-side phase marks of every sub-block (steady clock, s), one file per process
+void trace_host(uint64_t seq, const char *what, double at = -1)
+{
+	static const char *path = getenv("PANSVR_TRACE");
+	if (!path) return;
+	static std::mutex m; static FILE *f = nullptr;
+	std::lock_guard<std::mutex> lk(m);
+	if (!f) f = fopen((std::string(path) + "." + std::to_string((long)getpid()) + ".host").c_str(), "a");
+	if (f) { fprintf(f, "H %llu %s %.6f\n", (unsigned long long)seq, what, at >= 0 ? at : now()); fflush(f); }
+}
 
 // ---------------------------------------------------------------------------------------------- small pieces
 struct Dna5Table {                                              // charToDna5n, read_realignment.cpp:180-202, as a table (no branches)
@@ -1742,7 +1754,8 @@ bool AlnPipeline::align_block_host(const FastqRec *recs, size_t n_reads_in, Bloc
 	}
 	turn.pass();                                                          // the next block may replay now
 	{ std::lock_guard<std::mutex> lk(stats_m_); stats.t_in_order += now() - t_turn; stats.in_order_pairs += n_redo; }
-	if (getenv("PANSVR_TRACE")) fprintf(stderr, "T %llu in_order %.6f %.6f\n", (unsigned long long)seq, t_turn, now());
+	trace_host(seq, "io_begin", t_turn);
+	trace_host(seq, "io_end");
 	parallel(n_pairs, [&](size_t pb, size_t pe_, int) {                    // winners of the redrawn pairings
 		for (size_t pi = pb; pi < pe_; ++pi) {
 			if (redo[pi] != 2) continue;
@@ -1803,18 +1816,6 @@ bool AlnPipeline::align_block_text(const char *text, size_t bytes, size_t n_pair
 	out.sam_text.clear(); out.placed = false; out.placed_bytes = 0; out.place_called = false;
 	if (!stages_ || n_pairs == 0) { *reparse = true; return true; }
 	return align_block_dev(text, bytes, nullptr, n_pairs, out, err, seq, reparse);
-}
-
-namespace {
-void trace_host(uint64_t seq, const char *what)                       // PANSVR_TRACE=<file>: host-side phase marks of every sub-block (steady clock, s)
-{
-	static const char *path = getenv("PANSVR_TRACE");
-	if (!path) return;
-	static std::mutex m; static FILE *f = nullptr;
-	std::lock_guard<std::mutex> lk(m);
-	if (!f) f = fopen((std::string(path) + ".host").c_str(), "a");
-	if (f) { fprintf(f, "H %llu %s %.6f\n", (unsigned long long)seq, what, now()); fflush(f); }
-}
 }
 
 bool AlnPipeline::align_block_dev(const char *base, size_t text_bytes, const FastqRec *recs, size_t n_pairs, BlockOutput &out, std::string &err, uint64_t seq, bool *reparse)

@@ -3,6 +3,7 @@
 // dependent integer operations over a few hundred bytes, so the kernels are bound by HBM/L2 latency with every SM full of
 // reads in flight -- the layout goal is that a read's data is touched once per stage and never leaves the device in between.
 #include <cuda_runtime.h>
+#include <unistd.h>
 #include <cub/device/device_scan.cuh>
 #include <cub/device/device_radix_sort.cuh>
 #include <chrono>
@@ -82,12 +83,13 @@ struct CudaBackend {
 	{
 		const size_t bytes = n * sizeof(T);
 		if (bytes <= cap[slot]) return (T*)p[slot];
-		check(cudaStreamSynchronize(st), "cudaStreamSynchronize");
-		if (p[slot]) cudaFree(p[slot]);
+		// from the device's stream-ordered pool: growing a buffer is an operation of this block's stream like any other, not a
+		// device-wide synchronisation (cudaFree is: every other block in flight would stall whenever a buffer grows)
+		if (p[slot]) check(cudaFreeAsync(p[slot], st), "cudaFreeAsync");
 		p[slot] = nullptr; cap[slot] = 0;
 		const size_t want = bytes + bytes / 4 + 4096;
-		cudaError_t e = cudaMalloc(&p[slot], want);
-		if (e != cudaSuccess) { check(e, "cudaMalloc"); return nullptr; }
+		cudaError_t e = cudaMallocAsync(&p[slot], want, st);
+		if (e != cudaSuccess) { check(e, "cudaMallocAsync"); return nullptr; }
 		cap[slot] = want;
 		return (T*)p[slot];
 	}
@@ -191,7 +193,7 @@ struct CudaBackend {
 		if (!tried) {
 			tried = true;
 			if (const char *path = getenv("PANSVR_TRACE")) {
-				f = fopen(path, "a");
+				f = fopen((std::string(path) + "." + std::to_string((long)getpid())).c_str(), "a");
 				if (f && cudaEventCreate(&ref) == cudaSuccess) { cudaEventRecord(ref, st); cudaEventSynchronize(ref); fprintf(f, "# ref %.6f\n", std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count()); }
 			}
 		}
@@ -286,7 +288,8 @@ void stage_service_destroy(StageService *s)
 	if (!s) return;
 	cudaSetDevice(s->device);
 	if (s->be.st) cudaStreamSynchronize(s->be.st);
-	for (int i = 0; i < SL_COUNT; ++i) if (s->be.p[i]) cudaFree(s->be.p[i]);
+	for (int i = 0; i < SL_COUNT; ++i) if (s->be.p[i]) cudaFreeAsync(s->be.p[i], s->be.st);
+	if (s->be.st) cudaStreamSynchronize(s->be.st);
 	for (cudaEvent_t e : s->be.ev_pool) cudaEventDestroy(e);
 	if (s->d_pos) cudaFree(s->d_pos);
 	if (s->d_ref) cudaFree(s->d_ref);

@@ -141,19 +141,22 @@ __global__ void __launch_bounds__(256) int_pipe_peak_kernel(uint32_t *out, int i
 	if (r == 0x12345678u) out[blockIdx.x * blockDim.x + threadIdx.x] = r;
 }
 
+// Grow-only device buffer from the device's stream-ordered pool: growing it is no device-wide synchronisation (cudaFree is, and
+// with several contexts at work on one GPU every one of them would stall whenever one buffer grows).
 struct DevBuf {
-	void *p = nullptr; size_t cap = 0;
+	void *p = nullptr; size_t cap = 0; cudaStream_t st = nullptr;
 	cudaError_t reserve(size_t bytes)
 	{
 		if (bytes <= cap) return cudaSuccess;
-		if (p) cudaFree(p);
+		if (p) cudaFreeAsync(p, st);                               // (whatever used it was waited for before the call that grows it)
 		p = nullptr; cap = 0;
-		size_t want = bytes + bytes / 8 + 256;
-		cudaError_t e = cudaMalloc(&p, want);
-		if (e == cudaSuccess) cap = want;
+		size_t want = bytes + bytes / 4 + 256;
+		cudaError_t e = cudaMallocAsync(&p, want, st);
+		if (e == cudaSuccess) e = cudaStreamSynchronize(st);        // the buffer is used from other streams of the context too
+		if (e == cudaSuccess) cap = want; else p = nullptr;
 		return e;
 	}
-	void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+	void release() { if (p) { cudaFreeAsync(p, st); cudaStreamSynchronize(st); } p = nullptr; cap = 0; }
 };
 
 enum { V_TRIVIAL = 0, V_GENERIC = 1, V_FAST0 = 2 };   // team variants: V_FAST0 + 2*log2(TEAM/2) + wrap
@@ -450,6 +453,12 @@ int pansvr_ksw_create_prio(int device, int high_priority, pansvr_ksw_ctx **out)
 	const int prio = high_priority ? prio_hi : prio_lo;
 	CU(cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, prio));
 	for (auto &vs : c->vstream) CU(cudaStreamCreateWithPriority(&vs, cudaStreamNonBlocking, prio));
+	for (DevBuf *b : {&c->qseq, &c->tseq, &c->qoff, &c->toff, &c->qlen, &c->tlen, &c->res, &c->cigar, &c->order, &c->counters, &c->tb, &c->plan_variant, &c->plan_rows, &c->plan_stats}) b->st = c->stream;
+	for (DevBuf &b : c->tb_v) b.st = c->stream;
+	{   // freed buffers stay in the pool (the default threshold hands them back to the driver at the next synchronisation)
+		cudaMemPool_t pool;
+		if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) { uint64_t keep = ~0ull; cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep); }
+	}
 	CU(cudaEventCreateWithFlags(&c->vev_in, cudaEventDisableTiming));
 	for (auto &e : c->vev_done) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
 	for (auto &e : c->ev) CU(cudaEventCreate(&e));
@@ -467,7 +476,8 @@ void pansvr_ksw_destroy(pansvr_ksw_ctx *c)
 	for (auto &e : c->vev_done) if (e) cudaEventDestroy(e);
 	for (DevBuf &b : c->tb_v) b.release();
 	for (DevBuf *b : {&c->qseq, &c->tseq, &c->qoff, &c->toff, &c->qlen, &c->tlen, &c->res, &c->cigar, &c->order, &c->counters,
-	                  &c->tb, &c->gscratch}) b->release();
+	                  &c->tb, &c->plan_variant, &c->plan_rows, &c->plan_stats}) b->release();
+	if (c->gscratch.p) cudaFree(c->gscratch.p);                   // (the generic kernel's launcher sizes this one itself, with cudaMalloc)
 	for (auto &e : c->ev) if (e) cudaEventDestroy(e);
 	if (c->stream) cudaStreamDestroy(c->stream);
 	delete c;

@@ -428,100 +428,99 @@ LANE_DEV void align_team(const Params &P, bool have_task, int qlen, const uint8_
 		if (!max_known) { ez_max_t = t_old; ez_max_q = r_max - t_old; max_known = true; }
 	}
 
-	// ---- traceback (KSW:382-391, K2H:119-151): one alignment at a time, the whole warp walks its path
+	// ---- traceback (KSW:382-391, K2H:119-151): every team walks the path of its own alignment, TEAM cells of a run per round
+	// trip to the traceback bytes -- the alignments of a warp side by side (a warp of sixteen 40 x 40 extensions makes about as
+	// many dependent round trips for all of them as it used to make for one after the other)
 	const int ez_max = ez_max8 >> 3;
 	const int mqe = mqe8 == NEG_INF ? NEG_INF : mqe8 >> 3;
-	int my_n_cigar = 0, my_reach_end = 0, my_overflow = 0;
+	int n_cigar = 0, reach_end = 0, overflow = 0;
 	wsync();
-	for (int team = 0; team < 32 / TEAM; ++team) {
-		const int src = team * TEAM;
-		if (!shfl((int)have_task, src)) continue;
-		const int qlen_t = shfl(qlen, src), tlen_t = shfl(tlen, src);
-		const int w_t = P.w < 0 ? (tlen_t > qlen_t ? tlen_t : qlen_t) : P.w;
-		const int zd_t = shfl(zdropped, src), mqe_tm = shfl(mqe, src), mqe_t_t = shfl(mqe_t, src), max_tm = shfl(ez_max, src);
-		const int max_t_t = shfl(ez_max_t, src), max_q_t = shfl(ez_max_q, src);
-		const uint64_t tb_a = (uint64_t)(uintptr_t)tb, cg_a = (uint64_t)(uintptr_t)cigar;
-		const uint8_t *tb_t = (const uint8_t*)(uintptr_t)((uint64_t)shfl((uint32_t)tb_a, src) | (uint64_t)shfl((uint32_t)(tb_a >> 32), src) << 32);
-		uint32_t *cg_t = (uint32_t*)(uintptr_t)((uint64_t)shfl((uint32_t)cg_a, src) | (uint64_t)shfl((uint32_t)(cg_a >> 32), src) << 32);
-		int n_cigar = 0, reach_end = 0, overflow = 0;
-		if (with_cigar) {
-			int i = -1, j = -1;
-			if (!zd_t && !(P.flag & kswfast::F_EXTZ_ONLY)) { i = tlen_t - 1; j = qlen_t - 1; }
-			else if (!zd_t && (P.flag & kswfast::F_EXTZ_ONLY) && mqe_tm + P.end_bonus > max_tm) { reach_end = 1; i = mqe_t_t; j = qlen_t - 1; }
-			else if (max_t_t >= 0 && max_q_t >= 0) { i = max_t_t; j = max_q_t; }
-			int state = 0;
-			uint32_t cur = 0;                                         // last CIGAR element, not yet stored
-			auto push = [&](uint32_t op, int len) __attribute__((always_inline)) {
-				if (n_cigar == 0 || op != (cur & 0xfu)) {
-					if (n_cigar > 0) {
-						if (n_cigar - 1 < cigar_cap) { if (lane == 0) cg_t[n_cigar - 1] = cur; }
-						else overflow = 1;
-					}
-					++n_cigar;
-					cur = (uint32_t)len << 4 | op;
-				} else cur += (uint32_t)len << 4;
-			};
-			while (i >= 0 && j >= 0) {
-				const int di = (state == 0 || state == 1 || state == 3) ? 1 : 0;
-				const int dj = (state == 0 || state == 2 || state == 4) ? 1 : 0;
-				const int li = i - lane * di, lj = j - lane * dj;
-				const bool valid = li >= 0 && lj >= 0;
-				int forced = -1;
-				uint32_t tmp = 0;
-				bool clean = false;
-				if (valid) {
-					const int rr = li + lj;
-					int lo0, hi0;
-					band(rr, qlen_t, tlen_t, w_t, lo0, hi0);
-					if (li < (lo0 & ~15)) forced = 2;
-					if (li > (hi0 | 15)) forced = 1;
-					if (forced < 0) {
-						// a plain load: the bytes were stored by lanes of this same warp before the __syncwarp above
-						const uint32_t b = tb_t[(size_t)rr * W + (li & (W - 1))];
-						tmp = (b & 0x78u) | (4u - (b & 7u));
-					}
-					clean = forced < 0 && (state == 0 ? (tmp & 7u) == 0 : ((tmp >> (state + 2)) & 1u) != 0);
+	if (with_cigar) {
+		const int base = lane & ~(TEAM - 1);
+		const uint32_t tmask = TEAM == 32 ? 0xffffffffu : ((1u << TEAM) - 1u);
+		int i = -1, j = -1;
+		if (have_task) {
+			if (!zdropped && !(P.flag & kswfast::F_EXTZ_ONLY)) { i = tlen - 1; j = qlen - 1; }
+			else if (!zdropped && (P.flag & kswfast::F_EXTZ_ONLY) && mqe + P.end_bonus > ez_max) { reach_end = 1; i = mqe_t; j = qlen - 1; }
+			else if (ez_max_t >= 0 && ez_max_q >= 0) { i = ez_max_t; j = ez_max_q; }
+		}
+		int state = 0;
+		uint32_t cur = 0;                                             // last CIGAR element, not yet stored
+		auto push = [&](uint32_t op, int len) __attribute__((always_inline)) {
+			if (n_cigar == 0 || op != (cur & 0xfu)) {
+				if (n_cigar > 0) {
+					if (n_cigar - 1 < cigar_cap) { if (tl == 0) cigar[n_cigar - 1] = cur; }
+					else overflow = 1;
 				}
-				const uint32_t stop = wballot(!clean);
-				const int n = stop ? ffs32(stop) - 1 : 32;
+				++n_cigar;
+				cur = (uint32_t)len << 4 | op;
+			} else cur += (uint32_t)len << 4;
+		};
+		while (wballot(i >= 0 && j >= 0)) {
+			const bool walking = i >= 0 && j >= 0;                    // (team-uniform: every lane of a team holds the same i, j, state)
+			const int di = (state == 0 || state == 1 || state == 3) ? 1 : 0;
+			const int dj = (state == 0 || state == 2 || state == 4) ? 1 : 0;
+			const int li = i - tl * di, lj = j - tl * dj;
+			const bool valid = walking && li >= 0 && lj >= 0;
+			int forced = -1;
+			uint32_t tmp = 0;
+			bool clean = false;
+			if (valid) {
+				const int rr = li + lj;
+				int lo0, hi0;
+				band(rr, qlen, tlen, w, lo0, hi0);
+				if (li < (lo0 & ~15)) forced = 2;
+				if (li > (hi0 | 15)) forced = 1;
+				if (forced < 0) {
+					// a plain load: the bytes were stored by lanes of this same warp before the __syncwarp above
+					const uint32_t bb = tb[(size_t)rr * W + (li & (W - 1))];
+					tmp = (bb & 0x78u) | (4u - (bb & 7u));
+				}
+				clean = forced < 0 && (state == 0 ? (tmp & 7u) == 0 : ((tmp >> (state + 2)) & 1u) != 0);
+			}
+			const uint32_t stop = (wballot(!clean) >> base) & tmask;
+			const int n = stop ? ffs32(stop) - 1 : TEAM;
+			const int from = base + (n < TEAM ? n : 0);               // the first cell that breaks the run, if it exists
+			const int v = shfl((int)valid, from);
+			const uint32_t t2 = shfl(tmp, from);
+			const int f2 = shfl(forced, from);
+			if (walking) {
 				if (n > 0) {
 					push(state == 0 ? 0u : (di ? 2u : 1u), n);
 					i -= n * di; j -= n * dj;
 				}
-				if (n < 32) {                                         // the first cell that breaks the run, if it exists
-					const int v = shfl((int)valid, n);
-					const uint32_t t2 = shfl(tmp, n);
-					const int f2 = shfl(forced, n);
-					if (v) {
-						int s2 = state;
-						if (s2 == 0) s2 = t2 & 7;
-						else if (!((t2 >> (s2 + 2)) & 1)) s2 = 0;
-						if (s2 == 0) s2 = t2 & 7;
-						if (f2 >= 0) s2 = f2;
-						if (s2 == 0) { push(0, 1); --i; --j; }
-						else if (s2 == 1 || s2 == 3) { push(2, 1); --i; }
-						else { push(1, 1); --j; }
-						state = s2;
-					}
-				}
-			}
-			if (i >= 0) push(2, i + 1);
-			if (j >= 0) push(1, j + 1);
-			if (n_cigar > 0) {
-				if (n_cigar - 1 < cigar_cap) { if (lane == 0) cg_t[n_cigar - 1] = cur; }
-				else overflow = 1;
-			}
-			if (!(P.flag & kswfast::F_REV_CIGAR) && !overflow) {
-				wsync();
-				for (int k = lane; k < n_cigar >> 1; k += 32) {
-					const uint32_t x = cg_t[k], y = cg_t[n_cigar - 1 - k];
-					cg_t[k] = y; cg_t[n_cigar - 1 - k] = x;
+				if (n < TEAM && v) {
+					int s2 = state;
+					if (s2 == 0) s2 = t2 & 7;
+					else if (!((t2 >> (s2 + 2)) & 1)) s2 = 0;
+					if (s2 == 0) s2 = t2 & 7;
+					if (f2 >= 0) s2 = f2;
+					if (s2 == 0) { push(0, 1); --i; --j; }
+					else if (s2 == 1 || s2 == 3) { push(2, 1); --i; }
+					else { push(1, 1); --j; }
+					state = s2;
 				}
 			}
 		}
-		for (int k = n_cigar + lane; k < cigar_cap; k += 32) cg_t[k] = 0;   // deterministic tail of the CIGAR row
-		if (lane == src) { my_n_cigar = n_cigar; my_reach_end = reach_end; my_overflow = overflow; }
+		if (have_task) {
+			if (i >= 0) push(2, i + 1);
+			if (j >= 0) push(1, j + 1);
+			if (n_cigar > 0) {
+				if (n_cigar - 1 < cigar_cap) { if (tl == 0) cigar[n_cigar - 1] = cur; }
+				else overflow = 1;
+			}
+		}
+		if (!(P.flag & kswfast::F_REV_CIGAR)) {
+			wsync();
+			if (have_task && !overflow)
+				for (int k = tl; k < n_cigar >> 1; k += TEAM) {
+					const uint32_t x = cigar[k], y = cigar[n_cigar - 1 - k];
+					cigar[k] = y; cigar[n_cigar - 1 - k] = x;
+				}
+		}
 	}
+	if (have_task) for (int k = n_cigar + tl; k < cigar_cap; k += TEAM) cigar[k] = 0;   // deterministic tail of the CIGAR row
+	const int my_n_cigar = n_cigar, my_reach_end = reach_end, my_overflow = overflow;
 	if (have_task && tl == 0) {
 		res[0] = ez_max; res[1] = zdropped; res[2] = ez_max_q; res[3] = ez_max_t;
 		res[4] = mqe; res[5] = mqe_t; res[6] = mte8 == NEG_INF ? NEG_INF : mte8 >> 3; res[7] = mte_q;
