@@ -45,6 +45,7 @@ from bench_ksw import ClockSampler, env_int, measured_peaks  # noqa: E402
 
 OPS_PER_CELL = 55               # int ops per DP cell with traceback
 SEED_BYTES_MISS, SEED_BYTES_HIT = 64, 290      # SURVEY.md 8d seeding byte model: per miss probe / per hit
+KSW_TRAFFIC_BYTES = 384_961_280   # profiles/r2_ncu_stage_kernels.md (r2f): DRAM bytes of one ksw_team_kernel<4,0,1> launch, 262144-pair sub-block
 METRIC = "realigned reads/s (fc_aln stage: FASTQ text in, SAM text out; config 3)"
 
 
@@ -376,7 +377,10 @@ def main():
                      "cells_per_step": tot["ksw_cells"] / args.steps, "tasks_per_step": tot["ksw_tasks"] / args.steps,
                      "pipe_peaks_gops": pipes, "frac_of": {k: (ksw_gops / v if v else None) for k, v in pipes.items()},
                      "peak_source": "pansvr_int_pipe_peaks measured live on this GPU ('mixed' = IADD3/LOP3/VIMNMX chains; ALU pipe, FMA pipe and both together alongside)",
-                     "traffic": None},
+                     "traffic": KSW_TRAFFIC_BYTES,
+                     "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the largest variant, ksw_team_kernel<4,0,1>, on a 262144-pair "
+                                     "sub-block (1.34 ms; 90 MB read, 295 MB written = the traceback bytes), from the ncu --set full capture profiles/r2_ncu_stage_kernels.md "
+                                     "(r2f) -- not measured in this run; the kernel is bound by the integer pipes, HBM sees 0.29 TB/s"},
         "roofline_seed": {"bound": "hbm", "kernel": "for_each_kernel<FnSeed> + for_each_kernel<FnSeedPlace> (stage B)", "achieved": seed_gbs,
                           "peak": peaks.get("hbm_gbs"), "unit": "GB/s", "frac": seed_gbs / peaks["hbm_gbs"] if peaks.get("hbm_gbs") else None,
                           "kernel_ms_per_step": p_seed_ms, "probes_per_step": tot["seed_probes"] / args.steps,

@@ -500,7 +500,7 @@ int run_block(pansvr_aln_ctx *c, Piece *pieces, size_t n_pieces, std::vector<Par
 		const bool more = next_sub(next);
 		t_cut += tick() - t0;
 		if (!more) break;
-		if (k >= flight) { subs[k - flight].th.join(); hand_over(k - flight + 1); }
+		if (k >= flight) { trace_mark(k - flight, "join_wait"); subs[k - flight].th.join(); trace_mark(k - flight, "joined"); hand_over(k - flight + 1); }
 		subs.emplace_back(std::move(next));
 		Sub &S = subs.back();
 		S.seq = c->pipe->next_seq();
@@ -511,11 +511,13 @@ int run_block(pansvr_aln_ctx *c, Piece *pieces, size_t n_pieces, std::vector<Par
 		if ((first_of_piece && P.await_path) || (last_of_piece && P.publish_path))
 			c->pipe->chain_at(S.seq, first_of_piece ? P.await_path : nullptr, last_of_piece ? P.publish_path : nullptr);
 		if (c->outs.size() <= k) c->outs.emplace_back();
+		trace_mark(S.seq, "launch");
 		S.th = std::thread(run_sub, &S, &c->outs[k], k);
 	}
 	c->pipe->stats.t_stage[6] += t_cut;
 	const size_t n_sub = subs.size();
-	for (size_t k = 0; k < n_sub; ++k) if (subs[k].th.joinable()) { subs[k].th.join(); hand_over(k + 1); }
+	for (size_t k = 0; k < n_sub; ++k) if (subs[k].th.joinable()) { trace_mark(k, "join_wait"); subs[k].th.join(); trace_mark(k, "joined"); hand_over(k + 1); }
+	trace_mark(n_sub, "block_done");
 	for (size_t k = 0; k < n_sub; ++k) if (!subs[k].ok) { g_aln_err = subs[k].err; return PANSVR_E_CUDA; }
 	hand_over(n_sub);
 	sam.clear(); ori.clear();
@@ -891,7 +893,9 @@ int pansvr_fc_aln_main(int argc, char **argv)
 	});
 	bool ok = true;
 	for (;;) {
+		trace_mark(0, "cli_wait_job");
 		Job j = jobs.pop();
+		trace_mark(j.fastq.size(), "cli_job");
 		Result r; r.last = j.last;
 		if (ok && !failed && !j.fastq.empty()) {
 			int rc;
@@ -902,8 +906,11 @@ int pansvr_fc_aln_main(int argc, char **argv)
 		results.push(std::move(r));
 		if (j.last) break;
 	}
+	trace_mark(0, "cli_join_reader");
 	reader.join();
+	trace_mark(0, "cli_join_writer");
 	writer.join();
+	trace_mark(0, "cli_joined");
 	if (failed && ok) { fprintf(stderr, "pansvr_b200 fc_aln: writing the output failed: %s\n", pansvr_aln_last_error()); ok = false; }
 	in.close();
 	if (sam) { fclose(fo); fclose(fp); }
@@ -917,7 +924,9 @@ int pansvr_fc_aln_main(int argc, char **argv)
 	fprintf(stderr, "pansvr_b200 fc_aln: %ld reads, %ld MEMs, %ld ksw tasks; stage seconds A %.3f B %.3f C %.3f D %.3f E %.3f F %.3f parse %.3f emit %.3f\n",
 	        (long)st.reads, (long)st.mems, (long)st.ksw_tasks, st.stage_seconds[0], st.stage_seconds[1], st.stage_seconds[2], st.stage_seconds[3],
 	        st.stage_seconds[4], st.stage_seconds[5], st.stage_seconds[6], st.stage_seconds[7]);
+	trace_mark(0, "cli_destroy");
 	pansvr_aln_destroy(ctx);
+	trace_mark(0, "cli_exit");
 	return ok ? 0 : 1;
 }
 

@@ -1234,6 +1234,17 @@ void AlnPipeline::chain_at(uint64_t seq, const char *await, const char *publish)
 
 bool AlnPipeline::publish_streams(const std::string &path) { return write_streams(path, export_streams()); }
 
+void AlnPipeline::pass_turn_if_pending(uint64_t seq)
+{
+	std::unique_lock<std::mutex> lk(turn_m_);
+	turn_cv_.wait(lk, [&]() { return replay_turn_ >= seq; });
+	if (replay_turn_ != seq) return;                                     // it had its turn
+	replay_turn_ = seq + 1;
+	chain_.erase(seq);
+	lk.unlock();
+	turn_cv_.notify_all();
+}
+
 bool AlnPipeline::write_streams(const std::string &path, const StreamState &s)
 {
 	const std::string tmp = path + ".part";
@@ -1792,6 +1803,8 @@ bool AlnPipeline::align_block_host(const FastqRec *recs, size_t n_reads_in, Bloc
 }
 
 
+void trace_mark(uint64_t seq, const char *what) { trace_host(seq, what); }
+
 // ================================================================================================ the device path
 bool AlnPipeline::align_block(const FastqRec *recs, size_t n_reads_in, BlockOutput &out, std::string &err, uint64_t seq)
 {
@@ -1821,6 +1834,8 @@ bool AlnPipeline::align_block_text(const char *text, size_t bytes, size_t n_pair
 bool AlnPipeline::align_block_dev(const char *base, size_t text_bytes, const FastqRec *recs, size_t n_pairs, BlockOutput &out, std::string &err, uint64_t seq, bool *reparse)
 {
 	trace_host(seq, "enter");
+	// whatever happens on the way (but not when the block is handed back for the host parser: it comes again under the same number)
+	struct TurnOnExit { AlnPipeline &P; uint64_t seq; bool again; ~TurnOnExit() { if (!again) P.pass_turn_if_pending(seq); } } turn_on_exit{*this, seq, false};
 	const size_t nd = 2 * n_pairs;
 	Impl I(*this);
 	const DebgaIndex &idx = idx_;
@@ -1878,7 +1893,7 @@ bool AlnPipeline::align_block_dev(const char *base, size_t text_bytes, const Fas
 		trace_host(seq, "trip1_end");
 	}
 	DevStageOut &o = db->out;
-	if (!o.parse_ok) { if (reparse) { *reparse = true; return true; } err = "internal error: record table rejected"; return false; }
+	if (!o.parse_ok) { if (reparse) { *reparse = true; turn_on_exit.again = true; return true; } err = "internal error: record table rejected"; return false; }
 	// a record of the block as the host path sees it
 	const DevRec *drecs = recs ? db->recs.data() : o.recs.data();
 	auto rec_at = [&](size_t t) -> FastqRec {

@@ -152,6 +152,9 @@ struct BlockOutput {                  // record text of one block: buffer t hold
 	size_t placed_bytes = 0; const char *placed_ptr = nullptr; bool placed = false, place_called = false;
 };
 
+// PANSVR_TRACE=<file>: a mark in the process's phase trace (<file>.<pid>.host: "H <seq> <what> <steady clock seconds>")
+void trace_mark(uint64_t seq, const char *what);
+
 struct CigarPath { uint8_t type; int16_t size; };
 
 class AlnPipeline {
@@ -189,6 +192,8 @@ public:
 	// the same per block: the in-order section of block `seq` first waits for the file `await` and imports it, and writes `publish`
 	// the moment it is done (before the block's later stages) -- pieces of one input dealt to several processes in turn
 	void chain_at(uint64_t seq, const char *await, const char *publish);
+	// a block that ends without having had its in-order section (an error on its way) must still let the blocks behind it have theirs
+	void pass_turn_if_pending(uint64_t seq);
 	struct Stats { uint64_t reads = 0, probes_reads = 0, mems = 0, ksw_tasks = 0, ksw_cells = 0, deferred_pairs = 0, in_order_pairs = 0, in_order_draws = 0, host_pairs = 0;
 	               double t_in_order = 0;
 	               double t_stage[8] = {0, 0, 0, 0, 0, 0, 0, 0}; DevCounters dev; } stats;   // A..F, FASTQ parse, output assembly

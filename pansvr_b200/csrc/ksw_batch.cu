@@ -318,7 +318,12 @@ int launch_team_wc(pansvr_ksw_ctx *ctx, KArgs a, int max_rows, int max_qlen, cud
 	a.smem_per_team = kswteam::team_smem_bytes(TEAM, max_qlen);
 	const int smem = (a.smem_per_team * NT + 32 * 32) * WARPS_PER_CTA + 512;
 	auto kern = ksw_team_kernel<TEAM, WRAP, WC>;
-	CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+	// The limit is a property of the function, not of the launch: several contexts launch this kernel at the same time with
+	// different sizes (sub-blocks in flight, each with its own longest query), and a launch fails with "invalid argument" if
+	// another thread lowered the limit between this thread's setting it and its launch.  So everybody sets the same value, the
+	// most a CTA may have; what a launch uses is its own `smem`.
+	if (smem > ctx->smem_optin) return fail(PANSVR_E_UNSUPPORTED, "ksw team kernel does not fit an SM (query too long)");
+	CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_optin));
 	int per_sm = 0;
 	CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, THREADS, smem));
 	if (per_sm < 1) return fail(PANSVR_E_UNSUPPORTED, "ksw team kernel does not fit an SM (query too long)");
@@ -429,6 +434,7 @@ extern "C" {
 const char *pansvr_last_error(void) { return g_err.c_str(); }
 
 extern "C" int pansvr_ksw_create_prio(int device, int high_priority, pansvr_ksw_ctx **out);
+void pansvr_ksw_destroy(pansvr_ksw_ctx *c);
 int pansvr_ksw_create(int device, pansvr_ksw_ctx **out) { return pansvr_ksw_create_prio(device, 0, out); }
 
 // (not part of the ABI in include/: the aln stage makes the context of its host path with high-priority streams, so that the few
@@ -445,23 +451,27 @@ int pansvr_ksw_create_prio(int device, int high_priority, pansvr_ksw_ctx **out)
 	CU(cudaGetDeviceProperties(&prop, device));
 	if (prop.major < 10) return fail(PANSVR_E_CUDA, std::string("device is not sm_100 class: ") + prop.name);
 	pansvr_ksw_ctx *c = new pansvr_ksw_ctx();
+	// (a failure from here on must not leak the half-made context)
+#define CUX(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { pansvr_ksw_destroy(c); \
+	return fail(PANSVR_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); } } while (0)
 	c->device = device; c->sm_count = prop.multiProcessorCount;
 	if (cudaDeviceGetAttribute(&c->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device) != cudaSuccess) c->smem_optin = 227 * 1024;
 	memset(&c->stats, 0, sizeof(c->stats));
 	int prio_lo = 0, prio_hi = 0;
-	CU(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+	CUX(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
 	const int prio = high_priority ? prio_hi : prio_lo;
-	CU(cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, prio));
-	for (auto &vs : c->vstream) CU(cudaStreamCreateWithPriority(&vs, cudaStreamNonBlocking, prio));
+	CUX(cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, prio));
+	for (auto &vs : c->vstream) CUX(cudaStreamCreateWithPriority(&vs, cudaStreamNonBlocking, prio));
 	for (DevBuf *b : {&c->qseq, &c->tseq, &c->qoff, &c->toff, &c->qlen, &c->tlen, &c->res, &c->cigar, &c->order, &c->counters, &c->tb, &c->plan_variant, &c->plan_rows, &c->plan_stats}) b->st = c->stream;
 	for (DevBuf &b : c->tb_v) b.st = c->stream;
 	{   // freed buffers stay in the pool (the default threshold hands them back to the driver at the next synchronisation)
 		cudaMemPool_t pool;
 		if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) { uint64_t keep = ~0ull; cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep); }
 	}
-	CU(cudaEventCreateWithFlags(&c->vev_in, cudaEventDisableTiming));
-	for (auto &e : c->vev_done) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-	for (auto &e : c->ev) CU(cudaEventCreate(&e));
+	CUX(cudaEventCreateWithFlags(&c->vev_in, cudaEventDisableTiming));
+	for (auto &e : c->vev_done) CUX(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+	for (auto &e : c->ev) CUX(cudaEventCreate(&e));
+#undef CUX
 	*out = c;
 	return 0;
 }
@@ -505,7 +515,21 @@ int64_t pansvr_ksw_band_cells(int32_t qlen, int32_t tlen, int32_t w)
 	return n;
 }
 
-int pansvr_ksw_extd2_batch_device(pansvr_ksw_ctx *ctx, int64_t n, const uint8_t *d_qseq, const int64_t *d_qoff,
+// A call that fails half way must not leave copies or kernels in flight that still touch the caller's buffers (or the context's,
+// which the next call may grow): whatever was queued is waited for before the error is returned.
+static int drained(pansvr_ksw_ctx *ctx, int rc)
+{
+	if (rc != 0 && ctx) {
+		const std::string keep = g_err;
+		cudaStreamSynchronize(ctx->stream);
+		for (auto &vs : ctx->vstream) if (vs) cudaStreamSynchronize(vs);
+		cudaGetLastError();
+		g_err = keep;
+	}
+	return rc;
+}
+
+static int batch_device_impl(pansvr_ksw_ctx *ctx, int64_t n, const uint8_t *d_qseq, const int64_t *d_qoff,
                                   const int32_t *d_qlen, const uint8_t *d_tseq, const int64_t *d_toff, const int32_t *d_tlen,
                                   const int32_t *h_qlen, const int32_t *h_tlen, const pansvr_ksw_params_t *params,
                                   int32_t *d_results, uint32_t *d_cigar, int32_t cigar_cap)
@@ -521,7 +545,15 @@ int pansvr_ksw_extd2_batch_device(pansvr_ksw_ctx *ctx, int64_t n, const uint8_t 
 	return finish_stats(ctx);
 }
 
-int pansvr_ksw_extd2_batch(pansvr_ksw_ctx *ctx, int64_t n, const uint8_t *qseq, int64_t qseq_bytes, const int64_t *qoff,
+int pansvr_ksw_extd2_batch_device(pansvr_ksw_ctx *ctx, int64_t n, const uint8_t *d_qseq, const int64_t *d_qoff,
+                                  const int32_t *d_qlen, const uint8_t *d_tseq, const int64_t *d_toff, const int32_t *d_tlen,
+                                  const int32_t *h_qlen, const int32_t *h_tlen, const pansvr_ksw_params_t *params,
+                                  int32_t *d_results, uint32_t *d_cigar, int32_t cigar_cap)
+{
+	return drained(ctx, batch_device_impl(ctx, n, d_qseq, d_qoff, d_qlen, d_tseq, d_toff, d_tlen, h_qlen, h_tlen, params, d_results, d_cigar, cigar_cap));
+}
+
+static int batch_impl(pansvr_ksw_ctx *ctx, int64_t n, const uint8_t *qseq, int64_t qseq_bytes, const int64_t *qoff,
                            const int32_t *qlen, const uint8_t *tseq, int64_t tseq_bytes, const int64_t *toff,
                            const int32_t *tlen, const pansvr_ksw_params_t *params, int32_t *results, uint32_t *cigar,
                            int32_t cigar_cap)
@@ -559,6 +591,14 @@ int pansvr_ksw_extd2_batch(pansvr_ksw_ctx *ctx, int64_t n, const uint8_t *qseq, 
 	ctx->stats.d2h_bytes = (int64_t)(nn * sizeof(int32_t) * PANSVR_RES_WORDS) +
 	                       ((cigar_cap > 0 && !(params->flag & PANSVR_KSW_SCORE_ONLY)) ? (int64_t)(nn * 4 * (size_t)cigar_cap) : 0);
 	return finish_stats(ctx);
+}
+
+int pansvr_ksw_extd2_batch(pansvr_ksw_ctx *ctx, int64_t n, const uint8_t *qseq, int64_t qseq_bytes, const int64_t *qoff,
+                           const int32_t *qlen, const uint8_t *tseq, int64_t tseq_bytes, const int64_t *toff,
+                           const int32_t *tlen, const pansvr_ksw_params_t *params, int32_t *results, uint32_t *cigar,
+                           int32_t cigar_cap)
+{
+	return drained(ctx, batch_impl(ctx, n, qseq, qseq_bytes, qoff, qlen, tseq, tseq_bytes, toff, tlen, params, results, cigar, cigar_cap));
 }
 
 int pansvr_int_alu_peak(pansvr_ksw_ctx *ctx, double *gops)

@@ -113,3 +113,54 @@ def test_device_list_one_process_same_bytes():
         del os.environ["PANSVR_SUB_PAIRS"]
     assert first_diff(hdr + sam, read(demo.ref_sam)) is None
     assert hdr + ori == read(demo.ref_ori)
+
+
+@pytest.mark.parametrize("name,piece_pairs", [("multi_allele", 41), ("n_bases", 64)])
+def test_pieces_dealt_to_two_contexts_same_bytes(name, piece_pairs, tmp_path):
+    """SURVEY.md 8e on one GPU: the input is dealt piece by piece to two contexts (what two ranks of `bench.py --gpus 2` are), each
+    realigns its pieces in one pansvr_aln_pieces call from its own thread, and the in-order passes follow each other from context
+    to context through the stream-state files.  Joined in piece order the output is the reference's -- with rand() ties at almost
+    every pair, and with N bases (pairs the host path finishes in their turn)."""
+    import ctypes
+    import threading
+    need_ref_tools()
+    demo = get_demo(name)
+    lines = read(demo.data.reads_fq).split(b"\n")
+    n_pairs = len([1 for x in lines if x]) // 8
+    cuts = list(range(0, n_pairs, piece_pairs)) + [n_pairs]
+    texts = [b"\n".join(lines[8 * b:8 * e]) + b"\n" for b, e in zip(cuts[:-1], cuts[1:])]
+    head = b"\n".join(lines[:4]) + b"\n"
+    assert len(texts) >= 4
+    world = 2
+    ctxs = [aln.AlnContext(demo.data.index_dir, demo.data.header_sam, threads=2) for _ in range(world)]
+    results, errors = {}, []
+
+    def run(rank):
+        try:
+            ctx = ctxs[rank]
+            ctx.prime_read_stats(head)
+            mine = [b for b in range(len(texts)) if b % world == rank]
+            bufs = [ctypes.create_string_buffer(texts[b], len(texts[b])) for b in mine]
+            pieces = [(ctypes.addressof(buf), len(texts[b]), str(tmp_path / f"b{b}") if b > 0 else None,
+                       str(tmp_path / f"b{b + 1}") if b + 1 < len(texts) else None) for b, buf in zip(mine, bufs)]
+            (sa, sn), (oa, on), per, release = ctx.align_pieces(pieces)
+            sam, ori = ctypes.string_at(sa, sn), ctypes.string_at(oa, on)
+            release()
+            so = oo = 0
+            for b, (ps, po) in zip(mine, per):
+                results[b] = (sam[so:so + ps], ori[oo:oo + po]); so += ps; oo += po
+            assert so == sn and oo == on
+        except Exception as e:  # noqa: BLE001
+            errors.append(e)
+
+    th = [threading.Thread(target=run, args=(r,)) for r in range(world)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join(300)
+    hdr = ctxs[0].header_text().encode()
+    for c in ctxs:
+        c.close()
+    assert not errors, errors
+    assert first_diff(hdr + b"".join(results[b][0] for b in range(len(texts))), read(demo.ref_sam)) is None
+    assert hdr + b"".join(results[b][1] for b in range(len(texts))) == read(demo.ref_ori)

@@ -168,3 +168,32 @@ def test_long_query_narrow_band_goes_generic(ksw_ctx):
         res, cig = ksw_ctx.extd2_batch(b, cigar_cap=64)
         r0, c0, _ = pyoracle.run(b, "oracle", threads=4, cigar_cap=64)
         assert_same(r0, c0, res, cig, b.name)
+
+
+def test_contexts_in_flight_with_different_query_lengths():
+    """Several contexts launch the same kernel variants at the same time with different shared-memory sizes (the sub-blocks of
+    fc_aln in flight, each with its own longest query).  The limit on a kernel's dynamic shared memory is a property of the
+    function, so a context must not lower it under another one's launch (round 2: intermittent "invalid argument")."""
+    import threading
+    from pansvr_b200 import ksw
+    p = synth.KswParams(w=30)                                              # every task wider than the band: one TEAM variant for all lengths
+    batches = [synth.fuzz_batch(1500, 77, max_len=100, params=p), synth.fuzz_batch(1500, 78, max_len=700, params=p)]
+    want = [pyoracle.run(b, "oracle", threads=4, cigar_cap=64) for b in batches]
+    errors = []
+
+    def work(k):
+        try:
+            ctx = ksw.KswContext(0)
+            for _ in range(40):
+                res, cig = ctx.extd2_batch(batches[k], cigar_cap=64)
+                assert_same(want[k][0], want[k][1], res, cig, f"context {k}")
+            ctx.close()
+        except Exception as e:  # noqa: BLE001
+            errors.append(repr(e))
+
+    th = [threading.Thread(target=work, args=(k,)) for k in (0, 1, 0, 1)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    assert not errors, errors[:2]
