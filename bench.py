@@ -306,7 +306,7 @@ def main():
 
     # ---- gather the per-rank device counters (sums) on rank 0
     keys = ("reads", "mems", "ksw_tasks", "ksw_cells", "kernel_launches", "h2d_bytes", "d2h_bytes", "seed_probes",
-            "in_order_seconds", "in_order_pairs", "in_order_draws", "host_pairs")
+            "in_order_seconds", "in_order_pairs", "in_order_draws", "host_pairs", "tie_pairs")
     vec = [float(st[k]) for k in keys] + [float(e_st[k]) for k in keys]
     mx = [st["seed_kernel_ms"], st["ksw_kernel_ms"], st["stage_kernel_ms"]] + list(st["stage_seconds"])
     pmx = [pst["seed_kernel_ms"], pst["ksw_kernel_ms"], pst["stage_kernel_ms"], float(pst["ksw_cells"]), float(pst["seed_probes"]), float(pst["mems"])] + list(pst["stage_kernel_ms_by"])
@@ -396,6 +396,7 @@ def main():
                                      **dict(zip(("records_ori_encode", "seeding_", "merge_chain", "ksw_plan", "resolve", "cell_count", "pair_probe_finalize", "sam_text"), pmx[6:14]))},
         "in_order_chain": {"seconds_per_step": tot["in_order_seconds"] / args.steps, "pairs_with_draws_per_step": tot["in_order_pairs"] / args.steps,
                            "draws_per_step": tot["in_order_draws"] / args.steps, "host_path_pairs_per_step": tot["host_pairs"] / args.steps,
+                           "pairs_finished_in_order_from_device_results_per_step": tot["tie_pairs"] / args.steps,
                            "note": "the in-order passes over the reference's rand() stream, summed over all ranks: the one part of the stage that is sequential "
                                    "from pair to pair (one piece after the other, across ranks); everything else overlaps -- the lower bound of a step at any N"},
         "parity": parity,

@@ -169,7 +169,8 @@ typedef struct {
 	double in_order_seconds;    /* time inside the in-order sections, waiting for the turn not included */
 	int64_t in_order_pairs;     /* pairs that drew at least one random number */
 	int64_t in_order_draws;     /* rand() calls replayed */
-	int64_t host_pairs;         /* pairs the device path handed to the host path ('N', random_r sampling, ties that change the outcome) */
+	int64_t host_pairs;         /* pairs the device path handed to the host path ('N', random_r sampling) */
+	int64_t tie_pairs;          /* pairs whose rand() ties decide their outcome: finished by the in-order pass from the device's seeds, chains and candidates */
 } pansvr_aln_stats_t;
 
 typedef struct pansvr_aln_ctx pansvr_aln_ctx;

@@ -29,7 +29,7 @@ class AlnStatsC(C.Structure):
                 ("kernel_launches", C.c_int64), ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64), ("seed_probes", C.c_int64),
                 ("seed_kernel_ms", C.c_double), ("ksw_kernel_ms", C.c_double), ("stage_kernel_ms", C.c_double),
                 ("stage_kernel_ms_by", C.c_double * 8),
-                ("in_order_seconds", C.c_double), ("in_order_pairs", C.c_int64), ("in_order_draws", C.c_int64), ("host_pairs", C.c_int64)]
+                ("in_order_seconds", C.c_double), ("in_order_pairs", C.c_int64), ("in_order_draws", C.c_int64), ("host_pairs", C.c_int64), ("tie_pairs", C.c_int64)]
 
 
 def _bind(lib):
@@ -182,7 +182,7 @@ class AlnContext:
         self.lib.pansvr_aln_last_stats(self.h, C.byref(st))
         d = {k: getattr(st, k) for k in ("reads", "mems", "ksw_tasks", "ksw_cells", "deferred_pairs", "kernel_launches", "h2d_bytes",
                                          "d2h_bytes", "seed_probes", "seed_kernel_ms", "ksw_kernel_ms", "stage_kernel_ms",
-                                         "in_order_seconds", "in_order_pairs", "in_order_draws", "host_pairs")}
+                                         "in_order_seconds", "in_order_pairs", "in_order_draws", "host_pairs", "tie_pairs")}
         d["stage_seconds"] = list(st.stage_seconds)
         d["stage_kernel_ms_by"] = list(st.stage_kernel_ms_by)
         return d

@@ -731,7 +731,7 @@ int pansvr_aln_last_stats(const pansvr_aln_ctx *c, pansvr_aln_stats_t *out)
 	const AlnPipeline::Stats &s = c->pipe->stats;
 	out->reads = (int64_t)s.reads; out->mems = (int64_t)s.mems; out->ksw_tasks = (int64_t)s.ksw_tasks; out->ksw_cells = (int64_t)s.ksw_cells;
 	out->deferred_pairs = (int64_t)s.deferred_pairs;
-	out->in_order_seconds = s.t_in_order; out->in_order_pairs = (int64_t)s.in_order_pairs; out->in_order_draws = (int64_t)s.in_order_draws; out->host_pairs = (int64_t)s.host_pairs;
+	out->in_order_seconds = s.t_in_order; out->in_order_pairs = (int64_t)s.in_order_pairs; out->in_order_draws = (int64_t)s.in_order_draws; out->host_pairs = (int64_t)s.host_pairs; out->tie_pairs = (int64_t)s.tie_pairs;
 	for (int i = 0; i < 8; ++i) out->stage_seconds[i] = s.t_stage[i];
 	out->kernel_launches = s.dev.launches; out->h2d_bytes = s.dev.h2d_bytes; out->d2h_bytes = s.dev.d2h_bytes;
 	out->seed_probes = s.dev.seed_probes;
@@ -921,6 +921,7 @@ int pansvr_fc_aln_main(int argc, char **argv)
 		        (unsigned long long)nbad);
 	pansvr_aln_stats_t st;
 	pansvr_aln_last_stats(ctx, &st);
+	fprintf(stderr, "pansvr_b200 fc_aln: %ld pairs finished in order from device results, %ld by the host path\n", (long)st.tie_pairs, (long)st.host_pairs);
 	fprintf(stderr, "pansvr_b200 fc_aln: %ld reads, %ld MEMs, %ld ksw tasks; stage seconds A %.3f B %.3f C %.3f D %.3f E %.3f F %.3f parse %.3f emit %.3f\n",
 	        (long)st.reads, (long)st.mems, (long)st.ksw_tasks, st.stage_seconds[0], st.stage_seconds[1], st.stage_seconds[2], st.stage_seconds[3],
 	        st.stage_seconds[4], st.stage_seconds[5], st.stage_seconds[6], st.stage_seconds[7]);

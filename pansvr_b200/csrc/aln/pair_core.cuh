@@ -17,12 +17,14 @@
 #include <stdint.h>
 
 #include "stages_core.cuh"
+#include "refrand.hpp"
 
 namespace pansvr {
 
 enum { PR_FORWARD = 1, PR_REVERSE = 0, PR_MAX_OUTPUT = 6, PR_MAX_RES = 12, PR_MAX_SCRIPT = 12, PR_MAX_LEAVES = 24, PR_MAX_EVENTS = 32 };
 enum { PR_MIN_ALN_SCORE = 40 };
-enum { PR_REDO_HOST = 255 };                                       // the pair goes back to the host path
+enum { PR_REDO_HOST = 255 };                                       // the pair goes back to the host path ('N', random_r sampling)
+enum { PR_REDO_TIES = 254 };                                       // its rand() ties decide the outcome: finished in its turn of the in-order pass, from what the device computed
 const uint32_t PR_U32MAX = 0xffffffffu;
 
 struct DevOri { uint32_t chr, ref_bg, read_bg, align_score; uint8_t mapq, direction, unmapped, skip; };   // parse_ori_mapping_rst + RR:413-414
@@ -47,11 +49,15 @@ struct DevFinal {                                                  // what the r
 enum { FIN_PRIMARY = 1, FIN_P_ORI = 2, FIN_HAS_MATE = 4, FIN_SECONDARY = 8, FIN_P_FWD = 16, FIN_S_FWD = 32, FIN_P_CIGAR_OK = 64 };
 struct DevPairFinal { int32_t max_score, cur_isize; uint8_t gain, proper, valid, pad; };
 
-struct DevTap {                                                    // RandTap of pipeline.cpp in probe mode
+struct DevTap {                                                    // RandTap of pipeline.cpp: scripted (the probe), or the reference's stream itself (host only)
 	uint32_t calls, script_len; bool too_deep;
 	uint8_t script[PR_MAX_SCRIPT], moduli[PR_MAX_SCRIPT];
+	void *real = nullptr;                                          // host: a GlibcRandom to draw from (rand() % m, RR:247, RRH:553)
 	SEED_HD int32_t draw(int32_t m)
 	{
+#if !defined(__CUDA_ARCH__)
+		if (real) { ++calls; return (int32_t)(((GlibcRandom*)real)->next() % m); }
+#endif
 		const uint32_t k = calls++;
 		if (k >= PR_MAX_SCRIPT || m > 255) { too_deep = true; return 0; }
 		moduli[k] = (uint8_t)m;
@@ -342,7 +348,9 @@ SEED_HD void dev_pair_up(const PairIndexView &ix, const PairOpts &o, const PairS
 //   dev_explore_store   one read: its candidates and the number of rand() draws its ties make (-1: the outcomes differ)
 //   dev_probe_pair      the pair: pairing against the scripted generator.  pr.redo = what the in-order pass has to do for it:
 //     0 nothing; 1 advance the stream by draws0 + draws1; 2 the same, then redraw the pairing ties from the events;
-//     PR_REDO_HOST: the host path finishes this pair (outcomes of a read's ties differ, too many events, a read the device handed back)
+//     PR_REDO_TIES: the outcomes of a read's ties differ (or the pairing has too many events): the in-order pass finishes the pair
+//     against the stream itself, from the seeds, chains and candidates the device has (dev_finish_pair_in_order);
+//     PR_REDO_HOST (set by the caller): the host path finishes this pair (a read the device handed back)
 SEED_HD void dev_explore_store(const PairIndexView &ix, const ReadView &R, DevPairState &st, int k)
 {
 	DevTap probe;
@@ -357,7 +365,7 @@ SEED_HD void dev_probe_pair(const PairIndexView &ix, const PairOpts &o, const De
 {
 	pr.redo = 0; pr.draws0 = pr.draws1 = 0; pr.ev_cnt = 0; pr.tie_mask = 0;
 	const int c0 = st.draws[0], c1 = st.draws[1];
-	if (c0 < 0 || c1 < 0) { pr.redo = PR_REDO_HOST; return; }
+	if (c0 < 0 || c1 < 0) { pr.redo = PR_REDO_TIES; return; }
 	pr.draws0 = (uint8_t)c0; pr.draws1 = (uint8_t)c1;
 	PairSide S[2];
 	S[0].res = st.res[0]; S[0].n = st.n[0]; S[0].ori = ori[0];
@@ -368,7 +376,23 @@ SEED_HD void dev_probe_pair(const PairIndexView &ix, const PairOpts &o, const De
 	dev_pair_up(ix, o, S, st.pe, probe, &ev);
 	if (probe.calls == 0) { pr.redo = (c0 + c1) ? 1 : 0; pr.ev_cnt = 0; pr.tie_mask = 0; }
 	else if (!ev.overflow) pr.redo = 2;
-	else pr.redo = PR_REDO_HOST;
+	else pr.redo = PR_REDO_TIES;
+}
+
+// A pair whose ties decide its outcome, in its turn of the in-order pass: both reads finished and paired against the stream
+// itself (tap.real), exactly the reference's calls in the reference's order (RR:416-475 for each read, then RRH:434-499).
+// R[k]: the reads' seeds, chain tables and candidates as the device left them (host copies); st receives what dev_finalize_pair
+// and the record text read.
+SEED_HD void dev_finish_pair_in_order(const PairIndexView &ix, const PairOpts &o, const ReadView *R, DevPairState &st, DevTap &tap)
+{
+	PairSide S[2];
+	for (int k = 0; k < 2; ++k) {
+		int n = dev_finish_read(ix, R[k], st.res[k], tap);
+		if (n < 0) n = 0;
+		st.n[k] = (uint8_t)n; st.draws[k] = 0;
+		S[k].res = st.res[k]; S[k].n = n; S[k].ori = R[k].ori;
+	}
+	dev_pair_up(ix, o, S, st.pe, tap, nullptr);
 }
 
 // What a pair takes from the reference's rand() stream when nothing about it depends on the numbers but the pairing winner:
@@ -390,7 +414,7 @@ SEED_HD void dev_finalize_pair(const PairIndexView &ix, const PairOpts &o, const
 	for (int k = 0; k < 2; ++k) { DevFinal &f = fin[k]; f.flags = 0; f.p_ins = f.p_ncig = 0; f.p_chr = f.p_ref_bg = f.p_align = f.p_chain = f.p_mapq = 0; f.p_cand = f.p_sv = f.p_mate_sv = -1; f.mate_chr = f.mate_ref_bg = 0; f.s_chr = f.s_ref_bg = f.s_read_bg = f.s_align = 0; f.s_sv = -1; }
 	pf.max_score = 0; pf.cur_isize = 0; pf.gain = pf.proper = 0; pf.valid = 0; pf.pad = 0;
 	const uint8_t redo = pr.redo;
-	if (redo == PR_REDO_HOST) return;
+	if (redo == PR_REDO_HOST || redo == PR_REDO_TIES) return;         // (a pair finished in order arrives with redo 0 and its state in place)
 	PairSide S[2];
 	for (int k = 0; k < 2; ++k) { S[k].res = st.res[k]; S[k].n = st.n[k]; S[k].ori = ori[k]; }
 	DevPE pe = st.pe;

@@ -23,6 +23,7 @@ struct AlnPipeline::DevBuffers {                                  // one block's
 	HostVec<DevRead> reads;
 	HostVec<DevRec> recs;
 	HostVec<int32_t> drawn;                                       // what the in-order pass took from the rand() stream for the block's device pairs
+	HostVec<uint32_t> tie_pair; HostVec<DevPairState> tie_done;   // the pairs the in-order pass finished itself, and what came out
 	HostVec<uint32_t> host_len;
 	DevStageOut out;
 };
@@ -1156,6 +1157,11 @@ AlnPipeline::AlnPipeline(const DebgaIndex &idx, const AlnOptions &o, SeedService
 		dev_all_.push_back(b); dev_free_.push_back(b);
 	}
 	sites_.push_back(DevSite{device_, seeds_});
+	host_sv_.resize(idx_.sv_info.size() * sizeof(DevSv) + sizeof(DevSv));
+	for (size_t i = 0; i < idx_.sv_info.size(); ++i) {
+		DevSv v; v.chr_id = idx_.sv_info[i].chr_id; v.st_pos = (uint32_t)idx_.sv_info[i].st_pos; v.end_offset = idx_.sv_info[i].end_offset; v.pad = 0;
+		memcpy(host_sv_.data() + i * sizeof(DevSv), &v, sizeof v);
+	}
 	if (const char *e = getenv("PANSVR_TRIP1")) { const int v = atoi(e); if (v > 0) trip1_cap_ = v; }
 	reset();
 }
@@ -1926,24 +1932,66 @@ bool AlnPipeline::align_block_dev(const char *base, size_t text_bytes, const Fas
 			fclose(f);
 		}
 	}
-	// ---- the pairs the host path finishes: 'N' / 'n' in a read, a unipath that needs random_r, ties that change the outcome
+	// ---- the pairs the host path finishes: 'N' / 'n' in a read, a unipath that needs random_r
+	// (PANSVR_TIES_ON_HOST_PATH=1, tests: also the pairs whose ties decide their outcome, as before round 2's last change)
+	static const bool ties_on_host_path = getenv("PANSVR_TIES_ON_HOST_PATH") != nullptr;
 	std::vector<uint32_t> host_list;
 	size_t io_pairs = 0;
-	for (size_t p = 0; p < n_pairs; ++p) { if (o.redo[p] == PR_REDO_HOST) host_list.push_back((uint32_t)p); else io_pairs += o.redo[p] != 0; }
+	for (size_t p = 0; p < n_pairs; ++p) {
+		const uint8_t rd = o.redo[p];
+		if (rd == PR_REDO_HOST || (ties_on_host_path && rd == PR_REDO_TIES)) host_list.push_back((uint32_t)p);
+		else io_pairs += rd != 0;
+	}
 	std::vector<FastqRec> hrecs(2 * host_list.size());
 	for (size_t s = 0; s < host_list.size(); ++s) { hrecs[2 * s] = rec_at(2 * (size_t)host_list[s]); hrecs[2 * s + 1] = rec_at(2 * (size_t)host_list[s] + 1); }
 	// in-order pass of the device path's pairs: each advances the stream by a count the probe knows (its reads' draws, one per tied
 	// pairing event), so the pass only takes the numbers -- draw_off[p] of them before pair p -- and the second trip redraws the
-	// pairing winners from them on the device (RRH:553); the host path's pairs take their turn in between, against the stream itself
+	// pairing winners from them on the device (RRH:553).  In between, in their turn: the pairs whose ties decide their outcome,
+	// finished here against the stream itself from the seeds, chain tables and candidates the device computed (no stage is run
+	// again for them); and the host path's pairs.
 	const size_t n_drawn = n_pairs ? o.draw_off[n_pairs] : 0;
 	db->drawn.resize(n_drawn + 1);
-	size_t taken = 0;
+	const size_t n_ties = ties_on_host_path ? 0 : o.ties.size();
+	db->tie_pair.resize(n_ties); db->tie_done.resize(n_ties);
+	size_t taken = 0, tie_cur = 0;
+	std::vector<uint8_t> tie_used;
+	PairIndexView host_pix_;
+	host_pix_.chr_search_index = idx.chr_search_index.data(); host_pix_.chr_end_n = idx.chr_end_n.data(); host_pix_.sv = (const DevSv*)host_sv_.data();
+	auto finish_tie = [&](size_t k) {
+		const DevTie &t = o.ties[k];
+		ReadView R[2];
+		tie_used.assign((size_t)(t.seed_off[4] - t.seed_off[0]) + 1, 0);
+		for (int m = 0; m < 2; ++m) {
+			for (int s2 = 0; s2 < 2; ++s2) {
+				const uint32_t rel = t.seed_off[2 * m + s2] - t.seed_off[0], at = t.seed_at + rel;
+				R[m].v[s2] = o.tie_seeds.data() + at; R[m].dist[s2] = o.tie_dist.data() + at; R[m].pre[s2] = o.tie_pre.data() + at;
+				R[m].used[s2] = tie_used.data() + rel; R[m].n[s2] = t.seed_off[2 * m + s2 + 1] - t.seed_off[2 * m + s2];
+			}
+			R[m].cands = o.tie_cands.data();
+			R[m].cand_b = t.cand_at + (t.cand_off[m] - t.cand_off[0]); R[m].cand_e = t.cand_at + (t.cand_off[m + 1] - t.cand_off[0]);
+			R[m].ori = t.ori[m];
+		}
+		DevTap tap;
+		tap.restart(0);
+		tap.real = &rand_;
+		DevPairState &st = db->tie_done[k];
+		memset((void*)&st, 0, sizeof st);
+		dev_finish_pair_in_order(host_pix_, in.pair_opts, R, st, tap);
+		const int32_t delta = (int32_t)t.cand_off[0] - (int32_t)t.cand_at;     // candidate numbers back to the device's
+		for (int m = 0; m < 2; ++m) for (int x = 0; x < st.n[m]; ++x) if (st.res[m][x].cand >= 0) st.res[m][x].cand += delta;
+		db->tie_pair[k] = t.pair;
+	};
 	BlockHooks H;
 	H.global_pair = host_list.data();
 	H.fast_until = [&](uint64_t upto) {
-		const size_t to = o.draw_off[(size_t)std::min<uint64_t>(upto, n_pairs)];
 		int32_t *r = db->drawn.data();
-		for (; taken < to; ++taken) r[taken] = rand_.next();
+		for (;;) {
+			const uint64_t next_tie = tie_cur < n_ties ? (uint64_t)o.ties[tie_cur].pair : ~(uint64_t)0;
+			const size_t to = o.draw_off[(size_t)std::min<uint64_t>(std::min(upto, next_tie), n_pairs)];
+			for (; taken < to; ++taken) r[taken] = rand_.next();
+			if (next_tie >= upto) break;
+			finish_tie(tie_cur++);
+		}
 	};
 	H.emit = [&](const std::function<void(size_t, std::string&, std::string&)> &text_host, std::string &e2) -> bool {
 		double t1 = now();
@@ -1958,7 +2006,7 @@ bool AlnPipeline::align_block_dev(const char *base, size_t text_bytes, const Fas
 		bool got = false;
 		o.text_dest = [&](size_t total) -> char* { char *p = out.place ? out.place(total) : nullptr; out.place_called = true; got = p != nullptr; return p; };
 		trace_host(seq, "trip2_begin");
-		const bool fin_ok = stage_service_finalize(db->svc, in.pair_opts, opt.not_ori ? 1 : 0, n_pairs, db->drawn.data(), n_drawn, db->host_len.data(), o, out.sam_text, e2);
+		const bool fin_ok = stage_service_finalize(db->svc, in.pair_opts, opt.not_ori ? 1 : 0, n_pairs, db->drawn.data(), n_drawn, db->host_len.data(), db->tie_pair.data(), db->tie_done.data(), n_ties, o, out.sam_text, e2);
 		o.text_dest = nullptr;
 		trace_host(seq, "trip2_end");
 		if (!fin_ok) return false;
@@ -2043,7 +2091,7 @@ bool AlnPipeline::align_block_dev(const char *base, size_t text_bytes, const Fas
 	if (ok) {
 		std::lock_guard<std::mutex> lk(stats_m_);
 		stats.reads += 2 * (n_pairs - host_list.size());
-		stats.in_order_pairs += io_pairs; stats.in_order_draws += n_drawn; stats.host_pairs += host_list.size();
+		stats.in_order_pairs += io_pairs; stats.in_order_draws += n_drawn; stats.host_pairs += host_list.size(); stats.tie_pairs += n_ties;
 		stats.mems += o.mem_off[2 * nd]; stats.ksw_tasks += o.n_tasks; stats.ksw_cells += o.n_cells;
 		stats.dev.add(o.dev); stats.dev.seed_probes += (int64_t)o.probes;
 		o.dev = DevCounters();

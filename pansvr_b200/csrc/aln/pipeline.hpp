@@ -194,7 +194,7 @@ public:
 	void chain_at(uint64_t seq, const char *await, const char *publish);
 	// a block that ends without having had its in-order section (an error on its way) must still let the blocks behind it have theirs
 	void pass_turn_if_pending(uint64_t seq);
-	struct Stats { uint64_t reads = 0, probes_reads = 0, mems = 0, ksw_tasks = 0, ksw_cells = 0, deferred_pairs = 0, in_order_pairs = 0, in_order_draws = 0, host_pairs = 0;
+	struct Stats { uint64_t reads = 0, probes_reads = 0, mems = 0, ksw_tasks = 0, ksw_cells = 0, deferred_pairs = 0, in_order_pairs = 0, in_order_draws = 0, host_pairs = 0, tie_pairs = 0;
 	               double t_in_order = 0;
 	               double t_stage[8] = {0, 0, 0, 0, 0, 0, 0, 0}; DevCounters dev; } stats;   // A..F, FASTQ parse, output assembly
 	AlnOptions opt;                   // stat_set / read_len / isize_* are filled from the first comment
@@ -240,6 +240,7 @@ private:
 	GlibcRandom rand_r_[2];           // per-handler random_r states (RRH:339-340), seeded from rand_ at start-up
 	int min_filter_score_ = 0;
 	std::string await_path_;              // guarded by turn_m_
+	std::vector<uint8_t> host_sv_;        // per-anchor (chr_id, st_pos, end_offset) as the device stages see them (DevSv), for the pairs finished in order on the host
 	std::map<uint64_t, std::pair<std::string, std::string>> chain_;   // seq -> (await, publish); guarded by turn_m_
 	bool write_streams(const std::string &path, const StreamState &s);
 	friend struct Impl;

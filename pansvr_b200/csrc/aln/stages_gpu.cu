@@ -322,7 +322,8 @@ bool stage_service_run(StageService *s, const DevStageIn &in, DevStageOut &out, 
 	return ok;
 }
 
-bool stage_service_finalize(StageService *s, const PairOpts &o, int not_ori, size_t n_pairs, const int32_t *drawn, size_t n_drawn, const uint32_t *host_len, DevStageOut &out,
+bool stage_service_finalize(StageService *s, const PairOpts &o, int not_ori, size_t n_pairs, const int32_t *drawn, size_t n_drawn, const uint32_t *host_len,
+                            const uint32_t *tie_pair, const DevPairState *tie_done, size_t n_ties, DevStageOut &out,
                             HostVec<char> &text_out, std::string &err)
 {
 	if (cudaSetDevice(s->device) != cudaSuccess) { err = "cudaSetDevice failed"; return false; }
@@ -330,7 +331,7 @@ bool stage_service_finalize(StageService *s, const PairOpts &o, int not_ori, siz
 	be.failed = false; be.why.clear(); be.dev = DevCounters();
 	TextTables T = s->tt;
 	T.not_ori = not_ori;
-	const bool ok = run_device_finalize(be, s->pix, o, T, n_pairs, drawn, n_drawn, host_len, out, text_out, err);
+	const bool ok = run_device_finalize(be, s->pix, o, T, n_pairs, drawn, n_drawn, host_len, tie_pair, tie_done, n_ties, out, text_out, err);
 	be.sync();
 	be.collect_laps();
 	out.dev.add(be.dev);

@@ -31,7 +31,7 @@ namespace pansvr {
 enum DevSlot {
 	SL_TEXT, SL_READS, SL_BITS, SL_LIST, SL_FLAGS, SL_MEM_CNT, SL_MEM_OFF, SL_MEMS, SL_MEMS_TMP, SL_NVU, SL_SEED_CNT, SL_SEED_OFF,
 	SL_SEEDS, SL_SEEDS_TMP, SL_DIST, SL_PRE, SL_PLAN_CNT, SL_PLAN_OFF, SL_CANDS, SL_PIECES, SL_QLEN, SL_TLEN, SL_QOFF, SL_TOFF,
-	SL_Q, SL_T, SL_RES, SL_KCIG, SL_CIGS, SL_MISC, SL_SCAN_TMP, SL_USED, SL_ORI, SL_PSTATE, SL_PROBE, SL_WIN, SL_FINAL, SL_PFINAL, SL_RECS, SL_HOSTLEN, SL_TXT_LEN, SL_TXT_OFF, SL_TXT, SL_NL_CNT, SL_NL_OFF, SL_LINES, SL_LAY_CNT, SL_LAY_OFF, SL_SEL_PAIR, SL_SEL_FIN, SL_SEL_PFIN, SL_DRAW_CNT, SL_DRAW_OFF, SL_REDO, SL_DRAWN, SL_MEMS_KEPT, SL_WORK_KEY, SL_WORK_IDX, SL_WORK_PERM, SL_SORT_KEYS, SL_SORT_TMP, SL_COUNT
+	SL_Q, SL_T, SL_RES, SL_KCIG, SL_CIGS, SL_MISC, SL_SCAN_TMP, SL_USED, SL_ORI, SL_PSTATE, SL_PROBE, SL_WIN, SL_FINAL, SL_PFINAL, SL_RECS, SL_HOSTLEN, SL_TXT_LEN, SL_TXT_OFF, SL_TXT, SL_NL_CNT, SL_NL_OFF, SL_LINES, SL_LAY_CNT, SL_LAY_OFF, SL_SEL_PAIR, SL_SEL_FIN, SL_SEL_PFIN, SL_DRAW_CNT, SL_DRAW_OFF, SL_REDO, SL_DRAWN, SL_MEMS_KEPT, SL_WORK_KEY, SL_WORK_IDX, SL_WORK_PERM, SL_SORT_KEYS, SL_SORT_TMP, SL_TIE_CNT, SL_TIE_OFF, SL_TIE, SL_TIE_SEEDS, SL_TIE_DIST, SL_TIE_PRE, SL_TIE_CANDS, SL_TIE_PAIR, SL_TIE_DONE, SL_COUNT
 };
 
 // ---- functors (one element of work each; plain data members only, so they can be passed to a kernel by value)
@@ -259,6 +259,44 @@ struct FnProbe {                                                   // one pair =
 		redo[p] = pr.redo;
 	}
 };
+// The pairs whose ties decide their outcome (PR_REDO_TIES) are finished by the in-order pass on the host, from what the device
+// has for them: a pair's seeds (with the chain tables) and its candidates are contiguous ranges, copied into packed arrays that go
+// down with the rest of the first trip's results.
+struct DevTie { uint32_t pair, seed_at, cand_at; uint32_t seed_off[5], cand_off[3]; DevOri ori[2]; };   // seed_off / cand_off: the pair's global offsets (4 strands / 2 reads)
+enum { TIE_FIELDS = 3 };                                           // pairs, seeds, candidates
+struct FnTieCount {
+	const uint8_t *redo; const uint32_t *seed_off, *cand_off; size_t n_pairs; uint32_t *cnt;   // cnt: TIE_FIELDS planes of (n_pairs + 1)
+	SEED_HD void operator()(size_t p) const
+	{
+		const bool tie = redo[p] == PR_REDO_TIES;
+		const size_t P = n_pairs + 1;
+		cnt[p] = tie ? 1u : 0u;
+		cnt[P + p] = tie ? seed_off[4 * p + 4] - seed_off[4 * p] : 0u;
+		cnt[2 * P + p] = tie ? cand_off[2 * p + 2] - cand_off[2 * p] : 0u;
+	}
+};
+struct FnTieGather {
+	const uint8_t *redo; const uint32_t *seed_off, *cand_off, *off; size_t n_pairs;
+	const DevSeed *seeds; const float *dist; const int32_t *pre; const DevCand *cands; const DevOri *ori;
+	DevTie *tie; DevSeed *t_seeds; float *t_dist; int32_t *t_pre; DevCand *t_cands;
+	SEED_HD void operator()(size_t p) const
+	{
+		if (redo[p] != PR_REDO_TIES) return;
+		const size_t P = n_pairs + 1;
+		DevTie t;
+		t.pair = (uint32_t)p; t.seed_at = off[P + p]; t.cand_at = off[2 * P + p];
+		for (int k = 0; k < 5; ++k) t.seed_off[k] = seed_off[4 * p + k];
+		for (int k = 0; k < 3; ++k) t.cand_off[k] = cand_off[2 * p + k];
+		t.ori[0] = ori[2 * p]; t.ori[1] = ori[2 * p + 1];
+		tie[off[p]] = t;
+		for (uint32_t k = t.seed_off[0], d = t.seed_at; k < t.seed_off[4]; ++k, ++d) { t_seeds[d] = seeds[k]; t_dist[d] = dist[k]; t_pre[d] = pre[k]; }
+		for (uint32_t k = t.cand_off[0], d = t.cand_at; k < t.cand_off[2]; ++k, ++d) t_cands[d] = cands[k];
+	}
+};
+struct FnTieScatter {                                              // second trip: the pairs finished in order get their state, and count as decided
+	const uint32_t *pair; const DevPairState *done; DevPairState *state; DevProbe *probe;
+	SEED_HD void operator()(size_t k) const { state[pair[k]] = done[k]; probe[pair[k]].redo = 0; }
+};
 struct FnFinalize {
 	PairIndexView ix; PairOpts o; const DevOri *ori; DevPairState *state; const DevProbe *probe; const uint32_t *draw_off; const int32_t *drawn; const DevCand *cands; const DevCigar *cigs;
 	DevFinal *fin; DevPairFinal *pfin;
@@ -327,6 +365,8 @@ struct DevStageOut {                                               // host side,
 	HostVec<DevProbe> pair_probe;                                  // n / 2: the probe's record of each pair (want_tables only; it stays on the device)
 	HostVec<uint8_t> redo;                                         // n / 2: 0 nothing drawn, 1 / 2 advances the stream by a known count, PR_REDO_HOST: the host path's pair
 	HostVec<uint32_t> draw_off;                                    // n / 2 + 1: prefix sums of the pairs' draw counts = each pair's place in the block's drawn numbers
+	// the pairs the in-order pass finishes itself (PR_REDO_TIES), in input order, with their seeds / chain tables / candidates
+	HostVec<DevTie> ties; HostVec<DevSeed> tie_seeds; HostVec<float> tie_dist; HostVec<int32_t> tie_pre; HostVec<DevCand> tie_cands;
 	// after run_device_finalize: the results of the pairs that may go to the `-p` output (pair index, both reads, pair) -- or, if
 	// sel_all, of every pair (fin: n, pfin: n / 2)
 	HostVec<uint32_t> sel_pair; HostVec<DevFinal> sel_fin; HostVec<DevPairFinal> sel_pfin; bool sel_all = false;
@@ -346,7 +386,7 @@ bool run_device_stages(BE &be, const IndexView &ix, const uint64_t *d_pos, const
 	const size_t n = in.n_reads;
 	out.n_tasks = out.n_cells = out.probes = 0;
 	out.flags.resize(n); out.mem_off.resize(2 * n + 1); out.seed_off.resize(2 * n + 1); out.cand_off.resize(n + 1);
-	out.seeds.clear(); out.dist.clear(); out.pre.clear(); out.cands.clear(); out.cigs.clear(); out.redo.clear(); out.draw_off.clear();
+	out.seeds.clear(); out.dist.clear(); out.pre.clear(); out.cands.clear(); out.cigs.clear(); out.redo.clear(); out.draw_off.clear(); out.ties.clear();
 	if (n == 0) { out.mem_off[0] = out.seed_off[0] = out.cand_off[0] = 0; return true; }
 	// ---- upload
 	out.parse_ok = true;
@@ -518,6 +558,32 @@ bool run_device_stages(BE &be, const IndexView &ix, const uint64_t *d_pos, const
 		be.d2h(out.redo.data(), d_redo, np);
 		be.d2h(out.draw_off.data(), d_doff, (np + 1) * 4);
 		if (in.want_tables) { out.pair_probe.resize(np); be.d2h(out.pair_probe.data(), d_probe, np * sizeof(DevProbe)); }
+		// the pairs for the in-order pass itself: counted, placed, gathered
+		const size_t TP = np + 1;
+		uint32_t *d_tcnt = be.template buf<uint32_t>(SL_TIE_CNT, TIE_FIELDS * TP), *d_toff = be.template buf<uint32_t>(SL_TIE_OFF, TIE_FIELDS * TP);
+		if (!d_tcnt || !d_toff) { err = "device stages: out of device memory"; return false; }
+		for (int f = 0; f < TIE_FIELDS; ++f) be.zero(d_tcnt + f * TP + np, 4);
+		const DevCand *d_cands_all = be.template buf<DevCand>(SL_CANDS, 0);
+		be.for_each(np, FnTieCount{d_redo, d_seed_off, d_plan_off, np, d_tcnt}, 6);
+		for (int f = 0; f < TIE_FIELDS; ++f) be.scan(d_tcnt + f * TP, d_toff + f * TP, TP);
+		uint32_t ttot[TIE_FIELDS];
+		for (int f = 0; f < TIE_FIELDS; ++f) be.d2h(&ttot[f], d_toff + f * TP + np, 4);
+		be.sync();
+		out.ties.resize(ttot[0]); out.tie_seeds.resize(ttot[1]); out.tie_dist.resize(ttot[1]); out.tie_pre.resize(ttot[1]); out.tie_cands.resize(ttot[2]);
+		if (ttot[0]) {
+			DevTie *d_tie = be.template buf<DevTie>(SL_TIE, ttot[0]);
+			DevSeed *d_ts = be.template buf<DevSeed>(SL_TIE_SEEDS, ttot[1] + 1);
+			float *d_td = be.template buf<float>(SL_TIE_DIST, ttot[1] + 1);
+			int32_t *d_tp = be.template buf<int32_t>(SL_TIE_PRE, ttot[1] + 1);
+			DevCand *d_tc = be.template buf<DevCand>(SL_TIE_CANDS, ttot[2] + 1);
+			if (!d_tie || !d_ts || !d_td || !d_tp || !d_tc) { err = "device stages: out of device memory"; return false; }
+			be.for_each(np, FnTieGather{d_redo, d_seed_off, d_plan_off, d_toff, np, d_seeds, d_dist, d_pre, d_cands_all, d_ori, d_tie, d_ts, d_td, d_tp, d_tc}, 6);
+			be.d2h(out.ties.data(), d_tie, (size_t)ttot[0] * sizeof(DevTie));
+			be.d2h(out.tie_seeds.data(), d_ts, (size_t)ttot[1] * sizeof(DevSeed));
+			be.d2h(out.tie_dist.data(), d_td, (size_t)ttot[1] * 4);
+			be.d2h(out.tie_pre.data(), d_tp, (size_t)ttot[1] * 4);
+			be.d2h(out.tie_cands.data(), d_tc, (size_t)ttot[2] * sizeof(DevCand));
+		}
 		be.sync();
 	}
 	return true;
@@ -561,7 +627,7 @@ struct FnText {                                                    // the SAM re
 // every record in its place (gaps of host_len bytes where the host's pairs go: out.txt_off[2p] is the place of pair p).
 template <class BE>
 bool run_device_finalize(BE &be, const PairIndexView &pix, const PairOpts &o, const TextTables &T, size_t n_pairs, const int32_t *drawn, size_t n_drawn, const uint32_t *host_len,
-                         DevStageOut &out, HostVec<char> &text_out, std::string &err)
+                         const uint32_t *tie_pair, const DevPairState *tie_done, size_t n_ties, DevStageOut &out, HostVec<char> &text_out, std::string &err)
 {
 	out.fin.resize(2 * n_pairs); out.pfin.resize(n_pairs); out.txt_off.resize(2 * n_pairs + 1);
 	out.bad_records = 0;
@@ -579,6 +645,14 @@ bool run_device_finalize(BE &be, const PairIndexView &pix, const PairOpts &o, co
 	be.zero(d_misc, 64);
 	be.zero(d_len + n, 4);
 	const DevOri *d_ori = be.template buf<DevOri>(SL_ORI, 0);
+	if (n_ties) {                                                  // the pairs the in-order pass finished: their state goes in place
+		uint32_t *d_tpair = be.template buf<uint32_t>(SL_TIE_PAIR, n_ties);
+		DevPairState *d_tdone = be.template buf<DevPairState>(SL_TIE_DONE, n_ties);
+		if (!d_tpair || !d_tdone) { err = "device stages: out of device memory"; return false; }
+		be.h2d(d_tpair, tie_pair, n_ties * 4);
+		be.h2d(d_tdone, tie_done, n_ties * sizeof(DevPairState));
+		be.for_each(n_ties, FnTieScatter{d_tpair, d_tdone, be.template buf<DevPairState>(SL_PSTATE, 0), be.template buf<DevProbe>(SL_PROBE, 0)}, 6);
+	}
 	be.for_each(n_pairs, FnFinalize{pix, o, d_ori, be.template buf<DevPairState>(SL_PSTATE, 0), be.template buf<DevProbe>(SL_PROBE, 0), be.template buf<uint32_t>(SL_DRAW_OFF, 0), d_drawn,
 	                                be.template buf<DevCand>(SL_CANDS, 0), be.template buf<DevCigar>(SL_CIGS, 0), d_fin, d_pfin}, 6);
 	// the `-p` candidates: selected on the device, a short list for the host (all of it if the list overflows its room)
@@ -631,7 +705,8 @@ void stage_service_set_scoring(StageService *s, const AlnScores &o, int zdrop); 
 // A service instance holds one block's device state from stage_service_run to stage_service_finalize (two trips with the host's
 // in-order pass in between); blocks in flight at the same time use different instances.
 bool stage_service_run(StageService *s, const DevStageIn &in, DevStageOut &out, std::string &err);
-bool stage_service_finalize(StageService *s, const PairOpts &o, int not_ori, size_t n_pairs, const int32_t *drawn, size_t n_drawn, const uint32_t *host_len, DevStageOut &out,
+bool stage_service_finalize(StageService *s, const PairOpts &o, int not_ori, size_t n_pairs, const int32_t *drawn, size_t n_drawn, const uint32_t *host_len,
+                            const uint32_t *tie_pair, const DevPairState *tie_done, size_t n_ties, DevStageOut &out,
                             HostVec<char> &text_out, std::string &err);
 
 } // namespace pansvr

@@ -127,12 +127,13 @@ bool stage_service_run(StageService *s, const DevStageIn &in, DevStageOut &out, 
 {
 	return run_device_stages(s->be, s->view, s->pos, s->rf, s->pix, in, out, err);
 }
-bool stage_service_finalize(StageService *s, const PairOpts &o, int not_ori, size_t n_pairs, const int32_t *drawn, size_t n_drawn, const uint32_t *host_len, DevStageOut &out,
+bool stage_service_finalize(StageService *s, const PairOpts &o, int not_ori, size_t n_pairs, const int32_t *drawn, size_t n_drawn, const uint32_t *host_len,
+                            const uint32_t *tie_pair, const DevPairState *tie_done, size_t n_ties, DevStageOut &out,
                             HostVec<char> &text_out, std::string &err)
 {
 	TextTables T;
 	T.target_names = s->names.view(); T.sv_print = s->prints.view(); T.sv_id = s->ids.view(); T.not_ori = not_ori;
-	return run_device_finalize(s->be, s->pix, o, T, n_pairs, drawn, n_drawn, host_len, out, text_out, err);
+	return run_device_finalize(s->be, s->pix, o, T, n_pairs, drawn, n_drawn, host_len, tie_pair, tie_done, n_ties, out, text_out, err);
 }
 
 } // namespace pansvr
