@@ -297,3 +297,23 @@ def test_bgzf_gzip_and_pipe_inputs(fc_aln_emul):
     p = subprocess.run([exe, "-t", "2", "-S", "-o", os.path.join(demo.wd, "bad.sam"), "-p", os.path.join(demo.wd, "bad_ori.sam"), demo.data.index_dir, path,
                         demo.data.header_sam], env=env, capture_output=True)
     assert p.returncode != 0 and b"BGZF" in p.stderr
+
+
+def test_tie_pairs_in_order_equal_host_path(fc_aln_emul):
+    """Pairs whose rand() ties decide their outcome are finished by the in-order pass from the device stages' results; with
+    PANSVR_TIES_ON_HOST_PATH=1 the host path re-does them from scratch (the earlier way).  Same files either way, and the
+    reference's, on the data set where a tenth of the pairs are of that kind (tandem-repeat alleles)."""
+    need_ref_tools()
+    demo = get_demo("tandem_repeats")
+    outs = {}
+    for mode in ("in_order", "host_path"):
+        out, ori = os.path.join(demo.wd, f"tie_{mode}.sam"), os.path.join(demo.wd, f"tie_{mode}_ori.sam")
+        if mode == "host_path":
+            os.environ["PANSVR_TIES_ON_HOST_PATH"] = "1"
+        try:
+            fc_aln_emul(demo.data, out, ori, threads=3, sub_pairs=200)
+        finally:
+            os.environ.pop("PANSVR_TIES_ON_HOST_PATH", None)
+        outs[mode] = (read(out), read(ori))
+    assert outs["in_order"] == outs["host_path"]
+    assert first_diff(outs["in_order"][0], read(demo.ref_sam)) is None and outs["in_order"][1] == read(demo.ref_ori)
