@@ -100,7 +100,7 @@ private:
 
 struct DevCounters {                  // what the device services did for a block (bench.py: gpu_launches, e2e bytes, rooflines)
 	int64_t launches = 0, h2d_bytes = 0, d2h_bytes = 0;
-	int64_t seed_probes = 0;          // k-mer lookups of the seeding kernels (fill pass; the count pass repeats them)
+	int64_t seed_probes = 0;          // k-mer lookups of the seeding kernels (every probe is made once: the counting pass keeps what it finds)
 	double seed_kernel_ms = 0, ksw_kernel_ms = 0, stage_kernel_ms = 0;   // CUDA-event time of our kernels on their streams
 	double by_stage_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // the same by group: 0 records / original alignments / encode + census, 1 seeding,
 	                                                    // 2 merge + chain, 3 ksw planning, 4 candidate resolution, 5 cell count, 6 pairing probe + finalize, 7 SAM text

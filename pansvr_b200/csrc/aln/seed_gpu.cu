@@ -6,6 +6,9 @@
 // (seed_core.cuh): its probes are dependent random accesses, so throughput comes from having
 // every SM full of strands in flight, not from per-thread speed.  Two passes (count, exclusive
 // scan, fill) give a compact MEM list without a worst-case buffer per strand.
+// This service runs the small batches of the HOST path (pairs with 'N' or random_r sampling, pipeline.cpp) on a high-priority
+// stream; the device path seeds its sub-blocks with FnSeed / FnSeedPlace (stages_run.hpp) against the same index arrays
+// (seed_service_view), in one pass.
 #include <cuda_runtime.h>
 #include <cub/device/device_scan.cuh>
 #include <string>
