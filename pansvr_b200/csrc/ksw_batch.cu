@@ -7,6 +7,8 @@
 // order, scratch), persistent CTAs pull alignments from a global counter, one warp per alignment
 // (ksw_fast.cuh).  No CPU fallback: every entry point fails if CUDA does.
 #include <cuda_runtime.h>
+#include <sys/syscall.h>
+#include <unistd.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -662,7 +664,13 @@ void pansvr_ksw_extd2(void *km, int qlen, const uint8_t *query, int tlen, const 
                       pansvr_ksw_extz_t *ez)
 {
 	(void)km;
-	static thread_local pansvr_ksw_ctx *ctx = nullptr;
+	// one context per calling thread, like the reference's per-thread KSW_ALN_handler; it goes when its thread ends (the main
+	// thread's lives as long as the process: CUDA is on its way out by the time that thread's locals are destroyed)
+	static thread_local struct Holder {
+		pansvr_ksw_ctx *c = nullptr;
+		~Holder() { if (c && (long)syscall(SYS_gettid) != (long)getpid()) pansvr_ksw_destroy(c); }
+	} holder;
+	pansvr_ksw_ctx *&ctx = holder.c;
 	if (!ctx) {
 		int dev = 0;
 		if (cudaGetDevice(&dev) != cudaSuccess || pansvr_ksw_create(dev, &ctx) != 0) {
