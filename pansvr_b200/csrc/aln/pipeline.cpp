@@ -1895,6 +1895,7 @@ bool AlnPipeline::align_block_dev(const char *base, size_t text_bytes, const Fas
 		}
 		struct Leave { AlnPipeline &P; size_t site; ~Leave() { { std::lock_guard<std::mutex> lk(P.trip1_m_); --P.trip1_busy_[site]; } P.trip1_cv_.notify_all(); } } leave{*this, site};
 		trace_host(seq, "trip1_begin");
+		if (const char *e = getenv("PANSVR_TEST_FAIL_SEQ")) if ((uint64_t)atol(e) == seq) { err = "injected failure of this sub-block's first trip (test)"; return false; }
 		if (!stage_service_run(db->svc, in, db->out, err)) return false;
 		trace_host(seq, "trip1_end");
 	}

@@ -317,3 +317,16 @@ def test_tie_pairs_in_order_equal_host_path(fc_aln_emul):
         outs[mode] = (read(out), read(ori))
     assert outs["in_order"] == outs["host_path"]
     assert first_diff(outs["in_order"][0], read(demo.ref_sam)) is None and outs["in_order"][1] == read(demo.ref_ori)
+
+
+def test_failed_sub_block_is_an_error_not_a_hang():
+    """A sub-block that fails on its way (here: injected into the first trip of sub-block 1 of 5+) must still let the sub-blocks
+    behind it have their in-order turn: the call returns the error (round 2: a failed launch used to leave them waiting)."""
+    need_ref_tools()
+    subprocess.check_call(["make", "-s", "-C", os.path.join(HERE, "emul"), os.path.join(HERE, "emul", "fc_aln_emul")])
+    demo = get_demo("multi_allele")
+    env = dict(os.environ, PANSVR_ORACLE_SO=os.path.join(ROOT, "oracle", "libksw_oracle.so"), PANSVR_SUB_PAIRS="100", PANSVR_TEST_FAIL_SEQ="1")
+    p = subprocess.run([os.path.join(HERE, "emul", "fc_aln_emul"), "-t", "3", "-S", "-o", os.path.join(demo.wd, "fail.sam"), "-p",
+                        os.path.join(demo.wd, "fail_ori.sam"), demo.data.index_dir, demo.data.reads_fq, demo.data.header_sam],
+                       env=env, capture_output=True, timeout=120)
+    assert p.returncode != 0 and b"injected failure" in p.stderr
