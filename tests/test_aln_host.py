@@ -330,3 +330,62 @@ def test_failed_sub_block_is_an_error_not_a_hang():
                         os.path.join(demo.wd, "fail_ori.sam"), demo.data.index_dir, demo.data.reads_fq, demo.data.header_sam],
                        env=env, capture_output=True, timeout=120)
     assert p.returncode != 0 and b"injected failure" in p.stderr
+
+
+def test_pieces_api_edges_two_contexts(fc_aln_emul, tmp_path):
+    """pansvr_aln_pieces on the host-stepped build, two contexts in two threads: pieces of uneven size, an EMPTY piece in the middle
+    of the chain (it still takes the stream state over and hands it on), a context that owns consecutive pieces; and one piece
+    without files = pansvr_aln_block."""
+    import ctypes
+    import threading
+    from pansvr_b200 import aln
+    need_ref_tools()
+    os.environ["PANSVR_ORACLE_SO"] = os.path.join(ROOT, "oracle", "libksw_oracle.so")
+    lib = ctypes.CDLL(os.path.join(HERE, "emul", "libaln_emul.so"))
+    demo = get_demo("multi_allele")
+    lines = read(demo.data.reads_fq).split(b"\n")
+    n_pairs = len([1 for x in lines if x]) // 8
+    cuts = [0, 13, 13, 200, 201, 640, n_pairs]                        # piece 1 is empty, piece 3 is a single pair
+    texts = [b"\n".join(lines[8 * b:8 * e]) + (b"\n" if e > b else b"") for b, e in zip(cuts[:-1], cuts[1:])]
+    owner = [0, 1, 1, 0, 1, 0]                                        # (context 1 owns pieces 1 and 2: consecutive)
+    head = b"\n".join(lines[:4]) + b"\n"
+    ctxs = [aln.AlnContext(demo.data.index_dir, demo.data.header_sam, lib=lib, threads=2) for _ in range(2)]
+    results, errors = {}, []
+
+    def run(rank):
+        try:
+            ctx = ctxs[rank]
+            ctx.prime_read_stats(head)
+            mine = [b for b in range(len(texts)) if owner[b] == rank]
+            bufs = [ctypes.create_string_buffer(texts[b], max(len(texts[b]), 1)) for b in mine]
+            pieces = [(ctypes.addressof(buf), len(texts[b]), str(tmp_path / f"b{b}") if b > 0 else None,
+                       str(tmp_path / f"b{b + 1}") if b + 1 < len(texts) else None) for b, buf in zip(mine, bufs)]
+            (sa, sn), (oa, on), per, release = ctx.align_pieces(pieces)
+            sam, ori = ctypes.string_at(sa, sn), ctypes.string_at(oa, on)
+            release()
+            so = oo = 0
+            for b, (ps, po) in zip(mine, per):
+                results[b] = (sam[so:so + ps], ori[oo:oo + po]); so += ps; oo += po
+            assert so == sn and oo == on
+        except Exception as e:  # noqa: BLE001
+            errors.append(repr(e))
+
+    th = [threading.Thread(target=run, args=(r,)) for r in range(2)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join(300)
+    hdr = ctxs[0].header_text().encode()
+    assert not errors, errors
+    assert results[1] == (b"", b"")
+    assert first_diff(hdr + b"".join(results[b][0] for b in range(len(texts))), read(demo.ref_sam)) is None
+    assert hdr + b"".join(results[b][1] for b in range(len(texts))) == read(demo.ref_ori)
+    # one piece, no files: the block call
+    ctxs[0].reset()
+    whole = read(demo.data.reads_fq)
+    buf = ctypes.create_string_buffer(whole, len(whole))
+    (sa, sn), (oa, on), per, release = ctxs[0].align_pieces([(ctypes.addressof(buf), len(whole), None, None)])
+    assert hdr + ctypes.string_at(sa, sn) == read(demo.ref_sam) and per == [(sn, on)]
+    release()
+    for c in ctxs:
+        c.close()
