@@ -416,6 +416,8 @@ def main():
     print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()
+    import shutil
+    shutil.rmtree(state_dir, ignore_errors=True)                          # (the hand-over files are consumed; the directory is this run's)
 
 
 if __name__ == "__main__":
